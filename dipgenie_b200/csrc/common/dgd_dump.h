@@ -62,4 +62,61 @@ private:
     std::FILE* fp_ = nullptr;
 };
 
+// Minimal reader: loads the whole file, hands out typed views by name.
+class Reader {
+public:
+    explicit Reader(const std::string& path) {
+        std::FILE* fp = std::fopen(path.c_str(), "rb");
+        if (!fp) return;
+        std::fseek(fp, 0, SEEK_END);
+        long n = std::ftell(fp);
+        std::fseek(fp, 0, SEEK_SET);
+        buf_.resize((size_t)n);
+        size_t got = n ? std::fread(buf_.data(), 1, (size_t)n, fp) : 0;
+        std::fclose(fp);
+        if (got != (size_t)n || n < 4 || std::memcmp(buf_.data(), "DGD1", 4) != 0) { buf_.clear(); return; }
+        size_t pos = 4;
+        while (pos + 16 <= buf_.size()) {
+            uint32_t nl; std::memcpy(&nl, &buf_[pos], 4); pos += 4;
+            if (pos + nl + 12 > buf_.size()) break;
+            Entry e; e.name.assign((const char*)&buf_[pos], nl); pos += nl;
+            std::memcpy(&e.dtype, &buf_[pos], 4); pos += 4;
+            std::memcpy(&e.count, &buf_[pos], 8); pos += 8;
+            e.off = pos;
+            pos += (size_t)e.count * dtype_size(e.dtype);
+            if (pos > buf_.size()) break;
+            entries_.push_back(e);
+        }
+        ok_ = true;
+    }
+    bool ok() const { return ok_; }
+    // Copies entry `name` into `out` converting to T; returns false if absent.
+    template <class T>
+    bool get(const std::string& name, std::vector<T>& out) const {
+        for (const auto& e : entries_) {
+            if (e.name != name) continue;
+            out.resize((size_t)e.count);
+            const uint8_t* p = &buf_[e.off];
+            for (uint64_t i = 0; i < e.count; ++i) {
+                switch (e.dtype) {
+                    case U8:  out[i] = (T)p[i]; break;
+                    case I32: { int32_t x; std::memcpy(&x, p + 4 * i, 4); out[i] = (T)x; break; }
+                    case U32: { uint32_t x; std::memcpy(&x, p + 4 * i, 4); out[i] = (T)x; break; }
+                    case I64: { int64_t x; std::memcpy(&x, p + 8 * i, 8); out[i] = (T)x; break; }
+                    case U64: { uint64_t x; std::memcpy(&x, p + 8 * i, 8); out[i] = (T)x; break; }
+                    default:  { double x; std::memcpy(&x, p + 8 * i, 8); out[i] = (T)x; break; }
+                }
+            }
+            return true;
+        }
+        return false;
+    }
+
+private:
+    struct Entry { std::string name; uint32_t dtype = 0; uint64_t count = 0; size_t off = 0; };
+    std::vector<uint8_t> buf_;
+    std::vector<Entry> entries_;
+    bool ok_ = false;
+};
+
 }  // namespace dgd

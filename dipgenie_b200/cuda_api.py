@@ -1,0 +1,211 @@
+"""ctypes bindings to libdipgenie_cuda.so (include/dipgenie_cuda.h).
+
+This is the device side of the hot path; there is no CPU fallback.  `load()` raises if the
+library has not been built or no CUDA device can be opened.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _build
+
+_LIB: Optional[C.CDLL] = None
+
+
+class DipStats(C.Structure):
+    _fields_ = [
+        ("cell_updates", C.c_uint64), ("cells", C.c_uint64), ("algo_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
+        ("n_levels", C.c_int32), ("n_vertices", C.c_int32), ("max_width", C.c_int32), ("max_indegree", C.c_int32),
+        ("mask_words_max", C.c_int32), ("grid_ctas", C.c_int32), ("pred_bytes", C.c_int32), ("launches", C.c_int32),
+        ("sweep_ms", C.c_float), ("traceback_ms", C.c_float),
+    ]
+
+
+class DipGenieCudaError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library (must have been built in-tree by `__graft_entry__.build()`)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(_build.CUDA_LIB):
+            raise DipGenieCudaError(
+                f"{_build.CUDA_LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the device path)")
+        lib = C.CDLL(_build.CUDA_LIB)
+        lib.dg_create.restype = C.c_void_p
+        lib.dg_create.argtypes = [C.c_int]
+        lib.dg_destroy.argtypes = [C.c_void_p]
+        lib.dg_last_error.restype = C.c_char_p
+        lib.dg_last_error.argtypes = [C.c_void_p]
+        lib.dg_free.argtypes = [C.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@dataclass
+class LevelGraph:
+    """Flat levelized ExpandedGraph — the input contract of dg_dp_diploid (see include/dipgenie_cuda.h)."""
+    level_off: np.ndarray     # int32 [L+1]
+    adj_off: np.ndarray       # int64 [V+1]
+    adj_dst: np.ndarray       # int32 [E]
+    adj_w: np.ndarray         # uint8 [E]
+    col_off: np.ndarray       # int64 [V+1]
+    col_val: np.ndarray       # int32
+    colour_is_hom: np.ndarray  # uint8 [n_colours]
+
+    def __post_init__(self):
+        self.level_off = np.ascontiguousarray(self.level_off, np.int32)
+        self.adj_off = np.ascontiguousarray(self.adj_off, np.int64)
+        self.adj_dst = np.ascontiguousarray(self.adj_dst, np.int32)
+        self.adj_w = np.ascontiguousarray(self.adj_w, np.uint8)
+        self.col_off = np.ascontiguousarray(self.col_off, np.int64)
+        self.col_val = np.ascontiguousarray(self.col_val, np.int32)
+        self.colour_is_hom = np.ascontiguousarray(self.colour_is_hom, np.uint8)
+
+    @property
+    def n_levels(self) -> int:
+        return len(self.level_off) - 1
+
+    @property
+    def nbytes(self) -> int:
+        return sum(a.nbytes for a in (self.level_off, self.adj_off, self.adj_dst, self.adj_w, self.col_off,
+                                      self.col_val, self.colour_is_hom))
+
+    @staticmethod
+    def from_dgd(d, prefix: str = "dip_in.") -> "LevelGraph":
+        return LevelGraph(d[prefix + "lvl_vtx.off"], d[prefix + "adj.off"], d[prefix + "adj.dst"], d[prefix + "adj.w"],
+                          d[prefix + "color.off"], d[prefix + "color.val"], d[prefix + "color_homo"])
+
+    def to_npz(self, path: str, **extra) -> None:
+        outdeg = np.diff(self.adj_off)
+        ncol = np.diff(self.col_off)
+        np.savez_compressed(
+            path, level_off=self.level_off,
+            outdeg=outdeg.astype(np.uint16 if outdeg.max(initial=0) < 65536 else np.int32),
+            adj_dst_delta=np.diff(self.adj_dst, prepend=0).astype(np.int32), adj_w=np.packbits(self.adj_w),
+            n_edges=np.int64(len(self.adj_w)),
+            ncol=ncol.astype(np.uint16 if ncol.max(initial=0) < 65536 else np.int32), col_val=self.col_val,
+            colour_is_hom=np.packbits(self.colour_is_hom), n_colours=np.int64(len(self.colour_is_hom)), **extra)
+
+    @staticmethod
+    def from_npz(path: str):
+        z = np.load(path)
+        ne = int(z["n_edges"])
+        g = LevelGraph(
+            z["level_off"], np.concatenate([[0], np.cumsum(z["outdeg"].astype(np.int64))]),
+            np.cumsum(z["adj_dst_delta"].astype(np.int64)).astype(np.int32), np.unpackbits(z["adj_w"])[:ne],
+            np.concatenate([[0], np.cumsum(z["ncol"].astype(np.int64))]), z["col_val"],
+            np.unpackbits(z["colour_is_hom"])[: int(z["n_colours"])])
+        return g, z
+
+
+class Context:
+    """One dg_ctx (one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self.h = self.lib.dg_create(device)
+        if not self.h:
+            raise DipGenieCudaError(f"dg_create({device}) failed: no usable CUDA device (no CPU fallback exists)")
+
+    def close(self):
+        if self.h:
+            self.lib.dg_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            raise DipGenieCudaError(f"{what} failed ({rc}): {self.lib.dg_last_error(self.h).decode()}")
+
+    def device_info(self):
+        sm = C.c_int(0)
+        fr = C.c_size_t(0)
+        tot = C.c_size_t(0)
+        self.check(self.lib.dg_device_info(self.h, C.byref(sm), C.byref(fr), C.byref(tot)), "dg_device_info")
+        return dict(sm_count=sm.value, free_bytes=fr.value, total_bytes=tot.value)
+
+    # ---- diploid DP ------------------------------------------------------------------------
+    def dp_diploid(self, g: LevelGraph, R: int):
+        """One-shot host-buffer call (dg_dp_diploid): H2D, sweep, traceback, D2H."""
+        val = C.c_int32(0)
+        shet = C.c_int32(0)
+        n1 = C.c_int32(0)
+        n2 = C.c_int32(0)
+        p1 = np.zeros(2 * (R + 2), np.int32)
+        p2 = np.zeros(2 * (R + 2), np.int32)
+        rc = self.lib.dg_dp_diploid(
+            C.c_void_p(self.h), C.c_int32(g.n_levels), _ptr(g.level_off), _ptr(g.adj_off), _ptr(g.adj_dst), _ptr(g.adj_w),
+            _ptr(g.col_off), _ptr(g.col_val), _ptr(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R),
+            C.byref(val), C.byref(shet), _ptr(p1), C.byref(n1), _ptr(p2), C.byref(n2))
+        self.check(rc, "dg_dp_diploid")
+        return dict(value=val.value, s_het=shet.value, p1_edges=p1[: 2 * n1.value].reshape(-1, 2).copy(),
+                    p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy())
+
+    def dip_create(self, g: LevelGraph, R: int) -> "DipProblem":
+        return DipProblem(self, g, R)
+
+
+class DipProblem:
+    """A diploid DP problem resident in HBM (dg_dip_*)."""
+
+    def __init__(self, ctx: Context, g: LevelGraph, R: int):
+        self.ctx = ctx
+        self.R = R
+        self.L = g.n_levels
+        h = C.c_void_p(None)
+        rc = ctx.lib.dg_dip_create(
+            C.c_void_p(ctx.h), C.c_int32(g.n_levels), _ptr(g.level_off), _ptr(g.adj_off), _ptr(g.adj_dst), _ptr(g.adj_w),
+            _ptr(g.col_off), _ptr(g.col_val), _ptr(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R),
+            C.byref(h))
+        ctx.check(rc, "dg_dip_create")
+        self.h = h
+
+    def run(self, checksums: bool = False):
+        self.ctx.check(self.ctx.lib.dg_dip_run(C.c_void_p(self.ctx.h), self.h, C.c_uint32(1 if checksums else 0)), "dg_dip_run")
+
+    def result(self):
+        R = self.R
+        val = C.c_int32(0)
+        shet = C.c_int32(0)
+        n1 = C.c_int32(0)
+        n2 = C.c_int32(0)
+        p1 = np.zeros(2 * (R + 2), np.int32)
+        p2 = np.zeros(2 * (R + 2), np.int32)
+        rc = self.ctx.lib.dg_dip_result(C.c_void_p(self.ctx.h), self.h, C.byref(val), C.byref(shet), _ptr(p1), C.byref(n1),
+                                        _ptr(p2), C.byref(n2))
+        self.ctx.check(rc, "dg_dip_result")
+        return dict(value=val.value, s_het=shet.value, p1_edges=p1[: 2 * n1.value].reshape(-1, 2).copy(),
+                    p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy())
+
+    def checksums(self):
+        cs = np.zeros(self.L, np.uint64)
+        lv = np.zeros(self.L, np.uint64)
+        self.ctx.check(self.ctx.lib.dg_dip_checksums(C.c_void_p(self.ctx.h), self.h, _ptr(cs), _ptr(lv)), "dg_dip_checksums")
+        return cs, lv
+
+    def stats(self) -> dict:
+        s = DipStats()
+        self.ctx.check(self.ctx.lib.dg_dip_stats(C.c_void_p(self.ctx.h), self.h, C.byref(s)), "dg_dip_stats")
+        return {k: getattr(s, k) for k, _ in DipStats._fields_}
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dg_dip_destroy(C.c_void_p(self.ctx.h), self.h)
+            self.h = None

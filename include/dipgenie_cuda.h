@@ -1,0 +1,93 @@
+/* dipgenie_cuda.h — C ABI of libdipgenie_cuda.so, the B200 (sm_100a) device side of DipGenie's hot path.
+ *
+ * The reference (gsc74/DipGenie) has no plugin/FFI layer: its hot path is a handful of C++ member
+ * functions called from one place each.  Every entry point below names the reference seam it replaces
+ * (file:line into the reference tree); INTEGRATION.md shows the few lines a maintainer adds at that
+ * seam to call it.  Conventions: plain pointers and sizes only; caller-owned host buffers unless a
+ * parameter is documented as library-allocated (release those with dg_free); every function returns
+ * 0 on success or a negative error code, with text available from dg_last_error(); no exceptions and
+ * no C++ types cross the boundary; one dg_ctx per GPU, used by one host thread at a time.
+ * There is no CPU fallback: dg_create fails if no CUDA device is usable.
+ */
+#ifndef DIPGENIE_CUDA_H
+#define DIPGENIE_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dg_ctx dg_ctx;
+
+#define DG_OK 0
+#define DG_ERR_ARG (-1)       /* malformed input (see dg_last_error) */
+#define DG_ERR_CUDA (-2)      /* CUDA runtime error */
+#define DG_ERR_NOMEM (-3)     /* device or host allocation failed */
+#define DG_ERR_CAPACITY (-4)  /* an output did not fit the documented capacity */
+
+/* ---- context -------------------------------------------------------------------------------- */
+dg_ctx* dg_create(int device);               /* NULL if the device cannot be initialised */
+void dg_destroy(dg_ctx* ctx);
+const char* dg_last_error(dg_ctx* ctx);      /* valid until the next call on ctx */
+void dg_free(void* p);                       /* releases library-allocated host arrays */
+int dg_device_info(dg_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes);
+
+/* ---- diploid DP: Approximator::diploid_dp_approximation_solver, src/approximator.cpp:362-785 ---
+ * (the DP sweep :532-716 and the recombination-edge lists it returns :757-785; the caller keeps the
+ *  sequence stitching :787-930, which needs node_seq/paths).
+ *
+ * Input: the levelized ExpandedGraph (src/ExpandedGraph.hpp:16-26 after
+ * strict_bfs_levelize_and_reorder, :269-409), flattened:
+ *   level_off[L+1]   vertices are numbered in (level,id) order; level l owns [level_off[l], level_off[l+1])
+ *                    (= g.vertices_in_level, whose entries are consecutive ids after the reorder)
+ *   adj_off[V+1], adj_dst[E], adj_w[E]   g.adj_list as CSR, adjacency order preserved, weights 0/1
+ *   col_off[V+1], col_val[]              g.color as CSR (colour ids)
+ *   colour_is_hom[n_colours]             color_homo_bv (src/approximator.cpp:1283-1290)
+ *   R                                    recombination_limit
+ * Output (bit-exact with the reference, same tie-breaking :657-659):
+ *   sink_value   dp value of cell (r=R,0,0) of the last level ("DP value:", :774-776)
+ *   sink_s_het   dp_entry::s_het of that cell
+ *   p1_edges / p2_edges   weighted_p1_edges / weighted_p2_edges (:781-782) as (from,to) vertex-id pairs,
+ *                oldest first; capacity 2*(R+2) int32 each; n_p1 / n_p2 = number of pairs
+ */
+int dg_dp_diploid(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off,
+                  const int64_t* adj_off, const int32_t* adj_dst, const uint8_t* adj_w,
+                  const int64_t* col_off, const int32_t* col_val,
+                  const uint8_t* colour_is_hom, int32_t n_colours, int32_t R,
+                  int32_t* sink_value, int32_t* sink_s_het,
+                  int32_t* p1_edges, int32_t* n_p1, int32_t* p2_edges, int32_t* n_p2);
+
+/* The same computation split so that the graph can stay resident in HBM between runs
+ * (bench.py times dg_dip_run alone; tests read the per-level checksums). */
+typedef struct dg_dip dg_dip;
+
+int dg_dip_create(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off,
+                  const int64_t* adj_off, const int32_t* adj_dst, const uint8_t* adj_w,
+                  const int64_t* col_off, const int32_t* col_val,
+                  const uint8_t* colour_is_hom, int32_t n_colours, int32_t R, dg_dip** out);
+/* flags: bit0 = also fold every DP layer into per-level checksums (slower; tests only). */
+int dg_dip_run(dg_ctx* ctx, dg_dip* d, uint32_t flags);
+int dg_dip_result(dg_ctx* ctx, dg_dip* d, int32_t* sink_value, int32_t* sink_s_het,
+                  int32_t* p1_edges, int32_t* n_p1, int32_t* p2_edges, int32_t* n_p2);
+/* level_checksum/level_live: [n_levels]; entry l (l>=1) folds (flat index, value, pred_i, pred_j) of the
+ * live cells of level l exactly like oracle/ref_hook.h does inside the reference. */
+int dg_dip_checksums(dg_ctx* ctx, dg_dip* d, uint64_t* level_checksum, uint64_t* level_live);
+/* Work and traffic accounting: U = (R+1)*sum E_l^2 cell-updates, C = (R+1)*sum k_l^2
+ * destination cells, B = (R+1)*sum(4 k_l^2 + 5 k_{l+1}^2) algorithmic bytes; plus kernel launches and
+ * device milliseconds (CUDA events on the context's stream) of the last dg_dip_run. */
+typedef struct {
+    uint64_t cell_updates, cells, algo_bytes;
+    uint64_t device_bytes;       /* HBM held by this problem */
+    int32_t n_levels, n_vertices, max_width, max_indegree, mask_words_max, grid_ctas, pred_bytes;
+    int32_t launches;
+    float sweep_ms, traceback_ms;
+} dg_dip_stats_t;
+int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out);
+void dg_dip_destroy(dg_ctx* ctx, dg_dip* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIPGENIE_CUDA_H */

@@ -100,13 +100,64 @@ void dg_ref_level_checksum_push(int level, uint64_t checksum, uint64_t n_live) {
     g_lvl_live[level] = n_live;
 }
 
+// DP-only mode (-G graph.dgd): times the reference's own diploid solver
+// (Approximator::diploid_dp_approximation_solver, src/approximator.cpp:362) on a levelized graph given
+// as flat arrays (LevelGraph layout, see include/dipgenie_cuda.h), optionally truncated to its first
+// -M levels (a bounded sample of the same workload: a sink is appended after level M-1).
+// The sequence-stitching inputs are stubbed (one empty segment), so only the sweep + list recovery run.
+static int dp_only(const std::string& path, int R, int threads, int max_levels) {
+    dgd::Reader rd(path);
+    if (!rd.ok()) { fprintf(stderr, "ref_driver: cannot read %s\n", path.c_str()); return 1; }
+    std::vector<int32_t> level_off, adj_dst, col_val;
+    std::vector<int64_t> adj_off, col_off;
+    std::vector<uint8_t> adj_w, hom;
+    if (!rd.get("level_off", level_off) || !rd.get("adj_off", adj_off) || !rd.get("adj_dst", adj_dst) ||
+        !rd.get("adj_w", adj_w) || !rd.get("col_off", col_off) || !rd.get("col_val", col_val) ||
+        !rd.get("colour_is_hom", hom)) { fprintf(stderr, "ref_driver: graph arrays missing\n"); return 1; }
+    int L = (int)level_off.size() - 1;
+    int keep = (max_levels > 1 && max_levels < L) ? max_levels : L;
+    const int32_t V = level_off[keep];
+    const bool cut = keep < L;
+    ExpandedGraph g;
+    const int32_t n = V + (cut ? 1 : 0);
+    g.adj_list.resize(n); g.color.resize(n); g.original_vertex.assign(n, std::vector<int>{0});
+    g.haplotype.assign(n, 0); g.level.assign(n, 0); g.vertices_in_level.resize(keep + (cut ? 1 : 0));
+    unsigned long long U = 0;
+    for (int l = 0; l < keep; ++l) {
+        unsigned long long El = 0;
+        for (int32_t v = level_off[l]; v < level_off[l + 1]; ++v) {
+            g.level[v] = l; g.vertices_in_level[l].push_back(v);
+            for (int64_t c = col_off[v]; c < col_off[v + 1]; ++c) g.color[v].push_back(col_val[c]);
+            if (cut && l == keep - 1) { g.adj_list[v].push_back({V, 0}); El += 1; continue; }
+            for (int64_t e = adj_off[v]; e < adj_off[v + 1]; ++e) g.adj_list[v].push_back({adj_dst[e], (int)adj_w[e]});
+            El += (unsigned long long)(adj_off[v + 1] - adj_off[v]);
+        }
+        U += (unsigned long long)(R + 1) * El * El;
+    }
+    if (cut) { g.level[V] = keep; g.vertices_in_level[keep].push_back(V); }
+    std::vector<bool> bv(hom.size());
+    for (size_t i = 0; i < hom.size(); ++i) bv[i] = hom[i] != 0;
+    Approximator* A = new Approximator(nullptr);
+    A->num_threads = threads; A->recombination_limit = R;
+    A->paths.assign(1, std::vector<uint32_t>{0}); A->node_seq.assign(1, std::string());
+    std::vector<std::vector<Approximator::AnchorRec>> anchorsByHap(1);
+    double t0 = realtime();
+    auto sol = A->diploid_dp_approximation_solver(g, R, bv, anchorsByHap);
+    double ms = (realtime() - t0) * 1e3;
+    int r1 = sol.empty() ? -1 : std::get<0>(sol[0]), r2 = sol.empty() ? -1 : std::get<1>(sol[0]);
+    printf("\nDPONLY levels %d threads %d R %d cell_updates %llu ms %.3f r1 %d r2 %d\n", keep + (cut ? 1 : 0), threads, R, U, ms, r1, r2);
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    std::string gfa, reads, out = "/dev/null", dump;
-    int ploidy = 2, R = 18, k = 31, w = 25, threads = 4, skip_solve = 0, light = 0;
+    std::string gfa, reads, out = "/dev/null", dump, graph;
+    int ploidy = 2, R = 18, k = 31, w = 25, threads = 4, skip_solve = 0, light = 0, max_levels = 0;
     float threshold = 1.0f;
     int c;
-    while ((c = getopt(argc, argv, "g:r:o:D:p:R:k:w:t:T:SL")) >= 0) {
+    while ((c = getopt(argc, argv, "g:r:o:D:p:R:k:w:t:T:SLG:M:")) >= 0) {
         switch (c) {
+            case 'G': graph = optarg; break;
+            case 'M': max_levels = atoi(optarg); break;
             case 'g': gfa = optarg; break;
             case 'r': reads = optarg; break;
             case 'o': out = optarg; break;
@@ -122,6 +173,7 @@ int main(int argc, char** argv) {
             default: return 2;
         }
     }
+    if (!graph.empty()) return dp_only(graph, R, threads, max_levels);
     if (gfa.empty() || reads.empty()) { fprintf(stderr, "ref_driver: -g and -r required\n"); return 2; }
     if (!dump.empty()) g_w.reset(new dgd::Writer(dump));
 

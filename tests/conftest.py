@@ -1,0 +1,94 @@
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "ref: needs the reference binaries under oracle/_ref (build container only)")
+
+
+def pytest_collection_modifyitems(config, items):
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "DipGenie")) and os.path.isdir("/root/reference/test")
+    skip_ref = pytest.mark.skip(reason="reference build (oracle/_ref) or /root/reference not present")
+    for it in items:
+        if "ref" in it.keywords and not have_ref:
+            it.add_marker(skip_ref)
+
+
+@pytest.fixture(scope="session")
+def expected():
+    with open(os.path.join(GOLD, "expected.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def oracle_mod():
+    import oracle
+    oracle.build()
+    return oracle
+
+
+def _build_emu():
+    so = os.path.join(EMU_DIR, "libdpemu.so")
+    srcs = [os.path.join(EMU_DIR, "dp_emu.cpp"), os.path.join(ROOT, "dipgenie_b200", "csrc", "cuda", "dp_prep.cpp")]
+    deps = srcs + [os.path.join(ROOT, "dipgenie_b200", "csrc", "cuda", h) for h in ("dp_prep.h", "dp_cell.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so] + srcs)
+    return so
+
+
+class DpEmu:
+    """CPU emulation of the CUDA sweep's kernel logic (tests/emu/dp_emu.cpp)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(_build_emu())
+
+    def dp_diploid(self, g, R, force_pred32=False):
+        L = g.n_levels
+        val, sh, n1, n2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        p1 = np.zeros(2 * (R + 2), np.int32)
+        p2 = np.zeros(2 * (R + 2), np.int32)
+        cs = np.zeros(L, np.uint64)
+        lv = np.zeros(L, np.uint64)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = self.lib.emu_dp_diploid(
+            C.c_int32(L), P(g.level_off), P(g.adj_off), P(g.adj_dst), P(g.adj_w), P(g.col_off), P(g.col_val),
+            P(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R), C.byref(val), C.byref(sh), P(p1),
+            C.byref(n1), P(p2), C.byref(n2), P(cs), P(lv), C.c_int32(1 if force_pred32 else 0))
+        if rc != 0:
+            raise RuntimeError(f"emu_dp_diploid rc={rc}")
+        return dict(value=val.value, s_het=sh.value, p1_edges=p1[: 2 * n1.value].reshape(-1, 2).copy(),
+                    p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy(), checksum=cs, live=lv)
+
+
+@pytest.fixture(scope="session")
+def dp_emu():
+    return DpEmu()
+
+
+def oracle_dip(oracle_mod, g, R, want_checksums=True):
+    return oracle_mod.dp_diploid(g.level_off, g.adj_off, g.adj_dst, g.adj_w, g.col_off, g.col_val, g.colour_is_hom, R,
+                                 want_checksums=want_checksums)
+
+
+def assert_dip_equal(a, b, checks=True):
+    assert a["value"] == b["value"]
+    assert a["s_het"] == b["s_het"]
+    assert np.array_equal(a["p1_edges"], b["p1_edges"])
+    assert np.array_equal(a["p2_edges"], b["p2_edges"])
+    if checks and "checksum" in a and "checksum" in b:
+        assert np.array_equal(a["live"][1:], b["live"][1:])
+        assert np.array_equal(a["checksum"][1:], b["checksum"][1:])

@@ -1,0 +1,119 @@
+"""CPU-side checks of the diploid DP path (no GPU needed):
+  * the oracle (oracle/dp_diploid.c) against the reference's own results in tests/golden/
+    (sink value, s_het, recombination-edge lists, sha256 of all per-level DP checksums);
+  * the kernel-logic emulation (tests/emu: dp_prep.cpp + dp_cell.h, i.e. the code the CUDA kernels run)
+    against the oracle on random levelized graphs, including the edge cases the domain has
+    (R=0, dead sink, single transition, duplicate edges, fan-in > 255 -> 32-bit predecessor codes).
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, assert_dip_equal, oracle_dip
+from dipgenie_b200 import dgd, synth
+from dipgenie_b200.cuda_api import LevelGraph
+
+TINY_DIP = ["test_p2_R2_k5_w3", "test_p2_R0_k3_w2", "test_p2_R1_k3_w2", "test_p2_R2_k3_w2", "test2_p2_R2"]
+
+
+@pytest.mark.parametrize("name", TINY_DIP)
+def test_oracle_matches_reference_tiny(name, oracle_mod, expected):
+    d = dgd.load(os.path.join(GOLD, f"tiny_{name}.dgd"))
+    g = LevelGraph.from_dgd(d)
+    R = int(d["dip_in.R"][0])
+    o = oracle_dip(oracle_mod, g, R)
+    e = expected["tiny"][name]
+    assert o["value"] == e["value"] == int(d["dip_out.value"][0])
+    assert o["s_het"] == e["s_het"]
+    assert o["p1_edges"].ravel().tolist() == e["p1_edges"]
+    assert o["p2_edges"].ravel().tolist() == e["p2_edges"]
+    assert np.array_equal(o["checksum"][1:], d["dip_out.level_checksum"][1:])
+    assert np.array_equal(o["live"][1:], d["dip_out.level_live"][1:])
+
+
+@pytest.mark.parametrize("name", TINY_DIP)
+def test_emulated_kernel_matches_reference_tiny(name, dp_emu, expected):
+    d = dgd.load(os.path.join(GOLD, f"tiny_{name}.dgd"))
+    g = LevelGraph.from_dgd(d)
+    R = int(d["dip_in.R"][0])
+    for f32 in (False, True):
+        o = dp_emu.dp_diploid(g, R, force_pred32=f32)
+        e = expected["tiny"][name]
+        assert o["value"] == e["value"] and o["s_het"] == e["s_het"]
+        assert o["p1_edges"].ravel().tolist() == e["p1_edges"]
+        assert o["p2_edges"].ravel().tolist() == e["p2_edges"]
+        assert np.array_equal(o["checksum"][1:], d["dip_out.level_checksum"][1:])
+
+
+@pytest.mark.parametrize("R", [18, 0])
+def test_oracle_matches_reference_mhc(R, oracle_mod, expected):
+    """Full-size pin: MHC_4.gfa.gz + CHM13 reads, all 120 362 DP layers (about 15 s per R)."""
+    g, _ = LevelGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_dipin.npz"))
+    o = oracle_dip(oracle_mod, g, R)
+    e = expected["mhc4_chm13"]["diploid"][str(R)]
+    assert o["value"] == e["value"]
+    assert o["s_het"] == e["s_het"]
+    assert o["p1_edges"].ravel().tolist() == e["p1_edges"]
+    assert o["p2_edges"].ravel().tolist() == e["p2_edges"]
+    assert hashlib.sha256(o["checksum"][1:].tobytes()).hexdigest() == e["checksum_sha256"]
+    assert hashlib.sha256(o["live"][1:].tobytes()).hexdigest() == e["live_sha256"]
+
+
+def test_emulated_kernel_matches_reference_mhc(dp_emu, expected):
+    g, _ = LevelGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_dipin.npz"))
+    o = dp_emu.dp_diploid(g, 6)
+    e = expected["mhc4_chm13"]["diploid"]["6"]
+    assert o["value"] == e["value"] and o["s_het"] == e["s_het"]
+    assert o["p1_edges"].ravel().tolist() == e["p1_edges"]
+    assert o["p2_edges"].ravel().tolist() == e["p2_edges"]
+    assert hashlib.sha256(o["checksum"][1:].tobytes()).hexdigest() == e["checksum_sha256"]
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_emulated_kernel_matches_oracle_random(seed, oracle_mod, dp_emu):
+    rng = np.random.default_rng(1000 + seed)
+    g = synth.random_level_graph(seed, n_levels=int(rng.integers(2, 20)), max_width=int(rng.integers(1, 9)),
+                                 n_colours=int(rng.integers(0, 90)), p_weight1=float(rng.random() * 0.6),
+                                 p_colour=float(rng.random()), max_out=int(rng.integers(1, 5)))
+    R = int(rng.integers(0, 7))
+    assert_dip_equal(oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R))
+
+
+def test_single_level_and_single_transition(oracle_mod, dp_emu):
+    one = LevelGraph([0, 1], [0, 0], [], [], [0, 0], [], [0])
+    assert_dip_equal(oracle_dip(oracle_mod, one, 3), dp_emu.dp_diploid(one, 3))
+    two = LevelGraph([0, 1, 2], [0, 1, 1], [1], [1], [0, 1, 2], [0, 0], [1])
+    for R in (0, 1, 2):
+        assert_dip_equal(oracle_dip(oracle_mod, two, R), dp_emu.dp_diploid(two, R))
+
+
+def test_dead_sink_when_R_too_small(oracle_mod, dp_emu):
+    # source -w1-> a -w1-> sink : needs 4 recombinations for the pair of paths
+    g = LevelGraph([0, 1, 2, 3], [0, 1, 2, 2], [1, 2], [1, 1], [0, 0, 0, 0], [], [0])
+    for R in (0, 3, 4):
+        a, b = oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R)
+        assert_dip_equal(a, b)
+    assert oracle_dip(oracle_mod, g, 3)["value"] < 0 and oracle_dip(oracle_mod, g, 4)["value"] == 0
+
+
+def test_fan_in_above_255_uses_32bit_codes(oracle_mod, dp_emu):
+    k = 300
+    level_off = [0, 1, 1 + k, 2 + k, 3 + k]
+    adj_off = [0, k] + list(range(k + 1, 2 * k + 1)) + [2 * k + 1, 2 * k + 1]
+    adj_dst = list(range(1, 1 + k)) + [1 + k] * k + [2 + k]
+    adj_w = [0] * k + [i % 2 for i in range(k)] + [0]
+    ncol = np.zeros(3 + k, np.int64)
+    ncol[1:1 + k] = 1
+    col_off = np.concatenate([[0], np.cumsum(ncol)])
+    col_val = np.arange(k) % 7
+    g = LevelGraph(level_off, adj_off, adj_dst, adj_w, col_off, col_val, [1, 0, 1, 0, 0, 1, 0])
+    for R in (0, 2):
+        assert_dip_equal(oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R))
+
+
+def test_lane_panel_model(oracle_mod, dp_emu):
+    g = synth.lane_panel_graph(7, n_lanes=6, n_blocks=5, rec_per_block=2, p_colour=0.3, n_colours=64)
+    for R in (0, 3):
+        assert_dip_equal(oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R))

@@ -1,0 +1,110 @@
+"""GPU parity tests of the diploid DP (through the C ABI of libdipgenie_cuda.so, via ctypes):
+CUDA path vs the oracle on the same seeded inputs (bit-exact: value, s_het, edge lists and the
+per-level checksums of every DP layer), vs the reference's committed goldens, and — at full size —
+vs the reference's digest of all 120 362 layers of the bundled MHC data."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, assert_dip_equal, oracle_dip
+from dipgenie_b200 import dgd, synth
+from dipgenie_b200.cuda_api import Context, LevelGraph
+
+pytestmark = pytest.mark.gpu
+
+TINY_DIP = ["test_p2_R2_k5_w3", "test_p2_R0_k3_w2", "test_p2_R1_k3_w2", "test_p2_R2_k3_w2", "test2_p2_R2"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def cuda_dip(ctx, g, R, checks=True):
+    p = ctx.dip_create(g, R)
+    try:
+        p.run(checksums=checks)
+        out = p.result()
+        if checks:
+            out["checksum"], out["live"] = p.checksums()
+        out["stats"] = p.stats()
+        return out
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("name", TINY_DIP)
+def test_cuda_matches_reference_tiny(name, ctx, expected):
+    d = dgd.load(os.path.join(GOLD, f"tiny_{name}.dgd"))
+    g = LevelGraph.from_dgd(d)
+    R = int(d["dip_in.R"][0])
+    o = cuda_dip(ctx, g, R)
+    e = expected["tiny"][name]
+    assert o["value"] == e["value"] and o["s_het"] == e["s_het"]
+    assert o["p1_edges"].ravel().tolist() == e["p1_edges"]
+    assert o["p2_edges"].ravel().tolist() == e["p2_edges"]
+    assert np.array_equal(o["checksum"][1:], d["dip_out.level_checksum"][1:])
+    one_shot = ctx.dp_diploid(g, R)
+    assert one_shot["value"] == e["value"] and one_shot["p1_edges"].ravel().tolist() == e["p1_edges"]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_cuda_matches_oracle_random(seed, ctx, oracle_mod):
+    rng = np.random.default_rng(2000 + seed)
+    g = synth.random_level_graph(seed, n_levels=int(rng.integers(2, 40)), max_width=int(rng.integers(1, 24)),
+                                 n_colours=int(rng.integers(0, 200)), p_weight1=float(rng.random() * 0.6),
+                                 p_colour=float(rng.random()), max_out=int(rng.integers(1, 5)))
+    R = int(rng.integers(0, 9))
+    assert_dip_equal(oracle_dip(oracle_mod, g, R), cuda_dip(ctx, g, R))
+
+
+def test_cuda_edge_cases(ctx, oracle_mod):
+    one = LevelGraph([0, 1], [0, 0], [], [], [0, 0], [], [0])
+    assert_dip_equal(oracle_dip(oracle_mod, one, 3), cuda_dip(ctx, one, 3))
+    dead = LevelGraph([0, 1, 2, 3], [0, 1, 2, 2], [1, 2], [1, 1], [0, 0, 0, 0], [], [0])
+    for R in (0, 3, 4):
+        assert_dip_equal(oracle_dip(oracle_mod, dead, R), cuda_dip(ctx, dead, R))
+    k = 300   # fan-in above 255 -> 32-bit predecessor codes
+    level_off = [0, 1, 1 + k, 2 + k, 3 + k]
+    adj_off = [0, k] + list(range(k + 1, 2 * k + 1)) + [2 * k + 1, 2 * k + 1]
+    adj_dst = list(range(1, 1 + k)) + [1 + k] * k + [2 + k]
+    adj_w = [0] * k + [i % 2 for i in range(k)] + [0]
+    ncol = np.zeros(3 + k, np.int64)
+    ncol[1:1 + k] = 1
+    g = LevelGraph(level_off, adj_off, adj_dst, adj_w, np.concatenate([[0], np.cumsum(ncol)]), np.arange(k) % 7,
+                   [1, 0, 1, 0, 0, 1, 0])
+    o = cuda_dip(ctx, g, 2)
+    assert o["stats"]["pred_bytes"] == 4
+    assert_dip_equal(oracle_dip(oracle_mod, g, 2), o)
+
+
+def test_cuda_wide_levels_use_many_ctas(ctx, oracle_mod):
+    """Widths large enough that transitions are spread over the whole grid and closed by the counter barrier."""
+    g = synth.lane_panel_graph(11, n_lanes=40, n_blocks=12, rec_per_block=3, p_colour=0.2, n_colours=500)
+    o = cuda_dip(ctx, g, 5)
+    assert o["stats"]["grid_ctas"] > 1
+    assert_dip_equal(oracle_dip(oracle_mod, g, 5), o)
+
+
+@pytest.mark.parametrize("R", [18, 0, 6, 36])
+def test_cuda_matches_reference_mhc_full_size(R, ctx, expected):
+    """BASELINE config 2 graph (MHC_4.gfa.gz, CHM13 reads): every DP layer digest-equal to the reference."""
+    g, _ = LevelGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_dipin.npz"))
+    o = cuda_dip(ctx, g, R)
+    e = expected["mhc4_chm13"]["diploid"][str(R)]
+    assert o["value"] == e["value"]
+    assert o["s_het"] == e["s_het"]
+    assert o["p1_edges"].ravel().tolist() == e["p1_edges"]
+    assert o["p2_edges"].ravel().tolist() == e["p2_edges"]
+    assert hashlib.sha256(o["checksum"][1:].tobytes()).hexdigest() == e["checksum_sha256"]
+    assert hashlib.sha256(o["live"][1:].tobytes()).hexdigest() == e["live_sha256"]
+    # the unchecked (timed) kernel variant must give the same answer
+    p = ctx.dip_create(g, R)
+    p.run(checksums=False)
+    o2 = p.result()
+    p.close()
+    assert o2["value"] == e["value"] and o2["p1_edges"].ravel().tolist() == e["p1_edges"]
