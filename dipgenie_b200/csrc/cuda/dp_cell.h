@@ -10,6 +10,7 @@
 // so the winner is a plain integer max; key == 0 means "no live candidate" (cell stays NEG_INF, :568).
 // The winner's in-edge ordinals (e1 within in(i'), e2 within in(j')) are the predecessor code.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 #if defined(__CUDACC__)
@@ -30,20 +31,57 @@ DG_HD int popc64(uint64_t x) {
 #endif
 }
 
-// One transition (level l -> l+1) as the kernels see it.
-struct Transition {
+// One transition (level l -> l+1) as the kernels see it.  OffT = int32_t when in_off/in_edge point into
+// the global in-edge CSR, uint16_t when they point into a packed per-transition record staged in
+// shared memory (dp_prep.h: RecHeader), where offsets are relative to the record's own edge array.
+template <class OffT>
+struct TransitionT {
     int32_t k;                 // |level l|
     int32_t k2;                // |level l+1|
     int32_t W;                 // 64-bit mask words per set (0: no colours on either level)
-    const int32_t* in_off;     // in_off + first vertex of level l+1  (k2+1 readable entries)
-    const uint32_t* in_edge;   // whole in-edge pool; entry = source position | weight << 16
+    const OffT* in_off;        // k2+1 entries, indexed by destination position
+    const uint32_t* in_edge;   // entry = source position | weight << 16
     const uint64_t* msrc;      // [k ][2W]  hom words then het words
     const uint64_t* mdst;      // [k2][2W]
 };
+using Transition = TransitionT<int32_t>;
+
+// ---- packed per-transition records (staged through shared memory by the sweep kernel) ----------
+// record = RecHeader | in_off2 u16[k2+1] | pad4 | in_edge u32[n_in] | pad8 | msrc u64[k*2W] | mdst u64[k2*2W] | pad16
+// in_off2 is relative to the record's own in_edge array, so a record is self-contained.
+enum : uint16_t {
+    REC_WAIT = 1,        // grid-level wait (counter >= wait_target) before the transition
+    REC_ARRIVE = 2,      // grid-level arrive after the transition
+    REC_SRC_SMEM = 4,    // source layer lives in CTA 0's shared-memory tile
+    REC_DST_SMEM = 8,    // destination layer goes to CTA 0's shared-memory tile
+};
+enum : uint8_t { MODE_FAST = 0, MODE_STAGED = 1, MODE_GLOBAL = 2 };
+
+struct RecHeader {               // 32 bytes
+    uint16_t k, k2, W, flags;
+    uint32_t n_in, bytes;        // bytes: whole record, multiple of 16
+    uint32_t P, wait_target;
+    int64_t pred_off2;           // offset (cells) of level l+1's predecessor codes
+};
+static_assert(sizeof(RecHeader) == 32, "RecHeader layout");
+
+// View of a packed record (global or shared memory) as a transition.
+DG_HD void record_view(const uint8_t* rec, RecHeader& h, TransitionT<uint16_t>& tr) {
+    h = *reinterpret_cast<const RecHeader*>(rec);
+    tr.k = h.k; tr.k2 = h.k2; tr.W = h.W;
+    size_t o = sizeof(RecHeader);
+    tr.in_off = reinterpret_cast<const uint16_t*>(rec + o);
+    o += (((size_t)h.k2 + 1) * 2 + 3) & ~(size_t)3;
+    tr.in_edge = reinterpret_cast<const uint32_t*>(rec + o);
+    o += (size_t)h.n_in * 4; o = (o + 7) & ~(size_t)7;
+    tr.msrc = reinterpret_cast<const uint64_t*>(rec + o);
+    tr.mdst = tr.msrc + (size_t)h.k * 2 * h.W;
+}
 
 // delta = |(Hom u1 ∪ Hom v1) ∩ (Hom u2 ∪ Hom v2)| + |(Het u1 ∪ Het v1) △ (Het u2 ∪ Het v2)|
 // (approximator.cpp:614-619).  `het_only` returns just the second term (dp_entry::s_het, :662).
-DG_HD int pair_delta(const Transition& t, int i, int j, int i2, int j2, bool het_only = false) {
+template <class OffT>
+DG_HD int pair_delta(const TransitionT<OffT>& t, int i, int j, int i2, int j2, bool het_only = false) {
     const int W = t.W;
     if (W == 0) return 0;
     const uint64_t* si = t.msrc + (int64_t)i * 2 * W;
@@ -65,10 +103,10 @@ DG_HD int32_t key_value(uint64_t key) { return key ? (int32_t)(uint32_t)(key >> 
 
 // Gather for one destination cell.  `load(idx)` returns the source-layer value at flat index
 // (r*k + i)*k + j.  Returns the winning key (0 = dead cell); code = e1 << 16 | e2.
-template <class Load>
-DG_HD uint64_t relax_cell(const Transition& t, Load load, int r2, int i2, int j2, uint32_t& code) {
-    const int32_t a0 = t.in_off[i2], a1 = t.in_off[i2 + 1];
-    const int32_t b0 = t.in_off[j2], b1 = t.in_off[j2 + 1];
+template <class OffT, class Load>
+DG_HD uint64_t relax_cell(const TransitionT<OffT>& t, Load load, int r2, int i2, int j2, uint32_t& code) {
+    const int32_t a0 = (int32_t)t.in_off[i2], a1 = (int32_t)t.in_off[i2 + 1];
+    const int32_t b0 = (int32_t)t.in_off[j2], b1 = (int32_t)t.in_off[j2 + 1];
     uint64_t best = 0;
     uint32_t best_code = 0xFFFFFFFFu;
     for (int32_t e1 = a0; e1 < a1; ++e1) {

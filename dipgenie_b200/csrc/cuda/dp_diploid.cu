@@ -23,13 +23,21 @@
 
 namespace dg {
 
-constexpr int DIP_THREADS = 256;
-constexpr int DIP_CELLS_PER_CTA = DIP_THREADS * 8;
+// ---- kernel geometry -------------------------------------------------------------------------
+constexpr int DIP_CT = 512;                    // compute threads per CTA (16 warps)
+constexpr int DIP_THREADS = DIP_CT + 32;       // + one producer warp (record prefetch via bulk async copies)
+constexpr int DIP_CELLS_PER_CTA = DIP_CT * 4;
+constexpr int DIP_STAGES = 4;                  // record ring depth
+constexpr int DIP_STAGE_BYTES = 16384;
+constexpr int DIP_TILE_CELLS = 16384;          // int32 cells per shared-memory layer tile (x2)
+constexpr int DIP_QUEUE = 8;                   // look-ahead queue of (level, stage) entries
+constexpr size_t DIP_SMEM_BYTES = (size_t)DIP_STAGES * DIP_STAGE_BYTES + 2 * (size_t)DIP_TILE_CELLS * 4 +
+                                  DIP_STAGES * 8 + DIP_QUEUE * 8 + 16;
 
 constexpr uint32_t CTL_WAIT = 1u;     // grid-level wait before the transition
 constexpr uint32_t CTL_ARRIVE = 2u;   // grid-level arrive after the transition
 
-struct __align__(16) LevelCtl {       // one per transition l (level l -> l+1), 64 bytes
+struct __align__(16) LevelCtl {       // MODE_GLOBAL transitions read this instead of a staged record, 64 bytes
     int32_t voff2;                    // first vertex of level l+1
     int32_t k, k2, W;
     int32_t P;
@@ -40,8 +48,17 @@ struct __align__(16) LevelCtl {       // one per transition l (level l -> l+1), 
     int64_t pad1;
 };
 
+struct __align__(16) LevelIdx {       // one per transition, scanned by every CTA's producer lane, 16 bytes
+    int64_t rec_off;                  // byte offset of the packed record (-1: MODE_GLOBAL)
+    uint32_t rec_bytes;
+    uint16_t P;
+    uint16_t mode;
+};
+
 struct SweepArgs {
+    const LevelIdx* idx;
     const LevelCtl* ctl;
+    const uint8_t* records;
     const int32_t* in_off;
     const uint32_t* in_edge;
     const uint64_t* masks;
@@ -54,6 +71,7 @@ struct SweepArgs {
     int32_t l_begin, l_end, R;
 };
 
+// ---- PTX helpers -----------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -62,85 +80,203 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 __device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "DG_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DG_DONE_%=;\n"
+        "bra DG_WAIT_%=;\n"
+        "DG_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(DIP_CT) : "memory"); }
+
+// ---- the cell loop ---------------------------------------------------------------------------
+template <class OffT, class PredT, bool CHECK, bool SRC_SMEM, bool DST_SMEM>
+__device__ __forceinline__ void sweep_cells(const TransitionT<OffT>& t, const int32_t* __restrict__ src,
+                                            int32_t* __restrict__ dst, PredT* __restrict__ pl, int R, uint64_t first,
+                                            uint64_t stride, unsigned long long& hsum, unsigned long long& hlive) {
+    constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
+    auto load = [src](int64_t idx) { return SRC_SMEM ? src[idx] : __ldcg(src + idx); };
+    const uint32_t k2 = (uint32_t)t.k2, kk = k2 * k2;
+    const uint64_t ncell = (uint64_t)(R + 1) * kk;
+    if (ncell <= 0x7FFFFFFFull) {
+        const uint32_t n32 = (uint32_t)ncell, st32 = (uint32_t)stride;
+        for (uint32_t c = (uint32_t)first; c < n32; c += st32) {
+            const uint32_t r2 = c / kk, rem = c - r2 * kk;
+            const uint32_t i2 = rem / k2, j2 = rem - i2 * k2;
+            uint32_t code;
+            const uint64_t key = relax_cell(t, load, (int)r2, (int)i2, (int)j2, code);
+            if (DST_SMEM) dst[c] = key_value(key); else __stcg(dst + c, key_value(key));
+            pl[c] = key ? (PredT)(((code >> 16) << SH) | (code & 0xFFFFu)) : (PredT) ~(PredT)0;
+            if (CHECK && key) {
+                ++hlive;
+                hsum += cell_fold(c, key_value(key), 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+            }
+        }
+    } else {
+        for (uint64_t c = first; c < ncell; c += stride) {
+            const uint64_t r2 = c / kk, rem = c - r2 * kk;
+            const uint32_t i2 = (uint32_t)(rem / k2), j2 = (uint32_t)(rem - (uint64_t)i2 * k2);
+            uint32_t code;
+            const uint64_t key = relax_cell(t, load, (int)r2, (int)i2, (int)j2, code);
+            if (DST_SMEM) dst[c] = key_value(key); else __stcg(dst + c, key_value(key));
+            pl[c] = key ? (PredT)(((code >> 16) << SH) | (code & 0xFFFFu)) : (PredT) ~(PredT)0;
+            if (CHECK && key) {
+                ++hlive;
+                hsum += cell_fold(c, key_value(key), 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+            }
+        }
+    }
+}
+
+// Producer lane state: scans the level index for this CTA's next transitions, issues the bulk copies
+// of their records into free ring stages and publishes (level, stage) entries in the look-ahead queue.
+struct Producer {
+    int pf;            // scan cursor (level)
+    int n_written;     // queue entries published so far
+    int n_issued;      // records issued so far
+    bool ended;
+};
 
 template <class PredT, bool CHECK>
-__global__ void __launch_bounds__(DIP_THREADS) dip_sweep_kernel(const SweepArgs a) {
+__global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* const stage_base = smem;
+    int32_t* const tileS0 = reinterpret_cast<int32_t*>(smem + (size_t)DIP_STAGES * DIP_STAGE_BYTES);
+    int32_t* const tileS1 = tileS0 + DIP_TILE_CELLS;
+    uint64_t* const mbar = reinterpret_cast<uint64_t*>(tileS1 + DIP_TILE_CELLS);
+    int2* const queue = reinterpret_cast<int2*>(mbar + DIP_STAGES);
+
     const int cta = blockIdx.x, tid = threadIdx.x;
+    const bool is_compute = tid < DIP_CT;
+    const bool is_producer = tid == DIP_CT;          // lane 0 of the extra warp
     PredT* __restrict__ pred = reinterpret_cast<PredT*>(a.pred);
-    constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
 
-    for (int l = a.l_begin; l < a.l_end; ++l) {
-        const LevelCtl* __restrict__ cg = a.ctl + l;
-        const int P = __ldg(&cg->P);
-        if (cta >= P) continue;                       // not a participant of this transition
-        const uint32_t flags = __ldg(&cg->flags);
-        if (flags & CTL_WAIT) {
-            if (tid == 0) {
-                const unsigned int target = __ldg(&cg->wait_target);
-                while (ld_acquire_u32(a.counter) < target) __nanosleep(20);
+    if (tid == 0) {
+        for (int s = 0; s < DIP_STAGES; ++s) mbar_init(smem_u32(mbar + s), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int x = tid; x <= a.R; x += DIP_THREADS) tileS0[x] = 0;   // level 0: all R+1 layers start at 0 (approximator.cpp:535)
+    __syncthreads();
+
+    Producer pr;
+    pr.pf = a.l_begin; pr.n_written = 0; pr.n_issued = 0; pr.ended = false;
+    auto produce = [&](int t_cur, int rec_consumed) {
+        // publish entries for iterations < t_cur + DIP_QUEUE - 1, as far as ring stages are free
+        while (!pr.ended && pr.n_written < t_cur + DIP_QUEUE - 1) {
+            while (pr.pf < a.l_end && cta >= (int)__ldg(&a.idx[pr.pf].P)) ++pr.pf;
+            if (pr.pf >= a.l_end) {
+                queue[pr.n_written % DIP_QUEUE] = make_int2(-1, -1);
+                ++pr.n_written; pr.ended = true;
+                break;
             }
+            const int4 raw = __ldg(reinterpret_cast<const int4*>(a.idx + pr.pf));
+            LevelIdx li;
+            memcpy(&li, &raw, sizeof li);
+            int stage = -1;
+            if (li.rec_off >= 0) {
+                if (pr.n_issued - rec_consumed >= DIP_STAGES) break;      // ring full: retry after the next level
+                stage = pr.n_issued % DIP_STAGES;
+                const uint32_t bar = smem_u32(mbar + stage);
+                mbar_expect_tx(bar, li.rec_bytes);
+                bulk_g2s(smem_u32(stage_base + (size_t)stage * DIP_STAGE_BYTES), a.records + li.rec_off, li.rec_bytes, bar);
+                ++pr.n_issued;
+            }
+            queue[pr.n_written % DIP_QUEUE] = make_int2(pr.pf, stage);
+            ++pr.n_written; ++pr.pf;
         }
-        __syncthreads();
+    };
+    if (is_producer) produce(0, 0);
 
-        Transition t;
-        t.k = __ldg(&cg->k);
-        t.k2 = __ldg(&cg->k2);
-        t.W = __ldg(&cg->W);
-        t.in_off = a.in_off + __ldg(&cg->voff2);
-        t.in_edge = a.in_edge;
-        t.msrc = a.masks + __ldg(&cg->msrc_off);
-        t.mdst = a.masks + __ldg(&cg->mdst_off);
-        const int32_t* __restrict__ src = (l & 1) ? a.tile1 : a.tile0;
-        int32_t* __restrict__ dst = (l & 1) ? a.tile0 : a.tile1;
-        PredT* __restrict__ pl = pred + __ldg(&cg->pred_off2);
-        auto load = [src](int64_t idx) { return __ldcg(src + idx); };
-
-        const uint32_t kk = (uint32_t)t.k2 * (uint32_t)t.k2;
-        const uint64_t ncell = (uint64_t)(a.R + 1) * kk;
-        unsigned long long hsum = 0, hlive = 0;
-        if (ncell <= 0x7FFFFFFFull) {
-            const uint32_t n32 = (uint32_t)ncell, stride = (uint32_t)P * DIP_THREADS;
-            for (uint32_t c = (uint32_t)cta * DIP_THREADS + tid; c < n32; c += stride) {
-                const uint32_t r2 = c / kk, rem = c - r2 * kk;
-                const uint32_t i2 = rem / (uint32_t)t.k2, j2 = rem - i2 * (uint32_t)t.k2;
-                uint32_t code;
-                const uint64_t key = relax_cell(t, load, (int)r2, (int)i2, (int)j2, code);
-                __stcg(dst + c, key_value(key));
-                pl[c] = key ? (PredT)(((code >> 16) << SH) | (code & 0xFFFFu)) : (PredT) ~(PredT)0;
-                if (CHECK && key) {
-                    ++hlive;
-                    hsum += cell_fold(c, key_value(key), 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+    int t = 0, rc = 0;                               // iteration index, records consumed so far
+    for (;;) {
+        __syncthreads();                             // iteration t-1 complete: its layer is whole, its stage is free
+        const int2 e = queue[t % DIP_QUEUE];
+        const int l = e.x, stage = e.y;
+        if (l < 0) break;
+        if (is_producer) produce(t + 1, rc);
+        if (is_compute) {
+            unsigned long long hsum = 0, hlive = 0;
+            if (stage >= 0) {
+                const uint8_t* rec = stage_base + (size_t)stage * DIP_STAGE_BYTES;
+                mbar_wait(smem_u32(mbar + stage), (uint32_t)((rc / DIP_STAGES) & 1));
+                RecHeader h;
+                TransitionT<uint16_t> tr;
+                record_view(rec, h, tr);
+                if (h.flags & REC_WAIT) {
+                    if (tid == 0) while (ld_acquire_u32(a.counter) < h.wait_target) __nanosleep(20);
+                    bar_compute();
+                }
+                const bool ssm = (h.flags & REC_SRC_SMEM) != 0, dsm = (h.flags & REC_DST_SMEM) != 0;
+                const int32_t* src = ssm ? ((l & 1) ? tileS1 : tileS0) : ((l & 1) ? a.tile1 : a.tile0);
+                int32_t* dst = dsm ? ((l & 1) ? tileS0 : tileS1) : ((l & 1) ? a.tile0 : a.tile1);
+                PredT* pl = pred + h.pred_off2;
+                const uint64_t first = (uint64_t)cta * DIP_CT + tid, stride = (uint64_t)h.P * DIP_CT;
+                if (ssm) {
+                    if (dsm) sweep_cells<uint16_t, PredT, CHECK, true, true>(tr, src, dst, pl, a.R, first, stride, hsum, hlive);
+                    else sweep_cells<uint16_t, PredT, CHECK, true, false>(tr, src, dst, pl, a.R, first, stride, hsum, hlive);
+                } else {
+                    if (dsm) sweep_cells<uint16_t, PredT, CHECK, false, true>(tr, src, dst, pl, a.R, first, stride, hsum, hlive);
+                    else sweep_cells<uint16_t, PredT, CHECK, false, false>(tr, src, dst, pl, a.R, first, stride, hsum, hlive);
+                }
+                if (h.flags & REC_ARRIVE) {
+                    bar_compute();
+                    if (tid == 0) red_release_add_u32(a.counter, 1u);
+                }
+            } else {
+                const LevelCtl* __restrict__ cg = a.ctl + l;
+                const uint32_t flags = __ldg(&cg->flags);
+                if (flags & CTL_WAIT) {
+                    if (tid == 0) {
+                        const unsigned int target = __ldg(&cg->wait_target);
+                        while (ld_acquire_u32(a.counter) < target) __nanosleep(20);
+                    }
+                    bar_compute();
+                }
+                Transition tr;
+                tr.k = __ldg(&cg->k); tr.k2 = __ldg(&cg->k2); tr.W = __ldg(&cg->W);
+                tr.in_off = a.in_off + __ldg(&cg->voff2);
+                tr.in_edge = a.in_edge;
+                tr.msrc = a.masks + __ldg(&cg->msrc_off);
+                tr.mdst = a.masks + __ldg(&cg->mdst_off);
+                const int32_t* src = (l & 1) ? a.tile1 : a.tile0;
+                int32_t* dst = (l & 1) ? a.tile0 : a.tile1;
+                PredT* pl = pred + __ldg(&cg->pred_off2);
+                const uint64_t first = (uint64_t)cta * DIP_CT + tid, stride = (uint64_t)__ldg(&cg->P) * DIP_CT;
+                sweep_cells<int32_t, PredT, CHECK, false, false>(tr, src, dst, pl, a.R, first, stride, hsum, hlive);
+                if (flags & CTL_ARRIVE) {
+                    bar_compute();
+                    if (tid == 0) red_release_add_u32(a.counter, 1u);
                 }
             }
-        } else {
-            const uint64_t stride = (uint64_t)P * DIP_THREADS;
-            for (uint64_t c = (uint64_t)cta * DIP_THREADS + tid; c < ncell; c += stride) {
-                const uint64_t r2 = c / kk, rem = c - r2 * kk;
-                const uint32_t i2 = (uint32_t)(rem / (uint32_t)t.k2), j2 = (uint32_t)(rem - (uint64_t)i2 * (uint32_t)t.k2);
-                uint32_t code;
-                const uint64_t key = relax_cell(t, load, (int)r2, (int)i2, (int)j2, code);
-                __stcg(dst + c, key_value(key));
-                pl[c] = key ? (PredT)(((code >> 16) << SH) | (code & 0xFFFFu)) : (PredT) ~(PredT)0;
-                if (CHECK && key) {
-                    ++hlive;
-                    hsum += cell_fold(c, key_value(key), 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+            if (CHECK) {
+                for (int o = 16; o > 0; o >>= 1) {
+                    hsum += __shfl_down_sync(0xFFFFFFFFu, hsum, o);
+                    hlive += __shfl_down_sync(0xFFFFFFFFu, hlive, o);
+                }
+                if ((tid & 31) == 0 && hlive) {
+                    atomicAdd(a.level_sum + l + 1, hsum);
+                    atomicAdd(a.level_live + l + 1, hlive);
                 }
             }
         }
-        if (CHECK) {
-            for (int o = 16; o > 0; o >>= 1) {
-                hsum += __shfl_down_sync(0xFFFFFFFFu, hsum, o);
-                hlive += __shfl_down_sync(0xFFFFFFFFu, hlive, o);
-            }
-            if ((tid & 31) == 0 && hlive) {
-                atomicAdd(a.level_sum + l + 1, hsum);
-                atomicAdd(a.level_live + l + 1, hlive);
-            }
-        }
-        if (flags & CTL_ARRIVE) {
-            __syncthreads();
-            if (tid == 0) red_release_add_u32(a.counter, 1u);
-        }
+        if (stage >= 0) ++rc;
+        ++t;
     }
 }
 
@@ -168,6 +304,8 @@ struct dg_dip {
     int pred_bytes = 2;
     int grid = 1;
     DevBuf<LevelCtl> ctl;
+    DevBuf<LevelIdx> idx;
+    DevBuf<uint8_t> records;
     DevBuf<int32_t> level_off, in_off, lvlW;
     DevBuf<uint32_t> in_edge;
     DevBuf<uint64_t> masks;
@@ -195,19 +333,31 @@ static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out) {
     const int L = p.L;
     d->pred_bytes = (p.max_indeg <= 255) ? 2 : 4;
 
-    // grid: enough CTAs for the widest transition, at most one co-resident wave
+    // grid: enough CTAs for the widest transition, at most one co-resident wave (cooperative launch)
+    const void* fn = d->pred_bytes == 2 ? (const void*)dip_sweep_kernel<uint16_t, false> : (const void*)dip_sweep_kernel<uint32_t, false>;
+    const void* fnc = d->pred_bytes == 2 ? (const void*)dip_sweep_kernel<uint16_t, true> : (const void*)dip_sweep_kernel<uint32_t, true>;
+    DG_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
+    DG_CUDA(ctx, cudaFuncSetAttribute(fnc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
     int per_sm = 0;
-    if (d->pred_bytes == 2) DG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dip_sweep_kernel<uint16_t, false>, DIP_THREADS, 0));
-    else DG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dip_sweep_kernel<uint32_t, false>, DIP_THREADS, 0));
+    DG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fnc, DIP_THREADS, DIP_SMEM_BYTES));
     if (per_sm < 1) return fail(ctx, DG_ERR_CUDA, "dg_dip_create: sweep kernel cannot be resident");
-    const int max_grid = ctx->sm_count * std::min(per_sm, 2);
+    const int max_grid = ctx->sm_count * per_sm;
     const uint64_t widest = (uint64_t)(p.R + 1) * (uint64_t)p.kmax * (uint64_t)p.kmax;
     const uint64_t want = (widest + DIP_CELLS_PER_CTA - 1) / DIP_CELLS_PER_CTA;
-    d->grid = (int)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)max_grid);
-    plan_participants(p, d->grid, DIP_CELLS_PER_CTA);
+    SweepShape shape;
+    shape.grid = (int)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)max_grid);
+    shape.cells_per_cta = DIP_CELLS_PER_CTA;
+    shape.tile_cells = DIP_TILE_CELLS;
+    shape.stage_bytes = DIP_STAGE_BYTES;
+    plan_sweep(p, shape);
+    int gmax = 1;
+    for (int l = 0; l + 1 < L; ++l) gmax = std::max(gmax, p.P[l]);
+    d->grid = gmax;
 
     std::vector<LevelCtl> ctl((size_t)std::max(L - 1, 1));
+    std::vector<LevelIdx> idx((size_t)std::max(L - 1, 1));
     memset(ctl.data(), 0, ctl.size() * sizeof(LevelCtl));
+    memset(idx.data(), 0, idx.size() * sizeof(LevelIdx));
     for (int l = 0; l + 1 < L; ++l) {
         LevelCtl& c = ctl[l];
         c.voff2 = p.level_off[l + 1];
@@ -216,13 +366,25 @@ static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out) {
         c.W = p.lvlW[l];
         c.P = p.P[l];
         c.flags = 0;
-        if (l > 0 && p.bar_edge[l - 1]) { c.flags |= CTL_WAIT; c.wait_target = p.bar_target[l - 1]; }
-        if (p.bar_edge[l]) c.flags |= CTL_ARRIVE;
+        if (p.flags[l] & REC_WAIT) { c.flags |= CTL_WAIT; c.wait_target = p.bar_target[l - 1]; }
+        if (p.flags[l] & REC_ARRIVE) c.flags |= CTL_ARRIVE;
         c.msrc_off = p.msrc_off[l]; c.mdst_off = p.mdst_off[l]; c.pred_off2 = p.pred_off[l + 1];
+        LevelIdx& x = idx[l];
+        x.rec_off = p.rec_off[l];
+        x.rec_bytes = 0;
+        if (p.rec_off[l] >= 0) {
+            RecHeader h;
+            memcpy(&h, p.records.data() + p.rec_off[l], sizeof h);
+            x.rec_bytes = h.bytes;
+        }
+        x.P = (uint16_t)p.P[l];
+        x.mode = p.mode[l];
     }
 
     cudaStream_t s = ctx->stream;
     DG_CUDA(ctx, d->ctl.upload(ctl.data(), ctl.size(), s));
+    DG_CUDA(ctx, d->idx.upload(idx.data(), idx.size(), s));
+    DG_CUDA(ctx, d->records.upload(p.records.data(), p.records.size(), s));
     DG_CUDA(ctx, d->level_off.upload(p.level_off.data(), p.level_off.size(), s));
     DG_CUDA(ctx, d->in_off.upload(p.in_off.data(), p.in_off.size(), s));
     DG_CUDA(ctx, d->in_edge.upload(p.in_edge.data(), p.in_edge.size(), s));
@@ -243,11 +405,12 @@ static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out) {
     DG_CUDA(ctx, d->p2.alloc((size_t)2 * (p.R + 2)));
     for (auto& e : d->ev) DG_CUDA(ctx, cudaEventCreate(&e));
     DG_CUDA(ctx, cudaStreamSynchronize(s));
-    d->device_bytes = d->ctl.bytes() + d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->lvlW.bytes() +
+    d->device_bytes = d->idx.bytes() + d->records.bytes() + d->ctl.bytes() + d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->lvlW.bytes() +
                       d->masks.bytes() + d->msrc_off.bytes() + d->mdst_off.bytes() + d->pred_off.bytes() + d->tile0.bytes() +
                       d->tile1.bytes() + d->pred.bytes() + d->level_sum.bytes() + d->level_live.bytes();
     // the big host arrays are no longer needed
     std::vector<uint32_t>().swap(p.in_edge);
+    std::vector<uint8_t>().swap(p.records);
     std::vector<uint64_t>().swap(p.masks);
     std::vector<int32_t>().swap(p.in_off);
     *out = d.release();
@@ -267,6 +430,7 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
         DG_CUDA(ctx, cudaStreamSynchronize(s));   // basis is a stack-lifetime staging buffer
     }
     SweepArgs a;
+    a.idx = d->idx.p; a.records = d->records.p;
     a.ctl = d->ctl.p; a.in_off = d->in_off.p; a.in_edge = d->in_edge.p; a.masks = d->masks.p;
     a.tile0 = d->tile0.p; a.tile1 = d->tile1.p; a.pred = d->pred.p; a.counter = d->counter.p;
     a.level_sum = d->level_sum.p; a.level_live = d->level_live.p;
@@ -276,7 +440,7 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     if (p.L > 1) {
         void* args[] = {(void*)&a};
         const void* fn = check ? (const void*)dip_sweep_kernel<PredT, true> : (const void*)dip_sweep_kernel<PredT, false>;
-        DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, 0, s));
+        DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, s));
         ++d->launches;
     }
     DG_CUDA(ctx, cudaEventRecord(d->ev[1], s));

@@ -2,6 +2,7 @@
 #include "dp_prep.h"
 
 #include <algorithm>
+#include <cstring>
 
 namespace dg {
 
@@ -106,26 +107,83 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
     return true;
 }
 
-void plan_participants(DipPlan& p, int grid, int cells_per_cta) {
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+void plan_sweep(DipPlan& p, const SweepShape& sh) {
     const int L = p.L;
+    const int grid = sh.grid < 1 ? 1 : sh.grid;
+    const uint64_t cpc = sh.cells_per_cta < 1 ? 1 : (uint64_t)sh.cells_per_cta;
     p.P.assign(L, 1); p.bar_target.assign(L, 0); p.bar_edge.assign(L, 0);
-    if (grid < 1) grid = 1;
-    if (cells_per_cta < 1) cells_per_cta = 1;
-    for (int l = 0; l + 1 < L; ++l) {
-        const uint64_t k2 = (uint64_t)(p.level_off[l + 2] - p.level_off[l + 1]);
-        const uint64_t cells = (uint64_t)(p.R + 1) * k2 * k2;
-        uint64_t want = (cells + (uint64_t)cells_per_cta - 1) / (uint64_t)cells_per_cta;
-        p.P[l] = (int32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)grid);
+    p.mode.assign(L, MODE_GLOBAL); p.flags.assign(L, 0); p.rec_off.assign(L, -1);
+    p.records.clear(); p.n_fast = p.n_staged = p.n_global = 0;
+    const int T = L - 1;                       // number of transitions
+    std::vector<size_t> rec_bytes(L, 0);
+    auto cells_of = [&](int l) { const uint64_t k = (uint64_t)(p.level_off[l + 1] - p.level_off[l]); return (uint64_t)(p.R + 1) * k * k; };
+    for (int l = 0; l < T; ++l) {
+        const int32_t k = p.level_off[l + 1] - p.level_off[l], k2 = p.level_off[l + 2] - p.level_off[l + 1];
+        const int64_t n_in = (int64_t)p.in_off[p.level_off[l + 2]] - (int64_t)p.in_off[p.level_off[l + 1]];
+        const int W = p.lvlW[l];
+        size_t b = sizeof(RecHeader) + align_up((size_t)(k2 + 1) * 2, 4);
+        b += (size_t)n_in * 4; b = align_up(b, 8);
+        b += (size_t)(k + k2) * 2 * W * 8; b = align_up(b, 16);
+        rec_bytes[l] = b;
+        const bool staged_ok = b <= (size_t)sh.stage_bytes && n_in < 65536;
+        const bool fits = cells_of(l) <= (uint64_t)sh.tile_cells && cells_of(l + 1) <= (uint64_t)sh.tile_cells;
+        p.mode[l] = !staged_ok ? MODE_GLOBAL : (fits ? MODE_FAST : MODE_STAGED);
+        if (p.mode[l] == MODE_FAST) { p.P[l] = 1; ++p.n_fast; }
+        else {
+            const uint64_t want = (cells_of(l + 1) + cpc - 1) / cpc;
+            p.P[l] = (int32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)grid);
+            if (p.mode[l] == MODE_STAGED) ++p.n_staged; else ++p.n_global;
+        }
     }
     // A grid barrier follows transition l unless both it and the next one run on CTA 0 alone.
     uint32_t acc = 0;
-    for (int l = 0; l + 1 < L; ++l) {
-        const bool last = (l + 2 >= L);
-        const int pn = last ? 1 : p.P[l + 1];
+    for (int l = 0; l < T; ++l) {
+        const int pn = (l + 1 < T) ? p.P[l + 1] : 1;
         const bool edge = (p.P[l] > 1) || (pn > 1);
         p.bar_edge[l] = edge ? 1 : 0;
         if (edge) acc += (uint32_t)p.P[l];
         p.bar_target[l] = acc;
+    }
+    for (int l = 0; l < T; ++l) {
+        uint16_t f = 0;
+        if (l > 0 && p.bar_edge[l - 1]) f |= REC_WAIT;
+        if (p.bar_edge[l]) f |= REC_ARRIVE;
+        // layer l lives in shared memory iff it is produced and consumed by FAST transitions (level 0: by the kernel prologue)
+        const bool fast = p.mode[l] == MODE_FAST;
+        if (fast && (l == 0 || p.mode[l - 1] == MODE_FAST)) f |= REC_SRC_SMEM;
+        if (fast && l + 1 < T && p.mode[l + 1] == MODE_FAST) f |= REC_DST_SMEM;
+        p.flags[l] = f;
+    }
+    // pack records
+    size_t total = 0;
+    for (int l = 0; l < T; ++l) if (p.mode[l] != MODE_GLOBAL) { p.rec_off[l] = (int64_t)total; total += rec_bytes[l]; }
+    p.records.assign(total, 0);
+    for (int l = 0; l < T; ++l) {
+        if (p.mode[l] == MODE_GLOBAL) continue;
+        uint8_t* r = p.records.data() + p.rec_off[l];
+        const int32_t mid = p.level_off[l + 1];
+        const int32_t k = mid - p.level_off[l], k2 = p.level_off[l + 2] - mid;
+        const int32_t e0 = p.in_off[mid], e1 = p.in_off[p.level_off[l + 2]];
+        const int W = p.lvlW[l];
+        RecHeader h;
+        h.k = (uint16_t)k; h.k2 = (uint16_t)k2; h.W = (uint16_t)W; h.flags = p.flags[l];
+        h.n_in = (uint32_t)(e1 - e0); h.bytes = (uint32_t)rec_bytes[l];
+        h.P = (uint32_t)p.P[l]; h.wait_target = (l > 0) ? p.bar_target[l - 1] : 0;
+        h.pred_off2 = p.pred_off[l + 1];
+        memcpy(r, &h, sizeof h);
+        size_t o = sizeof(RecHeader);
+        uint16_t* off2 = reinterpret_cast<uint16_t*>(r + o);
+        for (int32_t x = 0; x <= k2; ++x) off2[x] = (uint16_t)(p.in_off[mid + x] - e0);
+        o += align_up((size_t)(k2 + 1) * 2, 4);
+        if (e1 > e0) memcpy(r + o, &p.in_edge[e0], (size_t)(e1 - e0) * 4);
+        o += (size_t)(e1 - e0) * 4; o = align_up(o, 8);
+        if (W > 0) {
+            memcpy(r + o, &p.masks[(size_t)p.msrc_off[l]], (size_t)k * 2 * W * 8);
+            o += (size_t)k * 2 * W * 8;
+            memcpy(r + o, &p.masks[(size_t)p.mdst_off[l]], (size_t)k2 * 2 * W * 8);
+        }
     }
 }
 

@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 
+#include "dp_cell.h"
+
 namespace dg {
 
 struct DipGraphView {
@@ -37,6 +39,13 @@ struct DipGraphView {
 constexpr uint32_t IN_POS_MASK = 0xFFFFu;   // in_edge = pos | (w << 16)
 constexpr int IN_W_SHIFT = 16;
 
+struct SweepShape {              // kernel geometry the plan is made for
+    int grid = 1;                // CTAs in the cooperative grid
+    int cells_per_cta = 2048;    // destination cells one CTA takes per transition before more CTAs join
+    int tile_cells = 16384;      // int32 cells per shared-memory layer tile (two tiles)
+    int stage_bytes = 16384;     // bytes per record stage in shared memory
+};
+
 struct DipPlan {
     int32_t L = 0, V = 0, R = 0;
     int32_t kmax = 0, max_indeg = 0, Wmax = 0;
@@ -52,6 +61,11 @@ struct DipPlan {
     std::vector<int32_t> P;            // [L]   CTAs taking part in transition l
     std::vector<uint32_t> bar_target;  // [L]   arrivals that must be visible once transition l is complete
     std::vector<uint8_t> bar_edge;     // [L]   1 = a grid-level barrier follows transition l
+    std::vector<uint8_t> mode;         // [L]   MODE_* of transition l
+    std::vector<uint16_t> flags;       // [L]   REC_* of transition l
+    std::vector<int64_t> rec_off;      // [L]   byte offset of transition l's record in `records` (-1: none)
+    std::vector<uint8_t> records;      // packed records of all FAST/STAGED transitions (16-byte aligned)
+    int64_t n_fast = 0, n_staged = 0, n_global = 0;
     // accounting
     uint64_t cell_updates = 0;         // U = (R+1) * sum_l E_l^2
     uint64_t cells = 0;                // C = (R+1) * sum_{l>=1} k_l^2
@@ -62,8 +76,10 @@ struct DipPlan {
 // Builds everything except P / bar_*; returns false and sets plan.error on malformed input.
 bool build_dip_plan(const DipGraphView& g, DipPlan& plan);
 
-// Chooses participants per transition for a grid of `grid` CTAs where one CTA comfortably handles
-// `cells_per_cta` destination cells, and derives the barrier schedule.
-void plan_participants(DipPlan& plan, int grid, int cells_per_cta);
+// Chooses, for the given kernel geometry, the mode (FAST: CTA 0 alone with both layers in shared
+// memory; STAGED: P CTAs, metadata staged through shared memory, layers in HBM/L2; GLOBAL: metadata
+// read in place) and the participants of every transition, derives the monotone-counter barrier
+// schedule, and packs the records.
+void plan_sweep(DipPlan& plan, const SweepShape& shape);
 
 }  // namespace dg

@@ -56,8 +56,11 @@ class DpEmu:
     def __init__(self):
         self.lib = C.CDLL(_build_emu())
 
-    def dp_diploid(self, g, R, force_pred32=False):
+    def dp_diploid(self, g, R, force_pred32=False, shape=None):
+        """shape = (grid, cells_per_cta, tile_cells, stage_bytes) of the emulated kernel geometry (0 = default)."""
         L = g.n_levels
+        shp = np.array(list(shape) if shape else [0, 0, 0, 0], np.int32)
+        modes = np.zeros(3, np.int64)
         val, sh, n1, n2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         p1 = np.zeros(2 * (R + 2), np.int32)
         p2 = np.zeros(2 * (R + 2), np.int32)
@@ -67,11 +70,12 @@ class DpEmu:
         rc = self.lib.emu_dp_diploid(
             C.c_int32(L), P(g.level_off), P(g.adj_off), P(g.adj_dst), P(g.adj_w), P(g.col_off), P(g.col_val),
             P(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R), C.byref(val), C.byref(sh), P(p1),
-            C.byref(n1), P(p2), C.byref(n2), P(cs), P(lv), C.c_int32(1 if force_pred32 else 0))
+            C.byref(n1), P(p2), C.byref(n2), P(cs), P(lv), C.c_int32(1 if force_pred32 else 0), P(shp), P(modes))
         if rc != 0:
             raise RuntimeError(f"emu_dp_diploid rc={rc}")
         return dict(value=val.value, s_het=sh.value, p1_edges=p1[: 2 * n1.value].reshape(-1, 2).copy(),
-                    p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy(), checksum=cs, live=lv)
+                    p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy(), checksum=cs, live=lv,
+                    modes=dict(fast=int(modes[0]), staged=int(modes[1]), global_=int(modes[2])))
 
 
 @pytest.fixture(scope="session")

@@ -1,8 +1,10 @@
 // tests/emu/dp_emu.cpp — TEST-ONLY CPU emulation of the CUDA diploid sweep.
-// Runs the exact host planning (dp_prep.cpp) and the exact per-cell / traceback code (dp_cell.h)
-// the kernels run, with the thread grid replaced by a serial loop, so that `-m "not gpu"` tests can
-// check the gather formulation, the mask construction, the predecessor codes and the traceback
-// against the oracle without a GPU.  Never part of the product library.
+// Runs the exact host planning (dp_prep.cpp: in-edge CSR, colour masks, modes, packed records, barrier
+// schedule) and the exact per-cell / record-view / traceback code (dp_cell.h) the kernels run, with the
+// thread grid replaced by serial loops and the shared-memory tiles / record stages by host buffers, so
+// that `-m "not gpu"` tests can check the gather formulation, the record packing, the tile placement
+// flags, the monotone barrier targets, the predecessor codes and the traceback against the oracle
+// without a GPU.  Never part of the product library.
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -12,42 +14,75 @@
 
 using namespace dg;
 
+template <class PredT, class OffT, class Load, class Store>
+static void cells(const TransitionT<OffT>& t, int R, Load load, Store store, PredT* pl, uint64_t& h, uint64_t& live) {
+    constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
+    const size_t ncell = (size_t)(R + 1) * t.k2 * t.k2;
+    for (size_t c = 0; c < ncell; ++c) {
+        const int j2 = (int)(c % t.k2), i2 = (int)((c / t.k2) % t.k2), r2 = (int)(c / ((size_t)t.k2 * t.k2));
+        uint32_t code;
+        const uint64_t key = relax_cell(t, load, r2, i2, j2, code);
+        store(c, key_value(key));
+        pl[c] = key ? (PredT)(((code >> 16) << SH) | (code & 0xFFFFu)) : (PredT) ~(PredT)0;
+        if (key) {
+            ++live;
+            h += cell_fold(c, key_value(key), 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+        }
+    }
+}
+
 template <class PredT>
-static int run(const DipPlan& p, int32_t* sink_value, int32_t* sink_s_het, int32_t* p1, int32_t* n1,
-               int32_t* p2, int32_t* n2, uint64_t* level_checksum, uint64_t* level_live) {
+static int run(const DipPlan& p, const SweepShape& sh, int32_t* sink_value, int32_t* sink_s_het, int32_t* p1,
+               int32_t* n1, int32_t* p2, int32_t* n2, uint64_t* level_checksum, uint64_t* level_live) {
     const int R = p.R, L = p.L;
     std::vector<PredT> pred((size_t)p.pred_off[L]);
-    std::vector<int32_t> cur((size_t)(R + 1), 0), next;
-    constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
+    const size_t widest = (size_t)(R + 1) * p.kmax * p.kmax;
+    // poison values make a wrong tile-placement flag visible
+    std::vector<int32_t> g0(widest, 0x5A5A5A5A), g1(widest, 0x5A5A5A5A), s0(sh.tile_cells, 0x3C3C3C3C), s1(sh.tile_cells, 0x3C3C3C3C);
+    for (int r = 0; r <= R; ++r) { g0[r] = 0; s0[r] = 0; }
+    std::vector<uint8_t> stage((size_t)sh.stage_bytes + 16);
+    uint32_t counter = 0;
     for (int l = 0; l + 1 < L; ++l) {
-        Transition t;
-        t.k = p.level_off[l + 1] - p.level_off[l];
-        t.k2 = p.level_off[l + 2] - p.level_off[l + 1];
-        t.W = p.lvlW[l];
-        t.in_off = p.in_off.data() + p.level_off[l + 1];
-        t.in_edge = p.in_edge.data();
-        t.msrc = p.masks.data() + p.msrc_off[l];
-        t.mdst = p.masks.data() + p.mdst_off[l];
-        const size_t ncell = (size_t)(R + 1) * t.k2 * t.k2;
-        next.assign(ncell, NEG_INF);
         uint64_t h = FOLD_BASIS, live = 0;
-        const int32_t* src = cur.data();
-        for (size_t c = 0; c < ncell; ++c) {
-            const int j2 = (int)(c % t.k2), i2 = (int)((c / t.k2) % t.k2), r2 = (int)(c / ((size_t)t.k2 * t.k2));
-            uint32_t code;
-            const uint64_t key = relax_cell(t, [src](int64_t idx) { return src[idx]; }, r2, i2, j2, code);
-            next[c] = key_value(key);
-            pred[(size_t)p.pred_off[l + 1] + c] = key ? (PredT)(((code >> 16) << SH) | (code & 0xFFFFu)) : (PredT)~(PredT)0;
-            if (key) {
-                ++live;
-                h += cell_fold(c, next[c], 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
-            }
+        PredT* pl = pred.data() + p.pred_off[l + 1];
+        if (p.mode[l] != MODE_GLOBAL) {
+            RecHeader hd;
+            memcpy(&hd, p.records.data() + p.rec_off[l], sizeof hd);
+            if (hd.bytes > (uint32_t)sh.stage_bytes || hd.bytes % 16 != 0 || p.rec_off[l] % 16 != 0) return -10;
+            memcpy(stage.data(), p.records.data() + p.rec_off[l], hd.bytes);
+            TransitionT<uint16_t> t;
+            record_view(stage.data(), hd, t);
+            if ((hd.flags & REC_WAIT) && counter < hd.wait_target) return -11;       // would dead-lock on the GPU
+            const bool ssm = hd.flags & REC_SRC_SMEM, dsm = hd.flags & REC_DST_SMEM;
+            if ((ssm || dsm) && (p.mode[l] != MODE_FAST || hd.P != 1)) return -12;
+            const int32_t* src = ssm ? ((l & 1) ? s1.data() : s0.data()) : ((l & 1) ? g1.data() : g0.data());
+            int32_t* dst = dsm ? ((l & 1) ? s0.data() : s1.data()) : ((l & 1) ? g0.data() : g1.data());
+            if ((ssm && (size_t)(R + 1) * t.k * t.k > (size_t)sh.tile_cells) ||
+                (dsm && (size_t)(R + 1) * t.k2 * t.k2 > (size_t)sh.tile_cells)) return -13;
+            if (hd.pred_off2 != p.pred_off[l + 1]) return -14;
+            cells<PredT>(t, R, [src](int64_t i) { return src[i]; }, [dst](size_t c, int32_t v) { dst[c] = v; }, pl, h, live);
+            if (hd.flags & REC_ARRIVE) counter += hd.P;
+        } else {
+            Transition t;
+            t.k = p.level_off[l + 1] - p.level_off[l];
+            t.k2 = p.level_off[l + 2] - p.level_off[l + 1];
+            t.W = p.lvlW[l];
+            t.in_off = p.in_off.data() + p.level_off[l + 1];
+            t.in_edge = p.in_edge.data();
+            t.msrc = p.masks.data() + p.msrc_off[l];
+            t.mdst = p.masks.data() + p.mdst_off[l];
+            if ((p.flags[l] & REC_WAIT) && counter < p.bar_target[l - 1]) return -11;
+            const int32_t* src = (l & 1) ? g1.data() : g0.data();
+            int32_t* dst = (l & 1) ? g0.data() : g1.data();
+            cells<PredT>(t, R, [src](int64_t i) { return src[i]; }, [dst](size_t c, int32_t v) { dst[c] = v; }, pl, h, live);
+            if (p.flags[l] & REC_ARRIVE) counter += (uint32_t)p.P[l];
         }
+        if (counter != p.bar_target[l]) return -15;
         if (level_checksum) { level_checksum[l + 1] = h; level_live[l + 1] = live; }
-        cur.swap(next);
     }
     const size_t ks = (size_t)(p.level_off[L] - p.level_off[L - 1]);
-    *sink_value = cur[(size_t)R * ks * ks];   // cell (r=R,0,0) of the last level (:730, :775)
+    const std::vector<int32_t>& last = ((L - 1) & 1) ? g1 : g0;     // the sink layer must be in global memory
+    *sink_value = last[(size_t)R * ks * ks];   // cell (r=R,0,0) of the last level (:730, :775)
     TraceView v;
     v.L = L; v.R = R; v.level_off = p.level_off.data(); v.in_off = p.in_off.data(); v.in_edge = p.in_edge.data();
     v.lvlW = p.lvlW.data(); v.msrc_off = p.msrc_off.data(); v.mdst_off = p.mdst_off.data();
@@ -61,19 +96,29 @@ static int run(const DipPlan& p, int32_t* sink_value, int32_t* sink_s_het, int32
     return 0;
 }
 
+// shape: [grid, cells_per_cta, tile_cells, stage_bytes] (0 = kernel default)
 extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
                               const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off,
                               const int32_t* col_val, const uint8_t* colour_is_hom, int32_t n_colours, int32_t R,
                               int32_t* sink_value, int32_t* sink_s_het, int32_t* p1_edges, int32_t* n_p1,
                               int32_t* p2_edges, int32_t* n_p2, uint64_t* level_checksum, uint64_t* level_live,
-                              int32_t force_pred32) {
+                              int32_t force_pred32, const int32_t* shape, int64_t* mode_counts) {
     DipGraphView g;
     g.n_levels = n_levels; g.level_off = level_off; g.adj_off = adj_off; g.adj_dst = adj_dst; g.adj_w = adj_w;
     g.col_off = col_off; g.col_val = col_val; g.colour_is_hom = colour_is_hom; g.n_colours = n_colours; g.R = R;
     DipPlan p;
     if (!build_dip_plan(g, p)) return -1;
-    plan_participants(p, 148, 2048);
+    SweepShape sh;
+    sh.grid = 148; sh.cells_per_cta = 2048; sh.tile_cells = 16384; sh.stage_bytes = 16384;
+    if (shape) {
+        if (shape[0] > 0) sh.grid = shape[0];
+        if (shape[1] > 0) sh.cells_per_cta = shape[1];
+        if (shape[2] > 0) sh.tile_cells = shape[2];
+        if (shape[3] > 0) sh.stage_bytes = shape[3];
+    }
+    plan_sweep(p, sh);
+    if (mode_counts) { mode_counts[0] = p.n_fast; mode_counts[1] = p.n_staged; mode_counts[2] = p.n_global; }
     if (p.max_indeg <= 255 && !force_pred32)
-        return run<uint16_t>(p, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
-    return run<uint32_t>(p, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
+        return run<uint16_t>(p, sh, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
+    return run<uint32_t>(p, sh, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
 }

@@ -117,3 +117,31 @@ def test_lane_panel_model(oracle_mod, dp_emu):
     g = synth.lane_panel_graph(7, n_lanes=6, n_blocks=5, rec_per_block=2, p_colour=0.3, n_colours=64)
     for R in (0, 3):
         assert_dip_equal(oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R))
+
+
+@pytest.mark.parametrize("shape", [(148, 2048, 16384, 16384), (8, 64, 256, 512), (4, 32, 64, 96), (3, 16, 100000, 64)])
+def test_all_sweep_modes_agree(shape, oracle_mod, dp_emu):
+    """FAST (shared-memory layers), STAGED (records through shared memory, layers in HBM) and GLOBAL
+    (metadata in place) transitions, and every hand-over between them, give the same layers."""
+    seen = dict(fast=0, staged=0, global_=0)
+    for seed in range(12):
+        rng = np.random.default_rng(77 + seed)
+        g = synth.random_level_graph(500 + seed, n_levels=int(rng.integers(3, 30)), max_width=int(rng.integers(2, 12)),
+                                     n_colours=int(rng.integers(0, 150)), p_colour=0.5)
+        R = int(rng.integers(0, 6))
+        o = dp_emu.dp_diploid(g, R, shape=shape)
+        assert_dip_equal(oracle_dip(oracle_mod, g, R), o)
+        for k in seen:
+            seen[k] += o["modes"][k]
+    if shape == (8, 64, 256, 512):
+        assert seen["fast"] > 0 and seen["staged"] > 0
+    if shape == (4, 32, 64, 96):
+        assert seen["global_"] > 0
+
+
+def test_mhc_mode_mix(dp_emu):
+    g, _ = LevelGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_dipin.npz"))
+    o = dp_emu.dp_diploid(g, 0)
+    m = o["modes"]
+    assert m["fast"] + m["staged"] + m["global_"] == g.n_levels - 1
+    assert m["fast"] > 0.9 * g.n_levels        # the bundled panel is almost entirely shared-memory resident
