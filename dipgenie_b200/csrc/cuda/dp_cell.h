@@ -129,6 +129,53 @@ DG_HD uint64_t relax_cell(const TransitionT<OffT>& t, Load load, int r2, int i2,
     return best;
 }
 
+// Gather for one destination pair (i',j') and RC consecutive layers r2 = r0 .. r0+RC-1 at once
+// ("pair-major" form used by the kernels).  The in-edge decode, the candidate's flat source offset, its
+// tie-break bits and its colour delta do not depend on r2, so they are computed once per candidate and
+// reused for all RC layers; the RC source loads of a candidate are independent (ILP).  For every layer
+// the winner is the same lexicographic max as relax_cell().  best[rr] == 0 means layer r0+rr is dead
+// (or beyond R).  code[rr] = e1 << 16 | e2.
+template <int RC, bool HAS_MASK, class OffT, class Load>
+DG_HD void relax_pair(const TransitionT<OffT>& t, Load load, int R, int r0, int i2, int j2,
+                      uint64_t (&best)[RC], uint32_t (&code)[RC]) {
+    const int32_t a0 = (int32_t)t.in_off[i2], a1 = (int32_t)t.in_off[i2 + 1];
+    const int32_t b0 = (int32_t)t.in_off[j2], b1 = (int32_t)t.in_off[j2 + 1];
+    const int64_t kk = (int64_t)t.k * t.k;
+#pragma unroll
+    for (int rr = 0; rr < RC; ++rr) { best[rr] = 0; code[rr] = 0xFFFFFFFFu; }
+    for (int32_t e1 = a0; e1 < a1; ++e1) {
+        const uint32_t x = t.in_edge[e1];
+        const int i = (int)(x & 0xFFFFu), wu = (int)(x >> 16);
+        for (int32_t e2 = b0; e2 < b1; ++e2) {
+            const uint32_t y = t.in_edge[e2];
+            const int j = (int)(y & 0xFFFFu), w = wu + (int)(y >> 16);
+            const int64_t base = (int64_t)i * t.k + j;
+            const uint64_t low = ((uint64_t)(0xFFFFu - (uint32_t)i) << 16) | (uint64_t)(0xFFFFu - (uint32_t)j);
+            const int d = HAS_MASK ? pair_delta(t, i, j, i2, j2) : 0;
+            const uint32_t cd = ((uint32_t)(e1 - a0) << 16) | (uint32_t)(e2 - b0);
+#pragma unroll
+            for (int rr = 0; rr < RC; ++rr) {
+                const int r = r0 + rr - w;
+                if (r >= 0 && r0 + rr <= R) {
+                    const int32_t s = load((int64_t)r * kk + base);
+                    if (s != NEG_INF) {
+                        const uint64_t key = ((uint64_t)(uint32_t)(s + d) << 32) | low;
+                        if (key > best[rr]) { best[rr] = key; code[rr] = cd; }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Layers handled per work item: as many as possible (amortises the decode) while still giving every
+// one of `nthreads` threads an item.
+DG_HD int choose_rc(uint64_t npairs, int R, uint64_t nthreads) {
+    int rc = 8;
+    while (rc > 1 && npairs * (uint64_t)((R + rc) / rc) < nthreads) rc >>= 1;
+    return rc;
+}
+
 // Same fold as oracle/ref_hook.h::dg_ref_level_done, for one live cell; the per-level checksum is the
 // wrapping sum of these plus the FNV offset basis.
 DG_HD uint64_t cell_fold(uint64_t flat, int32_t value, int pred_i, int pred_j) {

@@ -24,7 +24,7 @@
 namespace dg {
 
 // ---- kernel geometry -------------------------------------------------------------------------
-constexpr int DIP_CT = 512;                    // compute threads per CTA (16 warps)
+constexpr int DIP_CT = 480;                    // compute threads per CTA (15 warps; 16 warps total -> 128 regs/thread)
 constexpr int DIP_THREADS = DIP_CT + 32;       // + one producer warp (record prefetch via bulk async copies)
 constexpr int DIP_CELLS_PER_CTA = DIP_CT * 4;
 constexpr int DIP_STAGES = 4;                  // record ring depth
@@ -68,7 +68,9 @@ struct SweepArgs {
     unsigned int* counter;
     unsigned long long* level_sum;    // [L] (CHECK only)
     unsigned long long* level_live;   // [L]
+    unsigned long long* prof;         // [32] phase cycle counters of CTA 0 / thread 0 (nullable)
     int32_t l_begin, l_end, R;
+    int32_t pred32, check;
 };
 
 // ---- PTX helpers -----------------------------------------------------------------------------
@@ -79,6 +81,16 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 }
 __device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Spin until the monotone arrival counter reaches `target`.  CTAs that are many arrivals away back off,
+// so that the counter's L2 slice serves the arrivals of the CTAs that are actually working.
+__device__ __forceinline__ void wait_counter(const unsigned int* counter, unsigned int target) {
+    for (;;) {
+        const unsigned int v = ld_acquire_u32(counter);
+        if (v >= target) break;
+        const unsigned int diff = target - v;
+        __nanosleep(diff > 64u ? 2000u : (diff > 8u ? 200u : 20u));
+    }
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -106,40 +118,75 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(DIP_CT) : "memory"); }
 
 // ---- the cell loop ---------------------------------------------------------------------------
-template <class OffT, class PredT, bool CHECK, bool SRC_SMEM, bool DST_SMEM>
-__device__ __forceinline__ void sweep_cells(const TransitionT<OffT>& t, const int32_t* __restrict__ src,
-                                            int32_t* __restrict__ dst, PredT* __restrict__ pl, int R, uint64_t first,
+struct CellIO {
+    const int32_t* src;        // source layer (shared or global)
+    int32_t* dst;              // destination layer (shared or global)
+    uint8_t* pl;               // predecessor codes of the destination level
+    bool src_smem, dst_smem, pred32, check;
+};
+
+// Work item = (destination pair (i',j'), chunk of RC layers); pairs vary fastest so that the stores of a
+// warp are contiguous in every layer.  SMEM: both layers are shared-memory tiles (the common case inside
+// a narrow stretch) and plain LDS/STS are used; otherwise placement is a run-time flag and HBM layers
+// are read/written with L2-only (.cg) accesses, since other SMs produce and consume them.
+template <class OffT, int RC, bool HAS_MASK, bool SMEM>
+__device__ __forceinline__ void sweep_pairs(const TransitionT<OffT>& t, const CellIO& io, int R, uint64_t first,
                                             uint64_t stride, unsigned long long& hsum, unsigned long long& hlive) {
-    constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
-    auto load = [src](int64_t idx) { return SRC_SMEM ? src[idx] : __ldcg(src + idx); };
-    const uint32_t k2 = (uint32_t)t.k2, kk = k2 * k2;
-    const uint64_t ncell = (uint64_t)(R + 1) * kk;
-    if (ncell <= 0x7FFFFFFFull) {
-        const uint32_t n32 = (uint32_t)ncell, st32 = (uint32_t)stride;
-        for (uint32_t c = (uint32_t)first; c < n32; c += st32) {
-            const uint32_t r2 = c / kk, rem = c - r2 * kk;
-            const uint32_t i2 = rem / k2, j2 = rem - i2 * k2;
-            uint32_t code;
-            const uint64_t key = relax_cell(t, load, (int)r2, (int)i2, (int)j2, code);
-            if (DST_SMEM) dst[c] = key_value(key); else __stcg(dst + c, key_value(key));
-            pl[c] = key ? (PredT)(((code >> 16) << SH) | (code & 0xFFFFu)) : (PredT) ~(PredT)0;
-            if (CHECK && key) {
-                ++hlive;
-                hsum += cell_fold(c, key_value(key), 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+    const uint32_t k2 = (uint32_t)t.k2, npairs = k2 * k2;
+    const uint32_t nchunk = (uint32_t)(R + RC) / RC;
+    const uint64_t nitems = (uint64_t)npairs * nchunk;
+    const int32_t* __restrict__ src = io.src;
+    const bool ssm = io.src_smem;
+    auto load = [src, ssm](int64_t idx) -> int32_t {
+        if (SMEM) return src[idx];
+        return ssm ? src[idx] : __ldcg(src + idx);
+    };
+    for (uint64_t x = first; x < nitems; x += stride) {
+        uint32_t chunk, pair;
+        if (nitems <= 0xFFFFFFFFull) { chunk = (uint32_t)x / npairs; pair = (uint32_t)x - chunk * npairs; }
+        else { chunk = (uint32_t)(x / npairs); pair = (uint32_t)(x - (uint64_t)chunk * npairs); }
+        const uint32_t i2 = pair / k2, j2 = pair - i2 * k2;
+        const int r0 = (int)chunk * RC;
+        uint64_t best[RC];
+        uint32_t code[RC];
+        relax_pair<RC, HAS_MASK>(t, load, R, r0, (int)i2, (int)j2, best, code);
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) {
+            const int r2 = r0 + rr;
+            if (r2 <= R) {
+                const uint64_t c = (uint64_t)r2 * npairs + pair;
+                const uint64_t key = best[rr];
+                const int32_t v = key_value(key);
+                if (SMEM || io.dst_smem) io.dst[c] = v; else __stcg(io.dst + c, v);
+                if (io.pred32) reinterpret_cast<uint32_t*>(io.pl)[c] = key ? code[rr] : 0xFFFFFFFFu;
+                else reinterpret_cast<uint16_t*>(io.pl)[c] = key ? (uint16_t)(((code[rr] >> 16) << 8) | (code[rr] & 0xFFu)) : (uint16_t)0xFFFFu;
+                if (io.check && key) {
+                    ++hlive;
+                    hsum += cell_fold(c, v, 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+                }
             }
         }
+    }
+}
+
+template <class OffT, bool SMEM>
+__device__ __forceinline__ void sweep_dispatch(const TransitionT<OffT>& t, const CellIO& io, int R, uint64_t first,
+                                               uint64_t stride, uint64_t nthreads, unsigned long long& hsum,
+                                               unsigned long long& hlive) {
+    const int rc = choose_rc((uint64_t)t.k2 * t.k2, R, nthreads);
+    if (t.W > 0) {
+        switch (rc) {
+            case 8: sweep_pairs<OffT, 8, true, SMEM>(t, io, R, first, stride, hsum, hlive); break;
+            case 4: sweep_pairs<OffT, 4, true, SMEM>(t, io, R, first, stride, hsum, hlive); break;
+            case 2: sweep_pairs<OffT, 2, true, SMEM>(t, io, R, first, stride, hsum, hlive); break;
+            default: sweep_pairs<OffT, 1, true, SMEM>(t, io, R, first, stride, hsum, hlive); break;
+        }
     } else {
-        for (uint64_t c = first; c < ncell; c += stride) {
-            const uint64_t r2 = c / kk, rem = c - r2 * kk;
-            const uint32_t i2 = (uint32_t)(rem / k2), j2 = (uint32_t)(rem - (uint64_t)i2 * k2);
-            uint32_t code;
-            const uint64_t key = relax_cell(t, load, (int)r2, (int)i2, (int)j2, code);
-            if (DST_SMEM) dst[c] = key_value(key); else __stcg(dst + c, key_value(key));
-            pl[c] = key ? (PredT)(((code >> 16) << SH) | (code & 0xFFFFu)) : (PredT) ~(PredT)0;
-            if (CHECK && key) {
-                ++hlive;
-                hsum += cell_fold(c, key_value(key), 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
-            }
+        switch (rc) {
+            case 8: sweep_pairs<OffT, 8, false, SMEM>(t, io, R, first, stride, hsum, hlive); break;
+            case 4: sweep_pairs<OffT, 4, false, SMEM>(t, io, R, first, stride, hsum, hlive); break;
+            case 2: sweep_pairs<OffT, 2, false, SMEM>(t, io, R, first, stride, hsum, hlive); break;
+            default: sweep_pairs<OffT, 1, false, SMEM>(t, io, R, first, stride, hsum, hlive); break;
         }
     }
 }
@@ -153,7 +200,6 @@ struct Producer {
     bool ended;
 };
 
-template <class PredT, bool CHECK>
 __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const stage_base = smem;
@@ -165,7 +211,8 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepAr
     const int cta = blockIdx.x, tid = threadIdx.x;
     const bool is_compute = tid < DIP_CT;
     const bool is_producer = tid == DIP_CT;          // lane 0 of the extra warp
-    PredT* __restrict__ pred = reinterpret_cast<PredT*>(a.pred);
+    uint8_t* const pred = reinterpret_cast<uint8_t*>(a.pred);
+    const int pshift = a.pred32 ? 2 : 1;
 
     if (tid == 0) {
         for (int s = 0; s < DIP_STAGES; ++s) mbar_init(smem_u32(mbar + s), 1);
@@ -204,8 +251,14 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepAr
     if (is_producer) produce(0, 0);
 
     int t = 0, rc = 0;                               // iteration index, records consumed so far
+    const bool profiling = a.prof != nullptr && cta == 0 && tid == 0;
+    unsigned long long pc[24];
+    if (profiling) for (int x = 0; x < 24; ++x) pc[x] = 0;
+    long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0;
     for (;;) {
+        if (profiling) tk0 = clock64();
         __syncthreads();                             // iteration t-1 complete: its layer is whole, its stage is free
+        if (profiling) tk1 = clock64();
         const int2 e = queue[t % DIP_QUEUE];
         const int l = e.x, stage = e.y;
         if (l < 0) break;
@@ -215,56 +268,74 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepAr
             if (stage >= 0) {
                 const uint8_t* rec = stage_base + (size_t)stage * DIP_STAGE_BYTES;
                 mbar_wait(smem_u32(mbar + stage), (uint32_t)((rc / DIP_STAGES) & 1));
+                if (profiling) tk2 = clock64();
                 RecHeader h;
                 TransitionT<uint16_t> tr;
                 record_view(rec, h, tr);
                 if (h.flags & REC_WAIT) {
-                    if (tid == 0) while (ld_acquire_u32(a.counter) < h.wait_target) __nanosleep(20);
+                    if (tid == 0) wait_counter(a.counter, h.wait_target);
                     bar_compute();
                 }
+                if (profiling) tk3 = clock64();
                 const bool ssm = (h.flags & REC_SRC_SMEM) != 0, dsm = (h.flags & REC_DST_SMEM) != 0;
-                const int32_t* src = ssm ? ((l & 1) ? tileS1 : tileS0) : ((l & 1) ? a.tile1 : a.tile0);
-                int32_t* dst = dsm ? ((l & 1) ? tileS0 : tileS1) : ((l & 1) ? a.tile0 : a.tile1);
-                PredT* pl = pred + h.pred_off2;
+                CellIO io;
+                io.src = ssm ? ((l & 1) ? tileS1 : tileS0) : ((l & 1) ? a.tile1 : a.tile0);
+                io.dst = dsm ? ((l & 1) ? tileS0 : tileS1) : ((l & 1) ? a.tile0 : a.tile1);
+                io.pl = pred + ((size_t)h.pred_off2 << pshift);
+                io.src_smem = ssm; io.dst_smem = dsm; io.pred32 = a.pred32 != 0; io.check = a.check != 0;
                 const uint64_t first = (uint64_t)cta * DIP_CT + tid, stride = (uint64_t)h.P * DIP_CT;
-                if (ssm) {
-                    if (dsm) sweep_cells<uint16_t, PredT, CHECK, true, true>(tr, src, dst, pl, a.R, first, stride, hsum, hlive);
-                    else sweep_cells<uint16_t, PredT, CHECK, true, false>(tr, src, dst, pl, a.R, first, stride, hsum, hlive);
+                if (ssm && dsm) {
+                    CellIO ios = io;
+                    ios.src = (l & 1) ? tileS1 : tileS0;
+                    ios.dst = (l & 1) ? tileS0 : tileS1;
+                    sweep_dispatch<uint16_t, true>(tr, ios, a.R, first, stride, stride, hsum, hlive);
                 } else {
-                    if (dsm) sweep_cells<uint16_t, PredT, CHECK, false, true>(tr, src, dst, pl, a.R, first, stride, hsum, hlive);
-                    else sweep_cells<uint16_t, PredT, CHECK, false, false>(tr, src, dst, pl, a.R, first, stride, hsum, hlive);
+                    sweep_dispatch<uint16_t, false>(tr, io, a.R, first, stride, stride, hsum, hlive);
                 }
+                if (profiling) tk4 = clock64();
                 if (h.flags & REC_ARRIVE) {
                     bar_compute();
                     if (tid == 0) red_release_add_u32(a.counter, 1u);
                 }
+                if (profiling) {
+                    tk5 = clock64();
+                    const int m = (ssm || dsm) ? 0 : 1;       // 0: shared-memory layers, 1: staged record + HBM layers
+                    pc[m * 6 + 0] += 1; pc[m * 6 + 1] += tk1 - tk0; pc[m * 6 + 2] += tk2 - tk1;
+                    pc[m * 6 + 3] += tk3 - tk2; pc[m * 6 + 4] += tk4 - tk3; pc[m * 6 + 5] += tk5 - tk4;
+                }
             } else {
+                if (profiling) tk2 = clock64();
                 const LevelCtl* __restrict__ cg = a.ctl + l;
                 const uint32_t flags = __ldg(&cg->flags);
                 if (flags & CTL_WAIT) {
-                    if (tid == 0) {
-                        const unsigned int target = __ldg(&cg->wait_target);
-                        while (ld_acquire_u32(a.counter) < target) __nanosleep(20);
-                    }
+                    if (tid == 0) wait_counter(a.counter, __ldg(&cg->wait_target));
                     bar_compute();
                 }
+                if (profiling) tk3 = clock64();
                 Transition tr;
                 tr.k = __ldg(&cg->k); tr.k2 = __ldg(&cg->k2); tr.W = __ldg(&cg->W);
                 tr.in_off = a.in_off + __ldg(&cg->voff2);
                 tr.in_edge = a.in_edge;
                 tr.msrc = a.masks + __ldg(&cg->msrc_off);
                 tr.mdst = a.masks + __ldg(&cg->mdst_off);
-                const int32_t* src = (l & 1) ? a.tile1 : a.tile0;
-                int32_t* dst = (l & 1) ? a.tile0 : a.tile1;
-                PredT* pl = pred + __ldg(&cg->pred_off2);
+                CellIO io;
+                io.src = (l & 1) ? a.tile1 : a.tile0;
+                io.dst = (l & 1) ? a.tile0 : a.tile1;
+                io.pl = pred + ((size_t)__ldg(&cg->pred_off2) << pshift);
+                io.src_smem = false; io.dst_smem = false; io.pred32 = a.pred32 != 0; io.check = a.check != 0;
                 const uint64_t first = (uint64_t)cta * DIP_CT + tid, stride = (uint64_t)__ldg(&cg->P) * DIP_CT;
-                sweep_cells<int32_t, PredT, CHECK, false, false>(tr, src, dst, pl, a.R, first, stride, hsum, hlive);
+                sweep_dispatch<int32_t, false>(tr, io, a.R, first, stride, stride, hsum, hlive);
+                if (profiling) tk4 = clock64();
                 if (flags & CTL_ARRIVE) {
                     bar_compute();
                     if (tid == 0) red_release_add_u32(a.counter, 1u);
                 }
+                if (profiling) {
+                    tk5 = clock64();
+                    pc[12] += 1; pc[13] += tk1 - tk0; pc[14] += tk2 - tk1; pc[15] += tk3 - tk2; pc[16] += tk4 - tk3; pc[17] += tk5 - tk4;
+                }
             }
-            if (CHECK) {
+            if (a.check) {
                 for (int o = 16; o > 0; o >>= 1) {
                     hsum += __shfl_down_sync(0xFFFFFFFFu, hsum, o);
                     hlive += __shfl_down_sync(0xFFFFFFFFu, hlive, o);
@@ -278,6 +349,7 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepAr
         if (stage >= 0) ++rc;
         ++t;
     }
+    if (profiling) for (int x = 0; x < 24; ++x) a.prof[x] = pc[x];
 }
 
 struct TraceOut {           // device-side result block
@@ -313,7 +385,8 @@ struct dg_dip {
     DevBuf<int32_t> tile0, tile1;
     DevBuf<uint8_t> pred;
     DevBuf<unsigned int> counter;
-    DevBuf<unsigned long long> level_sum, level_live;
+    DevBuf<unsigned long long> level_sum, level_live, prof;
+    bool want_prof = false;
     DevBuf<TraceOut> tout;
     DevBuf<int32_t> p1, p2;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -334,9 +407,7 @@ static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out) {
     d->pred_bytes = (p.max_indeg <= 255) ? 2 : 4;
 
     // grid: enough CTAs for the widest transition, at most one co-resident wave (cooperative launch)
-    const void* fn = d->pred_bytes == 2 ? (const void*)dip_sweep_kernel<uint16_t, false> : (const void*)dip_sweep_kernel<uint32_t, false>;
-    const void* fnc = d->pred_bytes == 2 ? (const void*)dip_sweep_kernel<uint16_t, true> : (const void*)dip_sweep_kernel<uint32_t, true>;
-    DG_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
+    const void* fnc = (const void*)dip_sweep_kernel;
     DG_CUDA(ctx, cudaFuncSetAttribute(fnc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
     int per_sm = 0;
     DG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fnc, DIP_THREADS, DIP_SMEM_BYTES));
@@ -400,6 +471,7 @@ static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out) {
     DG_CUDA(ctx, d->counter.alloc(1));
     DG_CUDA(ctx, d->level_sum.alloc((size_t)L));
     DG_CUDA(ctx, d->level_live.alloc((size_t)L));
+    DG_CUDA(ctx, d->prof.alloc(32));
     DG_CUDA(ctx, d->tout.alloc(1));
     DG_CUDA(ctx, d->p1.alloc((size_t)2 * (p.R + 2)));
     DG_CUDA(ctx, d->p2.alloc((size_t)2 * (p.R + 2)));
@@ -434,12 +506,14 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     a.ctl = d->ctl.p; a.in_off = d->in_off.p; a.in_edge = d->in_edge.p; a.masks = d->masks.p;
     a.tile0 = d->tile0.p; a.tile1 = d->tile1.p; a.pred = d->pred.p; a.counter = d->counter.p;
     a.level_sum = d->level_sum.p; a.level_live = d->level_live.p;
+    a.prof = d->want_prof ? d->prof.p : nullptr;
     a.l_begin = 0; a.l_end = p.L - 1; a.R = p.R;
+    a.pred32 = sizeof(PredT) == 4 ? 1 : 0; a.check = check ? 1 : 0;
     d->launches = 0;
     DG_CUDA(ctx, cudaEventRecord(d->ev[0], s));
     if (p.L > 1) {
         void* args[] = {(void*)&a};
-        const void* fn = check ? (const void*)dip_sweep_kernel<PredT, true> : (const void*)dip_sweep_kernel<PredT, false>;
+        const void* fn = (const void*)dip_sweep_kernel;
         DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, s));
         ++d->launches;
     }
@@ -474,6 +548,7 @@ int dg_dip_run(dg_ctx* ctx, dg_dip* d, uint32_t flags) {
     if (!ctx || !d) return DG_ERR_ARG;
     DG_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool check = (flags & 1u) != 0;
+    d->want_prof = (flags & 2u) != 0;
     return d->pred_bytes == 2 ? dip_run_impl<uint16_t>(ctx, d, check) : dip_run_impl<uint32_t>(ctx, d, check);
 }
 
@@ -520,6 +595,14 @@ int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out) {
     out->pred_bytes = d->pred_bytes; out->launches = d->launches;
     out->sweep_ms = d->sweep_ms; out->traceback_ms = d->trace_ms;
     (void)ctx;
+    return DG_OK;
+}
+
+int dg_dip_profile(dg_ctx* ctx, dg_dip* d, uint64_t* out24) {
+    if (!ctx || !d || !d->ran || !d->want_prof) return fail(ctx, DG_ERR_ARG, "dg_dip_profile: run with flags bit1 first");
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DG_CUDA(ctx, cudaMemcpy(out24, d->prof.p, 24 * 8, cudaMemcpyDeviceToHost));
     return DG_OK;
 }
 

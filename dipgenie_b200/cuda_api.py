@@ -177,8 +177,15 @@ class DipProblem:
         ctx.check(rc, "dg_dip_create")
         self.h = h
 
-    def run(self, checksums: bool = False):
-        self.ctx.check(self.ctx.lib.dg_dip_run(C.c_void_p(self.ctx.h), self.h, C.c_uint32(1 if checksums else 0)), "dg_dip_run")
+    def run(self, checksums: bool = False, profile: bool = False):
+        flags = (1 if checksums else 0) | (2 if profile else 0)
+        self.ctx.check(self.ctx.lib.dg_dip_run(C.c_void_p(self.ctx.h), self.h, C.c_uint32(flags)), "dg_dip_run")
+
+    def profile(self) -> dict:
+        out = np.zeros(24, np.uint64)
+        self.ctx.check(self.ctx.lib.dg_dip_profile(C.c_void_p(self.ctx.h), self.h, _ptr(out)), "dg_dip_profile")
+        names = ["transitions", "block_barrier", "record_wait", "grid_wait", "cell_loop", "arrive"]
+        return {m: {n: int(out[i * 6 + j]) for j, n in enumerate(names)} for i, m in enumerate(["smem_layers", "staged", "in_place"])}
 
     def result(self):
         R = self.R

@@ -67,7 +67,8 @@ int dg_dip_create(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off,
                   const int64_t* adj_off, const int32_t* adj_dst, const uint8_t* adj_w,
                   const int64_t* col_off, const int32_t* col_val,
                   const uint8_t* colour_is_hom, int32_t n_colours, int32_t R, dg_dip** out);
-/* flags: bit0 = also fold every DP layer into per-level checksums (slower; tests only). */
+/* flags: bit0 = also fold every DP layer into per-level checksums (slower; tests only);
+ *        bit1 = record phase cycle counters of CTA 0 (read back with dg_dip_profile; diagnostics). */
 int dg_dip_run(dg_ctx* ctx, dg_dip* d, uint32_t flags);
 int dg_dip_result(dg_ctx* ctx, dg_dip* d, int32_t* sink_value, int32_t* sink_s_het,
                   int32_t* p1_edges, int32_t* n_p1, int32_t* p2_edges, int32_t* n_p2);
@@ -85,6 +86,9 @@ typedef struct {
     float sweep_ms, traceback_ms;
 } dg_dip_stats_t;
 int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out);
+/* out24: for each of {shared-memory layers, staged record + HBM layers, in-place metadata} six counters
+ * {transitions, block-barrier, record-wait, grid-wait, cell-loop, arrive} in SM clock cycles of CTA 0. */
+int dg_dip_profile(dg_ctx* ctx, dg_dip* d, uint64_t* out24);
 void dg_dip_destroy(dg_ctx* ctx, dg_dip* d);
 
 #ifdef __cplusplus

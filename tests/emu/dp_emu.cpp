@@ -14,19 +14,46 @@
 
 using namespace dg;
 
-template <class PredT, class OffT, class Load, class Store>
-static void cells(const TransitionT<OffT>& t, int R, Load load, Store store, PredT* pl, uint64_t& h, uint64_t& live) {
+template <int RC, bool HAS_MASK, class PredT, class OffT, class Load, class Store>
+static void items(const TransitionT<OffT>& t, int R, Load load, Store store, PredT* pl, uint64_t& h, uint64_t& live) {
     constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
-    const size_t ncell = (size_t)(R + 1) * t.k2 * t.k2;
-    for (size_t c = 0; c < ncell; ++c) {
-        const int j2 = (int)(c % t.k2), i2 = (int)((c / t.k2) % t.k2), r2 = (int)(c / ((size_t)t.k2 * t.k2));
-        uint32_t code;
-        const uint64_t key = relax_cell(t, load, r2, i2, j2, code);
-        store(c, key_value(key));
-        pl[c] = key ? (PredT)(((code >> 16) << SH) | (code & 0xFFFFu)) : (PredT) ~(PredT)0;
-        if (key) {
-            ++live;
-            h += cell_fold(c, key_value(key), 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+    const uint32_t k2 = (uint32_t)t.k2, npairs = k2 * k2, nchunk = (uint32_t)(R + RC) / RC;
+    for (uint64_t x = 0; x < (uint64_t)npairs * nchunk; ++x) {
+        const uint32_t chunk = (uint32_t)(x / npairs), pair = (uint32_t)(x - (uint64_t)chunk * npairs);
+        const uint32_t i2 = pair / k2, j2 = pair - i2 * k2;
+        uint64_t best[RC]; uint32_t code[RC];
+        relax_pair<RC, HAS_MASK>(t, load, R, (int)chunk * RC, (int)i2, (int)j2, best, code);
+        for (int rr = 0; rr < RC; ++rr) {
+            const int r2 = (int)chunk * RC + rr;
+            if (r2 > R) continue;
+            const uint64_t c = (uint64_t)r2 * npairs + pair, key = best[rr];
+            store(c, key_value(key));
+            pl[c] = key ? (PredT)(((code[rr] >> 16) << SH) | (code[rr] & 0xFFFFu)) : (PredT) ~(PredT)0;
+            if (key) {
+                ++live;
+                h += cell_fold(c, key_value(key), 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+            }
+        }
+    }
+}
+
+// same dispatch as sweep_dispatch() in dp_diploid.cu
+template <class PredT, class OffT, class Load, class Store>
+static void cells(const TransitionT<OffT>& t, int R, uint64_t nthreads, Load load, Store store, PredT* pl, uint64_t& h, uint64_t& live) {
+    const int rc = choose_rc((uint64_t)t.k2 * t.k2, R, nthreads);
+    if (t.W > 0) {
+        switch (rc) {
+            case 8: items<8, true>(t, R, load, store, pl, h, live); break;
+            case 4: items<4, true>(t, R, load, store, pl, h, live); break;
+            case 2: items<2, true>(t, R, load, store, pl, h, live); break;
+            default: items<1, true>(t, R, load, store, pl, h, live); break;
+        }
+    } else {
+        switch (rc) {
+            case 8: items<8, false>(t, R, load, store, pl, h, live); break;
+            case 4: items<4, false>(t, R, load, store, pl, h, live); break;
+            case 2: items<2, false>(t, R, load, store, pl, h, live); break;
+            default: items<1, false>(t, R, load, store, pl, h, live); break;
         }
     }
 }
@@ -60,7 +87,7 @@ static int run(const DipPlan& p, const SweepShape& sh, int32_t* sink_value, int3
             if ((ssm && (size_t)(R + 1) * t.k * t.k > (size_t)sh.tile_cells) ||
                 (dsm && (size_t)(R + 1) * t.k2 * t.k2 > (size_t)sh.tile_cells)) return -13;
             if (hd.pred_off2 != p.pred_off[l + 1]) return -14;
-            cells<PredT>(t, R, [src](int64_t i) { return src[i]; }, [dst](size_t c, int32_t v) { dst[c] = v; }, pl, h, live);
+            cells<PredT>(t, R, (uint64_t)hd.P * sh.cells_per_cta / 4, [src](int64_t i) { return src[i]; }, [dst](size_t c, int32_t v) { dst[c] = v; }, pl, h, live);
             if (hd.flags & REC_ARRIVE) counter += hd.P;
         } else {
             Transition t;
@@ -74,7 +101,7 @@ static int run(const DipPlan& p, const SweepShape& sh, int32_t* sink_value, int3
             if ((p.flags[l] & REC_WAIT) && counter < p.bar_target[l - 1]) return -11;
             const int32_t* src = (l & 1) ? g1.data() : g0.data();
             int32_t* dst = (l & 1) ? g0.data() : g1.data();
-            cells<PredT>(t, R, [src](int64_t i) { return src[i]; }, [dst](size_t c, int32_t v) { dst[c] = v; }, pl, h, live);
+            cells<PredT>(t, R, (uint64_t)p.P[l] * sh.cells_per_cta / 4, [src](int64_t i) { return src[i]; }, [dst](size_t c, int32_t v) { dst[c] = v; }, pl, h, live);
             if (p.flags[l] & REC_ARRIVE) counter += (uint32_t)p.P[l];
         }
         if (counter != p.bar_target[l]) return -15;

@@ -84,7 +84,7 @@ def test_cuda_edge_cases(ctx, oracle_mod):
 
 def test_cuda_wide_levels_use_many_ctas(ctx, oracle_mod):
     """Widths large enough that transitions are spread over the whole grid and closed by the counter barrier."""
-    g = synth.lane_panel_graph(11, n_lanes=40, n_blocks=12, rec_per_block=3, p_colour=0.2, n_colours=500)
+    g = synth.lane_panel_graph(11, n_lanes=72, n_blocks=8, rec_per_block=3, p_colour=0.2, n_colours=500)
     o = cuda_dip(ctx, g, 5)
     assert o["stats"]["grid_ctas"] > 1
     assert_dip_equal(oracle_dip(oracle_mod, g, 5), o)
