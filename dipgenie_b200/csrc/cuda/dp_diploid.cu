@@ -13,6 +13,7 @@
 //     the precomputed prefix sum of arrivals);
 //   * a single-thread traceback kernel turns predecessor codes into the two recombination-edge lists.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -82,15 +83,19 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
 __device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Spin until the monotone arrival counter reaches `target`.  CTAs that are many arrivals away back off,
-// so that the counter's L2 slice serves the arrivals of the CTAs that are actually working.
+// Spin until the monotone arrival counter reaches `target`.  Polls are relaxed loads (no L1 invalidate
+// per poll) with exponential back-off, so that idle CTAs — most of the grid during a narrow stretch —
+// do not hammer the counter's L2 slice; one acquire fence orders the layer reads after the last poll.
 __device__ __forceinline__ void wait_counter(const unsigned int* counter, unsigned int target) {
+    unsigned int ns = 32;
     for (;;) {
-        const unsigned int v = ld_acquire_u32(counter);
+        unsigned int v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
         if (v >= target) break;
-        const unsigned int diff = target - v;
-        __nanosleep(diff > 64u ? 2000u : (diff > 8u ? 200u : 20u));
+        __nanosleep(ns);
+        if (ns < 2048u) ns <<= 1;
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -412,7 +417,8 @@ static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out) {
     int per_sm = 0;
     DG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fnc, DIP_THREADS, DIP_SMEM_BYTES));
     if (per_sm < 1) return fail(ctx, DG_ERR_CUDA, "dg_dip_create: sweep kernel cannot be resident");
-    const int max_grid = ctx->sm_count * per_sm;
+    int max_grid = ctx->sm_count * per_sm;
+    if (const char* e = getenv("DG_DIP_MAX_GRID")) max_grid = std::max(1, std::min(max_grid, atoi(e)));   // diagnostics
     const uint64_t widest = (uint64_t)(p.R + 1) * (uint64_t)p.kmax * (uint64_t)p.kmax;
     const uint64_t want = (widest + DIP_CELLS_PER_CTA - 1) / DIP_CELLS_PER_CTA;
     SweepShape shape;

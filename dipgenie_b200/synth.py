@@ -132,3 +132,23 @@ def lane_panel_graph(seed: int, n_lanes: int, n_blocks: int, rec_per_block: int 
         col_val = col_val[o]
     hom = (rng.random(n_colours) < hom_frac).astype(np.uint8)
     return LevelGraph(level_off, adj_off, dst.astype(np.int32), w.astype(np.uint8), col_off, col_val, hom)
+
+
+def truncate_levels(g: LevelGraph, n_levels: int) -> LevelGraph:
+    """First `n_levels` levels of g with a single sink appended (every vertex of the last kept level gets one
+    weight-0 edge to it) — a bounded sample of the same workload, still a legal levelized graph."""
+    L = g.n_levels
+    if n_levels >= L:
+        return g
+    V = int(g.level_off[n_levels])
+    lo = int(g.level_off[n_levels - 1])
+    outdeg = np.diff(g.adj_off)[:V].copy()
+    e_keep = int(g.adj_off[lo])
+    adj_dst = np.concatenate([g.adj_dst[:e_keep], np.full(V - lo, V, np.int32)])
+    adj_w = np.concatenate([g.adj_w[:e_keep], np.zeros(V - lo, np.uint8)])
+    outdeg[lo:V] = 1
+    adj_off = np.concatenate([[0], np.cumsum(np.concatenate([outdeg, [0]]))]).astype(np.int64)
+    col_off = np.concatenate([g.col_off[: V + 1], [g.col_off[V]]]).astype(np.int64)
+    col_val = g.col_val[: int(g.col_off[V])]
+    level_off = np.concatenate([g.level_off[: n_levels + 1], [V + 1]]).astype(np.int32)
+    return LevelGraph(level_off, adj_off, adj_dst, adj_w, col_off, col_val, g.colour_is_hom)
