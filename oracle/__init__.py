@@ -82,3 +82,82 @@ def dp_diploid(level_off, adj_off, adj_dst, adj_w, col_off, col_val, colour_is_h
         out["checksum"] = cs
         out["live"] = lv
     return out
+
+
+def _take(ptr, n, dtype):
+    """Copy n items from a malloc'ed C array into numpy and free it."""
+    if n == 0:
+        lib().dgo_free(ptr)
+        return np.zeros(0, dtype)
+    a = np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+    lib().dgo_free(ptr)
+    return a
+
+
+def hash64(kmer: bytes) -> int:
+    f = lib().dgo_hash64
+    f.restype = C.c_uint64
+    buf = (C.c_uint8 * len(kmer)).from_buffer_copy(kmer)
+    return int(f(buf, C.c_int(len(kmer))))
+
+
+def sketch_reads(bases, read_off, k, w, per_read=False):
+    """Oracle for dg_sketch_reads: (spectrum sorted, read_count[, per-read off, val])."""
+    bases = _c(bases, np.uint8)
+    read_off = _c(read_off, np.uint64)
+    n = len(read_off) - 1
+    sp = _u64p()
+    rc = _u32p()
+    ns = C.c_uint64(0)
+    po = _u64p()
+    pv = _u64p()
+    L = lib()
+    L.dgo_free.argtypes = [C.c_void_p]
+    rcode = L.dgo_sketch_reads(_p(bases, _u8p), _p(read_off, _u64p), C.c_uint32(n), C.c_int(k), C.c_int(w),
+                               C.byref(sp), C.byref(rc), C.byref(ns), C.byref(po) if per_read else None,
+                               C.byref(pv) if per_read else None)
+    if rcode != 0:
+        raise RuntimeError(f"dgo_sketch_reads rc={rcode}")
+    spectrum = _take(sp, ns.value, np.uint64)
+    count = _take(rc, ns.value, np.uint32)
+    if not per_read:
+        return spectrum, count
+    off = _take(po, n + 1, np.uint64)
+    val = _take(pv, int(off[-1]), np.uint64)
+    return spectrum, count, off, val
+
+
+def index_walks(seg_bases, seg_off, walk_vtx, walk_off, top_order_map, k, w, spectrum, want_all=False):
+    """Oracle for dg_index_walks."""
+    seg_bases = _c(seg_bases, np.uint8)
+    seg_off = _c(seg_off, np.uint64)
+    walk_vtx = _c(walk_vtx, np.int32)
+    walk_off = _c(walk_off, np.uint64)
+    top_order_map = _c(top_order_map, np.int32)
+    spectrum = _c(spectrum, np.uint64)
+    nw = len(walk_off) - 1
+    nmin = np.zeros(nw, np.uint64)
+    ho = _u64p()
+    hs = _u32p()
+    vo = _u64p()
+    hv = _i32p()
+    ao = _u64p()
+    ah = _u64p()
+    L = lib()
+    L.dgo_free.argtypes = [C.c_void_p]
+    rcode = L.dgo_index_walks(_p(seg_bases, _u8p), _p(seg_off, _u64p), C.c_uint32(len(seg_off) - 1), _p(walk_vtx, _i32p),
+                              _p(walk_off, _u64p), C.c_uint32(nw), _p(top_order_map, _i32p), C.c_int(k), C.c_int(w),
+                              _p(spectrum, _u64p), C.c_uint64(len(spectrum)), _p(nmin, _u64p), C.byref(ho), C.byref(hs),
+                              C.byref(vo), C.byref(hv), C.byref(ao) if want_all else None, C.byref(ah) if want_all else None)
+    if rcode != 0:
+        raise RuntimeError(f"dgo_index_walks rc={rcode}")
+    hit_off = _take(ho, nw + 1, np.uint64)
+    nh = int(hit_off[-1])
+    hit_sid = _take(hs, nh, np.uint32)
+    hit_vtx_off = _take(vo, nh + 1, np.uint64)
+    hit_vtx = _take(hv, int(hit_vtx_off[-1]), np.int32)
+    out = dict(n_minimizers=nmin, hit_off=hit_off, hit_sid=hit_sid, hit_vtx_off=hit_vtx_off, hit_vtx=hit_vtx)
+    if want_all:
+        out["all_off"] = _take(ao, nw + 1, np.uint64)
+        out["all_hash"] = _take(ah, int(out["all_off"][-1]), np.uint64)
+    return out
