@@ -26,6 +26,14 @@ class DipStats(C.Structure):
     ]
 
 
+class HapStats(C.Structure):
+    _fields_ = [
+        ("cell_updates", C.c_uint64), ("cells", C.c_uint64), ("algo_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
+        ("n_levels", C.c_int32), ("n_vertices", C.c_int32), ("max_width", C.c_int32), ("max_indegree", C.c_int32),
+        ("launches", C.c_int32), ("sweep_ms", C.c_float), ("traceback_ms", C.c_float),
+    ]
+
+
 class DipGenieCudaError(RuntimeError):
     pass
 
@@ -110,6 +118,47 @@ class LevelGraph:
         return g, z
 
 
+@dataclass
+class HapGraph:
+    """Flat Kahn-ordered ExpandedGraph — the input contract of dg_dp_haploid (see include/dipgenie_cuda.h)."""
+    adj_off: np.ndarray       # int64 [n+1]
+    adj_dst: np.ndarray       # int32 [E]
+    adj_w: np.ndarray         # uint8 [E]
+    col_off: np.ndarray       # int64 [n+1]
+    col_val: np.ndarray       # int32
+    n_colours: int = 0
+
+    def __post_init__(self):
+        self.adj_off = np.ascontiguousarray(self.adj_off, np.int64)
+        self.adj_dst = np.ascontiguousarray(self.adj_dst, np.int32)
+        self.adj_w = np.ascontiguousarray(self.adj_w, np.uint8)
+        self.col_off = np.ascontiguousarray(self.col_off, np.int64)
+        self.col_val = np.ascontiguousarray(self.col_val, np.int32)
+        if not self.n_colours:
+            self.n_colours = int(self.col_val.max(initial=-1)) + 1
+
+    @property
+    def n(self) -> int:
+        return len(self.adj_off) - 1
+
+    @property
+    def nbytes(self) -> int:
+        return sum(a.nbytes for a in (self.adj_off, self.adj_dst, self.adj_w, self.col_off, self.col_val))
+
+    @staticmethod
+    def from_dgd(d, prefix: str = "hap_in.") -> "HapGraph":
+        return HapGraph(d[prefix + "adj.off"], d[prefix + "adj.dst"], d[prefix + "adj.w"], d[prefix + "color.off"],
+                        d[prefix + "color.val"])
+
+    @staticmethod
+    def from_npz(path: str) -> "HapGraph":
+        z = np.load(path)
+        ne = int(z["n_edges"])
+        return HapGraph(np.concatenate([[0], np.cumsum(z["outdeg"].astype(np.int64))]),
+                        np.cumsum(z["adj_dst_delta"].astype(np.int64)).astype(np.int32), np.unpackbits(z["adj_w"])[:ne],
+                        np.concatenate([[0], np.cumsum(z["ncol"].astype(np.int64))]), z["col_val"])
+
+
 class Context:
     """One dg_ctx (one GPU)."""
 
@@ -160,6 +209,64 @@ class Context:
 
     def dip_create(self, g: LevelGraph, R: int) -> "DipProblem":
         return DipProblem(self, g, R)
+
+    # ---- haploid DP ------------------------------------------------------------------------
+    def dp_haploid(self, g: "HapGraph", R: int):
+        """One-shot host-buffer call (dg_dp_haploid)."""
+        cby = np.zeros(R + 1, np.int32)
+        poff = np.zeros(R + 2, np.int64)
+        buf = C.POINTER(C.c_int32)()
+        rc = self.lib.dg_dp_haploid(C.c_void_p(self.h), C.c_int32(g.n), _ptr(g.adj_off), _ptr(g.adj_dst), _ptr(g.adj_w),
+                                    _ptr(g.col_off), _ptr(g.col_val), C.c_int32(g.n_colours), C.c_int32(R), _ptr(cby),
+                                    _ptr(poff), C.byref(buf))
+        self.check(rc, "dg_dp_haploid")
+        tot = int(poff[-1])
+        flat = np.ctypeslib.as_array(buf, shape=(max(tot, 1),))[:tot].copy()
+        self.lib.dg_free(buf)
+        return dict(colours_by_r=cby, paths=[flat[poff[r]:poff[r + 1]] for r in range(R + 1)])
+
+    def hap_create(self, g: "HapGraph", R: int) -> "HapProblem":
+        return HapProblem(self, g, R)
+
+
+class HapProblem:
+    """A haploid DP problem resident in HBM (dg_hap_*)."""
+
+    def __init__(self, ctx: "Context", g: "HapGraph", R: int):
+        self.ctx = ctx
+        self.R = R
+        self.n = g.n
+        h = C.c_void_p(None)
+        rc = ctx.lib.dg_hap_create(C.c_void_p(ctx.h), C.c_int32(g.n), _ptr(g.adj_off), _ptr(g.adj_dst), _ptr(g.adj_w),
+                                   _ptr(g.col_off), _ptr(g.col_val), C.c_int32(g.n_colours), C.c_int32(R), C.byref(h))
+        ctx.check(rc, "dg_hap_create")
+        self.h = h
+
+    def run(self):
+        self.ctx.check(self.ctx.lib.dg_hap_run(C.c_void_p(self.ctx.h), self.h), "dg_hap_run")
+
+    def result(self):
+        cby = np.zeros(self.R + 1, np.int32)
+        plen = np.zeros(self.R + 1, np.int32)
+        self.ctx.check(self.ctx.lib.dg_hap_result(C.c_void_p(self.ctx.h), self.h, _ptr(cby), _ptr(plen)), "dg_hap_result")
+        return dict(colours_by_r=cby, path_len=plen)
+
+    def path(self, r: int, cap: int):
+        buf = np.zeros(max(cap, 1), np.int32)
+        n = C.c_int32(0)
+        self.ctx.check(self.ctx.lib.dg_hap_path(C.c_void_p(self.ctx.h), self.h, C.c_int32(r), _ptr(buf), C.c_int32(cap),
+                                                C.byref(n)), "dg_hap_path")
+        return buf[: n.value].copy()
+
+    def stats(self) -> dict:
+        s = HapStats()
+        self.ctx.check(self.ctx.lib.dg_hap_stats(C.c_void_p(self.ctx.h), self.h, C.byref(s)), "dg_hap_stats")
+        return {k: getattr(s, k) for k, _ in HapStats._fields_}
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dg_hap_destroy(C.c_void_p(self.ctx.h), self.h)
+            self.h = None
 
 
 class DipProblem:

@@ -152,3 +152,33 @@ def truncate_levels(g: LevelGraph, n_levels: int) -> LevelGraph:
     col_val = g.col_val[: int(g.col_off[V])]
     level_off = np.concatenate([g.level_off[: n_levels + 1], [V + 1]]).astype(np.int32)
     return LevelGraph(level_off, adj_off, adj_dst, adj_w, col_off, col_val, g.colour_is_hom)
+
+
+def random_kahn_graph(seed: int, n: int = 200, max_out: int = 4, p_weight1: float = 0.3, p_colour: float = 0.3,
+                      n_colours: int = 64, max_span: int = 12, max_cols: int = 4, p_dup: float = 0.1):
+    """Random DAG whose vertex ids are already a topological order (what ExpandedGraph::topologically_reorder
+    hands to the haploid DP): every vertex i < n-1 gets 1..max_out forward edges of span <= max_span (duplicates
+    and mixed-weight parallel edges included, which exercise the first-writer tie-break), sorted colour sets."""
+    from .cuda_api import HapGraph
+    rng = np.random.default_rng(seed)
+    off = [0]
+    dst, wt = [], []
+    for u in range(n):
+        if u < n - 1:
+            for _ in range(int(rng.integers(1, max_out + 1))):
+                v = int(min(n - 1, u + 1 + rng.integers(0, max_span)))
+                dst.append(v)
+                wt.append(1 if rng.random() < p_weight1 else 0)
+                if rng.random() < p_dup:
+                    dst.append(v)
+                    wt.append(1 if rng.random() < 0.5 else 0)
+        off.append(len(dst))
+    coff = [0]
+    cval = []
+    for u in range(n):
+        if n_colours and rng.random() < p_colour:
+            cs = np.unique(rng.integers(0, n_colours, int(rng.integers(1, max_cols + 1))))
+            cval.extend(int(c) for c in cs)
+        coff.append(len(cval))
+    return HapGraph(np.array(off, np.int64), np.array(dst, np.int32), np.array(wt, np.uint8), np.array(coff, np.int64),
+                    np.array(cval, np.int32), n_colours=max(n_colours, 1))

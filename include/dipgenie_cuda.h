@@ -91,6 +91,43 @@ int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out);
 int dg_dip_profile(dg_ctx* ctx, dg_dip* d, uint64_t* out24);
 void dg_dip_destroy(dg_ctx* ctx, dg_dip* d);
 
+/* ---- haploid DP: Approximator::dp_approximation_solver, src/approximator.cpp:44-168 ------------
+ * (the push-relaxation loop :50-67, the R+1 tracebacks with their distinct-colour counts :70-102 and
+ *  the final traceback :141-153; the caller keeps the floating-point best_r rule :116-136, the
+ *  original-vertex expansion and de-duplication :154-167 and the FASTA writer :1266-1277).
+ *
+ * Input: the ExpandedGraph after topologically_reorder (src/ExpandedGraph.hpp:29-102), flattened:
+ *   n                                     vertices in Kahn order (every edge goes to a larger id; sink = n-1)
+ *   adj_off[n+1], adj_dst[E], adj_w[E]    g.adj_list as CSR, adjacency order preserved, weights 0/1
+ *   col_off[n+1], col_val[]               g.color as CSR (colour ids < n_colours)
+ *   R                                     recombination_limit
+ * Output (bit-exact with the reference, same first-writer tie-breaking :60):
+ *   colours_by_r[R+1]   distinct colours on the traceback path of layer r ("true score", :100)
+ *   path_off[R+2], *paths   the R+1 traceback paths, source first (:153), as vertex ids, concatenated;
+ *                       *paths is library-allocated (release with dg_free)
+ */
+int dg_dp_haploid(dg_ctx* ctx, int32_t n, const int64_t* adj_off, const int32_t* adj_dst, const uint8_t* adj_w,
+                  const int64_t* col_off, const int32_t* col_val, int32_t n_colours, int32_t R,
+                  int32_t* colours_by_r, int64_t* path_off, int32_t** paths);
+
+/* The same computation with the graph resident in HBM between runs. */
+typedef struct dg_hap dg_hap;
+int dg_hap_create(dg_ctx* ctx, int32_t n, const int64_t* adj_off, const int32_t* adj_dst, const uint8_t* adj_w,
+                  const int64_t* col_off, const int32_t* col_val, int32_t n_colours, int32_t R, dg_hap** out);
+int dg_hap_run(dg_ctx* ctx, dg_hap* d);
+int dg_hap_result(dg_ctx* ctx, dg_hap* d, int32_t* colours_by_r /* [R+1] */, int32_t* path_len /* [R+1] */);
+/* path of layer r, source first, vertex ids; DG_ERR_CAPACITY (with *len set) when cap is too small */
+int dg_hap_path(dg_ctx* ctx, dg_hap* d, int32_t r, int32_t* path, int32_t cap, int32_t* len);
+/* U = (R+1)*nE cell-updates, C = (R+1)*n cells, B = (R+1)*(8n + 8nE) algorithmic bytes */
+typedef struct {
+    uint64_t cell_updates, cells, algo_bytes, device_bytes;
+    int32_t n_levels, n_vertices, max_width, max_indegree;
+    int32_t launches;
+    float sweep_ms, traceback_ms;
+} dg_hap_stats_t;
+int dg_hap_stats(dg_ctx* ctx, dg_hap* d, dg_hap_stats_t* out);
+void dg_hap_destroy(dg_ctx* ctx, dg_hap* d);
+
 #ifdef __cplusplus
 }
 #endif

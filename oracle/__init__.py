@@ -84,6 +84,27 @@ def dp_diploid(level_off, adj_off, adj_dst, adj_w, col_off, col_val, colour_is_h
     return out
 
 
+def dp_haploid(adj_off, adj_dst, adj_w, col_off, col_val, n_colours, R):
+    """Oracle haploid DP on the Kahn-ordered expanded graph. Returns dict(colours_by_r, paths[list per r])."""
+    adj_off = _c(adj_off, np.int64)
+    adj_dst = _c(adj_dst, np.int32)
+    adj_w = _c(adj_w, np.uint8)
+    col_off = _c(col_off, np.int64)
+    col_val = _c(col_val, np.int32)
+    n = len(adj_off) - 1
+    cby = np.zeros(R + 1, np.int32)
+    poff = np.zeros(R + 2, np.int64)
+    cap = (R + 1) * n
+    pval = np.zeros(cap, np.int32)
+    f = lib().dgo_dp_haploid
+    f.restype = C.c_int
+    rc = f(C.c_int32(n), _p(adj_off, _i64p), _p(adj_dst, _i32p), _p(adj_w, _u8p), _p(col_off, _i64p), _p(col_val, _i32p),
+           C.c_int32(n_colours), C.c_int32(R), _p(cby, _i32p), _p(poff, _i64p), _p(pval, _i32p), C.c_int64(cap))
+    if rc != 0:
+        raise RuntimeError(f"dgo_dp_haploid failed rc={rc}")
+    return dict(colours_by_r=cby, paths=[pval[poff[r]:poff[r + 1]].copy() for r in range(R + 1)])
+
+
 def _take(ptr, n, dtype):
     """Copy n items from a malloc'ed C array into numpy and free it."""
     if n == 0:
