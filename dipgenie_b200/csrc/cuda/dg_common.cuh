@@ -14,6 +14,7 @@ struct dg_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     std::string err;
+    dg_sketch_stats_t sketch_stats = {};
 };
 
 namespace dg {

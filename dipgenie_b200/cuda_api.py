@@ -34,6 +34,11 @@ class HapStats(C.Structure):
     ]
 
 
+class SketchStats(C.Structure):
+    _fields_ = [("bases", C.c_uint64), ("minimizers", C.c_uint64), ("spectrum", C.c_uint64), ("hits", C.c_uint64),
+                ("kernel_ms", C.c_float), ("launches", C.c_int32)]
+
+
 class DipGenieCudaError(RuntimeError):
     pass
 
@@ -209,6 +214,69 @@ class Context:
 
     def dip_create(self, g: LevelGraph, R: int) -> "DipProblem":
         return DipProblem(self, g, R)
+
+    # ---- sketch / spectrum / join ------------------------------------------------------------
+    def _take(self, ptr, n, dtype):
+        a = np.ctypeslib.as_array(ptr, shape=(max(int(n), 1),))[: int(n)].astype(dtype, copy=True)
+        self.lib.dg_free(ptr)
+        return a
+
+    def sketch_stats(self) -> dict:
+        s = SketchStats()
+        self.check(self.lib.dg_sketch_last_stats(C.c_void_p(self.h), C.byref(s)), "dg_sketch_last_stats")
+        return {k: getattr(s, k) for k, _ in SketchStats._fields_}
+
+    def sketch_minimizers(self, bases, seq_off, k: int, w: int):
+        """dg_sketch_minimizers: (count per sequence, hashes, starts) in sequence order."""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        seq_off = np.ascontiguousarray(seq_off, np.uint64)
+        n = len(seq_off) - 1
+        cnt = np.zeros(max(n, 1), np.uint64)
+        hp = C.POINTER(C.c_uint64)()
+        sp = C.POINTER(C.c_uint64)()
+        rc = self.lib.dg_sketch_minimizers(C.c_void_p(self.h), _ptr(bases), _ptr(seq_off), C.c_uint32(n), C.c_int(k), C.c_int(w),
+                                           _ptr(cnt), C.byref(hp), C.byref(sp))
+        self.check(rc, "dg_sketch_minimizers")
+        tot = int(cnt[:n].sum())
+        return cnt[:n], self._take(hp, tot, np.uint64), self._take(sp, tot, np.uint64)
+
+    def sketch_reads(self, bases, read_off, k: int, w: int):
+        """dg_sketch_reads: (spectrum ascending, read_count)."""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        read_off = np.ascontiguousarray(read_off, np.uint64)
+        sp = C.POINTER(C.c_uint64)()
+        rc_ = C.POINTER(C.c_uint32)()
+        ns = C.c_uint64(0)
+        rc = self.lib.dg_sketch_reads(C.c_void_p(self.h), _ptr(bases), _ptr(read_off), C.c_uint32(len(read_off) - 1), C.c_int(k),
+                                      C.c_int(w), C.byref(sp), C.byref(rc_), C.byref(ns))
+        self.check(rc, "dg_sketch_reads")
+        return self._take(sp, ns.value, np.uint64), self._take(rc_, ns.value, np.uint32)
+
+    def index_walks(self, seg_bases, seg_off, walk_vtx, walk_off, top_order_map, k: int, w: int, spectrum):
+        """dg_index_walks: dict(n_minimizers, hit_off, hit_sid, hit_vtx_off, hit_vtx)."""
+        seg_bases = np.ascontiguousarray(seg_bases, np.uint8)
+        seg_off = np.ascontiguousarray(seg_off, np.uint64)
+        walk_vtx = np.ascontiguousarray(walk_vtx, np.int32)
+        walk_off = np.ascontiguousarray(walk_off, np.uint64)
+        top_order_map = np.ascontiguousarray(top_order_map, np.int32)
+        spectrum = np.ascontiguousarray(spectrum, np.uint64)
+        nw = len(walk_off) - 1
+        nmin = np.zeros(max(nw, 1), np.uint64)
+        ho = C.POINTER(C.c_uint64)()
+        hs = C.POINTER(C.c_uint32)()
+        vo = C.POINTER(C.c_uint64)()
+        hv = C.POINTER(C.c_int32)()
+        rc = self.lib.dg_index_walks(C.c_void_p(self.h), _ptr(seg_bases), _ptr(seg_off), C.c_uint32(len(seg_off) - 1),
+                                     _ptr(walk_vtx), _ptr(walk_off), C.c_uint32(nw), _ptr(top_order_map), C.c_int(k), C.c_int(w),
+                                     _ptr(spectrum), C.c_uint64(len(spectrum)), _ptr(nmin), C.byref(ho), C.byref(hs),
+                                     C.byref(vo), C.byref(hv))
+        self.check(rc, "dg_index_walks")
+        hit_off = self._take(ho, nw + 1, np.uint64)
+        nh = int(hit_off[-1])
+        hit_sid = self._take(hs, nh, np.uint32)
+        hit_vtx_off = self._take(vo, nh + 1, np.uint64)
+        hit_vtx = self._take(hv, int(hit_vtx_off[-1]), np.int32)
+        return dict(n_minimizers=nmin[:nw], hit_off=hit_off, hit_sid=hit_sid, hit_vtx_off=hit_vtx_off, hit_vtx=hit_vtx)
 
     # ---- haploid DP ------------------------------------------------------------------------
     def dp_haploid(self, g: "HapGraph", R: int):

@@ -128,6 +128,47 @@ typedef struct {
 int dg_hap_stats(dg_ctx* ctx, dg_hap* d, dg_hap_stats_t* out);
 void dg_hap_destroy(dg_ctx* ctx, dg_hap* d);
 
+/* ---- minimizer sketch / read spectrum / walk-index join ------------------------------------------
+ * Sequences are passed concatenated: sequence s = bases[seq_off[s] .. seq_off[s+1]) (any case, any bytes;
+ * the comparison order is the reference's: lexicographic on the upper-cased canonical ASCII k-mer,
+ * rightmost minimum in a window, emit when the hash changes).  hash = MurmurHash3_x64_128
+ * (seed 0) h1^h2 of the k canonical bytes (src/solver.cpp:16-24).  Arrays returned through T** are
+ * library-allocated host arrays (release with dg_free).
+ */
+
+/* Raw minimizer lists: Solver::index_kmers' (hash, start) sequence (src/solver.cpp:303-361) and the
+ * pre-set content of Solver::compute_hashes (:376-409) for every sequence, in sequence order.
+ * seq_count[n_seq] (nullable) = minimizers per sequence; starts = k-mer start within its sequence. */
+int dg_sketch_minimizers(dg_ctx* ctx, const uint8_t* bases, const uint64_t* seq_off, uint32_t n_seq, int k, int w,
+                         uint64_t* seq_count, uint64_t** hashes, uint64_t** starts);
+
+/* Solver::compute_hashes over all reads (src/solver.cpp:366-412, :528-532) + the read spectrum Sp_R
+ * (:534-555: distinct hashes ascending, id = index) + kmer_count (:711-732: reads containing the hash). */
+int dg_sketch_reads(dg_ctx* ctx, const uint8_t* bases, const uint64_t* read_off, uint32_t n_reads, int k, int w,
+                    uint64_t** spectrum, uint32_t** read_count, uint64_t* n_spectrum);
+
+/* Solver::index_kmers for every walk (src/solver.cpp:277-363) joined with the spectrum like
+ * Solver::compute_anchors (:415-446, :560-576).  Panel as flat arrays: segment v = seg_bases[seg_off[v] ..
+ * seg_off[v+1]) (node_seq), walk h = walk_vtx[walk_off[h] .. walk_off[h+1]) (paths), top_order_map[n_seg].
+ * Output, walk by walk in walk order: n_minimizers[n_walks] (all minimizers of the walk, before the join:
+ * the log line of :474), hit_off[n_walks+1], hit_sid[n_hits] (spectrum id), hit_vtx_off[n_hits+1] and
+ * hit_vtx (the unique vertices under bases [start,start+k) ordered by top_order_map, :343-357). */
+int dg_index_walks(dg_ctx* ctx, const uint8_t* seg_bases, const uint64_t* seg_off, uint32_t n_seg,
+                   const int32_t* walk_vtx, const uint64_t* walk_off, uint32_t n_walks,
+                   const int32_t* top_order_map, int k, int w,
+                   const uint64_t* spectrum, uint64_t n_spectrum,
+                   uint64_t* n_minimizers, uint64_t** hit_off, uint32_t** hit_sid,
+                   uint64_t** hit_vtx_off, int32_t** hit_vtx);
+
+/* Accounting of the last sketch call on ctx: input bases, emitted minimizers, spectrum size, join hits,
+ * device milliseconds (CUDA events on the context's stream around the kernels) and kernel launches. */
+typedef struct {
+    uint64_t bases, minimizers, spectrum, hits;
+    float kernel_ms;
+    int32_t launches;
+} dg_sketch_stats_t;
+int dg_sketch_last_stats(dg_ctx* ctx, dg_sketch_stats_t* out);
+
 #ifdef __cplusplus
 }
 #endif

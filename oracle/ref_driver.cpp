@@ -215,6 +215,18 @@ int main(int argc, char** argv) {
         for (auto& s : A->hap_id2name) { names += s; names += '\n'; }
         g_w->put_str("panel.walk_names", names);
         g_w->put_i64("reads.n", (int64_t)ip_reads.size());
+        if (!light) {
+            // raw inputs of the sketch stage (node_seq, src/solver.cpp:63-70; read sequences, :230-245) so
+            // that the sketch fixtures are self-contained
+            std::string segs, rds;
+            std::vector<int64_t> so, ro; so.push_back(0); ro.push_back(0);
+            for (auto& q : A->node_seq) { segs += q; so.push_back((int64_t)segs.size()); }
+            for (auto& rd : ip_reads) { rds += rd.second; ro.push_back((int64_t)rds.size()); }
+            g_w->put_str("panel.node_seq", segs);
+            g_w->put("panel.node_seq_off", so);
+            g_w->put_str("reads.bases", rds);
+            g_w->put("reads.off", ro);
+        }
 
         if (!light) {
             // per-walk minimizer index: Solver::index_kmers, src/solver.cpp:277-363
