@@ -17,7 +17,7 @@ CLI_BIN = os.path.join(PKG, "dipgenie")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "--expt-relaxed-constexpr", "--expt-extended-lambda",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-Xcompiler", "-Wall", "-Xcompiler", "-Wno-unknown-pragmas", "--expt-relaxed-constexpr", "--expt-extended-lambda",
 ]
 
 
@@ -46,7 +46,7 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = _sources("cuda", (".cu", ".cpp"))
     deps = srcs + _sources("cuda", (".h", ".cuh")) + _sources("common", (".h",)) + [os.path.join(ROOT, "include", "dipgenie_cuda.h")]
     if force or _newer(CUDA_LIB, deps):
-        cmd = [nvcc_path(), *NVCC_FLAGS, "-shared", "-o", CUDA_LIB, *srcs]
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-shared", "-o", CUDA_LIB, *srcs, "-lgomp"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.check_call(cmd)

@@ -18,6 +18,12 @@ dg_ctx* dg_create(int device) {
         delete ctx;
         return nullptr;
     }
+    // keep freed blocks in the stream-ordered pool (see DevBuf)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     return ctx;
 }
 

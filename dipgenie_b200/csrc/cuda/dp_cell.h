@@ -1,13 +1,14 @@
-// dp_cell.h — the per-cell arithmetic of the diploid DP, shared verbatim by the CUDA kernels
-// (dp_diploid.cu) and by the CPU kernel-logic emulator used in the `-m "not gpu"` tests
+// dp_cell.h — the per-cell arithmetic and the task format of the diploid DP, shared verbatim by the
+// CUDA kernels (dp_diploid.cu) and by the CPU kernel-logic emulator used in the `-m "not gpu"` tests
 // (tests/emu/dp_emu.cpp).  Nothing here is a fallback: the product path only ever runs it on the device.
 //
 // Reference semantics (src/approximator.cpp:627-701): destination cell (r2,i',j') of level l+1 receives
 //     max over edges (i -w1-> i'), (j -w2-> j'), r = r2-w1-w2 >= 0, src(r,i,j) live
 //         of  src(r,i,j).value + delta(i,j,i',j')
-// ties broken towards smaller i, then smaller j (:657-659).  Packed as one unsigned 64-bit key
-//     key = value << 32 | (0xFFFF - i) << 16 | (0xFFFF - j)
-// so the winner is a plain integer max; key == 0 means "no live candidate" (cell stays NEG_INF, :568).
+// ties broken towards smaller i, then smaller j (:657-659).  In-edge lists are kept in ascending source
+// position, so the *first strict maximum* in (e1, e2) iteration order is exactly that winner.  Live
+// values are >= 0 (level 0 starts at 0, :535; deltas are set sizes), dead cells hold NEG_INF, so a
+// running maximum initialised to -1 never accepts a dead source (NEG_INF + delta << -1).
 // The winner's in-edge ordinals (e1 within in(i'), e2 within in(j')) are the predecessor code.
 #pragma once
 #include <cstddef>
@@ -31,63 +32,114 @@ DG_HD int popc64(uint64_t x) {
 #endif
 }
 
-// One transition (level l -> l+1) as the kernels see it.  OffT = int32_t when in_off/in_edge point into
-// the global in-edge CSR, uint16_t when they point into a packed per-transition record staged in
-// shared memory (dp_prep.h: RecHeader), where offsets are relative to the record's own edge array.
+// ---- tasks ---------------------------------------------------------------------------------------
+// The host planner (dp_prep.cpp: plan_tasks) compiles the sweep into one task stream per CTA.  A task
+// is "rows [i0,i1) of the destination level of transition `level`"; the 128-byte header below travels
+// with the task's record into a shared-memory slot (three bulk copies on one mbarrier: header, record,
+// delta slice).  Narrow transitions are one task on CTA 0 with both DP layers in shared memory; wide
+// ones are split by destination row over P CTAs with the layers in HBM/L2 and closed by a
+// monotone-counter grid barrier.
+enum : uint32_t {
+    TK_WAIT = 1,           // grid-level wait (counter >= wait_target) before the task
+    TK_ARRIVE = 2,         // grid-level arrive after the task (implies TK_BAR)
+    TK_SRC_SMEM = 4,       // source layer lives in CTA 0's shared-memory tile
+    TK_DST_SMEM = 8,       // destination layer goes to CTA 0's shared-memory tile
+    TK_BAR = 16,           // block barrier after the task (last task of this CTA for the level)
+    TK_DELTA = 32,         // the transition has a pair-score matrix (colours on level l or l+1)
+    TK_DELTA_STAGED = 64,  // ... and this task's rows of it are staged in the slot
+    TK_REC_GLOBAL = 128,   // in-edge lists are read in place from the global CSR (record too big for a slot)
+    TK_DELTA_MASKS = 256,  // no matrix was materialised (too wide): popcount the colour masks on the fly
+    TK_LANES = 512,        // lane form (below); otherwise the pair form
+};
+
+// Two evaluation forms of a task, same results:
+//  * lane form (TK_LANES, the fast path): a warp takes a group of `rp` destination rows x one block of <= 32
+//    in-edges e2 of the destination level; lane = (row slot, e2).  Every lane walks the in-edges e1 of its row
+//    (same trip count for the lanes of a row: no divergence inside a row) and keeps the first strict maximum
+//    for its e2; the lanes of one destination column j' (adjacent: in-edges are grouped by destination, and a
+//    block never cuts a group) are then combined by a segmented warp-shuffle maximum (value desc, code asc),
+//    and the first lane of each group stores the cell.  Needs: staged record, pair scores absent or staged,
+//    every destination of the level with 1..32 in-edges.
+//  * pair form: one thread per (destination pair, chunk of layers) looping over in(i') x in(j') — any shape,
+//    any placement of records and scores (the general fallback).
+struct TaskHdr {             // 128 bytes
+    // fetch part (read by the producer lane before the copies are issued)
+    uint32_t rec_off16;      // record offset in `records`, units of 16 bytes
+    uint32_t rec_bytes;      // multiple of 16; 0: nothing staged besides the header
+    uint32_t delta_off16;    // 16-byte-aligned start of the staged delta slice in the delta buffer, units of 16 bytes
+    uint32_t delta_bytes;    // multiple of 16; 0: no staged slice
+    // exec part
+    int32_t level;           // transition level -> level+1
+    uint32_t flags;
+    uint32_t wait_target;
+    uint32_t delta_skew;     // u16 elements between the staged slice start and the first delta row of row i0
+    uint16_t k, k2;          // widths of the two levels
+    uint16_t i0, i1;         // destination rows of this task
+    uint32_t n_in;           // in-edges of level l+1 (valid unless TK_REC_GLOBAL)
+    uint32_t n_active;       // threads of the CTA that own work (warps beyond skip the task)
+    int64_t pred_off2;       // offset (cells) of level l+1's predecessor codes
+    uint32_t m_k2;           // pair form: magic of k2
+    uint32_t m_pairs;        //            magic of npairs = (i1-i0) * k2
+    uint16_t rc;             // layers per work item (pair form: DIP_RC; lane form: LANE_RC_SMALL / LANE_RC_BIG)
+    uint16_t groups;         // pair form: thread groups sharing the pairs (>= 1); chunks are dealt round-robin
+    uint16_t nblk;           // lane form: blocks of the in-edge range
+    uint16_t rp;             //            destination rows per warp item (> 1 only when nblk == 1)
+    uint32_t nrg;            //            row groups = ceil((i1-i0) / rp)
+    uint32_t m_nblk, m_nrg;  //            magics of nblk, nrg
+    uint32_t m_nin;          //            magic of n_in (lane -> row slot)
+    uint32_t n_witems;       //            warp items = nrg * nblk * chunks
+    uint32_t rounds;         //            shuffle rounds of the segmented maximum = ceil(log2(longest group))
+    uint32_t bstart_off;     //            byte offset of bstart[] inside the record
+    uint32_t pad[7];
+};
+static_assert(sizeof(TaskHdr) == 128, "TaskHdr layout");
+
+// x / d for 0 <= x < 2^16 * ... : with m = floor(2^32/d)+1 the product (x*m)>>32 is exact whenever
+// x * d < 2^32 (here x < 2^20 threads/pairs and d < 2^12 in every use; the planner checks).
+DG_HD uint32_t div_magic(uint32_t x, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(x, m);
+#else
+    return (uint32_t)(((uint64_t)x * m) >> 32);
+#endif
+}
+inline uint32_t make_magic(uint32_t d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / d) + 1u; }
+
+// One transition (level l -> l+1) as the kernels see it.  OffT = uint16_t when in_off points into a
+// staged record (offsets relative to the record's own in_edge array), int32_t when in_off / in_edge
+// are the global in-edge CSR (absolute offsets).
 template <class OffT>
 struct TransitionT {
     int32_t k;                 // |level l|
     int32_t k2;                // |level l+1|
-    int32_t W;                 // 64-bit mask words per set (0: no colours on either level)
-    const OffT* in_off;        // k2+1 entries, indexed by destination position
+    const OffT* in_off;        // indexed by destination position, k2+1 entries
     const uint32_t* in_edge;   // entry = source position | weight << 16
+    // pair-score matrix D[e1][e2] over the in-edges of level l+1 (approximator.cpp:604-624 precomputed):
+    // delta of candidate (e1,e2) = delta[(e1 - e1_base) * dstride + (e2 - e2_base)]
+    const uint16_t* delta;
+    int32_t dstride, e1_base, e2_base;
+    // on-the-fly form (TK_DELTA_MASKS): colour bit-masks of the two levels
+    int32_t W;                 // 64-bit mask words per set
     const uint64_t* msrc;      // [k ][2W]  hom words then het words
     const uint64_t* mdst;      // [k2][2W]
 };
-using Transition = TransitionT<int32_t>;
 
-// ---- packed per-transition records (staged through shared memory by the sweep kernel) ----------
-// record = RecHeader | in_off2 u16[k2+1] | pad4 | in_edge u32[n_in] | pad8 | msrc u64[k*2W] | mdst u64[k2*2W] | pad16
-// in_off2 is relative to the record's own in_edge array, so a record is self-contained.
-enum : uint16_t {
-    REC_WAIT = 1,        // grid-level wait (counter >= wait_target) before the transition
-    REC_ARRIVE = 2,      // grid-level arrive after the transition
-    REC_SRC_SMEM = 4,    // source layer lives in CTA 0's shared-memory tile
-    REC_DST_SMEM = 8,    // destination layer goes to CTA 0's shared-memory tile
-};
-enum : uint8_t { MODE_FAST = 0, MODE_STAGED = 1, MODE_GLOBAL = 2 };
-
-struct RecHeader {               // 32 bytes
-    uint16_t k, k2, W, flags;
-    uint32_t n_in, bytes;        // bytes: whole record, multiple of 16
-    uint32_t P, wait_target;
-    int64_t pred_off2;           // offset (cells) of level l+1's predecessor codes
-};
-static_assert(sizeof(RecHeader) == 32, "RecHeader layout");
-
-// View of a packed record (global or shared memory) as a transition.
-DG_HD void record_view(const uint8_t* rec, RecHeader& h, TransitionT<uint16_t>& tr) {
-    h = *reinterpret_cast<const RecHeader*>(rec);
-    tr.k = h.k; tr.k2 = h.k2; tr.W = h.W;
-    size_t o = sizeof(RecHeader);
-    tr.in_off = reinterpret_cast<const uint16_t*>(rec + o);
-    o += (((size_t)h.k2 + 1) * 2 + 3) & ~(size_t)3;
-    tr.in_edge = reinterpret_cast<const uint32_t*>(rec + o);
-    o += (size_t)h.n_in * 4; o = (o + 7) & ~(size_t)7;
-    tr.msrc = reinterpret_cast<const uint64_t*>(rec + o);
-    tr.mdst = tr.msrc + (size_t)h.k * 2 * h.W;
-}
+// record = in_off2 u16[k2+1] | pad16 | in_edge u32[n_in] | pad16 | in_dst u16[n_in] | pad16 | bstart u16[nblk+1] | pad16
+// (16-byte aligned, self-contained; in_dst = destination position of every in-edge, bstart = first in-edge of
+// every lane-form block, bstart[nblk] = n_in)
+DG_HD size_t rec_edge_offset(int k2) { return (((size_t)k2 + 1) * 2 + 15) & ~(size_t)15; }
+DG_HD size_t rec_dst_offset(int k2, int64_t n_in) { return rec_edge_offset(k2) + (((size_t)n_in * 4 + 15) & ~(size_t)15); }
+DG_HD size_t rec_bstart_offset(int k2, int64_t n_in) { return rec_dst_offset(k2, n_in) + (((size_t)n_in * 2 + 15) & ~(size_t)15); }
+DG_HD size_t rec_bytes_for(int k2, int64_t n_in, int nblk) { return rec_bstart_offset(k2, n_in) + ((((size_t)nblk + 1) * 2 + 15) & ~(size_t)15); }
 
 // delta = |(Hom u1 ∪ Hom v1) ∩ (Hom u2 ∪ Hom v2)| + |(Het u1 ∪ Het v1) △ (Het u2 ∪ Het v2)|
 // (approximator.cpp:614-619).  `het_only` returns just the second term (dp_entry::s_het, :662).
-template <class OffT>
-DG_HD int pair_delta(const TransitionT<OffT>& t, int i, int j, int i2, int j2, bool het_only = false) {
-    const int W = t.W;
+DG_HD int mask_delta(int W, const uint64_t* msrc, const uint64_t* mdst, int i, int j, int i2, int j2, bool het_only = false) {
     if (W == 0) return 0;
-    const uint64_t* si = t.msrc + (int64_t)i * 2 * W;
-    const uint64_t* sj = t.msrc + (int64_t)j * 2 * W;
-    const uint64_t* di = t.mdst + (int64_t)i2 * 2 * W;
-    const uint64_t* dj = t.mdst + (int64_t)j2 * 2 * W;
+    const uint64_t* si = msrc + (int64_t)i * 2 * W;
+    const uint64_t* sj = msrc + (int64_t)j * 2 * W;
+    const uint64_t* di = mdst + (int64_t)i2 * 2 * W;
+    const uint64_t* dj = mdst + (int64_t)j2 * 2 * W;
     int acc = 0;
     for (int w = 0; w < W; ++w) {
         if (!het_only) acc += popc64((si[w] | sj[w]) & (di[w] | dj[w]));
@@ -96,85 +148,62 @@ DG_HD int pair_delta(const TransitionT<OffT>& t, int i, int j, int i2, int j2, b
     return acc;
 }
 
-DG_HD uint64_t pack_key(int32_t value, int i, int j) {
-    return ((uint64_t)(uint32_t)value << 32) | ((uint64_t)(0xFFFFu - (uint32_t)i) << 16) | (uint64_t)(0xFFFFu - (uint32_t)j);
-}
-DG_HD int32_t key_value(uint64_t key) { return key ? (int32_t)(uint32_t)(key >> 32) : NEG_INF; }
-
-// Gather for one destination cell.  `load(idx)` returns the source-layer value at flat index
-// (r*k + i)*k + j.  Returns the winning key (0 = dead cell); code = e1 << 16 | e2.
-template <class OffT, class Load>
-DG_HD uint64_t relax_cell(const TransitionT<OffT>& t, Load load, int r2, int i2, int j2, uint32_t& code) {
-    const int32_t a0 = (int32_t)t.in_off[i2], a1 = (int32_t)t.in_off[i2 + 1];
-    const int32_t b0 = (int32_t)t.in_off[j2], b1 = (int32_t)t.in_off[j2 + 1];
-    uint64_t best = 0;
-    uint32_t best_code = 0xFFFFFFFFu;
-    for (int32_t e1 = a0; e1 < a1; ++e1) {
-        const uint32_t x = t.in_edge[e1];
-        const int i = (int)(x & 0xFFFFu), wu = (int)(x >> 16);
-        const int ra = r2 - wu;
-        if (ra < 0) continue;
-        for (int32_t e2 = b0; e2 < b1; ++e2) {
-            const uint32_t y = t.in_edge[e2];
-            const int j = (int)(y & 0xFFFFu), wv = (int)(y >> 16);
-            const int r = ra - wv;
-            if (r < 0) continue;
-            const int32_t s = load(((int64_t)r * t.k + i) * t.k + j);
-            if (s == NEG_INF) continue;
-            const uint64_t key = pack_key(s + pair_delta(t, i, j, i2, j2), i, j);
-            if (key > best) { best = key; best_code = ((uint32_t)(e1 - a0) << 16) | (uint32_t)(e2 - b0); }
-        }
-    }
-    code = best_code;
-    return best;
-}
-
-// Gather for one destination pair (i',j') and RC consecutive layers r2 = r0 .. r0+RC-1 at once
-// ("pair-major" form used by the kernels).  The in-edge decode, the candidate's flat source offset, its
-// tie-break bits and its colour delta do not depend on r2, so they are computed once per candidate and
-// reused for all RC layers; the RC source loads of a candidate are independent (ILP).  For every layer
-// the winner is the same lexicographic max as relax_cell().  best[rr] == 0 means layer r0+rr is dead
-// (or beyond R).  code[rr] = e1 << 16 | e2.
-template <int RC, bool HAS_MASK, class OffT, class Load>
+// MASKS = false: delta comes from the precomputed matrix (t.delta, null when the transition has no colours:
+// a warp-uniform predicate, so both cases share one code path); MASKS = true: masks on the fly.
+// Gather for one destination pair (i',j') and RC consecutive layers r2 = r0 .. r0+RC-1 at once.  The
+// in-edge decode, the candidate's flat source offset and its delta do not depend on r2, so they are
+// computed once per candidate; the RC source loads of a candidate are independent (ILP).
+// `load(idx)` returns the source-layer value at flat index (r*k + i)*k + j.
+// best[rr] < 0 means layer r0+rr is dead (or beyond R).  code[rr] = e1 ordinal << 16 | e2 ordinal.
+template <int RC, bool MASKS, class IdxT, class OffT, class Load>
 DG_HD void relax_pair(const TransitionT<OffT>& t, Load load, int R, int r0, int i2, int j2,
-                      uint64_t (&best)[RC], uint32_t (&code)[RC]) {
+                      int32_t (&best)[RC], uint32_t (&code)[RC]) {
     const int32_t a0 = (int32_t)t.in_off[i2], a1 = (int32_t)t.in_off[i2 + 1];
     const int32_t b0 = (int32_t)t.in_off[j2], b1 = (int32_t)t.in_off[j2 + 1];
-    const int64_t kk = (int64_t)t.k * t.k;
+    const IdxT kk = (IdxT)t.k * (IdxT)t.k;
+    const bool has_matrix = !MASKS && t.delta != nullptr;
 #pragma unroll
-    for (int rr = 0; rr < RC; ++rr) { best[rr] = 0; code[rr] = 0xFFFFFFFFu; }
+    for (int rr = 0; rr < RC; ++rr) { best[rr] = -1; code[rr] = 0xFFFFFFFFu; }
     for (int32_t e1 = a0; e1 < a1; ++e1) {
         const uint32_t x = t.in_edge[e1];
         const int i = (int)(x & 0xFFFFu), wu = (int)(x >> 16);
+        const uint16_t* drow = t.delta + ((int64_t)(e1 - t.e1_base) * t.dstride - t.e2_base);
         for (int32_t e2 = b0; e2 < b1; ++e2) {
             const uint32_t y = t.in_edge[e2];
             const int j = (int)(y & 0xFFFFu), w = wu + (int)(y >> 16);
-            const int64_t base = (int64_t)i * t.k + j;
-            const uint64_t low = ((uint64_t)(0xFFFFu - (uint32_t)i) << 16) | (uint64_t)(0xFFFFu - (uint32_t)j);
-            const int d = HAS_MASK ? pair_delta(t, i, j, i2, j2) : 0;
+            const IdxT base = (IdxT)i * (IdxT)t.k + (IdxT)j;
+            int d = 0;
+            if (has_matrix) d = (int)drow[e2];
+            if (MASKS) d = mask_delta(t.W, t.msrc, t.mdst, i, j, i2, j2);
             const uint32_t cd = ((uint32_t)(e1 - a0) << 16) | (uint32_t)(e2 - b0);
+            // the RC source loads are issued unconditionally (layer index clamped into [0,R]) so that they
+            // are independent and overlap; validity only gates the compare
+            int32_t v[RC];
 #pragma unroll
             for (int rr = 0; rr < RC; ++rr) {
-                const int r = r0 + rr - w;
-                if (r >= 0 && r0 + rr <= R) {
-                    const int32_t s = load((int64_t)r * kk + base);
-                    if (s != NEG_INF) {
-                        const uint64_t key = ((uint64_t)(uint32_t)(s + d) << 32) | low;
-                        if (key > best[rr]) { best[rr] = key; code[rr] = cd; }
-                    }
-                }
+                int r = r0 + rr - w;
+                r = r < 0 ? 0 : (r > R ? R : r);
+                v[rr] = load((IdxT)r * kk + base);
+            }
+#pragma unroll
+            for (int rr = 0; rr < RC; ++rr) {
+                const bool ok = (r0 + rr - w >= 0) && (r0 + rr <= R);
+                const int32_t c = v[rr] + d;
+                if (ok && c > best[rr]) { best[rr] = c; code[rr] = cd; }
             }
         }
     }
 }
 
-// Layers handled per work item: as many as possible (amortises the decode) while still giving every
-// one of `nthreads` threads an item.
-DG_HD int choose_rc(uint64_t npairs, int R, uint64_t nthreads) {
-    int rc = 8;
-    while (rc > 1 && npairs * (uint64_t)((R + rc) / rc) < nthreads) rc >>= 1;
-    return rc;
-}
+// Layers per work item.  One value for every task: the sweep kernel has to stay small (consecutive
+// levels would otherwise keep switching between unrolled variants) and register-lean; 4 layers give the
+// narrow levels enough items to spread over the CTA and still amortise the in-edge decode.
+constexpr int DIP_RC = 4;
+DG_HD int choose_rc(uint32_t, int, uint32_t) { return DIP_RC; }
+// Layers per lane in the lane form: two compiled variants; the planner picks one per problem
+// (SweepShape::lane_rc).  Measured on B200 (MHC_4, R=18): 4 is fastest — more, shorter warp items keep all
+// sub-partitions busy inside one level; 20 layers per lane was 1.7x slower.
+constexpr int LANE_RC_SMALL = 4, LANE_RC_BIG = 8;
 
 // Same fold as oracle/ref_hook.h::dg_ref_level_done, for one live cell; the per-level checksum is the
 // wrapping sum of these plus the FNV offset basis.
@@ -200,43 +229,49 @@ struct TraceView {
     const int64_t* pred_off;
 };
 
-// Walks the predecessor codes from the sink cell (r=R,0,0) back to level 0 and emits what the
-// reference keeps as linked lists (approximator.cpp:666-692, materialize_edges :757-764):
-// every edge with weight>0 on P1 (resp. P2), and the final edge into the sink level on both.
-// Edges come out newest-first into p1/p2 (capacity cap pairs); the caller reverses them.
-// Returns 0, or -1 if the sink cell is dead, -2 on capacity overflow.
+struct TraceState { int32_t r, i2, j2; };   // cell (r, i2, j2) of some level
+
+// One step of the walk: from cell `s` of level l+1 to its winning source cell of level l.  Returns false
+// when the cell is dead.  wu/wv = weights of the two edges taken, (i,j) = source positions.
 template <class PredT>
-DG_HD int traceback(const TraceView& v, const PredT* pred, int32_t sink_value,
-                    int32_t* p1, int32_t* n1_out, int32_t* p2, int32_t* n2_out, int cap, int32_t* s_het_out) {
-    int n1 = 0, n2 = 0, s_het = 0;
-    *n1_out = 0; *n2_out = 0; *s_het_out = 0;
-    if (sink_value == NEG_INF) return -1;
+DG_HD bool trace_step(const TraceView& v, const PredT* pred, int l, TraceState& s, int& wu, int& wv, int& i2_old, int& j2_old) {
     constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
     constexpr uint32_t MK = (sizeof(PredT) == 2) ? 0xFFu : 0xFFFFu;
-    int r = v.R, i2 = 0, j2 = 0;
-    for (int l = v.L - 2; l >= 0; --l) {
+    const int32_t mid = v.level_off[l + 1];
+    const int32_t k2 = v.level_off[l + 2] - mid;
+    const PredT raw = pred[v.pred_off[l + 1] + ((int64_t)s.r * k2 + s.i2) * k2 + s.j2];
+    if (raw == (PredT) ~(PredT)0) return false;
+    const uint32_t code = (uint32_t)raw;
+    const int32_t e1 = v.in_off[mid + s.i2] + (int32_t)((code >> SH) & MK);
+    const int32_t e2 = v.in_off[mid + s.j2] + (int32_t)(code & MK);
+    const uint32_t x = v.in_edge[e1], y = v.in_edge[e2];
+    wu = (int)(x >> 16); wv = (int)(y >> 16);
+    i2_old = s.i2; j2_old = s.j2;
+    s.r -= wu + wv; s.i2 = (int)(x & 0xFFFFu); s.j2 = (int)(y & 0xFFFFu);
+    return true;
+}
+
+// Walks the predecessor codes from cell `s` of level l_hi down to level l_lo and emits what the
+// reference keeps as linked lists (approximator.cpp:666-692, materialize_edges :757-764): every edge with
+// weight > 0 on P1 (resp. P2), and the final edge into the sink level on both.  Edges come out
+// newest-first into p1/p2 (capacity cap pairs).  Returns 0, or -1 on a dead cell, -2 on capacity overflow.
+template <class PredT>
+DG_HD int trace_segment(const TraceView& v, const PredT* pred, int l_hi, int l_lo, TraceState& s,
+                        int32_t* p1, int32_t* n1_out, int32_t* p2, int32_t* n2_out, int cap, int32_t* s_het_out) {
+    int n1 = 0, n2 = 0, s_het = 0;
+    for (int l = l_hi - 1; l >= l_lo; --l) {
         const int32_t lo = v.level_off[l], mid = v.level_off[l + 1];
-        const int32_t k = mid - lo, k2 = v.level_off[l + 2] - mid;
-        const uint32_t code = (uint32_t)pred[v.pred_off[l + 1] + ((int64_t)r * k2 + i2) * k2 + j2];
-        const int32_t e1 = v.in_off[mid + i2] + (int32_t)((code >> SH) & MK);
-        const int32_t e2 = v.in_off[mid + j2] + (int32_t)(code & MK);
-        const uint32_t x = v.in_edge[e1], y = v.in_edge[e2];
-        const int i = (int)(x & 0xFFFFu), wu = (int)(x >> 16);
-        const int j = (int)(y & 0xFFFFu), wv = (int)(y >> 16);
+        int wu, wv, i2, j2;
+        if (!trace_step<PredT>(v, pred, l, s, wu, wv, i2, j2)) return -1;
         if (l + 1 == v.L - 1) {   // both lists get the edge into the sink level (:684-692)
             if (n1 >= cap || n2 >= cap) return -2;
-            p1[2 * n1] = lo + i; p1[2 * n1 + 1] = mid + i2; ++n1;
-            p2[2 * n2] = lo + j; p2[2 * n2 + 1] = mid + j2; ++n2;
+            p1[2 * n1] = lo + s.i2; p1[2 * n1 + 1] = mid + i2; ++n1;
+            p2[2 * n2] = lo + s.j2; p2[2 * n2 + 1] = mid + j2; ++n2;
         }
-        if (wu > 0) { if (n1 >= cap) return -2; p1[2 * n1] = lo + i; p1[2 * n1 + 1] = mid + i2; ++n1; }
-        if (wv > 0) { if (n2 >= cap) return -2; p2[2 * n2] = lo + j; p2[2 * n2 + 1] = mid + j2; ++n2; }
-        if (v.lvlW[l] > 0) {
-            Transition t;
-            t.k = k; t.k2 = k2; t.W = v.lvlW[l]; t.in_off = nullptr; t.in_edge = nullptr;
-            t.msrc = v.masks + v.msrc_off[l]; t.mdst = v.masks + v.mdst_off[l];
-            s_het += pair_delta(t, i, j, i2, j2, true);
-        }
-        r -= wu + wv; i2 = i; j2 = j;
+        if (wu > 0) { if (n1 >= cap) return -2; p1[2 * n1] = lo + s.i2; p1[2 * n1 + 1] = mid + i2; ++n1; }
+        if (wv > 0) { if (n2 >= cap) return -2; p2[2 * n2] = lo + s.j2; p2[2 * n2 + 1] = mid + j2; ++n2; }
+        if (v.lvlW[l] > 0)
+            s_het += mask_delta(v.lvlW[l], v.masks + v.msrc_off[l], v.masks + v.mdst_off[l], s.i2, s.j2, i2, j2, true);
     }
     *n1_out = n1; *n2_out = n2; *s_het_out = s_het;
     return 0;

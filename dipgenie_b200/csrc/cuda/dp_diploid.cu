@@ -2,17 +2,24 @@
 //
 // Replaces Approximator::diploid_dp_approximation_solver's sweep and edge-list recovery
 // (reference src/approximator.cpp:532-716, :757-785).  Design:
-//   * gather form: one thread per destination cell (r2,i',j') takes the lexicographic max of
-//     (value, -i, -j) over in-edges(i') x in-edges(j') — no locks, no atomics, order-free, and the
+//   * gather form: every destination cell (r2,i',j') takes the first strict maximum over
+//     in-edges(i') x in-edges(j') in ascending source order — no locks, no atomics, order-free, and the
 //     winner is exactly the reference's (:657-659);
-//   * the (R+1) x k x k int32 score layers of two consecutive levels ping-pong between two HBM
-//     buffers that stay L2-resident; only a 2-byte predecessor code per cell is streamed out;
-//   * one persistent cooperative kernel walks all L-1 transitions.  Narrow transitions run on CTA 0
-//     alone (block barrier only); wide ones are spread over P_l CTAs and closed by a monotone-counter
-//     grid barrier (no reset, no last-arriver logic: transition l is complete when the counter reaches
-//     the precomputed prefix sum of arrivals);
-//   * a single-thread traceback kernel turns predecessor codes into the two recombination-edge lists.
+//   * K4 `dip_delta_kernel`: the pair scores of every (e1,e2) in-edge pair of a coloured transition
+//     (:604-624) are evaluated once, fully parallel, into a u16 matrix D_l[e1][e2];
+//   * K5 `dip_sweep_kernel`: one persistent cooperative launch interprets per-CTA task streams
+//     (dp_cell.h: TaskHdr).  Narrow transitions run on CTA 0 alone with both (R+1) x k x k int32 layers in
+//     shared memory and one named barrier per level; wide ones are split by destination row over P CTAs
+//     with the layers in HBM/L2 and closed by a monotone-counter grid barrier.  A producer warp streams
+//     every task's header, in-edge record and matrix rows into a 16-slot shared-memory ring with TMA bulk
+//     copies (cp.async.bulk + mbarrier full/empty pairs), far enough ahead to hide HBM latency;
+//   * only a 2-byte predecessor code per cell is streamed out to HBM;
+//   * K7 traceback: checkpoint every 128 levels; all cells of a checkpoint level walk back to the
+//     previous checkpoint in parallel (`dip_anc_kernel`), one thread hops checkpoint to checkpoint from the
+//     sink cell (`dip_hop_kernel`), the segments of the winning path are walked in parallel
+//     (`dip_seg_kernel`) and concatenated (`dip_merge_kernel`).
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -25,43 +32,27 @@
 namespace dg {
 
 // ---- kernel geometry -------------------------------------------------------------------------
-constexpr int DIP_CT = 480;                    // compute threads per CTA (15 warps; 16 warps total -> 128 regs/thread)
-constexpr int DIP_THREADS = DIP_CT + 32;       // + one producer warp (record prefetch via bulk async copies)
-constexpr int DIP_CELLS_PER_CTA = DIP_CT * 4;
-constexpr int DIP_STAGES = 4;                  // record ring depth
-constexpr int DIP_STAGE_BYTES = 16384;
+constexpr int DIP_NCW = 15;                    // compute warps per CTA (16 warps with the producer: 4 per SM sub-partition, 128 registers each)
+constexpr int DIP_CT = DIP_NCW * 32;           // compute threads per CTA
+constexpr int DIP_THREADS = DIP_CT + 32;       // + one producer warp (task prefetch via bulk async copies)
+constexpr int DIP_NSLOT = 16;                  // task ring depth
+constexpr int DIP_SLOT_BYTES = 4096;
 constexpr int DIP_TILE_CELLS = 16384;          // int32 cells per shared-memory layer tile (x2)
-constexpr int DIP_QUEUE = 8;                   // look-ahead queue of (level, stage) entries
-constexpr size_t DIP_SMEM_BYTES = (size_t)DIP_STAGES * DIP_STAGE_BYTES + 2 * (size_t)DIP_TILE_CELLS * 4 +
-                                  DIP_STAGES * 8 + DIP_QUEUE * 8 + 16;
-
-constexpr uint32_t CTL_WAIT = 1u;     // grid-level wait before the transition
-constexpr uint32_t CTL_ARRIVE = 2u;   // grid-level arrive after the transition
-
-struct __align__(16) LevelCtl {       // MODE_GLOBAL transitions read this instead of a staged record, 64 bytes
-    int32_t voff2;                    // first vertex of level l+1
-    int32_t k, k2, W;
-    int32_t P;
-    uint32_t wait_target;
-    uint32_t flags;
-    int32_t pad0;
-    int64_t msrc_off, mdst_off, pred_off2;
-    int64_t pad1;
-};
-
-struct __align__(16) LevelIdx {       // one per transition, scanned by every CTA's producer lane, 16 bytes
-    int64_t rec_off;                  // byte offset of the packed record (-1: MODE_GLOBAL)
-    uint32_t rec_bytes;
-    uint16_t P;
-    uint16_t mode;
-};
+constexpr size_t DIP_SMEM_BYTES = (size_t)DIP_NSLOT * DIP_SLOT_BYTES + 2 * (size_t)DIP_TILE_CELLS * 4 + 2 * DIP_NSLOT * 8;
+constexpr int DIP_TRACE_T = 128;               // levels between traceback checkpoints
 
 struct SweepArgs {
-    const LevelIdx* idx;
-    const LevelCtl* ctl;
+    const TaskHdr* tasks;
+    const int64_t* task_begin;
     const uint8_t* records;
+    const uint16_t* delta;
+    const int64_t* delta_off;
+    const int32_t* level_off;
     const int32_t* in_off;
     const uint32_t* in_edge;
+    const int32_t* lvlW;
+    const int64_t* msrc_off;
+    const int64_t* mdst_off;
     const uint64_t* masks;
     int32_t* tile0;
     int32_t* tile1;
@@ -70,30 +61,22 @@ struct SweepArgs {
     unsigned long long* level_sum;    // [L] (CHECK only)
     unsigned long long* level_live;   // [L]
     unsigned long long* prof;         // [32] phase cycle counters of CTA 0 / thread 0 (nullable)
-    int32_t l_begin, l_end, R;
-    int32_t pred32, check;
+    int32_t R;
 };
 
 // ---- PTX helpers -----------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void red_release_add_u32(unsigned int* p, unsigned int v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// Spin until the monotone arrival counter reaches `target`.  Polls are relaxed loads (no L1 invalidate
-// per poll) with exponential back-off, so that idle CTAs — most of the grid during a narrow stretch —
-// do not hammer the counter's L2 slice; one acquire fence orders the layer reads after the last poll.
+// Spin until the monotone arrival counter reaches `target`.  Polls are relaxed loads with a short fixed
+// sleep (the pollers are the idle CTAs of a narrow stretch: a few dozen, not a whole grid); one acquire
+// fence orders the layer reads after the last poll.
 __device__ __forceinline__ void wait_counter(const unsigned int* counter, unsigned int target) {
-    unsigned int ns = 32;
     for (;;) {
         unsigned int v;
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
         if (v >= target) break;
-        __nanosleep(ns);
-        if (ns < 2048u) ns <<= 1;
+        __nanosleep(40);
     }
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
@@ -103,6 +86,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -122,254 +108,529 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" ::"n"(DIP_CT) : "memory"); }
 
-// ---- the cell loop ---------------------------------------------------------------------------
+// ---- K4: pair-score matrices -------------------------------------------------------------------
+struct DeltaArgs {
+    const int32_t* delta_list;
+    int32_t n_list;
+    const int32_t* level_off;
+    const int32_t* in_off;
+    const uint32_t* in_edge;
+    const uint16_t* in_dst;
+    const int32_t* lvlW;
+    const int64_t* msrc_off;
+    const int64_t* mdst_off;
+    const uint64_t* masks;
+    const int64_t* delta_off;
+    uint16_t* delta;
+};
+
+// D_l[e1][e2] = |(Hom u1 ∪ Hom v1) ∩ (Hom u2 ∪ Hom v2)| + |(Het u1 ∪ Het v1) △ (Het u2 ∪ Het v2)| for the
+// edge pair e1 = (u1 -> u2), e2 = (v1 -> v2) entering level l+1 (approximator.cpp:604-624), one CTA per
+// coloured transition, all transitions in one launch.
+__global__ void __launch_bounds__(256) dip_delta_kernel(const DeltaArgs a) {
+    for (int t = blockIdx.x; t < a.n_list; t += gridDim.x) {
+        const int l = a.delta_list[t];
+        const int32_t mid = a.level_off[l + 1];
+        const int32_t e0 = a.in_off[mid];
+        const uint32_t n_in = (uint32_t)(a.in_off[a.level_off[l + 2]] - e0);
+        const int W = a.lvlW[l];
+        const uint64_t* msrc = a.masks + a.msrc_off[l];
+        const uint64_t* mdst = a.masks + a.mdst_off[l];
+        uint16_t* D = a.delta + a.delta_off[l];
+        const uint32_t total = n_in * n_in;
+        for (uint32_t x = threadIdx.x; x < total; x += blockDim.x) {
+            const uint32_t e1 = x / n_in, e2 = x - e1 * n_in;
+            const uint32_t ea = __ldg(a.in_edge + e0 + e1), eb = __ldg(a.in_edge + e0 + e2);
+            const int i2 = (int)__ldg(a.in_dst + e0 + e1), j2 = (int)__ldg(a.in_dst + e0 + e2);
+            D[x] = (uint16_t)mask_delta(W, msrc, mdst, (int)(ea & 0xFFFFu), (int)(eb & 0xFFFFu), i2, j2);
+        }
+    }
+}
+
+// ---- K5: the sweep ------------------------------------------------------------------------------
 struct CellIO {
     const int32_t* src;        // source layer (shared or global)
     int32_t* dst;              // destination layer (shared or global)
     uint8_t* pl;               // predecessor codes of the destination level
-    bool src_smem, dst_smem, pred32, check;
+    bool src_smem, dst_smem;
 };
 
-// Work item = (destination pair (i',j'), chunk of RC layers); pairs vary fastest so that the stores of a
-// warp are contiguous in every layer.  SMEM: both layers are shared-memory tiles (the common case inside
-// a narrow stretch) and plain LDS/STS are used; otherwise placement is a run-time flag and HBM layers
-// are read/written with L2-only (.cg) accesses, since other SMs produce and consume them.
-template <class OffT, int RC, bool HAS_MASK, bool SMEM>
-__device__ __forceinline__ void sweep_pairs(const TransitionT<OffT>& t, const CellIO& io, int R, uint64_t first,
-                                            uint64_t stride, unsigned long long& hsum, unsigned long long& hlive) {
-    const uint32_t k2 = (uint32_t)t.k2, npairs = k2 * k2;
+// Work item = (destination pair (i',j'), chunk of RC layers); pairs vary fastest over the threads so that
+// the stores of a warp are contiguous in every layer; when a task has fewer pairs than threads, `groups`
+// thread groups share the pairs and deal the chunks round-robin.  SMEM: both layers are shared-memory
+// tiles (the common case inside a narrow stretch): plain LDS/STS and 32-bit indices; otherwise placement
+// is a run-time flag and HBM layers are read/written with L2-only (.cg) accesses, since other SMs produce
+// and consume them.  CHECK / PRED32 are kernel-level template flags so that the timed kernel carries
+// neither the checksum fold nor the 32-bit code path.
+template <class OffT, int RC, bool MASKS, bool SMEM, bool CHECK, bool PRED32>
+__device__ __forceinline__ void sweep_items(const TransitionT<OffT>& t, const CellIO& io, int R, const TaskHdr& h, int tid,
+                                            unsigned long long& hsum, unsigned long long& hlive) {
+    using IdxT = typename std::conditional<SMEM, int32_t, int64_t>::type;
+    const uint32_t k2 = h.k2, npairs = (uint32_t)(h.i1 - h.i0) * k2;
     const uint32_t nchunk = (uint32_t)(R + RC) / RC;
-    const uint64_t nitems = (uint64_t)npairs * nchunk;
+    const uint32_t groups = h.groups;
+    uint32_t g = 0, p = (uint32_t)tid;
+    if (groups > 1) {
+        g = h.m_pairs ? div_magic((uint32_t)tid, h.m_pairs) : (uint32_t)tid;
+        p = (uint32_t)tid - g * npairs;
+        if (g >= groups) return;
+    }
     const int32_t* __restrict__ src = io.src;
     const bool ssm = io.src_smem;
-    auto load = [src, ssm](int64_t idx) -> int32_t {
+    auto load = [src, ssm](IdxT idx) -> int32_t {
         if (SMEM) return src[idx];
         return ssm ? src[idx] : __ldcg(src + idx);
     };
-    for (uint64_t x = first; x < nitems; x += stride) {
-        uint32_t chunk, pair;
-        if (nitems <= 0xFFFFFFFFull) { chunk = (uint32_t)x / npairs; pair = (uint32_t)x - chunk * npairs; }
-        else { chunk = (uint32_t)(x / npairs); pair = (uint32_t)(x - (uint64_t)chunk * npairs); }
-        const uint32_t i2 = pair / k2, j2 = pair - i2 * k2;
-        const int r0 = (int)chunk * RC;
-        uint64_t best[RC];
-        uint32_t code[RC];
-        relax_pair<RC, HAS_MASK>(t, load, R, r0, (int)i2, (int)j2, best, code);
+    const IdxT kk2 = (IdxT)k2 * (IdxT)k2;
+    for (uint32_t pair = p; pair < npairs; pair += DIP_CT) {
+        const uint32_t ir = h.m_k2 ? div_magic(pair, h.m_k2) : pair;
+        const uint32_t j2 = pair - ir * k2, i2 = (uint32_t)h.i0 + ir;
+        const IdxT cell0 = (IdxT)i2 * (IdxT)k2 + (IdxT)j2;
+        for (uint32_t chunk = g; chunk < nchunk; chunk += groups) {
+            const int r0 = (int)chunk * RC;
+            int32_t best[RC];
+            uint32_t code[RC];
+            relax_pair<RC, MASKS, IdxT>(t, load, R, r0, (int)i2, (int)j2, best, code);
 #pragma unroll
-        for (int rr = 0; rr < RC; ++rr) {
-            const int r2 = r0 + rr;
-            if (r2 <= R) {
-                const uint64_t c = (uint64_t)r2 * npairs + pair;
-                const uint64_t key = best[rr];
-                const int32_t v = key_value(key);
-                if (SMEM || io.dst_smem) io.dst[c] = v; else __stcg(io.dst + c, v);
-                if (io.pred32) reinterpret_cast<uint32_t*>(io.pl)[c] = key ? code[rr] : 0xFFFFFFFFu;
-                else reinterpret_cast<uint16_t*>(io.pl)[c] = key ? (uint16_t)(((code[rr] >> 16) << 8) | (code[rr] & 0xFFu)) : (uint16_t)0xFFFFu;
-                if (io.check && key) {
-                    ++hlive;
-                    hsum += cell_fold(c, v, 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+            for (int rr = 0; rr < RC; ++rr) {
+                const int r2 = r0 + rr;
+                if (r2 <= R) {
+                    const IdxT c = (IdxT)r2 * kk2 + cell0;
+                    const bool live = best[rr] >= 0;
+                    const int32_t v = live ? best[rr] : NEG_INF;
+                    if (SMEM || io.dst_smem) io.dst[c] = v; else __stcg(io.dst + c, v);
+                    if (PRED32) reinterpret_cast<uint32_t*>(io.pl)[c] = code[rr];
+                    else reinterpret_cast<uint16_t*>(io.pl)[c] = (uint16_t)(((code[rr] >> 16) << 8) | (code[rr] & 0xFFu));   // dead: 0xFFFF
+                    if (CHECK && live) {
+                        const int pi = (int)(t.in_edge[(int32_t)t.in_off[i2] + (int32_t)(code[rr] >> 16)] & 0xFFFFu);
+                        const int pj = (int)(t.in_edge[(int32_t)t.in_off[j2] + (int32_t)(code[rr] & 0xFFFFu)] & 0xFFFFu);
+                        ++hlive;
+                        hsum += cell_fold((uint64_t)c, v, pi, pj);
+                    }
                 }
             }
         }
     }
 }
 
-template <class OffT, bool SMEM>
-__device__ __forceinline__ void sweep_dispatch(const TransitionT<OffT>& t, const CellIO& io, int R, uint64_t first,
-                                               uint64_t stride, uint64_t nthreads, unsigned long long& hsum,
-                                               unsigned long long& hlive) {
-    const int rc = choose_rc((uint64_t)t.k2 * t.k2, R, nthreads);
-    if (t.W > 0) {
-        switch (rc) {
-            case 8: sweep_pairs<OffT, 8, true, SMEM>(t, io, R, first, stride, hsum, hlive); break;
-            case 4: sweep_pairs<OffT, 4, true, SMEM>(t, io, R, first, stride, hsum, hlive); break;
-            case 2: sweep_pairs<OffT, 2, true, SMEM>(t, io, R, first, stride, hsum, hlive); break;
-            default: sweep_pairs<OffT, 1, true, SMEM>(t, io, R, first, stride, hsum, hlive); break;
+template <class OffT, bool MASKS, bool SMEM, bool CHECK, bool PRED32>
+__device__ __forceinline__ void sweep_rc(const TransitionT<OffT>& t, const CellIO& io, int R, const TaskHdr& h, int tid,
+                                         unsigned long long& hsum, unsigned long long& hlive) {
+    sweep_items<OffT, DIP_RC, MASKS, SMEM, CHECK, PRED32>(t, io, R, h, tid, hsum, hlive);
+}
+
+template <class OffT, bool SMEM, bool CHECK, bool PRED32>
+__device__ __forceinline__ void sweep_dm(const TransitionT<OffT>& t, const CellIO& io, int R, const TaskHdr& h, int tid,
+                                         unsigned long long& hsum, unsigned long long& hlive) {
+    if (!SMEM && (h.flags & TK_DELTA_MASKS)) sweep_rc<OffT, true, false, CHECK, PRED32>(t, io, R, h, tid, hsum, hlive);
+    else sweep_rc<OffT, false, SMEM, CHECK, PRED32>(t, io, R, h, tid, hsum, hlive);
+}
+
+// ---- the lane form, written against 32-bit shared-window addresses --------------------------------
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int32_t lds_s32(uint32_t a) { int32_t v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_s32(uint32_t a, int32_t v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+__device__ __forceinline__ int32_t ldcg_s32(const int32_t* p) { return __ldcg(p); }
+
+// Lane form of a task (dp_cell.h).  SMEM: both layers are shared-memory tiles of this CTA (32-bit shared-window
+// addresses, LDS/STS only); otherwise both layers are in HBM/L2 (ld/st.global.cg: other SMs produce and consume
+// them).  The record and the staged rows of the pair-score matrix always sit in the task slot.
+struct LaneTask {
+    uint32_t sb32;           // slot base (shared window)
+    uint32_t src32, dst32;   // SMEM: tile addresses
+    const int32_t* gsrc;     // !SMEM: layers in global memory
+    int32_t* gdst;
+    uint8_t* pl;
+    uint32_t k, k2, i0, i1, n_in, rec_bytes, skew, nblk, rp, nrg, m_nblk, m_nrg, m_nin, n_witems, rounds, bstart_off;
+    bool staged;
+};
+
+struct LaneProf { unsigned long long items, setup, loop, reduce, store, iters; };
+
+template <int RC, bool SMEM, bool CHECK, bool PRED32, bool PROF>
+__device__ __forceinline__ void lane_task(const LaneTask& t, int R, int warp, int lane,
+                                          unsigned long long& hsum, unsigned long long& hlive, LaneProf& lp) {
+    const uint32_t off32 = t.sb32 + (uint32_t)sizeof(TaskHdr);
+    const uint32_t edge32 = off32 + (uint32_t)rec_edge_offset((int)t.k2);
+    const uint32_t dstp32 = off32 + (uint32_t)rec_dst_offset((int)t.k2, t.n_in);
+    const uint32_t bst32 = off32 + t.bstart_off;
+    const uint32_t k = t.k, k2 = t.k2, n_in = t.n_in;
+    const uint32_t kk = k * k, kk2 = k2 * k2;
+    // lane -> (row slot, in-edge within the block)
+    uint32_t rs = 0, el = (uint32_t)lane;
+    if (t.nblk == 1) {
+        rs = t.m_nin ? __umulhi((uint32_t)lane, t.m_nin) : (uint32_t)lane;
+        el = (uint32_t)lane - rs * n_in;
+    }
+    uint32_t delta32 = 0;
+    if (t.staged) delta32 = off32 + t.rec_bytes + 2u * t.skew - 2u * lds_u16(off32 + 2u * t.i0) * n_in;   // row of in-edge e1 at + 2*e1*n_in
+    for (uint32_t wi = (uint32_t)warp; wi < t.n_witems; wi += DIP_NCW) {
+        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        if (PROF) c0 = clock64();
+        const uint32_t q = t.m_nblk ? __umulhi(wi, t.m_nblk) : wi;
+        const uint32_t b = wi - q * t.nblk;
+        const uint32_t chunk = t.m_nrg ? __umulhi(q, t.m_nrg) : q;
+        const uint32_t rg = q - chunk * t.nrg;
+        const uint32_t bs = lds_u16(bst32 + 2u * b), be = lds_u16(bst32 + 2u * b + 2u);
+        const uint32_t row = t.i0 + rg * t.rp + rs, e2 = bs + el;
+        const bool valid = rs < t.rp && row < t.i1 && e2 < be;
+        const uint32_t rowc = valid ? row : t.i0, e2c = valid ? e2 : bs;
+        const uint32_t a0 = lds_u16(off32 + 2u * rowc);
+        uint32_t a1 = lds_u16(off32 + 2u * rowc + 2u);
+        if (!valid) a1 = a0;
+        const uint32_t y = lds_u32(edge32 + 4u * e2c);
+        const uint32_t j2 = lds_u16(dstp32 + 2u * e2c);
+        const uint32_t s0 = lds_u16(off32 + 2u * j2), s1 = lds_u16(off32 + 2u * j2 + 2u);
+        const uint32_t pos = e2c - s0, seg = s1 - s0;
+        const uint32_t j = y & 0xFFFFu;
+        const int wv = (int)(y >> 16);
+        const int r0 = (int)chunk * RC;
+        int32_t best[RC];
+        uint32_t code[RC];
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) { best[rr] = -1; code[rr] = 0xFFFFFFFFu; }
+        if (PROF) c1 = clock64();
+        for (uint32_t e1 = a0; e1 < a1; ++e1) {
+            if (PROF) ++lp.iters;
+            const uint32_t x = lds_u32(edge32 + 4u * e1);
+            const uint32_t base = (x & 0xFFFFu) * k + j;
+            const int w = (int)(x >> 16) + wv;
+            int d = 0;
+            if (t.staged) d = (int)lds_u16(delta32 + 2u * (e1 * n_in + e2c));
+            const uint32_t cd = ((e1 - a0) << 16) | pos;
+            // loads in batches of LB independent accesses (layer index clamped into [0,R]; validity gates the compare)
+            constexpr int LB = (RC % 10 == 0) ? 10 : ((RC % 8 == 0) ? 8 : RC);
+#pragma unroll
+            for (int b0 = 0; b0 < RC; b0 += LB) {
+                int32_t v[LB];
+#pragma unroll
+                for (int q = 0; q < LB; ++q) {
+                    int r = r0 + b0 + q - w;
+                    r = r < 0 ? 0 : (r > R ? R : r);
+                    if (SMEM) v[q] = lds_s32(t.src32 + 4u * ((uint32_t)r * kk + base));
+                    else v[q] = ldcg_s32(t.gsrc + ((size_t)r * kk + base));
+                }
+#pragma unroll
+                for (int q = 0; q < LB; ++q) {
+                    const int rr = b0 + q;
+                    const bool ok = (r0 + rr - w >= 0) && (r0 + rr <= R);
+                    const int32_t c = v[q] + d;
+                    if (ok && c > best[rr]) { best[rr] = c; code[rr] = cd; }
+                }
+            }
         }
-    } else {
-        switch (rc) {
-            case 8: sweep_pairs<OffT, 8, false, SMEM>(t, io, R, first, stride, hsum, hlive); break;
-            case 4: sweep_pairs<OffT, 4, false, SMEM>(t, io, R, first, stride, hsum, hlive); break;
-            case 2: sweep_pairs<OffT, 2, false, SMEM>(t, io, R, first, stride, hsum, hlive); break;
-            default: sweep_pairs<OffT, 1, false, SMEM>(t, io, R, first, stride, hsum, hlive); break;
+        if (PROF) c2 = clock64();
+        // segmented maximum over the lanes of one destination column: value desc, then code asc
+        for (uint32_t rd = 0, off = 1; rd < t.rounds; ++rd, off <<= 1) {
+            const bool partner = pos + off < seg;
+#pragma unroll
+            for (int rr = 0; rr < RC; ++rr) {
+                const int32_t ob = __shfl_down_sync(0xFFFFFFFFu, best[rr], off);
+                const uint32_t oc = __shfl_down_sync(0xFFFFFFFFu, code[rr], off);
+                if (partner && (ob > best[rr] || (ob == best[rr] && oc < code[rr]))) { best[rr] = ob; code[rr] = oc; }
+            }
         }
+        if (PROF) c3 = clock64();
+        if (valid && pos == 0) {
+            const uint32_t cell0 = row * k2 + j2;
+#pragma unroll
+            for (int rr = 0; rr < RC; ++rr) {
+                const int r2 = r0 + rr;
+                if (r2 <= R) {
+                    const bool live = best[rr] >= 0;
+                    const int32_t val = live ? best[rr] : NEG_INF;
+                    size_t c;
+                    if (SMEM) { const uint32_t c32 = (uint32_t)r2 * kk2 + cell0; sts_s32(t.dst32 + 4u * c32, val); c = c32; }
+                    else { c = (size_t)r2 * kk2 + cell0; __stcg(t.gdst + c, val); }
+                    if (PRED32) reinterpret_cast<uint32_t*>(t.pl)[c] = code[rr];
+                    else reinterpret_cast<uint16_t*>(t.pl)[c] = (uint16_t)(((code[rr] >> 16) << 8) | (code[rr] & 0xFFu));   // dead: 0xFFFF
+                    if (CHECK && live) {
+                        const int pi = (int)(lds_u32(edge32 + 4u * (a0 + (code[rr] >> 16))) & 0xFFFFu);
+                        const int pj = (int)(lds_u32(edge32 + 4u * (s0 + (code[rr] & 0xFFFFu))) & 0xFFFFu);
+                        ++hlive;
+                        hsum += cell_fold((uint64_t)c, val, pi, pj);
+                    }
+                }
+            }
+        }
+        if (PROF) { const long long c4 = clock64(); lp.items += 1; lp.setup += c1 - c0; lp.loop += c2 - c1; lp.reduce += c3 - c2; lp.store += c4 - c3; }
     }
 }
 
-// Producer lane state: scans the level index for this CTA's next transitions, issues the bulk copies
-// of their records into free ring stages and publishes (level, stage) entries in the look-ahead queue.
-struct Producer {
-    int pf;            // scan cursor (level)
-    int n_written;     // queue entries published so far
-    int n_issued;      // records issued so far
-    bool ended;
-};
+// The pair form (everything the lane form does not take): layers in HBM/L2 (or a hand-over between the two placements),
+// records staged or read in place, pair scores staged / in place / popcounted on the fly.  Kept out of line
+// so that the narrow loop gets its own register allocation and stays small.
+template <bool CHECK, bool PRED32>
+__device__ __noinline__ ulonglong2 generic_task(const SweepArgs& a, const uint8_t* sb, int32_t* tileS0, int32_t* tileS1, int tid) {
+    unsigned long long hsum = 0, hlive = 0;
+    const TaskHdr h = *reinterpret_cast<const TaskHdr*>(sb);
+    const uint32_t rec_bytes = h.rec_bytes;
+    CellIO io;
+    io.pl = reinterpret_cast<uint8_t*>(a.pred) + ((size_t)h.pred_off2 << (PRED32 ? 2 : 1));
+    io.src_smem = (h.flags & TK_SRC_SMEM) != 0; io.dst_smem = (h.flags & TK_DST_SMEM) != 0;
+    const int l = h.level;
+    const uint32_t flags = h.flags;
+    const bool ssm = io.src_smem, dsm = io.dst_smem;
+    io.src = ssm ? ((l & 1) ? tileS1 : tileS0) : ((l & 1) ? a.tile1 : a.tile0);
+    io.dst = dsm ? ((l & 1) ? tileS0 : tileS1) : ((l & 1) ? a.tile0 : a.tile1);
+    if (!(flags & TK_REC_GLOBAL)) {
+        TransitionT<uint16_t> tr;
+        tr.k = h.k; tr.k2 = h.k2;
+        tr.in_off = reinterpret_cast<const uint16_t*>(sb + sizeof(TaskHdr));
+        tr.in_edge = reinterpret_cast<const uint32_t*>(sb + sizeof(TaskHdr) + rec_edge_offset(h.k2));
+        tr.delta = nullptr; tr.dstride = h.n_in; tr.e1_base = 0; tr.e2_base = 0;
+        tr.W = 0; tr.msrc = nullptr; tr.mdst = nullptr;
+        if (flags & TK_DELTA_STAGED) {
+            tr.delta = reinterpret_cast<const uint16_t*>(sb + sizeof(TaskHdr) + rec_bytes) + h.delta_skew;
+            tr.e1_base = (int32_t)tr.in_off[h.i0];
+        } else if (flags & TK_DELTA) {
+            tr.delta = a.delta + __ldg(a.delta_off + l);
+        } else if (flags & TK_DELTA_MASKS) {
+            tr.W = __ldg(a.lvlW + l); tr.msrc = a.masks + __ldg(a.msrc_off + l); tr.mdst = a.masks + __ldg(a.mdst_off + l);
+        }
+        sweep_dm<uint16_t, false, CHECK, PRED32>(tr, io, a.R, h, tid, hsum, hlive);
+    } else {
+        const int32_t mid = __ldg(a.level_off + l + 1);
+        const int32_t ebase = __ldg(a.in_off + mid);
+        TransitionT<int32_t> tr;
+        tr.k = h.k; tr.k2 = h.k2;
+        tr.in_off = a.in_off + mid;
+        tr.in_edge = a.in_edge;
+        tr.delta = nullptr; tr.dstride = __ldg(a.in_off + __ldg(a.level_off + l + 2)) - ebase;
+        tr.e1_base = ebase; tr.e2_base = ebase;
+        tr.W = 0; tr.msrc = nullptr; tr.mdst = nullptr;
+        if (flags & TK_DELTA) tr.delta = a.delta + __ldg(a.delta_off + l);
+        else if (flags & TK_DELTA_MASKS) {
+            tr.W = __ldg(a.lvlW + l); tr.msrc = a.masks + __ldg(a.msrc_off + l); tr.mdst = a.masks + __ldg(a.mdst_off + l);
+        }
+        sweep_dm<int32_t, false, CHECK, PRED32>(tr, io, a.R, h, tid, hsum, hlive);
+    }
+    return make_ulonglong2(hsum, hlive);
+}
 
+template <bool CHECK, bool PRED32, bool PROF>
 __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* const stage_base = smem;
-    int32_t* const tileS0 = reinterpret_cast<int32_t*>(smem + (size_t)DIP_STAGES * DIP_STAGE_BYTES);
+    uint8_t* const slots = smem;
+    int32_t* const tileS0 = reinterpret_cast<int32_t*>(smem + (size_t)DIP_NSLOT * DIP_SLOT_BYTES);
     int32_t* const tileS1 = tileS0 + DIP_TILE_CELLS;
-    uint64_t* const mbar = reinterpret_cast<uint64_t*>(tileS1 + DIP_TILE_CELLS);
-    int2* const queue = reinterpret_cast<int2*>(mbar + DIP_STAGES);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(tileS1 + DIP_TILE_CELLS);
+    uint64_t* const empty = full + DIP_NSLOT;
 
-    const int cta = blockIdx.x, tid = threadIdx.x;
-    const bool is_compute = tid < DIP_CT;
-    const bool is_producer = tid == DIP_CT;          // lane 0 of the extra warp
+    const int cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int32_t n = (int32_t)(a.task_begin[cta + 1] - a.task_begin[cta]);
+    const TaskHdr* const my_tasks = a.tasks + a.task_begin[cta];
     uint8_t* const pred = reinterpret_cast<uint8_t*>(a.pred);
-    const int pshift = a.pred32 ? 2 : 1;
+    constexpr int pshift = PRED32 ? 2 : 1;
 
     if (tid == 0) {
-        for (int s = 0; s < DIP_STAGES; ++s) mbar_init(smem_u32(mbar + s), 1);
+        for (int s = 0; s < DIP_NSLOT; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), DIP_NCW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int x = tid; x <= a.R; x += DIP_THREADS) tileS0[x] = 0;   // level 0: all R+1 layers start at 0 (approximator.cpp:535)
     __syncthreads();
 
-    Producer pr;
-    pr.pf = a.l_begin; pr.n_written = 0; pr.n_issued = 0; pr.ended = false;
-    auto produce = [&](int t_cur, int rec_consumed) {
-        // publish entries for iterations < t_cur + DIP_QUEUE - 1, as far as ring stages are free
-        while (!pr.ended && pr.n_written < t_cur + DIP_QUEUE - 1) {
-            while (pr.pf < a.l_end && cta >= (int)__ldg(&a.idx[pr.pf].P)) ++pr.pf;
-            if (pr.pf >= a.l_end) {
-                queue[pr.n_written % DIP_QUEUE] = make_int2(-1, -1);
-                ++pr.n_written; pr.ended = true;
-                break;
+    if (tid >= DIP_CT) {
+        // ---- producer warp: lanes fetch 32 task descriptors at a time, lane 0 issues the copies ----
+        for (int32_t t0 = 0; t0 < n; t0 += 32) {
+            uint4 f = make_uint4(0u, 0u, 0u, 0u);
+            if (t0 + lane < n) f = __ldg(reinterpret_cast<const uint4*>(my_tasks + t0 + lane));
+            const int cnt = min(32, n - t0);
+            for (int j = 0; j < cnt; ++j) {
+                const uint32_t rec_off16 = __shfl_sync(0xFFFFFFFFu, f.x, j), rec_bytes = __shfl_sync(0xFFFFFFFFu, f.y, j);
+                const uint32_t d_off16 = __shfl_sync(0xFFFFFFFFu, f.z, j), d_bytes = __shfl_sync(0xFFFFFFFFu, f.w, j);
+                if (lane == 0) {
+                    const int32_t t = t0 + j;
+                    const int slot = t % DIP_NSLOT, use = t / DIP_NSLOT;
+                    if (use > 0) mbar_wait(smem_u32(empty + slot), (uint32_t)((use - 1) & 1));
+                    const uint32_t bar = smem_u32(full + slot);
+                    const uint32_t dst = smem_u32(slots + (size_t)slot * DIP_SLOT_BYTES);
+                    mbar_expect_tx(bar, (uint32_t)sizeof(TaskHdr) + rec_bytes + d_bytes);
+                    bulk_g2s(dst, my_tasks + t, (uint32_t)sizeof(TaskHdr), bar);
+                    if (rec_bytes) bulk_g2s(dst + (uint32_t)sizeof(TaskHdr), a.records + (size_t)rec_off16 * 16, rec_bytes, bar);
+                    if (d_bytes) bulk_g2s(dst + (uint32_t)sizeof(TaskHdr) + rec_bytes, reinterpret_cast<const uint8_t*>(a.delta) + (size_t)d_off16 * 16, d_bytes, bar);
+                }
             }
-            const int4 raw = __ldg(reinterpret_cast<const int4*>(a.idx + pr.pf));
-            LevelIdx li;
-            memcpy(&li, &raw, sizeof li);
-            int stage = -1;
-            if (li.rec_off >= 0) {
-                if (pr.n_issued - rec_consumed >= DIP_STAGES) break;      // ring full: retry after the next level
-                stage = pr.n_issued % DIP_STAGES;
-                const uint32_t bar = smem_u32(mbar + stage);
-                mbar_expect_tx(bar, li.rec_bytes);
-                bulk_g2s(smem_u32(stage_base + (size_t)stage * DIP_STAGE_BYTES), a.records + li.rec_off, li.rec_bytes, bar);
-                ++pr.n_issued;
-            }
-            queue[pr.n_written % DIP_QUEUE] = make_int2(pr.pf, stage);
-            ++pr.n_written; ++pr.pf;
         }
-    };
-    if (is_producer) produce(0, 0);
+        return;
+    }
 
-    int t = 0, rc = 0;                               // iteration index, records consumed so far
-    const bool profiling = a.prof != nullptr && cta == 0 && tid == 0;
-    unsigned long long pc[24];
-    if (profiling) for (int x = 0; x < 24; ++x) pc[x] = 0;
-    long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0;
-    for (;;) {
+    // ---- compute warps ----
+    const bool profiling = PROF && cta == 0 && tid == 0;
+    unsigned long long pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0, pc4 = 0, pc5 = 0, pc6 = 0, pc7 = 0, pc8 = 0, pc9 = 0;
+    long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0;
+    LaneProf lp = {0, 0, 0, 0, 0, 0};
+    for (int32_t t = 0; t < n; ++t) {
+        const int slot = t % DIP_NSLOT;
+        const uint8_t* const sb = slots + (size_t)slot * DIP_SLOT_BYTES;
         if (profiling) tk0 = clock64();
-        __syncthreads();                             // iteration t-1 complete: its layer is whole, its stage is free
+        mbar_wait(smem_u32(full + slot), (uint32_t)((t / DIP_NSLOT) & 1));
         if (profiling) tk1 = clock64();
-        const int2 e = queue[t % DIP_QUEUE];
-        const int l = e.x, stage = e.y;
-        if (l < 0) break;
-        if (is_producer) produce(t + 1, rc);
-        if (is_compute) {
-            unsigned long long hsum = 0, hlive = 0;
-            if (stage >= 0) {
-                const uint8_t* rec = stage_base + (size_t)stage * DIP_STAGE_BYTES;
-                mbar_wait(smem_u32(mbar + stage), (uint32_t)((rc / DIP_STAGES) & 1));
-                if (profiling) tk2 = clock64();
-                RecHeader h;
-                TransitionT<uint16_t> tr;
-                record_view(rec, h, tr);
-                if (h.flags & REC_WAIT) {
-                    if (tid == 0) wait_counter(a.counter, h.wait_target);
-                    bar_compute();
-                }
-                if (profiling) tk3 = clock64();
-                const bool ssm = (h.flags & REC_SRC_SMEM) != 0, dsm = (h.flags & REC_DST_SMEM) != 0;
-                CellIO io;
-                io.src = ssm ? ((l & 1) ? tileS1 : tileS0) : ((l & 1) ? a.tile1 : a.tile0);
-                io.dst = dsm ? ((l & 1) ? tileS0 : tileS1) : ((l & 1) ? a.tile0 : a.tile1);
-                io.pl = pred + ((size_t)h.pred_off2 << pshift);
-                io.src_smem = ssm; io.dst_smem = dsm; io.pred32 = a.pred32 != 0; io.check = a.check != 0;
-                const uint64_t first = (uint64_t)cta * DIP_CT + tid, stride = (uint64_t)h.P * DIP_CT;
-                if (ssm && dsm) {
-                    CellIO ios = io;
-                    ios.src = (l & 1) ? tileS1 : tileS0;
-                    ios.dst = (l & 1) ? tileS0 : tileS1;
-                    sweep_dispatch<uint16_t, true>(tr, ios, a.R, first, stride, stride, hsum, hlive);
+        // exec part of the header (16-byte shared loads; the lane-form words only when needed)
+        const uint4 h1 = reinterpret_cast<const uint4*>(sb)[1], h2 = reinterpret_cast<const uint4*>(sb)[2];
+        const uint32_t flags = h1.y;
+        const int l = (int)h1.x;
+        if (flags & TK_WAIT) {
+            if (tid == 0) wait_counter(a.counter, h1.z);
+            bar_compute();
+        }
+        if (profiling) tk2 = clock64();
+        unsigned long long hsum = 0, hlive = 0;
+        const bool ssm = (flags & TK_SRC_SMEM) != 0, dsm = (flags & TK_DST_SMEM) != 0;
+        if ((uint32_t)(tid & ~31) < h2.w) {          // this warp owns work of the task
+            if (flags & TK_LANES) {
+                const uint4 h0 = reinterpret_cast<const uint4*>(sb)[0], h3 = reinterpret_cast<const uint4*>(sb)[3],
+                            h4 = reinterpret_cast<const uint4*>(sb)[4], h5 = reinterpret_cast<const uint4*>(sb)[5];
+                LaneTask lt;
+                lt.sb32 = smem_u32(sb);
+                const uint32_t tiles32 = smem_u32(tileS0);
+                lt.src32 = tiles32 + ((l & 1) ? (uint32_t)DIP_TILE_CELLS * 4u : 0u);
+                lt.dst32 = tiles32 + ((l & 1) ? 0u : (uint32_t)DIP_TILE_CELLS * 4u);
+                lt.gsrc = (l & 1) ? a.tile1 : a.tile0;
+                lt.gdst = (l & 1) ? a.tile0 : a.tile1;
+                const unsigned long long pred_off2 = ((unsigned long long)h3.y << 32) | h3.x;
+                lt.pl = pred + ((size_t)pred_off2 << pshift);
+                lt.k = h2.x & 0xFFFFu; lt.k2 = h2.x >> 16; lt.i0 = h2.y & 0xFFFFu; lt.i1 = h2.y >> 16; lt.n_in = h2.z;
+                lt.rec_bytes = h0.y; lt.skew = h1.w;
+                lt.nblk = h4.y & 0xFFFFu; lt.rp = h4.y >> 16; lt.nrg = h4.z; lt.m_nblk = h4.w;
+                lt.m_nrg = h5.x; lt.m_nin = h5.y; lt.n_witems = h5.z; lt.rounds = h5.w;
+                lt.bstart_off = reinterpret_cast<const uint32_t*>(sb)[24];
+                lt.staged = (flags & TK_DELTA_STAGED) != 0;
+                const bool big = (h4.x & 0xFFFFu) == (uint32_t)LANE_RC_BIG;
+                if (ssm) {
+                    if (big) lane_task<LANE_RC_BIG, true, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
+                    else lane_task<LANE_RC_SMALL, true, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
                 } else {
-                    sweep_dispatch<uint16_t, false>(tr, io, a.R, first, stride, stride, hsum, hlive);
-                }
-                if (profiling) tk4 = clock64();
-                if (h.flags & REC_ARRIVE) {
-                    bar_compute();
-                    if (tid == 0) red_release_add_u32(a.counter, 1u);
-                }
-                if (profiling) {
-                    tk5 = clock64();
-                    const int m = (ssm || dsm) ? 0 : 1;       // 0: shared-memory layers, 1: staged record + HBM layers
-                    pc[m * 6 + 0] += 1; pc[m * 6 + 1] += tk1 - tk0; pc[m * 6 + 2] += tk2 - tk1;
-                    pc[m * 6 + 3] += tk3 - tk2; pc[m * 6 + 4] += tk4 - tk3; pc[m * 6 + 5] += tk5 - tk4;
+                    if (big) lane_task<LANE_RC_BIG, false, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
+                    else lane_task<LANE_RC_SMALL, false, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
                 }
             } else {
-                if (profiling) tk2 = clock64();
-                const LevelCtl* __restrict__ cg = a.ctl + l;
-                const uint32_t flags = __ldg(&cg->flags);
-                if (flags & CTL_WAIT) {
-                    if (tid == 0) wait_counter(a.counter, __ldg(&cg->wait_target));
-                    bar_compute();
-                }
-                if (profiling) tk3 = clock64();
-                Transition tr;
-                tr.k = __ldg(&cg->k); tr.k2 = __ldg(&cg->k2); tr.W = __ldg(&cg->W);
-                tr.in_off = a.in_off + __ldg(&cg->voff2);
-                tr.in_edge = a.in_edge;
-                tr.msrc = a.masks + __ldg(&cg->msrc_off);
-                tr.mdst = a.masks + __ldg(&cg->mdst_off);
-                CellIO io;
-                io.src = (l & 1) ? a.tile1 : a.tile0;
-                io.dst = (l & 1) ? a.tile0 : a.tile1;
-                io.pl = pred + ((size_t)__ldg(&cg->pred_off2) << pshift);
-                io.src_smem = false; io.dst_smem = false; io.pred32 = a.pred32 != 0; io.check = a.check != 0;
-                const uint64_t first = (uint64_t)cta * DIP_CT + tid, stride = (uint64_t)__ldg(&cg->P) * DIP_CT;
-                sweep_dispatch<int32_t, false>(tr, io, a.R, first, stride, stride, hsum, hlive);
-                if (profiling) tk4 = clock64();
-                if (flags & CTL_ARRIVE) {
-                    bar_compute();
-                    if (tid == 0) red_release_add_u32(a.counter, 1u);
-                }
-                if (profiling) {
-                    tk5 = clock64();
-                    pc[12] += 1; pc[13] += tk1 - tk0; pc[14] += tk2 - tk1; pc[15] += tk3 - tk2; pc[16] += tk4 - tk3; pc[17] += tk5 - tk4;
-                }
-            }
-            if (a.check) {
-                for (int o = 16; o > 0; o >>= 1) {
-                    hsum += __shfl_down_sync(0xFFFFFFFFu, hsum, o);
-                    hlive += __shfl_down_sync(0xFFFFFFFFu, hlive, o);
-                }
-                if ((tid & 31) == 0 && hlive) {
-                    atomicAdd(a.level_sum + l + 1, hsum);
-                    atomicAdd(a.level_live + l + 1, hlive);
-                }
+                const ulonglong2 hs = generic_task<CHECK, PRED32>(a, sb, tileS0, tileS1, tid);
+                hsum = hs.x; hlive = hs.y;
             }
         }
-        if (stage >= 0) ++rc;
-        ++t;
+        if (profiling) tk3 = clock64();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(empty + slot));    // this warp is done with the slot
+        if (flags & TK_BAR) bar_compute();                     // the destination rows of this CTA are whole
+        if ((flags & TK_ARRIVE) && tid == 0) red_release_add_u32(a.counter, 1u);
+        if (profiling) {
+            tk4 = clock64();
+            if (ssm || dsm) { pc0 += 1; pc1 += tk1 - tk0; pc2 += tk2 - tk1; pc3 += tk3 - tk2; pc4 += tk4 - tk3; }
+            else { pc5 += 1; pc6 += tk1 - tk0; pc7 += tk2 - tk1; pc8 += tk3 - tk2; pc9 += tk4 - tk3; }
+        }
+        if (CHECK) {
+            for (int o = 16; o > 0; o >>= 1) {
+                hsum += __shfl_down_sync(0xFFFFFFFFu, hsum, o);
+                hlive += __shfl_down_sync(0xFFFFFFFFu, hlive, o);
+            }
+            if (lane == 0 && hlive) {
+                atomicAdd(a.level_sum + l + 1, hsum);
+                atomicAdd(a.level_live + l + 1, hlive);
+            }
+        }
     }
-    if (profiling) for (int x = 0; x < 24; ++x) a.prof[x] = pc[x];
+    if (profiling) {
+        a.prof[0] = pc0; a.prof[1] = pc1; a.prof[2] = pc2; a.prof[3] = pc3; a.prof[4] = pc4; a.prof[5] = 0;
+        a.prof[6] = pc5; a.prof[7] = pc6; a.prof[8] = pc7; a.prof[9] = pc8; a.prof[10] = pc9; a.prof[11] = 0;
+        a.prof[12] = lp.items; a.prof[13] = lp.setup; a.prof[14] = lp.loop; a.prof[15] = lp.reduce; a.prof[16] = lp.store; a.prof[17] = lp.iters;
+    }
 }
 
+// ---- K7: traceback ------------------------------------------------------------------------------
 struct TraceOut {           // device-side result block
     int32_t rc, value, s_het, n1, n2, pad[3];
 };
 
+struct TraceArgs {
+    TraceView v;
+    const void* pred;
+    const int32_t* cp;        // [M+1] checkpoint levels, cp[0] = L-1 (sink level), descending, cp[M] = 0
+    const int64_t* aoff;      // [M+1] prefix of (R+1)*k^2 over checkpoint levels cp[0..M-1]
+    int32_t M;
+    int32_t* anc;             // [aoff[M]] flat cell at cp[m+1] that cell x of cp[m] descends from (-1: dead)
+    int32_t* path_cell;       // [M] cell of the winning path at cp[m] (-1: dead)
+    int32_t* seg_p1;          // [M][2*cap]
+    int32_t* seg_p2;
+    int32_t* seg_n;           // [M][4]: n1, n2, s_het, rc
+    const int32_t* sink_tile;
+    int cap;
+    TraceOut* out;
+    int32_t* p1;
+    int32_t* p2;
+};
+
+DG_HD void cell_to_state(int64_t cell, int32_t k, TraceState& s) {
+    const int64_t kk = (int64_t)k * k;
+    s.r = (int32_t)(cell / kk);
+    const int32_t rem = (int32_t)(cell - (int64_t)s.r * kk);
+    s.i2 = rem / k; s.j2 = rem - s.i2 * k;
+}
+
 template <class PredT>
-__global__ void dip_traceback_kernel(TraceView v, const PredT* pred, const int32_t* sink_tile, int cap,
-                                     TraceOut* out, int32_t* p1, int32_t* p2) {
+__global__ void __launch_bounds__(256) dip_anc_kernel(const TraceArgs a) {
+    const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.aoff[a.M]) return;
+    int lo = 0, hi = a.M - 1;                 // largest m with aoff[m] <= x
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.aoff[mid] <= x) lo = mid; else hi = mid - 1; }
+    const int m = lo;
+    const int l_hi = a.cp[m], l_lo = a.cp[m + 1];
+    TraceState s;
+    cell_to_state(x - a.aoff[m], a.v.level_off[l_hi + 1] - a.v.level_off[l_hi], s);
+    const PredT* pred = reinterpret_cast<const PredT*>(a.pred);
+    bool live = true;
+    for (int l = l_hi - 1; l >= l_lo && live; --l) {
+        int wu, wv, i2, j2;
+        live = trace_step<PredT>(a.v, pred, l, s, wu, wv, i2, j2);
+    }
+    const int32_t k = a.v.level_off[l_lo + 1] - a.v.level_off[l_lo];
+    a.anc[x] = live ? (int32_t)(((int64_t)s.r * k + s.i2) * k + s.j2) : -1;
+}
+
+__global__ void dip_hop_kernel(const TraceArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const int64_t ks = v.level_off[v.L] - v.level_off[v.L - 1];
-    const int32_t value = __ldcg(sink_tile + (int64_t)v.R * ks * ks);   // cell (r=R,0,0) of the last level (:730, :775)
-    int32_t n1 = 0, n2 = 0, s_het = 0;
-    const int rc = traceback<PredT>(v, pred, value, p1, &n1, p2, &n2, cap, &s_het);
-    out->rc = rc; out->value = value; out->s_het = s_het; out->n1 = n1; out->n2 = n2;
+    const int64_t ks = a.v.level_off[a.v.L] - a.v.level_off[a.v.L - 1];
+    const int32_t value = __ldcg(a.sink_tile + (int64_t)a.v.R * ks * ks);   // cell (r=R,0,0) of the last level (:730, :775)
+    a.out->value = value;
+    int64_t cur = (value == NEG_INF) ? -1 : (int64_t)a.v.R * ks * ks;
+    for (int m = 0; m < a.M; ++m) {
+        a.path_cell[m] = (int32_t)cur;
+        if (cur >= 0) cur = a.anc[a.aoff[m] + cur];
+    }
+}
+
+template <class PredT>
+__global__ void __launch_bounds__(128) dip_seg_kernel(const TraceArgs a) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= a.M) return;
+    int32_t* sn = a.seg_n + 4 * m;
+    sn[0] = sn[1] = sn[2] = 0; sn[3] = -1;
+    const int32_t cell = a.path_cell[m];
+    if (cell < 0) return;
+    const int l_hi = a.cp[m], l_lo = a.cp[m + 1];
+    TraceState s;
+    cell_to_state(cell, a.v.level_off[l_hi + 1] - a.v.level_off[l_hi], s);
+    int32_t n1 = 0, n2 = 0, sh = 0;
+    const int rc = trace_segment<PredT>(a.v, reinterpret_cast<const PredT*>(a.pred), l_hi, l_lo, s,
+                                        a.seg_p1 + (size_t)m * 2 * a.cap, &n1, a.seg_p2 + (size_t)m * 2 * a.cap, &n2, a.cap, &sh);
+    sn[0] = n1; sn[1] = n2; sn[2] = sh; sn[3] = rc;
+}
+
+__global__ void dip_merge_kernel(const TraceArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int n1 = 0, n2 = 0, sh = 0, rc = 0;
+    for (int m = 0; m < a.M && rc == 0; ++m) {      // m = 0 is nearest the sink: lists come out newest-first
+        const int32_t* sn = a.seg_n + 4 * m;
+        if (sn[3] != 0) { rc = sn[3]; break; }
+        if (n1 + sn[0] > a.cap || n2 + sn[1] > a.cap) { rc = -2; break; }
+        for (int x = 0; x < 2 * sn[0]; ++x) a.p1[2 * n1 + x] = a.seg_p1[(size_t)m * 2 * a.cap + x];
+        for (int x = 0; x < 2 * sn[1]; ++x) a.p2[2 * n2 + x] = a.seg_p2[(size_t)m * 2 * a.cap + x];
+        n1 += sn[0]; n2 += sn[1]; sh += sn[2];
+    }
+    if (rc == -1) { n1 = 0; n2 = 0; sh = 0; }
+    a.out->rc = rc; a.out->s_het = sh; a.out->n1 = n1; a.out->n2 = n2;
 }
 
 }  // namespace dg
@@ -380,11 +641,17 @@ struct dg_dip {
     DipPlan plan;                 // host copy (small arrays kept for stats; big ones released after upload)
     int pred_bytes = 2;
     int grid = 1;
-    DevBuf<LevelCtl> ctl;
-    DevBuf<LevelIdx> idx;
+    int M = 0;                    // traceback segments
+    int64_t anc_cells = 0;
+    DevBuf<TaskHdr> tasks;
+    DevBuf<int64_t> task_begin;
     DevBuf<uint8_t> records;
+    DevBuf<uint16_t> delta;
+    DevBuf<int64_t> delta_off;
+    DevBuf<int32_t> delta_list;
     DevBuf<int32_t> level_off, in_off, lvlW;
     DevBuf<uint32_t> in_edge;
+    DevBuf<uint16_t> in_dst;
     DevBuf<uint64_t> masks;
     DevBuf<int64_t> msrc_off, mdst_off, pred_off;
     DevBuf<int32_t> tile0, tile1;
@@ -392,105 +659,133 @@ struct dg_dip {
     DevBuf<unsigned int> counter;
     DevBuf<unsigned long long> level_sum, level_live, prof;
     bool want_prof = false;
+    DevBuf<int32_t> cp, anc, path_cell, seg_p1, seg_p2, seg_n;
+    DevBuf<int64_t> aoff;
     DevBuf<TraceOut> tout;
     DevBuf<int32_t> p1, p2;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
-    float sweep_ms = 0.f, trace_ms = 0.f;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float delta_ms = 0.f, sweep_ms = 0.f, trace_ms = 0.f, plan_ms = 0.f, upload_ms = 0.f;
     int launches = 0;
     bool ran = false, checks = false;
     uint64_t device_bytes = 0;
     ~dg_dip() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
 };
 
+static const void* sweep_fn(bool pred32, bool check, bool prof = false) {
+    if (prof && !check) return pred32 ? (const void*)dip_sweep_kernel<false, true, true> : (const void*)dip_sweep_kernel<false, false, true>;
+    if (pred32) return check ? (const void*)dip_sweep_kernel<true, true, false> : (const void*)dip_sweep_kernel<false, true, false>;
+    return check ? (const void*)dip_sweep_kernel<true, false, false> : (const void*)dip_sweep_kernel<false, false, false>;
+}
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out) {
     *out = nullptr;
     DG_CUDA(ctx, cudaSetDevice(ctx->device));
     std::unique_ptr<dg_dip> d(new dg_dip());
+    const double t_plan0 = now_ms();
     if (!build_dip_plan(g, d->plan)) return fail(ctx, DG_ERR_ARG, "dg_dip_create: %s", d->plan.error.c_str());
     DipPlan& p = d->plan;
     const int L = p.L;
     d->pred_bytes = (p.max_indeg <= 255) ? 2 : 4;
 
-    // grid: enough CTAs for the widest transition, at most one co-resident wave (cooperative launch)
-    const void* fnc = (const void*)dip_sweep_kernel;
-    DG_CUDA(ctx, cudaFuncSetAttribute(fnc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
+    // grid: enough CTAs that the widest transition leaves about 16 candidates per thread, at most one
+    // co-resident wave (cooperative launch)
+    const void* fnc = sweep_fn(d->pred_bytes == 4, false);
+    for (int v = 0; v < 8; ++v)
+        DG_CUDA(ctx, cudaFuncSetAttribute(sweep_fn(v & 1, v & 2, v & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
     int per_sm = 0;
     DG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fnc, DIP_THREADS, DIP_SMEM_BYTES));
     if (per_sm < 1) return fail(ctx, DG_ERR_CUDA, "dg_dip_create: sweep kernel cannot be resident");
     int max_grid = ctx->sm_count * per_sm;
-    if (const char* e = getenv("DG_DIP_MAX_GRID")) max_grid = std::max(1, std::min(max_grid, atoi(e)));   // diagnostics
-    const uint64_t widest = (uint64_t)(p.R + 1) * (uint64_t)p.kmax * (uint64_t)p.kmax;
-    const uint64_t want = (widest + DIP_CELLS_PER_CTA - 1) / DIP_CELLS_PER_CTA;
+    uint64_t widest_cand = 0;
+    for (int l = 0; l + 1 < L; ++l) {
+        const uint64_t n_in = (uint64_t)(p.in_off[p.level_off[l + 2]] - p.in_off[p.level_off[l + 1]]);
+        widest_cand = std::max(widest_cand, (uint64_t)(p.R + 1) * n_in * n_in);
+    }
+    uint64_t want = (widest_cand + (uint64_t)DIP_CT * 16 - 1) / ((uint64_t)DIP_CT * 16);
+    if (const char* e = getenv("DG_DIP_GRID")) want = (uint64_t)std::max(1, atoi(e));   // diagnostics / tuning
     SweepShape shape;
     shape.grid = (int)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)max_grid);
-    shape.cells_per_cta = DIP_CELLS_PER_CTA;
+    shape.threads = DIP_CT;
     shape.tile_cells = DIP_TILE_CELLS;
-    shape.stage_bytes = DIP_STAGE_BYTES;
-    plan_sweep(p, shape);
-    int gmax = 1;
-    for (int l = 0; l + 1 < L; ++l) gmax = std::max(gmax, p.P[l]);
-    d->grid = gmax;
+    shape.slot_bytes = DIP_SLOT_BYTES;
+    if (const char* e = getenv("DG_LANE_RC")) shape.lane_rc = atoi(e);   // diagnostics / tuning
+    size_t free_b = 0, total_b = 0;
+    DG_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    shape.delta_budget = (int64_t)(free_b / 8);
+    plan_tasks(p, shape);
+    d->grid = 1;
+    for (int c = 0; c < p.grid; ++c) if (p.task_begin[(size_t)c + 1] > p.task_begin[c]) d->grid = c + 1;
 
-    std::vector<LevelCtl> ctl((size_t)std::max(L - 1, 1));
-    std::vector<LevelIdx> idx((size_t)std::max(L - 1, 1));
-    memset(ctl.data(), 0, ctl.size() * sizeof(LevelCtl));
-    memset(idx.data(), 0, idx.size() * sizeof(LevelIdx));
-    for (int l = 0; l + 1 < L; ++l) {
-        LevelCtl& c = ctl[l];
-        c.voff2 = p.level_off[l + 1];
-        c.k = p.level_off[l + 1] - p.level_off[l];
-        c.k2 = p.level_off[l + 2] - p.level_off[l + 1];
-        c.W = p.lvlW[l];
-        c.P = p.P[l];
-        c.flags = 0;
-        if (p.flags[l] & REC_WAIT) { c.flags |= CTL_WAIT; c.wait_target = p.bar_target[l - 1]; }
-        if (p.flags[l] & REC_ARRIVE) c.flags |= CTL_ARRIVE;
-        c.msrc_off = p.msrc_off[l]; c.mdst_off = p.mdst_off[l]; c.pred_off2 = p.pred_off[l + 1];
-        LevelIdx& x = idx[l];
-        x.rec_off = p.rec_off[l];
-        x.rec_bytes = 0;
-        if (p.rec_off[l] >= 0) {
-            RecHeader h;
-            memcpy(&h, p.records.data() + p.rec_off[l], sizeof h);
-            x.rec_bytes = h.bytes;
-        }
-        x.P = (uint16_t)p.P[l];
-        x.mode = p.mode[l];
+    // traceback checkpoints: cp[0] = sink level, every DIP_TRACE_T levels down to level 0
+    std::vector<int32_t> cp;
+    std::vector<int64_t> aoff;
+    for (int l = L - 1; l > 0; l -= DIP_TRACE_T) cp.push_back(l);
+    cp.push_back(0);
+    d->M = (int)cp.size() - 1;
+    aoff.assign((size_t)d->M + 1, 0);
+    for (int m = 0; m < d->M; ++m) {
+        const int64_t k = p.level_off[cp[m] + 1] - p.level_off[cp[m]];
+        aoff[(size_t)m + 1] = aoff[m] + (int64_t)(p.R + 1) * k * k;
     }
+    d->anc_cells = aoff[d->M];
+    d->plan_ms = (float)(now_ms() - t_plan0);
 
+    const double t_up0 = now_ms();
     cudaStream_t s = ctx->stream;
-    DG_CUDA(ctx, d->ctl.upload(ctl.data(), ctl.size(), s));
-    DG_CUDA(ctx, d->idx.upload(idx.data(), idx.size(), s));
+    DG_CUDA(ctx, d->tasks.upload(p.tasks.data(), p.tasks.size(), s));
+    DG_CUDA(ctx, d->task_begin.upload(p.task_begin.data(), p.task_begin.size(), s));
     DG_CUDA(ctx, d->records.upload(p.records.data(), p.records.size(), s));
+    DG_CUDA(ctx, d->delta.alloc((size_t)p.delta_elems, s));
+    DG_CUDA(ctx, d->delta_off.upload(p.delta_off.data(), p.delta_off.size(), s));
+    DG_CUDA(ctx, d->delta_list.upload(p.delta_list.data(), p.delta_list.size(), s));
     DG_CUDA(ctx, d->level_off.upload(p.level_off.data(), p.level_off.size(), s));
     DG_CUDA(ctx, d->in_off.upload(p.in_off.data(), p.in_off.size(), s));
     DG_CUDA(ctx, d->in_edge.upload(p.in_edge.data(), p.in_edge.size(), s));
+    DG_CUDA(ctx, d->in_dst.upload(p.in_dst.data(), p.in_dst.size(), s));
     DG_CUDA(ctx, d->lvlW.upload(p.lvlW.data(), p.lvlW.size(), s));
     DG_CUDA(ctx, d->masks.upload(p.masks.data(), p.masks.size(), s));
     DG_CUDA(ctx, d->msrc_off.upload(p.msrc_off.data(), p.msrc_off.size(), s));
     DG_CUDA(ctx, d->mdst_off.upload(p.mdst_off.data(), p.mdst_off.size(), s));
     DG_CUDA(ctx, d->pred_off.upload(p.pred_off.data(), p.pred_off.size(), s));
+    DG_CUDA(ctx, d->cp.upload(cp.data(), cp.size(), s));
+    DG_CUDA(ctx, d->aoff.upload(aoff.data(), aoff.size(), s));
+    const uint64_t widest = (uint64_t)(p.R + 1) * (uint64_t)p.kmax * (uint64_t)p.kmax;
     const size_t tile = (size_t)std::max<uint64_t>(widest, (uint64_t)(p.R + 1));
-    DG_CUDA(ctx, d->tile0.alloc(tile));
-    DG_CUDA(ctx, d->tile1.alloc(tile));
-    DG_CUDA(ctx, d->pred.alloc((size_t)p.pred_off[L] * (size_t)d->pred_bytes));
-    DG_CUDA(ctx, d->counter.alloc(1));
-    DG_CUDA(ctx, d->level_sum.alloc((size_t)L));
-    DG_CUDA(ctx, d->level_live.alloc((size_t)L));
-    DG_CUDA(ctx, d->prof.alloc(32));
-    DG_CUDA(ctx, d->tout.alloc(1));
-    DG_CUDA(ctx, d->p1.alloc((size_t)2 * (p.R + 2)));
-    DG_CUDA(ctx, d->p2.alloc((size_t)2 * (p.R + 2)));
+    DG_CUDA(ctx, d->tile0.alloc(tile, s));
+    DG_CUDA(ctx, d->tile1.alloc(tile, s));
+    DG_CUDA(ctx, d->pred.alloc((size_t)p.pred_off[L] * (size_t)d->pred_bytes, s));
+    DG_CUDA(ctx, d->counter.alloc(1, s));
+    DG_CUDA(ctx, d->level_sum.alloc((size_t)L, s));
+    DG_CUDA(ctx, d->level_live.alloc((size_t)L, s));
+    DG_CUDA(ctx, d->prof.alloc(32, s));
+    DG_CUDA(ctx, d->anc.alloc((size_t)d->anc_cells, s));
+    DG_CUDA(ctx, d->path_cell.alloc((size_t)std::max(d->M, 1), s));
+    const size_t cap = (size_t)p.R + 2;
+    DG_CUDA(ctx, d->seg_p1.alloc((size_t)std::max(d->M, 1) * 2 * cap, s));
+    DG_CUDA(ctx, d->seg_p2.alloc((size_t)std::max(d->M, 1) * 2 * cap, s));
+    DG_CUDA(ctx, d->seg_n.alloc((size_t)std::max(d->M, 1) * 4, s));
+    DG_CUDA(ctx, d->tout.alloc(1, s));
+    DG_CUDA(ctx, d->p1.alloc(2 * cap, s));
+    DG_CUDA(ctx, d->p2.alloc(2 * cap, s));
     for (auto& e : d->ev) DG_CUDA(ctx, cudaEventCreate(&e));
     DG_CUDA(ctx, cudaStreamSynchronize(s));
-    d->device_bytes = d->idx.bytes() + d->records.bytes() + d->ctl.bytes() + d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->lvlW.bytes() +
-                      d->masks.bytes() + d->msrc_off.bytes() + d->mdst_off.bytes() + d->pred_off.bytes() + d->tile0.bytes() +
-                      d->tile1.bytes() + d->pred.bytes() + d->level_sum.bytes() + d->level_live.bytes();
+    d->upload_ms = (float)(now_ms() - t_up0);
+    d->device_bytes = d->tasks.bytes() + d->task_begin.bytes() + d->records.bytes() + d->delta.bytes() + d->delta_off.bytes() +
+                      d->delta_list.bytes() + d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->in_dst.bytes() +
+                      d->lvlW.bytes() + d->masks.bytes() + d->msrc_off.bytes() + d->mdst_off.bytes() + d->pred_off.bytes() +
+                      d->tile0.bytes() + d->tile1.bytes() + d->pred.bytes() + d->level_sum.bytes() + d->level_live.bytes() +
+                      d->anc.bytes() + d->seg_p1.bytes() + d->seg_p2.bytes();
     // the big host arrays are no longer needed
     std::vector<uint32_t>().swap(p.in_edge);
+    std::vector<uint16_t>().swap(p.in_dst);
     std::vector<uint8_t>().swap(p.records);
     std::vector<uint64_t>().swap(p.masks);
     std::vector<int32_t>().swap(p.in_off);
+    std::vector<TaskHdr>().swap(p.tasks);
     *out = d.release();
     return DG_OK;
 }
@@ -507,33 +802,59 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
         DG_CUDA(ctx, cudaMemsetAsync(d->level_live.p, 0, (size_t)p.L * 8, s));
         DG_CUDA(ctx, cudaStreamSynchronize(s));   // basis is a stack-lifetime staging buffer
     }
+    d->launches = 0;
+    DG_CUDA(ctx, cudaEventRecord(d->ev[0], s));
+    if (!p.delta_list.empty()) {
+        DeltaArgs da;
+        da.delta_list = d->delta_list.p; da.n_list = (int32_t)p.delta_list.size(); da.level_off = d->level_off.p;
+        da.in_off = d->in_off.p; da.in_edge = d->in_edge.p; da.in_dst = d->in_dst.p; da.lvlW = d->lvlW.p;
+        da.msrc_off = d->msrc_off.p; da.mdst_off = d->mdst_off.p; da.masks = d->masks.p; da.delta_off = d->delta_off.p;
+        da.delta = d->delta.p;
+        const int blocks = (int)std::min<size_t>(p.delta_list.size(), (size_t)ctx->sm_count * 16);
+        dip_delta_kernel<<<blocks, 256, 0, s>>>(da);
+        ++d->launches;
+        DG_CUDA(ctx, cudaGetLastError());
+    }
+    DG_CUDA(ctx, cudaEventRecord(d->ev[1], s));
     SweepArgs a;
-    a.idx = d->idx.p; a.records = d->records.p;
-    a.ctl = d->ctl.p; a.in_off = d->in_off.p; a.in_edge = d->in_edge.p; a.masks = d->masks.p;
+    a.tasks = d->tasks.p; a.task_begin = d->task_begin.p; a.records = d->records.p; a.delta = d->delta.p;
+    a.delta_off = d->delta_off.p; a.level_off = d->level_off.p; a.in_off = d->in_off.p; a.in_edge = d->in_edge.p;
+    a.lvlW = d->lvlW.p; a.msrc_off = d->msrc_off.p; a.mdst_off = d->mdst_off.p; a.masks = d->masks.p;
     a.tile0 = d->tile0.p; a.tile1 = d->tile1.p; a.pred = d->pred.p; a.counter = d->counter.p;
     a.level_sum = d->level_sum.p; a.level_live = d->level_live.p;
     a.prof = d->want_prof ? d->prof.p : nullptr;
-    a.l_begin = 0; a.l_end = p.L - 1; a.R = p.R;
-    a.pred32 = sizeof(PredT) == 4 ? 1 : 0; a.check = check ? 1 : 0;
-    d->launches = 0;
-    DG_CUDA(ctx, cudaEventRecord(d->ev[0], s));
+    a.R = p.R;
     if (p.L > 1) {
         void* args[] = {(void*)&a};
-        const void* fn = (const void*)dip_sweep_kernel;
+        const void* fn = sweep_fn(sizeof(PredT) == 4, check, d->want_prof);
         DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, s));
         ++d->launches;
     }
-    DG_CUDA(ctx, cudaEventRecord(d->ev[1], s));
-    TraceView v;
+    DG_CUDA(ctx, cudaEventRecord(d->ev[2], s));
+    TraceArgs ta;
+    TraceView& v = ta.v;
     v.L = p.L; v.R = p.R; v.level_off = d->level_off.p; v.in_off = d->in_off.p; v.in_edge = d->in_edge.p;
     v.lvlW = d->lvlW.p; v.msrc_off = d->msrc_off.p; v.mdst_off = d->mdst_off.p; v.masks = d->masks.p;
     v.pred_off = d->pred_off.p;
-    const int32_t* sink_tile = ((p.L - 1) & 1) ? d->tile1.p : d->tile0.p;
-    dip_traceback_kernel<PredT><<<1, 32, 0, s>>>(v, reinterpret_cast<const PredT*>(d->pred.p), sink_tile, p.R + 2,
-                                                 d->tout.p, d->p1.p, d->p2.p);
+    ta.pred = d->pred.p; ta.cp = d->cp.p; ta.aoff = d->aoff.p; ta.M = d->M; ta.anc = d->anc.p; ta.path_cell = d->path_cell.p;
+    ta.seg_p1 = d->seg_p1.p; ta.seg_p2 = d->seg_p2.p; ta.seg_n = d->seg_n.p;
+    ta.sink_tile = ((p.L - 1) & 1) ? d->tile1.p : d->tile0.p;
+    ta.cap = p.R + 2; ta.out = d->tout.p; ta.p1 = d->p1.p; ta.p2 = d->p2.p;
+    if (d->anc_cells > 0) {
+        const unsigned blocks = (unsigned)((d->anc_cells + 255) / 256);
+        dip_anc_kernel<PredT><<<blocks, 256, 0, s>>>(ta);
+        ++d->launches;
+    }
+    dip_hop_kernel<<<1, 32, 0, s>>>(ta);
+    ++d->launches;
+    if (d->M > 0) {
+        dip_seg_kernel<PredT><<<(d->M + 127) / 128, 128, 0, s>>>(ta);
+        ++d->launches;
+    }
+    dip_merge_kernel<<<1, 32, 0, s>>>(ta);
     ++d->launches;
     DG_CUDA(ctx, cudaGetLastError());
-    DG_CUDA(ctx, cudaEventRecord(d->ev[2], s));
+    DG_CUDA(ctx, cudaEventRecord(d->ev[3], s));
     d->ran = true; d->checks = check;
     return DG_OK;
 }
@@ -570,8 +891,9 @@ int dg_dip_result(dg_ctx* ctx, dg_dip* d, int32_t* sink_value, int32_t* sink_s_h
     DG_CUDA(ctx, cudaMemcpyAsync(a.data(), d->p1.p, a.size() * 4, cudaMemcpyDeviceToHost, s));
     DG_CUDA(ctx, cudaMemcpyAsync(b.data(), d->p2.p, b.size() * 4, cudaMemcpyDeviceToHost, s));
     DG_CUDA(ctx, cudaStreamSynchronize(s));
-    DG_CUDA(ctx, cudaEventElapsedTime(&d->sweep_ms, d->ev[0], d->ev[1]));
-    DG_CUDA(ctx, cudaEventElapsedTime(&d->trace_ms, d->ev[1], d->ev[2]));
+    DG_CUDA(ctx, cudaEventElapsedTime(&d->delta_ms, d->ev[0], d->ev[1]));
+    DG_CUDA(ctx, cudaEventElapsedTime(&d->sweep_ms, d->ev[1], d->ev[2]));
+    DG_CUDA(ctx, cudaEventElapsedTime(&d->trace_ms, d->ev[2], d->ev[3]));
     if (t.rc == -2) return fail(ctx, DG_ERR_CAPACITY, "dg_dip_result: more than R+2 recorded edges on a path");
     if (sink_value) *sink_value = t.value;
     if (sink_s_het) *sink_s_het = t.s_het;
@@ -600,6 +922,10 @@ int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out) {
     out->max_indegree = d->plan.max_indeg; out->mask_words_max = d->plan.Wmax; out->grid_ctas = d->grid;
     out->pred_bytes = d->pred_bytes; out->launches = d->launches;
     out->sweep_ms = d->sweep_ms; out->traceback_ms = d->trace_ms;
+    out->delta_ms = d->delta_ms; out->plan_ms = d->plan_ms; out->upload_ms = d->upload_ms;
+    out->n_narrow = (int32_t)d->plan.n_narrow; out->n_wide = (int32_t)d->plan.n_wide;
+    out->n_tasks = (int64_t)d->plan.task_begin.back();
+    out->delta_bytes = (uint64_t)d->plan.delta_elems * 2;
     (void)ctx;
     return DG_OK;
 }
@@ -608,6 +934,7 @@ int dg_dip_profile(dg_ctx* ctx, dg_dip* d, uint64_t* out24) {
     if (!ctx || !d || !d->ran || !d->want_prof) return fail(ctx, DG_ERR_ARG, "dg_dip_profile: run with flags bit1 first");
     DG_CUDA(ctx, cudaSetDevice(ctx->device));
     DG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memset(out24, 0, 24 * 8);
     DG_CUDA(ctx, cudaMemcpy(out24, d->prof.p, 24 * 8, cudaMemcpyDeviceToHost));
     return DG_OK;
 }
@@ -622,11 +949,20 @@ int dg_dp_diploid(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off, const
                   const uint8_t* colour_is_hom, int32_t n_colours, int32_t R, int32_t* sink_value,
                   int32_t* sink_s_het, int32_t* p1_edges, int32_t* n_p1, int32_t* p2_edges, int32_t* n_p2) {
     dg_dip* d = nullptr;
+    const bool timing = getenv("DG_TIMING") != nullptr;     // diagnostics: phase times of the one-shot call on stderr
+    const double t0 = now_ms();
     int rc = dg_dip_create(ctx, n_levels, level_off, adj_off, adj_dst, adj_w, col_off, col_val, colour_is_hom, n_colours, R, &d);
     if (rc) return rc;
+    const double t1 = now_ms();
     rc = dg_dip_run(ctx, d, 0);
+    const double t2 = now_ms();
     if (!rc) rc = dg_dip_result(ctx, d, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2);
+    const double t3 = now_ms();
+    const float plan_ms = d->plan_ms, upload_ms = d->upload_ms, sweep_ms = d->sweep_ms, trace_ms = d->trace_ms;
     dg_dip_destroy(ctx, d);
+    if (timing)
+        fprintf(stderr, "dg_dp_diploid: create %.1f ms (plan %.1f, alloc+upload %.1f) launch %.1f wait+result %.1f (sweep %.1f trace %.1f) destroy %.1f\n",
+                t1 - t0, plan_ms, upload_ms, t2 - t1, t3 - t2, sweep_ms, trace_ms, now_ms() - t3);
     return rc;
 }
 

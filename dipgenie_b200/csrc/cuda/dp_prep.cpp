@@ -1,10 +1,27 @@
-// dp_prep.cpp — see dp_prep.h.
+// dp_prep.cpp — see dp_prep.h.  Levels are independent for everything but a few prefix sums, so the
+// planner runs level-parallel on the host cores (OpenMP; compiles and runs serially without it).
 #include "dp_prep.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
+
 namespace dg {
+
+namespace {
+int n_threads() {
+#if defined(_OPENMP)
+    return std::max(1, std::min(omp_get_max_threads(), 32));
+#else
+    return 1;
+#endif
+}
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+}  // namespace
 
 bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
     p = DipPlan();
@@ -24,73 +41,118 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
         p.kmax = std::max(p.kmax, k);
     }
     if (g.adj_off[0] != 0) { p.error = "adj_off[0] must be 0"; return false; }
+    const int NT = n_threads();
+    (void)NT;
+    std::atomic<int> bad(0);      // 1 adj_off, 2 edge span, 3 colour id
 
     // ---- in-edge CSR (gather form of approximator.cpp:640-649) ----
+    // the in-edges of level l+1 come from level l only: counting and filling are level-parallel
     p.in_off.assign((size_t)V + 1, 0);
     const int64_t E = g.adj_off[V];
+    uint64_t cell_updates = 0;
+#pragma omp parallel for schedule(static) num_threads(NT) reduction(+ : cell_updates)
     for (int l = 0; l < L; ++l) {
         const int32_t lo = p.level_off[l], hi = p.level_off[l + 1];
         const int32_t nlo = (l + 1 < L) ? p.level_off[l + 1] : V, nhi = (l + 1 < L) ? p.level_off[l + 2] : V;
         uint64_t El = 0;
         for (int32_t u = lo; u < hi; ++u) {
-            if (g.adj_off[u + 1] < g.adj_off[u]) { p.error = "adj_off not monotone"; return false; }
+            if (g.adj_off[u + 1] < g.adj_off[u]) { bad = 1; break; }
             El += (uint64_t)(g.adj_off[u + 1] - g.adj_off[u]);
             for (int64_t e = g.adj_off[u]; e < g.adj_off[u + 1]; ++e) {
                 const int32_t v = g.adj_dst[e];
-                if (v < nlo || v >= nhi) { p.error = "edge does not span exactly one level"; return false; }
+                if (v < nlo || v >= nhi) { bad = 2; break; }
                 ++p.in_off[(size_t)v + 1];
             }
         }
-        if (l + 1 < L) p.cell_updates += (uint64_t)(g.R + 1) * El * El;
+        if (l + 1 < L) cell_updates += (uint64_t)(g.R + 1) * El * El;
     }
+    if (bad == 1) { p.error = "adj_off not monotone"; return false; }
+    if (bad == 2) { p.error = "edge does not span exactly one level"; return false; }
+    p.cell_updates = cell_updates;
     for (int32_t v = 0; v < V; ++v) {
         p.max_indeg = std::max(p.max_indeg, p.in_off[(size_t)v + 1]);
         p.in_off[(size_t)v + 1] += p.in_off[v];
     }
     p.n_in = E;
     p.in_edge.assign((size_t)E, 0);
+    p.in_dst.assign((size_t)E, 0);
     {
         std::vector<int32_t> fill(p.in_off.begin(), p.in_off.end() - 1);
-        for (int l = 0; l + 1 < L; ++l) {
+#pragma omp parallel for schedule(static) num_threads(NT)
+        for (int l = 0; l < L - 1; ++l) {
             const int32_t lo = p.level_off[l], hi = p.level_off[l + 1];
             for (int32_t u = lo; u < hi; ++u)
-                for (int64_t e = g.adj_off[u]; e < g.adj_off[u + 1]; ++e)
-                    p.in_edge[(size_t)fill[g.adj_dst[e]]++] = (uint32_t)(u - lo) | ((uint32_t)g.adj_w[e] << IN_W_SHIFT);
+                for (int64_t e = g.adj_off[u]; e < g.adj_off[u + 1]; ++e) {
+                    const int32_t v = g.adj_dst[e];
+                    const size_t slot = (size_t)fill[v]++;
+                    p.in_edge[slot] = (uint32_t)(u - lo) | ((uint32_t)g.adj_w[e] << IN_W_SHIFT);
+                    p.in_dst[slot] = (uint16_t)(v - hi);
+                }
         }
     }
 
     // ---- per-transition colour masks (approximator.cpp:431-453 + :269-311 as popcounts) ----
+    // pass 1: size of the local colour universe of every transition; prefix; pass 2: fill
     p.lvlW.assign(L, 0); p.msrc_off.assign(L, 0); p.mdst_off.assign(L, 0);
-    std::vector<int32_t> local(g.n_colours > 0 ? g.n_colours : 1, -1);
-    std::vector<int32_t> uni;
-    for (int l = 0; l + 1 < L; ++l) {
-        const int32_t lo = p.level_off[l], mid = p.level_off[l + 1], hi = p.level_off[l + 2];
-        if (g.col_off[hi] == g.col_off[lo]) continue;   // no colours on either level
-        uni.clear();
-        for (int64_t c = g.col_off[lo]; c < g.col_off[hi]; ++c) {
-            const int32_t col = g.col_val[c];
-            if (col < 0 || col >= g.n_colours) { p.error = "colour id out of range"; return false; }
-            if (local[col] < 0) { local[col] = 0; uni.push_back(col); }
-        }
-        std::sort(uni.begin(), uni.end());
-        for (size_t x = 0; x < uni.size(); ++x) local[uni[x]] = (int32_t)x;
-        const int W = (int)((uni.size() + 63) / 64);
-        p.lvlW[l] = W; p.Wmax = std::max(p.Wmax, W);
-        p.msrc_off[l] = (int64_t)p.masks.size();
-        p.masks.resize(p.masks.size() + (size_t)(mid - lo) * 2 * W, 0);
-        p.mdst_off[l] = (int64_t)p.masks.size();
-        p.masks.resize(p.masks.size() + (size_t)(hi - mid) * 2 * W, 0);
-        for (int32_t v = lo; v < hi; ++v) {
-            uint64_t* m = (v < mid) ? &p.masks[(size_t)p.msrc_off[l] + (size_t)(v - lo) * 2 * W]
-                                    : &p.masks[(size_t)p.mdst_off[l] + (size_t)(v - mid) * 2 * W];
-            for (int64_t c = g.col_off[v]; c < g.col_off[v + 1]; ++c) {
+    const size_t ncol = (size_t)(g.n_colours > 0 ? g.n_colours : 1);
+    int Wmax = 0;
+#pragma omp parallel num_threads(NT) reduction(max : Wmax)
+    {
+        std::vector<int32_t> seen(ncol, -1);
+#pragma omp for schedule(static)
+        for (int l = 0; l < L - 1; ++l) {
+            const int32_t lo = p.level_off[l], hi = p.level_off[l + 2];
+            if (g.col_off[hi] == g.col_off[lo]) continue;   // no colours on either level
+            int n = 0;
+            for (int64_t c = g.col_off[lo]; c < g.col_off[hi]; ++c) {
                 const int32_t col = g.col_val[c];
-                const int b = local[col];
-                const int half = (g.colour_is_hom[col] == 1) ? 0 : W;   // hom words first, then het
-                m[half + (b >> 6)] |= 1ull << (b & 63);
+                if (col < 0 || col >= g.n_colours) { bad = 3; break; }
+                if (seen[col] != l) { seen[col] = l; ++n; }
             }
+            const int W = (n + 63) / 64;
+            p.lvlW[l] = W;
+            Wmax = std::max(Wmax, W);
         }
-        for (int32_t col : uni) local[col] = -1;
+    }
+    if (bad == 3) { p.error = "colour id out of range"; return false; }
+    p.Wmax = Wmax;
+    size_t words = 0;
+    for (int l = 0; l + 1 < L; ++l) {
+        const size_t W = (size_t)p.lvlW[l];
+        if (!W) continue;
+        const int32_t lo = p.level_off[l], mid = p.level_off[l + 1], hi = p.level_off[l + 2];
+        p.msrc_off[l] = (int64_t)words; words += (size_t)(mid - lo) * 2 * W;
+        p.mdst_off[l] = (int64_t)words; words += (size_t)(hi - mid) * 2 * W;
+    }
+    p.masks.assign(words, 0);
+#pragma omp parallel num_threads(NT)
+    {
+        std::vector<int32_t> local(ncol, -1);
+        std::vector<int32_t> uni;
+#pragma omp for schedule(static)
+        for (int l = 0; l < L - 1; ++l) {
+            const int W = p.lvlW[l];
+            if (!W) continue;
+            const int32_t lo = p.level_off[l], mid = p.level_off[l + 1], hi = p.level_off[l + 2];
+            uni.clear();
+            for (int64_t c = g.col_off[lo]; c < g.col_off[hi]; ++c) {
+                const int32_t col = g.col_val[c];
+                if (local[col] < 0) { local[col] = 0; uni.push_back(col); }
+            }
+            std::sort(uni.begin(), uni.end());
+            for (size_t x = 0; x < uni.size(); ++x) local[uni[x]] = (int32_t)x;
+            for (int32_t v = lo; v < hi; ++v) {
+                uint64_t* m = (v < mid) ? &p.masks[(size_t)p.msrc_off[l] + (size_t)(v - lo) * 2 * W]
+                                        : &p.masks[(size_t)p.mdst_off[l] + (size_t)(v - mid) * 2 * W];
+                for (int64_t c = g.col_off[v]; c < g.col_off[v + 1]; ++c) {
+                    const int32_t col = g.col_val[c];
+                    const int b = local[col];
+                    const int half = (g.colour_is_hom[col] == 1) ? 0 : W;   // hom words first, then het
+                    m[half + (b >> 6)] |= 1ull << (b & 63);
+                }
+            }
+            for (int32_t col : uni) local[col] = -1;
+        }
     }
 
     // ---- predecessor-code offsets and accounting ----
@@ -107,37 +169,100 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
     return true;
 }
 
-static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+namespace {
 
-void plan_sweep(DipPlan& p, const SweepShape& sh) {
-    const int L = p.L;
-    const int grid = sh.grid < 1 ? 1 : sh.grid;
-    const uint64_t cpc = sh.cells_per_cta < 1 ? 1 : (uint64_t)sh.cells_per_cta;
-    p.P.assign(L, 1); p.bar_target.assign(L, 0); p.bar_edge.assign(L, 0);
-    p.mode.assign(L, MODE_GLOBAL); p.flags.assign(L, 0); p.rec_off.assign(L, -1);
-    p.records.clear(); p.n_fast = p.n_staged = p.n_global = 0;
-    const int T = L - 1;                       // number of transitions
-    std::vector<size_t> rec_bytes(L, 0);
-    auto cells_of = [&](int l) { const uint64_t k = (uint64_t)(p.level_off[l + 1] - p.level_off[l]); return (uint64_t)(p.R + 1) * k * k; };
-    for (int l = 0; l < T; ++l) {
-        const int32_t k = p.level_off[l + 1] - p.level_off[l], k2 = p.level_off[l + 2] - p.level_off[l + 1];
-        const int64_t n_in = (int64_t)p.in_off[p.level_off[l + 2]] - (int64_t)p.in_off[p.level_off[l + 1]];
-        const int W = p.lvlW[l];
-        size_t b = sizeof(RecHeader) + align_up((size_t)(k2 + 1) * 2, 4);
-        b += (size_t)n_in * 4; b = align_up(b, 8);
-        b += (size_t)(k + k2) * 2 * W * 8; b = align_up(b, 16);
-        rec_bytes[l] = b;
-        const bool staged_ok = b <= (size_t)sh.stage_bytes && n_in < 65536;
-        const bool fits = cells_of(l) <= (uint64_t)sh.tile_cells && cells_of(l + 1) <= (uint64_t)sh.tile_cells;
-        p.mode[l] = !staged_ok ? MODE_GLOBAL : (fits ? MODE_FAST : MODE_STAGED);
-        if (p.mode[l] == MODE_FAST) { p.P[l] = 1; ++p.n_fast; }
-        else {
-            const uint64_t want = (cells_of(l + 1) + cpc - 1) / cpc;
-            p.P[l] = (int32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)grid);
-            if (p.mode[l] == MODE_STAGED) ++p.n_staged; else ++p.n_global;
-        }
+// Lane-form blocks of level l+1: starts of the <= 32-wide in-edge blocks (never cutting a destination's group)
+// followed by n_in.  Returns the number of blocks, 0 when the level cannot use the lane form (a destination
+// with no or with more than 32 in-edges).  `out` may be null (count only); *rounds = ceil(log2(longest group)).
+int lane_blocks(const DipPlan& p, int l, uint16_t* out, int* rounds) {
+    const int32_t mid = p.level_off[l + 1], k2 = p.level_off[l + 2] - mid;
+    const int32_t e0 = p.in_off[mid];
+    const int64_t n_in = (int64_t)p.in_off[mid + k2] - e0;
+    if (n_in <= 0 || n_in >= 65536) return 0;
+    int32_t longest = 0, start = 0;
+    int nb = 0;
+    if (out) out[0] = 0;
+    for (int32_t x = 0; x < k2; ++x) {
+        const int32_t deg = p.in_off[mid + x + 1] - p.in_off[mid + x];
+        if (deg < 1 || deg > 32) return 0;
+        longest = std::max(longest, deg);
+        const int32_t end = p.in_off[mid + x + 1] - e0;      // in-edges up to and including destination x
+        if (end - start > 32) { start = p.in_off[mid + x] - e0; ++nb; if (out) out[nb] = (uint16_t)start; }
     }
-    // A grid barrier follows transition l unless both it and the next one run on CTA 0 alone.
+    ++nb;
+    if (out) out[nb] = (uint16_t)n_in;
+    if (rounds) { int r = 0; while ((1 << r) < longest) ++r; *rounds = r; }
+    return nb;
+}
+
+}  // namespace
+
+void plan_tasks(DipPlan& p, const SweepShape& sh) {
+    const int L = p.L, T = L - 1;                  // T = number of transitions
+    const int G = sh.grid < 1 ? 1 : sh.grid;
+    const uint32_t CT = sh.threads < 1 ? 1u : (uint32_t)sh.threads;
+    const size_t slot = (size_t)sh.slot_bytes;
+    const int lrc = (sh.lane_rc == LANE_RC_BIG) ? LANE_RC_BIG : LANE_RC_SMALL;
+    p.grid = G;
+    p.P.assign(L, 1); p.bar_target.assign(L, 0); p.bar_edge.assign(L, 0); p.narrow.assign(L, 0);
+    p.rec_off.assign(L, -1); p.delta_off.assign(L, -1); p.delta_list.clear(); p.delta_elems = 0;
+    p.records.clear(); p.tasks.clear(); p.task_begin.assign((size_t)G + 1, 0);
+    p.n_narrow = p.n_wide = p.n_tasks_global = p.n_tasks_masks = 0;
+    if (T <= 0) return;
+    const int NT = n_threads();
+    (void)NT;
+    auto width = [&](int l) { return p.level_off[l + 1] - p.level_off[l]; };
+    auto cells_of = [&](int l) { const uint64_t k = (uint64_t)width(l); return (uint64_t)(p.R + 1) * k * k; };
+    auto nin_of = [&](int l) { return (int64_t)p.in_off[p.level_off[l + 2]] - (int64_t)p.in_off[p.level_off[l + 1]]; };
+
+    // ---- 1. lane-form blocks, record sizes, pair-score matrix layout, placement of the layers ----
+    std::vector<int32_t> nblk(T, 0);
+    std::vector<uint8_t> rec_staged(T, 0), seg_rounds(T, 0);
+    std::vector<uint32_t> rec_bytes(T, 0);
+#pragma omp parallel for schedule(static) num_threads(NT)
+    for (int l = 0; l < T; ++l) {
+        int rounds = 0;
+        nblk[l] = lane_blocks(p, l, nullptr, &rounds);
+        seg_rounds[l] = (uint8_t)rounds;
+        const int64_t n_in = nin_of(l);
+        const size_t rb = rec_bytes_for(width(l + 1), n_in, nblk[l]);
+        rec_staged[l] = (sizeof(TaskHdr) + rb <= slot && n_in < 65536) ? 1 : 0;
+        rec_bytes[l] = rec_staged[l] ? (uint32_t)rb : 0u;
+    }
+    size_t rec_total = 0;
+    for (int l = 0; l < T; ++l) {
+        const int64_t n_in = nin_of(l);
+        if (rec_staged[l]) { p.rec_off[l] = (int64_t)rec_total; rec_total += rec_bytes[l]; }
+        if (p.lvlW[l] > 0 && n_in <= sh.delta_max_in && (p.delta_elems + n_in * n_in) * 2 <= sh.delta_budget) {
+            p.delta_off[l] = p.delta_elems;
+            p.delta_elems += (int64_t)align_up((size_t)(n_in * n_in), 8);
+            p.delta_list.push_back(l);
+        }
+        const bool masks_mode = p.lvlW[l] > 0 && p.delta_off[l] < 0;     // too wide for a matrix: never narrow
+        p.narrow[l] = (rec_staged[l] && !masks_mode && cells_of(l) <= (uint64_t)sh.tile_cells &&
+                       cells_of(l + 1) <= (uint64_t)sh.tile_cells) ? 1 : 0;
+        if (p.narrow[l]) ++p.n_narrow; else ++p.n_wide;
+    }
+    p.records.assign(rec_total, 0);
+#pragma omp parallel for schedule(static) num_threads(NT)
+    for (int l = 0; l < T; ++l) {
+        if (!rec_staged[l]) continue;
+        uint8_t* r = p.records.data() + p.rec_off[l];
+        const int32_t mid = p.level_off[l + 1], k2 = width(l + 1);
+        const int32_t e0 = p.in_off[mid], e1 = p.in_off[p.level_off[l + 2]];
+        uint16_t* off2 = reinterpret_cast<uint16_t*>(r);
+        for (int32_t x = 0; x <= k2; ++x) off2[x] = (uint16_t)(p.in_off[mid + x] - e0);
+        if (e1 > e0) {
+            memcpy(r + rec_edge_offset(k2), &p.in_edge[e0], (size_t)(e1 - e0) * 4);
+            memcpy(r + rec_dst_offset(k2, e1 - e0), &p.in_dst[e0], (size_t)(e1 - e0) * 2);
+        }
+        if (nblk[l] > 0) lane_blocks(p, l, reinterpret_cast<uint16_t*>(r + rec_bstart_offset(k2, e1 - e0)), nullptr);
+    }
+
+    // ---- 2. participants: narrow -> CTA 0 alone; wide -> P = min(G, k2) CTAs ----
+    for (int l = 0; l < T; ++l) p.P[l] = p.narrow[l] ? 1 : std::max(1, std::min(G, (int)width(l + 1)));
+
+    // ---- 3. barrier schedule: a grid barrier follows transition l unless both it and the next run on CTA 0 alone ----
     uint32_t acc = 0;
     for (int l = 0; l < T; ++l) {
         const int pn = (l + 1 < T) ? p.P[l + 1] : 1;
@@ -146,45 +271,154 @@ void plan_sweep(DipPlan& p, const SweepShape& sh) {
         if (edge) acc += (uint32_t)p.P[l];
         p.bar_target[l] = acc;
     }
-    for (int l = 0; l < T; ++l) {
-        uint16_t f = 0;
-        if (l > 0 && p.bar_edge[l - 1]) f |= REC_WAIT;
-        if (p.bar_edge[l]) f |= REC_ARRIVE;
-        // layer l lives in shared memory iff it is produced and consumed by FAST transitions (level 0: by the kernel prologue)
-        const bool fast = p.mode[l] == MODE_FAST;
-        if (fast && (l == 0 || p.mode[l - 1] == MODE_FAST)) f |= REC_SRC_SMEM;
-        if (fast && l + 1 < T && p.mode[l + 1] == MODE_FAST) f |= REC_DST_SMEM;
-        p.flags[l] = f;
-    }
-    // pack records
-    size_t total = 0;
-    for (int l = 0; l < T; ++l) if (p.mode[l] != MODE_GLOBAL) { p.rec_off[l] = (int64_t)total; total += rec_bytes[l]; }
-    p.records.assign(total, 0);
-    for (int l = 0; l < T; ++l) {
-        if (p.mode[l] == MODE_GLOBAL) continue;
-        uint8_t* r = p.records.data() + p.rec_off[l];
-        const int32_t mid = p.level_off[l + 1];
-        const int32_t k = mid - p.level_off[l], k2 = p.level_off[l + 2] - mid;
-        const int32_t e0 = p.in_off[mid], e1 = p.in_off[p.level_off[l + 2]];
-        const int W = p.lvlW[l];
-        RecHeader h;
-        h.k = (uint16_t)k; h.k2 = (uint16_t)k2; h.W = (uint16_t)W; h.flags = p.flags[l];
-        h.n_in = (uint32_t)(e1 - e0); h.bytes = (uint32_t)rec_bytes[l];
-        h.P = (uint32_t)p.P[l]; h.wait_target = (l > 0) ? p.bar_target[l - 1] : 0;
-        h.pred_off2 = p.pred_off[l + 1];
-        memcpy(r, &h, sizeof h);
-        size_t o = sizeof(RecHeader);
-        uint16_t* off2 = reinterpret_cast<uint16_t*>(r + o);
-        for (int32_t x = 0; x <= k2; ++x) off2[x] = (uint16_t)(p.in_off[mid + x] - e0);
-        o += align_up((size_t)(k2 + 1) * 2, 4);
-        if (e1 > e0) memcpy(r + o, &p.in_edge[e0], (size_t)(e1 - e0) * 4);
-        o += (size_t)(e1 - e0) * 4; o = align_up(o, 8);
-        if (W > 0) {
-            memcpy(r + o, &p.masks[(size_t)p.msrc_off[l]], (size_t)k * 2 * W * 8);
-            o += (size_t)k * 2 * W * 8;
-            memcpy(r + o, &p.masks[(size_t)p.mdst_off[l]], (size_t)k2 * 2 * W * 8);
+
+    // ---- 4. task streams: every host thread compiles a contiguous range of levels into per-CTA pieces, which
+    // are then concatenated in thread order (= level order) ----
+    std::vector<std::vector<std::vector<TaskHdr>>> piece((size_t)NT, std::vector<std::vector<TaskHdr>>((size_t)G));
+    std::vector<int64_t> n_glob((size_t)NT, 0), n_mask((size_t)NT, 0);
+#pragma omp parallel num_threads(NT)
+    {
+#if defined(_OPENMP)
+        const int tno = omp_get_thread_num(), tcount = omp_get_num_threads();
+#else
+        const int tno = 0, tcount = 1;
+#endif
+        const int l_begin = (int)((int64_t)T * tno / tcount), l_end = (int)((int64_t)T * (tno + 1) / tcount);
+        std::vector<std::vector<TaskHdr>>& stream = piece[(size_t)tno];
+        std::vector<int32_t> cut;
+        for (int l = l_begin; l < l_end; ++l) {
+            const int32_t mid = p.level_off[l + 1], k = width(l), k2 = width(l + 1);
+            const int64_t n_in = nin_of(l);
+            const int32_t e0 = p.in_off[mid];
+            const int P = p.P[l];
+            // row partition, balanced by candidates (indeg(i') * n_in) plus a per-pair overhead
+            cut.assign((size_t)P + 1, 0);
+            cut[(size_t)P] = k2;
+            if (P > 1) {
+                uint64_t total = 0;
+                for (int32_t x = 0; x < k2; ++x) total += (uint64_t)(p.in_off[mid + x + 1] - p.in_off[mid + x]) * (uint64_t)n_in + 4u * (uint64_t)k2;
+                uint64_t accw = 0;
+                int32_t x = 0;
+                for (int q = 1; q < P; ++q) {
+                    const uint64_t want = total * (uint64_t)q / (uint64_t)P;
+                    const int32_t lo_x = cut[(size_t)q - 1] + 1, hi_x = k2 - (P - q);   // >= 1 row per chunk, now and later
+                    while (x < hi_x && (x < lo_x || accw < want)) {
+                        accw += (uint64_t)(p.in_off[mid + x + 1] - p.in_off[mid + x]) * (uint64_t)n_in + 4u * (uint64_t)k2;
+                        ++x;
+                    }
+                    cut[(size_t)q] = x;
+                }
+            }
+            const size_t rb = rec_bytes[l];
+            uint32_t base_flags = 0;
+            // layer l lives in shared memory iff it is produced and consumed by narrow transitions (level 0: by the kernel prologue)
+            if (p.narrow[l] && (l == 0 || p.narrow[l - 1])) base_flags |= TK_SRC_SMEM;
+            if (p.narrow[l] && l + 1 < T && p.narrow[l + 1]) base_flags |= TK_DST_SMEM;
+            if (p.lvlW[l] > 0) base_flags |= (p.delta_off[l] >= 0) ? TK_DELTA : TK_DELTA_MASKS;
+            if (!rec_staged[l]) base_flags |= TK_REC_GLOBAL;
+            const bool same_place = ((base_flags & TK_SRC_SMEM) != 0) == ((base_flags & TK_DST_SMEM) != 0);   // hand-overs use the pair form
+            const uint64_t kk2 = (uint64_t)k2 * (uint64_t)k2;
+            const int32_t max_rows = (int32_t)std::max<uint64_t>(1, std::min<uint64_t>(65535, ((1ull << 32) - 1) / std::max<uint64_t>(kk2, 1)));
+            for (int c = 0; c < P; ++c) {
+                const int32_t ra = cut[(size_t)c], rbnd = cut[(size_t)c + 1];
+                int32_t x = ra;
+                bool first = true;
+                while (x < rbnd) {
+                    TaskHdr h;
+                    memset(&h, 0, sizeof h);
+                    h.level = l; h.k = (uint16_t)k; h.k2 = (uint16_t)k2; h.i0 = (uint16_t)x;
+                    h.n_in = (uint32_t)(rec_staged[l] ? n_in : 0);
+                    h.flags = base_flags;
+                    h.pred_off2 = p.pred_off[l + 1];
+                    int32_t y = std::min(rbnd, x + max_rows);
+                    if (rec_staged[l]) {
+                        h.rec_off16 = (uint32_t)(p.rec_off[l] / 16);
+                        h.rec_bytes = (uint32_t)rb;
+                        if (base_flags & TK_DELTA) {
+                            // stage as many whole rows of the matrix as the slot still holds
+                            const size_t avail = slot - sizeof(TaskHdr) - rb;
+                            const int64_t s_el = (int64_t)(p.in_off[mid + x] - e0) * n_in;
+                            const int64_t s_al = s_el & ~(int64_t)7;                  // 16-byte aligned (matrix base is)
+                            int32_t yy = x;
+                            int64_t bytes = 0;
+                            while (yy < y) {
+                                const int64_t e_el = (int64_t)(p.in_off[mid + yy + 1] - e0) * n_in;
+                                const int64_t b = (int64_t)align_up((size_t)((e_el - s_al) * 2), 16);
+                                if ((size_t)b > avail) break;
+                                bytes = b; ++yy;
+                            }
+                            if (yy > x) {
+                                y = yy;
+                                if (bytes > 0) {
+                                    h.flags |= TK_DELTA_STAGED;
+                                    h.delta_off16 = (uint32_t)((p.delta_off[l] + s_al) / 8);
+                                    h.delta_bytes = (uint32_t)bytes;
+                                    h.delta_skew = (uint32_t)(s_el - s_al);
+                                }
+                            } else {
+                                y = x + 1;          // one row larger than a slot: read its matrix rows in place
+                            }
+                        }
+                    } else {
+                        ++n_glob[(size_t)tno];
+                    }
+                    if (base_flags & TK_DELTA_MASKS) ++n_mask[(size_t)tno];
+                    h.i1 = (uint16_t)y;
+                    const uint32_t npairs = (uint32_t)(y - x) * (uint32_t)k2;
+                    h.m_k2 = make_magic((uint32_t)k2);
+                    h.m_pairs = make_magic(npairs);
+                    const int rc = choose_rc(npairs, p.R, CT);
+                    const uint32_t nchunk = (uint32_t)(p.R + rc) / (uint32_t)rc;
+                    h.rc = (uint16_t)rc;
+                    h.groups = (uint16_t)(npairs >= CT ? 1u : std::max(1u, std::min(nchunk, CT / npairs)));
+                    h.n_active = std::min<uint32_t>(CT, (uint32_t)h.groups * npairs);
+                    // lane form: record staged, level eligible, pair scores absent or staged for exactly these rows
+                    const bool scores_ok = !(base_flags & (TK_DELTA | TK_DELTA_MASKS)) || (h.flags & TK_DELTA_STAGED);
+                    const uint32_t lchunks = (uint32_t)(p.R + lrc) / (uint32_t)lrc;
+                    const uint64_t witems = (uint64_t)(y - x) * (uint64_t)std::max(nblk[l], 1) * lchunks;   // upper bound (rp >= 1)
+                    if (rec_staged[l] && nblk[l] > 0 && scores_ok && same_place && CT % 32 == 0 &&
+                        witems * (uint64_t)std::max<int64_t>(nblk[l], y - x) < (1ull << 32)) {
+                        h.flags |= TK_LANES;
+                        h.nblk = (uint16_t)nblk[l];
+                        h.rp = (uint16_t)((nblk[l] == 1) ? std::max<int64_t>(1, std::min<int64_t>(32 / n_in, y - x)) : 1);
+                        h.nrg = (uint32_t)((y - x + h.rp - 1) / h.rp);
+                        h.m_nblk = make_magic((uint32_t)nblk[l]);
+                        h.m_nrg = make_magic(h.nrg);
+                        h.m_nin = make_magic((uint32_t)n_in);
+                        h.rc = (uint16_t)lrc;
+                        h.n_witems = h.nrg * (uint32_t)nblk[l] * lchunks;
+                        h.rounds = seg_rounds[l];
+                        h.bstart_off = (uint32_t)rec_bstart_offset(k2, n_in);
+                        h.n_active = std::min<uint32_t>(CT, 32u * h.n_witems);
+                    }
+                    if (first && l > 0 && p.bar_edge[l - 1]) { h.flags |= TK_WAIT; h.wait_target = p.bar_target[l - 1]; }
+                    if (y >= rbnd) {
+                        h.flags |= TK_BAR;
+                        if (p.bar_edge[l]) h.flags |= TK_ARRIVE;
+                    }
+                    stream[(size_t)c].push_back(h);
+                    first = false;
+                    x = y;
+                }
+            }
         }
     }
+    for (int t = 0; t < NT; ++t) { p.n_tasks_global += n_glob[(size_t)t]; p.n_tasks_masks += n_mask[(size_t)t]; }
+    // offsets: CTA-major, then host-thread (level) order
+    std::vector<size_t> dst_off((size_t)NT * (size_t)G, 0);
+    size_t total = 0;
+    for (int c = 0; c < G; ++c) {
+        p.task_begin[(size_t)c] = (int64_t)total;
+        for (int t = 0; t < NT; ++t) { dst_off[(size_t)t * (size_t)G + (size_t)c] = total; total += piece[(size_t)t][(size_t)c].size(); }
+    }
+    p.task_begin[(size_t)G] = (int64_t)total;
+    p.tasks.resize(total);
+#pragma omp parallel for schedule(static) num_threads(NT)
+    for (int t = 0; t < NT; ++t)
+        for (int c = 0; c < G; ++c) {
+            const std::vector<TaskHdr>& v = piece[(size_t)t][(size_t)c];
+            if (!v.empty()) memcpy(p.tasks.data() + dst_off[(size_t)t * (size_t)G + (size_t)c], v.data(), v.size() * sizeof(TaskHdr));
+        }
 }
 
 }  // namespace dg

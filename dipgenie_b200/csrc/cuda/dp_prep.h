@@ -7,13 +7,15 @@
 // the kernels consume:
 //   * in-edge CSR per destination vertex, entries (source position in previous level, weight),
 //     ascending source position — the reference's scatter loop over (i, j, e1, e2)
-//     (approximator.cpp:627-701) becomes "every destination cell takes the lexicographic max of
-//     (value, -i, -j) over in-edges(i') x in-edges(j')", which needs no locks and is order-free;
+//     (approximator.cpp:627-701) becomes "every destination cell takes the first strict maximum over
+//     in-edges(i') x in-edges(j')", which needs no locks and is order-free;
 //   * per-transition colour bit-masks over the local colour universe of levels l and l+1, split
 //     hom/het with colour_is_hom (approximator.cpp:431-453), so that the reference's two 4-way sorted
 //     merges per edge pair (inter_size_union2x2 / symdiff_size_union2x2, :269-311, :604-624) become
 //     popcounts:  delta = popc((Hs[i]|Hs[j]) & (Hd[i']|Hd[j'])) + popc((Ts[i]|Ts[j]) ^ (Td[i']|Td[j']));
-//   * the per-transition participant count and the monotone barrier targets of the persistent sweep.
+//     a device kernel evaluates them once per (e1,e2) into the pair-score matrix of the transition;
+//   * one task stream per CTA (dp_cell.h: TaskHdr) with the monotone barrier targets of the
+//     persistent sweep.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -41,9 +43,12 @@ constexpr int IN_W_SHIFT = 16;
 
 struct SweepShape {              // kernel geometry the plan is made for
     int grid = 1;                // CTAs in the cooperative grid
-    int cells_per_cta = 2048;    // destination cells one CTA takes per transition before more CTAs join
+    int threads = 512;           // compute threads per CTA
     int tile_cells = 16384;      // int32 cells per shared-memory layer tile (two tiles)
-    int stage_bytes = 16384;     // bytes per record stage in shared memory
+    int slot_bytes = 4096;       // bytes per task slot in shared memory (header + record + delta slice)
+    int64_t delta_budget = (int64_t)8 << 30;   // bytes of pair-score matrices to materialise at most
+    int delta_max_in = 4096;     // widest in-edge count that still gets a matrix
+    int lane_rc = LANE_RC_SMALL; // layers per lane in the lane form (LANE_RC_SMALL or LANE_RC_BIG)
 };
 
 struct DipPlan {
@@ -52,20 +57,27 @@ struct DipPlan {
     int64_t n_in = 0;
     std::vector<int32_t> level_off;    // [L+1]
     std::vector<int32_t> in_off;       // [V+1]
-    std::vector<uint32_t> in_edge;     // [n_in]
+    std::vector<uint32_t> in_edge;     // [n_in]   source position | weight << 16
+    std::vector<uint16_t> in_dst;      // [n_in]   destination position of the in-edge (for the delta kernel)
     std::vector<int32_t> lvlW;         // [L]   64-bit mask words of transition l (0 = no colours)
     std::vector<int64_t> msrc_off;     // [L]   offset (u64 words) of level-l source masks
     std::vector<int64_t> mdst_off;     // [L]   offset of level-(l+1) destination masks
     std::vector<uint64_t> masks;
     std::vector<int64_t> pred_off;     // [L+1] offset of level l's predecessor codes
+    // --- task plan (plan_tasks) ---
     std::vector<int32_t> P;            // [L]   CTAs taking part in transition l
     std::vector<uint32_t> bar_target;  // [L]   arrivals that must be visible once transition l is complete
     std::vector<uint8_t> bar_edge;     // [L]   1 = a grid-level barrier follows transition l
-    std::vector<uint8_t> mode;         // [L]   MODE_* of transition l
-    std::vector<uint16_t> flags;       // [L]   REC_* of transition l
+    std::vector<uint8_t> narrow;       // [L]   1 = both layers of transition l fit CTA 0's shared-memory tiles
     std::vector<int64_t> rec_off;      // [L]   byte offset of transition l's record in `records` (-1: none)
-    std::vector<uint8_t> records;      // packed records of all FAST/STAGED transitions (16-byte aligned)
-    int64_t n_fast = 0, n_staged = 0, n_global = 0;
+    std::vector<uint8_t> records;      // packed records (16-byte aligned)
+    std::vector<int64_t> delta_off;    // [L]   u16-element offset of transition l's pair-score matrix (-1: none)
+    std::vector<int32_t> delta_list;   // transitions that own a matrix, ascending
+    int64_t delta_elems = 0;           // total u16 elements (every matrix start is 16-byte aligned)
+    std::vector<TaskHdr> tasks;        // all CTAs' streams, concatenated in CTA order
+    std::vector<int64_t> task_begin;   // [grid+1]
+    int32_t grid = 1;
+    int64_t n_narrow = 0, n_wide = 0, n_tasks_global = 0, n_tasks_masks = 0;
     // accounting
     uint64_t cell_updates = 0;         // U = (R+1) * sum_l E_l^2
     uint64_t cells = 0;                // C = (R+1) * sum_{l>=1} k_l^2
@@ -73,13 +85,12 @@ struct DipPlan {
     std::string error;
 };
 
-// Builds everything except P / bar_*; returns false and sets plan.error on malformed input.
+// Builds the gather-form arrays; returns false and sets plan.error on malformed input.
 bool build_dip_plan(const DipGraphView& g, DipPlan& plan);
 
-// Chooses, for the given kernel geometry, the mode (FAST: CTA 0 alone with both layers in shared
-// memory; STAGED: P CTAs, metadata staged through shared memory, layers in HBM/L2; GLOBAL: metadata
-// read in place) and the participants of every transition, derives the monotone-counter barrier
-// schedule, and packs the records.
-void plan_sweep(DipPlan& plan, const SweepShape& shape);
+// Compiles the sweep into per-CTA task streams for the given kernel geometry: narrow/wide placement of
+// every layer, row partition of wide transitions, slot-sized sub-tasks, barrier schedule, packed records
+// and the layout of the pair-score matrices.
+void plan_tasks(DipPlan& plan, const SweepShape& shape);
 
 }  // namespace dg

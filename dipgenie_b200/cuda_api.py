@@ -22,7 +22,9 @@ class DipStats(C.Structure):
         ("cell_updates", C.c_uint64), ("cells", C.c_uint64), ("algo_bytes", C.c_uint64), ("device_bytes", C.c_uint64),
         ("n_levels", C.c_int32), ("n_vertices", C.c_int32), ("max_width", C.c_int32), ("max_indegree", C.c_int32),
         ("mask_words_max", C.c_int32), ("grid_ctas", C.c_int32), ("pred_bytes", C.c_int32), ("launches", C.c_int32),
-        ("sweep_ms", C.c_float), ("traceback_ms", C.c_float),
+        ("sweep_ms", C.c_float), ("traceback_ms", C.c_float), ("delta_ms", C.c_float), ("plan_ms", C.c_float),
+        ("upload_ms", C.c_float), ("n_narrow", C.c_int32), ("n_wide", C.c_int32), ("n_tasks", C.c_int64),
+        ("delta_bytes", C.c_uint64),
     ]
 
 
@@ -359,8 +361,10 @@ class DipProblem:
     def profile(self) -> dict:
         out = np.zeros(24, np.uint64)
         self.ctx.check(self.ctx.lib.dg_dip_profile(C.c_void_p(self.ctx.h), self.h, _ptr(out)), "dg_dip_profile")
-        names = ["transitions", "block_barrier", "record_wait", "grid_wait", "cell_loop", "arrive"]
-        return {m: {n: int(out[i * 6 + j]) for j, n in enumerate(names)} for i, m in enumerate(["smem_layers", "staged", "in_place"])}
+        names = ["tasks", "slot_wait", "grid_wait", "cell_loop", "barrier_arrive"]
+        d = {m: {n: int(out[i * 6 + j]) for j, n in enumerate(names)} for i, m in enumerate(["smem_layers", "hbm_layers"])}
+        d["lane_form_warp0"] = {n: int(out[12 + j]) for j, n in enumerate(["items", "setup", "loop", "reduce", "store", "iters"])}
+        return d
 
     def result(self):
         R = self.R

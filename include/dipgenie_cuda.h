@@ -77,17 +77,23 @@ int dg_dip_result(dg_ctx* ctx, dg_dip* d, int32_t* sink_value, int32_t* sink_s_h
 int dg_dip_checksums(dg_ctx* ctx, dg_dip* d, uint64_t* level_checksum, uint64_t* level_live);
 /* Work and traffic accounting: U = (R+1)*sum E_l^2 cell-updates, C = (R+1)*sum k_l^2
  * destination cells, B = (R+1)*sum(4 k_l^2 + 5 k_{l+1}^2) algorithmic bytes; plus kernel launches and
- * device milliseconds (CUDA events on the context's stream) of the last dg_dip_run. */
+ * device milliseconds (CUDA events on the context's stream) of the last dg_dip_run (valid after
+ * dg_dip_result). */
 typedef struct {
     uint64_t cell_updates, cells, algo_bytes;
     uint64_t device_bytes;       /* HBM held by this problem */
     int32_t n_levels, n_vertices, max_width, max_indegree, mask_words_max, grid_ctas, pred_bytes;
     int32_t launches;
-    float sweep_ms, traceback_ms;
+    float sweep_ms, traceback_ms;       /* dip_sweep_kernel; the four traceback kernels */
+    float delta_ms;                     /* dip_delta_kernel (pair-score matrices) */
+    float plan_ms, upload_ms;           /* host planning and H2D inside dg_dip_create */
+    int32_t n_narrow, n_wide;           /* transitions run by CTA 0 alone in shared memory / spread over CTAs */
+    int64_t n_tasks;                    /* tasks over all CTA streams */
+    uint64_t delta_bytes;               /* HBM held by the pair-score matrices */
 } dg_dip_stats_t;
 int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out);
-/* out24: for each of {shared-memory layers, staged record + HBM layers, in-place metadata} six counters
- * {transitions, block-barrier, record-wait, grid-wait, cell-loop, arrive} in SM clock cycles of CTA 0. */
+/* out24: for each of {shared-memory layers, HBM/L2 layers} six counters {tasks, slot-wait, grid-wait,
+ * cell-loop, barrier+arrive, unused} in SM clock cycles of CTA 0 / thread 0; the rest is zero. */
 int dg_dip_profile(dg_ctx* ctx, dg_dip* d, uint64_t* out24);
 void dg_dip_destroy(dg_ctx* ctx, dg_dip* d);
 

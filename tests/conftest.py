@@ -46,7 +46,7 @@ def _build_emu():
     srcs = [os.path.join(EMU_DIR, "dp_emu.cpp"), os.path.join(ROOT, "dipgenie_b200", "csrc", "cuda", "dp_prep.cpp")]
     deps = srcs + [os.path.join(ROOT, "dipgenie_b200", "csrc", "cuda", h) for h in ("dp_prep.h", "dp_cell.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so] + srcs)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-o", so] + srcs)
     return so
 
 
@@ -57,10 +57,13 @@ class DpEmu:
         self.lib = C.CDLL(_build_emu())
 
     def dp_diploid(self, g, R, force_pred32=False, shape=None):
-        """shape = (grid, cells_per_cta, tile_cells, stage_bytes) of the emulated kernel geometry (0 = default)."""
+        """shape = (grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, lane_rc) of the emulated kernel geometry
+        (0 = default; delta_max_in < 0 forces the on-the-fly mask path)."""
         L = g.n_levels
-        shp = np.array(list(shape) if shape else [0, 0, 0, 0], np.int32)
-        modes = np.zeros(3, np.int64)
+        shp = np.zeros(7, np.int32)
+        if shape:
+            shp[: len(shape)] = list(shape)
+        counts = np.zeros(7, np.int64)
         val, sh, n1, n2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         p1 = np.zeros(2 * (R + 2), np.int32)
         p2 = np.zeros(2 * (R + 2), np.int32)
@@ -70,12 +73,14 @@ class DpEmu:
         rc = self.lib.emu_dp_diploid(
             C.c_int32(L), P(g.level_off), P(g.adj_off), P(g.adj_dst), P(g.adj_w), P(g.col_off), P(g.col_val),
             P(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R), C.byref(val), C.byref(sh), P(p1),
-            C.byref(n1), P(p2), C.byref(n2), P(cs), P(lv), C.c_int32(1 if force_pred32 else 0), P(shp), P(modes))
+            C.byref(n1), P(p2), C.byref(n2), P(cs), P(lv), C.c_int32(1 if force_pred32 else 0), P(shp), P(counts))
         if rc != 0:
             raise RuntimeError(f"emu_dp_diploid rc={rc}")
         return dict(value=val.value, s_het=sh.value, p1_edges=p1[: 2 * n1.value].reshape(-1, 2).copy(),
                     p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy(), checksum=cs, live=lv,
-                    modes=dict(fast=int(modes[0]), staged=int(modes[1]), global_=int(modes[2])))
+                    modes=dict(narrow=int(counts[0]), wide=int(counts[1]), tasks=int(counts[2]),
+                               tasks_global=int(counts[3]), tasks_masks=int(counts[4]), matrices=int(counts[5]),
+                               tasks_lanes=int(counts[6])))
 
 
 @pytest.fixture(scope="session")

@@ -1,10 +1,12 @@
 // tests/emu/dp_emu.cpp — TEST-ONLY CPU emulation of the CUDA diploid sweep.
-// Runs the exact host planning (dp_prep.cpp: in-edge CSR, colour masks, modes, packed records, barrier
-// schedule) and the exact per-cell / record-view / traceback code (dp_cell.h) the kernels run, with the
-// thread grid replaced by serial loops and the shared-memory tiles / record stages by host buffers, so
-// that `-m "not gpu"` tests can check the gather formulation, the record packing, the tile placement
-// flags, the monotone barrier targets, the predecessor codes and the traceback against the oracle
-// without a GPU.  Never part of the product library.
+// Runs the exact host planning (dp_prep.cpp: in-edge CSR, colour masks, task streams, packed records,
+// pair-score matrix layout, barrier schedule) and the exact per-cell / traceback code (dp_cell.h) the
+// kernels run, with the thread grid replaced by serial loops, the shared-memory tiles and task slots by
+// host buffers and the bulk copies by memcpy, so that `-m "not gpu"` tests can check the gather
+// formulation, the task/record packing, the slot layout (alignment, skew, sizes), the tile placement
+// flags, the monotone barrier targets, the predecessor codes and the checkpointed traceback against the
+// oracle without a GPU.  Never part of the product library.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -14,138 +16,388 @@
 
 using namespace dg;
 
-template <int RC, bool HAS_MASK, class PredT, class OffT, class Load, class Store>
-static void items(const TransitionT<OffT>& t, int R, Load load, Store store, PredT* pl, uint64_t& h, uint64_t& live) {
+namespace {
+
+struct Emu {
+    const DipPlan& p;
+    const SweepShape& sh;
+    std::vector<uint16_t> delta;
+    std::vector<int32_t> g0, g1, s0, s1;
+    std::vector<uint64_t> sum, live;
+    bool bad_rc = false;
+    int64_t n_lane_tasks = 0;
+    std::vector<uint8_t> written;      // cells of the current destination level stored so far (lane form: exactly once)
+    Emu(const DipPlan& pp, const SweepShape& s) : p(pp), sh(s) {}
+};
+
+// same thread -> item mapping as sweep_items() in dp_diploid.cu, threads run one after the other
+template <class PredT, class OffT, int RC, bool MASKS>
+void items(Emu& e, const TransitionT<OffT>& t, const TaskHdr& h, const int32_t* src, int32_t* dst, PredT* pl) {
     constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
-    const uint32_t k2 = (uint32_t)t.k2, npairs = k2 * k2, nchunk = (uint32_t)(R + RC) / RC;
-    for (uint64_t x = 0; x < (uint64_t)npairs * nchunk; ++x) {
-        const uint32_t chunk = (uint32_t)(x / npairs), pair = (uint32_t)(x - (uint64_t)chunk * npairs);
-        const uint32_t i2 = pair / k2, j2 = pair - i2 * k2;
-        uint64_t best[RC]; uint32_t code[RC];
-        relax_pair<RC, HAS_MASK>(t, load, R, (int)chunk * RC, (int)i2, (int)j2, best, code);
-        for (int rr = 0; rr < RC; ++rr) {
-            const int r2 = (int)chunk * RC + rr;
-            if (r2 > R) continue;
-            const uint64_t c = (uint64_t)r2 * npairs + pair, key = best[rr];
-            store(c, key_value(key));
-            pl[c] = key ? (PredT)(((code[rr] >> 16) << SH) | (code[rr] & 0xFFFFu)) : (PredT) ~(PredT)0;
-            if (key) {
-                ++live;
-                h += cell_fold(c, key_value(key), 0xFFFF - (int)((key >> 16) & 0xFFFF), 0xFFFF - (int)(key & 0xFFFF));
+    const int R = e.p.R;
+    const uint32_t CT = (uint32_t)e.sh.threads;
+    const uint32_t k2 = h.k2, npairs = (uint32_t)(h.i1 - h.i0) * k2, nchunk = (uint32_t)(R + RC) / RC, groups = h.groups;
+    auto load = [src](int64_t idx) { return src[idx]; };
+    for (uint32_t tid = 0; tid < CT; ++tid) {
+        uint32_t g = 0, pp = tid;
+        if (groups > 1) {
+            g = h.m_pairs ? div_magic(tid, h.m_pairs) : tid;
+            pp = tid - g * npairs;
+            if (g >= groups) continue;
+        }
+        for (uint32_t pair = pp; pair < npairs; pair += CT) {
+            const uint32_t ir = h.m_k2 ? div_magic(pair, h.m_k2) : pair;
+            const uint32_t j2 = pair - ir * k2, i2 = (uint32_t)h.i0 + ir;
+            for (uint32_t chunk = g; chunk < nchunk; chunk += groups) {
+                int32_t best[RC]; uint32_t code[RC];
+                relax_pair<RC, MASKS, int64_t>(t, load, R, (int)chunk * RC, (int)i2, (int)j2, best, code);
+                for (int rr = 0; rr < RC; ++rr) {
+                    const int r2 = (int)chunk * RC + rr;
+                    if (r2 > R) continue;
+                    const uint64_t c = ((uint64_t)r2 * k2 + i2) * k2 + j2;
+                    const bool lv = best[rr] >= 0;
+                    e.written[c] = 1;
+                    dst[c] = lv ? best[rr] : NEG_INF;
+                    pl[c] = lv ? (PredT)(((code[rr] >> 16) << SH) | (code[rr] & 0xFFFFu)) : (PredT) ~(PredT)0;
+                    if (lv) {
+                        const int pi = (int)(t.in_edge[(int32_t)t.in_off[i2] + (int32_t)(code[rr] >> 16)] & 0xFFFFu);
+                        const int pj = (int)(t.in_edge[(int32_t)t.in_off[j2] + (int32_t)(code[rr] & 0xFFFFu)] & 0xFFFFu);
+                        ++e.live[h.level + 1];
+                        e.sum[h.level + 1] += cell_fold(c, best[rr], pi, pj);
+                    }
+                }
             }
         }
     }
 }
 
-// same dispatch as sweep_dispatch() in dp_diploid.cu
-template <class PredT, class OffT, class Load, class Store>
-static void cells(const TransitionT<OffT>& t, int R, uint64_t nthreads, Load load, Store store, PredT* pl, uint64_t& h, uint64_t& live) {
-    const int rc = choose_rc((uint64_t)t.k2 * t.k2, R, nthreads);
-    if (t.W > 0) {
-        switch (rc) {
-            case 8: items<8, true>(t, R, load, store, pl, h, live); break;
-            case 4: items<4, true>(t, R, load, store, pl, h, live); break;
-            case 2: items<2, true>(t, R, load, store, pl, h, live); break;
-            default: items<1, true>(t, R, load, store, pl, h, live); break;
+template <class PredT, class OffT, bool MASKS>
+void by_rc(Emu& e, const TransitionT<OffT>& t, const TaskHdr& h, const int32_t* src, int32_t* dst, PredT* pl) {
+    if (h.rc != DIP_RC) { e.bad_rc = true; return; }
+    items<PredT, OffT, DIP_RC, MASKS>(e, t, h, src, dst, pl);
+}
+
+template <class PredT, class OffT>
+void by_dm(Emu& e, const TransitionT<OffT>& t, const TaskHdr& h, const int32_t* src, int32_t* dst, PredT* pl) {
+    if (h.flags & TK_DELTA_MASKS) by_rc<PredT, OffT, true>(e, t, h, src, dst, pl);
+    else by_rc<PredT, OffT, false>(e, t, h, src, dst, pl);
+}
+
+// the lane form (dp_diploid.cu: lane_task), warp by warp, the 32 lanes emulated in lock-step arrays
+template <class PredT, int RC>
+int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src, int32_t* dst, PredT* pl) {
+    constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
+    const int R = e.p.R;
+    const uint32_t NCW = (uint32_t)e.sh.threads / 32;
+    const uint8_t* rec = slot + sizeof(TaskHdr);
+    const uint16_t* in_off = reinterpret_cast<const uint16_t*>(rec);
+    const uint32_t* in_edge = reinterpret_cast<const uint32_t*>(rec + rec_edge_offset(h.k2));
+    const uint16_t* in_dst = reinterpret_cast<const uint16_t*>(rec + rec_dst_offset(h.k2, h.n_in));
+    if (h.bstart_off != rec_bstart_offset(h.k2, h.n_in) || h.bstart_off + 2u * (h.nblk + 1u) > h.rec_bytes) return -50;
+    const uint16_t* bstart = reinterpret_cast<const uint16_t*>(rec + h.bstart_off);
+    const bool staged = (h.flags & TK_DELTA_STAGED) != 0;
+    if ((h.flags & (TK_DELTA | TK_DELTA_MASKS)) && !staged) return -51;
+    const uint16_t* delta = staged ? reinterpret_cast<const uint16_t*>(rec + h.rec_bytes) + h.delta_skew - (size_t)in_off[h.i0] * h.n_in : nullptr;
+    const uint32_t k = h.k, k2 = h.k2, n_in = h.n_in, kk = k * k, kk2 = k2 * k2;
+    const uint32_t nchunk = (uint32_t)(R + RC) / RC;
+    if (h.n_witems != h.nrg * h.nblk * nchunk || h.nblk < 1 || h.rp < 1 || (h.nblk > 1 && h.rp != 1)) return -52;
+    if ((uint64_t)h.nrg * h.rp < (uint64_t)(h.i1 - h.i0) || bstart[0] != 0 || bstart[h.nblk] != n_in) return -53;
+    for (uint32_t warp = 0; warp < NCW; ++warp)
+        for (uint32_t wi = warp; wi < h.n_witems; wi += NCW) {
+            const uint32_t q = h.m_nblk ? div_magic(wi, h.m_nblk) : wi, b = wi - q * h.nblk;
+            const uint32_t chunk = h.m_nrg ? div_magic(q, h.m_nrg) : q, rg = q - chunk * h.nrg;
+            if (b >= h.nblk || rg >= h.nrg || chunk >= nchunk) return -54;
+            const uint32_t bs = bstart[b], be = bstart[b + 1];
+            if (be - bs > 32 || be <= bs) return -55;
+            const int r0 = (int)chunk * RC;
+            int32_t best[32][RC]; uint32_t code[32][RC];
+            bool valid[32]; uint32_t pos[32], seg[32], row[32], j2[32], a0[32], s0[32];
+            for (uint32_t lane = 0; lane < 32; ++lane) {
+                uint32_t rs = 0, el = lane;
+                if (h.nblk == 1) { rs = h.m_nin ? div_magic(lane, h.m_nin) : lane; el = lane - rs * n_in; }
+                row[lane] = h.i0 + rg * h.rp + rs;
+                const uint32_t e2 = bs + el;
+                valid[lane] = rs < h.rp && row[lane] < h.i1 && e2 < be;
+                const uint32_t rowc = valid[lane] ? row[lane] : h.i0, e2c = valid[lane] ? e2 : bs;
+                a0[lane] = in_off[rowc];
+                const uint32_t a1 = valid[lane] ? in_off[rowc + 1] : a0[lane];
+                const uint32_t y = in_edge[e2c];
+                j2[lane] = in_dst[e2c];
+                s0[lane] = in_off[j2[lane]];
+                pos[lane] = e2c - s0[lane]; seg[lane] = in_off[j2[lane] + 1] - s0[lane];
+                if (valid[lane] && (pos[lane] >= seg[lane] || s0[lane] < bs || s0[lane] + seg[lane] > be)) return -56;   // a block cut a group
+                const uint32_t j = y & 0xFFFFu; const int wv = (int)(y >> 16);
+                for (int rr = 0; rr < RC; ++rr) { best[lane][rr] = -1; code[lane][rr] = 0xFFFFFFFFu; }
+                for (uint32_t e1 = a0[lane]; e1 < a1; ++e1) {
+                    const uint32_t x = in_edge[e1];
+                    const uint32_t base = (x & 0xFFFFu) * k + j;
+                    const int w = (int)(x >> 16) + wv;
+                    const int d = staged ? (int)delta[(size_t)e1 * n_in + e2c] : 0;
+                    const uint32_t cd = ((e1 - a0[lane]) << 16) | pos[lane];
+                    for (int rr = 0; rr < RC; ++rr) {
+                        int r = r0 + rr - w;
+                        const bool ok = r >= 0 && r0 + rr <= R;
+                        r = r < 0 ? 0 : (r > R ? R : r);
+                        const int32_t c = src[(size_t)r * kk + base] + d;
+                        if (ok && c > best[lane][rr]) { best[lane][rr] = c; code[lane][rr] = cd; }
+                    }
+                }
+            }
+            for (uint32_t rd = 0, off = 1; rd < h.rounds; ++rd, off <<= 1) {
+                int32_t nb[32][RC]; uint32_t nc[32][RC];
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    for (int rr = 0; rr < RC; ++rr) {
+                        const uint32_t o = lane + off < 32 ? lane + off : lane;      // __shfl_down_sync semantics
+                        const int32_t ob = best[o][rr]; const uint32_t oc = code[o][rr];
+                        nb[lane][rr] = best[lane][rr]; nc[lane][rr] = code[lane][rr];
+                        if (pos[lane] + off < seg[lane] && (ob > best[lane][rr] || (ob == best[lane][rr] && oc < code[lane][rr]))) {
+                            if (lane + off >= 32) return -57;
+                            nb[lane][rr] = ob; nc[lane][rr] = oc;
+                        }
+                    }
+                memcpy(best, nb, sizeof best); memcpy(code, nc, sizeof code);
+            }
+            for (uint32_t lane = 0; lane < 32; ++lane) {
+                if (!valid[lane] || pos[lane] != 0) continue;
+                if ((1u << h.rounds) < seg[lane]) return -58;
+                for (int rr = 0; rr < RC; ++rr) {
+                    const int r2 = r0 + rr;
+                    if (r2 > R) continue;
+                    const uint64_t c = (uint64_t)r2 * kk2 + (uint64_t)row[lane] * k2 + j2[lane];
+                    const bool lv = best[lane][rr] >= 0;
+                    if (e.written[c]) return -59;
+                    e.written[c] = 1;
+                    dst[c] = lv ? best[lane][rr] : NEG_INF;
+                    pl[c] = lv ? (PredT)(((code[lane][rr] >> 16) << SH) | (code[lane][rr] & 0xFFFFu)) : (PredT) ~(PredT)0;
+                    if (lv) {
+                        const int pi = (int)(in_edge[a0[lane] + (code[lane][rr] >> 16)] & 0xFFFFu);
+                        const int pj = (int)(in_edge[s0[lane] + (code[lane][rr] & 0xFFFFu)] & 0xFFFFu);
+                        ++e.live[h.level + 1];
+                        e.sum[h.level + 1] += cell_fold(c, best[lane][rr], pi, pj);
+                    }
+                }
+            }
         }
-    } else {
-        switch (rc) {
-            case 8: items<8, false>(t, R, load, store, pl, h, live); break;
-            case 4: items<4, false>(t, R, load, store, pl, h, live); break;
-            case 2: items<2, false>(t, R, load, store, pl, h, live); break;
-            default: items<1, false>(t, R, load, store, pl, h, live); break;
-        }
-    }
+    return 0;
 }
 
 template <class PredT>
-static int run(const DipPlan& p, const SweepShape& sh, int32_t* sink_value, int32_t* sink_s_het, int32_t* p1,
-               int32_t* n1, int32_t* p2, int32_t* n2, uint64_t* level_checksum, uint64_t* level_live) {
+int run(const DipPlan& p, const SweepShape& sh, int trace_T, int64_t* n_lane_tasks, int32_t* sink_value, int32_t* sink_s_het, int32_t* p1,
+        int32_t* n1, int32_t* p2, int32_t* n2, uint64_t* level_checksum, uint64_t* level_live) {
     const int R = p.R, L = p.L;
+    Emu e(p, sh);
     std::vector<PredT> pred((size_t)p.pred_off[L]);
     const size_t widest = (size_t)(R + 1) * p.kmax * p.kmax;
     // poison values make a wrong tile-placement flag visible
-    std::vector<int32_t> g0(widest, 0x5A5A5A5A), g1(widest, 0x5A5A5A5A), s0(sh.tile_cells, 0x3C3C3C3C), s1(sh.tile_cells, 0x3C3C3C3C);
-    for (int r = 0; r <= R; ++r) { g0[r] = 0; s0[r] = 0; }
-    std::vector<uint8_t> stage((size_t)sh.stage_bytes + 16);
+    e.g0.assign(widest, 0x5A5A5A5A); e.g1.assign(widest, 0x5A5A5A5A);
+    e.s0.assign(sh.tile_cells, 0x3C3C3C3C); e.s1.assign(sh.tile_cells, 0x3C3C3C3C);
+    for (int r = 0; r <= R; ++r) { e.g0[r] = 0; e.s0[r] = 0; }
+    e.sum.assign(L, FOLD_BASIS); e.live.assign(L, 0);
+
+    // K4: pair-score matrices (dip_delta_kernel)
+    e.delta.assign((size_t)p.delta_elems, 0xDEAD);
+    for (int l : p.delta_list) {
+        const int32_t mid = p.level_off[l + 1], e0 = p.in_off[mid];
+        const uint32_t n_in = (uint32_t)(p.in_off[p.level_off[l + 2]] - e0);
+        if (p.delta_off[l] % 8 != 0) return -20;
+        uint16_t* D = e.delta.data() + p.delta_off[l];
+        for (uint32_t x = 0; x < n_in * n_in; ++x) {
+            const uint32_t e1 = x / n_in, e2 = x - e1 * n_in;
+            D[x] = (uint16_t)mask_delta(p.lvlW[l], p.masks.data() + p.msrc_off[l], p.masks.data() + p.mdst_off[l],
+                                        (int)(p.in_edge[e0 + e1] & 0xFFFFu), (int)(p.in_edge[e0 + e2] & 0xFFFFu),
+                                        (int)p.in_dst[e0 + e1], (int)p.in_dst[e0 + e2]);
+        }
+    }
+
+    // K5: task streams, executed level by level, CTA by CTA (any order the barriers allow is equivalent)
+    const int G = p.grid;
+    std::vector<int64_t> cur(p.task_begin.begin(), p.task_begin.end() - 1);
+    std::vector<uint8_t> slot((size_t)sh.slot_bytes + 16);
     uint32_t counter = 0;
     for (int l = 0; l + 1 < L; ++l) {
-        uint64_t h = FOLD_BASIS, live = 0;
         PredT* pl = pred.data() + p.pred_off[l + 1];
-        if (p.mode[l] != MODE_GLOBAL) {
-            RecHeader hd;
-            memcpy(&hd, p.records.data() + p.rec_off[l], sizeof hd);
-            if (hd.bytes > (uint32_t)sh.stage_bytes || hd.bytes % 16 != 0 || p.rec_off[l] % 16 != 0) return -10;
-            memcpy(stage.data(), p.records.data() + p.rec_off[l], hd.bytes);
-            TransitionT<uint16_t> t;
-            record_view(stage.data(), hd, t);
-            if ((hd.flags & REC_WAIT) && counter < hd.wait_target) return -11;       // would dead-lock on the GPU
-            const bool ssm = hd.flags & REC_SRC_SMEM, dsm = hd.flags & REC_DST_SMEM;
-            if ((ssm || dsm) && (p.mode[l] != MODE_FAST || hd.P != 1)) return -12;
-            const int32_t* src = ssm ? ((l & 1) ? s1.data() : s0.data()) : ((l & 1) ? g1.data() : g0.data());
-            int32_t* dst = dsm ? ((l & 1) ? s0.data() : s1.data()) : ((l & 1) ? g0.data() : g1.data());
-            if ((ssm && (size_t)(R + 1) * t.k * t.k > (size_t)sh.tile_cells) ||
-                (dsm && (size_t)(R + 1) * t.k2 * t.k2 > (size_t)sh.tile_cells)) return -13;
-            if (hd.pred_off2 != p.pred_off[l + 1]) return -14;
-            cells<PredT>(t, R, (uint64_t)hd.P * sh.cells_per_cta / 4, [src](int64_t i) { return src[i]; }, [dst](size_t c, int32_t v) { dst[c] = v; }, pl, h, live);
-            if (hd.flags & REC_ARRIVE) counter += hd.P;
-        } else {
-            Transition t;
-            t.k = p.level_off[l + 1] - p.level_off[l];
-            t.k2 = p.level_off[l + 2] - p.level_off[l + 1];
-            t.W = p.lvlW[l];
-            t.in_off = p.in_off.data() + p.level_off[l + 1];
-            t.in_edge = p.in_edge.data();
-            t.msrc = p.masks.data() + p.msrc_off[l];
-            t.mdst = p.masks.data() + p.mdst_off[l];
-            if ((p.flags[l] & REC_WAIT) && counter < p.bar_target[l - 1]) return -11;
-            const int32_t* src = (l & 1) ? g1.data() : g0.data();
-            int32_t* dst = (l & 1) ? g0.data() : g1.data();
-            cells<PredT>(t, R, (uint64_t)p.P[l] * sh.cells_per_cta / 4, [src](int64_t i) { return src[i]; }, [dst](size_t c, int32_t v) { dst[c] = v; }, pl, h, live);
-            if (p.flags[l] & REC_ARRIVE) counter += (uint32_t)p.P[l];
+        std::vector<uint8_t> row_done((size_t)(p.level_off[l + 2] - p.level_off[l + 1]), 0);
+        e.written.assign((size_t)(R + 1) * row_done.size() * row_done.size(), 0);
+        uint32_t arrivals = 0;
+        int participants = 0;
+        for (int c = 0; c < G; ++c) {
+            bool first = true, closed = false;
+            while (cur[c] < p.task_begin[(size_t)c + 1] && p.tasks[(size_t)cur[c]].level == l) {
+                const TaskHdr& gh = p.tasks[(size_t)cur[c]++];
+                if (closed) return -30;                         // a task after the CTA's TK_BAR task of this level
+                // --- what the producer warp does: three bulk copies into the slot ---
+                if ((size_t)sizeof(TaskHdr) + gh.rec_bytes + gh.delta_bytes > (size_t)sh.slot_bytes) return -10;
+                if (gh.rec_bytes % 16 || gh.delta_bytes % 16) return -10;
+                std::fill(slot.begin(), slot.end(), (uint8_t)0xEE);
+                memcpy(slot.data(), &gh, sizeof(TaskHdr));
+                if (gh.rec_bytes) {
+                    if ((size_t)gh.rec_off16 * 16 + gh.rec_bytes > p.records.size()) return -10;
+                    memcpy(slot.data() + sizeof(TaskHdr), p.records.data() + (size_t)gh.rec_off16 * 16, gh.rec_bytes);
+                }
+                if (gh.delta_bytes) {
+                    if ((size_t)gh.delta_off16 * 8 + gh.delta_bytes / 2 > e.delta.size() + 8) return -10;
+                    const size_t avail = (e.delta.size() - (size_t)gh.delta_off16 * 8) * 2;
+                    memcpy(slot.data() + sizeof(TaskHdr) + gh.rec_bytes, e.delta.data() + (size_t)gh.delta_off16 * 8,
+                           std::min<size_t>(gh.delta_bytes, avail));
+                }
+                // --- what the compute warps do ---
+                TaskHdr h;
+                memcpy(&h, slot.data(), sizeof h);
+                const bool needs_wait = l > 0 && p.bar_edge[l - 1];
+                if (first) {
+                    if (needs_wait != ((h.flags & TK_WAIT) != 0)) return -11;
+                    if (needs_wait && (h.wait_target != p.bar_target[l - 1] || counter < h.wait_target)) return -11;   // would race / dead-lock
+                } else if (h.flags & TK_WAIT) return -11;
+                first = false;
+                if (c >= p.P[l]) return -12;
+                const bool ssm = h.flags & TK_SRC_SMEM, dsm = h.flags & TK_DST_SMEM;
+                if ((ssm || dsm) && (!p.narrow[l] || c != 0)) return -12;
+                if ((ssm && (size_t)(R + 1) * h.k * h.k > (size_t)sh.tile_cells) ||
+                    (dsm && (size_t)(R + 1) * h.k2 * h.k2 > (size_t)sh.tile_cells)) return -13;
+                if (h.pred_off2 != p.pred_off[l + 1] || h.i0 >= h.i1 || h.i1 > h.k2) return -14;
+                if ((uint64_t)(h.i1 - h.i0) * h.k2 * h.k2 >= (1ull << 32)) return -14;    // div_magic exactness
+                const int32_t* src = ssm ? ((l & 1) ? e.s1.data() : e.s0.data()) : ((l & 1) ? e.g1.data() : e.g0.data());
+                int32_t* dst = dsm ? ((l & 1) ? e.s0.data() : e.s1.data()) : ((l & 1) ? e.g0.data() : e.g1.data());
+                for (int x = h.i0; x < h.i1; ++x) { if (row_done[x]) return -16; row_done[x] = 1; }
+                if (h.flags & TK_LANES) {
+                    if ((h.flags & TK_REC_GLOBAL) || ssm != dsm) return -60;
+                    if (h.rc != LANE_RC_BIG && h.rc != LANE_RC_SMALL) return -61;
+                    const int lrc = h.rc == LANE_RC_BIG ? lane_items<PredT, LANE_RC_BIG>(e, slot.data(), h, src, dst, pl)
+                                                        : lane_items<PredT, LANE_RC_SMALL>(e, slot.data(), h, src, dst, pl);
+                    if (lrc) return lrc;
+                    ++e.n_lane_tasks;
+                } else if (!(h.flags & TK_REC_GLOBAL)) {
+                    TransitionT<uint16_t> t;
+                    t.k = h.k; t.k2 = h.k2;
+                    t.in_off = reinterpret_cast<const uint16_t*>(slot.data() + sizeof(TaskHdr));
+                    t.in_edge = reinterpret_cast<const uint32_t*>(slot.data() + sizeof(TaskHdr) + rec_edge_offset(h.k2));
+                    t.delta = nullptr; t.dstride = h.n_in; t.e1_base = 0; t.e2_base = 0; t.W = 0; t.msrc = t.mdst = nullptr;
+                    if (h.flags & TK_DELTA_STAGED) {
+                        t.delta = reinterpret_cast<const uint16_t*>(slot.data() + sizeof(TaskHdr) + h.rec_bytes) + h.delta_skew;
+                        t.e1_base = (int32_t)t.in_off[h.i0];
+                    } else if (h.flags & TK_DELTA) {
+                        t.delta = e.delta.data() + p.delta_off[l];
+                    } else if (h.flags & TK_DELTA_MASKS) {
+                        t.W = p.lvlW[l]; t.msrc = p.masks.data() + p.msrc_off[l]; t.mdst = p.masks.data() + p.mdst_off[l];
+                    }
+                    by_dm<PredT, uint16_t>(e, t, h, src, dst, pl);
+                } else {
+                    const int32_t mid = p.level_off[l + 1], ebase = p.in_off[mid];
+                    TransitionT<int32_t> t;
+                    t.k = h.k; t.k2 = h.k2;
+                    t.in_off = p.in_off.data() + mid; t.in_edge = p.in_edge.data();
+                    t.delta = nullptr; t.dstride = p.in_off[p.level_off[l + 2]] - ebase; t.e1_base = ebase; t.e2_base = ebase;
+                    t.W = 0; t.msrc = t.mdst = nullptr;
+                    if (h.flags & TK_DELTA) t.delta = e.delta.data() + p.delta_off[l];
+                    else if (h.flags & TK_DELTA_MASKS) {
+                        t.W = p.lvlW[l]; t.msrc = p.masks.data() + p.msrc_off[l]; t.mdst = p.masks.data() + p.mdst_off[l];
+                    }
+                    by_dm<PredT, int32_t>(e, t, h, src, dst, pl);
+                }
+                if (h.flags & TK_BAR) closed = true;
+                if (h.flags & TK_ARRIVE) { if (!(h.flags & TK_BAR)) return -17; ++arrivals; }
+            }
+            if (!first) { ++participants; if (!closed) return -18; }
         }
+        for (uint8_t d : row_done) if (!d) return -19;
+        for (uint8_t d : e.written) if (!d) return -25;             // every cell of the level was stored              // every destination row belongs to exactly one task
+        if (participants != p.P[l]) return -21;
+        if (p.bar_edge[l] ? (arrivals != (uint32_t)p.P[l]) : (arrivals != 0)) return -22;
+        counter += arrivals;
         if (counter != p.bar_target[l]) return -15;
-        if (level_checksum) { level_checksum[l + 1] = h; level_live[l + 1] = live; }
+        if (level_checksum) { level_checksum[l + 1] = e.sum[l + 1]; level_live[l + 1] = e.live[l + 1]; }
     }
+    for (int c = 0; c < G; ++c) if (cur[c] != p.task_begin[(size_t)c + 1]) return -23;
+    if (e.bad_rc) return -24;
+    if (n_lane_tasks) *n_lane_tasks = e.n_lane_tasks;
+
+    // K7: checkpointed traceback (dip_anc_kernel / dip_hop_kernel / dip_seg_kernel / dip_merge_kernel)
     const size_t ks = (size_t)(p.level_off[L] - p.level_off[L - 1]);
-    const std::vector<int32_t>& last = ((L - 1) & 1) ? g1 : g0;     // the sink layer must be in global memory
+    const std::vector<int32_t>& last = ((L - 1) & 1) ? e.g1 : e.g0;     // the sink layer must be in global memory
     *sink_value = last[(size_t)R * ks * ks];   // cell (r=R,0,0) of the last level (:730, :775)
     TraceView v;
     v.L = L; v.R = R; v.level_off = p.level_off.data(); v.in_off = p.in_off.data(); v.in_edge = p.in_edge.data();
     v.lvlW = p.lvlW.data(); v.msrc_off = p.msrc_off.data(); v.mdst_off = p.mdst_off.data();
     v.masks = p.masks.data(); v.pred_off = p.pred_off.data();
-    std::vector<int32_t> a(2 * (R + 2)), b(2 * (R + 2));
-    int rc = traceback<PredT>(v, pred.data(), *sink_value, a.data(), n1, b.data(), n2, R + 2, sink_s_het);
-    if (rc == -1) { *n1 = 0; *n2 = 0; return 0; }
-    if (rc) return rc;
+    std::vector<int32_t> cp;
+    for (int l = L - 1; l > 0; l -= trace_T) cp.push_back(l);
+    cp.push_back(0);
+    const int M = (int)cp.size() - 1;
+    const int cap = R + 2;
+    *n1 = 0; *n2 = 0; *sink_s_het = 0;
+    if (*sink_value == NEG_INF) return 0;
+    auto state_of = [&](int64_t cell, int l, TraceState& s) {
+        const int32_t k = p.level_off[l + 1] - p.level_off[l];
+        s.r = (int32_t)(cell / ((int64_t)k * k));
+        const int32_t rem = (int32_t)(cell - (int64_t)s.r * k * k);
+        s.i2 = rem / k; s.j2 = rem - s.i2 * k;
+    };
+    std::vector<int32_t> a, b;
+    int64_t cur_cell = (int64_t)R * ks * ks;
+    int sh_total = 0;
+    for (int m = 0; m < M; ++m) {
+        // hop: the ancestor of cur_cell at cp[m+1] (what dip_anc_kernel stores for every cell of cp[m])
+        TraceState s;
+        state_of(cur_cell, cp[m], s);
+        TraceState w = s;
+        for (int l = cp[m] - 1; l >= cp[m + 1]; --l) {
+            int wu, wv, i2, j2;
+            if (!trace_step<PredT>(v, pred.data(), l, w, wu, wv, i2, j2)) return -40;
+        }
+        // segment walk
+        std::vector<int32_t> sa(2 * cap), sb(2 * cap);
+        int32_t sn1 = 0, sn2 = 0, ssh = 0;
+        const int rc = trace_segment<PredT>(v, pred.data(), cp[m], cp[m + 1], s, sa.data(), &sn1, sb.data(), &sn2, cap, &ssh);
+        if (rc) return rc == -2 ? -2 : -41;
+        if (s.r != w.r || s.i2 != w.i2 || s.j2 != w.j2) return -42;
+        a.insert(a.end(), sa.begin(), sa.begin() + 2 * sn1);
+        b.insert(b.end(), sb.begin(), sb.begin() + 2 * sn2);
+        sh_total += ssh;
+        const int32_t k = p.level_off[cp[m + 1] + 1] - p.level_off[cp[m + 1]];
+        cur_cell = ((int64_t)w.r * k + w.i2) * k + w.j2;
+    }
+    if ((int)a.size() > 2 * cap || (int)b.size() > 2 * cap) return -2;
+    *n1 = (int32_t)a.size() / 2; *n2 = (int32_t)b.size() / 2; *sink_s_het = sh_total;
     for (int x = 0; x < *n1; ++x) { p1[2 * x] = a[2 * (*n1 - 1 - x)]; p1[2 * x + 1] = a[2 * (*n1 - 1 - x) + 1]; }
     for (int x = 0; x < *n2; ++x) { p2[2 * x] = b[2 * (*n2 - 1 - x)]; p2[2 * x + 1] = b[2 * (*n2 - 1 - x) + 1]; }
     return 0;
 }
 
-// shape: [grid, cells_per_cta, tile_cells, stage_bytes] (0 = kernel default)
+}  // namespace
+
+// shape: [grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, lane_rc] (0 = kernel default)
+// counts: [narrow transitions, wide transitions, tasks, tasks with in-place records, tasks with on-the-fly masks, matrices,
+//          tasks run in lane form]
 extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
                               const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off,
                               const int32_t* col_val, const uint8_t* colour_is_hom, int32_t n_colours, int32_t R,
                               int32_t* sink_value, int32_t* sink_s_het, int32_t* p1_edges, int32_t* n_p1,
                               int32_t* p2_edges, int32_t* n_p2, uint64_t* level_checksum, uint64_t* level_live,
-                              int32_t force_pred32, const int32_t* shape, int64_t* mode_counts) {
+                              int32_t force_pred32, const int32_t* shape, int64_t* counts) {
     DipGraphView g;
     g.n_levels = n_levels; g.level_off = level_off; g.adj_off = adj_off; g.adj_dst = adj_dst; g.adj_w = adj_w;
     g.col_off = col_off; g.col_val = col_val; g.colour_is_hom = colour_is_hom; g.n_colours = n_colours; g.R = R;
     DipPlan p;
     if (!build_dip_plan(g, p)) return -1;
     SweepShape sh;
-    sh.grid = 148; sh.cells_per_cta = 2048; sh.tile_cells = 16384; sh.stage_bytes = 16384;
+    sh.grid = 32; sh.threads = 480; sh.tile_cells = 16384; sh.slot_bytes = 4096;
+    int trace_T = 128;
     if (shape) {
         if (shape[0] > 0) sh.grid = shape[0];
-        if (shape[1] > 0) sh.cells_per_cta = shape[1];
+        if (shape[1] > 0) sh.threads = shape[1];
         if (shape[2] > 0) sh.tile_cells = shape[2];
-        if (shape[3] > 0) sh.stage_bytes = shape[3];
+        if (shape[3] > 0) sh.slot_bytes = shape[3];
+        if (shape[4] > 0) sh.delta_max_in = shape[4];
+        if (shape[4] < 0) sh.delta_max_in = 0;
+        if (shape[5] > 0) trace_T = shape[5];
+        if (shape[6] > 0) sh.lane_rc = shape[6];
     }
-    plan_sweep(p, sh);
-    if (mode_counts) { mode_counts[0] = p.n_fast; mode_counts[1] = p.n_staged; mode_counts[2] = p.n_global; }
+    plan_tasks(p, sh);
+    if (counts) {
+        counts[0] = p.n_narrow; counts[1] = p.n_wide; counts[2] = (int64_t)p.tasks.size();
+        counts[3] = p.n_tasks_global; counts[4] = p.n_tasks_masks; counts[5] = (int64_t)p.delta_list.size();
+    }
     if (p.max_indeg <= 255 && !force_pred32)
-        return run<uint16_t>(p, sh, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
-    return run<uint32_t>(p, sh, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
+        return run<uint16_t>(p, sh, trace_T, counts ? counts + 6 : nullptr, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
+    return run<uint32_t>(p, sh, trace_T, counts ? counts + 6 : nullptr, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
 }

@@ -119,11 +119,23 @@ def test_lane_panel_model(oracle_mod, dp_emu):
         assert_dip_equal(oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R))
 
 
-@pytest.mark.parametrize("shape", [(148, 2048, 16384, 16384), (8, 64, 256, 512), (4, 32, 64, 96), (3, 16, 100000, 64)])
+# (grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T[, lane_rc])
+SHAPES = [
+    (32, 480, 16384, 4096, 0, 0),       # the kernel's geometry
+    (32, 480, 16384, 4096, 0, 0, 8),    # ... with 8 layers per lane
+    (8, 64, 256, 512, 0, 5),            # small tiles and slots: narrow/wide hand-overs, row-split tasks
+    (4, 32, 64, 160, 0, 3),             # slots too small for most records: in-place records
+    (3, 16, 100000, 256, -1, 1),        # no matrices: on-the-fly masks everywhere (never narrow when coloured)
+    (5, 32, 300, 200, 6, 2),            # matrices only for very few in-edges: mixed matrix / masks
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
 def test_all_sweep_modes_agree(shape, oracle_mod, dp_emu):
-    """FAST (shared-memory layers), STAGED (records through shared memory, layers in HBM) and GLOBAL
-    (metadata in place) transitions, and every hand-over between them, give the same layers."""
-    seen = dict(fast=0, staged=0, global_=0)
+    """Narrow (shared-memory layers) and wide (row-split over CTAs, layers in HBM) transitions, staged and
+    in-place records, staged / in-place / on-the-fly pair scores, and every hand-over between them, give the
+    same layers, and the checkpointed traceback gives the same lists for any checkpoint distance."""
+    seen = dict(narrow=0, wide=0, tasks=0, tasks_global=0, tasks_masks=0, matrices=0, tasks_lanes=0)
     for seed in range(12):
         rng = np.random.default_rng(77 + seed)
         g = synth.random_level_graph(500 + seed, n_levels=int(rng.integers(3, 30)), max_width=int(rng.integers(2, 12)),
@@ -133,15 +145,23 @@ def test_all_sweep_modes_agree(shape, oracle_mod, dp_emu):
         assert_dip_equal(oracle_dip(oracle_mod, g, R), o)
         for k in seen:
             seen[k] += o["modes"][k]
-    if shape == (8, 64, 256, 512):
-        assert seen["fast"] > 0 and seen["staged"] > 0
-    if shape == (4, 32, 64, 96):
-        assert seen["global_"] > 0
+    if shape[0] in (32, 8):
+        assert 0 < seen["tasks_lanes"] < seen["tasks"]    # both evaluation forms are exercised
+    if shape[0] == 8:
+        assert seen["narrow"] > 0 and seen["wide"] > 0 and seen["tasks"] > seen["narrow"] + seen["wide"]
+    if shape[0] == 4:
+        assert seen["tasks_global"] > 0
+    if shape[0] == 3:
+        assert seen["tasks_masks"] > 0 and seen["matrices"] == 0
+    if shape[0] == 5:
+        assert seen["tasks_masks"] > 0 and seen["matrices"] > 0
 
 
 def test_mhc_mode_mix(dp_emu):
     g, _ = LevelGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_dipin.npz"))
     o = dp_emu.dp_diploid(g, 0)
     m = o["modes"]
-    assert m["fast"] + m["staged"] + m["global_"] == g.n_levels - 1
-    assert m["fast"] > 0.9 * g.n_levels        # the bundled panel is almost entirely shared-memory resident
+    assert m["narrow"] + m["wide"] == g.n_levels - 1
+    assert m["narrow"] > 0.9 * g.n_levels        # the bundled panel is almost entirely shared-memory resident
+    assert m["tasks_global"] == 0 and m["tasks_masks"] == 0
+    assert m["tasks_lanes"] > 0.95 * m["tasks"]           # nearly every task of real data takes the lane form
