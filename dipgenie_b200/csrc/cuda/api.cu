@@ -6,6 +6,11 @@
 extern "C" {
 
 dg_ctx* dg_create(int device) {
+    // Batch slots are long-running persistent kernels on separate streams: with the default of 8 hardware
+    // work queues, streams 9+ share a queue with a resident sweep and wait for it (measured on B200: 12 slots
+    // ran as two waves).  Only effective if set before the process creates its CUDA context; hosts that
+    // initialise CUDA earlier (PyTorch) must export it themselves.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return nullptr;
     if (cudaSetDevice(device) != cudaSuccess) return nullptr;
@@ -30,6 +35,7 @@ dg_ctx* dg_create(int device) {
 void dg_destroy(dg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (cudaStream_t s : ctx->batch_streams) cudaStreamDestroy(s);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

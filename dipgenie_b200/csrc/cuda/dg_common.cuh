@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <vector>
 
 #include "../../../include/dipgenie_cuda.h"
 
@@ -13,6 +14,7 @@ struct dg_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    std::vector<cudaStream_t> batch_streams;   // dg_dp_diploid_batch: one per concurrently resident sample
     std::string err;
     dg_sketch_stats_t sketch_stats = {};
 };

@@ -22,8 +22,16 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
+
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
 
 #include "dg_common.cuh"
 #include "dp_cell.h"
@@ -638,6 +646,10 @@ __global__ void dip_merge_kernel(const TraceArgs a) {
 using namespace dg;
 
 struct dg_dip {
+    cudaStream_t stream = nullptr;   // the context's stream, or one of the batch streams
+    bool cooperative = true;         // batch slots use plain launches (see dip_run_impl)
+    std::vector<int32_t> h_cp;       // traceback checkpoints (host copies until uploaded)
+    std::vector<int64_t> h_aoff;
     DipPlan plan;                 // host copy (small arrays kept for stats; big ones released after upload)
     int pred_bytes = 2;
     int grid = 1;
@@ -681,25 +693,35 @@ static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out) {
-    *out = nullptr;
-    DG_CUDA(ctx, cudaSetDevice(ctx->device));
-    std::unique_ptr<dg_dip> d(new dg_dip());
-    const double t_plan0 = now_ms();
-    if (!build_dip_plan(g, d->plan)) return fail(ctx, DG_ERR_ARG, "dg_dip_create: %s", d->plan.error.c_str());
-    DipPlan& p = d->plan;
-    const int L = p.L;
-    d->pred_bytes = (p.max_indeg <= 255) ? 2 : 4;
+// What the kernels' geometry and the device allow (queried once per call that plans problems).
+struct DipLimits {
+    int max_grid = 1;
+    int64_t delta_budget = 0;
+};
 
-    // grid: enough CTAs that the widest transition leaves about 16 candidates per thread, at most one
-    // co-resident wave (cooperative launch)
-    const void* fnc = sweep_fn(d->pred_bytes == 4, false);
+static int dip_limits(dg_ctx* ctx, DipLimits& lim) {
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
     for (int v = 0; v < 8; ++v)
         DG_CUDA(ctx, cudaFuncSetAttribute(sweep_fn(v & 1, v & 2, v & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
     int per_sm = 0;
-    DG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fnc, DIP_THREADS, DIP_SMEM_BYTES));
+    DG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_fn(false, false), DIP_THREADS, DIP_SMEM_BYTES));
     if (per_sm < 1) return fail(ctx, DG_ERR_CUDA, "dg_dip_create: sweep kernel cannot be resident");
-    int max_grid = ctx->sm_count * per_sm;
+    lim.max_grid = ctx->sm_count * per_sm;
+    size_t free_b = 0, total_b = 0;
+    DG_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    lim.delta_budget = (int64_t)(free_b / 8);
+    return DG_OK;
+}
+
+// Host half of dg_dip_create: no CUDA calls, safe to run for several problems on several host threads.
+static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_cap, dg_dip* d) {
+    const double t_plan0 = now_ms();
+    if (!build_dip_plan(g, d->plan)) return false;
+    DipPlan& p = d->plan;
+    const int L = p.L;
+    d->pred_bytes = (p.max_indeg <= 255) ? 2 : 4;
+    // grid: enough CTAs that the widest transition leaves about 16 candidates per thread, at most one
+    // co-resident wave
     uint64_t widest_cand = 0;
     for (int l = 0; l + 1 < L; ++l) {
         const uint64_t n_in = (uint64_t)(p.in_off[p.level_off[l + 2]] - p.in_off[p.level_off[l + 1]]);
@@ -707,35 +729,56 @@ static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out) {
     }
     uint64_t want = (widest_cand + (uint64_t)DIP_CT * 16 - 1) / ((uint64_t)DIP_CT * 16);
     if (const char* e = getenv("DG_DIP_GRID")) want = (uint64_t)std::max(1, atoi(e));   // diagnostics / tuning
+    if (grid_cap > 0) want = std::min<uint64_t>(want, (uint64_t)grid_cap);
     SweepShape shape;
-    shape.grid = (int)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)max_grid);
+    shape.grid = (int)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)lim.max_grid);
     shape.threads = DIP_CT;
     shape.tile_cells = DIP_TILE_CELLS;
     shape.slot_bytes = DIP_SLOT_BYTES;
     if (const char* e = getenv("DG_LANE_RC")) shape.lane_rc = atoi(e);   // diagnostics / tuning
-    size_t free_b = 0, total_b = 0;
-    DG_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-    shape.delta_budget = (int64_t)(free_b / 8);
+    shape.delta_budget = lim.delta_budget;
     plan_tasks(p, shape);
     d->grid = 1;
     for (int c = 0; c < p.grid; ++c) if (p.task_begin[(size_t)c + 1] > p.task_begin[c]) d->grid = c + 1;
-
     // traceback checkpoints: cp[0] = sink level, every DIP_TRACE_T levels down to level 0
-    std::vector<int32_t> cp;
-    std::vector<int64_t> aoff;
-    for (int l = L - 1; l > 0; l -= DIP_TRACE_T) cp.push_back(l);
-    cp.push_back(0);
-    d->M = (int)cp.size() - 1;
-    aoff.assign((size_t)d->M + 1, 0);
+    d->h_cp.clear();
+    for (int l = L - 1; l > 0; l -= DIP_TRACE_T) d->h_cp.push_back(l);
+    d->h_cp.push_back(0);
+    d->M = (int)d->h_cp.size() - 1;
+    d->h_aoff.assign((size_t)d->M + 1, 0);
     for (int m = 0; m < d->M; ++m) {
-        const int64_t k = p.level_off[cp[m] + 1] - p.level_off[cp[m]];
-        aoff[(size_t)m + 1] = aoff[m] + (int64_t)(p.R + 1) * k * k;
+        const int64_t k = p.level_off[d->h_cp[m] + 1] - p.level_off[d->h_cp[m]];
+        d->h_aoff[(size_t)m + 1] = d->h_aoff[m] + (int64_t)(p.R + 1) * k * k;
     }
-    d->anc_cells = aoff[d->M];
+    d->anc_cells = d->h_aoff[d->M];
     d->plan_ms = (float)(now_ms() - t_plan0);
+    return true;
+}
 
+static int dip_create_device(dg_ctx* ctx, dg_dip* d);
+
+static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out, cudaStream_t stream = nullptr, int grid_cap = 0) {
+    *out = nullptr;
+    DipLimits lim;
+    if (int rc = dip_limits(ctx, lim)) return rc;
+    std::unique_ptr<dg_dip> d(new dg_dip());
+    d->stream = stream ? stream : ctx->stream;
+    d->cooperative = stream == nullptr;
+    if (!dip_plan_host(g, lim, grid_cap, d.get())) return fail(ctx, DG_ERR_ARG, "dg_dip_create: %s", d->plan.error.c_str());
+    if (int rc = dip_create_device(ctx, d.get())) return rc;
+    *out = d.release();
+    return DG_OK;
+}
+
+// Device half: allocations from the stream-ordered pool and H2D copies on the problem's stream.
+static int dip_create_device(dg_ctx* ctx, dg_dip* d) {
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DipPlan& p = d->plan;
+    const int L = p.L;
+    const std::vector<int32_t>& cp = d->h_cp;
+    const std::vector<int64_t>& aoff = d->h_aoff;
     const double t_up0 = now_ms();
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = d->stream;
     DG_CUDA(ctx, d->tasks.upload(p.tasks.data(), p.tasks.size(), s));
     DG_CUDA(ctx, d->task_begin.upload(p.task_begin.data(), p.task_begin.size(), s));
     DG_CUDA(ctx, d->records.upload(p.records.data(), p.records.size(), s));
@@ -786,14 +829,13 @@ static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out) {
     std::vector<uint64_t>().swap(p.masks);
     std::vector<int32_t>().swap(p.in_off);
     std::vector<TaskHdr>().swap(p.tasks);
-    *out = d.release();
     return DG_OK;
 }
 
 template <class PredT>
 static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     const DipPlan& p = d->plan;
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = d->stream;
     DG_CUDA(ctx, cudaMemsetAsync(d->counter.p, 0, sizeof(unsigned int), s));
     DG_CUDA(ctx, cudaMemsetAsync(d->tile0.p, 0, (size_t)(p.R + 1) * sizeof(int32_t), s));   // dp_cur.assign(R+1, {0,0}) :535
     if (check) {
@@ -827,7 +869,12 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     if (p.L > 1) {
         void* args[] = {(void*)&a};
         const void* fn = sweep_fn(sizeof(PredT) == 4, check, d->want_prof);
-        DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, s));
+        // A lone problem is launched cooperatively (the driver guarantees that its CTAs are co-resident, which the
+        // counter barrier needs).  Batch slots use plain launches: B200 runs at most 8 cooperative grids at a time
+        // (measured: 12 slots took two waves), and the batch scheduler already keeps slots x CTAs within the SM
+        // count with one CTA per SM (197 KB of shared memory each), so every grid becomes resident as a whole.
+        if (d->cooperative) DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, s));
+        else DG_CUDA(ctx, cudaLaunchKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, s));
         ++d->launches;
     }
     DG_CUDA(ctx, cudaEventRecord(d->ev[2], s));
@@ -859,6 +906,16 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     return DG_OK;
 }
 
+static int batch_stream(dg_ctx* ctx, int slot, cudaStream_t* out) {
+    while ((int)ctx->batch_streams.size() <= slot) {
+        cudaStream_t s = nullptr;
+        DG_CUDA(ctx, cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        ctx->batch_streams.push_back(s);
+    }
+    *out = ctx->batch_streams[(size_t)slot];
+    return DG_OK;
+}
+
 extern "C" {
 
 int dg_dip_create(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
@@ -886,7 +943,7 @@ int dg_dip_result(dg_ctx* ctx, dg_dip* d, int32_t* sink_value, int32_t* sink_s_h
     const int cap = d->plan.R + 2;
     TraceOut t;
     std::vector<int32_t> a((size_t)2 * cap), b((size_t)2 * cap);
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = d->stream;
     DG_CUDA(ctx, cudaMemcpyAsync(&t, d->tout.p, sizeof t, cudaMemcpyDeviceToHost, s));
     DG_CUDA(ctx, cudaMemcpyAsync(a.data(), d->p1.p, a.size() * 4, cudaMemcpyDeviceToHost, s));
     DG_CUDA(ctx, cudaMemcpyAsync(b.data(), d->p2.p, b.size() * 4, cudaMemcpyDeviceToHost, s));
@@ -907,7 +964,7 @@ int dg_dip_result(dg_ctx* ctx, dg_dip* d, int32_t* sink_value, int32_t* sink_s_h
 int dg_dip_checksums(dg_ctx* ctx, dg_dip* d, uint64_t* level_checksum, uint64_t* level_live) {
     if (!ctx || !d || !d->ran || !d->checks) return fail(ctx, DG_ERR_ARG, "dg_dip_checksums: run with flags bit0 first");
     DG_CUDA(ctx, cudaSetDevice(ctx->device));
-    DG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DG_CUDA(ctx, cudaStreamSynchronize(d->stream));
     DG_CUDA(ctx, cudaMemcpy(level_checksum, d->level_sum.p, (size_t)d->plan.L * 8, cudaMemcpyDeviceToHost));
     DG_CUDA(ctx, cudaMemcpy(level_live, d->level_live.p, (size_t)d->plan.L * 8, cudaMemcpyDeviceToHost));
     return DG_OK;
@@ -933,7 +990,7 @@ int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out) {
 int dg_dip_profile(dg_ctx* ctx, dg_dip* d, uint64_t* out24) {
     if (!ctx || !d || !d->ran || !d->want_prof) return fail(ctx, DG_ERR_ARG, "dg_dip_profile: run with flags bit1 first");
     DG_CUDA(ctx, cudaSetDevice(ctx->device));
-    DG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DG_CUDA(ctx, cudaStreamSynchronize(d->stream));
     memset(out24, 0, 24 * 8);
     DG_CUDA(ctx, cudaMemcpy(out24, d->prof.p, 24 * 8, cudaMemcpyDeviceToHost));
     return DG_OK;
@@ -963,6 +1020,148 @@ int dg_dp_diploid(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off, const
     if (timing)
         fprintf(stderr, "dg_dp_diploid: create %.1f ms (plan %.1f, alloc+upload %.1f) launch %.1f wait+result %.1f (sweep %.1f trace %.1f) destroy %.1f\n",
                 t1 - t0, plan_ms, upload_ms, t2 - t1, t3 - t2, sweep_ms, trace_ms, now_ms() - t3);
+    return rc;
+}
+
+int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip_output_t* out, int32_t max_concurrent,
+                        int32_t ctas_per_sample) {
+    if (!ctx || n < 0 || (n > 0 && (!in || !out))) return DG_ERR_ARG;
+    if (n == 0) return DG_OK;
+    DipLimits lim;
+    if (int r = dip_limits(ctx, lim)) return r;
+    const int grid = ctas_per_sample > 0 ? ctas_per_sample : 4;
+    int K = std::max(1, std::min(ctx->sm_count / grid, 32));    // slots x CTAs must fit the SMs (plain launches, spin barrier); 32 work queues
+    if (max_concurrent > 0) K = std::min(K, (int)max_concurrent);
+    K = std::min(K, (int)n);
+    { cudaStream_t last = nullptr; if (int r = batch_stream(ctx, K - 1, &last)) return r; }
+
+    // planning (host only) runs ahead on a few worker threads, each with its share of the cores; this thread
+    // uploads, launches and collects in sample order
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int W = std::max(1, std::min({(int)n, 4, hw / 2}));
+    const int lookahead = 2 * W + 2;
+    std::vector<std::unique_ptr<dg_dip>> planned((size_t)n);
+    std::vector<int> state((size_t)n, 0);                       // 0 pending, 1 planned, -1 failed
+    std::vector<std::string> perr((size_t)n);
+    std::mutex mu;
+    std::condition_variable cv;
+    int next = 0, consumed = 0;
+    auto worker = [&]() {
+#if defined(_OPENMP)
+        omp_set_num_threads(std::max(1, hw / W));
+#endif
+        for (;;) {
+            int i;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return next >= n || next < consumed + lookahead; });
+                if (next >= n) return;
+                i = next++;
+            }
+            const dg_dip_input_t& x = in[i];
+            std::unique_ptr<dg_dip> d(new dg_dip());
+            d->stream = ctx->batch_streams[(size_t)(i % K)];
+            d->cooperative = false;
+            DipGraphView g;
+            g.n_levels = x.n_levels; g.level_off = x.level_off; g.adj_off = x.adj_off; g.adj_dst = x.adj_dst; g.adj_w = x.adj_w;
+            g.col_off = x.col_off; g.col_val = x.col_val; g.colour_is_hom = x.colour_is_hom; g.n_colours = x.n_colours; g.R = x.R;
+            bool ok = x.R + 2 <= DG_BATCH_MAX_EDGES;
+            std::string err = ok ? "" : "R + 2 > DG_BATCH_MAX_EDGES";
+            if (ok) { ok = dip_plan_host(g, lim, grid, d.get()); if (!ok) err = d->plan.error; }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (ok) planned[(size_t)i] = std::move(d); else perr[(size_t)i] = err;
+                state[(size_t)i] = ok ? 1 : -1;
+            }
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int w = 0; w < W; ++w) pool.emplace_back(worker);
+
+    std::vector<dg_dip*> slot((size_t)K, nullptr);
+    std::vector<int32_t> owner((size_t)K, -1);
+    int rc = DG_OK;
+    auto collect = [&](int k) {
+        if (!slot[(size_t)k]) return;
+        dg_dip_output_t& o = out[owner[(size_t)k]];
+        const int r = dg_dip_result(ctx, slot[(size_t)k], &o.sink_value, &o.sink_s_het, o.p1_edges, &o.n_p1, o.p2_edges, &o.n_p2);
+        o.status = r;
+        if (r && !rc) rc = r;
+        dg_dip_destroy(ctx, slot[(size_t)k]);
+        slot[(size_t)k] = nullptr;
+    };
+    for (int32_t i = 0; i < n; ++i) {
+        std::unique_ptr<dg_dip> d;
+        int st;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return state[(size_t)i] != 0; });
+            st = state[(size_t)i];
+            d = std::move(planned[(size_t)i]);
+            consumed = i + 1;
+        }
+        cv.notify_all();
+        memset(&out[i], 0, sizeof out[i]);
+        if (st < 0) {
+            out[i].status = fail(ctx, perr[(size_t)i] == "R + 2 > DG_BATCH_MAX_EDGES" ? DG_ERR_CAPACITY : DG_ERR_ARG,
+                                 "dg_dp_diploid_batch: sample %d: %s", (int)i, perr[(size_t)i].c_str());
+            if (!rc) rc = out[i].status;
+            continue;
+        }
+        const int k = i % K;
+        collect(k);                               // the slot's previous sample (its kernels ran while the host planned others)
+        int r = dip_create_device(ctx, d.get());
+        if (!r) r = dg_dip_run(ctx, d.get(), 0);
+        if (r) { out[i].status = r; if (!rc) rc = r; continue; }
+        slot[(size_t)k] = d.release(); owner[(size_t)k] = i;
+    }
+    for (std::thread& t : pool) t.join();
+    for (int k = 0; k < K; ++k) collect(k);
+    return rc;
+}
+
+int dg_dip_create_slot(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
+                       const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off, const int32_t* col_val,
+                       const uint8_t* colour_is_hom, int32_t n_colours, int32_t R, int32_t slot, int32_t ctas, dg_dip** out) {
+    if (!ctx || !out || slot < 0 || slot >= 1024) return DG_ERR_ARG;
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = nullptr;
+    if (int rc = batch_stream(ctx, slot, &s)) return rc;
+    DipGraphView g;
+    g.n_levels = n_levels; g.level_off = level_off; g.adj_off = adj_off; g.adj_dst = adj_dst; g.adj_w = adj_w;
+    g.col_off = col_off; g.col_val = col_val; g.colour_is_hom = colour_is_hom; g.n_colours = n_colours; g.R = R;
+    return dip_create_impl(ctx, g, out, s, ctas > 0 ? ctas : 8);
+}
+
+int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
+    if (!ctx || n < 0 || (n > 0 && !ds)) return DG_ERR_ARG;
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    DG_CUDA(ctx, cudaEventCreate(&e0));
+    DG_CUDA(ctx, cudaEventCreate(&e1));
+    std::vector<cudaEvent_t> done((size_t)n, nullptr);
+    int rc = DG_OK;
+    int64_t ctas = 0;
+    for (int32_t i = 0; i < n; ++i) if (ds[i] && !ds[i]->cooperative) ctas += ds[i]->grid;
+    if (ctas > ctx->sm_count) return fail(ctx, DG_ERR_CAPACITY, "dg_dip_run_many: %lld sweep CTAs do not fit %d SMs", (long long)ctas, ctx->sm_count);
+    DG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    for (int32_t i = 0; i < n && !rc; ++i) {
+        if (!ds[i]) { rc = DG_ERR_ARG; break; }
+        DG_CUDA(ctx, cudaStreamWaitEvent(ds[i]->stream, e0, 0));
+        rc = dg_dip_run(ctx, ds[i], 0);
+        if (rc) break;
+        DG_CUDA(ctx, cudaEventCreateWithFlags(&done[(size_t)i], cudaEventDisableTiming));
+        DG_CUDA(ctx, cudaEventRecord(done[(size_t)i], ds[i]->stream));
+        DG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, done[(size_t)i], 0));
+    }
+    DG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    DG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    if (!rc) DG_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    if (wall_ms) *wall_ms = ms;
+    for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }
 

@@ -41,6 +41,21 @@ class SketchStats(C.Structure):
                 ("kernel_ms", C.c_float), ("launches", C.c_int32)]
 
 
+DG_BATCH_MAX_EDGES = 64
+
+
+class DipInput(C.Structure):
+    _fields_ = [("n_levels", C.c_int32), ("level_off", C.c_void_p), ("adj_off", C.c_void_p), ("adj_dst", C.c_void_p),
+                ("adj_w", C.c_void_p), ("col_off", C.c_void_p), ("col_val", C.c_void_p), ("colour_is_hom", C.c_void_p),
+                ("n_colours", C.c_int32), ("R", C.c_int32)]
+
+
+class DipOutput(C.Structure):
+    _fields_ = [("status", C.c_int32), ("sink_value", C.c_int32), ("sink_s_het", C.c_int32), ("n_p1", C.c_int32),
+                ("n_p2", C.c_int32), ("p1_edges", C.c_int32 * (2 * DG_BATCH_MAX_EDGES)),
+                ("p2_edges", C.c_int32 * (2 * DG_BATCH_MAX_EDGES))]
+
+
 class DipGenieCudaError(RuntimeError):
     pass
 
@@ -214,8 +229,36 @@ class Context:
         return dict(value=val.value, s_het=shet.value, p1_edges=p1[: 2 * n1.value].reshape(-1, 2).copy(),
                     p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy())
 
-    def dip_create(self, g: LevelGraph, R: int) -> "DipProblem":
-        return DipProblem(self, g, R)
+    def dp_diploid_batch(self, graphs, R, max_concurrent: int = 0, ctas_per_sample: int = 0):
+        """dg_dp_diploid_batch: independent samples resident on the GPU together; R is an int or one per sample."""
+        n = len(graphs)
+        Rs = [int(R)] * n if np.isscalar(R) else [int(r) for r in R]
+        ins = (DipInput * max(n, 1))()
+        outs = (DipOutput * max(n, 1))()
+        for i, g in enumerate(graphs):
+            ins[i] = DipInput(g.n_levels, g.level_off.ctypes.data, g.adj_off.ctypes.data, g.adj_dst.ctypes.data,
+                              g.adj_w.ctypes.data, g.col_off.ctypes.data, g.col_val.ctypes.data, g.colour_is_hom.ctypes.data,
+                              len(g.colour_is_hom), Rs[i])
+        rc = self.lib.dg_dp_diploid_batch(C.c_void_p(self.h), C.c_int32(n), ins, outs, C.c_int32(max_concurrent),
+                                          C.c_int32(ctas_per_sample))
+        self.check(rc, "dg_dp_diploid_batch")
+        res = []
+        for i in range(n):
+            o = outs[i]
+            res.append(dict(value=o.sink_value, s_het=o.sink_s_het,
+                            p1_edges=np.array(o.p1_edges[: 2 * o.n_p1], np.int32).reshape(-1, 2),
+                            p2_edges=np.array(o.p2_edges[: 2 * o.n_p2], np.int32).reshape(-1, 2)))
+        return res
+
+    def dip_create(self, g: LevelGraph, R: int, slot: Optional[int] = None, ctas: int = 0) -> "DipProblem":
+        return DipProblem(self, g, R, slot, ctas)
+
+    def dip_run_many(self, problems) -> float:
+        """dg_dip_run_many: run resident problems (distinct slots) together; returns the group's device ms."""
+        arr = (C.c_void_p * max(len(problems), 1))(*[p.h for p in problems])
+        ms = C.c_float(0)
+        self.check(self.lib.dg_dip_run_many(C.c_void_p(self.h), arr, C.c_int32(len(problems)), C.byref(ms)), "dg_dip_run_many")
+        return ms.value
 
     # ---- sketch / spectrum / join ------------------------------------------------------------
     def _take(self, ptr, n, dtype):
@@ -342,16 +385,17 @@ class HapProblem:
 class DipProblem:
     """A diploid DP problem resident in HBM (dg_dip_*)."""
 
-    def __init__(self, ctx: Context, g: LevelGraph, R: int):
+    def __init__(self, ctx: Context, g: LevelGraph, R: int, slot: Optional[int] = None, ctas: int = 0):
         self.ctx = ctx
         self.R = R
         self.L = g.n_levels
         h = C.c_void_p(None)
-        rc = ctx.lib.dg_dip_create(
-            C.c_void_p(ctx.h), C.c_int32(g.n_levels), _ptr(g.level_off), _ptr(g.adj_off), _ptr(g.adj_dst), _ptr(g.adj_w),
-            _ptr(g.col_off), _ptr(g.col_val), _ptr(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R),
-            C.byref(h))
-        ctx.check(rc, "dg_dip_create")
+        args = [C.c_void_p(ctx.h), C.c_int32(g.n_levels), _ptr(g.level_off), _ptr(g.adj_off), _ptr(g.adj_dst), _ptr(g.adj_w),
+                _ptr(g.col_off), _ptr(g.col_val), _ptr(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R)]
+        if slot is None:
+            ctx.check(ctx.lib.dg_dip_create(*args, C.byref(h)), "dg_dip_create")
+        else:
+            ctx.check(ctx.lib.dg_dip_create_slot(*args, C.c_int32(slot), C.c_int32(ctas), C.byref(h)), "dg_dip_create_slot")
         self.h = h
 
     def run(self, checksums: bool = False, profile: bool = False):

@@ -97,6 +97,39 @@ int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out);
 int dg_dip_profile(dg_ctx* ctx, dg_dip* d, uint64_t* out24);
 void dg_dip_destroy(dg_ctx* ctx, dg_dip* d);
 
+/* Independent samples on one GPU at the same time.  In the reference every sample is its own process
+ * (data/run_DipGenie_batch.sh:21-39: one DipGenie run per sample of the 22-sample leave-one-out study); the
+ * DP of one small-panel sample is a chain of dependent levels that keeps only a few SMs busy, so a batch is
+ * spread over the GPU: sample i runs as its own persistent sweep of `ctas_per_sample` CTAs (0 = 4) on its own
+ * stream, up to `max_concurrent` samples resident together (0 = min(SM count / ctas_per_sample, 32)), while
+ * host threads plan the next samples.  No data-path exchange between samples.  Results are identical to n calls of
+ * dg_dp_diploid.  out[i].status = DG_OK or that sample's error code; returns the first error, if any. */
+#define DG_BATCH_MAX_EDGES 64        /* capacity of the edge lists below: needs R + 2 <= 64 */
+typedef struct {
+    int32_t n_levels; const int32_t* level_off;
+    const int64_t* adj_off; const int32_t* adj_dst; const uint8_t* adj_w;
+    const int64_t* col_off; const int32_t* col_val;
+    const uint8_t* colour_is_hom; int32_t n_colours; int32_t R;
+} dg_dip_input_t;
+typedef struct {
+    int32_t status, sink_value, sink_s_het, n_p1, n_p2;
+    int32_t p1_edges[2 * DG_BATCH_MAX_EDGES], p2_edges[2 * DG_BATCH_MAX_EDGES];
+} dg_dip_output_t;
+int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip_output_t* out, int32_t max_concurrent,
+                        int32_t ctas_per_sample);
+
+/* The same with the graphs resident in HBM between runs (bench.py times dg_dip_run_many alone): a problem
+ * created in `slot` owns that slot's stream and a sweep grid of `ctas` CTAs (0 = 8); dg_dip_run_many starts the
+ * n problems together (distinct slots run concurrently), waits for all of them and returns the device time of
+ * the whole group (CUDA events on the context's stream around fork and join).  dg_dip_result / dg_dip_stats /
+ * dg_dip_destroy apply as for dg_dip_create. */
+int dg_dip_create_slot(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off,
+                       const int64_t* adj_off, const int32_t* adj_dst, const uint8_t* adj_w,
+                       const int64_t* col_off, const int32_t* col_val,
+                       const uint8_t* colour_is_hom, int32_t n_colours, int32_t R,
+                       int32_t slot, int32_t ctas, dg_dip** out);
+int dg_dip_run_many(dg_ctx* ctx, dg_dip** problems, int32_t n, float* device_ms);
+
 /* ---- haploid DP: Approximator::dp_approximation_solver, src/approximator.cpp:44-168 ------------
  * (the push-relaxation loop :50-67, the R+1 tracebacks with their distinct-colour counts :70-102 and
  *  the final traceback :141-153; the caller keeps the floating-point best_r rule :116-136, the

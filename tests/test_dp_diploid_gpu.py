@@ -108,3 +108,32 @@ def test_cuda_matches_reference_mhc_full_size(R, ctx, expected):
     o2 = p.result()
     p.close()
     assert o2["value"] == e["value"] and o2["p1_edges"].ravel().tolist() == e["p1_edges"]
+
+
+def test_cuda_batch_of_samples_matches_one_by_one(ctx, oracle_mod):
+    """dg_dp_diploid_batch: samples resident together on their own streams / CTA groups give exactly the
+    results of separate calls (shapes chosen so that narrow, wide and hand-over tasks all occur)."""
+    graphs, Rs = [], []
+    for seed in range(14):
+        rng = np.random.default_rng(4000 + seed)
+        if seed % 5 == 4:
+            g = synth.lane_panel_graph(seed, n_lanes=int(rng.integers(8, 40)), n_blocks=4, rec_per_block=2, p_colour=0.25, n_colours=300)
+        else:
+            g = synth.random_level_graph(900 + seed, n_levels=int(rng.integers(2, 60)), max_width=int(rng.integers(1, 30)),
+                                         n_colours=int(rng.integers(0, 120)), p_colour=float(rng.random()))
+        graphs.append(g)
+        Rs.append(int(rng.integers(0, 8)))
+    for conc, ctas in ((0, 0), (3, 2), (1, 1)):
+        outs = ctx.dp_diploid_batch(graphs, Rs, max_concurrent=conc, ctas_per_sample=ctas)
+        for g, R, o in zip(graphs, Rs, outs):
+            assert_dip_equal(oracle_dip(oracle_mod, g, R, want_checksums=False), o, checks=False)
+
+
+def test_cuda_batch_mhc_samples(ctx, expected):
+    g, _ = LevelGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_dipin.npz"))
+    Rs = [18, 0, 6, 36, 18, 6]
+    outs = ctx.dp_diploid_batch([g] * len(Rs), Rs)
+    for R, o in zip(Rs, outs):
+        e = expected["mhc4_chm13"]["diploid"][str(R)]
+        assert o["value"] == e["value"] and o["s_het"] == e["s_het"]
+        assert o["p1_edges"].ravel().tolist() == e["p1_edges"] and o["p2_edges"].ravel().tolist() == e["p2_edges"]
