@@ -28,6 +28,9 @@ import time
 # batch slots are concurrent persistent kernels: one hardware work queue each (see dg_create); must be set
 # before the first CUDA call of the process
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# rank 0 must print exactly one JSON line: keep NCCL's version banner off stdout
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np  # noqa: E402
 
@@ -36,6 +39,11 @@ sys.path.insert(0, ROOT)
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 REF_PLAIN = os.path.join(ROOT, "oracle", "_ref", "ref_driver_plain")
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one dip_sweep_kernel launch, from the `ncu --set full` capture
+# summarised in profiles/r01b_sweep_v3.md (114.9 MB + 804.7 MB); None where no capture exists.
+NCU_TRAFFIC = {("mhc4_chm13", 18): 919607040}
 
 
 def load_workload(name: str):
@@ -208,6 +216,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    # one process per GPU: this rank's share of the host cores for the planning threads of the batch call
+    os.environ.setdefault("DG_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))))
     g, desc = load_workload(args.workload)
     ctx = Context(local)
     S = max(1, args.samples_per_gpu)
@@ -293,7 +303,7 @@ def main():
                           "note": "per launch, with S launches resident together"},
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "hbm", "kernel": "dip_sweep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, args.R)), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": st["algo_bytes"], "launches_resident_together": S,
                          "aggregate_achieved": achieved * S,
                          "note": "latency-bound at H=5: 120 362 dependent level transitions per launch, almost all on one SM; "

@@ -1037,7 +1037,8 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
 
     // planning (host only) runs ahead on a few worker threads, each with its share of the cores; this thread
     // uploads, launches and collects in sample order
-    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (const char* e = getenv("DG_HOST_THREADS")) hw = std::max(1, atoi(e));   // this process's share of the host cores (one process per GPU)
     const int W = std::max(1, std::min({(int)n, 4, hw / 2}));
     const int lookahead = 2 * W + 2;
     std::vector<std::unique_ptr<dg_dip>> planned((size_t)n);
