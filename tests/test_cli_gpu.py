@@ -1,0 +1,60 @@
+"""The drop-in front end on the GPU: the `dipgenie` CLI (dipgenie_b200/csrc/host/main.cpp -> libdipgenie_host.so
+-> C ABI of libdipgenie_cuda.so) run on inputs materialised from the committed fixtures must write FASTA files
+byte-identical to the reference binary's (md5s in tests/golden/e2e_expected.json, recorded from the unmodified
+reference by tests/golden/make_e2e_inputs.py)."""
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+
+from conftest import GOLD
+from dipgenie_b200 import _build, fixtures
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cli():
+    assert os.path.exists(_build.CLI_BIN), "dipgenie CLI not built (run __graft_entry__.build())"
+    return _build.CLI_BIN
+
+
+@pytest.fixture(scope="module")
+def e2e_expected():
+    return json.load(open(os.path.join(GOLD, "e2e_expected.json")))
+
+
+def run(cli, gfa, reads, out, flags):
+    p = subprocess.run([cli, "-g", gfa, "-r", reads, "-o", out, "-t8", *flags], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stderr, hashlib.md5(open(out, "rb").read()).hexdigest()
+
+
+@pytest.mark.parametrize("toy,flags", [("test", ["-p1", "-R2", "-k3", "-w2"]), ("test", ["-p2", "-R2", "-k3", "-w2"]),
+                                        ("test", ["-p2", "-R2", "-k5", "-w3"]), ("test", ["-p2", "-R0", "-k3", "-w2"]),
+                                        ("test2", ["-p1", "-R2"]), ("test2", ["-p2", "-R2"])])
+def test_cli_toy_inputs(toy, flags, cli, e2e_expected, tmp_path):
+    gfa, fa = fixtures.materialize_toy(toy, str(tmp_path))
+    _, md5 = run(cli, gfa, fa, str(tmp_path / "out.fa"), flags)
+    assert md5 == e2e_expected[toy + " " + " ".join(flags)]
+
+
+@pytest.mark.parametrize("name,flags", [("mhc_p2_R18", ["-p2", "-R18"]), ("mhc_p2_R6", ["-p2", "-R6"]), ("mhc_p1", ["-p1"])])
+def test_cli_mhc(name, flags, cli, e2e_expected, tmp_path):
+    """BASELINE configs 1 and 2 (bundled CHM13 reads) end to end: sketch, join, DP and traceback on the GPU."""
+    gfa, fa = fixtures.materialize_mhc(GOLD, str(tmp_path))
+    log, md5 = run(cli, gfa, fa, str(tmp_path / "out.fa"), flags)
+    assert md5 == e2e_expected[name]
+    if name == "mhc_p2_R18":
+        assert "DP value: 60729" in log and "Count_Sp_R : 138834" in log
+
+
+def test_cli_usage_and_ploidy_contract(cli, tmp_path):
+    """src/main.cpp:90-111 (usage + exit 1 without -g/-r/-o) and :159-162 (unknown ploidy: message, exit 0)."""
+    p = subprocess.run([cli, "-g", "x.gfa"], capture_output=True, text=True)
+    assert p.returncode == 1 and "Usage" in p.stderr
+    gfa, fa = fixtures.materialize_toy("test2", str(tmp_path))
+    p = subprocess.run([cli, "-g", gfa, "-r", fa, "-o", str(tmp_path / "o.fa"), "-p3"], capture_output=True, text=True)
+    assert p.returncode == 0 and "Ploidy" in p.stderr and not os.path.exists(tmp_path / "o.fa")
