@@ -3,6 +3,7 @@
 // threshold; usage + exit 1 when an input is missing, message + exit 0 for an unknown ploidy, :159-162),
 // host glue from libdipgenie_host.so, hot path on the GPU through the C ABI of libdipgenie_cuda.so.
 // There is no CPU fallback: without a usable CUDA device the program exits with an error.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,7 +53,10 @@ int main(int argc, char** argv) {
     }
     if (o.gfa.empty() || o.reads.empty() || o.out.empty()) { usage(stderr); return 1; }
     if (o.ploidy != 1 && o.ploidy != 2) { fprintf(stderr, "Ploidy must be 1 or 2\n"); return 0; }
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     dg_ctx* ctx = dg_create(device);
+    if (o.verbose) fprintf(stderr, "[M::main] CUDA context ready after %.3f sec\n", now() - t0);
     if (!ctx) { fprintf(stderr, "dipgenie: %s\n", dg_last_error(nullptr)); return 1; }
     dgh::Backend be;
     be.ctx = ctx;
@@ -75,6 +79,8 @@ int main(int argc, char** argv) {
     std::string err;
     const int rc = dgh::run_pipeline(o, be, sum, err);
     if (rc) fprintf(stderr, "dipgenie: %s\n", err.c_str());
+    const double t1 = now();
     dg_destroy(ctx);
+    if (o.verbose) fprintf(stderr, "[M::main] released the device after %.3f sec; total %.3f sec\n", now() - t1, now() - t0);
     return rc;
 }
