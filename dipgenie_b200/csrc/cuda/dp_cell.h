@@ -118,6 +118,7 @@ struct TransitionT {
     // delta of candidate (e1,e2) = delta[(e1 - e1_base) * dstride + (e2 - e2_base)]
     const uint16_t* delta;
     int32_t dstride, e1_base, e2_base;
+    int32_t dshift;            // layers hold value << dshift (0 or KEY_SHIFT): deltas are shifted alike
     // on-the-fly form (TK_DELTA_MASKS): colour bit-masks of the two levels
     int32_t W;                 // 64-bit mask words per set
     const uint64_t* msrc;      // [k ][2W]  hom words then het words
@@ -175,6 +176,7 @@ DG_HD void relax_pair(const TransitionT<OffT>& t, Load load, int R, int r0, int 
             int d = 0;
             if (has_matrix) d = (int)drow[e2];
             if (MASKS) d = mask_delta(t.W, t.msrc, t.mdst, i, j, i2, j2);
+            d <<= t.dshift;
             const uint32_t cd = ((uint32_t)(e1 - a0) << 16) | (uint32_t)(e2 - b0);
             // the RC source loads are issued unconditionally (layer index clamped into [0,R]) so that they
             // are independent and overlap; validity only gates the compare
@@ -200,10 +202,20 @@ DG_HD void relax_pair(const TransitionT<OffT>& t, Load load, int R, int r0, int 
 // narrow levels enough items to spread over the CTA and still amortise the in-edge decode.
 constexpr int DIP_RC = 4;
 DG_HD int choose_rc(uint32_t, int, uint32_t) { return DIP_RC; }
-// Layers per lane in the lane form: two compiled variants; the planner picks one per problem
-// (SweepShape::lane_rc).  Measured on B200 (MHC_4, R=18): 4 is fastest — more, shorter warp items keep all
-// sub-partitions busy inside one level; 20 layers per lane was 1.7x slower.
-constexpr int LANE_RC_SMALL = 4, LANE_RC_BIG = 8;
+// Layers per lane in the lane form.  Measured on B200 (MHC_4, R=18): 4 is fastest — more, shorter warp items
+// keep all sub-partitions busy inside one level (8 layers per lane: 321 ms, 20: 564 ms, 4: 283 ms).
+constexpr int LANE_RC_SMALL = 4;
+
+// Packed keys.  When every DP value is known to stay below 2^21 (the planner bounds it by the sum over
+// transitions of the colours present, DipPlan::value_bound), the layers hold value << KEY_SHIFT and the lane
+// form keeps ONE word per layer: key = (value << 10) | (31 - e1 ordinal) << 5 | (31 - e2 ordinal).  The first
+// strict maximum in (e1,e2) order is then a plain integer maximum (larger value, then smaller e1, then smaller
+// e2), per lane and across the lanes of a destination column: one add + one max per layer instead of an add,
+// three compares and two selects, and one shuffle instead of two in the segmented maximum.  Dead cells stay
+// NEG_INF (NEG_INF + anything below 2^27 is still negative and never beats the initial -1).  shift == 0 selects
+// the unpacked arithmetic (values of any size).
+constexpr int KEY_SHIFT = 10, KEY_ORD_BITS = 5;
+constexpr int64_t KEY_VALUE_LIMIT = (int64_t)1 << (31 - KEY_SHIFT);
 
 // Same fold as oracle/ref_hook.h::dg_ref_level_done, for one live cell; the per-level checksum is the
 // wrapping sum of these plus the FNV offset basis.

@@ -70,6 +70,7 @@ struct SweepArgs {
     unsigned long long* level_live;   // [L]
     unsigned long long* prof;         // [32] phase cycle counters of CTA 0 / thread 0 (nullable)
     int32_t R;
+    int32_t shift;                    // layers hold value << shift (dp_cell.h: packed keys), 0 or KEY_SHIFT
 };
 
 // ---- PTX helpers -----------------------------------------------------------------------------
@@ -213,7 +214,7 @@ __device__ __forceinline__ void sweep_items(const TransitionT<OffT>& t, const Ce
                         const int pi = (int)(t.in_edge[(int32_t)t.in_off[i2] + (int32_t)(code[rr] >> 16)] & 0xFFFFu);
                         const int pj = (int)(t.in_edge[(int32_t)t.in_off[j2] + (int32_t)(code[rr] & 0xFFFFu)] & 0xFFFFu);
                         ++hlive;
-                        hsum += cell_fold((uint64_t)c, v, pi, pj);
+                        hsum += cell_fold((uint64_t)c, v >> t.dshift, pi, pj);
                     }
                 }
             }
@@ -367,6 +368,143 @@ __device__ __forceinline__ void lane_task(const LaneTask& t, int R, int warp, in
     }
 }
 
+// The same with packed keys (dp_cell.h): one word per layer, one add + one max per candidate layer, one shuffle
+// per layer and round.  Only the first chunk of layers runs a checked loop (layer index below 0 for weighted
+// edges); the tiles are padded to whole chunks, so the layers above R that the last chunk loads are in bounds
+// (and never stored).
+template <bool SMEM, bool CHECK, bool PRED32, bool PROF>
+__device__ __forceinline__ void lane_task_packed(const LaneTask& t, int R, int warp, int lane,
+                                                 unsigned long long& hsum, unsigned long long& hlive, LaneProf& lp) {
+    constexpr int RC = LANE_RC_SMALL;
+    constexpr uint32_t ORD_MASK = (1u << (2 * KEY_ORD_BITS)) - 1u, ORD_ONE = (1u << KEY_ORD_BITS) - 1u;
+    const uint32_t off32 = t.sb32 + (uint32_t)sizeof(TaskHdr);
+    const uint32_t edge32 = off32 + (uint32_t)rec_edge_offset((int)t.k2);
+    const uint32_t dstp32 = off32 + (uint32_t)rec_dst_offset((int)t.k2, t.n_in);
+    const uint32_t bst32 = off32 + t.bstart_off;
+    const uint32_t k = t.k, k2 = t.k2, n_in = t.n_in;
+    const uint32_t kk = k * k, kk2 = k2 * k2;
+    uint32_t rs = 0, el = (uint32_t)lane;
+    if (t.nblk == 1) {
+        rs = t.m_nin ? __umulhi((uint32_t)lane, t.m_nin) : (uint32_t)lane;
+        el = (uint32_t)lane - rs * n_in;
+    }
+    uint32_t delta32 = 0;
+    if (t.staged) delta32 = off32 + t.rec_bytes + 2u * t.skew - 2u * lds_u16(off32 + 2u * t.i0) * n_in;
+    // what depends on the lane's in-edge only; with a single block (the common case) it is the same for every
+    // warp item of the task and is computed once
+    uint32_t bs = 0, be = 0, e2c = 0, j2 = 0, s0 = 0, pos = 0, seg = 1, j = 0;
+    int wv = 0;
+    bool lane_ok = false;
+    auto lane_setup = [&](uint32_t b) {
+        bs = lds_u16(bst32 + 2u * b); be = lds_u16(bst32 + 2u * b + 2u);
+        const uint32_t e2 = bs + el;
+        lane_ok = e2 < be;
+        e2c = lane_ok ? e2 : bs;
+        const uint32_t y = lds_u32(edge32 + 4u * e2c);
+        j2 = lds_u16(dstp32 + 2u * e2c);
+        s0 = lds_u16(off32 + 2u * j2);
+        const uint32_t s1 = lds_u16(off32 + 2u * j2 + 2u);
+        pos = e2c - s0; seg = s1 - s0;
+        j = y & 0xFFFFu; wv = (int)(y >> 16);
+    };
+    if (t.nblk == 1) lane_setup(0);
+    for (uint32_t wi = (uint32_t)warp; wi < t.n_witems; wi += DIP_NCW) {
+        long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        if (PROF) c0 = clock64();
+        uint32_t q = wi;
+        if (t.nblk != 1) {
+            q = t.m_nblk ? __umulhi(wi, t.m_nblk) : wi;
+            lane_setup(wi - q * t.nblk);
+        }
+        const uint32_t chunk = t.m_nrg ? __umulhi(q, t.m_nrg) : q;
+        const uint32_t rg = q - chunk * t.nrg;
+        const uint32_t row = t.i0 + rg * t.rp + rs;
+        const bool valid = lane_ok && rs < t.rp && row < t.i1;
+        const uint32_t rowc = valid ? row : t.i0;
+        const uint32_t a0 = lds_u16(off32 + 2u * rowc);
+        uint32_t a1 = lds_u16(off32 + 2u * rowc + 2u);
+        if (!valid) a1 = a0;
+        const int r0 = (int)chunk * RC;
+        const bool edge_chunk = (r0 == 0);     // warp-uniform; layers above R (last chunk) are loaded inside the padded tile and never stored
+        int32_t key[RC];
+#pragma unroll
+        for (int rr = 0; rr < RC; ++rr) key[rr] = -1;
+        uint32_t ordbits = ((ORD_ONE) << KEY_ORD_BITS) | (ORD_ONE - pos);    // (31 - e1 ordinal) << 5 | (31 - e2 ordinal), e1 ordinal 0
+        if (PROF) c1 = clock64();
+        for (uint32_t e1 = a0; e1 < a1; ++e1, ordbits -= (1u << KEY_ORD_BITS)) {
+            if (PROF) ++lp.iters;
+            const uint32_t x = lds_u32(edge32 + 4u * e1);
+            const uint32_t base = (x & 0xFFFFu) * k + j;
+            const int w = (int)(x >> 16) + wv;
+            uint32_t dp = ordbits;
+            if (t.staged) dp += lds_u16(delta32 + 2u * (e1 * n_in + e2c)) << KEY_SHIFT;
+            int32_t v[RC];
+            if (!edge_chunk) {
+                if (SMEM) {
+                    const uint32_t a = t.src32 + 4u * ((uint32_t)(r0 - w) * kk + base);
+#pragma unroll
+                    for (int rr = 0; rr < RC; ++rr) v[rr] = lds_s32(a + 4u * (uint32_t)rr * kk);
+                } else {
+                    const int32_t* a = t.gsrc + ((size_t)(r0 - w) * kk + base);
+#pragma unroll
+                    for (int rr = 0; rr < RC; ++rr) v[rr] = ldcg_s32(a + (size_t)rr * kk);
+                }
+#pragma unroll
+                for (int rr = 0; rr < RC; ++rr) key[rr] = max(key[rr], v[rr] + (int32_t)dp);
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < RC; ++rr) {
+                    int r = r0 + rr - w;
+                    r = r < 0 ? 0 : (r > R ? R : r);
+                    if (SMEM) v[rr] = lds_s32(t.src32 + 4u * ((uint32_t)r * kk + base));
+                    else v[rr] = ldcg_s32(t.gsrc + ((size_t)r * kk + base));
+                }
+#pragma unroll
+                for (int rr = 0; rr < RC; ++rr) {
+                    const bool ok = (r0 + rr - w >= 0) && (r0 + rr <= R);
+                    key[rr] = max(key[rr], ok ? v[rr] + (int32_t)dp : -1);
+                }
+            }
+        }
+        if (PROF) c2 = clock64();
+        // segmented maximum over the lanes of one destination column (keys of different lanes never tie)
+        for (uint32_t rd = 0, off = 1; rd < t.rounds; ++rd, off <<= 1) {
+            const bool partner = pos + off < seg;
+#pragma unroll
+            for (int rr = 0; rr < RC; ++rr) {
+                const int32_t ok = __shfl_down_sync(0xFFFFFFFFu, key[rr], off);
+                key[rr] = max(key[rr], partner ? ok : -1);
+            }
+        }
+        if (PROF) c3 = clock64();
+        if (valid && pos == 0) {
+            const uint32_t cell0 = row * k2 + j2;
+#pragma unroll
+            for (int rr = 0; rr < RC; ++rr) {
+                const int r2 = r0 + rr;
+                if (r2 <= R) {
+                    const bool live = key[rr] >= 0;
+                    const int32_t val = live ? (int32_t)((uint32_t)key[rr] & ~ORD_MASK) : NEG_INF;
+                    const uint32_t inv = ~(uint32_t)key[rr] & ORD_MASK;                 // e1 ordinal << 5 | e2 ordinal
+                    const uint32_t o1 = inv >> KEY_ORD_BITS, o2 = inv & ORD_ONE;
+                    size_t c;
+                    if (SMEM) { const uint32_t c32 = (uint32_t)r2 * kk2 + cell0; sts_s32(t.dst32 + 4u * c32, val); c = c32; }
+                    else { c = (size_t)r2 * kk2 + cell0; __stcg(t.gdst + c, val); }
+                    if (PRED32) reinterpret_cast<uint32_t*>(t.pl)[c] = live ? ((o1 << 16) | o2) : 0xFFFFFFFFu;
+                    else reinterpret_cast<uint16_t*>(t.pl)[c] = live ? (uint16_t)((o1 << 8) | o2) : (uint16_t)0xFFFFu;
+                    if (CHECK && live) {
+                        const int pi = (int)(lds_u32(edge32 + 4u * (a0 + o1)) & 0xFFFFu);
+                        const int pj = (int)(lds_u32(edge32 + 4u * (s0 + o2)) & 0xFFFFu);
+                        ++hlive;
+                        hsum += cell_fold((uint64_t)c, val >> KEY_SHIFT, pi, pj);
+                    }
+                }
+            }
+        }
+        if (PROF) { const long long c4 = clock64(); lp.items += 1; lp.setup += c1 - c0; lp.loop += c2 - c1; lp.reduce += c3 - c2; lp.store += c4 - c3; }
+    }
+}
+
 // The pair form (everything the lane form does not take): layers in HBM/L2 (or a hand-over between the two placements),
 // records staged or read in place, pair scores staged / in place / popcounted on the fly.  Kept out of line
 // so that the narrow loop gets its own register allocation and stays small.
@@ -388,7 +526,7 @@ __device__ __noinline__ ulonglong2 generic_task(const SweepArgs& a, const uint8_
         tr.k = h.k; tr.k2 = h.k2;
         tr.in_off = reinterpret_cast<const uint16_t*>(sb + sizeof(TaskHdr));
         tr.in_edge = reinterpret_cast<const uint32_t*>(sb + sizeof(TaskHdr) + rec_edge_offset(h.k2));
-        tr.delta = nullptr; tr.dstride = h.n_in; tr.e1_base = 0; tr.e2_base = 0;
+        tr.delta = nullptr; tr.dstride = h.n_in; tr.e1_base = 0; tr.e2_base = 0; tr.dshift = a.shift;
         tr.W = 0; tr.msrc = nullptr; tr.mdst = nullptr;
         if (flags & TK_DELTA_STAGED) {
             tr.delta = reinterpret_cast<const uint16_t*>(sb + sizeof(TaskHdr) + rec_bytes) + h.delta_skew;
@@ -407,7 +545,7 @@ __device__ __noinline__ ulonglong2 generic_task(const SweepArgs& a, const uint8_
         tr.in_off = a.in_off + mid;
         tr.in_edge = a.in_edge;
         tr.delta = nullptr; tr.dstride = __ldg(a.in_off + __ldg(a.level_off + l + 2)) - ebase;
-        tr.e1_base = ebase; tr.e2_base = ebase;
+        tr.e1_base = ebase; tr.e2_base = ebase; tr.dshift = a.shift;
         tr.W = 0; tr.msrc = nullptr; tr.mdst = nullptr;
         if (flags & TK_DELTA) tr.delta = a.delta + __ldg(a.delta_off + l);
         else if (flags & TK_DELTA_MASKS) {
@@ -506,12 +644,11 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepAr
                 lt.m_nrg = h5.x; lt.m_nin = h5.y; lt.n_witems = h5.z; lt.rounds = h5.w;
                 lt.bstart_off = reinterpret_cast<const uint32_t*>(sb)[24];
                 lt.staged = (flags & TK_DELTA_STAGED) != 0;
-                const bool big = (h4.x & 0xFFFFu) == (uint32_t)LANE_RC_BIG;
-                if (ssm) {
-                    if (big) lane_task<LANE_RC_BIG, true, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
-                    else lane_task<LANE_RC_SMALL, true, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
+                if (a.shift) {
+                    if (ssm) lane_task_packed<true, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
+                    else lane_task_packed<false, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
                 } else {
-                    if (big) lane_task<LANE_RC_BIG, false, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
+                    if (ssm) lane_task<LANE_RC_SMALL, true, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
                     else lane_task<LANE_RC_SMALL, false, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
                 }
             } else {
@@ -565,6 +702,7 @@ struct TraceArgs {
     int32_t* seg_n;           // [M][4]: n1, n2, s_het, rc
     const int32_t* sink_tile;
     int cap;
+    int shift;               // layers hold value << shift
     TraceOut* out;
     int32_t* p1;
     int32_t* p2;
@@ -601,8 +739,8 @@ __global__ void dip_hop_kernel(const TraceArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int64_t ks = a.v.level_off[a.v.L] - a.v.level_off[a.v.L - 1];
     const int32_t value = __ldcg(a.sink_tile + (int64_t)a.v.R * ks * ks);   // cell (r=R,0,0) of the last level (:730, :775)
-    a.out->value = value;
-    int64_t cur = (value == NEG_INF) ? -1 : (int64_t)a.v.R * ks * ks;
+    a.out->value = value < 0 ? NEG_INF : (value >> a.shift);
+    int64_t cur = (value < 0) ? -1 : (int64_t)a.v.R * ks * ks;
     for (int m = 0; m < a.M; ++m) {
         a.path_cell[m] = (int32_t)cur;
         if (cur >= 0) cur = a.anc[a.aoff[m] + cur];
@@ -648,6 +786,7 @@ using namespace dg;
 struct dg_dip {
     cudaStream_t stream = nullptr;   // the context's stream, or one of the batch streams
     bool cooperative = true;         // batch slots use plain launches (see dip_run_impl)
+    int shift = 0;                   // KEY_SHIFT when every DP value provably stays below 2^21 (packed keys), else 0
     std::vector<int32_t> h_cp;       // traceback checkpoints (host copies until uploaded)
     std::vector<int64_t> h_aoff;
     DipPlan plan;                 // host copy (small arrays kept for stats; big ones released after upload)
@@ -720,6 +859,7 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
     DipPlan& p = d->plan;
     const int L = p.L;
     d->pred_bytes = (p.max_indeg <= 255) ? 2 : 4;
+    d->shift = (p.value_bound < KEY_VALUE_LIMIT && !getenv("DG_NO_PACK")) ? KEY_SHIFT : 0;
     // grid: enough CTAs that the widest transition leaves about 16 candidates per thread, at most one
     // co-resident wave
     uint64_t widest_cand = 0;
@@ -735,7 +875,6 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
     shape.threads = DIP_CT;
     shape.tile_cells = DIP_TILE_CELLS;
     shape.slot_bytes = DIP_SLOT_BYTES;
-    if (const char* e = getenv("DG_LANE_RC")) shape.lane_rc = atoi(e);   // diagnostics / tuning
     shape.delta_budget = lim.delta_budget;
     plan_tasks(p, shape);
     d->grid = 1;
@@ -796,7 +935,8 @@ static int dip_create_device(dg_ctx* ctx, dg_dip* d) {
     DG_CUDA(ctx, d->pred_off.upload(p.pred_off.data(), p.pred_off.size(), s));
     DG_CUDA(ctx, d->cp.upload(cp.data(), cp.size(), s));
     DG_CUDA(ctx, d->aoff.upload(aoff.data(), aoff.size(), s));
-    const uint64_t widest = (uint64_t)(p.R + 1) * (uint64_t)p.kmax * (uint64_t)p.kmax;
+    // (layers rounded up to whole lane-form chunks: the last chunk loads, but never stores, layers above R)
+    const uint64_t widest = (uint64_t)(p.R + LANE_RC_SMALL) * (uint64_t)p.kmax * (uint64_t)p.kmax;
     const size_t tile = (size_t)std::max<uint64_t>(widest, (uint64_t)(p.R + 1));
     DG_CUDA(ctx, d->tile0.alloc(tile, s));
     DG_CUDA(ctx, d->tile1.alloc(tile, s));
@@ -865,7 +1005,7 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     a.tile0 = d->tile0.p; a.tile1 = d->tile1.p; a.pred = d->pred.p; a.counter = d->counter.p;
     a.level_sum = d->level_sum.p; a.level_live = d->level_live.p;
     a.prof = d->want_prof ? d->prof.p : nullptr;
-    a.R = p.R;
+    a.R = p.R; a.shift = d->shift;
     if (p.L > 1) {
         void* args[] = {(void*)&a};
         const void* fn = sweep_fn(sizeof(PredT) == 4, check, d->want_prof);
@@ -886,7 +1026,7 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     ta.pred = d->pred.p; ta.cp = d->cp.p; ta.aoff = d->aoff.p; ta.M = d->M; ta.anc = d->anc.p; ta.path_cell = d->path_cell.p;
     ta.seg_p1 = d->seg_p1.p; ta.seg_p2 = d->seg_p2.p; ta.seg_n = d->seg_n.p;
     ta.sink_tile = ((p.L - 1) & 1) ? d->tile1.p : d->tile0.p;
-    ta.cap = p.R + 2; ta.out = d->tout.p; ta.p1 = d->p1.p; ta.p2 = d->p2.p;
+    ta.cap = p.R + 2; ta.shift = d->shift; ta.out = d->tout.p; ta.p1 = d->p1.p; ta.p2 = d->p2.p;
     if (d->anc_cells > 0) {
         const unsigned blocks = (unsigned)((d->anc_cells + 255) / 256);
         dip_anc_kernel<PredT><<<blocks, 256, 0, s>>>(ta);

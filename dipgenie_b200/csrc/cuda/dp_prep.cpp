@@ -96,7 +96,8 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
     p.lvlW.assign(L, 0); p.msrc_off.assign(L, 0); p.mdst_off.assign(L, 0);
     const size_t ncol = (size_t)(g.n_colours > 0 ? g.n_colours : 1);
     int Wmax = 0;
-#pragma omp parallel num_threads(NT) reduction(max : Wmax)
+    int64_t vbound = 0;
+#pragma omp parallel num_threads(NT) reduction(max : Wmax) reduction(+ : vbound)
     {
         std::vector<int32_t> seen(ncol, -1);
 #pragma omp for schedule(static)
@@ -112,10 +113,12 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
             const int W = (n + 63) / 64;
             p.lvlW[l] = W;
             Wmax = std::max(Wmax, W);
+            vbound += n;          // delta = |hom ∩| + |het △| <= colours present on the two levels
         }
     }
     if (bad == 3) { p.error = "colour id out of range"; return false; }
     p.Wmax = Wmax;
+    p.value_bound = vbound;
     size_t words = 0;
     for (int l = 0; l + 1 < L; ++l) {
         const size_t W = (size_t)p.lvlW[l];
@@ -202,7 +205,7 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
     const int G = sh.grid < 1 ? 1 : sh.grid;
     const uint32_t CT = sh.threads < 1 ? 1u : (uint32_t)sh.threads;
     const size_t slot = (size_t)sh.slot_bytes;
-    const int lrc = (sh.lane_rc == LANE_RC_BIG) ? LANE_RC_BIG : LANE_RC_SMALL;
+    const int lrc = LANE_RC_SMALL;
     p.grid = G;
     p.P.assign(L, 1); p.bar_target.assign(L, 0); p.bar_edge.assign(L, 0); p.narrow.assign(L, 0);
     p.rec_off.assign(L, -1); p.delta_off.assign(L, -1); p.delta_list.clear(); p.delta_elems = 0;
@@ -212,7 +215,10 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
     const int NT = n_threads();
     (void)NT;
     auto width = [&](int l) { return p.level_off[l + 1] - p.level_off[l]; };
-    auto cells_of = [&](int l) { const uint64_t k = (uint64_t)width(l); return (uint64_t)(p.R + 1) * k * k; };
+    // tile cells a layer set needs: R+1 layers rounded up to whole lane-form chunks, so that the loads of the last
+    // chunk's layers above R (never stored) stay inside the tile
+    const uint64_t layers_padded = (uint64_t)((p.R + LANE_RC_SMALL) / LANE_RC_SMALL) * LANE_RC_SMALL;
+    auto cells_of = [&](int l) { const uint64_t k = (uint64_t)width(l); return layers_padded * k * k; };
     auto nin_of = [&](int l) { return (int64_t)p.in_off[p.level_off[l + 2]] - (int64_t)p.in_off[p.level_off[l + 1]]; };
 
     // ---- 1. lane-form blocks, record sizes, pair-score matrix layout, placement of the layers ----

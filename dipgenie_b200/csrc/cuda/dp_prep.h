@@ -48,7 +48,6 @@ struct SweepShape {              // kernel geometry the plan is made for
     int slot_bytes = 4096;       // bytes per task slot in shared memory (header + record + delta slice)
     int64_t delta_budget = (int64_t)8 << 30;   // bytes of pair-score matrices to materialise at most
     int delta_max_in = 4096;     // widest in-edge count that still gets a matrix
-    int lane_rc = LANE_RC_SMALL; // layers per lane in the lane form (LANE_RC_SMALL or LANE_RC_BIG)
 };
 
 struct DipPlan {
@@ -82,6 +81,7 @@ struct DipPlan {
     uint64_t cell_updates = 0;         // U = (R+1) * sum_l E_l^2
     uint64_t cells = 0;                // C = (R+1) * sum_{l>=1} k_l^2
     uint64_t algo_bytes = 0;           // B = (R+1) * sum_l (4 k_l^2 + 5 k_{l+1}^2)
+    int64_t value_bound = 0;           // no DP value exceeds this: sum over transitions of the distinct colours present
     std::string error;
 };
 

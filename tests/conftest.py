@@ -57,7 +57,7 @@ class DpEmu:
         self.lib = C.CDLL(_build_emu())
 
     def dp_diploid(self, g, R, force_pred32=False, shape=None):
-        """shape = (grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, lane_rc) of the emulated kernel geometry
+        """shape = (grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, no_pack) of the emulated kernel geometry
         (0 = default; delta_max_in < 0 forces the on-the-fly mask path)."""
         L = g.n_levels
         shp = np.zeros(7, np.int32)

@@ -25,6 +25,7 @@ struct Emu {
     std::vector<int32_t> g0, g1, s0, s1;
     std::vector<uint64_t> sum, live;
     bool bad_rc = false;
+    int shift = 0;                     // layers hold value << shift (packed keys)
     int64_t n_lane_tasks = 0;
     std::vector<uint8_t> written;      // cells of the current destination level stored so far (lane form: exactly once)
     Emu(const DipPlan& pp, const SweepShape& s) : p(pp), sh(s) {}
@@ -63,7 +64,7 @@ void items(Emu& e, const TransitionT<OffT>& t, const TaskHdr& h, const int32_t* 
                         const int pi = (int)(t.in_edge[(int32_t)t.in_off[i2] + (int32_t)(code[rr] >> 16)] & 0xFFFFu);
                         const int pj = (int)(t.in_edge[(int32_t)t.in_off[j2] + (int32_t)(code[rr] & 0xFFFFu)] & 0xFFFFu);
                         ++e.live[h.level + 1];
-                        e.sum[h.level + 1] += cell_fold(c, best[rr], pi, pj);
+                        e.sum[h.level + 1] += cell_fold(c, best[rr] >> e.shift, pi, pj);
                     }
                 }
             }
@@ -96,6 +97,8 @@ int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src
     if (h.bstart_off != rec_bstart_offset(h.k2, h.n_in) || h.bstart_off + 2u * (h.nblk + 1u) > h.rec_bytes) return -50;
     const uint16_t* bstart = reinterpret_cast<const uint16_t*>(rec + h.bstart_off);
     const bool staged = (h.flags & TK_DELTA_STAGED) != 0;
+    const bool packed = e.shift != 0;
+    if (packed && e.shift != KEY_SHIFT) return -63;
     if ((h.flags & (TK_DELTA | TK_DELTA_MASKS)) && !staged) return -51;
     const uint16_t* delta = staged ? reinterpret_cast<const uint16_t*>(rec + h.rec_bytes) + h.delta_skew - (size_t)in_off[h.i0] * h.n_in : nullptr;
     const uint32_t k = h.k, k2 = h.k2, n_in = h.n_in, kk = k * k, kk2 = k2 * k2;
@@ -134,12 +137,20 @@ int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src
                     const int w = (int)(x >> 16) + wv;
                     const int d = staged ? (int)delta[(size_t)e1 * n_in + e2c] : 0;
                     const uint32_t cd = ((e1 - a0[lane]) << 16) | pos[lane];
+                    if (packed && ((e1 - a0[lane]) > 31 || pos[lane] > 31)) return -62;
+                    const int32_t dp = (int32_t)(((uint32_t)d << KEY_SHIFT) | ((31u - (e1 - a0[lane])) << KEY_ORD_BITS) | (31u - pos[lane]));
                     for (int rr = 0; rr < RC; ++rr) {
                         int r = r0 + rr - w;
                         const bool ok = r >= 0 && r0 + rr <= R;
                         r = r < 0 ? 0 : (r > R ? R : r);
-                        const int32_t c = src[(size_t)r * kk + base] + d;
-                        if (ok && c > best[lane][rr]) { best[lane][rr] = c; code[lane][rr] = cd; }
+                        const int32_t sv = src[(size_t)r * kk + base];
+                        if (packed) {                       // one word per layer: key = value << 10 | ordinals
+                            const int32_t key = ok ? sv + dp : -1;
+                            if (key > best[lane][rr]) best[lane][rr] = key;
+                        } else {
+                            const int32_t c = sv + d;
+                            if (ok && c > best[lane][rr]) { best[lane][rr] = c; code[lane][rr] = cd; }
+                        }
                     }
                 }
             }
@@ -150,7 +161,8 @@ int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src
                         const uint32_t o = lane + off < 32 ? lane + off : lane;      // __shfl_down_sync semantics
                         const int32_t ob = best[o][rr]; const uint32_t oc = code[o][rr];
                         nb[lane][rr] = best[lane][rr]; nc[lane][rr] = code[lane][rr];
-                        if (pos[lane] + off < seg[lane] && (ob > best[lane][rr] || (ob == best[lane][rr] && oc < code[lane][rr]))) {
+                        const bool take = packed ? (ob > best[lane][rr]) : (ob > best[lane][rr] || (ob == best[lane][rr] && oc < code[lane][rr]));
+                        if (pos[lane] + off < seg[lane] && take) {
                             if (lane + off >= 32) return -57;
                             nb[lane][rr] = ob; nc[lane][rr] = oc;
                         }
@@ -167,13 +179,20 @@ int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src
                     const bool lv = best[lane][rr] >= 0;
                     if (e.written[c]) return -59;
                     e.written[c] = 1;
-                    dst[c] = lv ? best[lane][rr] : NEG_INF;
-                    pl[c] = lv ? (PredT)(((code[lane][rr] >> 16) << SH) | (code[lane][rr] & 0xFFFFu)) : (PredT) ~(PredT)0;
+                    int32_t val = best[lane][rr];
+                    uint32_t cd = code[lane][rr];
+                    if (packed && lv) {
+                        const uint32_t inv = ~(uint32_t)val & 1023u;
+                        cd = ((inv >> KEY_ORD_BITS) << 16) | (inv & 31u);
+                        val = (int32_t)((uint32_t)val & ~1023u);
+                    }
+                    dst[c] = lv ? val : NEG_INF;
+                    pl[c] = lv ? (PredT)(((cd >> 16) << SH) | (cd & 0xFFFFu)) : (PredT) ~(PredT)0;
                     if (lv) {
-                        const int pi = (int)(in_edge[a0[lane] + (code[lane][rr] >> 16)] & 0xFFFFu);
-                        const int pj = (int)(in_edge[s0[lane] + (code[lane][rr] & 0xFFFFu)] & 0xFFFFu);
+                        const int pi = (int)(in_edge[a0[lane] + (cd >> 16)] & 0xFFFFu);
+                        const int pj = (int)(in_edge[s0[lane] + (cd & 0xFFFFu)] & 0xFFFFu);
                         ++e.live[h.level + 1];
-                        e.sum[h.level + 1] += cell_fold(c, best[lane][rr], pi, pj);
+                        e.sum[h.level + 1] += cell_fold(c, val >> e.shift, pi, pj);
                     }
                 }
             }
@@ -182,12 +201,13 @@ int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src
 }
 
 template <class PredT>
-int run(const DipPlan& p, const SweepShape& sh, int trace_T, int64_t* n_lane_tasks, int32_t* sink_value, int32_t* sink_s_het, int32_t* p1,
+int run(const DipPlan& p, const SweepShape& sh, int trace_T, bool no_pack, int64_t* n_lane_tasks, int32_t* sink_value, int32_t* sink_s_het, int32_t* p1,
         int32_t* n1, int32_t* p2, int32_t* n2, uint64_t* level_checksum, uint64_t* level_live) {
     const int R = p.R, L = p.L;
     Emu e(p, sh);
+    e.shift = (p.value_bound < KEY_VALUE_LIMIT && !no_pack) ? KEY_SHIFT : 0;    // same rule as dip_plan_host
     std::vector<PredT> pred((size_t)p.pred_off[L]);
-    const size_t widest = (size_t)(R + 1) * p.kmax * p.kmax;
+    const size_t widest = (size_t)(R + LANE_RC_SMALL) * p.kmax * p.kmax;
     // poison values make a wrong tile-placement flag visible
     e.g0.assign(widest, 0x5A5A5A5A); e.g1.assign(widest, 0x5A5A5A5A);
     e.s0.assign(sh.tile_cells, 0x3C3C3C3C); e.s1.assign(sh.tile_cells, 0x3C3C3C3C);
@@ -252,8 +272,8 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, int64_t* n_lane_tas
                 if (c >= p.P[l]) return -12;
                 const bool ssm = h.flags & TK_SRC_SMEM, dsm = h.flags & TK_DST_SMEM;
                 if ((ssm || dsm) && (!p.narrow[l] || c != 0)) return -12;
-                if ((ssm && (size_t)(R + 1) * h.k * h.k > (size_t)sh.tile_cells) ||
-                    (dsm && (size_t)(R + 1) * h.k2 * h.k2 > (size_t)sh.tile_cells)) return -13;
+                const size_t lp = (size_t)((R + LANE_RC_SMALL) / LANE_RC_SMALL) * LANE_RC_SMALL;       // whole lane-form chunks
+                if ((ssm && lp * h.k * h.k > (size_t)sh.tile_cells) || (dsm && lp * h.k2 * h.k2 > (size_t)sh.tile_cells)) return -13;
                 if (h.pred_off2 != p.pred_off[l + 1] || h.i0 >= h.i1 || h.i1 > h.k2) return -14;
                 if ((uint64_t)(h.i1 - h.i0) * h.k2 * h.k2 >= (1ull << 32)) return -14;    // div_magic exactness
                 const int32_t* src = ssm ? ((l & 1) ? e.s1.data() : e.s0.data()) : ((l & 1) ? e.g1.data() : e.g0.data());
@@ -261,9 +281,8 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, int64_t* n_lane_tas
                 for (int x = h.i0; x < h.i1; ++x) { if (row_done[x]) return -16; row_done[x] = 1; }
                 if (h.flags & TK_LANES) {
                     if ((h.flags & TK_REC_GLOBAL) || ssm != dsm) return -60;
-                    if (h.rc != LANE_RC_BIG && h.rc != LANE_RC_SMALL) return -61;
-                    const int lrc = h.rc == LANE_RC_BIG ? lane_items<PredT, LANE_RC_BIG>(e, slot.data(), h, src, dst, pl)
-                                                        : lane_items<PredT, LANE_RC_SMALL>(e, slot.data(), h, src, dst, pl);
+                    if (h.rc != LANE_RC_SMALL) return -61;
+                    const int lrc = lane_items<PredT, LANE_RC_SMALL>(e, slot.data(), h, src, dst, pl);
                     if (lrc) return lrc;
                     ++e.n_lane_tasks;
                 } else if (!(h.flags & TK_REC_GLOBAL)) {
@@ -271,7 +290,7 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, int64_t* n_lane_tas
                     t.k = h.k; t.k2 = h.k2;
                     t.in_off = reinterpret_cast<const uint16_t*>(slot.data() + sizeof(TaskHdr));
                     t.in_edge = reinterpret_cast<const uint32_t*>(slot.data() + sizeof(TaskHdr) + rec_edge_offset(h.k2));
-                    t.delta = nullptr; t.dstride = h.n_in; t.e1_base = 0; t.e2_base = 0; t.W = 0; t.msrc = t.mdst = nullptr;
+                    t.delta = nullptr; t.dstride = h.n_in; t.e1_base = 0; t.e2_base = 0; t.dshift = e.shift; t.W = 0; t.msrc = t.mdst = nullptr;
                     if (h.flags & TK_DELTA_STAGED) {
                         t.delta = reinterpret_cast<const uint16_t*>(slot.data() + sizeof(TaskHdr) + h.rec_bytes) + h.delta_skew;
                         t.e1_base = (int32_t)t.in_off[h.i0];
@@ -286,7 +305,7 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, int64_t* n_lane_tas
                     TransitionT<int32_t> t;
                     t.k = h.k; t.k2 = h.k2;
                     t.in_off = p.in_off.data() + mid; t.in_edge = p.in_edge.data();
-                    t.delta = nullptr; t.dstride = p.in_off[p.level_off[l + 2]] - ebase; t.e1_base = ebase; t.e2_base = ebase;
+                    t.delta = nullptr; t.dstride = p.in_off[p.level_off[l + 2]] - ebase; t.e1_base = ebase; t.e2_base = ebase; t.dshift = e.shift;
                     t.W = 0; t.msrc = t.mdst = nullptr;
                     if (h.flags & TK_DELTA) t.delta = e.delta.data() + p.delta_off[l];
                     else if (h.flags & TK_DELTA_MASKS) {
@@ -315,6 +334,7 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, int64_t* n_lane_tas
     const size_t ks = (size_t)(p.level_off[L] - p.level_off[L - 1]);
     const std::vector<int32_t>& last = ((L - 1) & 1) ? e.g1 : e.g0;     // the sink layer must be in global memory
     *sink_value = last[(size_t)R * ks * ks];   // cell (r=R,0,0) of the last level (:730, :775)
+    *sink_value = *sink_value < 0 ? NEG_INF : (*sink_value >> e.shift);
     TraceView v;
     v.L = L; v.R = R; v.level_off = p.level_off.data(); v.in_off = p.in_off.data(); v.in_edge = p.in_edge.data();
     v.lvlW = p.lvlW.data(); v.msrc_off = p.msrc_off.data(); v.mdst_off = p.mdst_off.data();
@@ -365,7 +385,7 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, int64_t* n_lane_tas
 
 }  // namespace
 
-// shape: [grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, lane_rc] (0 = kernel default)
+// shape: [grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, no_pack] (0 = kernel default)
 // counts: [narrow transitions, wide transitions, tasks, tasks with in-place records, tasks with on-the-fly masks, matrices,
 //          tasks run in lane form]
 extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
@@ -382,6 +402,7 @@ extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const 
     SweepShape sh;
     sh.grid = 32; sh.threads = 480; sh.tile_cells = 16384; sh.slot_bytes = 4096;
     int trace_T = 128;
+    bool no_pack = false;
     if (shape) {
         if (shape[0] > 0) sh.grid = shape[0];
         if (shape[1] > 0) sh.threads = shape[1];
@@ -390,7 +411,7 @@ extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const 
         if (shape[4] > 0) sh.delta_max_in = shape[4];
         if (shape[4] < 0) sh.delta_max_in = 0;
         if (shape[5] > 0) trace_T = shape[5];
-        if (shape[6] > 0) sh.lane_rc = shape[6];
+        no_pack = shape[6] != 0;
     }
     plan_tasks(p, sh);
     if (counts) {
@@ -398,6 +419,6 @@ extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const 
         counts[3] = p.n_tasks_global; counts[4] = p.n_tasks_masks; counts[5] = (int64_t)p.delta_list.size();
     }
     if (p.max_indeg <= 255 && !force_pred32)
-        return run<uint16_t>(p, sh, trace_T, counts ? counts + 6 : nullptr, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
-    return run<uint32_t>(p, sh, trace_T, counts ? counts + 6 : nullptr, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
+        return run<uint16_t>(p, sh, trace_T, no_pack, counts ? counts + 6 : nullptr, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
+    return run<uint32_t>(p, sh, trace_T, no_pack, counts ? counts + 6 : nullptr, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
 }

@@ -119,10 +119,10 @@ def test_lane_panel_model(oracle_mod, dp_emu):
         assert_dip_equal(oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R))
 
 
-# (grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T[, lane_rc])
+# (grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T[, no_pack])
 SHAPES = [
     (32, 480, 16384, 4096, 0, 0),       # the kernel's geometry
-    (32, 480, 16384, 4096, 0, 0, 8),    # ... with 8 layers per lane
+    (32, 480, 16384, 4096, 0, 0, 1),    # ... with the unpacked arithmetic (values of any size)
     (8, 64, 256, 512, 0, 5),            # small tiles and slots: narrow/wide hand-overs, row-split tasks
     (4, 32, 64, 160, 0, 3),             # slots too small for most records: in-place records
     (3, 16, 100000, 256, -1, 1),        # no matrices: on-the-fly masks everywhere (never narrow when coloured)

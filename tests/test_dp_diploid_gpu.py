@@ -137,3 +137,21 @@ def test_cuda_batch_mhc_samples(ctx, expected):
         e = expected["mhc4_chm13"]["diploid"][str(R)]
         assert o["value"] == e["value"] and o["s_het"] == e["s_het"]
         assert o["p1_edges"].ravel().tolist() == e["p1_edges"] and o["p2_edges"].ravel().tolist() == e["p2_edges"]
+
+
+def test_cuda_unpacked_arithmetic_path(ctx, oracle_mod, expected, monkeypatch):
+    """DG_NO_PACK=1 forces the unpacked lane/pair arithmetic that problems with DP values >= 2^21 take
+    (the default packs value and ordinals into one word per layer, dp_cell.h)."""
+    monkeypatch.setenv("DG_NO_PACK", "1")
+    for seed in range(8):
+        rng = np.random.default_rng(7000 + seed)
+        g = synth.random_level_graph(60 + seed, n_levels=int(rng.integers(2, 40)), max_width=int(rng.integers(1, 24)),
+                                     n_colours=int(rng.integers(0, 200)), p_weight1=float(rng.random() * 0.6),
+                                     p_colour=float(rng.random()), max_out=int(rng.integers(1, 5)))
+        R = int(rng.integers(0, 9))
+        assert_dip_equal(oracle_dip(oracle_mod, g, R), cuda_dip(ctx, g, R))
+    g, _ = LevelGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_dipin.npz"))
+    o = cuda_dip(ctx, g, 18)
+    e = expected["mhc4_chm13"]["diploid"]["18"]
+    assert o["value"] == e["value"] and o["p1_edges"].ravel().tolist() == e["p1_edges"]
+    assert hashlib.sha256(o["checksum"][1:].tobytes()).hexdigest() == e["checksum_sha256"]
