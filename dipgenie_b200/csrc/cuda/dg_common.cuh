@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -27,7 +28,11 @@ inline int fail(dg_ctx* ctx, int code, const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (ctx) ctx->err = buf;
+    if (ctx) {
+        static std::mutex mu;                  // batch workers may fail concurrently
+        std::lock_guard<std::mutex> lk(mu);
+        ctx->err = buf;
+    }
     return code;
 }
 

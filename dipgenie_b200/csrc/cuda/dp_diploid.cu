@@ -1252,7 +1252,8 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
         }
         const int k = i % K;
         collect(k);                               // the slot's previous sample (its kernels ran while the host planned others)
-        int r = dip_create_device(ctx, d.get());
+        int r = dip_create_device(ctx, d.get());     // (uploads stay on this thread: a pageable H2D issued by a worker on a
+                                                     //  busy slot stream blocks that worker until the slot's sweep ends)
         if (!r) r = dg_dip_run(ctx, d.get(), 0);
         if (r) { out[i].status = r; if (!rc) rc = r; continue; }
         slot[(size_t)k] = d.release(); owner[(size_t)k] = i;
