@@ -239,6 +239,11 @@ __device__ __forceinline__ void sweep_dm(const TransitionT<OffT>& t, const CellI
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int32_t lds_s32(uint32_t a) { int32_t v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ void sts_s32(uint32_t a, int32_t v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 __device__ __forceinline__ int32_t ldcg_s32(const int32_t* p) { return __ldcg(p); }
@@ -557,7 +562,7 @@ __device__ __noinline__ ulonglong2 generic_task(const SweepArgs& a, const uint8_
 }
 
 template <bool CHECK, bool PRED32, bool PROF>
-__global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepArgs a) {
+__global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_constant__ SweepArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const slots = smem;
     int32_t* const tileS0 = reinterpret_cast<int32_t*>(smem + (size_t)DIP_NSLOT * DIP_SLOT_BYTES);
@@ -608,14 +613,18 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepAr
     unsigned long long pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0, pc4 = 0, pc5 = 0, pc6 = 0, pc7 = 0, pc8 = 0, pc9 = 0;
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0;
     LaneProf lp = {0, 0, 0, 0, 0, 0};
+    // shared-window addresses, computed once
+    const uint32_t slots32 = smem_u32(slots), tiles32 = smem_u32(tileS0), full32 = smem_u32(full), empty32 = smem_u32(empty);
+    const int warp = tid >> 5;
     for (int32_t t = 0; t < n; ++t) {
-        const int slot = t % DIP_NSLOT;
+        const uint32_t slot = (uint32_t)t % DIP_NSLOT;
+        const uint32_t sb32 = slots32 + slot * DIP_SLOT_BYTES;
         const uint8_t* const sb = slots + (size_t)slot * DIP_SLOT_BYTES;
         if (profiling) tk0 = clock64();
-        mbar_wait(smem_u32(full + slot), (uint32_t)((t / DIP_NSLOT) & 1));
+        mbar_wait(full32 + 8u * slot, ((uint32_t)t / DIP_NSLOT) & 1u);
         if (profiling) tk1 = clock64();
         // exec part of the header (16-byte shared loads; the lane-form words only when needed)
-        const uint4 h1 = reinterpret_cast<const uint4*>(sb)[1], h2 = reinterpret_cast<const uint4*>(sb)[2];
+        const uint4 h1 = lds_v4(sb32 + 16u), h2 = lds_v4(sb32 + 32u);
         const uint32_t flags = h1.y;
         const int l = (int)h1.x;
         if (flags & TK_WAIT) {
@@ -627,29 +636,28 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepAr
         const bool ssm = (flags & TK_SRC_SMEM) != 0, dsm = (flags & TK_DST_SMEM) != 0;
         if ((uint32_t)(tid & ~31) < h2.w) {          // this warp owns work of the task
             if (flags & TK_LANES) {
-                const uint4 h0 = reinterpret_cast<const uint4*>(sb)[0], h3 = reinterpret_cast<const uint4*>(sb)[3],
-                            h4 = reinterpret_cast<const uint4*>(sb)[4], h5 = reinterpret_cast<const uint4*>(sb)[5];
+                const uint4 h0 = lds_v4(sb32), h3 = lds_v4(sb32 + 48u), h4 = lds_v4(sb32 + 64u), h5 = lds_v4(sb32 + 80u);
                 LaneTask lt;
-                lt.sb32 = smem_u32(sb);
-                const uint32_t tiles32 = smem_u32(tileS0);
-                lt.src32 = tiles32 + ((l & 1) ? (uint32_t)DIP_TILE_CELLS * 4u : 0u);
-                lt.dst32 = tiles32 + ((l & 1) ? 0u : (uint32_t)DIP_TILE_CELLS * 4u);
-                lt.gsrc = (l & 1) ? a.tile1 : a.tile0;
-                lt.gdst = (l & 1) ? a.tile0 : a.tile1;
+                lt.sb32 = sb32;
+                const uint32_t odd = (uint32_t)l & 1u;
+                lt.src32 = tiles32 + odd * ((uint32_t)DIP_TILE_CELLS * 4u);
+                lt.dst32 = tiles32 + (odd ^ 1u) * ((uint32_t)DIP_TILE_CELLS * 4u);
+                lt.gsrc = odd ? a.tile1 : a.tile0;
+                lt.gdst = odd ? a.tile0 : a.tile1;
                 const unsigned long long pred_off2 = ((unsigned long long)h3.y << 32) | h3.x;
                 lt.pl = pred + ((size_t)pred_off2 << pshift);
                 lt.k = h2.x & 0xFFFFu; lt.k2 = h2.x >> 16; lt.i0 = h2.y & 0xFFFFu; lt.i1 = h2.y >> 16; lt.n_in = h2.z;
                 lt.rec_bytes = h0.y; lt.skew = h1.w;
                 lt.nblk = h4.y & 0xFFFFu; lt.rp = h4.y >> 16; lt.nrg = h4.z; lt.m_nblk = h4.w;
                 lt.m_nrg = h5.x; lt.m_nin = h5.y; lt.n_witems = h5.z; lt.rounds = h5.w;
-                lt.bstart_off = reinterpret_cast<const uint32_t*>(sb)[24];
+                lt.bstart_off = lds_u32(sb32 + 96u);
                 lt.staged = (flags & TK_DELTA_STAGED) != 0;
                 if (a.shift) {
-                    if (ssm) lane_task_packed<true, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
-                    else lane_task_packed<false, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
+                    if (ssm) lane_task_packed<true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
+                    else lane_task_packed<false, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
                 } else {
-                    if (ssm) lane_task<LANE_RC_SMALL, true, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
-                    else lane_task<LANE_RC_SMALL, false, CHECK, PRED32, PROF>(lt, a.R, tid >> 5, lane, hsum, hlive, lp);
+                    if (ssm) lane_task<LANE_RC_SMALL, true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
+                    else lane_task<LANE_RC_SMALL, false, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
                 }
             } else {
                 const ulonglong2 hs = generic_task<CHECK, PRED32>(a, sb, tileS0, tileS1, tid);
@@ -658,7 +666,7 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const SweepAr
         }
         if (profiling) tk3 = clock64();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(empty + slot));    // this warp is done with the slot
+        if (lane == 0) mbar_arrive(empty32 + 8u * slot);       // this warp is done with the slot
         if (flags & TK_BAR) bar_compute();                     // the destination rows of this CTA are whole
         if ((flags & TK_ARRIVE) && tid == 0) red_release_add_u32(a.counter, 1u);
         if (profiling) {
