@@ -202,9 +202,11 @@ DG_HD void relax_pair(const TransitionT<OffT>& t, Load load, int R, int r0, int 
 // narrow levels enough items to spread over the CTA and still amortise the in-edge decode.
 constexpr int DIP_RC = 4;
 DG_HD int choose_rc(uint32_t, int, uint32_t) { return DIP_RC; }
-// Layers per lane in the lane form.  Measured on B200 (MHC_4, R=18): 4 is fastest — more, shorter warp items
-// keep all sub-partitions busy inside one level (8 layers per lane: 321 ms, 20: 564 ms, 4: 283 ms).
-constexpr int LANE_RC_SMALL = 4;
+// Layers per lane in the lane form (SweepShape::lane_rc).  Measured on B200 (MHC_4, R=18, 4 CTAs per sample):
+// unpacked arithmetic 4 / 8 / 20 layers -> 283 / 321 / 564 ms (register pressure, long serial items); packed keys
+// 4 / 5 / 8 / 10 layers -> 296 / 287 / 292 / 273 ms.  The planner takes LANE_RC_BIG with packed keys when there are
+// at least that many layers, else LANE_RC_SMALL.
+constexpr int LANE_RC_SMALL = 4, LANE_RC_BIG = 10;
 
 // Packed keys.  When every DP value is known to stay below 2^21 (the planner bounds it by the sum over
 // transitions of the colours present, DipPlan::value_bound), the layers hold value << KEY_SHIFT and the lane

@@ -377,10 +377,9 @@ __device__ __forceinline__ void lane_task(const LaneTask& t, int R, int warp, in
 // per layer and round.  Only the first chunk of layers runs a checked loop (layer index below 0 for weighted
 // edges); the tiles are padded to whole chunks, so the layers above R that the last chunk loads are in bounds
 // (and never stored).
-template <bool SMEM, bool CHECK, bool PRED32, bool PROF>
+template <int RC, bool SMEM, bool CHECK, bool PRED32, bool PROF>
 __device__ __forceinline__ void lane_task_packed(const LaneTask& t, int R, int warp, int lane,
                                                  unsigned long long& hsum, unsigned long long& hlive, LaneProf& lp) {
-    constexpr int RC = LANE_RC_SMALL;
     constexpr uint32_t ORD_MASK = (1u << (2 * KEY_ORD_BITS)) - 1u, ORD_ONE = (1u << KEY_ORD_BITS) - 1u;
     const uint32_t off32 = t.sb32 + (uint32_t)sizeof(TaskHdr);
     const uint32_t edge32 = off32 + (uint32_t)rec_edge_offset((int)t.k2);
@@ -653,8 +652,14 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
                 lt.bstart_off = lds_u32(sb32 + 96u);
                 lt.staged = (flags & TK_DELTA_STAGED) != 0;
                 if (a.shift) {
-                    if (ssm) lane_task_packed<true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
-                    else lane_task_packed<false, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
+                    const bool big = (h4.x & 0xFFFFu) == (uint32_t)LANE_RC_BIG;
+                    if (ssm) {
+                        if (big) lane_task_packed<LANE_RC_BIG, true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
+                        else lane_task_packed<LANE_RC_SMALL, true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
+                    } else {
+                        if (big) lane_task_packed<LANE_RC_BIG, false, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
+                        else lane_task_packed<LANE_RC_SMALL, false, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
+                    }
                 } else {
                     if (ssm) lane_task<LANE_RC_SMALL, true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
                     else lane_task<LANE_RC_SMALL, false, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
@@ -795,6 +800,7 @@ struct dg_dip {
     cudaStream_t stream = nullptr;   // the context's stream, or one of the batch streams
     bool cooperative = true;         // batch slots use plain launches (see dip_run_impl)
     int shift = 0;                   // KEY_SHIFT when every DP value provably stays below 2^21 (packed keys), else 0
+    int lane_rc = LANE_RC_SMALL;     // layers per lane of the lane form (tile padding follows it)
     std::vector<int32_t> h_cp;       // traceback checkpoints (host copies until uploaded)
     std::vector<int64_t> h_aoff;
     DipPlan plan;                 // host copy (small arrays kept for stats; big ones released after upload)
@@ -884,6 +890,8 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
     shape.tile_cells = DIP_TILE_CELLS;
     shape.slot_bytes = DIP_SLOT_BYTES;
     shape.delta_budget = lim.delta_budget;
+    shape.lane_rc = (d->shift != 0 && p.R + 1 >= LANE_RC_BIG) ? LANE_RC_BIG : LANE_RC_SMALL;
+    d->lane_rc = shape.lane_rc;
     plan_tasks(p, shape);
     d->grid = 1;
     for (int c = 0; c < p.grid; ++c) if (p.task_begin[(size_t)c + 1] > p.task_begin[c]) d->grid = c + 1;
@@ -944,7 +952,7 @@ static int dip_create_device(dg_ctx* ctx, dg_dip* d) {
     DG_CUDA(ctx, d->cp.upload(cp.data(), cp.size(), s));
     DG_CUDA(ctx, d->aoff.upload(aoff.data(), aoff.size(), s));
     // (layers rounded up to whole lane-form chunks: the last chunk loads, but never stores, layers above R)
-    const uint64_t widest = (uint64_t)(p.R + LANE_RC_SMALL) * (uint64_t)p.kmax * (uint64_t)p.kmax;
+    const uint64_t widest = (uint64_t)(p.R + d->lane_rc) * (uint64_t)p.kmax * (uint64_t)p.kmax;
     const size_t tile = (size_t)std::max<uint64_t>(widest, (uint64_t)(p.R + 1));
     DG_CUDA(ctx, d->tile0.alloc(tile, s));
     DG_CUDA(ctx, d->tile1.alloc(tile, s));

@@ -205,7 +205,7 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
     const int G = sh.grid < 1 ? 1 : sh.grid;
     const uint32_t CT = sh.threads < 1 ? 1u : (uint32_t)sh.threads;
     const size_t slot = (size_t)sh.slot_bytes;
-    const int lrc = LANE_RC_SMALL;
+    const int lrc = (sh.lane_rc == LANE_RC_BIG) ? LANE_RC_BIG : LANE_RC_SMALL;
     p.grid = G;
     p.P.assign(L, 1); p.bar_target.assign(L, 0); p.bar_edge.assign(L, 0); p.narrow.assign(L, 0);
     p.rec_off.assign(L, -1); p.delta_off.assign(L, -1); p.delta_list.clear(); p.delta_elems = 0;
@@ -217,7 +217,7 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
     auto width = [&](int l) { return p.level_off[l + 1] - p.level_off[l]; };
     // tile cells a layer set needs: R+1 layers rounded up to whole lane-form chunks, so that the loads of the last
     // chunk's layers above R (never stored) stay inside the tile
-    const uint64_t layers_padded = (uint64_t)((p.R + LANE_RC_SMALL) / LANE_RC_SMALL) * LANE_RC_SMALL;
+    const uint64_t layers_padded = (uint64_t)((p.R + lrc) / lrc) * lrc;
     auto cells_of = [&](int l) { const uint64_t k = (uint64_t)width(l); return layers_padded * k * k; };
     auto nin_of = [&](int l) { return (int64_t)p.in_off[p.level_off[l + 2]] - (int64_t)p.in_off[p.level_off[l + 1]]; };
 

@@ -207,7 +207,7 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, bool no_pack, int64
     Emu e(p, sh);
     e.shift = (p.value_bound < KEY_VALUE_LIMIT && !no_pack) ? KEY_SHIFT : 0;    // same rule as dip_plan_host
     std::vector<PredT> pred((size_t)p.pred_off[L]);
-    const size_t widest = (size_t)(R + LANE_RC_SMALL) * p.kmax * p.kmax;
+    const size_t widest = (size_t)(R + sh.lane_rc) * p.kmax * p.kmax;
     // poison values make a wrong tile-placement flag visible
     e.g0.assign(widest, 0x5A5A5A5A); e.g1.assign(widest, 0x5A5A5A5A);
     e.s0.assign(sh.tile_cells, 0x3C3C3C3C); e.s1.assign(sh.tile_cells, 0x3C3C3C3C);
@@ -272,7 +272,7 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, bool no_pack, int64
                 if (c >= p.P[l]) return -12;
                 const bool ssm = h.flags & TK_SRC_SMEM, dsm = h.flags & TK_DST_SMEM;
                 if ((ssm || dsm) && (!p.narrow[l] || c != 0)) return -12;
-                const size_t lp = (size_t)((R + LANE_RC_SMALL) / LANE_RC_SMALL) * LANE_RC_SMALL;       // whole lane-form chunks
+                const size_t lp = (size_t)((R + sh.lane_rc) / sh.lane_rc) * sh.lane_rc;       // whole lane-form chunks
                 if ((ssm && lp * h.k * h.k > (size_t)sh.tile_cells) || (dsm && lp * h.k2 * h.k2 > (size_t)sh.tile_cells)) return -13;
                 if (h.pred_off2 != p.pred_off[l + 1] || h.i0 >= h.i1 || h.i1 > h.k2) return -14;
                 if ((uint64_t)(h.i1 - h.i0) * h.k2 * h.k2 >= (1ull << 32)) return -14;    // div_magic exactness
@@ -281,8 +281,9 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, bool no_pack, int64
                 for (int x = h.i0; x < h.i1; ++x) { if (row_done[x]) return -16; row_done[x] = 1; }
                 if (h.flags & TK_LANES) {
                     if ((h.flags & TK_REC_GLOBAL) || ssm != dsm) return -60;
-                    if (h.rc != LANE_RC_SMALL) return -61;
-                    const int lrc = lane_items<PredT, LANE_RC_SMALL>(e, slot.data(), h, src, dst, pl);
+                    if (h.rc != e.sh.lane_rc) return -61;
+                    const int lrc = h.rc == LANE_RC_BIG ? lane_items<PredT, LANE_RC_BIG>(e, slot.data(), h, src, dst, pl)
+                                                        : lane_items<PredT, LANE_RC_SMALL>(e, slot.data(), h, src, dst, pl);
                     if (lrc) return lrc;
                     ++e.n_lane_tasks;
                 } else if (!(h.flags & TK_REC_GLOBAL)) {
@@ -413,6 +414,7 @@ extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const 
         if (shape[5] > 0) trace_T = shape[5];
         no_pack = shape[6] != 0;
     }
+    sh.lane_rc = (p.value_bound < KEY_VALUE_LIMIT && !no_pack && R + 1 >= LANE_RC_BIG) ? LANE_RC_BIG : LANE_RC_SMALL;   // as dip_plan_host
     plan_tasks(p, sh);
     if (counts) {
         counts[0] = p.n_narrow; counts[1] = p.n_wide; counts[2] = (int64_t)p.tasks.size();

@@ -165,3 +165,15 @@ def test_mhc_mode_mix(dp_emu):
     assert m["narrow"] > 0.9 * g.n_levels        # the bundled panel is almost entirely shared-memory resident
     assert m["tasks_global"] == 0 and m["tasks_masks"] == 0
     assert m["tasks_lanes"] > 0.95 * m["tasks"]           # nearly every task of real data takes the lane form
+
+
+@pytest.mark.parametrize("R", [9, 12, 25])
+def test_ten_layers_per_lane_variant(R, oracle_mod, dp_emu):
+    """With packed keys and at least 10 layers the lane form keeps 10 layers per lane (LANE_RC_BIG)."""
+    for seed in range(6):
+        rng = np.random.default_rng(9100 + seed)
+        g = synth.random_level_graph(800 + seed, n_levels=int(rng.integers(3, 25)), max_width=int(rng.integers(2, 14)),
+                                     n_colours=int(rng.integers(0, 120)), p_weight1=float(rng.random() * 0.6), p_colour=float(rng.random()))
+        assert_dip_equal(oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R))
+    g = synth.lane_panel_graph(5, n_lanes=10, n_blocks=6, rec_per_block=2, p_colour=0.3, n_colours=96)
+    assert_dip_equal(oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R))
