@@ -895,10 +895,8 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
     plan_tasks(p, shape);
     d->grid = 1;
     for (int c = 0; c < p.grid; ++c) if (p.task_begin[(size_t)c + 1] > p.task_begin[c]) d->grid = c + 1;
-    // traceback checkpoints: cp[0] = sink level, every DIP_TRACE_T levels down to level 0
-    d->h_cp.clear();
-    for (int l = L - 1; l > 0; l -= DIP_TRACE_T) d->h_cp.push_back(l);
-    d->h_cp.push_back(0);
+    // traceback checkpoints: cp[0] = sink level, then the narrowest level about every DIP_TRACE_T levels, down to level 0
+    d->h_cp = choose_checkpoints(p.level_off, DIP_TRACE_T);
     d->M = (int)d->h_cp.size() - 1;
     d->h_aoff.assign((size_t)d->M + 1, 0);
     for (int m = 0; m < d->M; ++m) {

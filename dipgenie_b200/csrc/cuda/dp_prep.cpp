@@ -200,6 +200,24 @@ int lane_blocks(const DipPlan& p, int l, uint16_t* out, int* rounds) {
 
 }  // namespace
 
+std::vector<int32_t> choose_checkpoints(const std::vector<int32_t>& level_off, int T) {
+    const int L = (int)level_off.size() - 1;
+    std::vector<int32_t> cp;
+    if (T < 1) T = 1;
+    int cur = L - 1;
+    cp.push_back(cur);
+    while (cur > 0) {
+        const int hi = cur - std::max(1, T / 2), lo = cur - (T + T / 2);
+        if (lo <= 0) { cp.push_back(0); break; }
+        int best = hi;
+        for (int l = hi; l >= lo; --l)
+            if (level_off[l + 1] - level_off[l] < level_off[best + 1] - level_off[best]) best = l;
+        cp.push_back(best);
+        cur = best;
+    }
+    return cp;
+}
+
 void plan_tasks(DipPlan& p, const SweepShape& sh) {
     const int L = p.L, T = L - 1;                  // T = number of transitions
     const int G = sh.grid < 1 ? 1 : sh.grid;

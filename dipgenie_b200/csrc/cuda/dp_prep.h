@@ -89,6 +89,11 @@ struct DipPlan {
 // Builds the gather-form arrays; returns false and sets plan.error on malformed input.
 bool build_dip_plan(const DipGraphView& g, DipPlan& plan);
 
+// Traceback checkpoints (dp_diploid.cu: dip_anc_kernel walks EVERY cell of a checkpoint level back to the previous
+// checkpoint, so narrow checkpoint levels are cheap ones): cp[0] = L-1 (sink level), then, about every T levels,
+// the narrowest level of the window [cur - 3T/2, cur - T/2]; the list ends with level 0.
+std::vector<int32_t> choose_checkpoints(const std::vector<int32_t>& level_off, int T);
+
 // Compiles the sweep into per-CTA task streams for the given kernel geometry: narrow/wide placement of
 // every layer, row partition of wide transitions, slot-sized sub-tasks, barrier schedule, packed records
 // and the layout of the pair-score matrices.

@@ -340,9 +340,9 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, bool no_pack, int64
     v.L = L; v.R = R; v.level_off = p.level_off.data(); v.in_off = p.in_off.data(); v.in_edge = p.in_edge.data();
     v.lvlW = p.lvlW.data(); v.msrc_off = p.msrc_off.data(); v.mdst_off = p.mdst_off.data();
     v.masks = p.masks.data(); v.pred_off = p.pred_off.data();
-    std::vector<int32_t> cp;
-    for (int l = L - 1; l > 0; l -= trace_T) cp.push_back(l);
-    cp.push_back(0);
+    const std::vector<int32_t> cp = choose_checkpoints(p.level_off, trace_T);
+    if (cp.front() != L - 1 || cp.back() != 0) return -43;
+    for (size_t x = 1; x < cp.size(); ++x) if (cp[x] >= cp[x - 1]) return -43;
     const int M = (int)cp.size() - 1;
     const int cap = R + 2;
     *n1 = 0; *n2 = 0; *sink_s_het = 0;
