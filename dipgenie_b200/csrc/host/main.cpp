@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../../include/dipgenie_cuda.h"
 #include "pipeline.h"
@@ -23,11 +24,14 @@ static void usage(FILE* f) {
     fprintf(f, "  -k INT    k-mer size [31]      -w INT   minimizer window [25]\n");
     fprintf(f, "  -T FLOAT  shared-anchor threshold [1.0]\n");
     fprintf(f, "  -d INT    CUDA device [0]      -q       quiet\n");
+    fprintf(f, "  -B FILE   batch: one job per line, \"graph<TAB>reads<TAB>out\" (then -g/-r/-o are not needed); the\n");
+    fprintf(f, "            diploid DPs of all jobs run side by side on the GPU\n");
 }
 
 int main(int argc, char** argv) {
     dgh::Options o;
     int device = 0;
+    std::string batch_file;
     for (int i = 1; i < argc; ++i) {
         const char* a = argv[i];
         if (!strcmp(a, "--version")) { puts("dipgenie-b200 1.0"); return 0; }
@@ -48,10 +52,11 @@ int main(int argc, char** argv) {
             case 'w': o.w = atoi(v); break;
             case 'T': o.threshold = (float)atof(v); break;
             case 'd': device = atoi(v); break;
+            case 'B': batch_file = v; break;
             default: break;                                                         // other reference flags (-c -m -N -H -P -l -a) steer the ILP branch only
         }
     }
-    if (o.gfa.empty() || o.reads.empty() || o.out.empty()) { usage(stderr); return 1; }
+    if (batch_file.empty() && (o.gfa.empty() || o.reads.empty() || o.out.empty())) { usage(stderr); return 1; }
     if (o.ploidy != 1 && o.ploidy != 2) { fprintf(stderr, "Ploidy must be 1 or 2\n"); return 0; }
     auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t0 = now();
@@ -73,12 +78,39 @@ int main(int argc, char** argv) {
                        const int32_t* cv, const uint8_t* hom, int32_t nc, int32_t R, int32_t* val, int32_t* sh, int32_t* p1, int32_t* n1,
                        int32_t* p2, int32_t* n2) {
         return dg_dp_diploid((dg_ctx*)c, L, lo, ao, ad, aw, co, cv, hom, nc, R, val, sh, p1, n1, p2, n2); };
+    be.dp_diploid_batch = [](void* c, int32_t n, const dg_dip_input_t* in, dg_dip_output_t* out, int32_t mc, int32_t cps) {
+        return dg_dp_diploid_batch((dg_ctx*)c, n, in, out, mc, cps); };
     be.free_array = [](void* p) { dg_free(p); };
     be.last_error = [](void* c) { return dg_last_error((dg_ctx*)c); };
-    dgh::RunSummary sum;
-    std::string err;
-    const int rc = dgh::run_pipeline(o, be, sum, err);
-    if (rc) fprintf(stderr, "dipgenie: %s\n", err.c_str());
+    int rc = 0;
+    if (!batch_file.empty()) {
+        std::vector<dgh::Options> jobs;
+        FILE* f = fopen(batch_file.c_str(), "r");
+        if (!f) { fprintf(stderr, "dipgenie: cannot open %s\n", batch_file.c_str()); dg_destroy(ctx); return 1; }
+        char line[8192];
+        while (fgets(line, sizeof line, f)) {
+            char g[4096], r[4096], out[4096];
+            if (sscanf(line, "%4095s %4095s %4095s", g, r, out) != 3) continue;
+            dgh::Options j = o;
+            j.gfa = g; j.reads = r; j.out = out; j.verbose = false;
+            jobs.push_back(j);
+        }
+        fclose(f);
+        std::vector<dgh::RunSummary> sums;
+        std::vector<std::string> errs;
+        const double tb = now();
+        rc = dgh::run_batch(jobs, be, sums, errs) ? 1 : 0;
+        for (size_t i = 0; i < jobs.size(); ++i) {
+            if (!errs[i].empty()) fprintf(stderr, "dipgenie: job %zu (%s): %s\n", i, jobs[i].out.c_str(), errs[i].c_str());
+            else if (o.verbose) fprintf(stderr, "job %zu\t%s\tDP value %d\tr %d/%d\tbp %lld/%lld\n", i, jobs[i].out.c_str(), sums[i].dp_value, sums[i].r1, sums[i].r2, (long long)sums[i].len1, (long long)sums[i].len2);
+        }
+        if (o.verbose) fprintf(stderr, "[M::main] %zu jobs in %.3f sec (%.2f samples/s)\n", jobs.size(), now() - tb, jobs.size() / (now() - tb));
+    } else {
+        dgh::RunSummary sum;
+        std::string err;
+        rc = dgh::run_pipeline(o, be, sum, err);
+        if (rc) fprintf(stderr, "dipgenie: %s\n", err.c_str());
+    }
     const double t1 = now();
     dg_destroy(ctx);
     if (o.verbose) fprintf(stderr, "[M::main] released the device after %.3f sec; total %.3f sec\n", now() - t1, now() - t0);

@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
+#include <vector>
 
 #include "dgh.h"
 
@@ -22,12 +25,28 @@ struct Owned {                         // library-allocated array, released with
 };
 }  // namespace
 
-int run_pipeline(const Options& o, const Backend& be, RunSummary& sum, std::string& err) {
+// Everything before the DP call: parse, panel, device sketch + join, anchors + classifier, expansion, (diploid)
+// levelization, flattening into the C-ABI arrays.  `gpu` serialises the device stages of concurrent samples (one
+// dg_ctx is used by one host thread at a time).
+struct Prepared {
+    Options o;
+    Panel panel;
+    Expanded ex;
+    std::vector<int64_t> adj_off, col_off;
+    std::vector<int32_t> adj_dst, col_val, level_off;
+    std::vector<uint8_t> adj_w;
+    RunSummary sum;
+    double t0 = 0;
+};
+
+static int prepare(const Options& o, const Backend& be, Prepared& P, std::mutex* gpu, std::string& err) {
     const double t0 = now_s();
+    P.o = o; P.t0 = t0;
+    RunSummary& sum = P.sum;
     sum = RunSummary();
     GfaGraph gfa;
     if (!read_gfa_file(o.gfa, gfa, err)) return 1;
-    Panel panel;
+    Panel& panel = P.panel;
     if (!build_panel(gfa, panel, err)) return 1;
     const int H = (int)panel.paths.size();
     if (o.verbose) fprintf(stderr, "[M::%s::%.3f] loaded the graph: %d segments, %d walks\n", __func__, now_s() - t0, panel.n_vtx, H);
@@ -45,6 +64,7 @@ int run_pipeline(const Options& o, const Backend& be, RunSummary& sum, std::stri
         Owned<uint64_t> sp; Owned<uint32_t> rc;
         sp.fr = rc.fr = be.free_array;
         uint64_t ns = 0;
+        std::unique_lock<std::mutex> lk; if (gpu) lk = std::unique_lock<std::mutex>(*gpu);
         const int e = be.sketch_reads(be.ctx, (const uint8_t*)bases.data(), off.data(), (uint32_t)reads.size(), o.k, o.w, &sp.p, &rc.p, &ns);
         if (e) { err = std::string("dg_sketch_reads: ") + (be.last_error ? be.last_error(be.ctx) : "failed"); return 1; }
         sk.spectrum.assign(sp.p, sp.p + ns);
@@ -66,6 +86,7 @@ int run_pipeline(const Options& o, const Backend& be, RunSummary& sum, std::stri
         sk.n_minimizers.assign((size_t)std::max(H, 1), 0);
         Owned<uint64_t> ho, vo; Owned<uint32_t> hs; Owned<int32_t> hv;
         ho.fr = vo.fr = hs.fr = hv.fr = be.free_array;
+        std::unique_lock<std::mutex> lk; if (gpu) lk = std::unique_lock<std::mutex>(*gpu);
         const int e = be.index_walks(be.ctx, (const uint8_t*)seg_bases.data(), seg_off.data(), (uint32_t)panel.n_vtx, walk_vtx.data(),
                                      walk_off.data(), (uint32_t)H, panel.top_order_map.data(), o.k, o.w, sk.spectrum.data(),
                                      (uint64_t)sk.spectrum.size(), sk.n_minimizers.data(), &ho.p, &hs.p, &vo.p, &hv.p);
@@ -91,7 +112,7 @@ int run_pipeline(const Options& o, const Backend& be, RunSummary& sum, std::stri
     }
 
     // ---- host: haplotype-expanded graph in Kahn order (approximator.cpp:1014-1256) ----
-    Expanded ex;
+    Expanded& ex = P.ex;
     if (!expand_graph(panel, anchors, ex, err)) return 1;
     auto flatten = [](const ExpGraph& g, std::vector<int64_t>& adj_off, std::vector<int32_t>& adj_dst, std::vector<uint8_t>& adj_w,
                       std::vector<int64_t>& col_off, std::vector<int32_t>& col_val) {
@@ -105,55 +126,132 @@ int run_pipeline(const Options& o, const Backend& be, RunSummary& sum, std::stri
             col_off[u + 1] = (int64_t)col_val.size();
         }
     };
-    std::vector<int64_t> adj_off, col_off;
-    std::vector<int32_t> adj_dst, col_val;
-    std::vector<uint8_t> adj_w;
 
-    if (o.ploidy == 1) {
-        // ---- device stage 3a: haploid DP + R+1 tracebacks (approximator.cpp:44-102, :141-153) ----
-        flatten(ex.g, adj_off, adj_dst, adj_w, col_off, col_val);
-        std::vector<int32_t> colours((size_t)o.R + 1, 0);
-        std::vector<int64_t> path_off((size_t)o.R + 2, 0);
-        Owned<int32_t> paths;
-        paths.fr = be.free_array;
-        const int e = be.dp_haploid(be.ctx, (int32_t)ex.g.adj.size(), adj_off.data(), adj_dst.data(), adj_w.data(), col_off.data(),
-                                    col_val.data(), ex.n_colours, o.R, colours.data(), path_off.data(), &paths.p);
-        if (e) { err = std::string("dg_dp_haploid: ") + (be.last_error ? be.last_error(be.ctx) : "failed"); return 1; }
-        std::string log;
-        const int best_r = haploid_best_r(std::vector<int>(colours.begin(), colours.end()), log);   // double arithmetic stays on the host
-        sum.best_r = best_r;
-        if (o.verbose) fprintf(stderr, "%sRecombination count: %d\n", log.c_str(), best_r);
-        std::vector<int32_t> path(paths.p + path_off[(size_t)best_r], paths.p + path_off[(size_t)best_r + 1]);
-        const std::string seq = haploid_sequence(panel, ex.g, path);
-        sum.len1 = (int64_t)seq.size();
-        if (!write_fasta_haploid(o.out, seq)) { err = "cannot write " + o.out; return 1; }
-    } else {
-        // ---- host: levelization (ExpandedGraph.hpp:269-409); device stage 3b: diploid DP + edge lists ----
-        if (!levelize(ex.g, err)) return 1;
-        flatten(ex.g, adj_off, adj_dst, adj_w, col_off, col_val);
+    if (o.ploidy != 1) {
+        if (!levelize(ex.g, err)) return 1;      // ExpandedGraph.hpp:269-409
         const int L = (int)ex.g.vertices_in_level.size();
-        std::vector<int32_t> level_off((size_t)L + 1, 0);
-        for (int l = 0; l < L; ++l) level_off[(size_t)l + 1] = level_off[l] + (int32_t)ex.g.vertices_in_level[l].size();
+        P.level_off.assign((size_t)L + 1, 0);
+        for (int l = 0; l < L; ++l) P.level_off[(size_t)l + 1] = P.level_off[l] + (int32_t)ex.g.vertices_in_level[l].size();
+    }
+    flatten(ex.g, P.adj_off, P.adj_dst, P.adj_w, P.col_off, P.col_val);
+    return 0;
+}
+
+// After the diploid DP: stitch the two sequences and write the FASTA (approximator.cpp:779-925, :1314-1325).
+static int finish_diploid(Prepared& P, int32_t value, const int32_t* e1, int32_t n1, const int32_t* e2, int32_t n2, std::string& err) {
+    const Options& o = P.o;
+    P.sum.dp_value = value;
+    if (o.verbose) fprintf(stderr, "DP value: %d\n", value);
+    std::vector<std::pair<int, int>> p1, p2;
+    for (int x = 0; x < n1; ++x) p1.emplace_back(e1[2 * x], e1[2 * x + 1]);
+    for (int x = 0; x < n2; ++x) p2.emplace_back(e2[2 * x], e2[2 * x + 1]);
+    DiploidSolution sol;
+    if (!stitch_diploid(P.panel, P.ex.g, p1, p2, sol, err)) return 1;
+    P.sum.r1 = sol.r1; P.sum.r2 = sol.r2; P.sum.len1 = (int64_t)sol.hap1.size(); P.sum.len2 = (int64_t)sol.hap2.size();
+    if (o.verbose)
+        fprintf(stderr, "Recombinations in P1: %d, P2: %d, bp: %lld / %lld\n", sol.r1, sol.r2, (long long)P.sum.len1, (long long)P.sum.len2);
+    if (!write_fasta_diploid(o.out, sol.hap1, sol.hap2)) { err = "cannot write " + o.out; return 1; }
+    return 0;
+}
+
+static int solve_haploid(Prepared& P, const Backend& be, std::string& err) {
+    const Options& o = P.o;
+    // ---- device stage 3a: haploid DP + R+1 tracebacks (approximator.cpp:44-102, :141-153) ----
+    std::vector<int32_t> colours((size_t)o.R + 1, 0);
+    std::vector<int64_t> path_off((size_t)o.R + 2, 0);
+    Owned<int32_t> paths;
+    paths.fr = be.free_array;
+    const int e = be.dp_haploid(be.ctx, (int32_t)P.ex.g.adj.size(), P.adj_off.data(), P.adj_dst.data(), P.adj_w.data(), P.col_off.data(),
+                                P.col_val.data(), P.ex.n_colours, o.R, colours.data(), path_off.data(), &paths.p);
+    if (e) { err = std::string("dg_dp_haploid: ") + (be.last_error ? be.last_error(be.ctx) : "failed"); return 1; }
+    std::string log;
+    const int best_r = haploid_best_r(std::vector<int>(colours.begin(), colours.end()), log);   // double arithmetic stays on the host
+    P.sum.best_r = best_r;
+    if (o.verbose) fprintf(stderr, "%sRecombination count: %d\n", log.c_str(), best_r);
+    std::vector<int32_t> path(paths.p + path_off[(size_t)best_r], paths.p + path_off[(size_t)best_r + 1]);
+    const std::string seq = haploid_sequence(P.panel, P.ex.g, path);
+    P.sum.len1 = (int64_t)seq.size();
+    if (!write_fasta_haploid(o.out, seq)) { err = "cannot write " + o.out; return 1; }
+    return 0;
+}
+
+int run_pipeline(const Options& o, const Backend& be, RunSummary& sum, std::string& err) {
+    Prepared P;
+    if (int rc = prepare(o, be, P, nullptr, err)) return rc;
+    int rc = 0;
+    if (o.ploidy == 1) {
+        rc = solve_haploid(P, be, err);
+    } else {
+        // ---- device stage 3b: diploid DP + edge lists ----
         int32_t value = 0, s_het = 0, n1 = 0, n2 = 0;
         std::vector<int32_t> e1(2 * ((size_t)o.R + 2)), e2(2 * ((size_t)o.R + 2));
-        const int e = be.dp_diploid(be.ctx, L, level_off.data(), adj_off.data(), adj_dst.data(), adj_w.data(), col_off.data(), col_val.data(),
-                                    ex.color_homo_bv.data(), (int32_t)ex.color_homo_bv.size(), o.R, &value, &s_het, e1.data(), &n1,
-                                    e2.data(), &n2);
+        const int e = be.dp_diploid(be.ctx, (int32_t)P.level_off.size() - 1, P.level_off.data(), P.adj_off.data(), P.adj_dst.data(),
+                                    P.adj_w.data(), P.col_off.data(), P.col_val.data(), P.ex.color_homo_bv.data(),
+                                    (int32_t)P.ex.color_homo_bv.size(), o.R, &value, &s_het, e1.data(), &n1, e2.data(), &n2);
         if (e) { err = std::string("dg_dp_diploid: ") + (be.last_error ? be.last_error(be.ctx) : "failed"); return 1; }
-        sum.dp_value = value;
-        if (o.verbose) fprintf(stderr, "DP value: %d\n", value);
-        std::vector<std::pair<int, int>> p1, p2;
-        for (int x = 0; x < n1; ++x) p1.emplace_back(e1[2 * x], e1[2 * x + 1]);
-        for (int x = 0; x < n2; ++x) p2.emplace_back(e2[2 * x], e2[2 * x + 1]);
-        DiploidSolution sol;
-        if (!stitch_diploid(panel, ex.g, p1, p2, sol, err)) return 1;
-        sum.r1 = sol.r1; sum.r2 = sol.r2; sum.len1 = (int64_t)sol.hap1.size(); sum.len2 = (int64_t)sol.hap2.size();
-        if (o.verbose)
-            fprintf(stderr, "Recombinations in P1: %d, P2: %d, bp: %lld / %lld\n", sol.r1, sol.r2, (long long)sum.len1, (long long)sum.len2);
-        if (!write_fasta_diploid(o.out, sol.hap1, sol.hap2)) { err = "cannot write " + o.out; return 1; }
+        rc = finish_diploid(P, value, e1.data(), n1, e2.data(), n2, err);
     }
-    if (o.verbose) fprintf(stderr, "[M::%s] Real time: %.3f sec\n", __func__, now_s() - t0);
-    return 0;
+    sum = P.sum;
+    if (!rc && o.verbose) fprintf(stderr, "[M::%s] Real time: %.3f sec\n", __func__, now_s() - P.t0);
+    return rc;
+}
+
+// Many samples in one process (the reference's batch script starts one process per sample,
+// data/run_DipGenie_batch.sh:21-39): the stages before the DP run sample-parallel on the host threads (device
+// sketch stages one at a time), all diploid DPs go to the GPU together (dg_dp_diploid_batch), stitching and FASTA
+// output run sample-parallel again.
+int run_batch(const std::vector<Options>& jobs, const Backend& be, std::vector<RunSummary>& sums, std::vector<std::string>& errs) {
+    const int n = (int)jobs.size();
+    sums.assign((size_t)n, RunSummary());
+    errs.assign((size_t)n, std::string());
+    std::vector<std::unique_ptr<Prepared>> P((size_t)n);
+    std::vector<int> rc((size_t)n, 0);
+    std::mutex gpu;
+    const int nt = std::max(1, std::min(n, jobs.empty() ? 1 : jobs[0].threads));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    for (int i = 0; i < n; ++i) {
+        P[(size_t)i].reset(new Prepared());
+        rc[(size_t)i] = prepare(jobs[(size_t)i], be, *P[(size_t)i], &gpu, errs[(size_t)i]);
+    }
+    std::vector<int> dip;
+    for (int i = 0; i < n; ++i) {
+        if (rc[(size_t)i]) continue;
+        if (jobs[(size_t)i].ploidy == 1) rc[(size_t)i] = solve_haploid(*P[(size_t)i], be, errs[(size_t)i]);
+        else dip.push_back(i);
+    }
+    std::vector<dg_dip_output_t> out(dip.size());
+    if (!dip.empty() && be.dp_diploid_batch) {
+        std::vector<dg_dip_input_t> in(dip.size());
+        for (size_t x = 0; x < dip.size(); ++x) {
+            Prepared& q = *P[(size_t)dip[x]];
+            in[x] = {(int32_t)q.level_off.size() - 1, q.level_off.data(), q.adj_off.data(), q.adj_dst.data(), q.adj_w.data(), q.col_off.data(),
+                     q.col_val.data(), q.ex.color_homo_bv.data(), (int32_t)q.ex.color_homo_bv.size(), q.o.R};
+        }
+        be.dp_diploid_batch(be.ctx, (int32_t)dip.size(), in.data(), out.data(), 0, 0);
+        for (size_t x = 0; x < dip.size(); ++x)
+            if (out[x].status) { rc[(size_t)dip[x]] = 1; errs[(size_t)dip[x]] = std::string("dg_dp_diploid_batch: ") + (be.last_error ? be.last_error(be.ctx) : "failed"); }
+    } else {
+        for (size_t x = 0; x < dip.size(); ++x) {
+            Prepared& q = *P[(size_t)dip[x]];
+            dg_dip_output_t& o = out[x];
+            memset(&o, 0, sizeof o);
+            if (q.o.R + 2 > DG_BATCH_MAX_EDGES) { rc[(size_t)dip[x]] = 1; errs[(size_t)dip[x]] = "R too large for the batch record"; continue; }
+            o.status = be.dp_diploid(be.ctx, (int32_t)q.level_off.size() - 1, q.level_off.data(), q.adj_off.data(), q.adj_dst.data(), q.adj_w.data(),
+                                     q.col_off.data(), q.col_val.data(), q.ex.color_homo_bv.data(), (int32_t)q.ex.color_homo_bv.size(), q.o.R,
+                                     &o.sink_value, &o.sink_s_het, o.p1_edges, &o.n_p1, o.p2_edges, &o.n_p2);
+            if (o.status) { rc[(size_t)dip[x]] = 1; errs[(size_t)dip[x]] = std::string("dg_dp_diploid: ") + (be.last_error ? be.last_error(be.ctx) : "failed"); }
+        }
+    }
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    for (int x = 0; x < (int)dip.size(); ++x) {
+        const int i = dip[(size_t)x];
+        if (rc[(size_t)i]) continue;
+        const dg_dip_output_t& o = out[(size_t)x];
+        rc[(size_t)i] = finish_diploid(*P[(size_t)i], o.sink_value, o.p1_edges, o.n_p1, o.p2_edges, o.n_p2, errs[(size_t)i]);
+    }
+    int bad = 0;
+    for (int i = 0; i < n; ++i) { sums[(size_t)i] = P[(size_t)i] ? P[(size_t)i]->sum : RunSummary(); if (rc[(size_t)i]) ++bad; }
+    return bad;
 }
 
 }  // namespace dgh

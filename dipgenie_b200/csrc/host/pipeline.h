@@ -5,6 +5,9 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <vector>
+
+#include "../../../include/dipgenie_cuda.h"
 
 namespace dgh {
 
@@ -26,6 +29,7 @@ struct Backend {                       // signatures of include/dipgenie_cuda.h 
     int (*dp_diploid)(void*, int32_t, const int32_t*, const int64_t*, const int32_t*, const uint8_t*, const int64_t*,
                       const int32_t*, const uint8_t*, int32_t, int32_t, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
                       int32_t*) = nullptr;
+    int (*dp_diploid_batch)(void*, int32_t, const dg_dip_input_t*, dg_dip_output_t*, int32_t, int32_t) = nullptr;   // optional
     void (*free_array)(void*) = nullptr;
     const char* (*last_error)(void*) = nullptr;
 };
@@ -38,5 +42,9 @@ struct RunSummary {                    // integer checkpoints of the reference's
 
 // Returns 0, or the reference's exit status for the failure (usage/IO errors 1).  Progress lines go to stderr.
 int run_pipeline(const Options& o, const Backend& be, RunSummary& sum, std::string& err);
+
+// Several runs in one process; diploid DPs are batched on the GPU when the backend offers dg_dp_diploid_batch.
+// Returns the number of failed jobs (errs[i] non-empty for those).
+int run_batch(const std::vector<Options>& jobs, const Backend& be, std::vector<RunSummary>& sums, std::vector<std::string>& errs);
 
 }  // namespace dgh

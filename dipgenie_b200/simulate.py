@@ -106,6 +106,31 @@ def make_reads(seed: int, panel, coverage: float = 4.0, read_len: int = 150, err
     return reads
 
 
+def reads_from_walks(seed: int, panel, walk_ids, coverage: float = 4.0, read_len: int = 150, err: float = 0.001):
+    """Reads drawn evenly from the given panel walks (leave-one-out study: the two walks of the held-out sample)."""
+    rng = np.random.default_rng(seed + 104729)
+    reads = []
+    for h in walk_ids:
+        hap = walk_sequence(panel, panel["walks"][h])
+        n = int(coverage / len(walk_ids) * len(hap) / read_len)
+        for st in rng.integers(0, max(1, len(hap) - read_len), n):
+            r = hap[st:st + read_len].copy()
+            m = rng.random(len(r)) < err
+            r[m] = _ACGT[rng.integers(0, 4, int(m.sum()))]
+            if rng.random() < 0.5:
+                r = _COMP[r[::-1]]
+            reads.append(r)
+    return reads
+
+
+def without_walks(panel, drop):
+    """The panel minus some walks (segments and links stay: the held-out sample's private alleles remain as
+    vertices no walk visits, as in a graph built from the full cohort)."""
+    keep = [h for h in range(len(panel["walks"])) if h not in set(drop)]
+    return dict(segs=panel["segs"], links=panel["links"], walks=[panel["walks"][h] for h in keep],
+                alleles=panel["alleles"][keep])
+
+
 def write_gfa(path, panel, samples=None):
     with open(path, "wb") as f:
         f.write(b"H\tVN:Z:1.1\n")

@@ -73,3 +73,27 @@ def test_cli_matches_reference_on_synthetic(name, seed, flags, tmp_path):
                        timeout=900)
     assert p.returncode == 0, p.stderr[-1500:]
     assert md5(str(tmp_path / "ours.fa")) == want
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_cli_batch_leave_one_out_matches_reference(tmp_path):
+    """SURVEY 8d config 5 at reduced scale: a 7-sample (14-walk) panel, every sample held out in turn (graph = panel
+    minus its two walks, reads from its two walks); one `dipgenie -B` process runs all jobs with the diploid DPs side
+    by side on the GPU; every FASTA must equal the reference binary's run on the same job."""
+    assert os.path.exists(_build.CLI_BIN)
+    panel = simulate.make_panel(11, backbone=30000, n_sites=220, n_walks=14, n_founders=6)
+    jobs = []
+    for s in range(7):
+        sub = simulate.without_walks(panel, [2 * s, 2 * s + 1])
+        g, r, o = str(tmp_path / f"loo{s}.gfa"), str(tmp_path / f"loo{s}.fa"), str(tmp_path / f"loo{s}.out.fa")
+        simulate.write_gfa(g, sub)
+        simulate.write_reads(r, simulate.reads_from_walks(100 + s, panel, [2 * s, 2 * s + 1], coverage=4.0))
+        jobs.append((g, r, o))
+    manifest = tmp_path / "jobs.tsv"
+    manifest.write_text("".join(f"{g}\t{r}\t{o}\n" for g, r, o in jobs))
+    p = subprocess.run([_build.CLI_BIN, "-B", str(manifest), "-p2", "-R6", "-t8"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-1500:]
+    assert "7 jobs" in p.stderr
+    for g, r, o in jobs:
+        assert md5(o) == run_ref(g, r, o + ".ref", ["-p2", "-R6"])
