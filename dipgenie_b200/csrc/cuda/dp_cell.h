@@ -50,6 +50,7 @@ enum : uint32_t {
     TK_REC_GLOBAL = 128,   // in-edge lists are read in place from the global CSR (record too big for a slot)
     TK_DELTA_MASKS = 256,  // no matrix was materialised (too wide): popcount the colour masks on the fly
     TK_LANES = 512,        // lane form (below); otherwise the pair form
+    TK_LONG = 1024,        // lane form with destinations of more than 32 in-edges (slice blocks + scratch combine)
 };
 
 // Two evaluation forms of a task, same results:
@@ -59,7 +60,10 @@ enum : uint32_t {
 //    for its e2; the lanes of one destination column j' (adjacent: in-edges are grouped by destination, and a
 //    block never cuts a group) are then combined by a segmented warp-shuffle maximum (value desc, code asc),
 //    and the first lane of each group stores the cell.  Needs: staged record, pair scores absent or staged,
-//    every destination of the level with 1..32 in-edges.
+//    every destination of the level with >= 1 in-edges.  A destination with more than 32 in-edges (a
+//    recombination vertex of a panel with more than 32 walks) is cut into slice blocks of 32 lanes; each slice is
+//    reduced over the whole warp and the slices of one cell meet in a 64-bit shared-memory scratch word
+//    (atomic maximum of value+1 << 32 | ~code), which a second pass after a block barrier turns into the cell.
 //  * pair form: one thread per (destination pair, chunk of layers) looping over in(i') x in(j') — any shape,
 //    any placement of records and scores (the general fallback).
 struct TaskHdr {             // 128 bytes
@@ -90,7 +94,9 @@ struct TaskHdr {             // 128 bytes
     uint32_t n_witems;       //            warp items = nrg * nblk * chunks
     uint32_t rounds;         //            shuffle rounds of the segmented maximum = ceil(log2(longest group))
     uint32_t bstart_off;     //            byte offset of bstart[] inside the record
-    uint32_t pad[7];
+    uint32_t n_long;         //            destinations with more than 32 in-edges (TK_LONG), <= LANE_MAX_LONG
+    uint32_t long_off;       //            byte offset of long_j[] (their positions, u16) inside the record
+    uint32_t pad[5];
 };
 static_assert(sizeof(TaskHdr) == 128, "TaskHdr layout");
 
@@ -126,12 +132,16 @@ struct TransitionT {
 };
 
 // record = in_off2 u16[k2+1] | pad16 | in_edge u32[n_in] | pad16 | in_dst u16[n_in] | pad16 | bstart u16[nblk+1] | pad16
+//          | long_j u16[n_long] | pad16
 // (16-byte aligned, self-contained; in_dst = destination position of every in-edge, bstart = first in-edge of
-// every lane-form block, bstart[nblk] = n_in)
+// every lane-form block, bstart[nblk] = n_in, long_j = destinations with more than 32 in-edges)
 DG_HD size_t rec_edge_offset(int k2) { return (((size_t)k2 + 1) * 2 + 15) & ~(size_t)15; }
 DG_HD size_t rec_dst_offset(int k2, int64_t n_in) { return rec_edge_offset(k2) + (((size_t)n_in * 4 + 15) & ~(size_t)15); }
 DG_HD size_t rec_bstart_offset(int k2, int64_t n_in) { return rec_dst_offset(k2, n_in) + (((size_t)n_in * 2 + 15) & ~(size_t)15); }
-DG_HD size_t rec_bytes_for(int k2, int64_t n_in, int nblk) { return rec_bstart_offset(k2, n_in) + ((((size_t)nblk + 1) * 2 + 15) & ~(size_t)15); }
+DG_HD size_t rec_long_offset(int k2, int64_t n_in, int nblk) { return rec_bstart_offset(k2, n_in) + ((((size_t)nblk + 1) * 2 + 15) & ~(size_t)15); }
+DG_HD size_t rec_bytes_for(int k2, int64_t n_in, int nblk, int n_long) { return rec_long_offset(k2, n_in, nblk) + (((size_t)n_long * 2 + 15) & ~(size_t)15); }
+constexpr int LANE_MAX_LONG = 16;            // long destinations per level the lane form accepts
+constexpr int LANE_SCRATCH_ENTRIES = 1024;   // 64-bit scratch words per CTA: rows x long destinations x layers of a task
 
 // delta = |(Hom u1 ∪ Hom v1) ∩ (Hom u2 ∪ Hom v2)| + |(Het u1 ∪ Het v1) △ (Het u2 ∪ Het v2)|
 // (approximator.cpp:614-619).  `het_only` returns just the second term (dp_entry::s_het, :662).

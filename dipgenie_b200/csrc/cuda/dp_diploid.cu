@@ -46,7 +46,8 @@ constexpr int DIP_THREADS = DIP_CT + 32;       // + one producer warp (task pref
 constexpr int DIP_NSLOT = 16;                  // task ring depth
 constexpr int DIP_SLOT_BYTES = 4096;
 constexpr int DIP_TILE_CELLS = 16384;          // int32 cells per shared-memory layer tile (x2)
-constexpr size_t DIP_SMEM_BYTES = (size_t)DIP_NSLOT * DIP_SLOT_BYTES + 2 * (size_t)DIP_TILE_CELLS * 4 + 2 * DIP_NSLOT * 8;
+constexpr size_t DIP_SMEM_BYTES = (size_t)DIP_NSLOT * DIP_SLOT_BYTES + 2 * (size_t)DIP_TILE_CELLS * 4 + 2 * DIP_NSLOT * 8 +
+                                  (size_t)LANE_SCRATCH_ENTRIES * 8;
 constexpr int DIP_TRACE_T = 128;               // levels between traceback checkpoints
 
 struct SweepArgs {
@@ -258,14 +259,51 @@ struct LaneTask {
     int32_t* gdst;
     uint8_t* pl;
     uint32_t k, k2, i0, i1, n_in, rec_bytes, skew, nblk, rp, nrg, m_nblk, m_nrg, m_nin, n_witems, rounds, bstart_off;
+    uint32_t n_long, long_off;       // TK_LONG: destinations with more than 32 in-edges, their positions in the record
+    unsigned long long* scratch;     //          64-bit combine words [(row - i0) * n_long + g][layer]
+    const uint16_t* gdelta;          // pair-score matrix of the transition in global memory when its rows are not staged (else null)
     bool staged;
 };
 
 struct LaneProf { unsigned long long items, setup, loop, reduce, store, iters; };
 
+// The lane-form view of the task staged in slot `sb32` (header words as laid out in dp_cell.h: TaskHdr).
+template <bool PRED32>
+__device__ __forceinline__ void fill_lane_task(const SweepArgs& a, uint32_t sb32, uint32_t tiles32, unsigned long long* scratch, LaneTask& lt) {
+    const uint4 h0 = lds_v4(sb32), h1 = lds_v4(sb32 + 16u), h2 = lds_v4(sb32 + 32u), h3 = lds_v4(sb32 + 48u), h4 = lds_v4(sb32 + 64u),
+                h5 = lds_v4(sb32 + 80u);
+    const uint32_t flags = h1.y;
+    const int l = (int)h1.x;
+    lt.sb32 = sb32;
+    const uint32_t odd = (uint32_t)l & 1u;
+    lt.src32 = tiles32 + odd * ((uint32_t)DIP_TILE_CELLS * 4u);
+    lt.dst32 = tiles32 + (odd ^ 1u) * ((uint32_t)DIP_TILE_CELLS * 4u);
+    lt.gsrc = odd ? a.tile1 : a.tile0;
+    lt.gdst = odd ? a.tile0 : a.tile1;
+    const unsigned long long pred_off2 = ((unsigned long long)h3.y << 32) | h3.x;
+    lt.pl = reinterpret_cast<uint8_t*>(a.pred) + ((size_t)pred_off2 << (PRED32 ? 2 : 1));
+    lt.k = h2.x & 0xFFFFu; lt.k2 = h2.x >> 16; lt.i0 = h2.y & 0xFFFFu; lt.i1 = h2.y >> 16; lt.n_in = h2.z;
+    lt.rec_bytes = h0.y; lt.skew = h1.w;
+    lt.nblk = h4.y & 0xFFFFu; lt.rp = h4.y >> 16; lt.nrg = h4.z; lt.m_nblk = h4.w;
+    lt.m_nrg = h5.x; lt.m_nin = h5.y; lt.n_witems = h5.z; lt.rounds = h5.w;
+    lt.bstart_off = lds_u32(sb32 + 96u);
+    lt.n_long = 0; lt.long_off = 0; lt.scratch = scratch;
+    if (flags & TK_LONG) { lt.n_long = lds_u32(sb32 + 100u); lt.long_off = lds_u32(sb32 + 104u); }
+    lt.staged = (flags & TK_DELTA_STAGED) != 0;
+    lt.gdelta = ((flags & TK_DELTA) && !lt.staged) ? a.delta + __ldg(a.delta_off + l) : nullptr;
+}
+
+// Unpacked arithmetic (value and code in separate registers): problems whose DP values may exceed the packed key
+// (shift == 0) and, with shift == KEY_SHIFT, the tasks of levels that have destinations with more than 32 in-edges
+// (TK_LONG: slice blocks are reduced over the whole warp and meet in the scratch words).  Out of line: the packed
+// loop keeps its own register allocation.
 template <int RC, bool SMEM, bool CHECK, bool PRED32, bool PROF>
-__device__ __forceinline__ void lane_task(const LaneTask& t, int R, int warp, int lane,
-                                          unsigned long long& hsum, unsigned long long& hlive, LaneProf& lp) {
+__device__ __noinline__ ulonglong2 lane_task(const SweepArgs& a, uint32_t sb32, uint32_t tiles32, unsigned long long* scratch, int warp, int lane) {
+    unsigned long long hsum = 0, hlive = 0;
+    LaneProf lp = {0, 0, 0, 0, 0, 0};
+    LaneTask t;
+    fill_lane_task<PRED32>(a, sb32, tiles32, scratch, t);
+    const int R = a.R, shift = a.shift;
     const uint32_t off32 = t.sb32 + (uint32_t)sizeof(TaskHdr);
     const uint32_t edge32 = off32 + (uint32_t)rec_edge_offset((int)t.k2);
     const uint32_t dstp32 = off32 + (uint32_t)rec_dst_offset((int)t.k2, t.n_in);
@@ -313,6 +351,8 @@ __device__ __forceinline__ void lane_task(const LaneTask& t, int R, int warp, in
             const int w = (int)(x >> 16) + wv;
             int d = 0;
             if (t.staged) d = (int)lds_u16(delta32 + 2u * (e1 * n_in + e2c));
+            else if (t.gdelta) d = (int)__ldg(t.gdelta + ((size_t)e1 * n_in + e2c));
+            d <<= shift;
             const uint32_t cd = ((e1 - a0) << 16) | pos;
             // loads in batches of LB independent accesses (layer index clamped into [0,R]; validity gates the compare)
             constexpr int LB = (RC % 10 == 0) ? 10 : ((RC % 8 == 0) ? 8 : RC);
@@ -336,9 +376,12 @@ __device__ __forceinline__ void lane_task(const LaneTask& t, int R, int warp, in
             }
         }
         if (PROF) c2 = clock64();
-        // segmented maximum over the lanes of one destination column: value desc, then code asc
-        for (uint32_t rd = 0, off = 1; rd < t.rounds; ++rd, off <<= 1) {
-            const bool partner = pos + off < seg;
+        // segmented maximum over the lanes of one destination column: value desc, then code asc; a slice block (one
+        // destination with more than 32 in-edges) is reduced over all its lanes
+        const bool slice = t.n_long && __any_sync(0xFFFFFFFFu, valid && seg > 32u);
+        const uint32_t nrd = slice ? 5u : t.rounds;
+        for (uint32_t rd = 0, off = 1; rd < nrd; ++rd, off <<= 1) {
+            const bool partner = slice ? (valid && el + off < be - bs) : (pos + off < seg);
 #pragma unroll
             for (int rr = 0; rr < RC; ++rr) {
                 const int32_t ob = __shfl_down_sync(0xFFFFFFFFu, best[rr], off);
@@ -347,7 +390,17 @@ __device__ __forceinline__ void lane_task(const LaneTask& t, int R, int warp, in
             }
         }
         if (PROF) c3 = clock64();
-        if (valid && pos == 0) {
+        if (slice) {
+            if (valid && el == 0) {              // the slice's partial maxima meet the other slices in the scratch words
+                uint32_t g = 0;
+                while (g + 1 < t.n_long && lds_u16(off32 + t.long_off + 2u * g) != j2) ++g;
+                unsigned long long* sc = t.scratch + ((size_t)(row - t.i0) * t.n_long + g) * (uint32_t)(R + 1);
+#pragma unroll
+                for (int rr = 0; rr < RC; ++rr)
+                    if (r0 + rr <= R && best[rr] >= 0)
+                        atomicMax(sc + (r0 + rr), ((unsigned long long)((uint32_t)best[rr] + 1u) << 32) | (unsigned long long)(0xFFFFFFFFu - code[rr]));
+            }
+        } else if (valid && pos == 0) {
             const uint32_t cell0 = row * k2 + j2;
 #pragma unroll
             for (int rr = 0; rr < RC; ++rr) {
@@ -364,13 +417,14 @@ __device__ __forceinline__ void lane_task(const LaneTask& t, int R, int warp, in
                         const int pi = (int)(lds_u32(edge32 + 4u * (a0 + (code[rr] >> 16))) & 0xFFFFu);
                         const int pj = (int)(lds_u32(edge32 + 4u * (s0 + (code[rr] & 0xFFFFu))) & 0xFFFFu);
                         ++hlive;
-                        hsum += cell_fold((uint64_t)c, val, pi, pj);
+                        hsum += cell_fold((uint64_t)c, val >> shift, pi, pj);
                     }
                 }
             }
         }
         if (PROF) { const long long c4 = clock64(); lp.items += 1; lp.setup += c1 - c0; lp.loop += c2 - c1; lp.reduce += c3 - c2; lp.store += c4 - c3; }
     }
+    return make_ulonglong2(hsum, hlive);
 }
 
 // The same with packed keys (dp_cell.h): one word per layer, one add + one max per candidate layer, one shuffle
@@ -442,6 +496,7 @@ __device__ __forceinline__ void lane_task_packed(const LaneTask& t, int R, int w
             const int w = (int)(x >> 16) + wv;
             uint32_t dp = ordbits;
             if (t.staged) dp += lds_u16(delta32 + 2u * (e1 * n_in + e2c)) << KEY_SHIFT;
+            else if (t.gdelta) dp += (uint32_t)__ldg(t.gdelta + ((size_t)e1 * n_in + e2c)) << KEY_SHIFT;
             int32_t v[RC];
             if (!edge_chunk) {
                 if (SMEM) {
@@ -509,6 +564,40 @@ __device__ __forceinline__ void lane_task_packed(const LaneTask& t, int R, int w
     }
 }
 
+// Second pass of a TK_LONG task: every scratch word (row, long destination, layer) becomes its cell.
+template <bool CHECK, bool PRED32>
+__device__ __noinline__ ulonglong2 long_finalize(const SweepArgs& a, uint32_t sb32, uint32_t tiles32, unsigned long long* scratch, bool smem_layers, int tid) {
+    unsigned long long hsum = 0, hlive = 0;
+    LaneTask t;
+    fill_lane_task<PRED32>(a, sb32, tiles32, scratch, t);
+    const int R = a.R;
+    const uint32_t RP1 = (uint32_t)R + 1u, G = t.n_long;
+    const uint32_t total = (t.i1 - t.i0) * G * RP1;
+    const uint32_t off32 = t.sb32 + (uint32_t)sizeof(TaskHdr);
+    const uint32_t edge32 = off32 + (uint32_t)rec_edge_offset((int)t.k2);
+    const uint32_t kk2 = t.k2 * t.k2;
+    for (uint32_t idx = (uint32_t)tid; idx < total; idx += DIP_CT) {
+        const unsigned long long K = t.scratch[idx];
+        const uint32_t q = idx / RP1, r2 = idx - q * RP1, rowrel = q / G, g = q - rowrel * G;
+        const uint32_t row = t.i0 + rowrel, j2 = lds_u16(off32 + t.long_off + 2u * g);
+        const bool live = K != 0ull;
+        const int32_t val = live ? (int32_t)((uint32_t)(K >> 32) - 1u) : NEG_INF;
+        const uint32_t code = live ? 0xFFFFFFFFu - (uint32_t)K : 0xFFFFFFFFu;
+        const size_t c = (size_t)r2 * kk2 + (size_t)row * t.k2 + j2;
+        if (smem_layers) sts_s32(t.dst32 + 4u * (uint32_t)c, val); else __stcg(t.gdst + c, val);
+        if (PRED32) reinterpret_cast<uint32_t*>(t.pl)[c] = code;
+        else reinterpret_cast<uint16_t*>(t.pl)[c] = (uint16_t)(((code >> 16) << 8) | (code & 0xFFu));   // dead: 0xFFFF
+        if (CHECK && live) {
+            const uint32_t a0 = lds_u16(off32 + 2u * row), s0 = lds_u16(off32 + 2u * j2);
+            const int pi = (int)(lds_u32(edge32 + 4u * (a0 + (code >> 16))) & 0xFFFFu);
+            const int pj = (int)(lds_u32(edge32 + 4u * (s0 + (code & 0xFFFFu))) & 0xFFFFu);
+            ++hlive;
+            hsum += cell_fold((uint64_t)c, val >> KEY_SHIFT, pi, pj);
+        }
+    }
+    return make_ulonglong2(hsum, hlive);
+}
+
 // The pair form (everything the lane form does not take): layers in HBM/L2 (or a hand-over between the two placements),
 // records staged or read in place, pair scores staged / in place / popcounted on the fly.  Kept out of line
 // so that the narrow loop gets its own register allocation and stays small.
@@ -568,6 +657,7 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
     int32_t* const tileS1 = tileS0 + DIP_TILE_CELLS;
     uint64_t* const full = reinterpret_cast<uint64_t*>(tileS1 + DIP_TILE_CELLS);
     uint64_t* const empty = full + DIP_NSLOT;
+    unsigned long long* const scratch = reinterpret_cast<unsigned long long*>(empty + DIP_NSLOT);   // TK_LONG tasks
 
     const int cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int32_t n = (int32_t)(a.task_begin[cta + 1] - a.task_begin[cta]);
@@ -633,26 +723,20 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
         if (profiling) tk2 = clock64();
         unsigned long long hsum = 0, hlive = 0;
         const bool ssm = (flags & TK_SRC_SMEM) != 0, dsm = (flags & TK_DST_SMEM) != 0;
+        const bool is_long = (flags & TK_LONG) != 0;
+        if (is_long) {                               // slices of a long destination meet in the scratch words: zero them
+            const uint32_t rows = (h2.y >> 16) - (h2.y & 0xFFFFu);
+            const uint32_t total = rows * lds_u32(sb32 + 100u) * ((uint32_t)a.R + 1u);
+            for (uint32_t x = (uint32_t)tid; x < total; x += DIP_CT) scratch[x] = 0ull;
+            bar_compute();
+        }
         if ((uint32_t)(tid & ~31) < h2.w) {          // this warp owns work of the task
             if (flags & TK_LANES) {
-                const uint4 h0 = lds_v4(sb32), h3 = lds_v4(sb32 + 48u), h4 = lds_v4(sb32 + 64u), h5 = lds_v4(sb32 + 80u);
-                LaneTask lt;
-                lt.sb32 = sb32;
-                const uint32_t odd = (uint32_t)l & 1u;
-                lt.src32 = tiles32 + odd * ((uint32_t)DIP_TILE_CELLS * 4u);
-                lt.dst32 = tiles32 + (odd ^ 1u) * ((uint32_t)DIP_TILE_CELLS * 4u);
-                lt.gsrc = odd ? a.tile1 : a.tile0;
-                lt.gdst = odd ? a.tile0 : a.tile1;
-                const unsigned long long pred_off2 = ((unsigned long long)h3.y << 32) | h3.x;
-                lt.pl = pred + ((size_t)pred_off2 << pshift);
-                lt.k = h2.x & 0xFFFFu; lt.k2 = h2.x >> 16; lt.i0 = h2.y & 0xFFFFu; lt.i1 = h2.y >> 16; lt.n_in = h2.z;
-                lt.rec_bytes = h0.y; lt.skew = h1.w;
-                lt.nblk = h4.y & 0xFFFFu; lt.rp = h4.y >> 16; lt.nrg = h4.z; lt.m_nblk = h4.w;
-                lt.m_nrg = h5.x; lt.m_nin = h5.y; lt.n_witems = h5.z; lt.rounds = h5.w;
-                lt.bstart_off = lds_u32(sb32 + 96u);
-                lt.staged = (flags & TK_DELTA_STAGED) != 0;
-                if (a.shift) {
-                    const bool big = (h4.x & 0xFFFFu) == (uint32_t)LANE_RC_BIG;
+                if (a.shift && !is_long) {
+                    LaneTask lt;
+                    fill_lane_task<PRED32>(a, sb32, tiles32, scratch, lt);
+                    const uint32_t rc = lds_u32(sb32 + 64u) & 0xFFFFu;
+                    const bool big = rc == (uint32_t)LANE_RC_BIG;
                     if (ssm) {
                         if (big) lane_task_packed<LANE_RC_BIG, true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
                         else lane_task_packed<LANE_RC_SMALL, true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
@@ -661,13 +745,19 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
                         else lane_task_packed<LANE_RC_SMALL, false, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
                     }
                 } else {
-                    if (ssm) lane_task<LANE_RC_SMALL, true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
-                    else lane_task<LANE_RC_SMALL, false, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
+                    const ulonglong2 hs = ssm ? lane_task<LANE_RC_SMALL, true, CHECK, PRED32, false>(a, sb32, tiles32, scratch, warp, lane)
+                                              : lane_task<LANE_RC_SMALL, false, CHECK, PRED32, false>(a, sb32, tiles32, scratch, warp, lane);
+                    hsum = hs.x; hlive = hs.y;
                 }
             } else {
                 const ulonglong2 hs = generic_task<CHECK, PRED32>(a, sb, tileS0, tileS1, tid);
                 hsum = hs.x; hlive = hs.y;
             }
+        }
+        if (is_long) {                               // second pass: every scratch word becomes its cell
+            bar_compute();
+            const ulonglong2 hs = long_finalize<CHECK, PRED32>(a, sb32, tiles32, scratch, ssm, tid);
+            hsum += hs.x; hlive += hs.y;
         }
         if (profiling) tk3 = clock64();
         __syncwarp();
@@ -892,6 +982,7 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
     shape.delta_budget = lim.delta_budget;
     shape.lane_rc = (d->shift != 0 && p.R + 1 >= LANE_RC_BIG) ? LANE_RC_BIG : LANE_RC_SMALL;
     d->lane_rc = shape.lane_rc;
+    shape.allow_long = d->shift != 0 && !getenv("DG_NO_LONG");     // slice blocks live in the packed-key kernel
     plan_tasks(p, shape);
     d->grid = 1;
     for (int c = 0; c < p.grid; ++c) if (p.task_begin[(size_t)c + 1] > p.task_begin[c]) d->grid = c + 1;

@@ -174,27 +174,41 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
 
 namespace {
 
-// Lane-form blocks of level l+1: starts of the <= 32-wide in-edge blocks (never cutting a destination's group)
-// followed by n_in.  Returns the number of blocks, 0 when the level cannot use the lane form (a destination
-// with no or with more than 32 in-edges).  `out` may be null (count only); *rounds = ceil(log2(longest group)).
-int lane_blocks(const DipPlan& p, int l, uint16_t* out, int* rounds) {
+// Lane-form blocks of level l+1: starts of the <= 32-wide in-edge blocks followed by n_in.  A block never cuts
+// the group of a destination with <= 32 in-edges; a destination with more (allowed only with `allow_long`, at
+// most LANE_MAX_LONG per level) is cut into slice blocks of its own.  Returns the number of blocks, 0 when the
+// level cannot use the lane form.  `out` / `long_j` may be null (count only); *rounds = ceil(log2(longest group
+// of <= 32)), *n_long = destinations with more than 32 in-edges.
+int lane_blocks(const DipPlan& p, int l, bool allow_long, uint16_t* out, uint16_t* long_j, int* rounds, int* n_long) {
     const int32_t mid = p.level_off[l + 1], k2 = p.level_off[l + 2] - mid;
     const int32_t e0 = p.in_off[mid];
     const int64_t n_in = (int64_t)p.in_off[mid + k2] - e0;
+    if (n_long) *n_long = 0;
     if (n_in <= 0 || n_in >= 65536) return 0;
     int32_t longest = 0, start = 0;
-    int nb = 0;
+    int nb = 0, nl = 0;
     if (out) out[0] = 0;
+    auto cut = [&](int32_t at) {                 // a block boundary at in-edge `at` (ignored if the open block is empty)
+        if (at > start) { ++nb; if (out) out[nb] = (uint16_t)at; start = at; }
+    };
     for (int32_t x = 0; x < k2; ++x) {
-        const int32_t deg = p.in_off[mid + x + 1] - p.in_off[mid + x];
-        if (deg < 1 || deg > 32) return 0;
+        const int32_t gs = p.in_off[mid + x] - e0, ge = p.in_off[mid + x + 1] - e0, deg = ge - gs;
+        if (deg < 1) return 0;
+        if (deg > 32) {
+            if (!allow_long || nl >= LANE_MAX_LONG) return 0;
+            if (long_j) long_j[nl] = (uint16_t)x;
+            ++nl;
+            cut(gs);
+            for (int32_t at = gs + 32; at < ge; at += 32) cut(at);
+            cut(ge);
+            continue;
+        }
         longest = std::max(longest, deg);
-        const int32_t end = p.in_off[mid + x + 1] - e0;      // in-edges up to and including destination x
-        if (end - start > 32) { start = p.in_off[mid + x] - e0; ++nb; if (out) out[nb] = (uint16_t)start; }
+        if (ge - start > 32) cut(gs);
     }
-    ++nb;
-    if (out) out[nb] = (uint16_t)n_in;
+    if (start < n_in) { ++nb; if (out) out[nb] = (uint16_t)n_in; }
     if (rounds) { int r = 0; while ((1 << r) < longest) ++r; *rounds = r; }
+    if (n_long) *n_long = nl;
     return nb;
 }
 
@@ -241,15 +255,17 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
 
     // ---- 1. lane-form blocks, record sizes, pair-score matrix layout, placement of the layers ----
     std::vector<int32_t> nblk(T, 0);
-    std::vector<uint8_t> rec_staged(T, 0), seg_rounds(T, 0);
+    std::vector<uint8_t> rec_staged(T, 0), seg_rounds(T, 0), nlong(T, 0);
     std::vector<uint32_t> rec_bytes(T, 0);
 #pragma omp parallel for schedule(static) num_threads(NT)
     for (int l = 0; l < T; ++l) {
-        int rounds = 0;
-        nblk[l] = lane_blocks(p, l, nullptr, &rounds);
+        int rounds = 0, nl = 0;
+        nblk[l] = lane_blocks(p, l, sh.allow_long, nullptr, nullptr, &rounds, &nl);
+        if (nblk[l] > 0 && nl > 0 && nl * (p.R + 1) > LANE_SCRATCH_ENTRIES) { nblk[l] = 0; nl = 0; }     // not even one row fits the scratch
         seg_rounds[l] = (uint8_t)rounds;
+        nlong[l] = (uint8_t)(nblk[l] > 0 ? nl : 0);
         const int64_t n_in = nin_of(l);
-        const size_t rb = rec_bytes_for(width(l + 1), n_in, nblk[l]);
+        const size_t rb = rec_bytes_for(width(l + 1), n_in, nblk[l], nlong[l]);
         rec_staged[l] = (sizeof(TaskHdr) + rb <= slot && n_in < 65536) ? 1 : 0;
         rec_bytes[l] = rec_staged[l] ? (uint32_t)rb : 0u;
     }
@@ -280,7 +296,9 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
             memcpy(r + rec_edge_offset(k2), &p.in_edge[e0], (size_t)(e1 - e0) * 4);
             memcpy(r + rec_dst_offset(k2, e1 - e0), &p.in_dst[e0], (size_t)(e1 - e0) * 2);
         }
-        if (nblk[l] > 0) lane_blocks(p, l, reinterpret_cast<uint16_t*>(r + rec_bstart_offset(k2, e1 - e0)), nullptr);
+        if (nblk[l] > 0)
+            lane_blocks(p, l, sh.allow_long, reinterpret_cast<uint16_t*>(r + rec_bstart_offset(k2, e1 - e0)),
+                        reinterpret_cast<uint16_t*>(r + rec_long_offset(k2, e1 - e0, nblk[l])), nullptr, nullptr);
     }
 
     // ---- 2. participants: narrow -> CTA 0 alone; wide -> P = min(G, k2) CTAs ----
@@ -355,6 +373,8 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
                     h.flags = base_flags;
                     h.pred_off2 = p.pred_off[l + 1];
                     int32_t y = std::min(rbnd, x + max_rows);
+                    if (nlong[l] > 0)          // rows x long destinations x layers of a task share the CTA's scratch words
+                        y = std::min(y, x + std::max(1, LANE_SCRATCH_ENTRIES / ((int)nlong[l] * (p.R + 1))));
                     if (rec_staged[l]) {
                         h.rec_off16 = (uint32_t)(p.rec_off[l] / 16);
                         h.rec_bytes = (uint32_t)rb;
@@ -396,8 +416,9 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
                     h.rc = (uint16_t)rc;
                     h.groups = (uint16_t)(npairs >= CT ? 1u : std::max(1u, std::min(nchunk, CT / npairs)));
                     h.n_active = std::min<uint32_t>(CT, (uint32_t)h.groups * npairs);
-                    // lane form: record staged, level eligible, pair scores absent or staged for exactly these rows
-                    const bool scores_ok = !(base_flags & (TK_DELTA | TK_DELTA_MASKS)) || (h.flags & TK_DELTA_STAGED);
+                    // lane form: record staged, level eligible, pair scores absent or in a matrix (staged rows or in place)
+                    // (a matrix whose rows do not fit the slot is read in place from HBM/L2: wide levels, long rows)
+                    const bool scores_ok = !(base_flags & TK_DELTA_MASKS);
                     const uint32_t lchunks = (uint32_t)(p.R + lrc) / (uint32_t)lrc;
                     const uint64_t witems = (uint64_t)(y - x) * (uint64_t)std::max(nblk[l], 1) * lchunks;   // upper bound (rp >= 1)
                     if (rec_staged[l] && nblk[l] > 0 && scores_ok && same_place && CT % 32 == 0 &&
@@ -409,10 +430,17 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
                         h.m_nblk = make_magic((uint32_t)nblk[l]);
                         h.m_nrg = make_magic(h.nrg);
                         h.m_nin = make_magic((uint32_t)n_in);
-                        h.rc = (uint16_t)lrc;
-                        h.n_witems = h.nrg * (uint32_t)nblk[l] * lchunks;
+                        // (levels with long destinations run the unpacked lane task, which is compiled for LANE_RC_SMALL)
+                        const int trc = nlong[l] > 0 ? LANE_RC_SMALL : lrc;
+                        h.rc = (uint16_t)trc;
+                        h.n_witems = h.nrg * (uint32_t)nblk[l] * ((uint32_t)(p.R + trc) / (uint32_t)trc);
                         h.rounds = seg_rounds[l];
                         h.bstart_off = (uint32_t)rec_bstart_offset(k2, n_in);
+                        if (nlong[l] > 0) {
+                            h.flags |= TK_LONG;
+                            h.n_long = nlong[l];
+                            h.long_off = (uint32_t)rec_long_offset(k2, n_in, nblk[l]);
+                        }
                         h.n_active = std::min<uint32_t>(CT, 32u * h.n_witems);
                     }
                     if (first && l > 0 && p.bar_edge[l - 1]) { h.flags |= TK_WAIT; h.wait_target = p.bar_target[l - 1]; }

@@ -49,6 +49,7 @@ struct SweepShape {              // kernel geometry the plan is made for
     int64_t delta_budget = (int64_t)8 << 30;   // bytes of pair-score matrices to materialise at most
     int delta_max_in = 4096;     // widest in-edge count that still gets a matrix
     int lane_rc = LANE_RC_SMALL; // layers per lane in the lane form (LANE_RC_SMALL or LANE_RC_BIG)
+    bool allow_long = false;     // lane form may take destinations with more than 32 in-edges (needs packed keys' kernel)
 };
 
 struct DipPlan {

@@ -57,13 +57,13 @@ class DpEmu:
         self.lib = C.CDLL(_build_emu())
 
     def dp_diploid(self, g, R, force_pred32=False, shape=None):
-        """shape = (grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, no_pack) of the emulated kernel geometry
+        """shape = (grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, no_pack, no_long) of the emulated kernel geometry
         (0 = default; delta_max_in < 0 forces the on-the-fly mask path)."""
         L = g.n_levels
-        shp = np.zeros(7, np.int32)
+        shp = np.zeros(8, np.int32)
         if shape:
             shp[: len(shape)] = list(shape)
-        counts = np.zeros(7, np.int64)
+        counts = np.zeros(8, np.int64)
         val, sh, n1, n2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         p1 = np.zeros(2 * (R + 2), np.int32)
         p2 = np.zeros(2 * (R + 2), np.int32)
@@ -80,7 +80,7 @@ class DpEmu:
                     p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy(), checksum=cs, live=lv,
                     modes=dict(narrow=int(counts[0]), wide=int(counts[1]), tasks=int(counts[2]),
                                tasks_global=int(counts[3]), tasks_masks=int(counts[4]), matrices=int(counts[5]),
-                               tasks_lanes=int(counts[6])))
+                               tasks_lanes=int(counts[6]), tasks_long=int(counts[7])))
 
 
 @pytest.fixture(scope="session")

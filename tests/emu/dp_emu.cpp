@@ -26,6 +26,7 @@ struct Emu {
     std::vector<uint64_t> sum, live;
     bool bad_rc = false;
     int shift = 0;                     // layers hold value << shift (packed keys)
+    std::vector<uint64_t> scratch;     // TK_LONG combine words
     int64_t n_lane_tasks = 0;
     std::vector<uint8_t> written;      // cells of the current destination level stored so far (lane form: exactly once)
     Emu(const DipPlan& pp, const SweepShape& s) : p(pp), sh(s) {}
@@ -84,7 +85,8 @@ void by_dm(Emu& e, const TransitionT<OffT>& t, const TaskHdr& h, const int32_t* 
     else by_rc<PredT, OffT, false>(e, t, h, src, dst, pl);
 }
 
-// the lane form (dp_diploid.cu: lane_task), warp by warp, the 32 lanes emulated in lock-step arrays
+// the lane form (dp_diploid.cu: lane_task / lane_task_packed / long_finalize), warp by warp, the 32 lanes emulated
+// in lock-step arrays
 template <class PredT, int RC>
 int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src, int32_t* dst, PredT* pl) {
     constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
@@ -98,13 +100,37 @@ int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src
     const uint16_t* bstart = reinterpret_cast<const uint16_t*>(rec + h.bstart_off);
     const bool staged = (h.flags & TK_DELTA_STAGED) != 0;
     const bool packed = e.shift != 0;
+    const bool is_long = (h.flags & TK_LONG) != 0;
+    const uint16_t* long_j = nullptr;
     if (packed && e.shift != KEY_SHIFT) return -63;
-    if ((h.flags & (TK_DELTA | TK_DELTA_MASKS)) && !staged) return -51;
-    const uint16_t* delta = staged ? reinterpret_cast<const uint16_t*>(rec + h.rec_bytes) + h.delta_skew - (size_t)in_off[h.i0] * h.n_in : nullptr;
+    if (is_long) {
+        if (!packed || h.n_long < 1 || h.n_long > (uint32_t)LANE_MAX_LONG || h.long_off != rec_long_offset(h.k2, h.n_in, h.nblk) ||
+            h.long_off + 2u * h.n_long > h.rec_bytes) return -64;
+        if ((uint64_t)(h.i1 - h.i0) * h.n_long * (uint64_t)(R + 1) > (uint64_t)LANE_SCRATCH_ENTRIES) return -65;
+        long_j = reinterpret_cast<const uint16_t*>(rec + h.long_off);
+        e.scratch.assign((size_t)(h.i1 - h.i0) * h.n_long * (size_t)(R + 1), 0);       // zeroed by all threads + barrier
+    } else if (h.n_long) return -64;
+    if (h.flags & TK_DELTA_MASKS) return -51;
+    const bool has_delta = staged || (h.flags & TK_DELTA);
+    const uint16_t* delta = staged ? reinterpret_cast<const uint16_t*>(rec + h.rec_bytes) + h.delta_skew - (size_t)in_off[h.i0] * h.n_in
+                                   : ((h.flags & TK_DELTA) ? e.delta.data() + e.p.delta_off[h.level] : nullptr);     // in place
     const uint32_t k = h.k, k2 = h.k2, n_in = h.n_in, kk = k * k, kk2 = k2 * k2;
     const uint32_t nchunk = (uint32_t)(R + RC) / RC;
     if (h.n_witems != h.nrg * h.nblk * nchunk || h.nblk < 1 || h.rp < 1 || (h.nblk > 1 && h.rp != 1)) return -52;
     if ((uint64_t)h.nrg * h.rp < (uint64_t)(h.i1 - h.i0) || bstart[0] != 0 || bstart[h.nblk] != n_in) return -53;
+    auto store_cell = [&](uint64_t c, bool lv, int32_t val, uint32_t cd, uint32_t a0, uint32_t s0) -> int {
+        if (e.written[c]) return -59;
+        e.written[c] = 1;
+        dst[c] = lv ? val : NEG_INF;
+        pl[c] = lv ? (PredT)(((cd >> 16) << SH) | (cd & 0xFFFFu)) : (PredT) ~(PredT)0;
+        if (lv) {
+            const int pi = (int)(in_edge[a0 + (cd >> 16)] & 0xFFFFu);
+            const int pj = (int)(in_edge[s0 + (cd & 0xFFFFu)] & 0xFFFFu);
+            ++e.live[h.level + 1];
+            e.sum[h.level + 1] += cell_fold(c, val >> e.shift, pi, pj);
+        }
+        return 0;
+    };
     for (uint32_t warp = 0; warp < NCW; ++warp)
         for (uint32_t wi = warp; wi < h.n_witems; wi += NCW) {
             const uint32_t q = h.m_nblk ? div_magic(wi, h.m_nblk) : wi, b = wi - q * h.nblk;
@@ -114,55 +140,68 @@ int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src
             if (be - bs > 32 || be <= bs) return -55;
             const int r0 = (int)chunk * RC;
             int32_t best[32][RC]; uint32_t code[32][RC];
-            bool valid[32]; uint32_t pos[32], seg[32], row[32], j2[32], a0[32], s0[32];
+            bool valid[32]; uint32_t pos[32], seg[32], row[32], j2[32], a0[32], a1[32], s0[32], el[32], e2c[32], jv[32]; int wv[32];
+            bool any_long = false, any_slice = false;
             for (uint32_t lane = 0; lane < 32; ++lane) {
-                uint32_t rs = 0, el = lane;
-                if (h.nblk == 1) { rs = h.m_nin ? div_magic(lane, h.m_nin) : lane; el = lane - rs * n_in; }
+                uint32_t rs = 0; el[lane] = lane;
+                if (h.nblk == 1) { rs = h.m_nin ? div_magic(lane, h.m_nin) : lane; el[lane] = lane - rs * n_in; }
                 row[lane] = h.i0 + rg * h.rp + rs;
-                const uint32_t e2 = bs + el;
+                const uint32_t e2 = bs + el[lane];
                 valid[lane] = rs < h.rp && row[lane] < h.i1 && e2 < be;
-                const uint32_t rowc = valid[lane] ? row[lane] : h.i0, e2c = valid[lane] ? e2 : bs;
+                const uint32_t rowc = valid[lane] ? row[lane] : h.i0;
+                e2c[lane] = valid[lane] ? e2 : bs;
                 a0[lane] = in_off[rowc];
-                const uint32_t a1 = valid[lane] ? in_off[rowc + 1] : a0[lane];
-                const uint32_t y = in_edge[e2c];
-                j2[lane] = in_dst[e2c];
+                a1[lane] = valid[lane] ? in_off[rowc + 1] : a0[lane];
+                const uint32_t y = in_edge[e2c[lane]];
+                j2[lane] = in_dst[e2c[lane]];
                 s0[lane] = in_off[j2[lane]];
-                pos[lane] = e2c - s0[lane]; seg[lane] = in_off[j2[lane] + 1] - s0[lane];
-                if (valid[lane] && (pos[lane] >= seg[lane] || s0[lane] < bs || s0[lane] + seg[lane] > be)) return -56;   // a block cut a group
-                const uint32_t j = y & 0xFFFFu; const int wv = (int)(y >> 16);
+                pos[lane] = e2c[lane] - s0[lane]; seg[lane] = in_off[j2[lane] + 1] - s0[lane];
+                if (valid[lane] && pos[lane] >= seg[lane]) return -56;
+                if (valid[lane] && seg[lane] <= 32 && (s0[lane] < bs || s0[lane] + seg[lane] > be)) return -56;   // a block cut a short group
+                if (valid[lane] && seg[lane] > 32 && (!is_long || s0[lane] > bs || s0[lane] + seg[lane] < be)) return -56;  // a slice holds one long group only
+                jv[lane] = y & 0xFFFFu; wv[lane] = (int)(y >> 16);
+                if (valid[lane] && (seg[lane] > 32 || a1[lane] - a0[lane] > 32)) any_long = true;
+                if (valid[lane] && seg[lane] > 32) any_slice = true;
+            }
+            const bool unp = is_long;                        // TK_LONG tasks run the unpacked lane task
+            if (any_long && !is_long) return -66;
+            const bool use_packed = packed && !unp;
+            for (uint32_t lane = 0; lane < 32; ++lane) {
                 for (int rr = 0; rr < RC; ++rr) { best[lane][rr] = -1; code[lane][rr] = 0xFFFFFFFFu; }
-                for (uint32_t e1 = a0[lane]; e1 < a1; ++e1) {
+                for (uint32_t e1 = a0[lane]; e1 < a1[lane]; ++e1) {
                     const uint32_t x = in_edge[e1];
-                    const uint32_t base = (x & 0xFFFFu) * k + j;
-                    const int w = (int)(x >> 16) + wv;
-                    const int d = staged ? (int)delta[(size_t)e1 * n_in + e2c] : 0;
+                    const uint32_t base = (x & 0xFFFFu) * k + jv[lane];
+                    const int w = (int)(x >> 16) + wv[lane];
+                    const int d = has_delta ? (int)delta[(size_t)e1 * n_in + e2c[lane]] : 0;
                     const uint32_t cd = ((e1 - a0[lane]) << 16) | pos[lane];
-                    if (packed && ((e1 - a0[lane]) > 31 || pos[lane] > 31)) return -62;
+                    if (use_packed && ((e1 - a0[lane]) > 31 || pos[lane] > 31)) return -62;
                     const int32_t dp = (int32_t)(((uint32_t)d << KEY_SHIFT) | ((31u - (e1 - a0[lane])) << KEY_ORD_BITS) | (31u - pos[lane]));
                     for (int rr = 0; rr < RC; ++rr) {
                         int r = r0 + rr - w;
                         const bool ok = r >= 0 && r0 + rr <= R;
                         r = r < 0 ? 0 : (r > R ? R : r);
                         const int32_t sv = src[(size_t)r * kk + base];
-                        if (packed) {                       // one word per layer: key = value << 10 | ordinals
+                        if (use_packed) {                       // one word per layer: key = value << 10 | ordinals
                             const int32_t key = ok ? sv + dp : -1;
                             if (key > best[lane][rr]) best[lane][rr] = key;
                         } else {
-                            const int32_t c = sv + d;
+                            const int32_t c = sv + (d << e.shift);
                             if (ok && c > best[lane][rr]) { best[lane][rr] = c; code[lane][rr] = cd; }
                         }
                     }
                 }
             }
-            for (uint32_t rd = 0, off = 1; rd < h.rounds; ++rd, off <<= 1) {
+            const uint32_t nrd = (unp && any_slice) ? 5u : h.rounds;
+            for (uint32_t rd = 0, off = 1; rd < nrd; ++rd, off <<= 1) {
                 int32_t nb[32][RC]; uint32_t nc[32][RC];
                 for (uint32_t lane = 0; lane < 32; ++lane)
                     for (int rr = 0; rr < RC; ++rr) {
                         const uint32_t o = lane + off < 32 ? lane + off : lane;      // __shfl_down_sync semantics
                         const int32_t ob = best[o][rr]; const uint32_t oc = code[o][rr];
                         nb[lane][rr] = best[lane][rr]; nc[lane][rr] = code[lane][rr];
-                        const bool take = packed ? (ob > best[lane][rr]) : (ob > best[lane][rr] || (ob == best[lane][rr] && oc < code[lane][rr]));
-                        if (pos[lane] + off < seg[lane] && take) {
+                        const bool partner = (unp && any_slice) ? (valid[lane] && el[lane] + off < be - bs) : (pos[lane] + off < seg[lane]);
+                        const bool take = use_packed ? (ob > best[lane][rr]) : (ob > best[lane][rr] || (ob == best[lane][rr] && oc < code[lane][rr]));
+                        if (partner && take) {
                             if (lane + off >= 32) return -57;
                             nb[lane][rr] = ob; nc[lane][rr] = oc;
                         }
@@ -170,33 +209,52 @@ int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src
                 memcpy(best, nb, sizeof best); memcpy(code, nc, sizeof code);
             }
             for (uint32_t lane = 0; lane < 32; ++lane) {
-                if (!valid[lane] || pos[lane] != 0) continue;
-                if ((1u << h.rounds) < seg[lane]) return -58;
+                if (!valid[lane]) continue;
+                if (unp && any_slice) {
+                    if (el[lane] != 0) continue;                 // the slice's leader: into the scratch words
+                    uint32_t g = 0;
+                    while (g + 1 < h.n_long && long_j[g] != j2[lane]) ++g;
+                    if (long_j[g] != j2[lane]) return -67;
+                    for (int rr = 0; rr < RC; ++rr) {
+                        const int r2 = r0 + rr;
+                        if (r2 > R || best[lane][rr] < 0) continue;
+                        uint64_t& w = e.scratch[((size_t)(row[lane] - h.i0) * h.n_long + g) * (size_t)(R + 1) + r2];
+                        const uint64_t K = ((uint64_t)((uint32_t)best[lane][rr] + 1u) << 32) | (uint64_t)(0xFFFFFFFFu - code[lane][rr]);
+                        if (K > w) w = K;
+                    }
+                    continue;
+                }
+                if (pos[lane] != 0) continue;
+                if (!unp && (1u << h.rounds) < seg[lane]) return -58;
                 for (int rr = 0; rr < RC; ++rr) {
                     const int r2 = r0 + rr;
                     if (r2 > R) continue;
                     const uint64_t c = (uint64_t)r2 * kk2 + (uint64_t)row[lane] * k2 + j2[lane];
                     const bool lv = best[lane][rr] >= 0;
-                    if (e.written[c]) return -59;
-                    e.written[c] = 1;
                     int32_t val = best[lane][rr];
                     uint32_t cd = code[lane][rr];
-                    if (packed && lv) {
+                    if (use_packed && lv) {
                         const uint32_t inv = ~(uint32_t)val & 1023u;
                         cd = ((inv >> KEY_ORD_BITS) << 16) | (inv & 31u);
                         val = (int32_t)((uint32_t)val & ~1023u);
                     }
-                    dst[c] = lv ? val : NEG_INF;
-                    pl[c] = lv ? (PredT)(((cd >> 16) << SH) | (cd & 0xFFFFu)) : (PredT) ~(PredT)0;
-                    if (lv) {
-                        const int pi = (int)(in_edge[a0[lane] + (cd >> 16)] & 0xFFFFu);
-                        const int pj = (int)(in_edge[s0[lane] + (cd & 0xFFFFu)] & 0xFFFFu);
-                        ++e.live[h.level + 1];
-                        e.sum[h.level + 1] += cell_fold(c, val >> e.shift, pi, pj);
-                    }
+                    if (int rcs = store_cell(c, lv, val, cd, a0[lane], s0[lane])) return rcs;
                 }
             }
         }
+    if (is_long) {                                               // long_finalize, after a block barrier
+        const uint32_t RP1 = (uint32_t)R + 1u, G = h.n_long;
+        for (uint32_t idx = 0; idx < (h.i1 - h.i0) * G * RP1; ++idx) {
+            const uint64_t K = e.scratch[idx];
+            const uint32_t q = idx / RP1, r2 = idx - q * RP1, rowrel = q / G, g = q - rowrel * G;
+            const uint32_t row = h.i0 + rowrel, j2 = long_j[g];
+            const bool lv = K != 0;
+            const int32_t val = lv ? (int32_t)((uint32_t)(K >> 32) - 1u) : NEG_INF;
+            const uint32_t cd = lv ? 0xFFFFFFFFu - (uint32_t)K : 0xFFFFFFFFu;
+            const uint64_t c = (uint64_t)r2 * kk2 + (uint64_t)row * k2 + j2;
+            if (int rcs = store_cell(c, lv, val, cd, in_off[row], in_off[j2])) return rcs;
+        }
+    }
     return 0;
 }
 
@@ -281,7 +339,7 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, bool no_pack, int64
                 for (int x = h.i0; x < h.i1; ++x) { if (row_done[x]) return -16; row_done[x] = 1; }
                 if (h.flags & TK_LANES) {
                     if ((h.flags & TK_REC_GLOBAL) || ssm != dsm) return -60;
-                    if (h.rc != e.sh.lane_rc) return -61;
+                    if (h.rc != ((h.flags & TK_LONG) ? LANE_RC_SMALL : e.sh.lane_rc)) return -61;
                     const int lrc = h.rc == LANE_RC_BIG ? lane_items<PredT, LANE_RC_BIG>(e, slot.data(), h, src, dst, pl)
                                                         : lane_items<PredT, LANE_RC_SMALL>(e, slot.data(), h, src, dst, pl);
                     if (lrc) return lrc;
@@ -386,9 +444,9 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, bool no_pack, int64
 
 }  // namespace
 
-// shape: [grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, no_pack] (0 = kernel default)
+// shape: [grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, no_pack, no_long] (0 = kernel default)
 // counts: [narrow transitions, wide transitions, tasks, tasks with in-place records, tasks with on-the-fly masks, matrices,
-//          tasks run in lane form]
+//          tasks run in lane form, TK_LONG tasks]
 extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
                               const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off,
                               const int32_t* col_val, const uint8_t* colour_is_hom, int32_t n_colours, int32_t R,
@@ -415,10 +473,13 @@ extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const 
         no_pack = shape[6] != 0;
     }
     sh.lane_rc = (p.value_bound < KEY_VALUE_LIMIT && !no_pack && R + 1 >= LANE_RC_BIG) ? LANE_RC_BIG : LANE_RC_SMALL;   // as dip_plan_host
+    sh.allow_long = (p.value_bound < KEY_VALUE_LIMIT && !no_pack) && !(shape && shape[7] != 0);
     plan_tasks(p, sh);
     if (counts) {
         counts[0] = p.n_narrow; counts[1] = p.n_wide; counts[2] = (int64_t)p.tasks.size();
         counts[3] = p.n_tasks_global; counts[4] = p.n_tasks_masks; counts[5] = (int64_t)p.delta_list.size();
+        counts[7] = 0;
+        for (const TaskHdr& t : p.tasks) if (t.flags & TK_LONG) ++counts[7];
     }
     if (p.max_indeg <= 255 && !force_pred32)
         return run<uint16_t>(p, sh, trace_T, no_pack, counts ? counts + 6 : nullptr, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);

@@ -135,7 +135,7 @@ def test_all_sweep_modes_agree(shape, oracle_mod, dp_emu):
     """Narrow (shared-memory layers) and wide (row-split over CTAs, layers in HBM) transitions, staged and
     in-place records, staged / in-place / on-the-fly pair scores, and every hand-over between them, give the
     same layers, and the checkpointed traceback gives the same lists for any checkpoint distance."""
-    seen = dict(narrow=0, wide=0, tasks=0, tasks_global=0, tasks_masks=0, matrices=0, tasks_lanes=0)
+    seen = dict(narrow=0, wide=0, tasks=0, tasks_global=0, tasks_masks=0, matrices=0, tasks_lanes=0, tasks_long=0)
     for seed in range(12):
         rng = np.random.default_rng(77 + seed)
         g = synth.random_level_graph(500 + seed, n_levels=int(rng.integers(3, 30)), max_width=int(rng.integers(2, 12)),
@@ -177,3 +177,64 @@ def test_ten_layers_per_lane_variant(R, oracle_mod, dp_emu):
         assert_dip_equal(oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R))
     g = synth.lane_panel_graph(5, n_lanes=10, n_blocks=6, rec_per_block=2, p_colour=0.3, n_colours=96)
     assert_dip_equal(oracle_dip(oracle_mod, g, R), dp_emu.dp_diploid(g, R))
+
+
+def funnel_graph(seed, lanes, n_funnels=2, n_colours=64):
+    """source -> `lanes` lane vertices; per funnel: every lane also feeds (weight 1) one recombination vertex, which
+    feeds every lane of the next level (weight 0) — a destination and a row with `lanes` in-edges; ... -> sink."""
+    rng = np.random.default_rng(seed)
+    level_sizes = [1, lanes]
+    for _ in range(n_funnels):
+        level_sizes += [lanes + 1, lanes]
+    level_sizes += [1]
+    level_off = np.concatenate([[0], np.cumsum(level_sizes)])
+    adj = [[] for _ in range(level_off[-1])]
+    for i in range(lanes):
+        adj[0].append((level_off[1] + i, 0))
+    l = 1
+    for _ in range(n_funnels):
+        a, b, c = level_off[l], level_off[l + 1], level_off[l + 2]
+        x = b + lanes                                   # the recombination vertex, last position of its level
+        for i in range(lanes):
+            adj[a + i].append((b + i, 0))
+            adj[a + i].append((x, 1))
+            adj[b + i].append((c + i, 0))
+            adj[x].append((c + i, 0))
+        l += 2
+    for i in range(lanes):
+        adj[level_off[l] + i].append((level_off[l + 1], 0))
+    adj_off = np.concatenate([[0], np.cumsum([len(x) for x in adj])])
+    adj_dst = [v for x in adj for v, _ in x]
+    adj_w = [w for x in adj for _, w in x]
+    ncol = (rng.random(level_off[-1]) < 0.4).astype(np.int64) * rng.integers(1, 4, level_off[-1])
+    ncol[0] = 0
+    col_off = np.concatenate([[0], np.cumsum(ncol)])
+    col_val = np.concatenate([np.sort(rng.choice(n_colours, int(c), replace=False)) for c in ncol] + [np.zeros(0, np.int64)])
+    return LevelGraph(level_off, adj_off, adj_dst, adj_w, col_off, col_val, rng.integers(0, 2, n_colours))
+
+
+@pytest.mark.parametrize("R", [0, 3, 12])
+def test_destinations_with_more_than_32_in_edges(R, oracle_mod, dp_emu):
+    """Panels with more than 32 walks: recombination vertices collect > 32 in-edges; the lane form cuts them into
+    slice blocks and combines the slices through scratch words (TK_LONG); without it those levels take the pair form."""
+    for seed, lanes in ((21, 40), (22, 70), (23, 33), (24, 97)):
+        g = funnel_graph(seed, lanes)
+        ref = oracle_dip(oracle_mod, g, R)
+        o = dp_emu.dp_diploid(g, R)
+        assert_dip_equal(ref, o)
+        assert o["modes"]["tasks_long"] > 0
+        o2 = dp_emu.dp_diploid(g, R, shape=(0, 0, 0, 0, 0, 0, 0, 1))
+        assert_dip_equal(ref, o2)
+        assert o2["modes"]["tasks_long"] == 0
+    # the fan-in-300 graph of the 32-bit-code test: one destination with 300 in-edges
+    k = 300
+    level_off = [0, 1, 1 + k, 2 + k, 3 + k]
+    adj_off = [0, k] + list(range(k + 1, 2 * k + 1)) + [2 * k + 1, 2 * k + 1]
+    adj_dst = list(range(1, 1 + k)) + [1 + k] * k + [2 + k]
+    adj_w = [0] * k + [i % 2 for i in range(k)] + [0]
+    ncol = np.zeros(3 + k, np.int64)
+    ncol[1:1 + k] = 1
+    g = LevelGraph(level_off, adj_off, adj_dst, adj_w, np.concatenate([[0], np.cumsum(ncol)]), np.arange(k) % 7, [1, 0, 1, 0, 0, 1, 0])
+    o = dp_emu.dp_diploid(g, R)
+    assert_dip_equal(oracle_dip(oracle_mod, g, R), o)
+    assert o["modes"]["tasks_long"] > 0

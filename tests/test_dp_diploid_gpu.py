@@ -155,3 +155,18 @@ def test_cuda_unpacked_arithmetic_path(ctx, oracle_mod, expected, monkeypatch):
     e = expected["mhc4_chm13"]["diploid"]["18"]
     assert o["value"] == e["value"] and o["p1_edges"].ravel().tolist() == e["p1_edges"]
     assert hashlib.sha256(o["checksum"][1:].tobytes()).hexdigest() == e["checksum_sha256"]
+
+
+def test_cuda_destinations_with_more_than_32_in_edges(ctx, oracle_mod, monkeypatch):
+    """Slice blocks + scratch combine (TK_LONG) for recombination vertices of panels with more than 32 walks, in
+    shared-memory (small R) and HBM layers, with staged and in-place pair scores; DG_NO_LONG=1 forces the pair form."""
+    from test_dp_diploid_cpu import funnel_graph
+    for seed, lanes in ((21, 40), (22, 70), (23, 33), (24, 97)):
+        g = funnel_graph(seed, lanes)
+        for R in (0, 3, 12):
+            ref = oracle_dip(oracle_mod, g, R)
+            assert_dip_equal(ref, cuda_dip(ctx, g, R))
+    g = funnel_graph(31, 64, n_funnels=3)
+    ref = oracle_dip(oracle_mod, g, 5)
+    monkeypatch.setenv("DG_NO_LONG", "1")
+    assert_dip_equal(ref, cuda_dip(ctx, g, 5))
