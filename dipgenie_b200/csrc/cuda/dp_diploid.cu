@@ -269,9 +269,9 @@ struct LaneProf { unsigned long long items, setup, loop, reduce, store, iters; }
 
 // The lane-form view of the task staged in slot `sb32` (header words as laid out in dp_cell.h: TaskHdr).
 template <bool PRED32>
-__device__ __forceinline__ void fill_lane_task(const SweepArgs& a, uint32_t sb32, uint32_t tiles32, unsigned long long* scratch, LaneTask& lt) {
-    const uint4 h0 = lds_v4(sb32), h1 = lds_v4(sb32 + 16u), h2 = lds_v4(sb32 + 32u), h3 = lds_v4(sb32 + 48u), h4 = lds_v4(sb32 + 64u),
-                h5 = lds_v4(sb32 + 80u);
+__device__ __forceinline__ void fill_lane_task(const SweepArgs& a, uint32_t sb32, uint32_t tiles32, unsigned long long* scratch,
+                                               const uint4& h1, const uint4& h2, LaneTask& lt) {
+    const uint4 h3 = lds_v4(sb32 + 48u), h4 = lds_v4(sb32 + 64u), h5 = lds_v4(sb32 + 80u);
     const uint32_t flags = h1.y;
     const int l = (int)h1.x;
     lt.sb32 = sb32;
@@ -283,7 +283,7 @@ __device__ __forceinline__ void fill_lane_task(const SweepArgs& a, uint32_t sb32
     const unsigned long long pred_off2 = ((unsigned long long)h3.y << 32) | h3.x;
     lt.pl = reinterpret_cast<uint8_t*>(a.pred) + ((size_t)pred_off2 << (PRED32 ? 2 : 1));
     lt.k = h2.x & 0xFFFFu; lt.k2 = h2.x >> 16; lt.i0 = h2.y & 0xFFFFu; lt.i1 = h2.y >> 16; lt.n_in = h2.z;
-    lt.rec_bytes = h0.y; lt.skew = h1.w;
+    lt.rec_bytes = lds_u32(sb32 + 4u); lt.skew = h1.w;
     lt.nblk = h4.y & 0xFFFFu; lt.rp = h4.y >> 16; lt.nrg = h4.z; lt.m_nblk = h4.w;
     lt.m_nrg = h5.x; lt.m_nin = h5.y; lt.n_witems = h5.z; lt.rounds = h5.w;
     lt.bstart_off = lds_u32(sb32 + 96u);
@@ -302,7 +302,7 @@ __device__ __noinline__ ulonglong2 lane_task(const SweepArgs& a, uint32_t sb32, 
     unsigned long long hsum = 0, hlive = 0;
     LaneProf lp = {0, 0, 0, 0, 0, 0};
     LaneTask t;
-    fill_lane_task<PRED32>(a, sb32, tiles32, scratch, t);
+    fill_lane_task<PRED32>(a, sb32, tiles32, scratch, lds_v4(sb32 + 16u), lds_v4(sb32 + 32u), t);
     const int R = a.R, shift = a.shift;
     const uint32_t off32 = t.sb32 + (uint32_t)sizeof(TaskHdr);
     const uint32_t edge32 = off32 + (uint32_t)rec_edge_offset((int)t.k2);
@@ -569,7 +569,7 @@ template <bool CHECK, bool PRED32>
 __device__ __noinline__ ulonglong2 long_finalize(const SweepArgs& a, uint32_t sb32, uint32_t tiles32, unsigned long long* scratch, bool smem_layers, int tid) {
     unsigned long long hsum = 0, hlive = 0;
     LaneTask t;
-    fill_lane_task<PRED32>(a, sb32, tiles32, scratch, t);
+    fill_lane_task<PRED32>(a, sb32, tiles32, scratch, lds_v4(sb32 + 16u), lds_v4(sb32 + 32u), t);
     const int R = a.R;
     const uint32_t RP1 = (uint32_t)R + 1u, G = t.n_long;
     const uint32_t total = (t.i1 - t.i0) * G * RP1;
@@ -734,7 +734,7 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
             if (flags & TK_LANES) {
                 if (a.shift && !is_long) {
                     LaneTask lt;
-                    fill_lane_task<PRED32>(a, sb32, tiles32, scratch, lt);
+                    fill_lane_task<PRED32>(a, sb32, tiles32, scratch, h1, h2, lt);
                     const uint32_t rc = lds_u32(sb32 + 64u) & 0xFFFFu;
                     const bool big = rc == (uint32_t)LANE_RC_BIG;
                     if (ssm) {
