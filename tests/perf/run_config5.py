@@ -1,4 +1,4 @@
-"""SURVEY 8d config 5 at reduced scale: 22-sample leave-one-out batch from a seeded 24-sample (48-walk) synthetic
+"""TEST INFRASTRUCTURE (runs the reference binary under oracle/_ref as the checker / baseline).  SURVEY 8d config 5 at reduced scale: 22-sample leave-one-out batch from a seeded 24-sample (48-walk) synthetic
 panel.  Runs all 22 jobs in ONE `dipgenie -B` process (diploid DPs side by side on the GPU) and the unmodified
 reference binary on the first `--ref-samples` jobs (one process per sample, all host threads, like
 data/run_DipGenie_batch.sh); checks md5 parity on those and reports samples/s of both."""

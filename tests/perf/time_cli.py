@@ -1,4 +1,4 @@
-"""Wall time of the whole run: this repo's CLI (GPU) vs the unmodified reference binary (CPU), same inputs."""
+"""TEST INFRASTRUCTURE (runs the reference binary under oracle/_ref as the checker / baseline).  Wall time of the whole run: this repo's CLI (GPU) vs the unmodified reference binary (CPU), same inputs."""
 import hashlib, json, os, subprocess, sys, tempfile, time
 sys.path.insert(0, os.getcwd())
 from dipgenie_b200 import _build, fixtures
