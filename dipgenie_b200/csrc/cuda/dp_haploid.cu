@@ -10,8 +10,8 @@
 //     candidate that does not beat 0 leaves the cell without a predecessor (:50-52) — reproduced.
 //   * vertices are renumbered level-major ("slots") so that one level is one contiguous run of the score
 //     table [slot][r]; a level only reads earlier levels, so one block barrier per level is all the
-//     synchronisation the persistent sweep needs.  The in-edge ordinal of the winner (2 bytes) is the
-//     only predecessor state kept.
+//     synchronisation the persistent sweep needs.  The winner's in-edge (source slot | weight, 4 bytes) is
+//     the only predecessor state kept, so a traceback step is one dependent load.
 //   * R+1 independent traceback chains (one CTA each), then a fully parallel distinct-colour count per
 //     chain (bitmaps + popcount), which is what the reference's best_r rule consumes (:116-136; the
 //     floating-point rule itself stays on the host).
@@ -29,7 +29,7 @@ namespace dg {
 constexpr int HAP_THREADS = 1024;
 constexpr uint32_t HAP_W_SHIFT = 30;            // in_edge = source slot | weight << 30
 constexpr uint32_t HAP_SLOT_MASK = (1u << HAP_W_SHIFT) - 1;
-constexpr uint16_t HAP_NO_PRED = 0xFFFFu;
+constexpr uint32_t HAP_NO_PRED = 0xFFFFFFFFu;  // slots stay below 2^30 - 1, so this is never a real in-edge
 
 struct HapSweepArgs {
     const int32_t* level_off;   // [L+1] slot ranges
@@ -37,41 +37,115 @@ struct HapSweepArgs {
     const uint32_t* in_edge;    // source slot | w << 30, reference visiting order
     const int32_t* ncol;        // [n] by slot: |color[v]|
     int32_t* dp;                // [n][R+1] by slot
-    uint16_t* pred;             // [n][R+1] winner's in-edge ordinal, HAP_NO_PRED = none
+    uint32_t* pred;             // [n][R+1] winner's in-edge (source slot | w << 30), HAP_NO_PRED = none
     int32_t L, R;
+    int32_t ring;               // slots held by the shared-memory score ring (power of two)
 };
 
 // One persistent CTA walks the levels; level 0 (no in-edges) keeps the initial 0 / no-pred state.
+// A level costs one dependent chain in-edge offsets -> in-edge -> source score.  Everything but the score is
+// independent of the DP, so every thread fetches the offsets and the colour count of its cell two levels ahead
+// and its first in-edge one level ahead: after the barrier only the score load (shared-memory ring) is left.
+struct HapCell {
+    int32_t s, r2, add;
+    int64_t e0, e1;
+    uint32_t x0;
+    bool has;
+};
+// stage A: which cell, its in-edge range and colour count (loads that depend on nothing)
+__device__ __forceinline__ HapCell hap_stage_a(const HapSweepArgs& a, int l, int S, int c) {
+    HapCell p;
+    p.has = false; p.s = 0; p.r2 = 0; p.add = 0; p.e0 = 0; p.e1 = 0; p.x0 = 0;
+    if (l >= a.L) return p;
+    const int lo = __ldg(a.level_off + l), hi = __ldg(a.level_off + l + 1);
+    if (c >= (hi - lo) * S) return p;
+    p.has = true;
+    p.s = lo + c / S; p.r2 = c - (c / S) * S;
+    p.e0 = __ldg(a.in_off + p.s); p.e1 = __ldg(a.in_off + p.s + 1);
+    p.add = __ldg(a.ncol + p.s);
+    return p;
+}
+// stage B: the first in-edge (depends on stage A's offsets, issued one level later)
+__device__ __forceinline__ void hap_stage_b(const HapSweepArgs& a, HapCell& p) {
+    if (p.has && p.e0 < p.e1) p.x0 = __ldg(a.in_edge + p.e0);
+}
+__device__ __forceinline__ HapCell hap_prefetch(const HapSweepArgs& a, int l, int S, int c) {
+    HapCell p = hap_stage_a(a, l, S, c);
+    hap_stage_b(a, p);
+    return p;
+}
+// The scores of the most recent `ring` slots (slots are level-major, so these are the last few hundred levels)
+// also live in a shared-memory ring: almost every in-edge comes from there (29-cycle LDS instead of an L2 round
+// trip on the per-level critical chain); older sources are read from the table in HBM/L2.  `hi` = end of the level
+// being written: entries below hi - ring are being overwritten by this level and must not be read from the ring.
+__device__ __forceinline__ void hap_cell(const HapSweepArgs& a, int S, const HapCell& p, int32_t* ring, int hi, int valid_from) {
+    int32_t best = 0;
+    uint32_t code = HAP_NO_PRED;
+    const int mask = a.ring - 1, oldest = max(hi - a.ring, valid_from);
+    for (int64_t e = p.e0; e < p.e1; ++e) {
+        const uint32_t x = (e == p.e0) ? p.x0 : __ldg(a.in_edge + e);
+        const int r = p.r2 - (int)(x >> HAP_W_SHIFT);
+        if (r >= 0) {
+            const int src = (int)(x & HAP_SLOT_MASK);
+            const int32_t v = (src >= oldest) ? ring[(src & mask) * S + r] : a.dp[(int64_t)src * S + r];
+            const int32_t cand = v + p.add;
+            if (cand > best) { best = cand; code = x; }        // the winner's in-edge itself: source slot | weight << 30
+        }
+    }
+    ring[(p.s & mask) * S + p.r2] = best;
+    a.dp[(int64_t)p.s * S + p.r2] = best;
+    a.pred[(int64_t)p.s * S + p.r2] = code;
+}
+
 __global__ void __launch_bounds__(HAP_THREADS, 1) hap_sweep_kernel(const HapSweepArgs a) {
-    const int S = a.R + 1;
+    extern __shared__ int32_t hap_ring[];
+    const int S = a.R + 1, T = (int)blockDim.x;     // narrow panels run with fewer warps: the per-level barrier is cheaper
+    {   // level 0 keeps the initial 0 state (:50)
+        const int hi0 = __ldg(a.level_off + 1);
+        for (int c = threadIdx.x; c < min(hi0, a.ring) * S; c += T) hap_ring[c] = 0;
+    }
+    int valid_from = (__ldg(a.level_off + 1) > a.ring) ? __ldg(a.level_off + 1) : 0;   // slots >= valid_from (and young enough) are in the ring
+    __syncthreads();
+    // two-deep software pipeline over the levels: offsets of level l+2 and the first in-edge of level l+1 are
+    // requested while level l is computed, so each of the two dependent graph loads has a whole level to arrive
+    HapCell cur = hap_prefetch(a, 1, S, threadIdx.x);
+    HapCell nxt = hap_stage_a(a, 2, S, threadIdx.x);
     for (int l = 1; l < a.L; ++l) {
+        const HapCell nn = hap_stage_a(a, l + 2, S, threadIdx.x);
+        hap_stage_b(a, nxt);
         const int lo = __ldg(a.level_off + l), hi = __ldg(a.level_off + l + 1);
-        const int cells = (hi - lo) * S;
-        for (int c = threadIdx.x; c < cells; c += HAP_THREADS) {
-            const int s = lo + c / S, r2 = c - (c / S) * S;
-            const int64_t e0 = __ldg(a.in_off + s), e1 = __ldg(a.in_off + s + 1);
-            const int32_t add = __ldg(a.ncol + s);
-            int32_t best = 0;
-            uint32_t code = HAP_NO_PRED;
-            for (int64_t e = e0; e < e1; ++e) {
-                const uint32_t x = __ldg(a.in_edge + e);
-                const int r = r2 - (int)(x >> HAP_W_SHIFT);
-                if (r >= 0) {
-                    const int32_t cand = a.dp[(int64_t)(x & HAP_SLOT_MASK) * S + r] + add;
-                    if (cand > best) { best = cand; code = (uint32_t)(e - e0); }
+        if (hi - lo > a.ring) {          // a level wider than the ring cannot use it (its own stores would collide)
+            for (int c = threadIdx.x; c < (hi - lo) * S; c += T) {
+                HapCell p = hap_prefetch(a, l, S, c);
+                int32_t best = 0;
+                uint32_t code = HAP_NO_PRED;
+                for (int64_t e = p.e0; e < p.e1; ++e) {
+                    const uint32_t x = __ldg(a.in_edge + e);
+                    const int r = p.r2 - (int)(x >> HAP_W_SHIFT);
+                    if (r >= 0) {
+                        const int32_t cand = a.dp[(int64_t)(x & HAP_SLOT_MASK) * S + r] + p.add;
+                        if (cand > best) { best = cand; code = x; }
+                    }
                 }
+                a.dp[(int64_t)p.s * S + p.r2] = best;
+                a.pred[(int64_t)p.s * S + p.r2] = code;
             }
-            a.dp[(int64_t)s * S + r2] = best;
-            a.pred[(int64_t)s * S + r2] = (uint16_t)code;
+            valid_from = hi;
+        } else if (cur.has) {
+            // sources older than hi - ring, and everything older than the last level wider than the ring, come from HBM/L2
+            hap_cell(a, S, cur, hap_ring, hi, valid_from);
+            const int cells = (hi - lo) * S;
+            for (int c = threadIdx.x + T; c < cells; c += T) hap_cell(a, S, hap_prefetch(a, l, S, c), hap_ring, hi, valid_from);
         }
         __syncthreads();
+        cur = nxt;
+        nxt = nn;
     }
 }
 
-// Chain r: follow predecessor codes from the last vertex (n-1) in layer r until a cell without a
-// predecessor (:141-151); slots are written sink-first into path[r][0..len).
-__global__ void hap_trace_kernel(const int64_t* in_off, const uint32_t* in_edge, const uint16_t* pred, int32_t sink_slot,
-                                 int32_t R, int32_t cap, int32_t* path, int32_t* path_len) {
+// Chain r: follow the predecessors from the last vertex (n-1) in layer r until a cell without one (:141-151);
+// slots are written sink-first into path[r][0..len).  One dependent load per step.
+__global__ void hap_trace_kernel(const uint32_t* pred, int32_t sink_slot, int32_t R, int32_t cap, int32_t* path, int32_t* path_len) {
     if (threadIdx.x != 0) return;
     const int r0 = blockIdx.x, S = R + 1;
     int32_t* out = path + (int64_t)r0 * cap;
@@ -79,9 +153,8 @@ __global__ void hap_trace_kernel(const int64_t* in_off, const uint32_t* in_edge,
     for (;;) {
         if (len < cap) out[len] = s;
         ++len;
-        const uint16_t code = __ldcg(pred + (int64_t)s * S + r);
-        if (code == HAP_NO_PRED) break;
-        const uint32_t x = __ldg(in_edge + __ldg(in_off + s) + code);
+        const uint32_t x = __ldcg(pred + (int64_t)s * S + r);
+        if (x == HAP_NO_PRED) break;
         s = (int32_t)(x & HAP_SLOT_MASK);
         r -= (int)(x >> HAP_W_SHIFT);
     }
@@ -130,7 +203,7 @@ struct dg_hap {
     DevBuf<int64_t> in_off, col_off;
     DevBuf<uint32_t> in_edge;
     DevBuf<int32_t> col_val;
-    DevBuf<uint16_t> pred;
+    DevBuf<uint32_t> pred;
     DevBuf<unsigned int> bits;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     float sweep_ms = 0.f, trace_ms = 0.f;
@@ -177,7 +250,6 @@ int dg_hap_create(dg_ctx* ctx, int32_t n, const int64_t* adj_off, const int32_t*
     std::vector<int64_t> in_off((size_t)n + 1, 0);
     for (int64_t e = 0; e < nE; ++e) ++in_off[slot[adj_dst[e]] + 1];
     for (int32_t s = 0; s < n; ++s) { d->max_indeg = std::max<int64_t>(d->max_indeg, in_off[s + 1]); in_off[s + 1] += in_off[s]; }
-    if (d->max_indeg >= HAP_NO_PRED) return fail(ctx, DG_ERR_ARG, "dg_hap_create: in-degree %d exceeds the 16-bit predecessor code", d->max_indeg);
     std::vector<uint32_t> in_edge((size_t)nE);
     {
         std::vector<int64_t> cur(in_off.begin(), in_off.end() - 1);
@@ -246,16 +318,23 @@ int dg_hap_run(dg_ctx* ctx, dg_hap* d) {
     d->launches = 0;
     DG_CUDA(ctx, cudaEventRecord(d->ev[0], st));
     DG_CUDA(ctx, cudaMemsetAsync(d->dp.p, 0, cells * sizeof(int32_t), st));            // :50
-    DG_CUDA(ctx, cudaMemsetAsync(d->pred.p, 0xFF, cells * sizeof(uint16_t), st));       // :51-52
+    DG_CUDA(ctx, cudaMemsetAsync(d->pred.p, 0xFF, cells * sizeof(uint32_t), st));       // :51-52
     DG_CUDA(ctx, cudaMemsetAsync(d->bits.p, 0, d->bits.bytes(), st));
     HapSweepArgs a;
     a.level_off = d->level_off.p; a.in_off = d->in_off.p; a.in_edge = d->in_edge.p; a.ncol = d->ncol.p;
     a.dp = d->dp.p; a.pred = d->pred.p; a.L = d->L; a.R = d->R;
-    hap_sweep_kernel<<<1, HAP_THREADS, 0, st>>>(a);
+    // score ring: as many slots (power of two) as fit ~160 KB of shared memory
+    int ring = 4096;
+    while (ring > 1 && (size_t)ring * (size_t)(d->R + 1) * 4 > (size_t)160 * 1024) ring >>= 1;
+    a.ring = ring;
+    const size_t ring_bytes = (size_t)ring * (size_t)(d->R + 1) * 4;
+    DG_CUDA(ctx, cudaFuncSetAttribute((const void*)hap_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_bytes));
+    const int threads = ((int64_t)d->max_width * (d->R + 1) <= 512) ? 256 : HAP_THREADS;
+    hap_sweep_kernel<<<1, threads, ring_bytes, st>>>(a);
     ++d->launches;
     DG_CUDA(ctx, cudaGetLastError());
     DG_CUDA(ctx, cudaEventRecord(d->ev[1], st));
-    hap_trace_kernel<<<d->R + 1, 32, 0, st>>>(d->in_off.p, d->in_edge.p, d->pred.p, d->sink_slot, d->R, d->cap, d->path.p, d->path_len.p);
+    hap_trace_kernel<<<d->R + 1, 32, 0, st>>>(d->pred.p, d->sink_slot, d->R, d->cap, d->path.p, d->path_len.p);
     ++d->launches;
     DG_CUDA(ctx, cudaGetLastError());
     const int bx = std::max(1, std::min(64, (d->cap + 255) / 256));
