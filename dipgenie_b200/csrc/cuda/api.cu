@@ -36,6 +36,7 @@ void dg_destroy(dg_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (cudaStream_t s : ctx->batch_streams) cudaStreamDestroy(s);
+    for (auto& b : ctx->pinned_free) cudaFreeHost(b.p);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

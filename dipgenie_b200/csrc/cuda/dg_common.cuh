@@ -16,6 +16,10 @@ struct dg_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     std::vector<cudaStream_t> batch_streams;   // dg_dp_diploid_batch: one per concurrently resident sample
+    // page-locked staging blocks of the batch planners (kept for the life of the context: pinning is slow)
+    struct Pinned { void* p; size_t bytes; };
+    std::vector<Pinned> pinned_free;
+    std::mutex pinned_mu;
     std::string err;
     dg_sketch_stats_t sketch_stats = {};
 };

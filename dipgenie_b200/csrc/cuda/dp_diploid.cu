@@ -24,6 +24,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <memory>
+#include <memory_resource>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -886,7 +887,40 @@ __global__ void dip_merge_kernel(const TraceArgs a) {
 
 using namespace dg;
 
+// Page-locked staging block of one planned problem (batch path): the plan's big arrays are written into it.
+struct PlanStaging {
+    dg_ctx* ctx = nullptr;
+    dg_ctx::Pinned block = {nullptr, 0};
+    std::unique_ptr<std::pmr::monotonic_buffer_resource> res;
+    // A free block of at least `bytes` from the context's pool, else a new one; on failure the plan simply lives on the heap.
+    void acquire(dg_ctx* c, size_t bytes) {
+        ctx = c;
+        {
+            std::lock_guard<std::mutex> lk(c->pinned_mu);
+            for (size_t x = 0; x < c->pinned_free.size(); ++x)
+                if (c->pinned_free[x].bytes >= bytes) { block = c->pinned_free[x]; c->pinned_free.erase(c->pinned_free.begin() + (long)x); break; }
+        }
+        if (!block.p) {
+            cudaSetDevice(c->device);
+            void* q = nullptr;
+            if (cudaHostAlloc(&q, bytes, cudaHostAllocDefault) == cudaSuccess) block = {q, bytes};
+            else (void)cudaGetLastError();
+        }
+        if (block.p) res.reset(new std::pmr::monotonic_buffer_resource(block.p, block.bytes, std::pmr::new_delete_resource()));
+    }
+    std::pmr::memory_resource* resource() { return res ? res.get() : std::pmr::get_default_resource(); }
+    void release() {                     // only once nothing allocated from the block is alive or in flight
+        res.reset();
+        if (block.p) { std::lock_guard<std::mutex> lk(ctx->pinned_mu); ctx->pinned_free.push_back(block); }
+        block = {nullptr, 0};
+    }
+    ~PlanStaging() { release(); }
+};
+
 struct dg_dip {
+    explicit dg_dip(std::unique_ptr<PlanStaging> st = nullptr)
+        : staging(std::move(st)), plan(staging ? staging->resource() : std::pmr::get_default_resource()) {}
+    std::unique_ptr<PlanStaging> staging;   // declared before `plan`: outlives the plan's arrays
     cudaStream_t stream = nullptr;   // the context's stream, or one of the batch streams
     bool cooperative = true;         // batch slots use plain launches (see dip_run_impl)
     int shift = 0;                   // KEY_SHIFT when every DP value provably stays below 2^21 (packed keys), else 0
@@ -1068,12 +1102,13 @@ static int dip_create_device(dg_ctx* ctx, dg_dip* d) {
                       d->tile0.bytes() + d->tile1.bytes() + d->pred.bytes() + d->level_sum.bytes() + d->level_live.bytes() +
                       d->anc.bytes() + d->seg_p1.bytes() + d->seg_p2.bytes();
     // the big host arrays are no longer needed
-    std::vector<uint32_t>().swap(p.in_edge);
-    std::vector<uint16_t>().swap(p.in_dst);
-    std::vector<uint8_t>().swap(p.records);
-    std::vector<uint64_t>().swap(p.masks);
-    std::vector<int32_t>().swap(p.in_off);
-    std::vector<TaskHdr>().swap(p.tasks);
+    p.in_edge.clear(); p.in_edge.shrink_to_fit();
+    p.in_dst.clear(); p.in_dst.shrink_to_fit();
+    p.records.clear(); p.records.shrink_to_fit();
+    p.masks.clear(); p.masks.shrink_to_fit();
+    p.in_off.clear(); p.in_off.shrink_to_fit();
+    p.tasks.clear(); p.tasks.shrink_to_fit();
+    if (d->staging) d->staging->release();     // (the copies were synchronized above)
     return DG_OK;
 }
 
@@ -1284,8 +1319,12 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
     // uploads, launches and collects in sample order
     int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     if (const char* e = getenv("DG_HOST_THREADS")) hw = std::max(1, atoi(e));   // this process's share of the host cores (one process per GPU)
-    const int W = std::max(1, std::min({(int)n, 4, hw / 2}));
-    const int lookahead = 2 * W + 2;
+    int W = std::max(1, std::min({(int)n, 8, hw / 2}));          // two planner threads per worker scale best (profiles/r01b)
+    if (const char* e = getenv("DG_PLAN_WORKERS")) W = std::max(1, std::min({atoi(e), (int)n, hw}));
+    const int lookahead = W + 2;
+    const bool pinned = !getenv("DG_NO_PINNED_PLAN");
+    const bool timing = getenv("DG_TIMING") != nullptr;
+    const double t_batch0 = now_ms();
     std::vector<std::unique_ptr<dg_dip>> planned((size_t)n);
     std::vector<int> state((size_t)n, 0);                       // 0 pending, 1 planned, -1 failed
     std::vector<std::string> perr((size_t)n);
@@ -1305,7 +1344,15 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
                 i = next++;
             }
             const dg_dip_input_t& x = in[i];
-            std::unique_ptr<dg_dip> d(new dg_dip());
+            // the plan is written straight into page-locked memory: about 60 bytes per vertex on the pangenome
+            // panels (an array that does not fit any more goes to the heap and is copied from there)
+            std::unique_ptr<PlanStaging> st;
+            if (pinned && x.n_levels > 0 && x.level_off) {
+                st.reset(new PlanStaging());
+                const size_t V = (size_t)x.level_off[x.n_levels];
+                st->acquire(ctx, ((size_t)68 * V + ((size_t)4 << 20) + ((size_t)1 << 20) - 1) >> 20 << 20);
+            }
+            std::unique_ptr<dg_dip> d(new dg_dip(std::move(st)));
             d->stream = ctx->batch_streams[(size_t)(i % K)];
             d->cooperative = false;
             DipGraphView g;
@@ -1314,6 +1361,7 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
             bool ok = x.R + 2 <= DG_BATCH_MAX_EDGES;
             std::string err = ok ? "" : "R + 2 > DG_BATCH_MAX_EDGES";
             if (ok) { ok = dip_plan_host(g, lim, grid, d.get()); if (!ok) err = d->plan.error; }
+            if (timing) fprintf(stderr, "batch: sample %d planned at %.1f ms (plan %.1f ms)\n", i, now_ms() - t_batch0, d->plan_ms);
             {
                 std::lock_guard<std::mutex> lk(mu);
                 if (ok) planned[(size_t)i] = std::move(d); else perr[(size_t)i] = err;
@@ -1360,11 +1408,13 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
         int r = dip_create_device(ctx, d.get());     // (uploads stay on this thread: a pageable H2D issued by a worker on a
                                                      //  busy slot stream blocks that worker until the slot's sweep ends)
         if (!r) r = dg_dip_run(ctx, d.get(), 0);
+        if (timing) fprintf(stderr, "batch: sample %d launched at %.1f ms (alloc+upload %.1f ms)\n", (int)i, now_ms() - t_batch0, d->upload_ms);
         if (r) { out[i].status = r; if (!rc) rc = r; continue; }
         slot[(size_t)k] = d.release(); owner[(size_t)k] = i;
     }
     for (std::thread& t : pool) t.join();
     for (int k = 0; k < K; ++k) collect(k);
+    if (timing) fprintf(stderr, "batch: %d samples done at %.1f ms\n", (int)n, now_ms() - t_batch0);
     return rc;
 }
 

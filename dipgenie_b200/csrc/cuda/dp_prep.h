@@ -18,6 +18,7 @@
 //     persistent sweep.
 #pragma once
 #include <cstdint>
+#include <memory_resource>
 #include <string>
 #include <vector>
 
@@ -53,17 +54,22 @@ struct SweepShape {              // kernel geometry the plan is made for
 };
 
 struct DipPlan {
+    // The arrays that go to the device wholesale take their storage from `res` (default: the heap).  The batch
+    // entry point hands every planner a block of page-locked host memory, so that the plan is written once, into
+    // memory the copy engine reads directly.
+    explicit DipPlan(std::pmr::memory_resource* res = std::pmr::get_default_resource())
+        : in_off(res), in_edge(res), in_dst(res), masks(res), records(res), tasks(res) {}
     int32_t L = 0, V = 0, R = 0;
     int32_t kmax = 0, max_indeg = 0, Wmax = 0;
     int64_t n_in = 0;
     std::vector<int32_t> level_off;    // [L+1]
-    std::vector<int32_t> in_off;       // [V+1]
-    std::vector<uint32_t> in_edge;     // [n_in]   source position | weight << 16
-    std::vector<uint16_t> in_dst;      // [n_in]   destination position of the in-edge (for the delta kernel)
+    std::pmr::vector<int32_t> in_off;  // [V+1]
+    std::pmr::vector<uint32_t> in_edge;  // [n_in]   source position | weight << 16
+    std::pmr::vector<uint16_t> in_dst;  // [n_in]   destination position of the in-edge (for the delta kernel)
     std::vector<int32_t> lvlW;         // [L]   64-bit mask words of transition l (0 = no colours)
     std::vector<int64_t> msrc_off;     // [L]   offset (u64 words) of level-l source masks
     std::vector<int64_t> mdst_off;     // [L]   offset of level-(l+1) destination masks
-    std::vector<uint64_t> masks;
+    std::pmr::vector<uint64_t> masks;
     std::vector<int64_t> pred_off;     // [L+1] offset of level l's predecessor codes
     // --- task plan (plan_tasks) ---
     std::vector<int32_t> P;            // [L]   CTAs taking part in transition l
@@ -71,11 +77,11 @@ struct DipPlan {
     std::vector<uint8_t> bar_edge;     // [L]   1 = a grid-level barrier follows transition l
     std::vector<uint8_t> narrow;       // [L]   1 = both layers of transition l fit CTA 0's shared-memory tiles
     std::vector<int64_t> rec_off;      // [L]   byte offset of transition l's record in `records` (-1: none)
-    std::vector<uint8_t> records;      // packed records (16-byte aligned)
+    std::pmr::vector<uint8_t> records; // packed records (16-byte aligned)
     std::vector<int64_t> delta_off;    // [L]   u16-element offset of transition l's pair-score matrix (-1: none)
     std::vector<int32_t> delta_list;   // transitions that own a matrix, ascending
     int64_t delta_elems = 0;           // total u16 elements (every matrix start is 16-byte aligned)
-    std::vector<TaskHdr> tasks;        // all CTAs' streams, concatenated in CTA order
+    std::pmr::vector<TaskHdr> tasks;   // all CTAs' streams, concatenated in CTA order
     std::vector<int64_t> task_begin;   // [grid+1]
     int32_t grid = 1;
     int64_t n_narrow = 0, n_wide = 0, n_tasks_global = 0, n_tasks_masks = 0;
