@@ -51,6 +51,8 @@ enum : uint32_t {
     TK_DELTA_MASKS = 256,  // no matrix was materialised (too wide): popcount the colour masks on the fly
     TK_LANES = 512,        // lane form (below); otherwise the pair form
     TK_LONG = 1024,        // lane form with destinations of more than 32 in-edges (slice blocks + scratch combine)
+    TK_PUSH = 4096,        // row-sharded sweep over several GPUs: after the CTA's rows of the level are whole, copy rows
+                           // [push_i0, push_i1) of the destination layer and of its predecessor codes to every peer GPU
 };
 
 // Two evaluation forms of a task, same results:
@@ -96,7 +98,8 @@ struct TaskHdr {             // 128 bytes
     uint32_t bstart_off;     //            byte offset of bstart[] inside the record
     uint32_t n_long;         //            destinations with more than 32 in-edges (TK_LONG), <= LANE_MAX_LONG
     uint32_t long_off;       //            byte offset of long_j[] (their positions, u16) inside the record
-    uint32_t pad[5];
+    uint16_t push_i0, push_i1;   // TK_PUSH: the CTA's whole row range of the level (byte 108)
+    uint32_t pad[4];
 };
 static_assert(sizeof(TaskHdr) == 128, "TaskHdr layout");
 

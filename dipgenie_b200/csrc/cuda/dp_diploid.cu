@@ -51,6 +51,8 @@ constexpr size_t DIP_SMEM_BYTES = (size_t)DIP_NSLOT * DIP_SLOT_BYTES + 2 * (size
                                   (size_t)LANE_SCRATCH_ENTRIES * 8;
 constexpr int DIP_TRACE_T = 128;               // levels between traceback checkpoints
 
+constexpr int DG_MAX_PEERS = 8;
+
 struct SweepArgs {
     const TaskHdr* tasks;
     const int64_t* task_begin;
@@ -73,6 +75,15 @@ struct SweepArgs {
     unsigned long long* prof;         // [32] phase cycle counters of CTA 0 / thread 0 (nullable)
     int32_t R;
     int32_t shift;                    // layers hold value << shift (dp_cell.h: packed keys), 0 or KEY_SHIFT
+    // row-sharded sweep over `world` GPUs (1 = off): the peers' layer tiles, predecessor codes and counters, mapped
+    // through CUDA IPC (entry `rank` = this GPU's own); counter[0] = level arrivals, counter[1] = CTAs that left
+    int32_t world, rank;
+    int32_t* peer_tile0[DG_MAX_PEERS];
+    int32_t* peer_tile1[DG_MAX_PEERS];
+    uint8_t* peer_pred[DG_MAX_PEERS];
+    unsigned int* peer_counter[DG_MAX_PEERS];
+    uint32_t exit_target;             // world x CTAs per rank
+    unsigned long long timeout_ns;    // a barrier wait longer than this fails the run (counter[2] = level + 1)
 };
 
 // ---- PTX helpers -----------------------------------------------------------------------------
@@ -90,6 +101,30 @@ __device__ __forceinline__ void wait_counter(const unsigned int* counter, unsign
         __nanosleep(40);
     }
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+// The same across GPUs (row-sharded sweep): system-scope release / acquire on peer-mapped counters.
+__device__ __forceinline__ void red_release_sys_add_u32(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Gives up after `timeout_ns` (a peer that never launched or died must not hang this GPU): returns false, and the
+// caller flags the run as failed.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ bool wait_counter_sys(const unsigned int* counter, unsigned int target, unsigned long long timeout_ns) {
+    const unsigned long long t0 = global_ns();
+    bool ok = true;
+    for (unsigned int it = 0;; ++it) {
+        unsigned int v;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (v >= target) break;
+        __nanosleep(40);
+        if ((it & 1023u) == 1023u && global_ns() - t0 > timeout_ns) { ok = false; break; }
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    return ok;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -650,6 +685,30 @@ __device__ __noinline__ ulonglong2 generic_task(const SweepArgs& a, const uint8_
     return make_ulonglong2(hsum, hlive);
 }
 
+// Row-sharded sweep: copies rows [i0, i1) of every layer of level l+1 — values from this GPU's tile, predecessor codes
+// from its code array — to the same places on every peer GPU (plain stores through the NVLink peer mappings).
+template <bool PRED32>
+__device__ __noinline__ void push_rows(const SweepArgs& a, int l, uint32_t k2, uint32_t i0, uint32_t i1,
+                                       unsigned long long pred_off2, int tid) {
+    const uint32_t kk2 = k2 * k2, seg = (i1 - i0) * k2, first = i0 * k2;
+    const bool odd = ((l + 1) & 1) != 0;
+    const int32_t* const src = odd ? a.tile1 : a.tile0;
+    const uint8_t* const psrc = reinterpret_cast<const uint8_t*>(a.pred);
+    for (int q = 0; q < a.world; ++q) {
+        if (q == a.rank) continue;
+        int32_t* const dst = odd ? a.peer_tile1[q] : a.peer_tile0[q];
+        uint8_t* const pdst = a.peer_pred[q];
+        for (int r = 0; r <= a.R; ++r) {
+            const size_t base = (size_t)r * kk2 + first;
+            for (uint32_t x = (uint32_t)tid; x < seg; x += DIP_CT) {
+                dst[base + x] = __ldcg(src + base + x);
+                if (PRED32) reinterpret_cast<uint32_t*>(pdst)[pred_off2 + base + x] = __ldcg(reinterpret_cast<const uint32_t*>(psrc) + pred_off2 + base + x);
+                else reinterpret_cast<uint16_t*>(pdst)[pred_off2 + base + x] = __ldcg(reinterpret_cast<const uint16_t*>(psrc) + pred_off2 + base + x);
+            }
+        }
+    }
+}
+
 template <bool CHECK, bool PRED32, bool PROF>
 __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_constant__ SweepArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -718,7 +777,14 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
         const uint32_t flags = h1.y;
         const int l = (int)h1.x;
         if (flags & TK_WAIT) {
-            if (tid == 0) wait_counter(a.counter, h1.z);
+            if (tid == 0) {
+                if (a.world > 1) {
+                    if (!wait_counter_sys(a.counter, h1.z, a.timeout_ns)) {
+                        if (atomicCAS(a.counter + 2, 0u, (unsigned int)l + 1u) == 0u)
+                            printf("dip_sweep_kernel: rank %d CTA %d gave up at level %d: %u of %u arrivals\n", a.rank, cta, l, *(volatile unsigned int*)a.counter, h1.z);
+                    }
+                } else wait_counter(a.counter, h1.z);
+            }
             bar_compute();
         }
         if (profiling) tk2 = clock64();
@@ -761,10 +827,25 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
             hsum += hs.x; hlive += hs.y;
         }
         if (profiling) tk3 = clock64();
+        uint32_t pw = 0;                                        // TK_PUSH: header words read before the slot is handed back
+        unsigned long long push_pred_off = 0;
+        if (flags & TK_PUSH) {
+            pw = lds_u32(sb32 + 108u);
+            push_pred_off = ((unsigned long long)lds_u32(sb32 + 52u) << 32) | lds_u32(sb32 + 48u);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty32 + 8u * slot);       // this warp is done with the slot
         if (flags & TK_BAR) bar_compute();                     // the destination rows of this CTA are whole
-        if ((flags & TK_ARRIVE) && tid == 0) red_release_add_u32(a.counter, 1u);
+        if (flags & TK_PUSH) {
+            // row-sharded sweep: this CTA's rows of layer l+1 (values and predecessor codes) go to every peer over NVLink
+            push_rows<PRED32>(a, l, h2.x >> 16, pw & 0xFFFFu, pw >> 16, push_pred_off, tid);
+            __threadfence_system();
+            bar_compute();
+        }
+        if ((flags & TK_ARRIVE) && tid == 0) {
+            if (a.world > 1) { for (int q = 0; q < a.world; ++q) red_release_sys_add_u32(a.peer_counter[q], 1u); }
+            else red_release_add_u32(a.counter, 1u);
+        }
         if (profiling) {
             tk4 = clock64();
             if (ssm || dsm) { pc0 += 1; pc1 += tk1 - tk0; pc2 += tk2 - tk1; pc3 += tk3 - tk2; pc4 += tk4 - tk3; }
@@ -778,6 +859,19 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
             if (lane == 0 && hlive) {
                 atomicAdd(a.level_sum + l + 1, hsum);
                 atomicAdd(a.level_live + l + 1, hlive);
+            }
+        }
+    }
+    if (a.world > 1) {
+        // every CTA of every rank reports that all its pushes are out; CTA 0 keeps the kernel alive until all have,
+        // so that what follows on the stream (traceback) sees the complete predecessor codes
+        __threadfence_system();
+        bar_compute();
+        if (tid == 0) {
+            for (int q = 0; q < a.world; ++q) red_release_sys_add_u32(a.peer_counter[q] + 1, 1u);
+            if (cta == 0 && !wait_counter_sys(a.counter + 1, a.exit_target, a.timeout_ns)) {
+                if (atomicCAS(a.counter + 2, 0u, 0x7FFFFFFFu) == 0u)
+                    printf("dip_sweep_kernel: rank %d gave up at the exit barrier: %u of %u CTAs\n", a.rank, *(volatile unsigned int*)(a.counter + 1), a.exit_target);
             }
         }
     }
@@ -930,6 +1024,10 @@ struct dg_dip {
     DipPlan plan;                 // host copy (small arrays kept for stats; big ones released after upload)
     int pred_bytes = 2;
     int grid = 1;
+    // row-sharded over `world` GPUs (dg_dip_create_sharded): peer mappings of tile0, tile1, pred, counter
+    int world = 1, rank = 0;
+    void* peer[4][DG_MAX_PEERS] = {};
+    bool attached = false, armed = false, ipc_opened = false;
     int M = 0;                    // traceback segments
     int64_t anc_cells = 0;
     DevBuf<TaskHdr> tasks;
@@ -957,7 +1055,12 @@ struct dg_dip {
     int launches = 0;
     bool ran = false, checks = false;
     uint64_t device_bytes = 0;
-    ~dg_dip() { for (auto& e : ev) if (e) cudaEventDestroy(e); }
+    ~dg_dip() {
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (ipc_opened)
+            for (int a = 0; a < 4; ++a)
+                for (int q = 0; q < world; ++q) if (q != rank && peer[a][q]) cudaIpcCloseMemHandle(peer[a][q]);
+    }
 };
 
 static const void* sweep_fn(bool pred32, bool check, bool prof = false) {
@@ -980,6 +1083,15 @@ static int dip_limits(dg_ctx* ctx, DipLimits& lim) {
     DG_CUDA(ctx, cudaSetDevice(ctx->device));
     for (int v = 0; v < 8; ++v)
         DG_CUDA(ctx, cudaFuncSetAttribute(sweep_fn(v & 1, v & 2, v & 4), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
+    // Load every kernel a run launches now: with CUDA's lazy module loading the first launch of a kernel can wait for
+    // the device to drain, and a sweep that spins on a peer (row-sharded problems) never drains by itself.
+    {
+        cudaFuncAttributes fa;
+        const void* fns[] = {(const void*)dip_delta_kernel, (const void*)dip_anc_kernel<uint16_t>, (const void*)dip_anc_kernel<uint32_t>,
+                             (const void*)dip_hop_kernel, (const void*)dip_seg_kernel<uint16_t>, (const void*)dip_seg_kernel<uint32_t>,
+                             (const void*)dip_merge_kernel};
+        for (const void* f : fns) DG_CUDA(ctx, cudaFuncGetAttributes(&fa, f));
+    }
     int per_sm = 0;
     DG_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_fn(false, false), DIP_THREADS, DIP_SMEM_BYTES));
     if (per_sm < 1) return fail(ctx, DG_ERR_CUDA, "dg_dip_create: sweep kernel cannot be resident");
@@ -1017,9 +1129,11 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
     shape.lane_rc = (d->shift != 0 && p.R + 1 >= LANE_RC_BIG) ? LANE_RC_BIG : LANE_RC_SMALL;
     d->lane_rc = shape.lane_rc;
     shape.allow_long = d->shift != 0 && !getenv("DG_NO_LONG");     // slice blocks live in the packed-key kernel
+    shape.replicas = d->world; shape.rank = d->rank;
     plan_tasks(p, shape);
     d->grid = 1;
     for (int c = 0; c < p.grid; ++c) if (p.task_begin[(size_t)c + 1] > p.task_begin[c]) d->grid = c + 1;
+    if (d->world > 1) d->grid = p.grid;            // every rank launches the same grid (the exit barrier counts CTAs)
     // traceback checkpoints: cp[0] = sink level, then the narrowest level about every DIP_TRACE_T levels, down to level 0
     d->h_cp = choose_checkpoints(p.level_off, DIP_TRACE_T);
     d->M = (int)d->h_cp.size() - 1;
@@ -1077,10 +1191,17 @@ static int dip_create_device(dg_ctx* ctx, dg_dip* d) {
     // (layers rounded up to whole lane-form chunks: the last chunk loads, but never stores, layers above R)
     const uint64_t widest = (uint64_t)(p.R + d->lane_rc) * (uint64_t)p.kmax * (uint64_t)p.kmax;
     const size_t tile = (size_t)std::max<uint64_t>(widest, (uint64_t)(p.R + 1));
-    DG_CUDA(ctx, d->tile0.alloc(tile, s));
-    DG_CUDA(ctx, d->tile1.alloc(tile, s));
-    DG_CUDA(ctx, d->pred.alloc((size_t)p.pred_off[L] * (size_t)d->pred_bytes, s));
-    DG_CUDA(ctx, d->counter.alloc(1, s));
+    if (d->world > 1) {          // what the peers map through CUDA IPC cannot come from the stream-ordered pool
+        DG_CUDA(ctx, d->tile0.alloc(tile));
+        DG_CUDA(ctx, d->tile1.alloc(tile));
+        DG_CUDA(ctx, d->pred.alloc((size_t)p.pred_off[L] * (size_t)d->pred_bytes));
+        DG_CUDA(ctx, d->counter.alloc(4));
+    } else {
+        DG_CUDA(ctx, d->tile0.alloc(tile, s));
+        DG_CUDA(ctx, d->tile1.alloc(tile, s));
+        DG_CUDA(ctx, d->pred.alloc((size_t)p.pred_off[L] * (size_t)d->pred_bytes, s));
+        DG_CUDA(ctx, d->counter.alloc(4, s));
+    }
     DG_CUDA(ctx, d->level_sum.alloc((size_t)L, s));
     DG_CUDA(ctx, d->level_live.alloc((size_t)L, s));
     DG_CUDA(ctx, d->prof.alloc(32, s));
@@ -1116,8 +1237,16 @@ template <class PredT>
 static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     const DipPlan& p = d->plan;
     cudaStream_t s = d->stream;
-    DG_CUDA(ctx, cudaMemsetAsync(d->counter.p, 0, sizeof(unsigned int), s));
-    DG_CUDA(ctx, cudaMemsetAsync(d->tile0.p, 0, (size_t)(p.R + 1) * sizeof(int32_t), s));   // dp_cur.assign(R+1, {0,0}) :535
+    if (d->world > 1) {
+        // counters and level 0 were reset by dg_dip_shard_arm, before the ranks' host barrier: a peer may arrive on
+        // this GPU's counter before this launch
+        if (!d->attached || !d->armed) return fail(ctx, DG_ERR_ARG, "dg_dip_run: sharded problem needs dg_dip_ipc_attach and dg_dip_shard_arm first");
+        if (check) return fail(ctx, DG_ERR_ARG, "dg_dip_run: level checksums are not available on a sharded problem");
+        d->armed = false;
+    } else {
+        DG_CUDA(ctx, cudaMemsetAsync(d->counter.p, 0, 2 * sizeof(unsigned int), s));
+        DG_CUDA(ctx, cudaMemsetAsync(d->tile0.p, 0, (size_t)(p.R + 1) * sizeof(int32_t), s));   // dp_cur.assign(R+1, {0,0}) :535
+    }
     if (check) {
         std::vector<unsigned long long> basis((size_t)p.L, FOLD_BASIS);
         DG_CUDA(ctx, cudaMemcpyAsync(d->level_sum.p, basis.data(), basis.size() * 8, cudaMemcpyHostToDevice, s));
@@ -1146,6 +1275,13 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     a.level_sum = d->level_sum.p; a.level_live = d->level_live.p;
     a.prof = d->want_prof ? d->prof.p : nullptr;
     a.R = p.R; a.shift = d->shift;
+    a.world = d->world; a.rank = d->rank; a.exit_target = (uint32_t)(d->world * d->grid);
+    a.timeout_ns = 10000ull * 1000000ull;
+    if (const char* e = getenv("DG_SHARD_TIMEOUT_MS")) a.timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
+    for (int q = 0; q < DG_MAX_PEERS; ++q) {
+        a.peer_tile0[q] = (int32_t*)d->peer[0][q]; a.peer_tile1[q] = (int32_t*)d->peer[1][q];
+        a.peer_pred[q] = (uint8_t*)d->peer[2][q]; a.peer_counter[q] = (unsigned int*)d->peer[3][q];
+    }
     if (p.L > 1) {
         void* args[] = {(void*)&a};
         const void* fn = sweep_fn(sizeof(PredT) == 4, check, d->want_prof);
@@ -1224,10 +1360,15 @@ int dg_dip_result(dg_ctx* ctx, dg_dip* d, int32_t* sink_value, int32_t* sink_s_h
     TraceOut t;
     std::vector<int32_t> a((size_t)2 * cap), b((size_t)2 * cap);
     cudaStream_t s = d->stream;
+    unsigned int shard_err = 0;
+    if (d->world > 1) DG_CUDA(ctx, cudaMemcpyAsync(&shard_err, d->counter.p + 2, sizeof shard_err, cudaMemcpyDeviceToHost, s));
     DG_CUDA(ctx, cudaMemcpyAsync(&t, d->tout.p, sizeof t, cudaMemcpyDeviceToHost, s));
     DG_CUDA(ctx, cudaMemcpyAsync(a.data(), d->p1.p, a.size() * 4, cudaMemcpyDeviceToHost, s));
     DG_CUDA(ctx, cudaMemcpyAsync(b.data(), d->p2.p, b.size() * 4, cudaMemcpyDeviceToHost, s));
     DG_CUDA(ctx, cudaStreamSynchronize(s));
+    if (shard_err)
+        return fail(ctx, DG_ERR_CUDA, "dg_dip_result: row-sharded sweep of rank %d timed out at a cross-GPU barrier (%s %u): a peer is not running",
+                    d->rank, shard_err == 0x7FFFFFFFu ? "exit barrier, code" : "level", shard_err == 0x7FFFFFFFu ? shard_err : shard_err - 1);
     DG_CUDA(ctx, cudaEventElapsedTime(&d->delta_ms, d->ev[0], d->ev[1]));
     DG_CUDA(ctx, cudaEventElapsedTime(&d->sweep_ms, d->ev[1], d->ev[2]));
     DG_CUDA(ctx, cudaEventElapsedTime(&d->trace_ms, d->ev[2], d->ev[3]));
@@ -1416,6 +1557,97 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
     for (int k = 0; k < K; ++k) collect(k);
     if (timing) fprintf(stderr, "batch: %d samples done at %.1f ms\n", (int)n, now_ms() - t_batch0);
     return rc;
+}
+
+// ---- row-sharded diploid DP over several GPUs of one node (one process per GPU) --------------------------------
+// Every rank plans the same graph for world x ctas global CTAs and keeps its share of the wide transitions' rows;
+// the sweep kernels of all ranks run at the same time and exchange rows and barrier arrivals through NVLink peer
+// mappings (no NCCL call on the data path: the exchange is fused into the sweep kernel).
+int dg_dip_create_sharded(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
+                          const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off, const int32_t* col_val,
+                          const uint8_t* colour_is_hom, int32_t n_colours, int32_t R, int32_t rank, int32_t world,
+                          int32_t ctas, dg_dip** out) {
+    if (!ctx || !out || world < 1 || world > DG_MAX_PEERS || rank < 0 || rank >= world) return DG_ERR_ARG;
+    *out = nullptr;
+    DipLimits lim;
+    if (int rc = dip_limits(ctx, lim)) return rc;
+    DipGraphView g;
+    g.n_levels = n_levels; g.level_off = level_off; g.adj_off = adj_off; g.adj_dst = adj_dst; g.adj_w = adj_w;
+    g.col_off = col_off; g.col_val = col_val; g.colour_is_hom = colour_is_hom; g.n_colours = n_colours; g.R = R;
+    std::unique_ptr<dg_dip> d(new dg_dip());
+    d->stream = ctx->stream;
+    d->cooperative = true;
+    d->world = world; d->rank = rank;
+    if (!dip_plan_host(g, lim, ctas > 0 ? ctas : lim.max_grid, d.get())) return fail(ctx, DG_ERR_ARG, "dg_dip_create_sharded: %s", d->plan.error.c_str());
+    if (int rc = dip_create_device(ctx, d.get())) return rc;
+    d->peer[0][rank] = d->tile0.p; d->peer[1][rank] = d->tile1.p; d->peer[2][rank] = d->pred.p; d->peer[3][rank] = d->counter.p;
+    *out = d.release();
+    return DG_OK;
+}
+
+int dg_dip_ipc_export(dg_ctx* ctx, dg_dip* d, uint8_t* handles) {
+    if (!ctx || !d || !handles) return DG_ERR_ARG;
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == DG_IPC_HANDLE_BYTES, "handle size");
+    void* ptrs[4] = {d->tile0.p, d->tile1.p, d->pred.p, d->counter.p};
+    for (int a = 0; a < 4; ++a) {
+        cudaIpcMemHandle_t h;
+        DG_CUDA(ctx, cudaIpcGetMemHandle(&h, ptrs[a]));
+        memcpy(handles + (size_t)a * DG_IPC_HANDLE_BYTES, &h, sizeof h);
+    }
+    return DG_OK;
+}
+
+int dg_dip_ipc_attach(dg_ctx* ctx, dg_dip* d, const uint8_t* all_handles) {
+    if (!ctx || !d || !all_handles || d->world < 2 || d->attached) return DG_ERR_ARG;
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int q = 0; q < d->world; ++q) {
+        if (q == d->rank) continue;
+        for (int a = 0; a < 4; ++a) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all_handles + ((size_t)q * 4 + (size_t)a) * DG_IPC_HANDLE_BYTES, sizeof h);
+            DG_CUDA(ctx, cudaIpcOpenMemHandle(&d->peer[a][q], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+    }
+    d->attached = true; d->ipc_opened = true;
+    return DG_OK;
+}
+
+// The ranks of one sharded problem as sibling problems of ONE process on ONE GPU (tests, single-GPU boxes): the
+// "peers" are the siblings' buffers themselves; every sibling gets a stream of its own and a plain launch, and the
+// caller runs them together (world x ctas CTAs must fit the GPU, as for dg_dip_run_many).
+int dg_dip_attach_in_process(dg_ctx* ctx, dg_dip** all, int32_t world) {
+    if (!ctx || !all || world < 2 || world > DG_MAX_PEERS) return DG_ERR_ARG;
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t ctas = 0;
+    for (int q = 0; q < world; ++q) {
+        if (!all[q] || all[q]->world != world || all[q]->rank != q || all[q]->attached) return DG_ERR_ARG;
+        ctas += all[q]->grid;
+    }
+    if (ctas > ctx->sm_count) return fail(ctx, DG_ERR_CAPACITY, "dg_dip_attach_in_process: %lld sweep CTAs do not fit %d SMs", (long long)ctas, ctx->sm_count);
+    for (int q = 0; q < world; ++q) {
+        dg_dip* d = all[q];
+        cudaStream_t s = nullptr;
+        if (int rc = batch_stream(ctx, q, &s)) return rc;
+        d->stream = s; d->cooperative = false;
+        for (int t = 0; t < world; ++t) {
+            d->peer[0][t] = all[t]->tile0.p; d->peer[1][t] = all[t]->tile1.p;
+            d->peer[2][t] = all[t]->pred.p; d->peer[3][t] = all[t]->counter.p;
+        }
+        d->armed = false;
+    }
+    for (int q = 0; q < world; ++q) all[q]->attached = true;
+    return DG_OK;
+}
+
+int dg_dip_shard_arm(dg_ctx* ctx, dg_dip* d) {
+    if (!ctx || !d || d->world < 2) return DG_ERR_ARG;
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DG_CUDA(ctx, cudaMemsetAsync(d->counter.p, 0, 4 * sizeof(unsigned int), d->stream));
+    DG_CUDA(ctx, cudaMemsetAsync(d->tile0.p, 0, (size_t)(d->plan.R + 1) * sizeof(int32_t), d->stream));
+    DG_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    d->armed = true;
+    return DG_OK;
 }
 
 int dg_dip_create_slot(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,

@@ -235,6 +235,8 @@ std::vector<int32_t> choose_checkpoints(const std::vector<int32_t>& level_off, i
 void plan_tasks(DipPlan& p, const SweepShape& sh) {
     const int L = p.L, T = L - 1;                  // T = number of transitions
     const int G = sh.grid < 1 ? 1 : sh.grid;
+    const int NR = sh.replicas < 1 ? 1 : sh.replicas, RK = sh.rank;      // row-sharded over NR ranks (dp_prep.h)
+    const int GG = G * NR;                                                // global CTAs
     const uint32_t CT = sh.threads < 1 ? 1u : (uint32_t)sh.threads;
     const size_t slot = (size_t)sh.slot_bytes;
     const int lrc = (sh.lane_rc == LANE_RC_BIG) ? LANE_RC_BIG : LANE_RC_SMALL;
@@ -302,15 +304,16 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
     }
 
     // ---- 2. participants: narrow -> CTA 0 alone; wide -> P = min(G, k2) CTAs ----
-    for (int l = 0; l < T; ++l) p.P[l] = p.narrow[l] ? 1 : std::max(1, std::min(G, (int)width(l + 1)));
+    for (int l = 0; l < T; ++l) p.P[l] = p.narrow[l] ? 1 : std::max(1, std::min(GG, (int)width(l + 1)));
 
     // ---- 3. barrier schedule: a grid barrier follows transition l unless both it and the next run on CTA 0 alone ----
     uint32_t acc = 0;
     for (int l = 0; l < T; ++l) {
         const int pn = (l + 1 < T) ? p.P[l + 1] : 1;
-        const bool edge = (p.P[l] > 1) || (pn > 1);
+        bool edge = (p.P[l] > 1) || (pn > 1);
+        if (NR > 1) edge = !p.narrow[l] || (l + 1 < T && !p.narrow[l + 1]);   // (a one-CTA wide transition still has to reach the peers)
         p.bar_edge[l] = edge ? 1 : 0;
-        if (edge) acc += (uint32_t)p.P[l];
+        if (edge) acc += (uint32_t)(p.narrow[l] ? NR : p.P[l]);      // a narrow transition runs (and arrives) once per rank
         p.bar_target[l] = acc;
     }
 
@@ -362,6 +365,9 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
             const uint64_t kk2 = (uint64_t)k2 * (uint64_t)k2;
             const int32_t max_rows = (int32_t)std::max<uint64_t>(1, std::min<uint64_t>(65535, ((1ull << 32) - 1) / std::max<uint64_t>(kk2, 1)));
             for (int c = 0; c < P; ++c) {
+                // global CTA c of a wide transition belongs to rank c % NR; narrow ones (P == 1) run on every rank's CTA 0
+                if (NR > 1 && !p.narrow[l] && c % NR != RK) continue;
+                const int lc = p.narrow[l] ? 0 : c / NR;
                 const int32_t ra = cut[(size_t)c], rbnd = cut[(size_t)c + 1];
                 int32_t x = ra;
                 bool first = true;
@@ -447,8 +453,9 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
                     if (y >= rbnd) {
                         h.flags |= TK_BAR;
                         if (p.bar_edge[l]) h.flags |= TK_ARRIVE;
+                        if (NR > 1 && !p.narrow[l]) { h.flags |= TK_PUSH; h.push_i0 = (uint16_t)ra; h.push_i1 = (uint16_t)rbnd; }
                     }
-                    stream[(size_t)c].push_back(h);
+                    stream[(size_t)lc].push_back(h);
                     first = false;
                     x = y;
                 }

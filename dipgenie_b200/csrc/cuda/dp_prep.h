@@ -51,6 +51,12 @@ struct SweepShape {              // kernel geometry the plan is made for
     int delta_max_in = 4096;     // widest in-edge count that still gets a matrix
     int lane_rc = LANE_RC_SMALL; // layers per lane in the lane form (LANE_RC_SMALL or LANE_RC_BIG)
     bool allow_long = false;     // lane form may take destinations with more than 32 in-edges (needs packed keys' kernel)
+    // Row-sharded sweep over `replicas` GPUs (one process each): the plan is made for replicas x grid global CTAs and
+    // keeps the streams of this rank's (global CTA c -> rank c % replicas, local CTA c / replicas).  Narrow transitions
+    // run on the local CTA 0 of every rank; wide transitions are row-split over all global CTAs and every CTA pushes
+    // its rows to the peers (TK_PUSH); every arrival is broadcast to all ranks' counters.
+    int replicas = 1;
+    int rank = 0;
 };
 
 struct DipPlan {

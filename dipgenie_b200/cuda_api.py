@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 from dataclasses import dataclass
-from typing import Optional
+from typing import Optional, Sequence
 
 import numpy as np
 
@@ -253,6 +253,26 @@ class Context:
     def dip_create(self, g: LevelGraph, R: int, slot: Optional[int] = None, ctas: int = 0) -> "DipProblem":
         return DipProblem(self, g, R, slot, ctas)
 
+    def dip_create_sharded(self, g: LevelGraph, R: int, rank: int, world: int, ctas: int = 0) -> "DipProblem":
+        """One rank's part of a diploid DP whose wide transitions are row-split over `world` GPUs (shard.RowShardedDip)."""
+        return DipProblem(self, g, R, None, ctas, shard=(rank, world))
+
+    def dip_sharded_in_process(self, g: LevelGraph, R: int, world: int, ctas: int = 4) -> list:
+        """All `world` ranks of a row-sharded problem as sibling problems on this one GPU (dg_dip_attach_in_process)."""
+        probs = [self.dip_create_sharded(g, R, q, world, ctas) for q in range(world)]
+        arr = (C.c_void_p * world)(*[p.h for p in probs])
+        self.check(self.lib.dg_dip_attach_in_process(C.c_void_p(self.h), arr, C.c_int32(world)), "dg_dip_attach_in_process")
+        return probs
+
+    @staticmethod
+    def run_sharded_siblings(probs) -> list:
+        """arm all, launch all (asynchronous, own streams), collect all."""
+        for p in probs:
+            p.shard_arm()
+        for p in probs:
+            p.run()
+        return [p.result() for p in probs]
+
     def dip_run_many(self, problems) -> float:
         """dg_dip_run_many: run resident problems (distinct slots) together; returns the group's device ms."""
         arr = (C.c_void_p * max(len(problems), 1))(*[p.h for p in problems])
@@ -385,18 +405,43 @@ class HapProblem:
 class DipProblem:
     """A diploid DP problem resident in HBM (dg_dip_*)."""
 
-    def __init__(self, ctx: Context, g: LevelGraph, R: int, slot: Optional[int] = None, ctas: int = 0):
+    IPC_HANDLE_BYTES = 64          # include/dipgenie_cuda.h: DG_IPC_HANDLE_BYTES
+
+    def __init__(self, ctx: Context, g: LevelGraph, R: int, slot: Optional[int] = None, ctas: int = 0,
+                 shard: Optional[tuple] = None):
         self.ctx = ctx
         self.R = R
         self.L = g.n_levels
+        self.shard = shard
         h = C.c_void_p(None)
         args = [C.c_void_p(ctx.h), C.c_int32(g.n_levels), _ptr(g.level_off), _ptr(g.adj_off), _ptr(g.adj_dst), _ptr(g.adj_w),
                 _ptr(g.col_off), _ptr(g.col_val), _ptr(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R)]
-        if slot is None:
+        if shard is not None:      # (rank, world): row-sharded over the GPUs of the node (dg_dip_create_sharded)
+            ctx.check(ctx.lib.dg_dip_create_sharded(*args, C.c_int32(shard[0]), C.c_int32(shard[1]), C.c_int32(ctas), C.byref(h)),
+                      "dg_dip_create_sharded")
+        elif slot is None:
             ctx.check(ctx.lib.dg_dip_create(*args, C.byref(h)), "dg_dip_create")
         else:
             ctx.check(ctx.lib.dg_dip_create_slot(*args, C.c_int32(slot), C.c_int32(ctas), C.byref(h)), "dg_dip_create_slot")
         self.h = h
+
+    def ipc_export(self) -> bytes:
+        """dg_dip_ipc_export: the 4 CUDA IPC handles (layer tiles, predecessor codes, counters) the peers map."""
+        buf = (C.c_uint8 * (4 * self.IPC_HANDLE_BYTES))()
+        self.ctx.check(self.ctx.lib.dg_dip_ipc_export(C.c_void_p(self.ctx.h), self.h, buf), "dg_dip_ipc_export")
+        return bytes(buf)
+
+    def ipc_attach(self, all_handles: Sequence[bytes]):
+        """dg_dip_ipc_attach: `all_handles[q]` = rank q's ipc_export()."""
+        blob = b"".join(all_handles)
+        if len(blob) != self.shard[1] * 4 * self.IPC_HANDLE_BYTES:
+            raise ValueError("ipc_attach: need one 256-byte handle block per rank")
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self.ctx.check(self.ctx.lib.dg_dip_ipc_attach(C.c_void_p(self.ctx.h), self.h, buf), "dg_dip_ipc_attach")
+
+    def shard_arm(self):
+        """dg_dip_shard_arm: reset counters and level 0; every rank must do this and pass a host barrier before run()."""
+        self.ctx.check(self.ctx.lib.dg_dip_shard_arm(C.c_void_p(self.ctx.h), self.h), "dg_dip_shard_arm")
 
     def run(self, checksums: bool = False, profile: bool = False):
         flags = (1 if checksums else 0) | (2 if profile else 0)

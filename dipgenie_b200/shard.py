@@ -1,5 +1,10 @@
-"""Multi-GPU driver for independent samples: one process per GPU, samples dealt to ranks with no
-data-path collective; `torch.distributed` only carries the small result records back to rank 0.
+"""Multi-GPU drivers, one process per GPU.
+
+1. Independent samples: dealt to ranks with no data-path collective; `torch.distributed` only carries the small result
+   records back to rank 0 (shard_indices / merge_shards / run_sharded).
+2. One large diploid DP, row-sharded (north_star: "h1-row tiles of the diploid matrix"): RowShardedDip.  The exchange is
+   fused into the sweep kernel (rows and barrier arrivals go through NVLink peer mappings); `torch.distributed` only
+   all-gathers the CUDA IPC handles once and provides the host barrier before each launch.
 
 The reference runs one DipGenie process per sample (data/run_DipGenie_batch.sh:21-39: the 22-sample
 leave-one-out study); here a rank takes its share of the samples and runs them side by side on its GPU with
@@ -43,3 +48,39 @@ def run_sharded(samples: Sequence, run_local: Callable[[list], list], dist=None)
     if rank != 0:
         return None
     return merge_shards(len(samples), gathered, world)
+
+
+class RowShardedDip:
+    """One diploid DP over all the GPUs of the process group (include/dipgenie_cuda.h: dg_dip_create_sharded).
+
+    Every rank passes the same LevelGraph.  Wide level transitions (approximator.cpp:627-701) are split by destination
+    row over world x ctas CTAs; narrow ones run redundantly on every rank; every rank ends with the full result.
+
+        prob = RowShardedDip(ctx, graph, R, dist)      # collective: all ranks
+        out = prob.run()                               # collective; the same dict on every rank
+    """
+
+    def __init__(self, ctx, graph, R: int, dist, ctas: int = 0):
+        if dist is None or not dist.is_initialized():
+            raise RuntimeError("RowShardedDip needs an initialised torch.distributed process group")
+        self.dist = dist
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.problem = ctx.dip_create_sharded(graph, R, self.rank, self.world, ctas)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.problem.ipc_export())
+        self.problem.ipc_attach(handles)
+
+    def run(self) -> dict:
+        self.problem.shard_arm()
+        self.dist.barrier()            # every rank's counters are reset before any sweep can arrive on them
+        self.problem.run()
+        out = self.problem.result()
+        self.dist.barrier()            # nobody re-arms while a peer's kernel may still be running
+        return out
+
+    def stats(self) -> dict:
+        return self.problem.stats()
+
+    def close(self):
+        self.dist.barrier()
+        self.problem.close()

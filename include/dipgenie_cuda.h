@@ -118,6 +118,28 @@ typedef struct {
 int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip_output_t* out, int32_t max_concurrent,
                         int32_t ctas_per_sample);
 
+/* ---- Row-sharded diploid DP over the GPUs of one node (north_star: "h1-row tiles of the diploid matrix" for large
+ * panels).  One process per GPU.  Every rank passes the SAME graph; wide level transitions are split by
+ * destination row (P1 axis) over world x ctas CTAs, each CTA writes its rows of the layer and of the predecessor
+ * codes into every peer's buffers over NVLink and all grid barriers span the GPUs; narrow transitions run redundantly
+ * on every rank.  Every rank ends with the complete result (dg_dip_result).  Protocol, per rank:
+ *   dg_dip_create_sharded -> dg_dip_ipc_export -> (all-gather the world x 4 handles, e.g. torch.distributed)
+ *   -> dg_dip_ipc_attach -> { dg_dip_shard_arm -> host barrier over the ranks -> dg_dip_run -> dg_dip_result }*
+ * The sweeps of all ranks must be launched concurrently (they spin on each other).  ctas = 0: one CTA per SM. */
+#define DG_IPC_HANDLE_BYTES 64
+#define DG_MAX_SHARD_RANKS 8
+int dg_dip_create_sharded(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
+                          const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off, const int32_t* col_val,
+                          const uint8_t* colour_is_hom, int32_t n_colours, int32_t R, int32_t rank, int32_t world,
+                          int32_t ctas, dg_dip** out);
+int dg_dip_ipc_export(dg_ctx* ctx, dg_dip* d, uint8_t* handles /* [4 * DG_IPC_HANDLE_BYTES] */);
+int dg_dip_ipc_attach(dg_ctx* ctx, dg_dip* d, const uint8_t* all_handles /* [world * 4 * DG_IPC_HANDLE_BYTES], rank-major */);
+int dg_dip_shard_arm(dg_ctx* ctx, dg_dip* d);
+/* The same protocol with all `world` ranks as sibling problems of one process on one GPU (no IPC; tests and
+ * single-GPU boxes): replaces export/attach; then arm every sibling, dg_dip_run every sibling (asynchronous, own
+ * streams), dg_dip_result. */
+int dg_dip_attach_in_process(dg_ctx* ctx, dg_dip** all, int32_t world);
+
 /* The same with the graphs resident in HBM between runs (bench.py times dg_dip_run_many alone): a problem
  * created in `slot` owns that slot's stream and a sweep grid of `ctas` CTAs (0 = 8); dg_dip_run_many starts the
  * n problems together (distinct slots run concurrently), waits for all of them and returns the device time of

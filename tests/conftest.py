@@ -83,6 +83,24 @@ class DpEmu:
                                tasks_lanes=int(counts[6]), tasks_long=int(counts[7])))
 
 
+    def dp_diploid_sharded(self, g, R, n_ranks, grid=4, tile_cells=0):
+        """The row-sharded sweep over `n_ranks` emulated GPUs (dg_dip_create_sharded)."""
+        counts = np.zeros(8, np.int64)
+        val, sh, n1, n2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        p1 = np.zeros(2 * (R + 2), np.int32)
+        p2 = np.zeros(2 * (R + 2), np.int32)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = self.lib.emu_dp_diploid_sharded(
+            C.c_int32(g.n_levels), P(g.level_off), P(g.adj_off), P(g.adj_dst), P(g.adj_w), P(g.col_off), P(g.col_val),
+            P(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R), C.c_int32(n_ranks), C.c_int32(grid),
+            C.c_int32(tile_cells), C.byref(val), C.byref(sh), P(p1), C.byref(n1), P(p2), C.byref(n2), P(counts))
+        if rc != 0:
+            raise RuntimeError(f"emu_dp_diploid_sharded rc={rc}")
+        return dict(value=val.value, s_het=sh.value, p1_edges=p1[: 2 * n1.value].reshape(-1, 2).copy(),
+                    p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy(),
+                    modes=dict(narrow=int(counts[0]), wide=int(counts[1]), wide_tasks=int(counts[2]), pushes=int(counts[3])))
+
+
 @pytest.fixture(scope="session")
 def dp_emu():
     return DpEmu()

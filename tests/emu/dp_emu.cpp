@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <memory>
 #include <vector>
 
 #include "../../dipgenie_b200/csrc/cuda/dp_cell.h"
@@ -258,138 +259,80 @@ int lane_items(Emu& e, const uint8_t* slot, const TaskHdr& h, const int32_t* src
     return 0;
 }
 
+// One task, as the producer warp (three bulk copies into the slot) and the compute warps execute it.  `c` = the local
+// CTA running it; `h` receives the header as the compute warps see it.
 template <class PredT>
-int run(const DipPlan& p, const SweepShape& sh, int trace_T, bool no_pack, int64_t* n_lane_tasks, int32_t* sink_value, int32_t* sink_s_het, int32_t* p1,
-        int32_t* n1, int32_t* p2, int32_t* n2, uint64_t* level_checksum, uint64_t* level_live) {
-    const int R = p.R, L = p.L;
-    Emu e(p, sh);
-    e.shift = (p.value_bound < KEY_VALUE_LIMIT && !no_pack) ? KEY_SHIFT : 0;    // same rule as dip_plan_host
-    std::vector<PredT> pred((size_t)p.pred_off[L]);
-    const size_t widest = (size_t)(R + sh.lane_rc) * p.kmax * p.kmax;
-    // poison values make a wrong tile-placement flag visible
-    e.g0.assign(widest, 0x5A5A5A5A); e.g1.assign(widest, 0x5A5A5A5A);
-    e.s0.assign(sh.tile_cells, 0x3C3C3C3C); e.s1.assign(sh.tile_cells, 0x3C3C3C3C);
-    for (int r = 0; r <= R; ++r) { e.g0[r] = 0; e.s0[r] = 0; }
-    e.sum.assign(L, FOLD_BASIS); e.live.assign(L, 0);
-
-    // K4: pair-score matrices (dip_delta_kernel)
-    e.delta.assign((size_t)p.delta_elems, 0xDEAD);
-    for (int l : p.delta_list) {
-        const int32_t mid = p.level_off[l + 1], e0 = p.in_off[mid];
-        const uint32_t n_in = (uint32_t)(p.in_off[p.level_off[l + 2]] - e0);
-        if (p.delta_off[l] % 8 != 0) return -20;
-        uint16_t* D = e.delta.data() + p.delta_off[l];
-        for (uint32_t x = 0; x < n_in * n_in; ++x) {
-            const uint32_t e1 = x / n_in, e2 = x - e1 * n_in;
-            D[x] = (uint16_t)mask_delta(p.lvlW[l], p.masks.data() + p.msrc_off[l], p.masks.data() + p.mdst_off[l],
-                                        (int)(p.in_edge[e0 + e1] & 0xFFFFu), (int)(p.in_edge[e0 + e2] & 0xFFFFu),
-                                        (int)p.in_dst[e0 + e1], (int)p.in_dst[e0 + e2]);
+int exec_task(Emu& e, const DipPlan& p, const SweepShape& sh, const TaskHdr& gh, int l, int c, std::vector<uint8_t>& slot,
+              std::vector<uint8_t>& row_done, PredT* pl, TaskHdr& h) {
+    const int R = p.R;
+        // --- what the producer warp does: three bulk copies into the slot ---
+        if ((size_t)sizeof(TaskHdr) + gh.rec_bytes + gh.delta_bytes > (size_t)sh.slot_bytes) return -10;
+        if (gh.rec_bytes % 16 || gh.delta_bytes % 16) return -10;
+        std::fill(slot.begin(), slot.end(), (uint8_t)0xEE);
+        memcpy(slot.data(), &gh, sizeof(TaskHdr));
+        if (gh.rec_bytes) {
+            if ((size_t)gh.rec_off16 * 16 + gh.rec_bytes > p.records.size()) return -10;
+            memcpy(slot.data() + sizeof(TaskHdr), p.records.data() + (size_t)gh.rec_off16 * 16, gh.rec_bytes);
         }
-    }
-
-    // K5: task streams, executed level by level, CTA by CTA (any order the barriers allow is equivalent)
-    const int G = p.grid;
-    std::vector<int64_t> cur(p.task_begin.begin(), p.task_begin.end() - 1);
-    std::vector<uint8_t> slot((size_t)sh.slot_bytes + 16);
-    uint32_t counter = 0;
-    for (int l = 0; l + 1 < L; ++l) {
-        PredT* pl = pred.data() + p.pred_off[l + 1];
-        std::vector<uint8_t> row_done((size_t)(p.level_off[l + 2] - p.level_off[l + 1]), 0);
-        e.written.assign((size_t)(R + 1) * row_done.size() * row_done.size(), 0);
-        uint32_t arrivals = 0;
-        int participants = 0;
-        for (int c = 0; c < G; ++c) {
-            bool first = true, closed = false;
-            while (cur[c] < p.task_begin[(size_t)c + 1] && p.tasks[(size_t)cur[c]].level == l) {
-                const TaskHdr& gh = p.tasks[(size_t)cur[c]++];
-                if (closed) return -30;                         // a task after the CTA's TK_BAR task of this level
-                // --- what the producer warp does: three bulk copies into the slot ---
-                if ((size_t)sizeof(TaskHdr) + gh.rec_bytes + gh.delta_bytes > (size_t)sh.slot_bytes) return -10;
-                if (gh.rec_bytes % 16 || gh.delta_bytes % 16) return -10;
-                std::fill(slot.begin(), slot.end(), (uint8_t)0xEE);
-                memcpy(slot.data(), &gh, sizeof(TaskHdr));
-                if (gh.rec_bytes) {
-                    if ((size_t)gh.rec_off16 * 16 + gh.rec_bytes > p.records.size()) return -10;
-                    memcpy(slot.data() + sizeof(TaskHdr), p.records.data() + (size_t)gh.rec_off16 * 16, gh.rec_bytes);
-                }
-                if (gh.delta_bytes) {
-                    if ((size_t)gh.delta_off16 * 8 + gh.delta_bytes / 2 > e.delta.size() + 8) return -10;
-                    const size_t avail = (e.delta.size() - (size_t)gh.delta_off16 * 8) * 2;
-                    memcpy(slot.data() + sizeof(TaskHdr) + gh.rec_bytes, e.delta.data() + (size_t)gh.delta_off16 * 8,
-                           std::min<size_t>(gh.delta_bytes, avail));
-                }
-                // --- what the compute warps do ---
-                TaskHdr h;
-                memcpy(&h, slot.data(), sizeof h);
-                const bool needs_wait = l > 0 && p.bar_edge[l - 1];
-                if (first) {
-                    if (needs_wait != ((h.flags & TK_WAIT) != 0)) return -11;
-                    if (needs_wait && (h.wait_target != p.bar_target[l - 1] || counter < h.wait_target)) return -11;   // would race / dead-lock
-                } else if (h.flags & TK_WAIT) return -11;
-                first = false;
-                if (c >= p.P[l]) return -12;
-                const bool ssm = h.flags & TK_SRC_SMEM, dsm = h.flags & TK_DST_SMEM;
-                if ((ssm || dsm) && (!p.narrow[l] || c != 0)) return -12;
-                const size_t lp = (size_t)((R + sh.lane_rc) / sh.lane_rc) * sh.lane_rc;       // whole lane-form chunks
-                if ((ssm && lp * h.k * h.k > (size_t)sh.tile_cells) || (dsm && lp * h.k2 * h.k2 > (size_t)sh.tile_cells)) return -13;
-                if (h.pred_off2 != p.pred_off[l + 1] || h.i0 >= h.i1 || h.i1 > h.k2) return -14;
-                if ((uint64_t)(h.i1 - h.i0) * h.k2 * h.k2 >= (1ull << 32)) return -14;    // div_magic exactness
-                const int32_t* src = ssm ? ((l & 1) ? e.s1.data() : e.s0.data()) : ((l & 1) ? e.g1.data() : e.g0.data());
-                int32_t* dst = dsm ? ((l & 1) ? e.s0.data() : e.s1.data()) : ((l & 1) ? e.g0.data() : e.g1.data());
-                for (int x = h.i0; x < h.i1; ++x) { if (row_done[x]) return -16; row_done[x] = 1; }
-                if (h.flags & TK_LANES) {
-                    if ((h.flags & TK_REC_GLOBAL) || ssm != dsm) return -60;
-                    if (h.rc != ((h.flags & TK_LONG) ? LANE_RC_SMALL : e.sh.lane_rc)) return -61;
-                    const int lrc = h.rc == LANE_RC_BIG ? lane_items<PredT, LANE_RC_BIG>(e, slot.data(), h, src, dst, pl)
-                                                        : lane_items<PredT, LANE_RC_SMALL>(e, slot.data(), h, src, dst, pl);
-                    if (lrc) return lrc;
-                    ++e.n_lane_tasks;
-                } else if (!(h.flags & TK_REC_GLOBAL)) {
-                    TransitionT<uint16_t> t;
-                    t.k = h.k; t.k2 = h.k2;
-                    t.in_off = reinterpret_cast<const uint16_t*>(slot.data() + sizeof(TaskHdr));
-                    t.in_edge = reinterpret_cast<const uint32_t*>(slot.data() + sizeof(TaskHdr) + rec_edge_offset(h.k2));
-                    t.delta = nullptr; t.dstride = h.n_in; t.e1_base = 0; t.e2_base = 0; t.dshift = e.shift; t.W = 0; t.msrc = t.mdst = nullptr;
-                    if (h.flags & TK_DELTA_STAGED) {
-                        t.delta = reinterpret_cast<const uint16_t*>(slot.data() + sizeof(TaskHdr) + h.rec_bytes) + h.delta_skew;
-                        t.e1_base = (int32_t)t.in_off[h.i0];
-                    } else if (h.flags & TK_DELTA) {
-                        t.delta = e.delta.data() + p.delta_off[l];
-                    } else if (h.flags & TK_DELTA_MASKS) {
-                        t.W = p.lvlW[l]; t.msrc = p.masks.data() + p.msrc_off[l]; t.mdst = p.masks.data() + p.mdst_off[l];
-                    }
-                    by_dm<PredT, uint16_t>(e, t, h, src, dst, pl);
-                } else {
-                    const int32_t mid = p.level_off[l + 1], ebase = p.in_off[mid];
-                    TransitionT<int32_t> t;
-                    t.k = h.k; t.k2 = h.k2;
-                    t.in_off = p.in_off.data() + mid; t.in_edge = p.in_edge.data();
-                    t.delta = nullptr; t.dstride = p.in_off[p.level_off[l + 2]] - ebase; t.e1_base = ebase; t.e2_base = ebase; t.dshift = e.shift;
-                    t.W = 0; t.msrc = t.mdst = nullptr;
-                    if (h.flags & TK_DELTA) t.delta = e.delta.data() + p.delta_off[l];
-                    else if (h.flags & TK_DELTA_MASKS) {
-                        t.W = p.lvlW[l]; t.msrc = p.masks.data() + p.msrc_off[l]; t.mdst = p.masks.data() + p.mdst_off[l];
-                    }
-                    by_dm<PredT, int32_t>(e, t, h, src, dst, pl);
-                }
-                if (h.flags & TK_BAR) closed = true;
-                if (h.flags & TK_ARRIVE) { if (!(h.flags & TK_BAR)) return -17; ++arrivals; }
+        if (gh.delta_bytes) {
+            if ((size_t)gh.delta_off16 * 8 + gh.delta_bytes / 2 > e.delta.size() + 8) return -10;
+            const size_t avail = (e.delta.size() - (size_t)gh.delta_off16 * 8) * 2;
+            memcpy(slot.data() + sizeof(TaskHdr) + gh.rec_bytes, e.delta.data() + (size_t)gh.delta_off16 * 8,
+                   std::min<size_t>(gh.delta_bytes, avail));
+        }
+        // --- what the compute warps do ---
+        memcpy(&h, slot.data(), sizeof h);
+        const bool ssm = h.flags & TK_SRC_SMEM, dsm = h.flags & TK_DST_SMEM;
+        if ((ssm || dsm) && (!p.narrow[l] || c != 0)) return -12;
+        const size_t lp = (size_t)((R + sh.lane_rc) / sh.lane_rc) * sh.lane_rc;       // whole lane-form chunks
+        if ((ssm && lp * h.k * h.k > (size_t)sh.tile_cells) || (dsm && lp * h.k2 * h.k2 > (size_t)sh.tile_cells)) return -13;
+        if (h.pred_off2 != p.pred_off[l + 1] || h.i0 >= h.i1 || h.i1 > h.k2) return -14;
+        if ((uint64_t)(h.i1 - h.i0) * h.k2 * h.k2 >= (1ull << 32)) return -14;    // div_magic exactness
+        const int32_t* src = ssm ? ((l & 1) ? e.s1.data() : e.s0.data()) : ((l & 1) ? e.g1.data() : e.g0.data());
+        int32_t* dst = dsm ? ((l & 1) ? e.s0.data() : e.s1.data()) : ((l & 1) ? e.g0.data() : e.g1.data());
+        for (int x = h.i0; x < h.i1; ++x) { if (row_done[x]) return -16; row_done[x] = 1; }
+        if (h.flags & TK_LANES) {
+            if ((h.flags & TK_REC_GLOBAL) || ssm != dsm) return -60;
+            if (h.rc != ((h.flags & TK_LONG) ? LANE_RC_SMALL : e.sh.lane_rc)) return -61;
+            const int lrc = h.rc == LANE_RC_BIG ? lane_items<PredT, LANE_RC_BIG>(e, slot.data(), h, src, dst, pl)
+                                                : lane_items<PredT, LANE_RC_SMALL>(e, slot.data(), h, src, dst, pl);
+            if (lrc) return lrc;
+            ++e.n_lane_tasks;
+        } else if (!(h.flags & TK_REC_GLOBAL)) {
+            TransitionT<uint16_t> t;
+            t.k = h.k; t.k2 = h.k2;
+            t.in_off = reinterpret_cast<const uint16_t*>(slot.data() + sizeof(TaskHdr));
+            t.in_edge = reinterpret_cast<const uint32_t*>(slot.data() + sizeof(TaskHdr) + rec_edge_offset(h.k2));
+            t.delta = nullptr; t.dstride = h.n_in; t.e1_base = 0; t.e2_base = 0; t.dshift = e.shift; t.W = 0; t.msrc = t.mdst = nullptr;
+            if (h.flags & TK_DELTA_STAGED) {
+                t.delta = reinterpret_cast<const uint16_t*>(slot.data() + sizeof(TaskHdr) + h.rec_bytes) + h.delta_skew;
+                t.e1_base = (int32_t)t.in_off[h.i0];
+            } else if (h.flags & TK_DELTA) {
+                t.delta = e.delta.data() + p.delta_off[l];
+            } else if (h.flags & TK_DELTA_MASKS) {
+                t.W = p.lvlW[l]; t.msrc = p.masks.data() + p.msrc_off[l]; t.mdst = p.masks.data() + p.mdst_off[l];
             }
-            if (!first) { ++participants; if (!closed) return -18; }
-        }
-        for (uint8_t d : row_done) if (!d) return -19;
-        for (uint8_t d : e.written) if (!d) return -25;             // every cell of the level was stored              // every destination row belongs to exactly one task
-        if (participants != p.P[l]) return -21;
-        if (p.bar_edge[l] ? (arrivals != (uint32_t)p.P[l]) : (arrivals != 0)) return -22;
-        counter += arrivals;
-        if (counter != p.bar_target[l]) return -15;
-        if (level_checksum) { level_checksum[l + 1] = e.sum[l + 1]; level_live[l + 1] = e.live[l + 1]; }
-    }
-    for (int c = 0; c < G; ++c) if (cur[c] != p.task_begin[(size_t)c + 1]) return -23;
-    if (e.bad_rc) return -24;
-    if (n_lane_tasks) *n_lane_tasks = e.n_lane_tasks;
+            by_dm<PredT, uint16_t>(e, t, h, src, dst, pl);
+        } else {
+            const int32_t mid = p.level_off[l + 1], ebase = p.in_off[mid];
+            TransitionT<int32_t> t;
+            t.k = h.k; t.k2 = h.k2;
+            t.in_off = p.in_off.data() + mid; t.in_edge = p.in_edge.data();
+            t.delta = nullptr; t.dstride = p.in_off[p.level_off[l + 2]] - ebase; t.e1_base = ebase; t.e2_base = ebase; t.dshift = e.shift;
+            t.W = 0; t.msrc = t.mdst = nullptr;
+            if (h.flags & TK_DELTA) t.delta = e.delta.data() + p.delta_off[l];
+            else if (h.flags & TK_DELTA_MASKS) {
+                t.W = p.lvlW[l]; t.msrc = p.masks.data() + p.msrc_off[l]; t.mdst = p.masks.data() + p.mdst_off[l];
+            }
+            by_dm<PredT, int32_t>(e, t, h, src, dst, pl);
+        }    return 0;
+}
 
-    // K7: checkpointed traceback (dip_anc_kernel / dip_hop_kernel / dip_seg_kernel / dip_merge_kernel)
+// K7: checkpointed traceback (dip_anc_kernel / dip_hop_kernel / dip_seg_kernel / dip_merge_kernel)
+template <class PredT>
+int traceback(const DipPlan& p, const Emu& e, const std::vector<PredT>& pred, int trace_T, int32_t* sink_value, int32_t* sink_s_het,
+              int32_t* p1, int32_t* n1, int32_t* p2, int32_t* n2) {
+    const int R = p.R, L = p.L;
     const size_t ks = (size_t)(p.level_off[L] - p.level_off[L - 1]);
     const std::vector<int32_t>& last = ((L - 1) & 1) ? e.g1 : e.g0;     // the sink layer must be in global memory
     *sink_value = last[(size_t)R * ks * ks];   // cell (r=R,0,0) of the last level (:730, :775)
@@ -442,6 +385,216 @@ int run(const DipPlan& p, const SweepShape& sh, int trace_T, bool no_pack, int64
     return 0;
 }
 
+template <class PredT>
+int run(const DipPlan& p, const SweepShape& sh, int trace_T, bool no_pack, int64_t* n_lane_tasks, int32_t* sink_value, int32_t* sink_s_het, int32_t* p1,
+        int32_t* n1, int32_t* p2, int32_t* n2, uint64_t* level_checksum, uint64_t* level_live) {
+    const int R = p.R, L = p.L;
+    Emu e(p, sh);
+    e.shift = (p.value_bound < KEY_VALUE_LIMIT && !no_pack) ? KEY_SHIFT : 0;    // same rule as dip_plan_host
+    std::vector<PredT> pred((size_t)p.pred_off[L]);
+    const size_t widest = (size_t)(R + sh.lane_rc) * p.kmax * p.kmax;
+    // poison values make a wrong tile-placement flag visible
+    e.g0.assign(widest, 0x5A5A5A5A); e.g1.assign(widest, 0x5A5A5A5A);
+    e.s0.assign(sh.tile_cells, 0x3C3C3C3C); e.s1.assign(sh.tile_cells, 0x3C3C3C3C);
+    for (int r = 0; r <= R; ++r) { e.g0[r] = 0; e.s0[r] = 0; }
+    e.sum.assign(L, FOLD_BASIS); e.live.assign(L, 0);
+
+    // K4: pair-score matrices (dip_delta_kernel)
+    e.delta.assign((size_t)p.delta_elems, 0xDEAD);
+    for (int l : p.delta_list) {
+        const int32_t mid = p.level_off[l + 1], e0 = p.in_off[mid];
+        const uint32_t n_in = (uint32_t)(p.in_off[p.level_off[l + 2]] - e0);
+        if (p.delta_off[l] % 8 != 0) return -20;
+        uint16_t* D = e.delta.data() + p.delta_off[l];
+        for (uint32_t x = 0; x < n_in * n_in; ++x) {
+            const uint32_t e1 = x / n_in, e2 = x - e1 * n_in;
+            D[x] = (uint16_t)mask_delta(p.lvlW[l], p.masks.data() + p.msrc_off[l], p.masks.data() + p.mdst_off[l],
+                                        (int)(p.in_edge[e0 + e1] & 0xFFFFu), (int)(p.in_edge[e0 + e2] & 0xFFFFu),
+                                        (int)p.in_dst[e0 + e1], (int)p.in_dst[e0 + e2]);
+        }
+    }
+
+    // K5: task streams, executed level by level, CTA by CTA (any order the barriers allow is equivalent)
+    const int G = p.grid;
+    std::vector<int64_t> cur(p.task_begin.begin(), p.task_begin.end() - 1);
+    std::vector<uint8_t> slot((size_t)sh.slot_bytes + 16);
+    uint32_t counter = 0;
+    for (int l = 0; l + 1 < L; ++l) {
+        PredT* pl = pred.data() + p.pred_off[l + 1];
+        std::vector<uint8_t> row_done((size_t)(p.level_off[l + 2] - p.level_off[l + 1]), 0);
+        e.written.assign((size_t)(R + 1) * row_done.size() * row_done.size(), 0);
+        uint32_t arrivals = 0;
+        int participants = 0;
+        for (int c = 0; c < G; ++c) {
+            bool first = true, closed = false;
+            while (cur[c] < p.task_begin[(size_t)c + 1] && p.tasks[(size_t)cur[c]].level == l) {
+                const TaskHdr& gh = p.tasks[(size_t)cur[c]++];
+                if (closed) return -30;                         // a task after the CTA's TK_BAR task of this level
+                TaskHdr h;
+                if (int rc = exec_task<PredT>(e, p, sh, gh, l, c, slot, row_done, pl, h)) return rc;
+                const bool needs_wait = l > 0 && p.bar_edge[l - 1];
+                if (first) {
+                    if (needs_wait != ((h.flags & TK_WAIT) != 0)) return -11;
+                    if (needs_wait && (h.wait_target != p.bar_target[l - 1] || counter < h.wait_target)) return -11;   // would race / dead-lock
+                } else if (h.flags & TK_WAIT) return -11;
+                first = false;
+                if (c >= p.P[l]) return -12;
+                if (h.flags & TK_BAR) closed = true;
+                if (h.flags & TK_ARRIVE) { if (!(h.flags & TK_BAR)) return -17; ++arrivals; }
+            }
+            if (!first) { ++participants; if (!closed) return -18; }
+        }
+        for (uint8_t d : row_done) if (!d) return -19;
+        for (uint8_t d : e.written) if (!d) return -25;             // every cell of the level was stored              // every destination row belongs to exactly one task
+        if (participants != p.P[l]) return -21;
+        if (p.bar_edge[l] ? (arrivals != (uint32_t)p.P[l]) : (arrivals != 0)) return -22;
+        counter += arrivals;
+        if (counter != p.bar_target[l]) return -15;
+        if (level_checksum) { level_checksum[l + 1] = e.sum[l + 1]; level_live[l + 1] = e.live[l + 1]; }
+    }
+    for (int c = 0; c < G; ++c) if (cur[c] != p.task_begin[(size_t)c + 1]) return -23;
+    if (e.bad_rc) return -24;
+    if (n_lane_tasks) *n_lane_tasks = e.n_lane_tasks;
+
+    return traceback<PredT>(p, e, pred, trace_T, sink_value, sink_s_het, p1, n1, p2, n2);
+}
+
+// The row-sharded sweep (dg_dip_create_sharded): N ranks, each with its own plan (same graph, its own rank), layers,
+// predecessor codes and counter; levels are executed rank by rank, then the TK_PUSH row copies and the broadcast
+// arrivals are applied.  Checks: every destination row of a wide transition belongs to exactly one task over all ranks,
+// every rank's counter meets the (identical) barrier targets, all ranks end with identical layers and codes.
+template <class PredT>
+int run_sharded(const DipGraphView& g, const SweepShape& sh0, int N, int trace_T, bool no_pack, int32_t* sink_value, int32_t* sink_s_het,
+                int32_t* p1, int32_t* n1, int32_t* p2, int32_t* n2, int64_t* counts) {
+    std::vector<std::unique_ptr<DipPlan>> plans;
+    std::vector<SweepShape> shapes((size_t)N, sh0);
+    std::vector<std::unique_ptr<Emu>> emus;
+    std::vector<std::vector<PredT>> preds((size_t)N);
+    for (int r = 0; r < N; ++r) {
+        plans.emplace_back(new DipPlan());
+        if (!build_dip_plan(g, *plans[r])) return -1;
+        shapes[r].replicas = N; shapes[r].rank = r;
+        plan_tasks(*plans[r], shapes[r]);
+    }
+    const DipPlan& p0 = *plans[0];
+    const int R = p0.R, L = p0.L, G = p0.grid;
+    const size_t widest = (size_t)(R + sh0.lane_rc) * p0.kmax * p0.kmax;
+    for (int r = 0; r < N; ++r) {
+        const DipPlan& p = *plans[r];
+        if (p.bar_target != p0.bar_target || p.bar_edge != p0.bar_edge || p.P != p0.P || p.narrow != p0.narrow) return -70;
+        emus.emplace_back(new Emu(p, shapes[r]));
+        Emu& e = *emus[r];
+        e.shift = (p.value_bound < KEY_VALUE_LIMIT && !no_pack) ? KEY_SHIFT : 0;
+        preds[r].assign((size_t)p.pred_off[L], (PredT)0x7B7B);
+        e.g0.assign(widest, 0x5A5A5A5A); e.g1.assign(widest, 0x5A5A5A5A);
+        e.s0.assign(sh0.tile_cells, 0x3C3C3C3C); e.s1.assign(sh0.tile_cells, 0x3C3C3C3C);
+        for (int x = 0; x <= R; ++x) { e.g0[x] = 0; e.s0[x] = 0; }
+        e.sum.assign(L, FOLD_BASIS); e.live.assign(L, 0);
+        e.delta.assign((size_t)p.delta_elems, 0xDEAD);
+        for (int l : p.delta_list) {
+            const int32_t mid = p.level_off[l + 1], e0 = p.in_off[mid];
+            const uint32_t n_in = (uint32_t)(p.in_off[p.level_off[l + 2]] - e0);
+            uint16_t* D = e.delta.data() + p.delta_off[l];
+            for (uint32_t x = 0; x < n_in * n_in; ++x) {
+                const uint32_t e1 = x / n_in, e2 = x - e1 * n_in;
+                D[x] = (uint16_t)mask_delta(p.lvlW[l], p.masks.data() + p.msrc_off[l], p.masks.data() + p.mdst_off[l],
+                                            (int)(p.in_edge[e0 + e1] & 0xFFFFu), (int)(p.in_edge[e0 + e2] & 0xFFFFu),
+                                            (int)p.in_dst[e0 + e1], (int)p.in_dst[e0 + e2]);
+            }
+        }
+    }
+    std::vector<std::vector<int64_t>> cur((size_t)N);
+    for (int r = 0; r < N; ++r) cur[r].assign(plans[r]->task_begin.begin(), plans[r]->task_begin.end() - 1);
+    std::vector<uint8_t> slot((size_t)sh0.slot_bytes + 16);
+    std::vector<uint32_t> counter((size_t)N, 0);
+    int64_t n_push = 0, n_wide_tasks = 0;
+    for (int l = 0; l + 1 < L; ++l) {
+        const size_t k2 = (size_t)(p0.level_off[l + 2] - p0.level_off[l + 1]);
+        const bool narrow = p0.narrow[l] != 0;
+        std::vector<uint8_t> rows_shared(k2, 0);
+        uint32_t arrivals = 0;
+        int participants = 0;
+        struct Push { int rank; int i0, i1; };
+        std::vector<Push> pushes;
+        for (int r = 0; r < N; ++r) {
+            const DipPlan& p = *plans[r];
+            Emu& e = *emus[r];
+            PredT* pl = preds[r].data() + p.pred_off[l + 1];
+            std::vector<uint8_t> rows_own(k2, 0);
+            std::vector<uint8_t>& row_done = narrow ? rows_own : rows_shared;
+            e.written.assign((size_t)(R + 1) * k2 * k2, 0);
+            for (int c = 0; c < G; ++c) {
+                bool first = true, closed = false;
+                while (cur[r][c] < p.task_begin[(size_t)c + 1] && p.tasks[(size_t)cur[r][c]].level == l) {
+                    const TaskHdr& gh = p.tasks[(size_t)cur[r][c]++];
+                    if (closed) return -30;
+                    TaskHdr h;
+                    if (int rc = exec_task<PredT>(e, p, shapes[r], gh, l, c, slot, row_done, pl, h)) return rc;
+                    const bool needs_wait = l > 0 && p.bar_edge[l - 1];
+                    if (first) {
+                        if (needs_wait != ((h.flags & TK_WAIT) != 0)) return -11;
+                        if (needs_wait && (h.wait_target != p.bar_target[l - 1] || counter[r] < h.wait_target)) return -11;
+                    } else if (h.flags & TK_WAIT) return -11;
+                    first = false;
+                    if (narrow ? c != 0 : (c * N + r >= p.P[l])) return -12;          // local CTA c of rank r = global CTA c * N + r
+                    if (!narrow) ++n_wide_tasks;
+                    if (h.flags & TK_BAR) closed = true;
+                    if (h.flags & TK_ARRIVE) { if (!(h.flags & TK_BAR)) return -17; ++arrivals; }
+                    if (((h.flags & TK_PUSH) != 0) != (!narrow && (h.flags & TK_BAR))) return -71;
+                    if (h.flags & TK_PUSH) {
+                        if (h.flags & TK_DST_SMEM) return -72;
+                        if (h.push_i0 > h.i0 || h.push_i1 != h.i1) return -72;       // the CTA's whole range ends with this task
+                        pushes.push_back({r, (int)h.push_i0, (int)h.push_i1});
+                        ++n_push;
+                    }
+                }
+                if (!first) { ++participants; if (!closed) return -18; }
+            }
+            if (narrow) {
+                for (uint8_t d : rows_own) if (!d) return -19;
+                for (uint8_t d : e.written) if (!d) return -25;
+            }
+        }
+        if (!narrow) for (uint8_t d : rows_shared) if (!d) return -19;
+        if (participants != (narrow ? N : p0.P[l])) return -21;
+        if (p0.bar_edge[l] ? (arrivals != (uint32_t)(narrow ? N : p0.P[l])) : (arrivals != 0)) return -22;
+        // the pushes: rows of layer l+1 and of its codes, from the owner's global tile to every peer's
+        std::vector<uint8_t> pushed(k2, 0);
+        for (const Push& q : pushes) {
+            const std::vector<int32_t>& src = (l & 1) ? emus[q.rank]->g0 : emus[q.rank]->g1;
+            const PredT* ps = preds[q.rank].data() + p0.pred_off[l + 1];
+            for (int x = q.i0; x < q.i1; ++x) { if (pushed[x]) return -73; pushed[x] = 1; }
+            for (int t = 0; t < N; ++t) {
+                if (t == q.rank) continue;
+                std::vector<int32_t>& dst = (l & 1) ? emus[t]->g0 : emus[t]->g1;
+                PredT* pd = preds[t].data() + p0.pred_off[l + 1];
+                for (int rr = 0; rr <= R; ++rr)
+                    for (size_t x = (size_t)q.i0 * k2; x < (size_t)q.i1 * k2; ++x) {
+                        dst[(size_t)rr * k2 * k2 + x] = src[(size_t)rr * k2 * k2 + x];
+                        pd[(size_t)rr * k2 * k2 + x] = ps[(size_t)rr * k2 * k2 + x];
+                    }
+            }
+        }
+        if (!narrow) for (uint8_t d : pushed) if (!d) return -74;
+        for (int r = 0; r < N; ++r) {                       // arrivals are broadcast
+            counter[r] += arrivals;
+            if (counter[r] != p0.bar_target[l]) return -15;
+        }
+    }
+    for (int r = 0; r < N; ++r) {
+        for (int c = 0; c < G; ++c) if (cur[r][c] != plans[r]->task_begin[(size_t)c + 1]) return -23;
+        if (emus[r]->bad_rc) return -24;
+        if (preds[r] != preds[0]) return -75;               // every rank holds the complete codes
+        const std::vector<int32_t>& last = ((L - 1) & 1) ? emus[r]->g1 : emus[r]->g0;
+        const std::vector<int32_t>& last0 = ((L - 1) & 1) ? emus[0]->g1 : emus[0]->g0;
+        const size_t ks = (size_t)(p0.level_off[L] - p0.level_off[L - 1]);
+        for (size_t x = 0; x < (size_t)(R + 1) * ks * ks; ++x) if (last[x] != last0[x]) return -76;
+    }
+    if (counts) { counts[0] = p0.n_narrow; counts[1] = p0.n_wide; counts[2] = n_wide_tasks; counts[3] = n_push; }
+    const int last_rank = N - 1;                            // any rank can trace
+    return traceback<PredT>(*plans[last_rank], *emus[last_rank], preds[last_rank], trace_T, sink_value, sink_s_het, p1, n1, p2, n2);
+}
+
 }  // namespace
 
 // shape: [grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, no_pack, no_long] (0 = kernel default)
@@ -484,4 +637,26 @@ extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const 
     if (p.max_indeg <= 255 && !force_pred32)
         return run<uint16_t>(p, sh, trace_T, no_pack, counts ? counts + 6 : nullptr, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
     return run<uint32_t>(p, sh, trace_T, no_pack, counts ? counts + 6 : nullptr, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);
+}
+
+// Row-sharded sweep over `n_ranks` emulated GPUs (dg_dip_create_sharded).  counts: [narrow, wide, wide tasks over all ranks, pushes]
+extern "C" int emu_dp_diploid_sharded(int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
+                                      const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off,
+                                      const int32_t* col_val, const uint8_t* colour_is_hom, int32_t n_colours, int32_t R,
+                                      int32_t n_ranks, int32_t grid, int32_t tile_cells,
+                                      int32_t* sink_value, int32_t* sink_s_het, int32_t* p1_edges, int32_t* n_p1,
+                                      int32_t* p2_edges, int32_t* n_p2, int64_t* counts) {
+    DipGraphView g;
+    g.n_levels = n_levels; g.level_off = level_off; g.adj_off = adj_off; g.adj_dst = adj_dst; g.adj_w = adj_w;
+    g.col_off = col_off; g.col_val = col_val; g.colour_is_hom = colour_is_hom; g.n_colours = n_colours; g.R = R;
+    DipPlan probe;
+    if (!build_dip_plan(g, probe)) return -1;
+    SweepShape sh;
+    sh.grid = grid > 0 ? grid : 4; sh.threads = 480; sh.tile_cells = tile_cells > 0 ? tile_cells : 16384; sh.slot_bytes = 4096;
+    const bool packed = probe.value_bound < KEY_VALUE_LIMIT;
+    sh.lane_rc = (packed && R + 1 >= LANE_RC_BIG) ? LANE_RC_BIG : LANE_RC_SMALL;
+    sh.allow_long = packed;
+    if (probe.max_indeg <= 255)
+        return run_sharded<uint16_t>(g, sh, n_ranks, 128, false, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, counts);
+    return run_sharded<uint32_t>(g, sh, n_ranks, 128, false, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, counts);
 }

@@ -238,3 +238,33 @@ def test_destinations_with_more_than_32_in_edges(R, oracle_mod, dp_emu):
     o = dp_emu.dp_diploid(g, R)
     assert_dip_equal(oracle_dip(oracle_mod, g, R), o)
     assert o["modes"]["tasks_long"] > 0
+
+
+# ---- row-sharded sweep over several GPUs (dg_dip_create_sharded), emulated rank by rank -------------------------------
+@pytest.mark.parametrize("n_ranks,grid,tile_cells", [(2, 4, 256), (3, 2, 64), (4, 3, 300), (8, 1, 128), (2, 4, 16384)])
+def test_row_sharded_sweep_matches_oracle(n_ranks, grid, tile_cells, oracle_mod, dp_emu):
+    """Wide transitions row-split over n_ranks x grid CTAs with pushed rows and broadcast arrivals, narrow ones
+    replicated: every rank ends with the same layers and predecessor codes, and the result is the oracle's."""
+    seen = dict(narrow=0, wide=0, wide_tasks=0, pushes=0)
+    for seed in range(10):
+        rng = np.random.default_rng(900 + seed)
+        g = synth.random_level_graph(700 + seed, n_levels=int(rng.integers(3, 30)), max_width=int(rng.integers(2, 14)),
+                                     n_colours=int(rng.integers(0, 150)), p_colour=0.5)
+        R = int(rng.integers(0, 6))
+        o = dp_emu.dp_diploid_sharded(g, R, n_ranks, grid=grid, tile_cells=tile_cells)
+        assert_dip_equal(oracle_dip(oracle_mod, g, R), o, checks=False)
+        for k in seen:
+            seen[k] += o["modes"][k]
+    if tile_cells < 1000:
+        assert seen["wide"] > 0 and seen["narrow"] > 0 and seen["pushes"] >= seen["wide"]
+
+
+def test_row_sharded_lane_panel_and_long_destinations(oracle_mod, dp_emu):
+    g = synth.lane_panel_graph(11, n_lanes=12, n_blocks=4, rec_per_block=2, p_colour=0.3, n_colours=64)
+    for n_ranks in (2, 4):
+        o = dp_emu.dp_diploid_sharded(g, 3, n_ranks, grid=4, tile_cells=512)
+        assert_dip_equal(oracle_dip(oracle_mod, g, 3), o, checks=False)
+        assert o["modes"]["wide"] > 0
+    g = funnel_graph(5, lanes=40)
+    o = dp_emu.dp_diploid_sharded(g, 2, 2, grid=4, tile_cells=2048)
+    assert_dip_equal(oracle_dip(oracle_mod, g, 2), o, checks=False)
