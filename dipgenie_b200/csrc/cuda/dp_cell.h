@@ -99,7 +99,11 @@ struct TaskHdr {             // 128 bytes
     uint32_t n_long;         //            destinations with more than 32 in-edges (TK_LONG), <= LANE_MAX_LONG
     uint32_t long_off;       //            byte offset of long_j[] (their positions, u16) inside the record
     uint16_t push_i0, push_i1;   // TK_PUSH: the CTA's whole row range of the level (byte 108)
-    uint32_t pad[4];
+    // row-sharded sweep, TK_ARRIVE: the CTAs of one rank first count themselves on a local word; the one that brings it
+    // to arrive_local_target (cumulative over the levels) forwards arrive_n arrivals to every rank's counter
+    uint32_t arrive_local_target;   // byte 112
+    uint32_t arrive_n;              // byte 116
+    uint32_t pad[2];
 };
 static_assert(sizeof(TaskHdr) == 128, "TaskHdr layout");
 

@@ -694,17 +694,20 @@ __device__ __noinline__ void push_rows(const SweepArgs& a, int l, uint32_t k2, u
     const bool odd = ((l + 1) & 1) != 0;
     const int32_t* const src = odd ? a.tile1 : a.tile0;
     const uint8_t* const psrc = reinterpret_cast<const uint8_t*>(a.pred);
-    for (int q = 0; q < a.world; ++q) {
-        if (q == a.rank) continue;
-        int32_t* const dst = odd ? a.peer_tile1[q] : a.peer_tile0[q];
-        uint8_t* const pdst = a.peer_pred[q];
-        for (int r = 0; r <= a.R; ++r) {
-            const size_t base = (size_t)r * kk2 + first;
-            for (uint32_t x = (uint32_t)tid; x < seg; x += DIP_CT) {
-                dst[base + x] = __ldcg(src + base + x);
-                if (PRED32) reinterpret_cast<uint32_t*>(pdst)[pred_off2 + base + x] = __ldcg(reinterpret_cast<const uint32_t*>(psrc) + pred_off2 + base + x);
-                else reinterpret_cast<uint16_t*>(pdst)[pred_off2 + base + x] = __ldcg(reinterpret_cast<const uint16_t*>(psrc) + pred_off2 + base + x);
-            }
+    const uint32_t total = ((uint32_t)a.R + 1u) * seg;          // (layer, cell of the row range), one index
+#pragma unroll 4
+    for (uint32_t idx = (uint32_t)tid; idx < total; idx += DIP_CT) {
+        const uint32_t r = idx / seg, x = idx - r * seg;
+        const size_t cell = (size_t)r * kk2 + first + x;
+        const int32_t v = __ldcg(src + cell);
+        uint32_t code;
+        if (PRED32) code = __ldcg(reinterpret_cast<const uint32_t*>(psrc) + pred_off2 + cell);
+        else code = __ldcg(reinterpret_cast<const uint16_t*>(psrc) + pred_off2 + cell);
+        for (int q = 0; q < a.world; ++q) {
+            if (q == a.rank) continue;
+            (odd ? a.peer_tile1[q] : a.peer_tile0[q])[cell] = v;
+            if (PRED32) reinterpret_cast<uint32_t*>(a.peer_pred[q])[pred_off2 + cell] = code;
+            else reinterpret_cast<uint16_t*>(a.peer_pred[q])[pred_off2 + cell] = (uint16_t)code;
         }
     }
 }
@@ -829,6 +832,8 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
         if (profiling) tk3 = clock64();
         uint32_t pw = 0;                                        // TK_PUSH: header words read before the slot is handed back
         unsigned long long push_pred_off = 0;
+        uint32_t arr_target = 0, arr_n = 0;
+        if ((flags & TK_ARRIVE) && a.world > 1) { arr_target = lds_u32(sb32 + 112u); arr_n = lds_u32(sb32 + 116u); }
         if (flags & TK_PUSH) {
             pw = lds_u32(sb32 + 108u);
             push_pred_off = ((unsigned long long)lds_u32(sb32 + 52u) << 32) | lds_u32(sb32 + 48u);
@@ -843,7 +848,14 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
             bar_compute();
         }
         if ((flags & TK_ARRIVE) && tid == 0) {
-            if (a.world > 1) { for (int q = 0; q < a.world; ++q) red_release_sys_add_u32(a.peer_counter[q], 1u); }
+            if (a.world > 1) {
+                // count on this GPU first; the rank's last CTA of the level forwards all of them at once (one remote
+                // atomic per rank and level instead of one per CTA: remote atomics on one word serialise)
+                unsigned int old;
+                asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(a.counter + 3) : "memory");
+                if (old + 1u == arr_target)
+                    for (int q = 0; q < a.world; ++q) red_release_sys_add_u32(a.peer_counter[q], arr_n);
+            }
             else red_release_add_u32(a.counter, 1u);
         }
         if (profiling) {

@@ -307,13 +307,21 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
     for (int l = 0; l < T; ++l) p.P[l] = p.narrow[l] ? 1 : std::max(1, std::min(GG, (int)width(l + 1)));
 
     // ---- 3. barrier schedule: a grid barrier follows transition l unless both it and the next run on CTA 0 alone ----
-    uint32_t acc = 0;
+    uint32_t acc = 0, acc_local = 0;
+    std::vector<uint32_t> loc_target((size_t)T, 0), loc_n((size_t)T, 0);     // this rank's share of the arrivals (row-sharded sweep)
     for (int l = 0; l < T; ++l) {
         const int pn = (l + 1 < T) ? p.P[l + 1] : 1;
         bool edge = (p.P[l] > 1) || (pn > 1);
         if (NR > 1) edge = !p.narrow[l] || (l + 1 < T && !p.narrow[l + 1]);   // (a one-CTA wide transition still has to reach the peers)
         p.bar_edge[l] = edge ? 1 : 0;
         if (edge) acc += (uint32_t)(p.narrow[l] ? NR : p.P[l]);      // a narrow transition runs (and arrives) once per rank
+        if (edge && NR > 1) {
+            // arriving CTAs of this rank: its CTA 0 for a narrow transition, else the global CTAs c < P with c % NR == RK
+            loc_n[l] = p.narrow[l] ? 1u : (uint32_t)((p.P[l] - RK + NR - 1) / NR);
+            if (!p.narrow[l] && RK >= p.P[l]) loc_n[l] = 0;
+            acc_local += loc_n[l];
+            loc_target[l] = acc_local;
+        }
         p.bar_target[l] = acc;
     }
 
@@ -452,7 +460,7 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
                     if (first && l > 0 && p.bar_edge[l - 1]) { h.flags |= TK_WAIT; h.wait_target = p.bar_target[l - 1]; }
                     if (y >= rbnd) {
                         h.flags |= TK_BAR;
-                        if (p.bar_edge[l]) h.flags |= TK_ARRIVE;
+                        if (p.bar_edge[l]) { h.flags |= TK_ARRIVE; h.arrive_local_target = loc_target[l]; h.arrive_n = loc_n[l]; }
                         if (NR > 1 && !p.narrow[l]) { h.flags |= TK_PUSH; h.push_i0 = (uint16_t)ra; h.push_i1 = (uint16_t)rbnd; }
                     }
                     stream[(size_t)lc].push_back(h);

@@ -506,7 +506,7 @@ int run_sharded(const DipGraphView& g, const SweepShape& sh0, int N, int trace_T
     std::vector<std::vector<int64_t>> cur((size_t)N);
     for (int r = 0; r < N; ++r) cur[r].assign(plans[r]->task_begin.begin(), plans[r]->task_begin.end() - 1);
     std::vector<uint8_t> slot((size_t)sh0.slot_bytes + 16);
-    std::vector<uint32_t> counter((size_t)N, 0);
+    std::vector<uint32_t> counter((size_t)N, 0), local_count((size_t)N, 0);
     int64_t n_push = 0, n_wide_tasks = 0;
     for (int l = 0; l + 1 < L; ++l) {
         const size_t k2 = (size_t)(p0.level_off[l + 2] - p0.level_off[l + 1]);
@@ -539,7 +539,12 @@ int run_sharded(const DipGraphView& g, const SweepShape& sh0, int N, int trace_T
                     if (narrow ? c != 0 : (c * N + r >= p.P[l])) return -12;          // local CTA c of rank r = global CTA c * N + r
                     if (!narrow) ++n_wide_tasks;
                     if (h.flags & TK_BAR) closed = true;
-                    if (h.flags & TK_ARRIVE) { if (!(h.flags & TK_BAR)) return -17; ++arrivals; }
+                    if (h.flags & TK_ARRIVE) {
+                        if (!(h.flags & TK_BAR)) return -17;
+                        // counted on the rank's local word; the CTA that completes the rank's share forwards it
+                        if (++local_count[r] > h.arrive_local_target) return -77;
+                        if (local_count[r] == h.arrive_local_target) arrivals += h.arrive_n;
+                    }
                     if (((h.flags & TK_PUSH) != 0) != (!narrow && (h.flags & TK_BAR))) return -71;
                     if (h.flags & TK_PUSH) {
                         if (h.flags & TK_DST_SMEM) return -72;
