@@ -298,8 +298,22 @@ struct LaneTask {
     uint32_t n_long, long_off;       // TK_LONG: destinations with more than 32 in-edges, their positions in the record
     unsigned long long* scratch;     //          64-bit combine words [(row - i0) * n_long + g][layer]
     const uint16_t* gdelta;          // pair-score matrix of the transition in global memory when its rows are not staged (else null)
+    const uint8_t* grec;             // TK_REC_GLOBAL: the record, read in place (too big for a slot); else null
     bool staged;
 };
+
+// Record reads of the lane form: `off` = byte offset inside the record.  RG: in place from global memory (read-only
+// path), else from the task slot.
+template <bool RG>
+__device__ __forceinline__ uint32_t rec16(const LaneTask& t, uint32_t off) {
+    if (RG) return (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(t.grec + off));
+    return lds_u16(t.sb32 + (uint32_t)sizeof(TaskHdr) + off);
+}
+template <bool RG>
+__device__ __forceinline__ uint32_t rec32(const LaneTask& t, uint32_t off) {
+    if (RG) return __ldg(reinterpret_cast<const uint32_t*>(t.grec + off));
+    return lds_u32(t.sb32 + (uint32_t)sizeof(TaskHdr) + off);
+}
 
 struct LaneProf { unsigned long long items, setup, loop, reduce, store, iters; };
 
@@ -327,23 +341,24 @@ __device__ __forceinline__ void fill_lane_task(const SweepArgs& a, uint32_t sb32
     if (flags & TK_LONG) { lt.n_long = lds_u32(sb32 + 100u); lt.long_off = lds_u32(sb32 + 104u); }
     lt.staged = (flags & TK_DELTA_STAGED) != 0;
     lt.gdelta = ((flags & TK_DELTA) && !lt.staged) ? a.delta + __ldg(a.delta_off + l) : nullptr;
+    lt.grec = (flags & TK_REC_GLOBAL) ? a.records + (size_t)lds_u32(sb32) * 16 : nullptr;
 }
 
 // Unpacked arithmetic (value and code in separate registers): problems whose DP values may exceed the packed key
 // (shift == 0) and, with shift == KEY_SHIFT, the tasks of levels that have destinations with more than 32 in-edges
 // (TK_LONG: slice blocks are reduced over the whole warp and meet in the scratch words).  Out of line: the packed
 // loop keeps its own register allocation.
-template <int RC, bool SMEM, bool CHECK, bool PRED32, bool PROF>
+template <int RC, bool SMEM, bool CHECK, bool PRED32, bool PROF, bool RG>
 __device__ __noinline__ ulonglong2 lane_task(const SweepArgs& a, uint32_t sb32, uint32_t tiles32, unsigned long long* scratch, int warp, int lane) {
     unsigned long long hsum = 0, hlive = 0;
     LaneProf lp = {0, 0, 0, 0, 0, 0};
     LaneTask t;
     fill_lane_task<PRED32>(a, sb32, tiles32, scratch, lds_v4(sb32 + 16u), lds_v4(sb32 + 32u), t);
     const int R = a.R, shift = a.shift;
-    const uint32_t off32 = t.sb32 + (uint32_t)sizeof(TaskHdr);
-    const uint32_t edge32 = off32 + (uint32_t)rec_edge_offset((int)t.k2);
-    const uint32_t dstp32 = off32 + (uint32_t)rec_dst_offset((int)t.k2, t.n_in);
-    const uint32_t bst32 = off32 + t.bstart_off;
+    const uint32_t slot32 = t.sb32 + (uint32_t)sizeof(TaskHdr);      // staged pair-score rows follow the staged record
+    const uint32_t edge_o = (uint32_t)rec_edge_offset((int)t.k2);    // byte offsets inside the record
+    const uint32_t dstp_o = (uint32_t)rec_dst_offset((int)t.k2, t.n_in);
+    const uint32_t bst_o = t.bstart_off;
     const uint32_t k = t.k, k2 = t.k2, n_in = t.n_in;
     const uint32_t kk = k * k, kk2 = k2 * k2;
     // lane -> (row slot, in-edge within the block)
@@ -353,7 +368,7 @@ __device__ __noinline__ ulonglong2 lane_task(const SweepArgs& a, uint32_t sb32, 
         el = (uint32_t)lane - rs * n_in;
     }
     uint32_t delta32 = 0;
-    if (t.staged) delta32 = off32 + t.rec_bytes + 2u * t.skew - 2u * lds_u16(off32 + 2u * t.i0) * n_in;   // row of in-edge e1 at + 2*e1*n_in
+    if (t.staged) delta32 = slot32 + t.rec_bytes + 2u * t.skew - 2u * rec16<RG>(t, 2u * t.i0) * n_in;   // row of in-edge e1 at + 2*e1*n_in
     for (uint32_t wi = (uint32_t)warp; wi < t.n_witems; wi += DIP_NCW) {
         long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
         if (PROF) c0 = clock64();
@@ -361,16 +376,16 @@ __device__ __noinline__ ulonglong2 lane_task(const SweepArgs& a, uint32_t sb32, 
         const uint32_t b = wi - q * t.nblk;
         const uint32_t chunk = t.m_nrg ? __umulhi(q, t.m_nrg) : q;
         const uint32_t rg = q - chunk * t.nrg;
-        const uint32_t bs = lds_u16(bst32 + 2u * b), be = lds_u16(bst32 + 2u * b + 2u);
+        const uint32_t bs = rec16<RG>(t, bst_o + 2u * b), be = rec16<RG>(t, bst_o + 2u * b + 2u);
         const uint32_t row = t.i0 + rg * t.rp + rs, e2 = bs + el;
         const bool valid = rs < t.rp && row < t.i1 && e2 < be;
         const uint32_t rowc = valid ? row : t.i0, e2c = valid ? e2 : bs;
-        const uint32_t a0 = lds_u16(off32 + 2u * rowc);
-        uint32_t a1 = lds_u16(off32 + 2u * rowc + 2u);
+        const uint32_t a0 = rec16<RG>(t, 2u * rowc);
+        uint32_t a1 = rec16<RG>(t, 2u * rowc + 2u);
         if (!valid) a1 = a0;
-        const uint32_t y = lds_u32(edge32 + 4u * e2c);
-        const uint32_t j2 = lds_u16(dstp32 + 2u * e2c);
-        const uint32_t s0 = lds_u16(off32 + 2u * j2), s1 = lds_u16(off32 + 2u * j2 + 2u);
+        const uint32_t y = rec32<RG>(t, edge_o + 4u * e2c);
+        const uint32_t j2 = rec16<RG>(t, dstp_o + 2u * e2c);
+        const uint32_t s0 = rec16<RG>(t, 2u * j2), s1 = rec16<RG>(t, 2u * j2 + 2u);
         const uint32_t pos = e2c - s0, seg = s1 - s0;
         const uint32_t j = y & 0xFFFFu;
         const int wv = (int)(y >> 16);
@@ -382,7 +397,7 @@ __device__ __noinline__ ulonglong2 lane_task(const SweepArgs& a, uint32_t sb32, 
         if (PROF) c1 = clock64();
         for (uint32_t e1 = a0; e1 < a1; ++e1) {
             if (PROF) ++lp.iters;
-            const uint32_t x = lds_u32(edge32 + 4u * e1);
+            const uint32_t x = rec32<RG>(t, edge_o + 4u * e1);
             const uint32_t base = (x & 0xFFFFu) * k + j;
             const int w = (int)(x >> 16) + wv;
             int d = 0;
@@ -429,7 +444,7 @@ __device__ __noinline__ ulonglong2 lane_task(const SweepArgs& a, uint32_t sb32, 
         if (slice) {
             if (valid && el == 0) {              // the slice's partial maxima meet the other slices in the scratch words
                 uint32_t g = 0;
-                while (g + 1 < t.n_long && lds_u16(off32 + t.long_off + 2u * g) != j2) ++g;
+                while (g + 1 < t.n_long && rec16<RG>(t, t.long_off + 2u * g) != j2) ++g;
                 unsigned long long* sc = t.scratch + ((size_t)(row - t.i0) * t.n_long + g) * (uint32_t)(R + 1);
 #pragma unroll
                 for (int rr = 0; rr < RC; ++rr)
@@ -450,8 +465,8 @@ __device__ __noinline__ ulonglong2 lane_task(const SweepArgs& a, uint32_t sb32, 
                     if (PRED32) reinterpret_cast<uint32_t*>(t.pl)[c] = code[rr];
                     else reinterpret_cast<uint16_t*>(t.pl)[c] = (uint16_t)(((code[rr] >> 16) << 8) | (code[rr] & 0xFFu));   // dead: 0xFFFF
                     if (CHECK && live) {
-                        const int pi = (int)(lds_u32(edge32 + 4u * (a0 + (code[rr] >> 16))) & 0xFFFFu);
-                        const int pj = (int)(lds_u32(edge32 + 4u * (s0 + (code[rr] & 0xFFFFu))) & 0xFFFFu);
+                        const int pi = (int)(rec32<RG>(t, edge_o + 4u * (a0 + (code[rr] >> 16))) & 0xFFFFu);
+                        const int pj = (int)(rec32<RG>(t, edge_o + 4u * (s0 + (code[rr] & 0xFFFFu))) & 0xFFFFu);
                         ++hlive;
                         hsum += cell_fold((uint64_t)c, val >> shift, pi, pj);
                     }
@@ -467,14 +482,14 @@ __device__ __noinline__ ulonglong2 lane_task(const SweepArgs& a, uint32_t sb32, 
 // per layer and round.  Only the first chunk of layers runs a checked loop (layer index below 0 for weighted
 // edges); the tiles are padded to whole chunks, so the layers above R that the last chunk loads are in bounds
 // (and never stored).
-template <int RC, bool SMEM, bool CHECK, bool PRED32, bool PROF>
+template <int RC, bool SMEM, bool CHECK, bool PRED32, bool PROF, bool RG>
 __device__ __forceinline__ void lane_task_packed(const LaneTask& t, int R, int warp, int lane,
                                                  unsigned long long& hsum, unsigned long long& hlive, LaneProf& lp) {
     constexpr uint32_t ORD_MASK = (1u << (2 * KEY_ORD_BITS)) - 1u, ORD_ONE = (1u << KEY_ORD_BITS) - 1u;
-    const uint32_t off32 = t.sb32 + (uint32_t)sizeof(TaskHdr);
-    const uint32_t edge32 = off32 + (uint32_t)rec_edge_offset((int)t.k2);
-    const uint32_t dstp32 = off32 + (uint32_t)rec_dst_offset((int)t.k2, t.n_in);
-    const uint32_t bst32 = off32 + t.bstart_off;
+    const uint32_t slot32 = t.sb32 + (uint32_t)sizeof(TaskHdr);      // staged pair-score rows follow the staged record
+    const uint32_t edge_o = (uint32_t)rec_edge_offset((int)t.k2);    // byte offsets inside the record
+    const uint32_t dstp_o = (uint32_t)rec_dst_offset((int)t.k2, t.n_in);
+    const uint32_t bst_o = t.bstart_off;
     const uint32_t k = t.k, k2 = t.k2, n_in = t.n_in;
     const uint32_t kk = k * k, kk2 = k2 * k2;
     uint32_t rs = 0, el = (uint32_t)lane;
@@ -483,21 +498,21 @@ __device__ __forceinline__ void lane_task_packed(const LaneTask& t, int R, int w
         el = (uint32_t)lane - rs * n_in;
     }
     uint32_t delta32 = 0;
-    if (t.staged) delta32 = off32 + t.rec_bytes + 2u * t.skew - 2u * lds_u16(off32 + 2u * t.i0) * n_in;
+    if (t.staged) delta32 = slot32 + t.rec_bytes + 2u * t.skew - 2u * rec16<RG>(t, 2u * t.i0) * n_in;
     // what depends on the lane's in-edge only; with a single block (the common case) it is the same for every
     // warp item of the task and is computed once
     uint32_t bs = 0, be = 0, e2c = 0, j2 = 0, s0 = 0, pos = 0, seg = 1, j = 0;
     int wv = 0;
     bool lane_ok = false;
     auto lane_setup = [&](uint32_t b) {
-        bs = lds_u16(bst32 + 2u * b); be = lds_u16(bst32 + 2u * b + 2u);
+        bs = rec16<RG>(t, bst_o + 2u * b); be = rec16<RG>(t, bst_o + 2u * b + 2u);
         const uint32_t e2 = bs + el;
         lane_ok = e2 < be;
         e2c = lane_ok ? e2 : bs;
-        const uint32_t y = lds_u32(edge32 + 4u * e2c);
-        j2 = lds_u16(dstp32 + 2u * e2c);
-        s0 = lds_u16(off32 + 2u * j2);
-        const uint32_t s1 = lds_u16(off32 + 2u * j2 + 2u);
+        const uint32_t y = rec32<RG>(t, edge_o + 4u * e2c);
+        j2 = rec16<RG>(t, dstp_o + 2u * e2c);
+        s0 = rec16<RG>(t, 2u * j2);
+        const uint32_t s1 = rec16<RG>(t, 2u * j2 + 2u);
         pos = e2c - s0; seg = s1 - s0;
         j = y & 0xFFFFu; wv = (int)(y >> 16);
     };
@@ -515,8 +530,8 @@ __device__ __forceinline__ void lane_task_packed(const LaneTask& t, int R, int w
         const uint32_t row = t.i0 + rg * t.rp + rs;
         const bool valid = lane_ok && rs < t.rp && row < t.i1;
         const uint32_t rowc = valid ? row : t.i0;
-        const uint32_t a0 = lds_u16(off32 + 2u * rowc);
-        uint32_t a1 = lds_u16(off32 + 2u * rowc + 2u);
+        const uint32_t a0 = rec16<RG>(t, 2u * rowc);
+        uint32_t a1 = rec16<RG>(t, 2u * rowc + 2u);
         if (!valid) a1 = a0;
         const int r0 = (int)chunk * RC;
         const bool edge_chunk = (r0 == 0);     // warp-uniform; layers above R (last chunk) are loaded inside the padded tile and never stored
@@ -527,7 +542,7 @@ __device__ __forceinline__ void lane_task_packed(const LaneTask& t, int R, int w
         if (PROF) c1 = clock64();
         for (uint32_t e1 = a0; e1 < a1; ++e1, ordbits -= (1u << KEY_ORD_BITS)) {
             if (PROF) ++lp.iters;
-            const uint32_t x = lds_u32(edge32 + 4u * e1);
+            const uint32_t x = rec32<RG>(t, edge_o + 4u * e1);
             const uint32_t base = (x & 0xFFFFu) * k + j;
             const int w = (int)(x >> 16) + wv;
             uint32_t dp = ordbits;
@@ -588,8 +603,8 @@ __device__ __forceinline__ void lane_task_packed(const LaneTask& t, int R, int w
                     if (PRED32) reinterpret_cast<uint32_t*>(t.pl)[c] = live ? ((o1 << 16) | o2) : 0xFFFFFFFFu;
                     else reinterpret_cast<uint16_t*>(t.pl)[c] = live ? (uint16_t)((o1 << 8) | o2) : (uint16_t)0xFFFFu;
                     if (CHECK && live) {
-                        const int pi = (int)(lds_u32(edge32 + 4u * (a0 + o1)) & 0xFFFFu);
-                        const int pj = (int)(lds_u32(edge32 + 4u * (s0 + o2)) & 0xFFFFu);
+                        const int pi = (int)(rec32<RG>(t, edge_o + 4u * (a0 + o1)) & 0xFFFFu);
+                        const int pj = (int)(rec32<RG>(t, edge_o + 4u * (s0 + o2)) & 0xFFFFu);
                         ++hlive;
                         hsum += cell_fold((uint64_t)c, val >> KEY_SHIFT, pi, pj);
                     }
@@ -609,13 +624,15 @@ __device__ __noinline__ ulonglong2 long_finalize(const SweepArgs& a, uint32_t sb
     const int R = a.R;
     const uint32_t RP1 = (uint32_t)R + 1u, G = t.n_long;
     const uint32_t total = (t.i1 - t.i0) * G * RP1;
-    const uint32_t off32 = t.sb32 + (uint32_t)sizeof(TaskHdr);
-    const uint32_t edge32 = off32 + (uint32_t)rec_edge_offset((int)t.k2);
+    const uint32_t edge_o = (uint32_t)rec_edge_offset((int)t.k2);
     const uint32_t kk2 = t.k2 * t.k2;
+    // (not a hot loop: the record is read through a run-time switch between the slot and its place in global memory)
+    auto r16 = [&](uint32_t off) { return t.grec ? rec16<true>(t, off) : rec16<false>(t, off); };
+    auto r32 = [&](uint32_t off) { return t.grec ? rec32<true>(t, off) : rec32<false>(t, off); };
     for (uint32_t idx = (uint32_t)tid; idx < total; idx += DIP_CT) {
         const unsigned long long K = t.scratch[idx];
         const uint32_t q = idx / RP1, r2 = idx - q * RP1, rowrel = q / G, g = q - rowrel * G;
-        const uint32_t row = t.i0 + rowrel, j2 = lds_u16(off32 + t.long_off + 2u * g);
+        const uint32_t row = t.i0 + rowrel, j2 = r16(t.long_off + 2u * g);
         const bool live = K != 0ull;
         const int32_t val = live ? (int32_t)((uint32_t)(K >> 32) - 1u) : NEG_INF;
         const uint32_t code = live ? 0xFFFFFFFFu - (uint32_t)K : 0xFFFFFFFFu;
@@ -624,9 +641,9 @@ __device__ __noinline__ ulonglong2 long_finalize(const SweepArgs& a, uint32_t sb
         if (PRED32) reinterpret_cast<uint32_t*>(t.pl)[c] = code;
         else reinterpret_cast<uint16_t*>(t.pl)[c] = (uint16_t)(((code >> 16) << 8) | (code & 0xFFu));   // dead: 0xFFFF
         if (CHECK && live) {
-            const uint32_t a0 = lds_u16(off32 + 2u * row), s0 = lds_u16(off32 + 2u * j2);
-            const int pi = (int)(lds_u32(edge32 + 4u * (a0 + (code >> 16))) & 0xFFFFu);
-            const int pj = (int)(lds_u32(edge32 + 4u * (s0 + (code & 0xFFFFu))) & 0xFFFFu);
+            const uint32_t a0 = r16(2u * row), s0 = r16(2u * j2);
+            const int pi = (int)(r32(edge_o + 4u * (a0 + (code >> 16))) & 0xFFFFu);
+            const int pj = (int)(r32(edge_o + 4u * (s0 + (code & 0xFFFFu))) & 0xFFFFu);
             ++hlive;
             hsum += cell_fold((uint64_t)c, val >> KEY_SHIFT, pi, pj);
         }
@@ -808,15 +825,19 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
                     const uint32_t rc = lds_u32(sb32 + 64u) & 0xFFFFu;
                     const bool big = rc == (uint32_t)LANE_RC_BIG;
                     if (ssm) {
-                        if (big) lane_task_packed<LANE_RC_BIG, true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
-                        else lane_task_packed<LANE_RC_SMALL, true, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
+                        if (big) lane_task_packed<LANE_RC_BIG, true, CHECK, PRED32, PROF, false>(lt, a.R, warp, lane, hsum, hlive, lp);
+                        else lane_task_packed<LANE_RC_SMALL, true, CHECK, PRED32, PROF, false>(lt, a.R, warp, lane, hsum, hlive, lp);
+                    } else if (flags & TK_REC_GLOBAL) {      // record read in place (wide panels)
+                        if (big) lane_task_packed<LANE_RC_BIG, false, CHECK, PRED32, PROF, true>(lt, a.R, warp, lane, hsum, hlive, lp);
+                        else lane_task_packed<LANE_RC_SMALL, false, CHECK, PRED32, PROF, true>(lt, a.R, warp, lane, hsum, hlive, lp);
                     } else {
-                        if (big) lane_task_packed<LANE_RC_BIG, false, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
-                        else lane_task_packed<LANE_RC_SMALL, false, CHECK, PRED32, PROF>(lt, a.R, warp, lane, hsum, hlive, lp);
+                        if (big) lane_task_packed<LANE_RC_BIG, false, CHECK, PRED32, PROF, false>(lt, a.R, warp, lane, hsum, hlive, lp);
+                        else lane_task_packed<LANE_RC_SMALL, false, CHECK, PRED32, PROF, false>(lt, a.R, warp, lane, hsum, hlive, lp);
                     }
                 } else {
-                    const ulonglong2 hs = ssm ? lane_task<LANE_RC_SMALL, true, CHECK, PRED32, false>(a, sb32, tiles32, scratch, warp, lane)
-                                              : lane_task<LANE_RC_SMALL, false, CHECK, PRED32, false>(a, sb32, tiles32, scratch, warp, lane);
+                    const ulonglong2 hs = ssm ? lane_task<LANE_RC_SMALL, true, CHECK, PRED32, false, false>(a, sb32, tiles32, scratch, warp, lane)
+                                          : (flags & TK_REC_GLOBAL) ? lane_task<LANE_RC_SMALL, false, CHECK, PRED32, false, true>(a, sb32, tiles32, scratch, warp, lane)
+                                                                    : lane_task<LANE_RC_SMALL, false, CHECK, PRED32, false, false>(a, sb32, tiles32, scratch, warp, lane);
                     hsum = hs.x; hlive = hs.y;
                 }
             } else {

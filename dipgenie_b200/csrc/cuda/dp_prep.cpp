@@ -257,7 +257,7 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
 
     // ---- 1. lane-form blocks, record sizes, pair-score matrix layout, placement of the layers ----
     std::vector<int32_t> nblk(T, 0);
-    std::vector<uint8_t> rec_staged(T, 0), seg_rounds(T, 0), nlong(T, 0);
+    std::vector<uint8_t> rec_staged(T, 0), rec_inplace(T, 0), seg_rounds(T, 0), nlong(T, 0);
     std::vector<uint32_t> rec_bytes(T, 0);
 #pragma omp parallel for schedule(static) num_threads(NT)
     for (int l = 0; l < T; ++l) {
@@ -269,12 +269,15 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
         const int64_t n_in = nin_of(l);
         const size_t rb = rec_bytes_for(width(l + 1), n_in, nblk[l], nlong[l]);
         rec_staged[l] = (sizeof(TaskHdr) + rb <= slot && n_in < 65536) ? 1 : 0;
-        rec_bytes[l] = rec_staged[l] ? (uint32_t)rb : 0u;
+        // a record too big for a slot still exists when the level can run in lane form: the lanes then read it in place
+        // (wide panels: thousands of in-edges per level)
+        rec_inplace[l] = (!rec_staged[l] && sh.allow_long && nblk[l] > 0 && n_in < 65536 && rb < ((size_t)1 << 31)) ? 1 : 0;
+        rec_bytes[l] = (rec_staged[l] || rec_inplace[l]) ? (uint32_t)rb : 0u;
     }
     size_t rec_total = 0;
     for (int l = 0; l < T; ++l) {
         const int64_t n_in = nin_of(l);
-        if (rec_staged[l]) { p.rec_off[l] = (int64_t)rec_total; rec_total += rec_bytes[l]; }
+        if (rec_staged[l] || rec_inplace[l]) { p.rec_off[l] = (int64_t)rec_total; rec_total += rec_bytes[l]; }
         if (p.lvlW[l] > 0 && n_in <= sh.delta_max_in && (p.delta_elems + n_in * n_in) * 2 <= sh.delta_budget) {
             p.delta_off[l] = p.delta_elems;
             p.delta_elems += (int64_t)align_up((size_t)(n_in * n_in), 8);
@@ -288,7 +291,7 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
     p.records.assign(rec_total, 0);
 #pragma omp parallel for schedule(static) num_threads(NT)
     for (int l = 0; l < T; ++l) {
-        if (!rec_staged[l]) continue;
+        if (!rec_staged[l] && !rec_inplace[l]) continue;
         uint8_t* r = p.records.data() + p.rec_off[l];
         const int32_t mid = p.level_off[l + 1], k2 = width(l + 1);
         const int32_t e0 = p.in_off[mid], e1 = p.in_off[p.level_off[l + 2]];
@@ -362,7 +365,7 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
                     cut[(size_t)q] = x;
                 }
             }
-            const size_t rb = rec_bytes[l];
+            const size_t rb = rec_staged[l] ? rec_bytes[l] : 0;      // bytes the producer stages
             uint32_t base_flags = 0;
             // layer l lives in shared memory iff it is produced and consumed by narrow transitions (level 0: by the kernel prologue)
             if (p.narrow[l] && (l == 0 || p.narrow[l - 1])) base_flags |= TK_SRC_SMEM;
@@ -383,7 +386,7 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
                     TaskHdr h;
                     memset(&h, 0, sizeof h);
                     h.level = l; h.k = (uint16_t)k; h.k2 = (uint16_t)k2; h.i0 = (uint16_t)x;
-                    h.n_in = (uint32_t)(rec_staged[l] ? n_in : 0);
+                    h.n_in = (uint32_t)((rec_staged[l] || rec_inplace[l]) ? n_in : 0);
                     h.flags = base_flags;
                     h.pred_off2 = p.pred_off[l + 1];
                     int32_t y = std::min(rbnd, x + max_rows);
@@ -418,6 +421,7 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
                             }
                         }
                     } else {
+                        if (rec_inplace[l]) h.rec_off16 = (uint32_t)(p.rec_off[l] / 16);      // read in place; rec_bytes stays 0
                         ++n_glob[(size_t)tno];
                     }
                     if (base_flags & TK_DELTA_MASKS) ++n_mask[(size_t)tno];
@@ -435,7 +439,7 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
                     const bool scores_ok = !(base_flags & TK_DELTA_MASKS);
                     const uint32_t lchunks = (uint32_t)(p.R + lrc) / (uint32_t)lrc;
                     const uint64_t witems = (uint64_t)(y - x) * (uint64_t)std::max(nblk[l], 1) * lchunks;   // upper bound (rp >= 1)
-                    if (rec_staged[l] && nblk[l] > 0 && scores_ok && same_place && CT % 32 == 0 &&
+                    if ((rec_staged[l] || rec_inplace[l]) && nblk[l] > 0 && scores_ok && same_place && CT % 32 == 0 &&
                         witems * (uint64_t)std::max<int64_t>(nblk[l], y - x) < (1ull << 32)) {
                         h.flags |= TK_LANES;
                         h.nblk = (uint16_t)nblk[l];

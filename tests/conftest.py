@@ -63,7 +63,7 @@ class DpEmu:
         shp = np.zeros(8, np.int32)
         if shape:
             shp[: len(shape)] = list(shape)
-        counts = np.zeros(8, np.int64)
+        counts = np.zeros(10, np.int64)
         val, sh, n1, n2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         p1 = np.zeros(2 * (R + 2), np.int32)
         p2 = np.zeros(2 * (R + 2), np.int32)
@@ -80,7 +80,7 @@ class DpEmu:
                     p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy(), checksum=cs, live=lv,
                     modes=dict(narrow=int(counts[0]), wide=int(counts[1]), tasks=int(counts[2]),
                                tasks_global=int(counts[3]), tasks_masks=int(counts[4]), matrices=int(counts[5]),
-                               tasks_lanes=int(counts[6]), tasks_long=int(counts[7])))
+                               tasks_lanes=int(counts[6]), tasks_long=int(counts[7]), tasks_lanes_inplace=int(counts[8])))
 
 
     def dp_diploid_sharded(self, g, R, n_ranks, grid=4, tile_cells=0):

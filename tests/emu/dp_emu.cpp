@@ -292,10 +292,24 @@ int exec_task(Emu& e, const DipPlan& p, const SweepShape& sh, const TaskHdr& gh,
         int32_t* dst = dsm ? ((l & 1) ? e.s0.data() : e.s1.data()) : ((l & 1) ? e.g0.data() : e.g1.data());
         for (int x = h.i0; x < h.i1; ++x) { if (row_done[x]) return -16; row_done[x] = 1; }
         if (h.flags & TK_LANES) {
-            if ((h.flags & TK_REC_GLOBAL) || ssm != dsm) return -60;
+            if (ssm != dsm) return -60;
             if (h.rc != ((h.flags & TK_LONG) ? LANE_RC_SMALL : e.sh.lane_rc)) return -61;
-            const int lrc = h.rc == LANE_RC_BIG ? lane_items<PredT, LANE_RC_BIG>(e, slot.data(), h, src, dst, pl)
-                                                : lane_items<PredT, LANE_RC_SMALL>(e, slot.data(), h, src, dst, pl);
+            const uint8_t* view = slot.data();
+            TaskHdr hv = h;
+            std::vector<uint8_t> inplace;
+            if (h.flags & TK_REC_GLOBAL) {
+                // record too big for a slot: the lanes read it in place (a.records + rec_off16 * 16); nothing of it is staged
+                if (ssm || h.rec_bytes != 0 || (h.flags & TK_DELTA_STAGED) || p.rec_off[l] < 0 || (int64_t)h.rec_off16 * 16 != p.rec_off[l]) return -66;
+                const size_t len = rec_bytes_for(h.k2, h.n_in, h.nblk, (int)h.n_long);
+                if ((size_t)p.rec_off[l] + len > p.records.size()) return -66;
+                if (sizeof(TaskHdr) + len <= (size_t)sh.slot_bytes) return -66;         // would have been staged
+                inplace.resize(sizeof(TaskHdr) + len);
+                memcpy(inplace.data() + sizeof(TaskHdr), p.records.data() + p.rec_off[l], len);
+                hv.rec_bytes = (uint32_t)len;
+                view = inplace.data();
+            }
+            const int lrc = hv.rc == LANE_RC_BIG ? lane_items<PredT, LANE_RC_BIG>(e, view, hv, src, dst, pl)
+                                                 : lane_items<PredT, LANE_RC_SMALL>(e, view, hv, src, dst, pl);
             if (lrc) return lrc;
             ++e.n_lane_tasks;
         } else if (!(h.flags & TK_REC_GLOBAL)) {
@@ -604,7 +618,7 @@ int run_sharded(const DipGraphView& g, const SweepShape& sh0, int N, int trace_T
 
 // shape: [grid, threads, tile_cells, slot_bytes, delta_max_in, trace_T, no_pack, no_long] (0 = kernel default)
 // counts: [narrow transitions, wide transitions, tasks, tasks with in-place records, tasks with on-the-fly masks, matrices,
-//          tasks run in lane form, TK_LONG tasks]
+//          tasks run in lane form, TK_LONG tasks, lane-form tasks with in-place records]
 extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
                               const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off,
                               const int32_t* col_val, const uint8_t* colour_is_hom, int32_t n_colours, int32_t R,
@@ -636,8 +650,11 @@ extern "C" int emu_dp_diploid(int32_t n_levels, const int32_t* level_off, const 
     if (counts) {
         counts[0] = p.n_narrow; counts[1] = p.n_wide; counts[2] = (int64_t)p.tasks.size();
         counts[3] = p.n_tasks_global; counts[4] = p.n_tasks_masks; counts[5] = (int64_t)p.delta_list.size();
-        counts[7] = 0;
-        for (const TaskHdr& t : p.tasks) if (t.flags & TK_LONG) ++counts[7];
+        counts[7] = 0; counts[8] = 0;
+        for (const TaskHdr& t : p.tasks) {
+            if (t.flags & TK_LONG) ++counts[7];
+            if ((t.flags & TK_LANES) && (t.flags & TK_REC_GLOBAL)) ++counts[8];      // lane form over an in-place record
+        }
     }
     if (p.max_indeg <= 255 && !force_pred32)
         return run<uint16_t>(p, sh, trace_T, no_pack, counts ? counts + 6 : nullptr, sink_value, sink_s_het, p1_edges, n_p1, p2_edges, n_p2, level_checksum, level_live);

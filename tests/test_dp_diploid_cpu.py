@@ -135,7 +135,7 @@ def test_all_sweep_modes_agree(shape, oracle_mod, dp_emu):
     """Narrow (shared-memory layers) and wide (row-split over CTAs, layers in HBM) transitions, staged and
     in-place records, staged / in-place / on-the-fly pair scores, and every hand-over between them, give the
     same layers, and the checkpointed traceback gives the same lists for any checkpoint distance."""
-    seen = dict(narrow=0, wide=0, tasks=0, tasks_global=0, tasks_masks=0, matrices=0, tasks_lanes=0, tasks_long=0)
+    seen = dict(narrow=0, wide=0, tasks=0, tasks_global=0, tasks_masks=0, matrices=0, tasks_lanes=0, tasks_long=0, tasks_lanes_inplace=0)
     for seed in range(12):
         rng = np.random.default_rng(77 + seed)
         g = synth.random_level_graph(500 + seed, n_levels=int(rng.integers(3, 30)), max_width=int(rng.integers(2, 12)),
@@ -151,6 +151,7 @@ def test_all_sweep_modes_agree(shape, oracle_mod, dp_emu):
         assert seen["narrow"] > 0 and seen["wide"] > 0 and seen["tasks"] > seen["narrow"] + seen["wide"]
     if shape[0] == 4:
         assert seen["tasks_global"] > 0
+        assert seen["tasks_lanes_inplace"] > 0          # lane form reading a record that is too big for a slot in place
     if shape[0] == 3:
         assert seen["tasks_masks"] > 0 and seen["matrices"] == 0
     if shape[0] == 5:

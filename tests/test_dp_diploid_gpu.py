@@ -170,3 +170,13 @@ def test_cuda_destinations_with_more_than_32_in_edges(ctx, oracle_mod, monkeypat
     ref = oracle_dip(oracle_mod, g, 5)
     monkeypatch.setenv("DG_NO_LONG", "1")
     assert_dip_equal(ref, cuda_dip(ctx, g, 5))
+
+
+def test_records_larger_than_a_slot_run_in_lane_form(ctx, oracle_mod):
+    """Panels of several hundred lanes: a level's record (offsets, in-edges, destinations, blocks) no longer fits a 4 KB
+    task slot; the lane form then reads it in place from global memory instead of falling back to the pair form."""
+    g = synth.lane_panel_graph(21, n_lanes=400, n_blocks=3, rec_per_block=3, p_colour=0.1, n_colours=4096)
+    for R in (2, 9):
+        o = cuda_dip(ctx, g, R)                      # value, paths and the per-level checksums of every layer
+        assert_dip_equal(oracle_dip(oracle_mod, g, R), o)
+        assert o["stats"]["n_wide"] > 0

@@ -4,7 +4,8 @@ sys.path.insert(0, os.getcwd())
 from dipgenie_b200 import synth
 from dipgenie_b200.cuda_api import Context
 ctx = Context(0)
-for H, nb, R in ((16, 200, 18), (48, 60, 18), (90, 24, 18)):
+shapes = ((16, 200, 18), (48, 60, 18), (90, 24, 18), (320, 12, 18), (640, 8, 18)) if len(sys.argv) < 2 else [tuple(int(x) for x in a.split(',')) for a in sys.argv[1:]]
+for H, nb, R in shapes:
     g = synth.lane_panel_graph(90, n_lanes=H, n_blocks=nb, rec_per_block=max(2, H // 16), p_colour=0.08, n_colours=1 << 15)
     p = ctx.dip_create(g, R)
     for i in range(2):
