@@ -70,10 +70,10 @@ class RowShardedDip:
         dist.all_gather_object(handles, self.problem.ipc_export())
         self.problem.ipc_attach(handles)
 
-    def run(self) -> dict:
+    def run(self, profile: bool = False) -> dict:
         self.problem.shard_arm()
         self.dist.barrier()            # every rank's counters are reset before any sweep can arrive on them
-        self.problem.run()
+        self.problem.run(profile=profile)
         out = self.problem.result()
         self.dist.barrier()            # nobody re-arms while a peer's kernel may still be running
         return out

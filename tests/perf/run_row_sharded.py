@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--check", action="store_true", help="small problems only")
 ap.add_argument("--lanes", type=int, nargs="*", default=[48, 90, 160])
 ap.add_argument("--R", type=int, default=18)
+ap.add_argument("--profile", action="store_true", help="phase cycle counters of CTA 0 / thread 0 of every rank")
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -48,6 +49,9 @@ for name, g, R in problems:
     for _ in range(3):
         out = prob.run(); tn.append(prob.stats()["sweep_ms"])
     st = prob.stats()
+    if a.profile:
+        prob.run(profile=True)
+        print(f"rank {rank} {name}: {json.dumps(prob.problem.profile()['hbm_layers'])}", flush=True)
     prob.close()
     good = same(ref, out)
     flags = [None] * world
