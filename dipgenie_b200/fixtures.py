@@ -46,6 +46,28 @@ def materialize_mhc(gold_dir: str, out_dir: str):
     return gfa, fa
 
 
+def materialize_mhc_hg002_reads(gold_dir: str, out_dir: str, seed: int = 20261018, coverage: float = 2.0):
+    """BASELINE config 2 with the documented substitute for the absent HG002 2x read set: 150-bp reads drawn
+    uniformly from the HG002.1 and HG002.2 walk sequences of the MHC_4 panel (half each), random strand, 0.1 %
+    substitutions, 2 x 5 Mbp in total (about 66 000 reads), seeded.  Returns (gfa path, reads path)."""
+    from . import simulate
+    z = np.load(os.path.join(gold_dir, "sketch_mhc4_chm13.npz"))
+    k = np.load(os.path.join(gold_dir, "mhc4_panel_links.npz"))
+    gfa, _ = materialize_mhc(gold_dir, out_dir)
+    seg_bases, seg_off = np.asarray(z["seg_bases"], np.uint8), z["seg_off"]
+    segs = [seg_bases[int(seg_off[v]):int(seg_off[v + 1])] for v in range(len(seg_off) - 1)]
+    walk_vtx, walk_off = z["walk_vtx"], z["walk_off"]
+    walks = [np.asarray(walk_vtx[int(walk_off[h]):int(walk_off[h + 1])]).tolist() for h in range(len(walk_off) - 1)]
+    names = [s.decode() if isinstance(s, bytes) else str(s) for s in k["walk_sample"].tolist()]
+    target = [h for h, n in enumerate(names) if n == "HG002"]
+    if len(target) != 2:
+        raise RuntimeError(f"expected the two HG002 walks in the MHC_4 panel, found {target}")
+    reads = simulate.reads_from_walks(seed, dict(segs=segs, walks=walks, links=[]), target, coverage=coverage)
+    fa = os.path.join(out_dir, "hg002_sim_reads.fa")
+    simulate.write_reads(fa, reads)
+    return gfa, fa
+
+
 # The reference's two toy inputs (test/test.gfa + read.fa: 8 segments, 5 walks, one 19-bp read;
 # test/test2.gfa + read2.fa: 4 segments, 2 walks, one 87-bp read), restated as data.
 TOY = {

@@ -3,13 +3,14 @@ import hashlib, json, os, subprocess, sys, tempfile, time
 sys.path.insert(0, os.getcwd())
 from dipgenie_b200 import _build, fixtures
 td = tempfile.mkdtemp()
-gfa, fa = fixtures.materialize_mhc("tests/golden", td)
+config2 = len(sys.argv) > 1 and sys.argv[1] == "--config2"      # HG002 read substitute (66 607 seeded reads) instead of the CHM13 reads
+gfa, fa = fixtures.materialize_mhc_hg002_reads("tests/golden", td) if config2 else fixtures.materialize_mhc("tests/golden", td)
 ncpu = os.cpu_count()
 res = {}
 for name, exe in (("dipgenie_b200", _build.CLI_BIN), ("reference", "oracle/_ref/DipGenie")):
     if not os.path.exists(exe):
         continue
-    for flags in (["-p2", "-R18"], ["-p1"]):
+    for flags in ((["-p2", "-R18"],) if config2 else (["-p2", "-R18"], ["-p1"])):
         out = os.path.join(td, name + ".fa")
         best = None
         for rep in range(2 if name == "dipgenie_b200" else 1):
@@ -20,4 +21,4 @@ for name, exe in (("dipgenie_b200", _build.CLI_BIN), ("reference", "oracle/_ref/
         res[name + " " + " ".join(flags)] = dict(seconds=round(best, 3), md5=hashlib.md5(open(out, "rb").read()).hexdigest(), rc=p.returncode)
         if name == "dipgenie_b200":
             res[name + " " + " ".join(flags)]["log"] = [l for l in p.stderr.splitlines() if l.startswith("[M::")][-6:]
-print(json.dumps(dict(host_cpus=ncpu, runs=res), indent=1))
+print(json.dumps(dict(host_cpus=ncpu, reads="HG002 substitute (seed 20261018)" if config2 else "CHM13", runs=res), indent=1))

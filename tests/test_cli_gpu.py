@@ -51,6 +51,17 @@ def test_cli_mhc(name, flags, cli, e2e_expected, tmp_path):
         assert "DP value: 60729" in log and "Count_Sp_R : 138834" in log
 
 
+def test_cli_mhc_hg002_simulated_reads(cli, e2e_expected, tmp_path):
+    """BASELINE config 2 with the documented substitute for the absent HG002 2x reads (66 607 seeded reads from
+    the HG002.1 / HG002.2 walks of MHC_4): FASTA byte-identical to the unmodified reference's
+    (tests/golden/make_config2_golden.py; DP value 184 562, 12 + 6 recombinations)."""
+    gfa, fa = fixtures.materialize_mhc_hg002_reads(GOLD, str(tmp_path))
+    assert hashlib.md5(open(fa, "rb").read()).hexdigest() == e2e_expected["mhc_hg002sim_reads_md5"]
+    log, md5 = run(cli, gfa, fa, str(tmp_path / "out.fa"), ["-p2", "-R18"])
+    assert md5 == e2e_expected["mhc_hg002sim_p2_R18"]
+    assert "DP value: 184562" in log
+
+
 def test_cli_usage_and_ploidy_contract(cli, tmp_path):
     """src/main.cpp:90-111 (usage + exit 1 without -g/-r/-o) and :159-162 (unknown ploidy: message, exit 0)."""
     p = subprocess.run([cli, "-g", "x.gfa"], capture_output=True, text=True)

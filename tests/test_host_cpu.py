@@ -70,3 +70,16 @@ def test_mhc_haploid_matches_reference(host_check, e2e_expected, tmp_path):
     s, md5 = run(host_check, gfa, fa, str(tmp_path / "out.fa"), ["-p1"])
     assert md5 == e2e_expected["mhc_p1"] == "0c4df87ded10634a36db0a2c90521ff0"
     assert s["len1"] == 4916718 and s["best_r"] == 0
+
+
+def test_config2_read_substitute_is_reproducible(tmp_path):
+    """The seeded HG002 read substitute of BASELINE config 2 (fixtures.materialize_mhc_hg002_reads) must come out
+    byte-identical wherever it is generated: its reference golden was recorded in the build container."""
+    import hashlib
+    import json
+    from dipgenie_b200 import fixtures
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    exp = json.load(open(os.path.join(gold, "e2e_expected.json")))
+    _, fa = fixtures.materialize_mhc_hg002_reads(gold, str(tmp_path))
+    assert hashlib.md5(open(fa, "rb").read()).hexdigest() == exp["mhc_hg002sim_reads_md5"]
+    assert sum(1 for line in open(fa, "rb") if line.startswith(b">")) == exp["mhc_hg002sim_n_reads"] == 66607
