@@ -68,6 +68,16 @@ def materialize_mhc_hg002_reads(gold_dir: str, out_dir: str, seed: int = 2026101
     return gfa, fa
 
 
+def materialize_vcf_panel(gold_dir: str, out_dir: str) -> str:
+    """BASELINE config 3's graph: the GFA that dipgenie_b200/vcf2gfa.py derives from the reference's test/MHC_4.vcf.gz +
+    MHC-CHM13.0.fa.gz, stored as tests/golden/mhc4_vcf_panel.npz (tests/golden/make_config3_golden.py) -> gfa path."""
+    k = np.load(os.path.join(gold_dir, "mhc4_vcf_panel.npz"))
+    gfa = os.path.join(out_dir, "mhc4_vcf_panel.gfa")
+    write_gfa(gfa, k["seg_bases"], k["seg_off"], k["walk_vtx"], k["walk_off"], k["link_src"], k["link_dst"],
+              [s.decode() if isinstance(s, bytes) else str(s) for s in k["walk_sample"].tolist()], k["walk_hap"])
+    return gfa
+
+
 # The reference's two toy inputs (test/test.gfa + read.fa: 8 segments, 5 walks, one 19-bp read;
 # test/test2.gfa + read2.fa: 4 segments, 2 walks, one 87-bp read), restated as data.
 TOY = {

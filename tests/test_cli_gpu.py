@@ -62,6 +62,18 @@ def test_cli_mhc_hg002_simulated_reads(cli, e2e_expected, tmp_path):
     assert "DP value: 184562" in log
 
 
+def test_cli_vcf_derived_graph(cli, e2e_expected, tmp_path):
+    """BASELINE config 3: -p2 -R18 on the graph dipgenie_b200/vcf2gfa.py derives from MHC_4.vcf.gz + MHC-CHM13.0.fa.gz
+    (fixture tests/golden/mhc4_vcf_panel.npz; 100 714 segments, 5 walks) with the HG002 read substitute: FASTA
+    byte-identical to the unmodified reference's on the same files (DP value 194 046, 9 + 9 recombinations)."""
+    gfa = fixtures.materialize_vcf_panel(GOLD, str(tmp_path))
+    assert hashlib.md5(open(gfa, "rb").read()).hexdigest() == e2e_expected["mhc_vcf_gfa_md5"]
+    _, fa = fixtures.materialize_mhc_hg002_reads(GOLD, str(tmp_path))
+    log, md5 = run(cli, gfa, fa, str(tmp_path / "out.fa"), ["-p2", "-R18"])
+    assert md5 == e2e_expected["mhc_vcf_hg002sim_p2_R18"]
+    assert "DP value: 194046" in log
+
+
 def test_cli_usage_and_ploidy_contract(cli, tmp_path):
     """src/main.cpp:90-111 (usage + exit 1 without -g/-r/-o) and :159-162 (unknown ploidy: message, exit 0)."""
     p = subprocess.run([cli, "-g", "x.gfa"], capture_output=True, text=True)

@@ -83,3 +83,59 @@ def test_config2_read_substitute_is_reproducible(tmp_path):
     _, fa = fixtures.materialize_mhc_hg002_reads(gold, str(tmp_path))
     assert hashlib.md5(open(fa, "rb").read()).hexdigest() == exp["mhc_hg002sim_reads_md5"]
     assert sum(1 for line in open(fa, "rb") if line.startswith(b">")) == exp["mhc_hg002sim_n_reads"] == 66607
+
+
+def test_vcf2gfa_small_cases(tmp_path):
+    """Own VCF -> GFA converter (dipgenie_b200/vcf2gfa.py, replaces the external-tool pipeline of the reference's
+    vcf2gfa.py): every walk must spell its haplotype; overlapping and symbolic records are skipped."""
+    from dipgenie_b200 import vcf2gfa
+    ref = "ACGTACGTTTGACCAGTAGGCATCGATTACA"
+    (tmp_path / "r.fa").write_text(">chrT\n" + ref[:16] + "\n" + ref[16:] + "\n")
+    recs = [(3, "G", "T", "0|1", "1|1"),            # SNP
+            (6, "CGTT", "C", "1|0", "0|0"),         # deletion (anchor base kept)
+            (8, "T", "TAAA", "0|1", "0|0"),         # overlaps the deletion: skipped
+            (12, "A", "AGG,C", "1|2", "0|2"),       # multi-allelic: insertion and SNP
+            (13, "C", "G", "1|1", "1|0"),           # adjacent site (no backbone between)
+            (20, "G", "<DEL>", "0|1", "0|0"),       # symbolic: skipped
+            (26, "A", "T", "0|0", "0|0")]           # nobody carries ALT: only the REF allele becomes a segment
+    vcf = "##fileformat=VCFv4.2\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tS1\tS2\n"
+    for pos, r, a, g1, g2 in recs:
+        assert ref[pos - 1:pos - 1 + len(r)] == r
+        vcf += f"chrT\t{pos}\t.\t{r}\t{a}\t60\t.\t.\tGT\t{g1}\t{g2}\n"
+    (tmp_path / "v.vcf").write_text(vcf)
+    g = vcf2gfa.convert(str(tmp_path / "v.vcf"), str(tmp_path / "r.fa"), "REF")
+    assert g["skipped"] == 2
+    assert g["names"] == [("REF", 0), ("S1", 1), ("S1", 2), ("S2", 1), ("S2", 2)]
+
+    def hap(col, idx):            # apply the accepted records to the reference, right to left
+        s = ref
+        for pos, r, a, g1, g2 in reversed([x for x in recs if x[0] not in (8, 20)]):
+            al = int((g1, g2)[col].split("|")[idx])
+            if al:
+                s = s[:pos - 1] + a.split(",")[al - 1] + s[pos - 1 + len(r):]
+        return s
+    spelled = ["".join(g["segs"][v] for v in w) for w in g["walks"]]
+    assert spelled[0] == ref
+    assert spelled[1:] == [hap(0, 0), hap(0, 1), hap(1, 0), hap(1, 1)]
+    for w in g["walks"]:          # every step of a walk is an L line; ids ascend (topological order)
+        assert all((a, b) in set(g["links"]) and a < b for a, b in zip(w, w[1:]))
+    assert sum(1 for s in g["segs"] if s == "T") >= 1 and len(g["segs"]) == len(set(v for w in g["walks"] for v in w))
+
+
+def test_vcf2gfa_reproduces_the_config3_fixture(tmp_path):
+    """tests/golden/mhc4_vcf_panel.npz (what the GPU box runs config 3 on) is exactly what the converter derives from the
+    reference's test/MHC_4.vcf.gz + MHC-CHM13.0.fa.gz (only checkable where the reference tree exists)."""
+    ref_test = "/root/reference/test"
+    if not os.path.exists(os.path.join(ref_test, "MHC_4.vcf.gz")):
+        pytest.skip("reference test data not present")
+    from dipgenie_b200 import vcf2gfa
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    exp = json.load(open(os.path.join(gold, "e2e_expected.json")))
+    gfa = fixtures.materialize_vcf_panel(gold, str(tmp_path))
+    assert hashlib.md5(open(gfa, "rb").read()).hexdigest() == exp["mhc_vcf_gfa_md5"]
+    g = vcf2gfa.convert(os.path.join(ref_test, "MHC_4.vcf.gz"), os.path.join(ref_test, "MHC-CHM13.0.fa.gz"))
+    assert len(g["segs"]) == exp["mhc_vcf_segments"] and g["skipped"] == exp["mhc_vcf_skipped_records"]
+    with open(tmp_path / "direct.gfa", "w") as f:
+        vcf2gfa.write_gfa(g, f)
+    strip = lambda p: [l for l in open(p) if l[0] in "SLW"]          # noqa: E731
+    assert strip(tmp_path / "direct.gfa") == strip(gfa)
