@@ -191,8 +191,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="mhc4_chm13")
     ap.add_argument("--R", type=int, default=18)
-    ap.add_argument("--samples-per-gpu", type=int, default=32, help="samples resident together on one GPU in the timed step")
-    ap.add_argument("--ctas-per-sample", type=int, default=4)
+    ap.add_argument("--samples-per-gpu", type=int, default=128, help="samples resident together on one GPU in the timed step (about 1 GB of HBM each)")
+    ap.add_argument("--ctas-per-sample", type=int, default=1, help="sweep CTAs per resident sample (samples x CTAs <= SM count)")
+    ap.add_argument("--batch-ctas", type=int, default=0, help="CTAs per sample of the end-to-end batch call (0 = library default)")
     ap.add_argument("--batch", type=int, default=22, help="samples per GPU in the end-to-end batch call (22-sample study)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -220,9 +221,32 @@ def main():
     os.environ.setdefault("DG_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))))
     g, desc = load_workload(args.workload)
     ctx = Context(local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    # end-to-end through the host-buffer C-ABI batch call (planning, H2D, kernels, D2H inside the timed region)
+    graphs = [g] * max(1, args.batch)
+    e2e_t, single_t = [], []
+    for i in range(args.e2e_steps + 1):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = ctx.dp_diploid_batch(graphs, args.R, ctas_per_sample=args.batch_ctas)
+        dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        o1 = ctx.dp_diploid(g, args.R)
+        d1 = time.perf_counter() - t0
+        if i > 0:
+            e2e_t.append(dt)
+            single_t.append(d1)
+        assert all(r["value"] == o1["value"] for r in res)
+    e2e_value = o1["value"]
+    e2e_s, single_s = float(np.mean(e2e_t)), float(np.mean(single_t))
+    print("bench: e2e batch calls (s): %s; single-sample calls (s): %s" % ([round(x, 3) for x in e2e_t], [round(x, 3) for x in single_t]), file=sys.stderr)
+
+
+    # device-resident throughput: S samples in HBM, swept together
     S = max(1, args.samples_per_gpu)
     probs = [ctx.dip_create(g, args.R, slot=i, ctas=args.ctas_per_sample) for i in range(S)]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():
         if world > 1:
@@ -254,25 +278,7 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     st = sts[0]
     dev_ms = float(np.mean(group_ms))
-    assert all(o["value"] == outs[0]["value"] for o in outs)
-
-    # end-to-end through the host-buffer C-ABI batch call (planning, H2D, kernels, D2H inside the timed region)
-    graphs = [g] * max(1, args.batch)
-    e2e_t, single_t = [], []
-    for i in range(args.e2e_steps + 1):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = ctx.dp_diploid_batch(graphs, args.R, ctas_per_sample=args.ctas_per_sample)
-        dt = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        o1 = ctx.dp_diploid(g, args.R)
-        d1 = time.perf_counter() - t0
-        if i > 0:
-            e2e_t.append(dt)
-            single_t.append(d1)
-        assert all(r["value"] == outs[0]["value"] for r in res) and o1["value"] == outs[0]["value"]
-    e2e_s, single_s = float(np.mean(e2e_t)), float(np.mean(single_t))
+    assert all(o["value"] == e2e_value for o in outs)
 
     tmax = torch.tensor([dev_ms, e2e_s * 1e3, single_s * 1e3, float(np.mean(sweep))], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -284,7 +290,11 @@ def main():
         B = len(graphs)
         peak, peak_src = peaks()
         sweep_ms = float(np.mean(sweep))
-        achieved = st["algo_bytes"] / (sweep_ms * 1e-3) / 1e9
+        # dg_dip_run_many sweeps all S resident samples in ONE launch (dip_sweep_many_kernel) when it can: that launch's
+        # algorithmic bytes are S samples' worth
+        fused = S >= 2 and sts[1]["launches"] == sts[0]["launches"] - 1
+        per_launch = S if fused else 1
+        achieved = per_launch * st["algo_bytes"] / (sweep_ms * 1e-3) / 1e9
         line = {
             "metric": "dp_cell_updates_per_sec", "value": world * S * U / (dev_ms_max * 1e-3), "unit": "cell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max, "higher_is_better": True,
@@ -293,21 +303,25 @@ def main():
             "config": {"workload": args.workload, "description": desc, "R": args.R, "ploidy": 2, "levels": st["n_levels"],
                        "vertices": st["n_vertices"], "max_width": st["max_width"], "cell_updates_per_sample": U,
                        "dest_cells_per_sample": st["cells"], "samples_per_step": world * S, "samples_per_gpu": S,
-                       "ctas_per_sample": st["grid_ctas"], "sharding": "independent samples per GPU and per CTA group, no collective",
+                       "ctas_per_sample": st["grid_ctas"], "sharding": "independent samples per GPU and per CTA group, no collective", "fused_sweep_launch": bool(S >= 2 and sts[1]["launches"] == sts[0]["launches"] - 1),
                        "l2": "256 MiB device buffer rewritten between timed iterations",
                        "timing": "CUDA events on the library stream around the fork/join of the S resident sweeps (delta + sweep + traceback kernels)"},
             "samples_per_sec": world * B / (e2e_ms_max * 1e-3),
             "dp_value": outs[0]["value"],
             "gpu_launches": int(sum(x["launches"] for x in sts)) * args.steps,
             "kernel_ms": {"pair_scores": float(np.mean(delta)), "sweep": sweep_ms, "traceback": float(np.mean(trace)),
-                          "note": "per launch, with S launches resident together"},
+                          "note": ("sweep: the one fused launch over all S samples; pair scores / traceback: per sample, S of them side by side"
+                                   if fused else "per launch, with S launches resident together")},
             "wall_s_timed_region": t_wall,
-            "roofline": {"bound": "hbm", "kernel": "dip_sweep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((args.workload, args.R)), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": st["algo_bytes"], "launches_resident_together": S,
-                         "aggregate_achieved": achieved * S,
-                         "note": "latency-bound at H=5: 120 362 dependent level transitions per launch, almost all on one SM; "
-                                 "the machine is filled by running samples side by side (see DESIGN.md)"},
+            "roofline": {"bound": "hbm", "kernel": "dip_sweep_many_kernel" if fused else "dip_sweep_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (NCU_TRAFFIC.get((args.workload, args.R)) or 0) * per_launch or None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": st["algo_bytes"] * per_launch, "samples_per_launch": per_launch,
+                         "launches_resident_together": 1 if fused else S,
+                         "aggregate_achieved": achieved * (1 if fused else S),
+                         "traffic_note": "dram bytes of ONE sample's sweep (ncu --set full of dip_sweep_kernel, profiles/r01b_sweep_v3.md) x samples per launch",
+                         "note": "latency-bound at H=5: every sample is a chain of 120 362 dependent level transitions, almost all on one SM; "
+                                 "the machine is filled by sweeping samples side by side, one CTA each, in one launch (see DESIGN.md)"},
             "e2e": {"value": world * B * U / (e2e_ms_max * 1e-3), "unit": "cell-updates/s", "ms_per_step": e2e_ms_max,
                     "samples_per_step": world * B, "h2d_bytes_per_step": int(g.nbytes) * B,
                     "d2h_bytes_per_step": int(ctypes_out_bytes()) * B,

@@ -45,6 +45,16 @@ const char* dg_last_error(dg_ctx* ctx) { return ctx ? ctx->err.c_str() : "no con
 
 void dg_free(void* p) { free(p); }
 
+int dg_release_cached_memory(dg_ctx* ctx) {
+    if (!ctx) return DG_ERR_ARG;
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DG_CUDA(ctx, cudaDeviceSynchronize());
+    cudaMemPool_t pool = nullptr;
+    DG_CUDA(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    DG_CUDA(ctx, cudaMemPoolTrimTo(pool, 0));
+    return DG_OK;
+}
+
 int dg_device_info(dg_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes) {
     if (!ctx) return DG_ERR_ARG;
     DG_CUDA(ctx, cudaSetDevice(ctx->device));

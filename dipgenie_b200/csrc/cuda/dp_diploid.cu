@@ -730,7 +730,7 @@ __device__ __noinline__ void push_rows(const SweepArgs& a, int l, uint32_t k2, u
 }
 
 template <bool CHECK, bool PRED32, bool PROF>
-__global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_constant__ SweepArgs a) {
+__device__ __forceinline__ void sweep_body(const SweepArgs& a, const int cta) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* const slots = smem;
     int32_t* const tileS0 = reinterpret_cast<int32_t*>(smem + (size_t)DIP_NSLOT * DIP_SLOT_BYTES);
@@ -739,7 +739,7 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
     uint64_t* const empty = full + DIP_NSLOT;
     unsigned long long* const scratch = reinterpret_cast<unsigned long long*>(empty + DIP_NSLOT);   // TK_LONG tasks
 
-    const int cta = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int32_t n = (int32_t)(a.task_begin[cta + 1] - a.task_begin[cta]);
     const TaskHdr* const my_tasks = a.tasks + a.task_begin[cta];
     uint8_t* const pred = reinterpret_cast<uint8_t*>(a.pred);
@@ -915,6 +915,26 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_
     }
 }
 
+template <bool CHECK, bool PRED32, bool PROF>
+__global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_kernel(const __grid_constant__ SweepArgs a) {
+    sweep_body<CHECK, PRED32, PROF>(a, (int)blockIdx.x);
+}
+
+// Many independent problems in ONE launch (dg_dip_run_many): CTA b works on problem cta_map[b].x as its local CTA
+// cta_map[b].y.  A GPU runs at most 32 streams' kernels side by side (hardware work queues), a grid has no such
+// limit: one or two CTAs per sample fill all SMs with samples.  The problem's arguments are copied to shared memory once.
+template <bool PRED32>
+__global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_many_kernel(const SweepArgs* __restrict__ all, const int2* __restrict__ cta_map) {
+    __shared__ SweepArgs sa;
+    const int2 who = cta_map[blockIdx.x];
+    static_assert(sizeof(SweepArgs) % 4 == 0, "word copy");
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(all + who.x);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sa);
+    for (uint32_t x = threadIdx.x; x < sizeof(SweepArgs) / 4; x += blockDim.x) dst[x] = src[x];
+    __syncthreads();
+    sweep_body<false, PRED32, false>(sa, who.y);
+}
+
 // ---- K7: traceback ------------------------------------------------------------------------------
 struct TraceOut {           // device-side result block
     int32_t rc, value, s_het, n1, n2, pad[3];
@@ -1030,8 +1050,12 @@ struct PlanStaging {
         if (!block.p) {
             cudaSetDevice(c->device);
             void* q = nullptr;
-            if (cudaHostAlloc(&q, bytes, cudaHostAllocDefault) == cudaSuccess) block = {q, bytes};
-            else (void)cudaGetLastError();
+            const cudaError_t e = cudaHostAlloc(&q, bytes, cudaHostAllocDefault);
+            if (e == cudaSuccess) block = {q, bytes};
+            else {
+                (void)cudaGetLastError();
+                if (getenv("DG_TIMING")) fprintf(stderr, "batch: no page-locked block of %zu bytes (%s): this plan goes to the heap\n", bytes, cudaGetErrorString(e));
+            }
         }
         if (block.p) res.reset(new std::pmr::monotonic_buffer_resource(block.p, block.bytes, std::pmr::new_delete_resource()));
     }
@@ -1085,6 +1109,7 @@ struct dg_dip {
     DevBuf<int32_t> p1, p2;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float delta_ms = 0.f, sweep_ms = 0.f, trace_ms = 0.f, plan_ms = 0.f, upload_ms = 0.f;
+    float fused_ms = 0.f;            // > 0: the last run's sweep was part of a fused launch of this duration (dg_dip_run_many)
     int launches = 0;
     bool ran = false, checks = false;
     uint64_t device_bytes = 0;
@@ -1122,7 +1147,7 @@ static int dip_limits(dg_ctx* ctx, DipLimits& lim) {
         cudaFuncAttributes fa;
         const void* fns[] = {(const void*)dip_delta_kernel, (const void*)dip_anc_kernel<uint16_t>, (const void*)dip_anc_kernel<uint32_t>,
                              (const void*)dip_hop_kernel, (const void*)dip_seg_kernel<uint16_t>, (const void*)dip_seg_kernel<uint32_t>,
-                             (const void*)dip_merge_kernel};
+                             (const void*)dip_merge_kernel, (const void*)dip_sweep_many_kernel<false>, (const void*)dip_sweep_many_kernel<true>};
         for (const void* f : fns) DG_CUDA(ctx, cudaFuncGetAttributes(&fa, f));
     }
     int per_sm = 0;
@@ -1266,8 +1291,7 @@ static int dip_create_device(dg_ctx* ctx, dg_dip* d) {
     return DG_OK;
 }
 
-template <class PredT>
-static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
+static int dip_run_pre(dg_ctx* ctx, dg_dip* d, bool check) {
     const DipPlan& p = d->plan;
     cudaStream_t s = d->stream;
     if (d->world > 1) {
@@ -1300,7 +1324,11 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
         DG_CUDA(ctx, cudaGetLastError());
     }
     DG_CUDA(ctx, cudaEventRecord(d->ev[1], s));
-    SweepArgs a;
+    return DG_OK;
+}
+
+static void fill_sweep_args(const dg_dip* d, SweepArgs& a) {
+    const DipPlan& p = d->plan;
     a.tasks = d->tasks.p; a.task_begin = d->task_begin.p; a.records = d->records.p; a.delta = d->delta.p;
     a.delta_off = d->delta_off.p; a.level_off = d->level_off.p; a.in_off = d->in_off.p; a.in_edge = d->in_edge.p;
     a.lvlW = d->lvlW.p; a.msrc_off = d->msrc_off.p; a.mdst_off = d->mdst_off.p; a.masks = d->masks.p;
@@ -1315,17 +1343,12 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
         a.peer_tile0[q] = (int32_t*)d->peer[0][q]; a.peer_tile1[q] = (int32_t*)d->peer[1][q];
         a.peer_pred[q] = (uint8_t*)d->peer[2][q]; a.peer_counter[q] = (unsigned int*)d->peer[3][q];
     }
-    if (p.L > 1) {
-        void* args[] = {(void*)&a};
-        const void* fn = sweep_fn(sizeof(PredT) == 4, check, d->want_prof);
-        // A lone problem is launched cooperatively (the driver guarantees that its CTAs are co-resident, which the
-        // counter barrier needs).  Batch slots use plain launches: B200 runs at most 8 cooperative grids at a time
-        // (measured: 12 slots took two waves), and the batch scheduler already keeps slots x CTAs within the SM
-        // count with one CTA per SM (197 KB of shared memory each), so every grid becomes resident as a whole.
-        if (d->cooperative) DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, s));
-        else DG_CUDA(ctx, cudaLaunchKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, s));
-        ++d->launches;
-    }
+}
+
+template <class PredT>
+static int dip_run_post(dg_ctx* ctx, dg_dip* d, bool check) {
+    const DipPlan& p = d->plan;
+    cudaStream_t s = d->stream;
     DG_CUDA(ctx, cudaEventRecord(d->ev[2], s));
     TraceArgs ta;
     TraceView& v = ta.v;
@@ -1353,6 +1376,29 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     DG_CUDA(ctx, cudaEventRecord(d->ev[3], s));
     d->ran = true; d->checks = check;
     return DG_OK;
+}
+
+
+template <class PredT>
+static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
+    if (int rc = dip_run_pre(ctx, d, check)) return rc;
+    d->fused_ms = 0.f;
+    const DipPlan& p = d->plan;
+    cudaStream_t s = d->stream;
+    SweepArgs a;
+    fill_sweep_args(d, a);
+    if (p.L > 1) {
+        void* args[] = {(void*)&a};
+        const void* fn = sweep_fn(sizeof(PredT) == 4, check, d->want_prof);
+        // A lone problem is launched cooperatively (the driver guarantees that its CTAs are co-resident, which the
+        // counter barrier needs).  Batch slots use plain launches: B200 runs at most 8 cooperative grids at a time
+        // (measured: 12 slots took two waves), and the batch scheduler already keeps slots x CTAs within the SM
+        // count with one CTA per SM (197 KB of shared memory each), so every grid becomes resident as a whole.
+        if (d->cooperative) DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, s));
+        else DG_CUDA(ctx, cudaLaunchKernel(fn, dim3(d->grid), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, s));
+        ++d->launches;
+    }
+    return dip_run_post<PredT>(ctx, d, check);
 }
 
 static int batch_stream(dg_ctx* ctx, int slot, cudaStream_t* out) {
@@ -1404,6 +1450,7 @@ int dg_dip_result(dg_ctx* ctx, dg_dip* d, int32_t* sink_value, int32_t* sink_s_h
                     d->rank, shard_err == 0x7FFFFFFFu ? "exit barrier, code" : "level", shard_err == 0x7FFFFFFFu ? shard_err : shard_err - 1);
     DG_CUDA(ctx, cudaEventElapsedTime(&d->delta_ms, d->ev[0], d->ev[1]));
     DG_CUDA(ctx, cudaEventElapsedTime(&d->sweep_ms, d->ev[1], d->ev[2]));
+    if (d->fused_ms > 0.f) d->sweep_ms = d->fused_ms;      // (its own events also cover the wait for the other problems' pair scores)
     DG_CUDA(ctx, cudaEventElapsedTime(&d->trace_ms, d->ev[2], d->ev[3]));
     if (t.rc == -2) return fail(ctx, DG_ERR_CAPACITY, "dg_dip_result: more than R+2 recorded edges on a path");
     if (sink_value) *sink_value = t.value;
@@ -1707,7 +1754,69 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
     int64_t ctas = 0;
     for (int32_t i = 0; i < n; ++i) if (ds[i] && !ds[i]->cooperative) ctas += ds[i]->grid;
     if (ctas > ctx->sm_count) return fail(ctx, DG_ERR_CAPACITY, "dg_dip_run_many: %lld sweep CTAs do not fit %d SMs", (long long)ctas, ctx->sm_count);
+    // One fused sweep launch for all problems when they allow it (plain-launch slots, same code width, no sharding):
+    // the sweeps then do not need a hardware work queue each, so more than 32 samples can be resident together.
+    bool fused = n >= 2 && !getenv("DG_NO_FUSED_MANY");
+    for (int32_t i = 0; i < n && fused; ++i)
+        fused = ds[i] && !ds[i]->cooperative && ds[i]->world == 1 && ds[i]->plan.L > 1 && ds[i]->pred_bytes == ds[0]->pred_bytes;
     DG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    if (fused) {
+        std::vector<SweepArgs> h_args((size_t)n);
+        std::vector<int2> h_map;
+        for (int32_t i = 0; i < n; ++i) {
+            dg_dip* d = ds[i];
+            d->want_prof = false;
+            DG_CUDA(ctx, cudaStreamWaitEvent(d->stream, e0, 0));
+            if (int r = dip_run_pre(ctx, d, false)) { rc = r; break; }           // resets + pair scores, on the problem's stream
+            DG_CUDA(ctx, cudaEventCreateWithFlags(&done[(size_t)i], cudaEventDisableTiming));
+            DG_CUDA(ctx, cudaEventRecord(done[(size_t)i], d->stream));
+            DG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, done[(size_t)i], 0));
+            fill_sweep_args(d, h_args[(size_t)i]);
+            for (int c = 0; c < d->grid; ++c) h_map.push_back(make_int2(i, c));
+        }
+        DevBuf<SweepArgs> d_args;
+        DevBuf<int2> d_map;
+        cudaEvent_t swept = nullptr, f0 = nullptr;
+        if (!rc) {
+            DG_CUDA(ctx, d_args.upload(h_args.data(), h_args.size(), ctx->stream));
+            DG_CUDA(ctx, d_map.upload(h_map.data(), h_map.size(), ctx->stream));
+            const bool p32 = ds[0]->pred_bytes == 4;
+            const void* fn = p32 ? (const void*)dip_sweep_many_kernel<true> : (const void*)dip_sweep_many_kernel<false>;
+            DG_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
+            const SweepArgs* pa = d_args.p;
+            const int2* pm = d_map.p;
+            void* args[] = {(void*)&pa, (void*)&pm};
+            DG_CUDA(ctx, cudaEventCreate(&f0));
+            DG_CUDA(ctx, cudaEventRecord(f0, ctx->stream));
+            DG_CUDA(ctx, cudaLaunchKernel(fn, dim3((unsigned)h_map.size()), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, ctx->stream));
+            DG_CUDA(ctx, cudaEventCreate(&swept));
+            DG_CUDA(ctx, cudaEventRecord(swept, ctx->stream));
+            for (int32_t i = 0; i < n && !rc; ++i) {
+                dg_dip* d = ds[i];
+                DG_CUDA(ctx, cudaStreamWaitEvent(d->stream, swept, 0));
+                if (i == 0) ++d->launches;                                      // the one fused launch is counted once
+                rc = d->pred_bytes == 2 ? dip_run_post<uint16_t>(ctx, d, false) : dip_run_post<uint32_t>(ctx, d, false);
+                if (rc) break;
+                DG_CUDA(ctx, cudaEventRecord(done[(size_t)i], d->stream));
+                DG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, done[(size_t)i], 0));
+            }
+        }
+        DG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        DG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // (h_args / h_map are read by the copies until here)
+        float ms = 0.f;
+        if (!rc) DG_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        if (wall_ms) *wall_ms = ms;
+        if (!rc && f0 && swept) {
+            float fm = 0.f;
+            DG_CUDA(ctx, cudaEventElapsedTime(&fm, f0, swept));
+            for (int32_t i = 0; i < n; ++i) ds[i]->fused_ms = fm;
+        }
+        if (f0) cudaEventDestroy(f0);
+        if (swept) cudaEventDestroy(swept);
+        for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return rc;
+    }
     for (int32_t i = 0; i < n && !rc; ++i) {
         if (!ds[i]) { rc = DG_ERR_ARG; break; }
         DG_CUDA(ctx, cudaStreamWaitEvent(ds[i]->stream, e0, 0));

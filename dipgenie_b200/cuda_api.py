@@ -250,6 +250,10 @@ class Context:
                             p2_edges=np.array(o.p2_edges[: 2 * o.n_p2], np.int32).reshape(-1, 2)))
         return res
 
+    def release_cached_memory(self):
+        """dg_release_cached_memory: return the pool's cached device blocks (after closing many resident problems)."""
+        self.check(self.lib.dg_release_cached_memory(C.c_void_p(self.h)), "dg_release_cached_memory")
+
     def dip_create(self, g: LevelGraph, R: int, slot: Optional[int] = None, ctas: int = 0) -> "DipProblem":
         return DipProblem(self, g, R, slot, ctas)
 

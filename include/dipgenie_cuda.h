@@ -32,6 +32,10 @@ dg_ctx* dg_create(int device);               /* NULL if the device cannot be ini
 void dg_destroy(dg_ctx* ctx);
 const char* dg_last_error(dg_ctx* ctx);      /* valid until the next call on ctx */
 void dg_free(void* p);                       /* releases library-allocated host arrays */
+/* Device buffers of destroyed problems stay in the context's stream-ordered pool for reuse (a cudaFree of a GB costs
+ * tens of ms).  After a phase that held far more device memory than what follows (e.g. a hundred resident problems),
+ * hand the cached blocks back: waits for the device to be idle. */
+int dg_release_cached_memory(dg_ctx* ctx);
 int dg_device_info(dg_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes);
 
 /* ---- diploid DP: Approximator::diploid_dp_approximation_solver, src/approximator.cpp:362-785 ---

@@ -180,3 +180,34 @@ def test_records_larger_than_a_slot_run_in_lane_form(ctx, oracle_mod):
         o = cuda_dip(ctx, g, R)                      # value, paths and the per-level checksums of every layer
         assert_dip_equal(oracle_dip(oracle_mod, g, R), o)
         assert o["stats"]["n_wide"] > 0
+
+
+def test_cuda_many_resident_problems_one_fused_launch(ctx, oracle_mod, monkeypatch):
+    """dg_dip_run_many starts problems that live in distinct slots together; more than the 32 hardware work queues'
+    worth of them run as ONE sweep launch (dip_sweep_many_kernel: CTA -> (problem, local CTA) map).  Same results as
+    one-by-one runs and as the per-stream launches (DG_NO_FUSED_MANY=1)."""
+    graphs, Rs = [], []
+    for seed in range(40):
+        rng = np.random.default_rng(8100 + seed)
+        if seed % 7 == 3:
+            g = synth.lane_panel_graph(seed, n_lanes=int(rng.integers(8, 50)), n_blocks=3, rec_per_block=2, p_colour=0.25, n_colours=300)
+        else:
+            g = synth.random_level_graph(400 + seed, n_levels=int(rng.integers(2, 50)), max_width=int(rng.integers(1, 26)),
+                                         n_colours=int(rng.integers(0, 120)), p_colour=float(rng.random()))
+        graphs.append(g)
+        Rs.append(int(rng.integers(0, 7)))
+    want = [oracle_dip(oracle_mod, g, R, want_checksums=False) for g, R in zip(graphs, Rs)]
+    probs = [ctx.dip_create(g, R, slot=i, ctas=1 + i % 3) for i, (g, R) in enumerate(zip(graphs, Rs))]
+    try:
+        for mode in ("fused", "streams", "fused"):
+            if mode == "streams":
+                monkeypatch.setenv("DG_NO_FUSED_MANY", "1")
+            else:
+                monkeypatch.delenv("DG_NO_FUSED_MANY", raising=False)
+            ms = ctx.dip_run_many(probs)
+            assert ms > 0
+            for w, p in zip(want, probs):
+                assert_dip_equal(w, p.result(), checks=False)
+    finally:
+        for p in probs:
+            p.close()
