@@ -1273,8 +1273,10 @@ static int dip_create_device(dg_ctx* ctx, dg_dip* d) {
     DG_CUDA(ctx, d->p1.alloc(2 * cap, s));
     DG_CUDA(ctx, d->p2.alloc(2 * cap, s));
     for (auto& e : d->ev) DG_CUDA(ctx, cudaEventCreate(&e));
+    const double t_issued = now_ms();
     DG_CUDA(ctx, cudaStreamSynchronize(s));
     d->upload_ms = (float)(now_ms() - t_up0);
+    if (getenv("DG_TIMING_UPLOAD")) fprintf(stderr, "dip_create_device: allocations + copies issued in %.2f ms, synchronized after %.2f ms\n", t_issued - t_up0, now_ms() - t_up0);
     d->device_bytes = d->tasks.bytes() + d->task_begin.bytes() + d->records.bytes() + d->delta.bytes() + d->delta_off.bytes() +
                       d->delta_list.bytes() + d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->in_dst.bytes() +
                       d->lvlW.bytes() + d->masks.bytes() + d->msrc_off.bytes() + d->mdst_off.bytes() + d->pred_off.bytes() +

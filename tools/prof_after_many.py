@@ -2,6 +2,10 @@
 import sys, os, time
 os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
 sys.path.insert(0, os.getcwd())
+if '--torch' in sys.argv:
+    import torch
+    torch.cuda.set_device(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda'); flush.fill_(1); torch.cuda.synchronize()
 from dipgenie_b200.cuda_api import Context, LevelGraph
 g, _ = LevelGraph.from_npz('tests/golden/mhc4_chm13_dipin.npz')
 ctx = Context(0)
@@ -17,5 +21,5 @@ ctx.dip_run_many(probs)
 if "--no-first" not in sys.argv: batch(f"with {S} resident problems alive:")
 for p in probs: p.close()
 batch(f"after closing them:")
-os.environ["DG_TIMING"] = "1"
+os.environ["DG_TIMING_UPLOAD"] = "1"
 ctx.dp_diploid_batch([g] * 22, 18)
