@@ -173,23 +173,40 @@ struct DeltaArgs {
 // D_l[e1][e2] = |(Hom u1 ∪ Hom v1) ∩ (Hom u2 ∪ Hom v2)| + |(Het u1 ∪ Het v1) △ (Het u2 ∪ Het v2)| for the
 // edge pair e1 = (u1 -> u2), e2 = (v1 -> v2) entering level l+1 (approximator.cpp:604-624), one CTA per
 // coloured transition, all transitions in one launch.
+// One transition's matrix, its elements dealt to `nthr` threads starting at `thr`.
+__device__ __forceinline__ void delta_matrix(const DeltaArgs& a, int l, uint32_t thr, uint32_t nthr) {
+    const int32_t mid = a.level_off[l + 1];
+    const int32_t e0 = a.in_off[mid];
+    const uint32_t n_in = (uint32_t)(a.in_off[a.level_off[l + 2]] - e0);
+    const int W = a.lvlW[l];
+    const uint64_t* msrc = a.masks + a.msrc_off[l];
+    const uint64_t* mdst = a.masks + a.mdst_off[l];
+    uint16_t* D = a.delta + a.delta_off[l];
+    const uint32_t total = n_in * n_in;
+    for (uint32_t x = thr; x < total; x += nthr) {
+        const uint32_t e1 = x / n_in, e2 = x - e1 * n_in;
+        const uint32_t ea = __ldg(a.in_edge + e0 + e1), eb = __ldg(a.in_edge + e0 + e2);
+        const int i2 = (int)__ldg(a.in_dst + e0 + e1), j2 = (int)__ldg(a.in_dst + e0 + e2);
+        D[x] = (uint16_t)mask_delta(W, msrc, mdst, (int)(ea & 0xFFFFu), (int)(eb & 0xFFFFu), i2, j2);
+    }
+}
+
+// Small matrices (a few hundred elements: nearly all of them on real panels) go one per WARP, so that eight times as
+// many chains of dependent index loads are in flight; matrices of more than DELTA_WARP_MAX elements one per block.
+constexpr uint32_t DELTA_WARP_MAX = 2048;
+__device__ __forceinline__ uint32_t delta_elems_of(const DeltaArgs& a, int l) {
+    const uint32_t n_in = (uint32_t)(a.in_off[a.level_off[l + 2]] - a.in_off[a.level_off[l + 1]]);
+    return n_in * n_in;
+}
 __global__ void __launch_bounds__(256) dip_delta_kernel(const DeltaArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int t = blockIdx.x * wpb + warp; t < a.n_list; t += gridDim.x * wpb) {
+        const int l = a.delta_list[t];
+        if (delta_elems_of(a, l) <= DELTA_WARP_MAX) delta_matrix(a, l, (uint32_t)lane, 32u);
+    }
     for (int t = blockIdx.x; t < a.n_list; t += gridDim.x) {
         const int l = a.delta_list[t];
-        const int32_t mid = a.level_off[l + 1];
-        const int32_t e0 = a.in_off[mid];
-        const uint32_t n_in = (uint32_t)(a.in_off[a.level_off[l + 2]] - e0);
-        const int W = a.lvlW[l];
-        const uint64_t* msrc = a.masks + a.msrc_off[l];
-        const uint64_t* mdst = a.masks + a.mdst_off[l];
-        uint16_t* D = a.delta + a.delta_off[l];
-        const uint32_t total = n_in * n_in;
-        for (uint32_t x = threadIdx.x; x < total; x += blockDim.x) {
-            const uint32_t e1 = x / n_in, e2 = x - e1 * n_in;
-            const uint32_t ea = __ldg(a.in_edge + e0 + e1), eb = __ldg(a.in_edge + e0 + e2);
-            const int i2 = (int)__ldg(a.in_dst + e0 + e1), j2 = (int)__ldg(a.in_dst + e0 + e2);
-            D[x] = (uint16_t)mask_delta(W, msrc, mdst, (int)(ea & 0xFFFFu), (int)(eb & 0xFFFFu), i2, j2);
-        }
+        if (delta_elems_of(a, l) > DELTA_WARP_MAX) delta_matrix(a, l, threadIdx.x, blockDim.x);
     }
 }
 
