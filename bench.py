@@ -41,9 +41,10 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 REF_PLAIN = os.path.join(ROOT, "oracle", "_ref", "ref_driver_plain")
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one dip_sweep_kernel launch, from the `ncu --set full` capture
-# summarised in profiles/r01b_sweep_v3.md (114.9 MB + 804.7 MB); None where no capture exists.
-NCU_TRAFFIC = {("mhc4_chm13", 18): 919607040}
+# dram__bytes_read.sum + dram__bytes_write.sum PER SAMPLE of the sweep, from the `ncu --set full` capture of an 8-sample
+# dip_sweep_many_kernel launch (profiles/r01c_sweep_many_ncu.md: 0.740 GB + 6.981 GB for 8 samples; the single-sample
+# dip_sweep_kernel capture of profiles/r01b_sweep_v3.md gave 919.6 MB); None where no capture exists.
+NCU_TRAFFIC = {("mhc4_chm13", 18): 965196000}
 
 
 def load_workload(name: str):
@@ -320,7 +321,7 @@ def main():
                          "algorithmic_bytes_per_launch": st["algo_bytes"] * per_launch, "samples_per_launch": per_launch,
                          "launches_resident_together": 1 if fused else S,
                          "aggregate_achieved": achieved * (1 if fused else S),
-                         "traffic_note": "dram bytes of ONE sample's sweep (ncu --set full of dip_sweep_kernel, profiles/r01b_sweep_v3.md) x samples per launch",
+                         "traffic_note": "dram bytes per sample from the ncu --set full capture of an 8-sample fused launch (profiles/r01c_sweep_many_ncu.md) x samples per launch",
                          "note": "latency-bound at H=5: every sample is a chain of 120 362 dependent level transitions, almost all on one SM; "
                                  "the machine is filled by sweeping samples side by side, one CTA each, in one launch (see DESIGN.md)"},
             "e2e": {"value": world * B * U / (e2e_ms_max * 1e-3), "unit": "cell-updates/s", "ms_per_step": e2e_ms_max,
