@@ -247,6 +247,15 @@ DG_HD uint64_t cell_fold(uint64_t flat, int32_t value, int pred_i, int pred_j) {
 }
 constexpr uint64_t FOLD_BASIS = 1469598103934665603ull;
 
+// Slot of a multi-candidate cell in the level-program engine's code array (dp_prog.h: enumeration A = M x S1,
+// B = S1 x M, C = M x M); vinfo = rank in class | class << 30 (0 S1, 1 M, 2 Z).
+DG_HD int64_t multi_slot_of(uint32_t vi_i, uint32_t vi_j, uint32_t n1, uint32_t m) {
+    const uint32_t ci = vi_i >> 30, cj = vi_j >> 30, ri = vi_i & 0x3FFFFFFFu, rj = vi_j & 0x3FFFFFFFu;
+    if (ci == 1 && cj == 0) return (int64_t)ri * n1 + rj;
+    if (ci == 0 && cj == 1) return (int64_t)m * n1 + (int64_t)rj * n1 + ri;
+    return 2 * (int64_t)m * n1 + (int64_t)ri * m + rj;
+}
+
 // Arrays the traceback needs (device or host pointers).
 struct TraceView {
     int32_t L, R;
@@ -258,6 +267,12 @@ struct TraceView {
     const int64_t* mdst_off;
     const uint64_t* masks;
     const int64_t* pred_off;
+    // level-program engine (dp_prog.h): codes exist for multi-candidate cells only, one u16 per (layer, slot), the
+    // winner's ordinal in (e1,e2) order as 1023 - (code & 1023); vinfo == nullptr selects the task-stream layout
+    const uint32_t* vinfo = nullptr;    // [V] rank in class | class << 30
+    const uint32_t* lvl_n1 = nullptr;   // [L] S1 vertices of the level
+    const uint32_t* lvl_m = nullptr;    // [L] M vertices of the level
+    int32_t RL = 0;                     // layers per level in the code array
 };
 
 struct TraceState { int32_t r, i2, j2; };   // cell (r, i2, j2) of some level
@@ -269,6 +284,26 @@ DG_HD bool trace_step(const TraceView& v, const PredT* pred, int l, TraceState& 
     constexpr int SH = (sizeof(PredT) == 2) ? 8 : 16;
     constexpr uint32_t MK = (sizeof(PredT) == 2) ? 0xFFu : 0xFFFFu;
     const int32_t mid = v.level_off[l + 1];
+    if (v.vinfo) {
+        const int32_t a0 = v.in_off[mid + s.i2], d1 = v.in_off[mid + s.i2 + 1] - a0;
+        const int32_t b0 = v.in_off[mid + s.j2], d2 = v.in_off[mid + s.j2 + 1] - b0;
+        if (d1 <= 0 || d2 <= 0) return false;
+        int32_t ord = 0;
+        if (d1 * d2 > 1) {
+            const uint32_t n1 = v.lvl_n1[l + 1], m = v.lvl_m[l + 1];
+            const int64_t slot = multi_slot_of(v.vinfo[mid + s.i2], v.vinfo[mid + s.j2], n1, m);
+            const int64_t nm = 2 * (int64_t)m * n1 + (int64_t)m * m;
+            const uint32_t raw = (uint32_t)pred[v.pred_off[l + 1] + (int64_t)s.r * nm + slot];
+            ord = (int32_t)(1023u - (raw & 1023u));
+            if (ord >= d1 * d2) ord = d1 * d2 - 1;       // (codes of dead cells are arbitrary; only live paths are ever followed)
+        }
+        const int32_t o1 = ord / d2, o2 = ord - o1 * d2;
+        const uint32_t x = v.in_edge[a0 + o1], y = v.in_edge[b0 + o2];
+        wu = (int)(x >> 16); wv = (int)(y >> 16);
+        i2_old = s.i2; j2_old = s.j2;
+        s.r -= wu + wv; s.i2 = (int)(x & 0xFFFFu); s.j2 = (int)(y & 0xFFFFu);
+        return s.r >= 0;
+    }
     const int32_t k2 = v.level_off[l + 2] - mid;
     const PredT raw = pred[v.pred_off[l + 1] + ((int64_t)s.r * k2 + s.i2) * k2 + s.j2];
     if (raw == (PredT) ~(PredT)0) return false;

@@ -106,6 +106,55 @@ def dp_emu():
     return DpEmu()
 
 
+def _build_emu4():
+    so = os.path.join(EMU_DIR, "libdpemu4.so")
+    cu = os.path.join(ROOT, "dipgenie_b200", "csrc", "cuda")
+    srcs = [os.path.join(EMU_DIR, "dp_emu4.cpp"), os.path.join(cu, "dp_prep.cpp"), os.path.join(cu, "dp_plan4.cpp")]
+    deps = srcs + [os.path.join(cu, h) for h in ("dp_prep.h", "dp_cell.h", "dp_prog.h", "dp_plan4.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-fwrapv", "-fPIC", "-shared", "-o", so] + srcs)
+    return so
+
+
+class DpEmu4:
+    """CPU emulation of the level-program sweep (engine v4: dp_prog.h / dp_plan4.cpp, tests/emu/dp_emu4.cpp)."""
+
+    def __init__(self):
+        self.lib = C.CDLL(_build_emu4())
+
+    def dp_diploid(self, g, R, shape=None):
+        """shape = (slog, kn, slot_bytes, grid, rc) of the emulated kernel geometry (0 = default)."""
+        L = g.n_levels
+        shp = np.zeros(8, np.int32)
+        if shape:
+            shp[: len(shape)] = list(shape)
+        counts = np.zeros(10, np.int64)
+        val, sh, n1, n2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        p1 = np.zeros(2 * (R + 2), np.int32)
+        p2 = np.zeros(2 * (R + 2), np.int32)
+        cs = np.zeros(L, np.uint64)
+        lv = np.zeros(L, np.uint64)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        rc = self.lib.emu4_dp_diploid(
+            C.c_int32(L), P(g.level_off), P(g.adj_off), P(g.adj_dst), P(g.adj_w), P(g.col_off), P(g.col_val),
+            P(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R), C.byref(val), C.byref(sh), P(p1),
+            C.byref(n1), P(p2), C.byref(n2), P(cs), P(lv), P(shp), P(counts))
+        if rc == -2:
+            return None          # outside what the packed-key level program covers (the task-stream engine takes it)
+        if rc != 0:
+            raise RuntimeError(f"emu4_dp_diploid rc={rc}")
+        return dict(value=val.value, s_het=sh.value, p1_edges=p1[: 2 * n1.value].reshape(-1, 2).copy(),
+                    p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy(), checksum=cs, live=lv,
+                    modes=dict(smem=int(counts[0]), all_ctas=int(counts[1]), compact=int(counts[2]), staged=int(counts[3]),
+                               big_cells=int(counts[4]), prog_bytes=int(counts[5]), code_elems=int(counts[6]),
+                               max_cand=int(counts[7])))
+
+
+@pytest.fixture(scope="session")
+def dp_emu4():
+    return DpEmu4()
+
+
 def oracle_dip(oracle_mod, g, R, want_checksums=True):
     return oracle_mod.dp_diploid(g.level_off, g.adj_off, g.adj_dst, g.adj_w, g.col_off, g.col_val, g.colour_is_hom, R,
                                  want_checksums=want_checksums)
