@@ -36,6 +36,7 @@
 
 #include "dg_common.cuh"
 #include "dp_cell.h"
+#include "dp_plan4.h"
 #include "dp_prep.h"
 
 namespace dg {
@@ -952,6 +953,12 @@ __global__ void __launch_bounds__(DIP_THREADS, 1) dip_sweep_many_kernel(const Sw
     sweep_body<false, PRED32, false>(sa, who.y);
 }
 
+}  // namespace dg
+
+#include "dp_sweep4.cuh"
+
+namespace dg {
+
 // ---- K7: traceback ------------------------------------------------------------------------------
 struct TraceOut {           // device-side result block
     int32_t rc, value, s_het, n1, n2, pad[3];
@@ -969,6 +976,7 @@ struct TraceArgs {
     int32_t* seg_p2;
     int32_t* seg_n;           // [M][4]: n1, n2, s_het, rc
     const int32_t* sink_tile;
+    const int32_t* sink_v4;   // level-program engine: the sink cell's layers [R+1] (else null)
     int cap;
     int shift;               // layers hold value << shift
     TraceOut* out;
@@ -1006,7 +1014,8 @@ __global__ void __launch_bounds__(256) dip_anc_kernel(const TraceArgs a) {
 __global__ void dip_hop_kernel(const TraceArgs a) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const int64_t ks = a.v.level_off[a.v.L] - a.v.level_off[a.v.L - 1];
-    const int32_t value = __ldcg(a.sink_tile + (int64_t)a.v.R * ks * ks);   // cell (r=R,0,0) of the last level (:730, :775)
+    const int32_t value = a.sink_v4 ? __ldcg(a.sink_v4 + a.v.R)
+                                    : __ldcg(a.sink_tile + (int64_t)a.v.R * ks * ks);   // cell (r=R,0,0) of the last level (:730, :775)
     a.out->value = value < 0 ? NEG_INF : (value >> a.shift);
     int64_t cur = (value < 0) ? -1 : (int64_t)a.v.R * ks * ks;
     for (int m = 0; m < a.M; ++m) {
@@ -1130,6 +1139,19 @@ struct dg_dip {
     int launches = 0;
     bool ran = false, checks = false;
     uint64_t device_bytes = 0;
+    // level-program engine (dp_prog.h, dp_sweep4.cuh); v4 == false: the task-stream engine above
+    bool v4 = false;
+    Plan4 p4;
+    int v4_ncw = 12;
+    float build_ms = 0.f;            // prog_fill_kernel
+    DevBuf<ProgDir> v4_dir;
+    DevBuf<ProgHdr> v4_hdr;
+    DevBuf<uint64_t> v4_prog_off;
+    DevBuf<int32_t> v4_wide, v4_sink;
+    DevBuf<uint8_t> v4_prog;
+    DevBuf<uint16_t> v4_pred, v4_cls;
+    DevBuf<uint32_t> v4_vinfo, v4_mpre, v4_n1, v4_m, v4_z, v4_dm;
+    DevBuf<int64_t> v4_mpre_off;
     ~dg_dip() {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (ipc_opened)
@@ -1142,6 +1164,43 @@ static const void* sweep_fn(bool pred32, bool check, bool prof = false) {
     if (prof && !check) return pred32 ? (const void*)dip_sweep_kernel<false, true, true> : (const void*)dip_sweep_kernel<false, false, true>;
     if (pred32) return check ? (const void*)dip_sweep_kernel<true, true, false> : (const void*)dip_sweep_kernel<false, true, false>;
     return check ? (const void*)dip_sweep_kernel<true, false, false> : (const void*)dip_sweep_kernel<false, false, false>;
+}
+
+// ---- level-program engine: kernel variants and geometry ----
+static const void* sweep4_fn(int slog, int rc, bool check) {
+    if (slog == 10 && rc == 10) return check ? (const void*)dip_sweep4_kernel<10, 10, true> : (const void*)dip_sweep4_kernel<10, 10, false>;
+    if (slog == 10 && rc == 5) return check ? (const void*)dip_sweep4_kernel<10, 5, true> : (const void*)dip_sweep4_kernel<10, 5, false>;
+    if (slog == 9 && rc == 10) return check ? (const void*)dip_sweep4_kernel<9, 10, true> : (const void*)dip_sweep4_kernel<9, 10, false>;
+    if (slog == 9 && rc == 5) return check ? (const void*)dip_sweep4_kernel<9, 5, true> : (const void*)dip_sweep4_kernel<9, 5, false>;
+    return nullptr;
+}
+static const void* sweep4_many_fn(int slog, int rc) {
+    if (slog == 10 && rc == 10) return (const void*)dip_sweep4_many_kernel<10, 10>;
+    if (slog == 10 && rc == 5) return (const void*)dip_sweep4_many_kernel<10, 5>;
+    if (slog == 9 && rc == 10) return (const void*)dip_sweep4_many_kernel<9, 10>;
+    if (slog == 9 && rc == 5) return (const void*)dip_sweep4_many_kernel<9, 5>;
+    return nullptr;
+}
+constexpr size_t S4_SMEM_MAX = 226 * 1024;   // 227 KB per CTA, less the fused kernel's static argument block
+// Layer chunk and shared-memory layer stride for R: the widest stride whose two tiles of RL + 2 layers fit beside the
+// slot ring.  False: no variant fits (R too large): the task-stream engine takes the problem.
+static bool sweep4_shape(int R, int grid, Sweep4Shape& sh, int& rc) {
+    rc = 10;
+    if (const char* e = getenv("DG_V4_RC")) rc = atoi(e) == 5 ? 5 : 10;
+    sh.slot_bytes = 8192;
+    if (const char* e = getenv("DG_V4_SLOT")) sh.slot_bytes = std::max(256, atoi(e) / 16 * 16);
+    sh.nslot = 4;
+    if (const char* e = getenv("DG_V4_NSLOT")) sh.nslot = std::max(2, std::min(16, atoi(e)));
+    sh.grid = std::max(1, grid);
+    const int RL = (R + rc) / rc * rc;
+    int want = 10;
+    if (const char* e = getenv("DG_V4_SLOG")) want = atoi(e) == 9 ? 9 : 10;
+    for (int slog = want; slog >= 9; --slog)
+        if (sweep4_smem_bytes(slog, RL, sh.slot_bytes, sh.nslot) <= S4_SMEM_MAX) {
+            sh.slog = slog; sh.kn = slog == 10 ? 32 : 22;
+            return true;
+        }
+    return false;
 }
 
 static double now_ms() {
@@ -1164,7 +1223,8 @@ static int dip_limits(dg_ctx* ctx, DipLimits& lim) {
         cudaFuncAttributes fa;
         const void* fns[] = {(const void*)dip_delta_kernel, (const void*)dip_anc_kernel<uint16_t>, (const void*)dip_anc_kernel<uint32_t>,
                              (const void*)dip_hop_kernel, (const void*)dip_seg_kernel<uint16_t>, (const void*)dip_seg_kernel<uint32_t>,
-                             (const void*)dip_merge_kernel, (const void*)dip_sweep_many_kernel<false>, (const void*)dip_sweep_many_kernel<true>};
+                             (const void*)dip_merge_kernel, (const void*)dip_sweep_many_kernel<false>, (const void*)dip_sweep_many_kernel<true>,
+                             (const void*)prog_fill_kernel, (const void*)fill_dead_kernel};
         for (const void* f : fns) DG_CUDA(ctx, cudaFuncGetAttributes(&fa, f));
     }
     int per_sm = 0;
@@ -1205,10 +1265,25 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
     d->lane_rc = shape.lane_rc;
     shape.allow_long = d->shift != 0 && !getenv("DG_NO_LONG");     // slice blocks live in the packed-key kernel
     shape.replicas = d->world; shape.rank = d->rank;
-    plan_tasks(p, shape);
-    d->grid = 1;
-    for (int c = 0; c < p.grid; ++c) if (p.task_begin[(size_t)c + 1] > p.task_begin[c]) d->grid = c + 1;
-    if (d->world > 1) d->grid = p.grid;            // every rank launches the same grid (the exit barrier counts CTAs)
+    d->v4 = false;
+    if (d->world == 1 && !getenv("DG_ENGINE_V3") && !getenv("DG_NO_PACK")) {
+        Sweep4Shape s4;
+        int rc = 10;
+        std::string why = "no kernel variant for this R";
+        if (sweep4_shape(p.R, shape.grid, s4, rc) && plan4_build(p, s4, rc, d->p4, why)) d->v4 = true;
+        else if (getenv("DG_TIMING")) fprintf(stderr, "dg_dip: task-stream engine (%s)\n", why.c_str());
+    }
+    if (d->v4) {
+        d->grid = d->p4.wide_list.empty() ? 1 : shape.grid;      // no HBM-resident transition: CTA 0 does everything
+        d->pred_bytes = 2; d->shift = KEY_SHIFT;
+        d->v4_ncw = 12;
+        if (const char* e = getenv("DG_V4_NCW")) d->v4_ncw = std::max(1, std::min(16, atoi(e)));
+    } else {
+        plan_tasks(p, shape);
+        d->grid = 1;
+        for (int c = 0; c < p.grid; ++c) if (p.task_begin[(size_t)c + 1] > p.task_begin[c]) d->grid = c + 1;
+        if (d->world > 1) d->grid = p.grid;            // every rank launches the same grid (the exit barrier counts CTAs)
+    }
     // traceback checkpoints: cp[0] = sink level, then the narrowest level about every DIP_TRACE_T levels, down to level 0
     d->h_cp = choose_checkpoints(p.level_off, DIP_TRACE_T);
     d->M = (int)d->h_cp.size() - 1;
@@ -1237,8 +1312,101 @@ static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out, cud
     return DG_OK;
 }
 
+// Device half of the level-program engine: the O(V) tables go up, the O(sum E^2) program is written by the device.
+static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DipPlan& p = d->plan;
+    Plan4& q = d->p4;
+    const int L = p.L;
+    const double t_up0 = now_ms();
+    cudaStream_t s = d->stream;
+    {
+        const int smem = (int)sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
+        for (int c = 0; c < 2; ++c) DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_fn(q.shape.slog, q.rc, c != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_many_fn(q.shape.slog, q.rc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    DG_CUDA(ctx, d->level_off.upload(p.level_off.data(), p.level_off.size(), s));
+    DG_CUDA(ctx, d->in_off.upload(p.in_off.data(), p.in_off.size(), s));
+    DG_CUDA(ctx, d->in_edge.upload(p.in_edge.data(), p.in_edge.size(), s));
+    DG_CUDA(ctx, d->lvlW.upload(p.lvlW.data(), p.lvlW.size(), s));
+    DG_CUDA(ctx, d->masks.upload(p.masks.data(), p.masks.size(), s));
+    DG_CUDA(ctx, d->msrc_off.upload(p.msrc_off.data(), p.msrc_off.size(), s));
+    DG_CUDA(ctx, d->mdst_off.upload(p.mdst_off.data(), p.mdst_off.size(), s));
+    DG_CUDA(ctx, d->pred_off.upload(q.pred_off.data(), q.pred_off.size(), s));
+    DG_CUDA(ctx, d->cp.upload(d->h_cp.data(), d->h_cp.size(), s));
+    DG_CUDA(ctx, d->aoff.upload(d->h_aoff.data(), d->h_aoff.size(), s));
+    DG_CUDA(ctx, d->v4_dir.upload(q.dir.data(), q.dir.size(), s));
+    DG_CUDA(ctx, d->v4_hdr.upload(q.hdr.data(), q.hdr.size(), s));
+    DG_CUDA(ctx, d->v4_prog_off.upload(q.prog_off.data(), q.prog_off.size(), s));
+    DG_CUDA(ctx, d->v4_wide.upload(q.wide_list.data(), q.wide_list.size(), s));
+    DG_CUDA(ctx, d->v4_cls.upload(q.cls_list.data(), q.cls_list.size(), s));
+    DG_CUDA(ctx, d->v4_vinfo.upload(q.vinfo.data(), q.vinfo.size(), s));
+    DG_CUDA(ctx, d->v4_mpre.upload(q.mpre.data(), q.mpre.size(), s));
+    DG_CUDA(ctx, d->v4_mpre_off.upload(q.mpre_off.data(), q.mpre_off.size(), s));
+    DG_CUDA(ctx, d->v4_n1.upload(q.lvl_n1.data(), q.lvl_n1.size(), s));
+    DG_CUDA(ctx, d->v4_m.upload(q.lvl_m.data(), q.lvl_m.size(), s));
+    DG_CUDA(ctx, d->v4_z.upload(q.lvl_z.data(), q.lvl_z.size(), s));
+    DG_CUDA(ctx, d->v4_dm.upload(q.lvl_dm.data(), q.lvl_dm.size(), s));
+    DG_CUDA(ctx, d->v4_prog.alloc((size_t)q.prog_bytes + 16, s));
+    DG_CUDA(ctx, d->v4_pred.alloc((size_t)q.pred_elems + 8, s));
+    DG_CUDA(ctx, d->v4_sink.alloc((size_t)p.R + 1, s));
+    DG_CUDA(ctx, d->tile0.alloc((size_t)std::max<int64_t>(q.gtile_cells, 1), s));
+    DG_CUDA(ctx, d->tile1.alloc((size_t)std::max<int64_t>(q.gtile_cells, 1), s));
+    DG_CUDA(ctx, d->counter.alloc(4, s));
+    DG_CUDA(ctx, d->level_sum.alloc((size_t)L, s));
+    DG_CUDA(ctx, d->level_live.alloc((size_t)L, s));
+    DG_CUDA(ctx, d->prof.alloc(32, s));
+    DG_CUDA(ctx, cudaMemsetAsync(d->prof.p, 0, 32 * 8, s));
+    DG_CUDA(ctx, d->anc.alloc((size_t)d->anc_cells, s));
+    DG_CUDA(ctx, d->path_cell.alloc((size_t)std::max(d->M, 1), s));
+    const size_t cap = (size_t)p.R + 2;
+    DG_CUDA(ctx, d->seg_p1.alloc((size_t)std::max(d->M, 1) * 2 * cap, s));
+    DG_CUDA(ctx, d->seg_p2.alloc((size_t)std::max(d->M, 1) * 2 * cap, s));
+    DG_CUDA(ctx, d->seg_n.alloc((size_t)std::max(d->M, 1) * 4, s));
+    DG_CUDA(ctx, d->tout.alloc(1, s));
+    DG_CUDA(ctx, d->p1.alloc(2 * cap, s));
+    DG_CUDA(ctx, d->p2.alloc(2 * cap, s));
+    for (auto& e : d->ev) DG_CUDA(ctx, cudaEventCreate(&e));
+    // the program: zero (section padding), then one CTA per transition
+    DG_CUDA(ctx, cudaEventRecord(d->ev[0], s));
+    DG_CUDA(ctx, cudaMemsetAsync(d->v4_prog.p, 0, (size_t)q.prog_bytes + 16, s));
+    if (q.gpad > 0) {
+        fill_dead_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(d->tile0.p, (long long)q.gpad);
+        fill_dead_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(d->tile1.p, (long long)q.gpad);
+    }
+    Fill4Args fa;
+    fa.l0 = 0; fa.l1 = L - 1; fa.level_off = d->level_off.p; fa.in_off = d->in_off.p; fa.in_edge = d->in_edge.p;
+    fa.cls_list = d->v4_cls.p; fa.mpre = d->v4_mpre.p; fa.mpre_off = d->v4_mpre_off.p;
+    fa.lvl_n1 = d->v4_n1.p; fa.lvl_m = d->v4_m.p; fa.lvl_z = d->v4_z.p; fa.lvl_dm = d->v4_dm.p;
+    fa.lvlW = d->lvlW.p; fa.msrc_off = d->msrc_off.p; fa.mdst_off = d->mdst_off.p; fa.masks = d->masks.p;
+    fa.hdr = d->v4_hdr.p; fa.dir = d->v4_dir.p; fa.prog_off = d->v4_prog_off.p; fa.prog_base = 0; fa.prog = d->v4_prog.p;
+    prog_fill_kernel<<<std::min(L - 1, ctx->sm_count * 16), FILL4_THREADS, 0, s>>>(fa);
+    DG_CUDA(ctx, cudaGetLastError());
+    DG_CUDA(ctx, cudaEventRecord(d->ev[1], s));
+    DG_CUDA(ctx, cudaStreamSynchronize(s));
+    DG_CUDA(ctx, cudaEventElapsedTime(&d->build_ms, d->ev[0], d->ev[1]));
+    d->upload_ms = (float)(now_ms() - t_up0);
+    d->device_bytes = d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->lvlW.bytes() + d->masks.bytes() +
+                      d->msrc_off.bytes() + d->mdst_off.bytes() + d->pred_off.bytes() + d->v4_dir.bytes() + d->v4_hdr.bytes() +
+                      d->v4_prog_off.bytes() + d->v4_cls.bytes() + d->v4_vinfo.bytes() + d->v4_mpre.bytes() + d->v4_prog.bytes() +
+                      d->v4_pred.bytes() + d->tile0.bytes() + d->tile1.bytes() + d->level_sum.bytes() + d->level_live.bytes() +
+                      d->anc.bytes() + d->seg_p1.bytes() + d->seg_p2.bytes();
+    p.in_edge.clear(); p.in_edge.shrink_to_fit();
+    p.in_dst.clear(); p.in_dst.shrink_to_fit();
+    p.masks.clear(); p.masks.shrink_to_fit();
+    p.in_off.clear(); p.in_off.shrink_to_fit();
+    q.cls_list.clear(); q.cls_list.shrink_to_fit();
+    q.vinfo.clear(); q.vinfo.shrink_to_fit();
+    q.mpre.clear(); q.mpre.shrink_to_fit();
+    q.hdr.clear(); q.hdr.shrink_to_fit();
+    q.dir.clear(); q.dir.shrink_to_fit();
+    if (d->staging) d->staging->release();
+    return DG_OK;
+}
+
 // Device half: allocations from the stream-ordered pool and H2D copies on the problem's stream.
 static int dip_create_device(dg_ctx* ctx, dg_dip* d) {
+    if (d->v4) return dip4_create_device(ctx, d);
     DG_CUDA(ctx, cudaSetDevice(ctx->device));
     DipPlan& p = d->plan;
     const int L = p.L;
@@ -1319,6 +1487,8 @@ static int dip_run_pre(dg_ctx* ctx, dg_dip* d, bool check) {
         if (!d->attached || !d->armed) return fail(ctx, DG_ERR_ARG, "dg_dip_run: sharded problem needs dg_dip_ipc_attach and dg_dip_shard_arm first");
         if (check) return fail(ctx, DG_ERR_ARG, "dg_dip_run: level checksums are not available on a sharded problem");
         d->armed = false;
+    } else if (d->v4) {
+        DG_CUDA(ctx, cudaMemsetAsync(d->counter.p, 0, 4 * sizeof(unsigned int), s));            // (level 0 is set up by the kernel)
     } else {
         DG_CUDA(ctx, cudaMemsetAsync(d->counter.p, 0, 2 * sizeof(unsigned int), s));
         DG_CUDA(ctx, cudaMemsetAsync(d->tile0.p, 0, (size_t)(p.R + 1) * sizeof(int32_t), s));   // dp_cur.assign(R+1, {0,0}) :535
@@ -1331,7 +1501,7 @@ static int dip_run_pre(dg_ctx* ctx, dg_dip* d, bool check) {
     }
     d->launches = 0;
     DG_CUDA(ctx, cudaEventRecord(d->ev[0], s));
-    if (!p.delta_list.empty()) {
+    if (!d->v4 && !p.delta_list.empty()) {
         DeltaArgs da;
         da.delta_list = d->delta_list.p; da.n_list = (int32_t)p.delta_list.size(); da.level_off = d->level_off.p;
         da.in_off = d->in_off.p; da.in_edge = d->in_edge.p; da.in_dst = d->in_dst.p; da.lvlW = d->lvlW.p;
@@ -1364,6 +1534,20 @@ static void fill_sweep_args(const dg_dip* d, SweepArgs& a) {
     }
 }
 
+static void fill_sweep4_args(const dg_dip* d, Sweep4Args& a) {
+    const DipPlan& p = d->plan;
+    const Plan4& q = d->p4;
+    a.dir = d->v4_dir.p; a.wide_list = d->v4_wide.p; a.n_trans = p.L - 1; a.n_wide = (int32_t)q.wide_list.size();
+    a.prog = d->v4_prog.p; a.gtile0 = d->tile0.p; a.gtile1 = d->tile1.p; a.gpad = (long long)q.gpad;
+    a.pred = d->v4_pred.p; a.counter = d->counter.p; a.level_sum = d->level_sum.p; a.level_live = d->level_live.p;
+    a.sink = d->v4_sink.p; a.R = p.R; a.nchunk = q.nchunk; a.grid = d->grid; a.ncw = d->v4_ncw;
+    a.slot_bytes = q.shape.slot_bytes; a.nslot = q.shape.nslot; a.m_nchunk = make_magic((uint32_t)q.nchunk); a.last_k = p.level_off[p.L] - p.level_off[p.L - 1]; a.kn = q.shape.kn;
+    a.final_target = q.final_target;
+    a.prof = d->want_prof ? d->prof.p : nullptr;
+    a.timeout_ns = 10000ull * 1000000ull;
+    if (const char* e = getenv("DG_SHARD_TIMEOUT_MS")) a.timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
+}
+
 template <class PredT>
 static int dip_run_post(dg_ctx* ctx, dg_dip* d, bool check) {
     const DipPlan& p = d->plan;
@@ -1377,6 +1561,11 @@ static int dip_run_post(dg_ctx* ctx, dg_dip* d, bool check) {
     ta.pred = d->pred.p; ta.cp = d->cp.p; ta.aoff = d->aoff.p; ta.M = d->M; ta.anc = d->anc.p; ta.path_cell = d->path_cell.p;
     ta.seg_p1 = d->seg_p1.p; ta.seg_p2 = d->seg_p2.p; ta.seg_n = d->seg_n.p;
     ta.sink_tile = ((p.L - 1) & 1) ? d->tile1.p : d->tile0.p;
+    ta.sink_v4 = nullptr;
+    if (d->v4) {
+        ta.pred = d->v4_pred.p; ta.sink_v4 = d->v4_sink.p;
+        v.vinfo = d->v4_vinfo.p; v.lvl_n1 = d->v4_n1.p; v.lvl_m = d->v4_m.p; v.RL = d->p4.RL;
+    }
     ta.cap = p.R + 2; ta.shift = d->shift; ta.out = d->tout.p; ta.p1 = d->p1.p; ta.p2 = d->p2.p;
     if (d->anc_cells > 0) {
         const unsigned blocks = (unsigned)((d->anc_cells + 255) / 256);
@@ -1404,6 +1593,19 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     d->fused_ms = 0.f;
     const DipPlan& p = d->plan;
     cudaStream_t s = d->stream;
+    if (d->v4) {
+        Sweep4Args a4;
+        fill_sweep4_args(d, a4);
+        void* args[] = {(void*)&a4};
+        const Plan4& q = d->p4;
+        const void* fn = sweep4_fn(q.shape.slog, q.rc, check);
+        const size_t smem = sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
+        const dim3 block((unsigned)(d->v4_ncw + 1) * 32u);
+        if (d->cooperative) DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), block, args, smem, s));
+        else DG_CUDA(ctx, cudaLaunchKernel(fn, dim3(d->grid), block, args, smem, s));
+        ++d->launches;
+        return dip_run_post<PredT>(ctx, d, check);
+    }
     SweepArgs a;
     fill_sweep_args(d, a);
     if (p.L > 1) {
@@ -1501,8 +1703,17 @@ int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out) {
     out->sweep_ms = d->sweep_ms; out->traceback_ms = d->trace_ms;
     out->delta_ms = d->delta_ms; out->plan_ms = d->plan_ms; out->upload_ms = d->upload_ms;
     out->n_narrow = (int32_t)d->plan.n_narrow; out->n_wide = (int32_t)d->plan.n_wide;
-    out->n_tasks = (int64_t)d->plan.task_begin.back();
+    out->n_tasks = d->plan.task_begin.empty() ? 0 : (int64_t)d->plan.task_begin.back();
     out->delta_bytes = (uint64_t)d->plan.delta_elems * 2;
+    out->engine = d->v4 ? 4 : 3;
+    if (d->v4) {
+        out->n_narrow = (int32_t)d->p4.n_smem_trans; out->n_wide = (int32_t)d->p4.wide_list.size();
+        out->n_tasks = d->plan.L - 1;
+        out->prog_bytes = d->p4.prog_bytes; out->code_bytes = (uint64_t)d->p4.pred_elems * 2;
+        out->build_ms = d->build_ms;
+    } else {
+        out->code_bytes = (uint64_t)d->plan.pred_off[(size_t)d->plan.L] * (uint64_t)d->pred_bytes;
+    }
     (void)ctx;
     return DG_OK;
 }
@@ -1513,6 +1724,17 @@ int dg_dip_profile(dg_ctx* ctx, dg_dip* d, uint64_t* out24) {
     DG_CUDA(ctx, cudaStreamSynchronize(d->stream));
     memset(out24, 0, 24 * 8);
     DG_CUDA(ctx, cudaMemcpy(out24, d->prof.p, 24 * 8, cudaMemcpyDeviceToHost));
+    return DG_OK;
+}
+
+int dg_dip_debug_program(dg_ctx* ctx, dg_dip* d, uint8_t* out, uint64_t cap, uint64_t* bytes) {
+    if (!ctx || !d || !bytes) return DG_ERR_ARG;
+    *bytes = d->v4 ? d->p4.prog_bytes : 0;
+    if (!d->v4 || !out) return DG_OK;
+    if (cap < d->p4.prog_bytes) return fail(ctx, DG_ERR_CAPACITY, "dg_dip_debug_program: %llu bytes needed", (unsigned long long)d->p4.prog_bytes);
+    DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    DG_CUDA(ctx, cudaStreamSynchronize(d->stream));
+    DG_CUDA(ctx, cudaMemcpy(out, d->v4_prog.p, (size_t)d->p4.prog_bytes, cudaMemcpyDeviceToHost));
     return DG_OK;
 }
 
@@ -1776,11 +1998,19 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
     // One fused sweep launch for all problems when they allow it (plain-launch slots, same code width, no sharding):
     // the sweeps then do not need a hardware work queue each, so more than 32 samples can be resident together.
     bool fused = n >= 2 && !getenv("DG_NO_FUSED_MANY");
-    for (int32_t i = 0; i < n && fused; ++i)
-        fused = ds[i] && !ds[i]->cooperative && ds[i]->world == 1 && ds[i]->plan.L > 1 && ds[i]->pred_bytes == ds[0]->pred_bytes;
+    for (int32_t i = 0; i < n && fused; ++i) {
+        fused = ds[i] && !ds[i]->cooperative && ds[i]->world == 1 && ds[i]->plan.L > 1 && ds[i]->pred_bytes == ds[0]->pred_bytes &&
+                ds[i]->v4 == ds[0]->v4;
+        if (fused && ds[i]->v4)
+            fused = ds[i]->p4.shape.slog == ds[0]->p4.shape.slog && ds[i]->p4.rc == ds[0]->p4.rc && ds[i]->p4.RL == ds[0]->p4.RL &&
+                    ds[i]->p4.shape.slot_bytes == ds[0]->p4.shape.slot_bytes && ds[i]->p4.shape.nslot == ds[0]->p4.shape.nslot &&
+                    ds[i]->v4_ncw == ds[0]->v4_ncw;
+    }
     DG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     if (fused) {
-        std::vector<SweepArgs> h_args((size_t)n);
+        const bool v4 = ds[0]->v4;
+        std::vector<SweepArgs> h_args(v4 ? 0 : (size_t)n);
+        std::vector<Sweep4Args> h_args4(v4 ? (size_t)n : 0);
         std::vector<int2> h_map;
         for (int32_t i = 0; i < n; ++i) {
             dg_dip* d = ds[i];
@@ -1790,24 +2020,36 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
             DG_CUDA(ctx, cudaEventCreateWithFlags(&done[(size_t)i], cudaEventDisableTiming));
             DG_CUDA(ctx, cudaEventRecord(done[(size_t)i], d->stream));
             DG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, done[(size_t)i], 0));
-            fill_sweep_args(d, h_args[(size_t)i]);
+            if (v4) fill_sweep4_args(d, h_args4[(size_t)i]); else fill_sweep_args(d, h_args[(size_t)i]);
             for (int c = 0; c < d->grid; ++c) h_map.push_back(make_int2(i, c));
         }
         DevBuf<SweepArgs> d_args;
+        DevBuf<Sweep4Args> d_args4;
         DevBuf<int2> d_map;
         cudaEvent_t swept = nullptr, f0 = nullptr;
         if (!rc) {
-            DG_CUDA(ctx, d_args.upload(h_args.data(), h_args.size(), ctx->stream));
+            if (v4) DG_CUDA(ctx, d_args4.upload(h_args4.data(), h_args4.size(), ctx->stream));
+            else DG_CUDA(ctx, d_args.upload(h_args.data(), h_args.size(), ctx->stream));
             DG_CUDA(ctx, d_map.upload(h_map.data(), h_map.size(), ctx->stream));
-            const bool p32 = ds[0]->pred_bytes == 4;
-            const void* fn = p32 ? (const void*)dip_sweep_many_kernel<true> : (const void*)dip_sweep_many_kernel<false>;
-            DG_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
-            const SweepArgs* pa = d_args.p;
             const int2* pm = d_map.p;
-            void* args[] = {(void*)&pa, (void*)&pm};
             DG_CUDA(ctx, cudaEventCreate(&f0));
-            DG_CUDA(ctx, cudaEventRecord(f0, ctx->stream));
-            DG_CUDA(ctx, cudaLaunchKernel(fn, dim3((unsigned)h_map.size()), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, ctx->stream));
+            if (v4) {
+                const Plan4& q = ds[0]->p4;
+                const void* fn = sweep4_many_fn(q.shape.slog, q.rc);
+                const size_t smem = sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
+                const Sweep4Args* pa = d_args4.p;
+                void* args[] = {(void*)&pa, (void*)&pm};
+                DG_CUDA(ctx, cudaEventRecord(f0, ctx->stream));
+                DG_CUDA(ctx, cudaLaunchKernel(fn, dim3((unsigned)h_map.size()), dim3((unsigned)(ds[0]->v4_ncw + 1) * 32u), args, smem, ctx->stream));
+            } else {
+                const bool p32 = ds[0]->pred_bytes == 4;
+                const void* fn = p32 ? (const void*)dip_sweep_many_kernel<true> : (const void*)dip_sweep_many_kernel<false>;
+                DG_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIP_SMEM_BYTES));
+                const SweepArgs* pa = d_args.p;
+                void* args[] = {(void*)&pa, (void*)&pm};
+                DG_CUDA(ctx, cudaEventRecord(f0, ctx->stream));
+                DG_CUDA(ctx, cudaLaunchKernel(fn, dim3((unsigned)h_map.size()), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, ctx->stream));
+            }
             DG_CUDA(ctx, cudaEventCreate(&swept));
             DG_CUDA(ctx, cudaEventRecord(swept, ctx->stream));
             for (int32_t i = 0; i < n && !rc; ++i) {
@@ -1821,7 +2063,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
             }
         }
         DG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
-        DG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // (h_args / h_map are read by the copies until here)
+        DG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // (the argument vectors are read by the copies until here)
         float ms = 0.f;
         if (!rc) DG_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
         if (wall_ms) *wall_ms = ms;

@@ -16,6 +16,7 @@ bool plan4_build(const DipPlan& p, const Sweep4Shape& shape, int rc, Plan4& q, s
     if (L < 2) { why = "single level"; return false; }
     if (p.value_bound >= KEY_VALUE_LIMIT) { why = "DP values may exceed the packed key"; return false; }
     if ((int64_t)shape.kn * shape.kn > ((int64_t)1 << shape.slog)) { why = "bad shape"; return false; }
+    if (p.kmax >= 32768) { why = "level wider than 32767 vertices"; return false; }
     const int32_t V = p.V;
     q.cls_list.assign((size_t)V, 0);
     q.vinfo.assign((size_t)V, 0);
@@ -81,11 +82,15 @@ bool plan4_build(const DipPlan& p, const Sweep4Shape& shape, int rc, Plan4& q, s
         if (k <= shape.kn) f |= PF_SRC_SMEM;
         if (k2 <= shape.kn) f |= PF_DST_SMEM;
         q.dir[l].flags = f;
-        bytes[l] = prog_layout(compact, n.n_copy, n.n_multi, n.n_cand, n.n_big, n.n_dead).end;
+        const ProgLayout lay = prog_layout(compact, n.n_copy, n.n_multi, n.n_cand, n.n_big, n.n_dead);
+        h.off_cell = (uint32_t)lay.cell; h.off_cand = (uint32_t)lay.cand; h.off_big = (uint32_t)lay.big; h.off_dead = (uint32_t)lay.dead;
+        if (lay.end > 0xFFFFFFFFull) bytes[l] = ~0ull; else
+        bytes[l] = lay.end;
     }
     uint32_t cum = 0;
     int64_t kg = 0;
     for (int l = 0; l + 1 < L; ++l) {
+        if (bytes[l] == ~0ull) { why = "a transition's program exceeds 4 GB"; return false; }
         q.prog_off[(size_t)l + 1] = q.prog_off[l] + bytes[l];
         ProgDir& d = q.dir[l];
         const bool ss = d.flags & PF_SRC_SMEM, ds = d.flags & PF_DST_SMEM;
@@ -100,6 +105,7 @@ bool plan4_build(const DipPlan& p, const Sweep4Shape& shape, int rc, Plan4& q, s
         if (bytes[l] + sizeof(ProgDir) <= (uint64_t)shape.slot_bytes) { d.flags |= PF_STAGED; d.stage_bytes = (uint32_t)bytes[l]; }
         else d.stage_bytes = (uint32_t)sizeof(ProgHdr);
     }
+    q.final_target = cum;
     q.prog_bytes = q.prog_off[(size_t)L - 1];
     for (int l = 0; l < L; ++l) {
         const int64_t nm = l >= 1 ? (int64_t)q.hdr[(size_t)l - 1].n_multi : 0;

@@ -35,6 +35,7 @@ struct Plan4 {
     int64_t gpad = 0, gtile_cells = 0;   // HBM tile: gpad dead cells, then RL layers of the widest HBM-resident level
     int64_t n_smem_trans = 0;            // transitions with both layers in shared memory
     uint32_t max_cand = 0;
+    uint32_t final_target = 0;           // barrier arrivals once the last transition is complete
 };
 
 // Returns false (with `why`) when the problem is outside what the packed-key level program covers; the caller then

@@ -64,15 +64,16 @@ struct ProgDir {
 };
 static_assert(sizeof(ProgDir) == 16, "ProgDir layout");
 
-struct ProgHdr {           // 48 bytes
+struct ProgHdr {           // 64 bytes
     uint16_t k, k2;
     uint32_t n_copy, n_multi, n_cand, n_big, n_dead;
     uint32_t max_n;        // most candidates of a thread-form multi cell (loop bound hint)
     uint32_t rsv;
     uint64_t pred_off;     // u16 elements: codes of level l+1 start here, layout [layer][slot]
     uint64_t rsv2;
+    uint32_t off_cell, off_cand, off_big, off_dead;   // section offsets from the header's start (prog_layout; the copy section follows the header)
 };
-static_assert(sizeof(ProgHdr) == 48, "ProgHdr layout");
+static_assert(sizeof(ProgHdr) == 64, "ProgHdr layout");
 
 DG_HD size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
 
@@ -243,6 +244,7 @@ struct Sweep4Shape {
     int slog = 10;             // shared-memory layer stride = 1 << slog cells
     int kn = 32;               // levels at most this wide live in shared memory (kn * kn <= 1 << slog)
     int slot_bytes = 8192;     // ring slot (directory entry + program)
+    int nslot = 4;             // ring depth
     int grid = 1;              // CTAs of the problem
 };
 

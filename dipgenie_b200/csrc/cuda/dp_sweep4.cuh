@@ -1,0 +1,724 @@
+// dp_sweep4.cuh — device side of the level-program engine (v4) of the diploid DP: the program builder
+// (prog_fill_kernel) and the persistent sweep kernel (dip_sweep4_kernel / dip_sweep4_many_kernel).  Included by
+// dp_diploid.cu only (it uses that file's PTX helpers).  Format and semantics: dp_prog.h; host planning: dp_plan4.cpp.
+//
+// Replaces the relax loop of Approximator::diploid_dp_approximation_solver (reference src/approximator.cpp:627-701).
+//
+// Sweep kernel, per problem:
+//   * CTA 0 keeps the two DP layers of every level at most `kn` wide in shared-memory tiles of FIXED layer stride
+//     (1 << SLOG cells): layer r of a cell is one LDS/STS with an immediate offset, no address arithmetic per layer;
+//     wider levels live in HBM/L2 tiles and their transitions are shared by all CTAs of the problem (monotone
+//     counter barrier); hand-over transitions between the two placements run on CTA 0;
+//   * a producer warp streams every transition's directory entry and program into a ring of shared-memory slots
+//     with TMA bulk copies (cp.async.bulk + mbarrier full/empty pairs), several levels ahead;
+//   * the compute warps share a transition's work units round-robin: big cells (one warp per cell, lanes over
+//     candidates, REDUX.MAX per layer), blocks of 32 multi cells (one thread per cell, candidates in a loop), blocks
+//     of 32 copy cells (one thread per cell) and blocks of dead cells; every unit handles all layers, RC at a time
+//     in registers;
+//   * one named barrier per level; predecessor codes (u16 per layer and multi cell) are the only HBM stream.
+#pragma once
+
+#include "dg_common.cuh"
+#include "dp_cell.h"
+#include "dp_prog.h"
+
+namespace dg {
+
+// ---- builder -----------------------------------------------------------------------------------------------------
+struct Fill4Args {
+    int32_t l0, l1;                      // transitions [l0, l1) are written (a window of the program)
+    const int32_t* level_off;
+    const int32_t* in_off;
+    const uint32_t* in_edge;
+    const uint16_t* cls_list;
+    const uint32_t* mpre;
+    const int64_t* mpre_off;
+    const uint32_t* lvl_n1; const uint32_t* lvl_m; const uint32_t* lvl_z; const uint32_t* lvl_dm;
+    const int32_t* lvlW;
+    const int64_t* msrc_off; const int64_t* mdst_off;
+    const uint64_t* masks;
+    const ProgHdr* hdr;
+    const ProgDir* dir;
+    const uint64_t* prog_off;            // byte offsets, absolute
+    uint64_t prog_base;                  // byte offset of `prog` within the whole program (windowed building)
+    uint8_t* prog;
+};
+
+constexpr int FILL4_THREADS = 256;
+
+// One CTA per transition (grid-stride).  The buffer is zeroed beforehand (section padding).
+__global__ void __launch_bounds__(FILL4_THREADS) prog_fill_kernel(const Fill4Args a) {
+    __shared__ uint32_t warp_cnt[FILL4_THREADS / 32];
+    __shared__ uint32_t big_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int l = a.l0 + (int)blockIdx.x; l < a.l1; l += (int)gridDim.x) {
+        const ProgHdr h = a.hdr[l];
+        const bool compact = (a.dir[l].flags & PF_COMPACT) != 0;
+        const ProgLayout lay = prog_layout(compact, h.n_copy, h.n_multi, h.n_cand, h.n_big, h.n_dead);
+        uint8_t* const out = a.prog + (a.prog_off[l] - a.prog_base);
+        ProgLevelIn in;
+        const int32_t mid = a.level_off[l + 1];
+        in.k = h.k; in.k2 = h.k2;
+        in.in_off = a.in_off + mid;
+        in.in_edge = a.in_edge;
+        in.cls.k2 = h.k2; in.cls.n1 = a.lvl_n1[l + 1]; in.cls.m = a.lvl_m[l + 1]; in.cls.z = a.lvl_z[l + 1]; in.cls.dm = a.lvl_dm[l + 1];
+        in.cls.list = a.cls_list + mid;
+        in.cls.mpre = a.mpre + a.mpre_off[l + 1];
+        in.W = a.lvlW[l];
+        in.msrc = in.W ? a.masks + a.msrc_off[l] : nullptr;
+        in.mdst = in.W ? a.masks + a.mdst_off[l] : nullptr;
+        if (tid < (int)(sizeof(ProgHdr) / 4)) reinterpret_cast<uint32_t*>(out)[tid] = reinterpret_cast<const uint32_t*>(&a.hdr[l])[tid];
+        if (tid == 0) big_base = 0;
+        __syncthreads();
+        for (uint32_t t = (uint32_t)tid; t < h.n_copy; t += FILL4_THREADS) {
+            const CopyDesc d = make_copy(in, t);
+            if (compact) reinterpret_cast<uint32_t*>(out + lay.copy)[t] = pack_copy_c(d);
+            else reinterpret_cast<uint4*>(out + lay.copy)[t] = make_uint4(d.src | (d.w << 30), d.dst, d.delta, 0u);
+        }
+        // multi cells in slot order, FILL4_THREADS at a time (the big list is an ordered compaction)
+        for (uint32_t t0 = 0; t0 < h.n_multi; t0 += FILL4_THREADS) {
+            const uint32_t t = t0 + (uint32_t)tid;
+            bool is_big = false;
+            if (t < h.n_multi) {
+                const MultiCell c = multi_cell(in, t);
+                const uint32_t dst = c.i2 * in.k2 + c.j2;
+                if (compact) reinterpret_cast<uint2*>(out + lay.cell)[t] = make_uint2(dst | (c.n << 16), (uint32_t)c.cand_off);
+                else reinterpret_cast<uint4*>(out + lay.cell)[t] = make_uint4(dst, c.n, (uint32_t)c.cand_off, 0u);
+                for (uint32_t o = 0; o < c.n; ++o) {
+                    const CandDesc d = make_cand(in, c, o);
+                    if (compact) reinterpret_cast<uint32_t*>(out + lay.cand)[c.cand_off + o] = pack_cand_c(d);
+                    else reinterpret_cast<uint2*>(out + lay.cand)[c.cand_off + o] = make_uint2(d.src | (d.w << 30), d.delta);
+                }
+                is_big = c.n >= PROG_BIG_MIN;
+            }
+            if (h.n_big) {                                         // (uniform over the CTA)
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, is_big);
+                if (lane == 0) warp_cnt[warp] = (uint32_t)__popc(bal);
+                __syncthreads();
+                uint32_t before = big_base;
+                for (int w = 0; w < warp; ++w) before += warp_cnt[w];
+                if (is_big) reinterpret_cast<uint32_t*>(out + lay.big)[before + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = t;
+                __syncthreads();
+                if (tid == 0) { uint32_t s = 0; for (int w = 0; w < FILL4_THREADS / 32; ++w) s += warp_cnt[w]; big_base += s; }
+                __syncthreads();
+            }
+        }
+        for (uint32_t x = (uint32_t)tid; x < h.n_dead; x += FILL4_THREADS) reinterpret_cast<uint32_t*>(out + lay.dead)[x] = dead_cell(in, x);
+        __syncthreads();
+    }
+}
+
+// Fills `n` int32 cells with DEAD (padding layers of the HBM tiles).
+__global__ void fill_dead_kernel(int32_t* p, long long n) {
+    for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) p[x] = V4_DEAD;
+}
+
+// ---- sweep -------------------------------------------------------------------------------------------------------
+
+struct Sweep4Args {
+    const ProgDir* dir;           // [L-1]
+    const int32_t* wide_list;     // transitions every CTA takes part in
+    int32_t n_trans, n_wide;
+    const uint8_t* prog;
+    int32_t* gtile0; int32_t* gtile1;     // HBM tiles: gpad dead cells, then RL layers of stride k^2
+    long long gpad;
+    uint16_t* pred;
+    unsigned int* counter;        // [0] level arrivals, [1] first barrier that timed out (level + 1), sticky
+    unsigned long long* level_sum;
+    unsigned long long* level_live;
+    int32_t* sink;                // [R+1] layer values (still shifted) of cell (0,0) of the last level
+    int32_t R, nchunk;            // nchunk * RC layers are computed
+    int32_t grid, ncw;            // CTAs of the problem, compute warps per CTA
+    int32_t slot_bytes, nslot;    // ring geometry
+    uint32_t m_nchunk;            // magic of nchunk (dp_cell.h: make_magic; 0 when nchunk == 1)
+    int32_t last_k;               // width of the last level
+    int32_t kn;
+    uint32_t final_target;        // arrivals once the last transition is complete
+    unsigned long long* prof;     // diagnostics (nullable): cycles of CTA 0 / thread 0 in [slot wait, level work, barrier], levels
+    unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ void bar_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+template <int IMM> __device__ __forceinline__ int32_t lds_imm(uint32_t a) {
+    int32_t v;
+    asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(IMM));
+    return v;
+}
+template <int IMM> __device__ __forceinline__ void sts_imm(uint32_t a, int32_t v) {
+    asm volatile("st.shared.s32 [%0+%1], %2;" ::"r"(a), "n"(IMM), "r"(v) : "memory");
+}
+template <int SLOG, int RC, int Q = 0>
+__device__ __forceinline__ void lds_layers(uint32_t a, int32_t (&v)[RC]) {
+    if constexpr (Q < RC) { v[Q] = lds_imm<(Q << (SLOG + 2))>(a); lds_layers<SLOG, RC, Q + 1>(a, v); }
+}
+template <int SLOG, int RC, int Q = 0>
+__device__ __forceinline__ void sts_layers(uint32_t a, const int32_t (&v)[RC]) {
+    if constexpr (Q < RC) { sts_imm<(Q << (SLOG + 2))>(a, v[Q]); sts_layers<SLOG, RC, Q + 1>(a, v); }
+}
+
+// What a compute warp knows about the transition it is working on.
+struct Lvl4 {
+    const uint8_t* copy_p; const uint8_t* cell_p; const uint8_t* cand_p; const uint8_t* big_p; const uint8_t* dead_p;   // generic pointers (slot or HBM)
+    uint32_t k, k2, n_copy, n_multi, n_big, n_dead;
+    uint32_t src32, dst32;                // shared-memory tiles: address of padding layer -2
+    const int32_t* gsrc; int32_t* gdst;   // HBM tiles: address of layer 0
+    long long kk, kk2;
+    uint16_t* pl;                         // codes of level l+1, [layer][slot]
+    int level, R, nchunk;
+};
+
+template <bool COMPACT> __device__ __forceinline__ CopyDesc ld_copy(const uint8_t* p, uint32_t t) {
+    if (COMPACT) return unpack_copy_c(reinterpret_cast<const uint32_t*>(p)[t]);
+    const uint4 x = reinterpret_cast<const uint4*>(p)[t];
+    return {x.x & 0x3FFFFFFFu, x.y, x.x >> 30, x.z};
+}
+template <bool COMPACT> __device__ __forceinline__ CellDesc ld_cell(const uint8_t* p, uint32_t t) {
+    if (COMPACT) { const uint2 x = reinterpret_cast<const uint2*>(p)[t]; return {x.x & 1023u, x.x >> 16, x.y}; }
+    const uint4 x = reinterpret_cast<const uint4*>(p)[t];
+    return {x.x, x.y, x.z};
+}
+template <bool COMPACT> __device__ __forceinline__ CandDesc ld_cand(const uint8_t* p, uint32_t x) {
+    if (COMPACT) return unpack_cand_c(reinterpret_cast<const uint32_t*>(p)[x]);
+    const uint2 y = reinterpret_cast<const uint2*>(p)[x];
+    return {y.x & 0x3FFFFFFFu, y.x >> 30, y.y};
+}
+
+// RC consecutive layers r0 .. r0+RC-1 of source cell `src`, read w layers lower (padding layers are DEAD).
+template <int SLOG, int RC, bool SS>
+__device__ __forceinline__ void load_layers(const Lvl4& c, int r0, uint32_t src, uint32_t w, int32_t (&v)[RC]) {
+    if (SS) {
+        lds_layers<SLOG, RC>(c.src32 + ((((uint32_t)(r0 + 2) - w) << SLOG) + src) * 4u, v);
+    } else {
+        const int32_t* p = c.gsrc + ((long long)(r0 - (int)w) * c.kk + (long long)src);
+#pragma unroll
+        for (int q = 0; q < RC; ++q) v[q] = __ldcg(p + (long long)q * c.kk);
+    }
+}
+template <int SLOG, int RC, bool DS>
+__device__ __forceinline__ void store_layers(const Lvl4& c, int r0, uint32_t dst, const int32_t (&v)[RC]) {
+    if (DS) {
+        sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, v);
+    } else {
+        int32_t* p = c.gdst + ((long long)r0 * c.kk2 + (long long)dst);
+#pragma unroll
+        for (int q = 0; q < RC; ++q) __stcg(p + (long long)q * c.kk2, v[q]);
+    }
+}
+
+struct Fold4 { unsigned long long sum, live; };
+__device__ __forceinline__ void fold4(Fold4& f, const Lvl4& c, int r, uint32_t dst, int32_t val, uint32_t src) {
+    if (r > c.R || val < 0) return;
+    ++f.live;
+    f.sum += cell_fold((uint64_t)r * (uint64_t)c.kk2 + dst, val >> V4_SHIFT, (int)(src / c.k), (int)(src % c.k));
+}
+
+// 32 copy cells, one thread each: dst = src shifted by w layers, plus delta.
+template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
+__device__ __forceinline__ void copy_block(const Lvl4& c, uint32_t blk, int lane, Fold4& f) {
+    const uint32_t t = blk * 32u + (uint32_t)lane;
+    const bool active = t < c.n_copy;
+    CopyDesc d = {0u, 0u, 0u, 0u};
+    if (active) d = ld_copy<COMPACT>(c.copy_p, t);
+    const int32_t add = (int32_t)(d.delta << V4_SHIFT);
+    for (int ch = 0; ch < c.nchunk; ++ch) {
+        const int r0 = ch * RC;
+        int32_t v[RC];
+        load_layers<SLOG, RC, SS>(c, r0, d.src, d.w, v);
+#pragma unroll
+        for (int q = 0; q < RC; ++q) v[q] += add;
+        if (active) {
+            store_layers<SLOG, RC, DS>(c, r0, d.dst, v);
+            if (CHECK) {
+#pragma unroll
+                for (int q = 0; q < RC; ++q) fold4(f, c, r0 + q, d.dst, v[q], d.src);
+            }
+        }
+    }
+}
+
+// 32 multi cells, one thread each, candidates in a loop (cells of PROG_BIG_MIN candidates or more belong to the warp form).
+template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
+__device__ __forceinline__ void multi_block(const Lvl4& c, uint32_t blk, int lane, Fold4& f) {
+    const uint32_t t = blk * 32u + (uint32_t)lane;
+    CellDesc cd = {0u, 0u, 0u};
+    if (t < c.n_multi) cd = ld_cell<COMPACT>(c.cell_p, t);
+    const uint32_t n = cd.n >= PROG_BIG_MIN ? 0u : cd.n;
+    const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n);
+    if (nmax == 0) return;
+    for (int ch = 0; ch < c.nchunk; ++ch) {
+        const int r0 = ch * RC;
+        int32_t key[RC];
+#pragma unroll
+        for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
+        for (uint32_t o = 0; o < nmax; ++o) {
+            if (o < n) {
+                const CandDesc e = ld_cand<COMPACT>(c.cand_p, cd.cand_off + o);
+                const int32_t add = (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - o));
+                int32_t v[RC];
+                load_layers<SLOG, RC, SS>(c, r0, e.src, e.w, v);
+#pragma unroll
+                for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
+            }
+        }
+        if (n) {
+            uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
+            int32_t val[RC];
+#pragma unroll
+            for (int q = 0; q < RC; ++q) {
+                val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
+                pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
+            }
+            store_layers<SLOG, RC, DS>(c, r0, cd.dst, val);
+            if (CHECK) {
+#pragma unroll
+                for (int q = 0; q < RC; ++q) {
+                    if (val[q] >= 0 && r0 + q <= c.R) {
+                        const uint32_t o = V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
+                        fold4(f, c, r0 + q, cd.dst, val[q], ld_cand<COMPACT>(c.cand_p, cd.cand_off + o).src);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One big cell per warp: lanes over candidates, 32 at a time, then one REDUX.MAX per layer.
+template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
+__device__ __forceinline__ void big_cell(const Lvl4& c, uint32_t u, int lane, Fold4& f) {
+    const uint32_t t = reinterpret_cast<const uint32_t*>(c.big_p)[u];
+    const CellDesc cd = ld_cell<COMPACT>(c.cell_p, t);
+    for (int ch = 0; ch < c.nchunk; ++ch) {
+        const int r0 = ch * RC;
+        int32_t key[RC];
+#pragma unroll
+        for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
+        for (uint32_t o = (uint32_t)lane; o < cd.n; o += 32u) {
+            const CandDesc e = ld_cand<COMPACT>(c.cand_p, cd.cand_off + o);
+            const int32_t add = (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - o));
+            int32_t v[RC];
+            load_layers<SLOG, RC, SS>(c, r0, e.src, e.w, v);
+#pragma unroll
+            for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
+        }
+#pragma unroll
+        for (int q = 0; q < RC; ++q) key[q] = __reduce_max_sync(0xFFFFFFFFu, key[q]);
+        if (lane == 0) {
+            uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
+            int32_t val[RC];
+#pragma unroll
+            for (int q = 0; q < RC; ++q) {
+                val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
+                pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
+            }
+            store_layers<SLOG, RC, DS>(c, r0, cd.dst, val);
+            if (CHECK) {
+#pragma unroll
+                for (int q = 0; q < RC; ++q) {
+                    if (val[q] >= 0 && r0 + q <= c.R) {
+                        const uint32_t o = V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
+                        fold4(f, c, r0 + q, cd.dst, val[q], ld_cand<COMPACT>(c.cand_p, cd.cand_off + o).src);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int SLOG, int RC, bool DS>
+__device__ __forceinline__ void dead_block(const Lvl4& c, uint32_t blk, int lane) {
+    const uint32_t x = blk * 32u + (uint32_t)lane;
+    if (x >= c.n_dead) return;
+    const uint32_t dst = reinterpret_cast<const uint32_t*>(c.dead_p)[x];
+    int32_t v[RC];
+#pragma unroll
+    for (int q = 0; q < RC; ++q) v[q] = V4_DEAD;
+    for (int ch = 0; ch < c.nchunk; ++ch) store_layers<SLOG, RC, DS>(c, ch * RC, dst, v);
+}
+
+// The work units of one transition, dealt round-robin to the (global) warps gw, gw + gstride, ...: heaviest first.
+template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
+__device__ __forceinline__ void run_level(const Lvl4& c, uint32_t gw, uint32_t gstride, int lane, Fold4& f) {
+    const uint32_t nmb = (c.n_multi + 31u) >> 5, ncb = (c.n_copy + 31u) >> 5, ndb = (c.n_dead + 31u) >> 5;
+    const uint32_t e0 = c.n_big, e1 = e0 + nmb, e2 = e1 + ncb, e3 = e2 + ndb;
+    for (uint32_t u = gw; u < e3; u += gstride) {
+        if (u < e0) big_cell<SLOG, RC, SS, DS, COMPACT, CHECK>(c, u, lane, f);
+        else if (u < e1) multi_block<SLOG, RC, SS, DS, COMPACT, CHECK>(c, u - e0, lane, f);
+        else if (u < e2) copy_block<SLOG, RC, SS, DS, COMPACT, CHECK>(c, u - e1, lane, f);
+        else dead_block<SLOG, RC, DS>(c, u - e2, lane);
+    }
+}
+
+// Everything but the staged compact transitions (below): hand-overs between the placements, HBM-resident levels,
+// wide-format programs, programs read in place.  Out of line, with a handful of scalar arguments: the narrow loop keeps
+// its own register allocation.  `sb` = the ring slot (directory entry, then the header and, if staged, the program).
+template <int SLOG, int RC, bool CHECK>
+__device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_t* sb, uint32_t tiles32, uint32_t tile_bytes,
+                                               int l, int cta, int warp, int lane) {
+    const ProgDir d = *reinterpret_cast<const ProgDir*>(sb);
+    const ProgHdr h = *reinterpret_cast<const ProgHdr*>(sb + sizeof(ProgDir));
+    const uint32_t flags = d.flags;
+    Lvl4 c;
+    c.k = h.k; c.k2 = h.k2; c.n_copy = h.n_copy; c.n_multi = h.n_multi; c.n_big = h.n_big; c.n_dead = h.n_dead;
+    const uint8_t* const pb = (flags & PF_STAGED) ? sb + sizeof(ProgDir) : a.prog + (size_t)d.off16 * 16;
+    c.copy_p = pb + sizeof(ProgHdr); c.cell_p = pb + h.off_cell; c.cand_p = pb + h.off_cand; c.big_p = pb + h.off_big; c.dead_p = pb + h.off_dead;
+    c.level = l; c.R = a.R; c.nchunk = a.nchunk;
+    const uint32_t odd = (uint32_t)l & 1u;
+    c.src32 = tiles32 + odd * tile_bytes; c.dst32 = tiles32 + (odd ^ 1u) * tile_bytes;
+    c.gsrc = (odd ? a.gtile1 : a.gtile0) + a.gpad; c.gdst = (odd ? a.gtile0 : a.gtile1) + a.gpad;
+    c.kk = (long long)c.k * c.k; c.kk2 = (long long)c.k2 * c.k2;
+    c.pl = a.pred + h.pred_off;
+    const bool all = (flags & PF_ALL_CTAS) != 0;
+    const uint32_t gw = all ? (uint32_t)(cta * a.ncw + warp) : (uint32_t)warp;
+    const uint32_t gs = all ? (uint32_t)(a.grid * a.ncw) : (uint32_t)a.ncw;
+    const bool ss = (flags & PF_SRC_SMEM) != 0, ds = (flags & PF_DST_SMEM) != 0;
+    Fold4 f = {0ull, 0ull};
+    if (flags & PF_COMPACT) run_level<SLOG, RC, true, true, true, CHECK>(c, gw, gs, lane, f);
+    else if (ss && ds) run_level<SLOG, RC, true, true, false, CHECK>(c, gw, gs, lane, f);
+    else if (ss) run_level<SLOG, RC, true, false, false, CHECK>(c, gw, gs, lane, f);
+    else if (ds) run_level<SLOG, RC, false, true, false, CHECK>(c, gw, gs, lane, f);
+    else run_level<SLOG, RC, false, false, false, CHECK>(c, gw, gs, lane, f);
+    return make_ulonglong2(f.sum, f.live);
+}
+
+// ---- the narrow loop: compact program staged in the slot, both layers in shared memory -------------------------------
+// Everything is a 32-bit shared-window address; a unit is (kind, block of 32 cells or one big cell, chunk of RC layers), so
+// that the dozen units of a typical level spread over as many warps and the level's critical path is one chunk of one block.
+struct Fast4 {
+    uint32_t copy32, cell32, cand32, big32, dead32;
+    uint32_t n_copy, n_multi, n_big, n_dead;
+    uint32_t src32, dst32;        // tiles: address of padding layer -2
+    uint16_t* pl;                 // codes of level l+1
+    uint32_t k, kk2;
+    int R;
+};
+
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+
+__device__ __forceinline__ void fold4f(Fold4& f, const Fast4& c, int r, uint32_t dst, int32_t val, uint32_t src) {
+    if (r > c.R || val < 0) return;
+    ++f.live;
+    f.sum += cell_fold((uint64_t)r * c.kk2 + dst, val >> V4_SHIFT, (int)(src / c.k), (int)(src % c.k));
+}
+
+template <int SLOG, int RC, bool CHECK>
+__device__ __forceinline__ void fast_copy(const Fast4& c, uint32_t blk, int r0, int lane, Fold4& f) {
+    const uint32_t t = blk * 32u + (uint32_t)lane;
+    const bool active = t < c.n_copy;
+    const uint32_t x = active ? lds_u32(c.copy32 + 4u * t) : 0u;
+    const uint32_t src = x & 1023u, dst = (x >> 10) & 1023u, w = (x >> 20) & 3u;
+    const int32_t add = (int32_t)((x >> 22) << V4_SHIFT);
+    int32_t v[RC];
+    lds_layers<SLOG, RC>(c.src32 + ((((uint32_t)(r0 + 2) - w) << SLOG) + src) * 4u, v);
+#pragma unroll
+    for (int q = 0; q < RC; ++q) v[q] += add;
+    if (active) {
+        sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, v);
+        if (CHECK) {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) fold4f(f, c, r0 + q, dst, v[q], src);
+        }
+    }
+}
+
+template <int SLOG, int RC, bool CHECK>
+__device__ __forceinline__ void fast_multi(const Fast4& c, uint32_t blk, int r0, int lane, Fold4& f) {
+    const uint32_t t = blk * 32u + (uint32_t)lane;
+    uint2 cd = make_uint2(0u, 0u);
+    if (t < c.n_multi) cd = lds_v2(c.cell32 + 8u * t);
+    const uint32_t dst = cd.x & 1023u;
+    uint32_t n = cd.x >> 16;
+    if (n >= PROG_BIG_MIN) n = 0u;                                   // the warp form's
+    const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n);
+    if (nmax == 0u) return;
+    const uint32_t ca = c.cand32 + 4u * cd.y;
+    const uint32_t base = c.src32 + ((uint32_t)(r0 + 2) << (SLOG + 2));
+    int32_t key[RC];
+#pragma unroll
+    for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
+    uint32_t x = n ? lds_u32(ca) : 0u;                               // candidate descriptors one ahead
+    for (uint32_t o = 0; o < nmax; ++o) {
+        if (o < n) {
+            const uint32_t e = x;
+            if (o + 1u < n) x = lds_u32(ca + 4u * (o + 1u));
+            const uint32_t src = e & 1023u, w = (e >> 10) & 3u;
+            const int32_t add = (int32_t)(((e >> 12) << V4_SHIFT) + (V4_ORD_MASK - o));
+            int32_t v[RC];
+            lds_layers<SLOG, RC>(base + (src << 2) - (w << (SLOG + 2)), v);
+#pragma unroll
+            for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
+        }
+    }
+    if (n) {
+        uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
+        int32_t val[RC];
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+            val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
+            pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
+        }
+        sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, val);
+        if (CHECK) {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) {
+                if (val[q] >= 0 && r0 + q <= c.R) {
+                    const uint32_t o = V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
+                    fold4f(f, c, r0 + q, dst, val[q], lds_u32(ca + 4u * o) & 1023u);
+                }
+            }
+        }
+    }
+}
+
+template <int SLOG, int RC, bool CHECK>
+__device__ __forceinline__ void fast_big(const Fast4& c, uint32_t u, int r0, int lane, Fold4& f) {
+    const uint32_t t = lds_u32(c.big32 + 4u * u);
+    const uint2 cd = lds_v2(c.cell32 + 8u * t);
+    const uint32_t dst = cd.x & 1023u, n = cd.x >> 16;
+    const uint32_t ca = c.cand32 + 4u * cd.y;
+    const uint32_t base = c.src32 + ((uint32_t)(r0 + 2) << (SLOG + 2));
+    int32_t key[RC];
+#pragma unroll
+    for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
+    for (uint32_t o = (uint32_t)lane; o < n; o += 32u) {
+        const uint32_t e = lds_u32(ca + 4u * o);
+        const uint32_t src = e & 1023u, w = (e >> 10) & 3u;
+        const int32_t add = (int32_t)(((e >> 12) << V4_SHIFT) + (V4_ORD_MASK - o));
+        int32_t v[RC];
+        lds_layers<SLOG, RC>(base + (src << 2) - (w << (SLOG + 2)), v);
+#pragma unroll
+        for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
+    }
+#pragma unroll
+    for (int q = 0; q < RC; ++q) key[q] = __reduce_max_sync(0xFFFFFFFFu, key[q]);
+    if (lane == 0) {
+        uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
+        int32_t val[RC];
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+            val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
+            pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
+        }
+        sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, val);
+        if (CHECK) {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) {
+                if (val[q] >= 0 && r0 + q <= c.R) {
+                    const uint32_t o = V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
+                    fold4f(f, c, r0 + q, dst, val[q], lds_u32(ca + 4u * o) & 1023u);
+                }
+            }
+        }
+    }
+}
+
+template <int SLOG, int RC>
+__device__ __forceinline__ void fast_dead(const Fast4& c, uint32_t blk, int r0, int lane) {
+    const uint32_t x = blk * 32u + (uint32_t)lane;
+    if (x >= c.n_dead) return;
+    const uint32_t dst = lds_u32(c.dead32 + 4u * x);
+    int32_t v[RC];
+#pragma unroll
+    for (int q = 0; q < RC; ++q) v[q] = V4_DEAD;
+    sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, v);
+}
+
+// Spin until the monotone arrival counter reaches `target`; gives up after timeout_ns or when another wait of the
+// problem has already failed (counter[1] != 0: sticky), so that a lost CTA can never hang the GPU.
+__device__ __noinline__ bool wait_counter4(unsigned int* counter, unsigned int target, unsigned long long timeout_ns, int level) {
+    const unsigned long long t0 = global_ns();
+    bool ok = true;
+    for (unsigned int it = 0;; ++it) {
+        unsigned int v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (v >= target) break;
+        __nanosleep(40);
+        if ((it & 255u) == 255u) {
+            unsigned int err;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(err) : "l"(counter + 1) : "memory");
+            if (err != 0u || global_ns() - t0 > timeout_ns) { atomicCAS(counter + 1, 0u, (unsigned int)level + 1u); ok = false; break; }
+        }
+    }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    return ok;
+}
+
+template <int SLOG, int RC, bool CHECK>
+__device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) {
+    extern __shared__ __align__(128) uint8_t smem4[];
+    const int RL = a.nchunk * RC;
+    const uint32_t tile_bytes = (uint32_t)(RL + 2) << (SLOG + 2);
+    uint8_t* const slots = smem4;
+    uint8_t* const tiles = slots + (size_t)a.nslot * a.slot_bytes;
+    uint64_t* const full = reinterpret_cast<uint64_t*>(tiles + 2 * (size_t)tile_bytes);
+    uint64_t* const empty = full + a.nslot;
+    uint64_t* const failw = empty + a.nslot;               // set once a barrier of the problem has timed out
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncw = a.ncw, CT = ncw * 32, NS = a.nslot;
+    const int32_t n_my = cta == 0 ? a.n_trans : a.n_wide;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), (uint32_t)ncw); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        *failw = 0ull;
+    }
+    if (cta == 0) {
+        // two dead padding layers below layer 0 of both tiles; level 0 (one vertex): every layer starts at 0 (:535)
+        int32_t* const t0 = reinterpret_cast<int32_t*>(tiles);
+        int32_t* const t1 = reinterpret_cast<int32_t*>(tiles + tile_bytes);
+        for (int x = tid; x < (2 << SLOG); x += blockDim.x) { t0[x] = V4_DEAD; t1[x] = V4_DEAD; }
+        for (int r = tid; r < RL; r += blockDim.x) t0[((r + 2) << SLOG)] = r <= a.R ? 0 : V4_DEAD;
+    }
+    __syncthreads();
+
+    if (tid >= CT) {
+        // ---- producer warp: lanes fetch 32 directory entries at a time, lane 0 issues the copies ----
+        int slot = 0;
+        uint32_t use_parity = 0u;                           // parity of the previous use of the slot (first round: no wait)
+        bool first_round = true;
+        for (int32_t i0 = 0; i0 < n_my; i0 += 32) {
+            int32_t lv = 0;
+            uint4 f = make_uint4(0u, 0u, 0u, 0u);
+            if (i0 + lane < n_my) {
+                lv = cta == 0 ? i0 + lane : __ldg(a.wide_list + i0 + lane);
+                f = __ldg(reinterpret_cast<const uint4*>(a.dir + lv));
+            }
+            const int cnt = min(32, n_my - i0);
+            for (int j = 0; j < cnt; ++j) {
+                const int32_t l = __shfl_sync(0xFFFFFFFFu, lv, j);
+                const uint32_t off16 = __shfl_sync(0xFFFFFFFFu, f.x, j), bytes = __shfl_sync(0xFFFFFFFFu, f.y, j);
+                if (lane == 0) {
+                    if (!first_round) mbar_wait(smem_u32(empty + slot), use_parity);
+                    const uint32_t bar = smem_u32(full + slot);
+                    const uint32_t dst = smem_u32(slots + (size_t)slot * a.slot_bytes);
+                    mbar_expect_tx(bar, (uint32_t)sizeof(ProgDir) + bytes);
+                    bulk_g2s(dst, a.dir + l, (uint32_t)sizeof(ProgDir), bar);
+                    bulk_g2s(dst + (uint32_t)sizeof(ProgDir), a.prog + (size_t)off16 * 16, bytes, bar);
+                }
+                if (++slot == NS) { slot = 0; if (first_round) first_round = false; else use_parity ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    // ---- compute warps ----
+    const uint32_t slots32 = smem_u32(slots), tiles32 = smem_u32(tiles), full32 = smem_u32(full), empty32 = smem_u32(empty);
+    const uint32_t fail32 = smem_u32(failw);
+    bool failed = false;                    // a barrier of this problem timed out: stop working, keep the ring moving
+    const bool profiling = a.prof != nullptr && cta == 0 && tid == 0;
+    unsigned long long pc_wait = 0, pc_work = 0, pc_bar = 0;
+    long long tk0 = 0, tk1 = 0, tk2 = 0;
+    uint32_t slot = 0, parity = 0;
+    for (int32_t i = 0; i < n_my; ++i) {
+        if (profiling) tk0 = clock64();
+        const uint32_t sb32 = slots32 + slot * (uint32_t)a.slot_bytes;
+        mbar_wait(full32 + 8u * slot, parity);
+        if (profiling) tk1 = clock64();
+        const uint4 d = lds_v4(sb32);                       // directory entry
+        const uint32_t flags = d.w;
+        const int l = cta == 0 ? i : __ldg(a.wide_list + i);
+        if (a.grid > 1 && (flags & PF_WAIT) && !failed) {
+            if (tid == 0 && !wait_counter4(a.counter, d.z, a.timeout_ns, l)) sts_s32(fail32, 1);
+            bar_named(1, CT);
+            failed = lds_s32(fail32) != 0;
+        }
+        Fold4 f = {0ull, 0ull};
+        constexpr uint32_t FAST = PF_COMPACT | PF_STAGED;
+        if (!failed) {
+            if ((flags & FAST) == FAST) {
+                const uint4 h0 = lds_v4(sb32 + 16u), h1 = lds_v4(sb32 + 32u), h2 = lds_v4(sb32 + 48u), h3 = lds_v4(sb32 + 64u);
+                Fast4 c;
+                const uint32_t pb32 = sb32 + (uint32_t)sizeof(ProgDir);
+                c.copy32 = pb32 + (uint32_t)sizeof(ProgHdr); c.cell32 = pb32 + h3.x; c.cand32 = pb32 + h3.y; c.big32 = pb32 + h3.z; c.dead32 = pb32 + h3.w;
+                c.n_copy = h0.y; c.n_multi = h0.z; c.n_big = h1.x; c.n_dead = h1.y;
+                const uint32_t odd = (uint32_t)l & 1u;
+                c.src32 = tiles32 + odd * tile_bytes; c.dst32 = tiles32 + (odd ^ 1u) * tile_bytes;
+                c.pl = a.pred + (((unsigned long long)h2.y << 32) | h2.x);
+                c.k = h0.x & 0xFFFFu; c.kk2 = (h0.x >> 16) * (h0.x >> 16); c.R = a.R;
+                const uint32_t nch = (uint32_t)a.nchunk;
+                const uint32_t e0 = c.n_big * nch, e1 = e0 + ((c.n_multi + 31u) >> 5) * nch, e2 = e1 + ((c.n_copy + 31u) >> 5) * nch,
+                               e3 = e2 + ((c.n_dead + 31u) >> 5) * nch;
+                for (uint32_t u = (uint32_t)warp; u < e3; u += (uint32_t)ncw) {
+                    // unit -> (kind, block, chunk): chunks of one block are neighbours
+                    const uint32_t lo = u < e0 ? 0u : (u < e1 ? e0 : (u < e2 ? e1 : e2));
+                    const uint32_t v = u - lo, blk = a.m_nchunk ? __umulhi(v, a.m_nchunk) : v, ch = v - blk * nch;
+                    const int r0 = (int)ch * RC;
+                    if (u < e0) fast_big<SLOG, RC, CHECK>(c, blk, r0, lane, f);
+                    else if (u < e1) fast_multi<SLOG, RC, CHECK>(c, blk, r0, lane, f);
+                    else if (u < e2) fast_copy<SLOG, RC, CHECK>(c, blk, r0, lane, f);
+                    else fast_dead<SLOG, RC>(c, blk, r0, lane);
+                }
+            } else {
+                const ulonglong2 fs = run_generic<SLOG, RC, CHECK>(a, slots + (size_t)slot * a.slot_bytes, tiles32, tile_bytes, l, cta, warp, lane);
+                f.sum = fs.x; f.live = fs.y;
+            }
+        }
+        __syncwarp();
+        if (profiling) tk2 = clock64();
+        if (lane == 0) mbar_arrive(empty32 + 8u * slot);       // this warp is done with the slot
+        bar_named(1, CT);                                       // the level is whole within this CTA
+        if (a.grid > 1 && (flags & PF_ARRIVE) && tid == 0) red_release_add_u32(a.counter, 1u);
+        if (profiling) {
+            const long long tk3 = clock64();
+            pc_wait += tk1 - tk0; pc_work += tk2 - tk1; pc_bar += tk3 - tk2;
+            const int cls = (flags & FAST) == FAST ? 0 : ((flags & PF_ALL_CTAS) ? 2 : 1);      // narrow loop / hand-over and other / HBM to HBM
+            a.prof[4 + 2 * cls] += 1; a.prof[5 + 2 * cls] += (unsigned long long)(tk3 - tk0);
+        }
+        if (CHECK) {
+            for (int o = 16; o > 0; o >>= 1) {
+                f.sum += __shfl_down_sync(0xFFFFFFFFu, f.sum, o);
+                f.live += __shfl_down_sync(0xFFFFFFFFu, f.live, o);
+            }
+            if (lane == 0 && f.live) {
+                atomicAdd(a.level_sum + l + 1, f.sum);
+                atomicAdd(a.level_live + l + 1, f.live);
+            }
+        }
+        if (++slot == (uint32_t)NS) { slot = 0; parity ^= 1u; }
+    }
+    if (profiling) { a.prof[0] = pc_wait; a.prof[1] = pc_work; a.prof[2] = pc_bar; a.prof[3] = (unsigned long long)n_my; }
+    // the sink: layers of cell (0,0) of the last level (the traceback starts from layer R, :774-776)
+    if (cta == 0) {
+        const int last = a.n_trans;                             // level index L-1
+        if (a.last_k > a.kn) {                                  // last level in HBM (DipGenie's sink level is one vertex: never there)
+            if (a.grid > 1 && tid == 0 && !failed) wait_counter4(a.counter, a.final_target, a.timeout_ns, last);
+            bar_named(1, CT);
+        }
+        const long long kk = (long long)a.last_k * a.last_k;
+        for (int r = tid; r <= a.R; r += CT) {
+            int32_t v;
+            if (a.last_k <= a.kn) v = lds_s32(tiles32 + ((uint32_t)last & 1u) * tile_bytes + ((uint32_t)(r + 2) << (SLOG + 2)));
+            else v = __ldcg(((last & 1) ? a.gtile1 : a.gtile0) + a.gpad + (long long)r * kk);
+            a.sink[r] = v;
+        }
+    }
+}
+
+template <int SLOG, int RC, bool CHECK>
+__global__ void __launch_bounds__(544, 1) dip_sweep4_kernel(const __grid_constant__ Sweep4Args a) {
+    sweep4_body<SLOG, RC, CHECK>(a, (int)blockIdx.x);
+}
+
+// Many independent problems in ONE launch (dg_dip_run_many): CTA b works on problem cta_map[b].x as its local CTA
+// cta_map[b].y; the problem's arguments are copied to shared memory once.
+template <int SLOG, int RC>
+__global__ void __launch_bounds__(544, 1) dip_sweep4_many_kernel(const Sweep4Args* __restrict__ all, const int2* __restrict__ cta_map) {
+    __shared__ Sweep4Args sa;
+    const int2 who = cta_map[blockIdx.x];
+    static_assert(sizeof(Sweep4Args) % 4 == 0, "word copy");
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(all + who.x);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sa);
+    for (uint32_t x = threadIdx.x; x < sizeof(Sweep4Args) / 4; x += blockDim.x) dst[x] = src[x];
+    __syncthreads();
+    sweep4_body<SLOG, RC, false>(sa, who.y);
+}
+
+constexpr size_t sweep4_smem_bytes(int slog, int RL, int slot_bytes, int nslot) {
+    return (size_t)nslot * (size_t)slot_bytes + 2 * ((size_t)(RL + 2) << (slog + 2)) + (2 * (size_t)nslot + 1) * 8;
+}
+
+}  // namespace dg

@@ -24,7 +24,8 @@ class DipStats(C.Structure):
         ("mask_words_max", C.c_int32), ("grid_ctas", C.c_int32), ("pred_bytes", C.c_int32), ("launches", C.c_int32),
         ("sweep_ms", C.c_float), ("traceback_ms", C.c_float), ("delta_ms", C.c_float), ("plan_ms", C.c_float),
         ("upload_ms", C.c_float), ("n_narrow", C.c_int32), ("n_wide", C.c_int32), ("n_tasks", C.c_int64),
-        ("delta_bytes", C.c_uint64),
+        ("delta_bytes", C.c_uint64), ("prog_bytes", C.c_uint64), ("code_bytes", C.c_uint64), ("engine", C.c_int32),
+        ("build_ms", C.c_float),
     ]
 
 
@@ -458,6 +459,17 @@ class DipProblem:
         d = {m: {n: int(out[i * 6 + j]) for j, n in enumerate(names)} for i, m in enumerate(["smem_layers", "hbm_layers"])}
         d["lane_form_warp0"] = {n: int(out[12 + j]) for j, n in enumerate(["items", "setup", "loop", "reduce", "store", "iters"])}
         return d
+
+    def debug_program(self) -> np.ndarray:
+        """dg_dip_debug_program: the level programs the device builder wrote (engine 4; empty otherwise)."""
+        n = C.c_uint64(0)
+        self.ctx.check(self.ctx.lib.dg_dip_debug_program(C.c_void_p(self.ctx.h), self.h, None, C.c_uint64(0), C.byref(n)),
+                       "dg_dip_debug_program")
+        out = np.zeros(int(n.value), np.uint8)
+        if n.value:
+            self.ctx.check(self.ctx.lib.dg_dip_debug_program(C.c_void_p(self.ctx.h), self.h, _ptr(out), C.c_uint64(n.value),
+                                                             C.byref(n)), "dg_dip_debug_program")
+        return out
 
     def result(self):
         R = self.R

@@ -94,11 +94,18 @@ typedef struct {
     int32_t n_narrow, n_wide;           /* transitions run by CTA 0 alone in shared memory / spread over CTAs */
     int64_t n_tasks;                    /* tasks over all CTA streams */
     uint64_t delta_bytes;               /* HBM held by the pair-score matrices */
+    uint64_t prog_bytes;                /* level-program engine: HBM held by the level programs */
+    uint64_t code_bytes;                /* HBM held by the predecessor codes */
+    int32_t engine;                     /* 4 = level programs (dp_prog.h), 3 = task streams */
+    float build_ms;                     /* prog_fill_kernel inside dg_dip_create (engine 4) */
 } dg_dip_stats_t;
 int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out);
 /* out24: for each of {shared-memory layers, HBM/L2 layers} six counters {tasks, slot-wait, grid-wait,
  * cell-loop, barrier+arrive, unused} in SM clock cycles of CTA 0 / thread 0; the rest is zero. */
 int dg_dip_profile(dg_ctx* ctx, dg_dip* d, uint64_t* out24);
+/* Diagnostics/tests: the level programs the device builder wrote for this problem (engine 4; *bytes = 0 otherwise).
+ * out may be NULL to query the size. */
+int dg_dip_debug_program(dg_ctx* ctx, dg_dip* d, uint8_t* out, uint64_t cap, uint64_t* bytes);
 void dg_dip_destroy(dg_ctx* ctx, dg_dip* d);
 
 /* Independent samples on one GPU at the same time.  In the reference every sample is its own process

@@ -150,6 +150,24 @@ class DpEmu4:
                                max_cand=int(counts[7])))
 
 
+    def build_program(self, g, R, shape=None) -> np.ndarray:
+        """The level programs as the host builder writes them (compare with DipProblem.debug_program())."""
+        shp = np.zeros(8, np.int32)
+        if shape:
+            shp[: len(shape)] = list(shape)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        f = self.lib.emu4_build_program
+        f.restype = C.c_int64
+        args = [C.c_int32(g.n_levels), P(g.level_off), P(g.adj_off), P(g.adj_dst), P(g.adj_w), P(g.col_off), P(g.col_val),
+                P(g.colour_is_hom), C.c_int32(len(g.colour_is_hom)), C.c_int32(R), P(shp)]
+        n = f(*args, None, C.c_int64(0))
+        if n < 0:
+            return None
+        out = np.zeros(n, np.uint8)
+        assert f(*args, P(out), C.c_int64(n)) == n
+        return out
+
+
 @pytest.fixture(scope="session")
 def dp_emu4():
     return DpEmu4()

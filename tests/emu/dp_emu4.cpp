@@ -186,3 +186,33 @@ extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const
     for (int x = 0; x < n2; ++x) { p2_edges[2 * x] = b[2 * (n2 - 1 - x)]; p2_edges[2 * x + 1] = b[2 * (n2 - 1 - x) + 1]; }
     return 0;
 }
+
+// The whole program as the HOST builder writes it (prog_fill_level_host), for the byte-for-byte comparison with what
+// the device builder (prog_fill_kernel) wrote.  shape as above.  Returns the size; fills `out` when it is large enough.
+extern "C" int64_t emu4_build_program(int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
+                                      const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off,
+                                      const int32_t* col_val, const uint8_t* colour_is_hom, int32_t n_colours, int32_t R,
+                                      const int32_t* shape, uint8_t* out, int64_t cap) {
+    DipGraphView gv;
+    gv.n_levels = n_levels; gv.level_off = level_off; gv.adj_off = adj_off; gv.adj_dst = adj_dst; gv.adj_w = adj_w;
+    gv.col_off = col_off; gv.col_val = col_val; gv.colour_is_hom = colour_is_hom; gv.n_colours = n_colours; gv.R = R;
+    DipPlan p;
+    if (!build_dip_plan(gv, p)) return -1;
+    Sweep4Shape sh;
+    int rc = 10;
+    if (shape) {
+        if (shape[0] > 0) sh.slog = shape[0];
+        if (shape[1] > 0) sh.kn = shape[1];
+        if (shape[2] > 0) sh.slot_bytes = shape[2];
+        if (shape[3] > 0) sh.grid = shape[3];
+        if (shape[4] > 0) rc = shape[4];
+    }
+    Plan4 q;
+    std::string why;
+    if (!plan4_build(p, sh, rc, q, why)) return -2;
+    if (out && cap >= (int64_t)q.prog_bytes) {
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int l = 0; l < p.L - 1; ++l) prog_fill_level_host(p, q, l, out + q.prog_off[l]);
+    }
+    return (int64_t)q.prog_bytes;
+}

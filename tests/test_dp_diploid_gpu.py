@@ -52,14 +52,65 @@ def test_cuda_matches_reference_tiny(name, ctx, expected):
     assert one_shot["value"] == e["value"] and one_shot["p1_edges"].ravel().tolist() == e["p1_edges"]
 
 
+@pytest.fixture(params=["v4", "v3"])
+def engine(request, monkeypatch):
+    """The level-program engine (default) or, with DG_ENGINE_V3=1, the task-stream engine that takes the problems
+    outside the packed-key program's range."""
+    if request.param == "v3":
+        monkeypatch.setenv("DG_ENGINE_V3", "1")
+    return request.param
+
+
 @pytest.mark.parametrize("seed", range(24))
-def test_cuda_matches_oracle_random(seed, ctx, oracle_mod):
+def test_cuda_matches_oracle_random(seed, ctx, oracle_mod, engine):
     rng = np.random.default_rng(2000 + seed)
     g = synth.random_level_graph(seed, n_levels=int(rng.integers(2, 40)), max_width=int(rng.integers(1, 24)),
                                  n_colours=int(rng.integers(0, 200)), p_weight1=float(rng.random() * 0.6),
                                  p_colour=float(rng.random()), max_out=int(rng.integers(1, 5)))
     R = int(rng.integers(0, 9))
-    assert_dip_equal(oracle_dip(oracle_mod, g, R), cuda_dip(ctx, g, R))
+    o = cuda_dip(ctx, g, R)
+    assert_dip_equal(oracle_dip(oracle_mod, g, R), o)
+    assert o["stats"]["engine"] in ((3,) if engine == "v3" else (3, 4))     # (a cell of more than 1024 candidates: not the program's)
+
+
+@pytest.mark.parametrize("variant", [dict(DG_V4_SLOG="9"), dict(DG_V4_RC="5"), dict(DG_V4_SLOT="256"), dict(DG_V4_NCW="3"),
+                                     dict(DG_V4_SLOG="9", DG_V4_RC="5", DG_V4_NCW="16")])
+def test_cuda_level_program_kernel_variants(variant, ctx, oracle_mod, monkeypatch):
+    """Narrower shared-memory layers (stride 512: levels wider than 22 go to HBM), 5 layers per register chunk, ring slots
+    too small for a program (descriptors read in place from HBM), few / many compute warps."""
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    n4 = 0
+    for seed in range(10):
+        rng = np.random.default_rng(5000 + seed)
+        if seed % 4 == 3:
+            g = synth.lane_panel_graph(seed, n_lanes=int(rng.integers(8, 31)), n_blocks=4, rec_per_block=2, p_colour=0.25, n_colours=300)
+        else:
+            g = synth.random_level_graph(700 + seed, n_levels=int(rng.integers(2, 50)), max_width=int(rng.integers(1, 40)),
+                                         n_colours=int(rng.integers(0, 200)), p_weight1=float(rng.random() * 0.6),
+                                         p_colour=float(rng.random()), max_out=int(rng.integers(1, 5)))
+        R = int(rng.integers(0, 12))
+        o = cuda_dip(ctx, g, R)
+        n4 += o["stats"]["engine"] == 4
+        assert_dip_equal(oracle_dip(oracle_mod, g, R), o)
+    assert n4 >= 8
+
+
+def test_device_built_program_equals_host_built(ctx, dp_emu4):
+    """prog_fill_kernel against prog_fill_level_host (the same dp_prog.h functions, run serially): byte for byte."""
+    cases = [(synth.random_level_graph(300 + s, n_levels=30, max_width=36, n_colours=150, p_colour=0.5, max_out=4), 4) for s in range(4)]
+    cases.append((synth.lane_panel_graph(5, n_lanes=24, n_blocks=5, rec_per_block=3, p_colour=0.3, n_colours=2000), 7))
+    cases.append((LevelGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_dipin.npz"))[0], 18))
+    for g, R in cases:
+        p = ctx.dip_create(g, R)
+        try:
+            dev = p.debug_program()
+            st = p.stats()
+        finally:
+            p.close()
+        host = dp_emu4.build_program(g, R, shape=(10, 32, 8192, 1, 10))
+        assert st["engine"] == 4 and st["prog_bytes"] == len(host) == len(dev)
+        assert np.array_equal(dev, host)
 
 
 def test_cuda_edge_cases(ctx, oracle_mod):
@@ -91,10 +142,13 @@ def test_cuda_wide_levels_use_many_ctas(ctx, oracle_mod):
 
 
 @pytest.mark.parametrize("R", [18, 0, 6, 36])
-def test_cuda_matches_reference_mhc_full_size(R, ctx, expected):
+def test_cuda_matches_reference_mhc_full_size(R, ctx, expected, engine):
     """BASELINE config 2 graph (MHC_4.gfa.gz, CHM13 reads): every DP layer digest-equal to the reference."""
+    if engine == "v3" and R not in (18, 36):
+        pytest.skip("task-stream engine: R = 18 and 36 only (time)")
     g, _ = LevelGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_dipin.npz"))
     o = cuda_dip(ctx, g, R)
+    assert o["stats"]["engine"] == (3 if engine == "v3" else 4)
     e = expected["mhc4_chm13"]["diploid"][str(R)]
     assert o["value"] == e["value"]
     assert o["s_het"] == e["s_het"]
@@ -110,7 +164,7 @@ def test_cuda_matches_reference_mhc_full_size(R, ctx, expected):
     assert o2["value"] == e["value"] and o2["p1_edges"].ravel().tolist() == e["p1_edges"]
 
 
-def test_cuda_batch_of_samples_matches_one_by_one(ctx, oracle_mod):
+def test_cuda_batch_of_samples_matches_one_by_one(ctx, oracle_mod, engine):
     """dg_dp_diploid_batch: samples resident together on their own streams / CTA groups give exactly the
     results of separate calls (shapes chosen so that narrow, wide and hand-over tasks all occur)."""
     graphs, Rs = [], []
@@ -182,7 +236,7 @@ def test_records_larger_than_a_slot_run_in_lane_form(ctx, oracle_mod):
         assert o["stats"]["n_wide"] > 0
 
 
-def test_cuda_many_resident_problems_one_fused_launch(ctx, oracle_mod, monkeypatch):
+def test_cuda_many_resident_problems_one_fused_launch(ctx, oracle_mod, monkeypatch, engine):
     """dg_dip_run_many starts problems that live in distinct slots together; more than the 32 hardware work queues'
     worth of them run as ONE sweep launch (dip_sweep_many_kernel: CTA -> (problem, local CTA) map).  Same results as
     one-by-one runs and as the per-stream launches (DG_NO_FUSED_MANY=1)."""
