@@ -992,7 +992,7 @@ DG_HD void cell_to_state(int64_t cell, int32_t k, TraceState& s) {
 }
 
 template <class PredT>
-__global__ void __launch_bounds__(256) dip_anc_kernel(const TraceArgs a) {
+__device__ __forceinline__ void anc_body(const TraceArgs& a) {
     const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= a.aoff[a.M]) return;
     int lo = 0, hi = a.M - 1;                 // largest m with aoff[m] <= x
@@ -1010,9 +1010,13 @@ __global__ void __launch_bounds__(256) dip_anc_kernel(const TraceArgs a) {
     const int32_t k = a.v.level_off[l_lo + 1] - a.v.level_off[l_lo];
     a.anc[x] = live ? (int32_t)(((int64_t)s.r * k + s.i2) * k + s.j2) : -1;
 }
+template <class PredT>
+__global__ void __launch_bounds__(256) dip_anc_kernel(const TraceArgs a) { anc_body<PredT>(a); }
+// The same for many problems in one launch: blockIdx.y = problem (blocks beyond a problem's cells leave at once).
+template <class PredT>
+__global__ void __launch_bounds__(256) dip_anc_many_kernel(const TraceArgs* __restrict__ all) { anc_body<PredT>(all[blockIdx.y]); }
 
-__global__ void dip_hop_kernel(const TraceArgs a) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void hop_body(const TraceArgs& a) {
     const int64_t ks = a.v.level_off[a.v.L] - a.v.level_off[a.v.L - 1];
     const int32_t value = a.sink_v4 ? __ldcg(a.sink_v4 + a.v.R)
                                     : __ldcg(a.sink_tile + (int64_t)a.v.R * ks * ks);   // cell (r=R,0,0) of the last level (:730, :775)
@@ -1023,9 +1027,17 @@ __global__ void dip_hop_kernel(const TraceArgs a) {
         if (cur >= 0) cur = a.anc[a.aoff[m] + cur];
     }
 }
+__global__ void dip_hop_kernel(const TraceArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    hop_body(a);
+}
+__global__ void dip_hop_many_kernel(const TraceArgs* __restrict__ all, int n) {       // one thread per problem
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hop_body(all[i]);
+}
 
 template <class PredT>
-__global__ void __launch_bounds__(128) dip_seg_kernel(const TraceArgs a) {
+__device__ __forceinline__ void seg_body(const TraceArgs& a) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= a.M) return;
     int32_t* sn = a.seg_n + 4 * m;
@@ -1040,9 +1052,12 @@ __global__ void __launch_bounds__(128) dip_seg_kernel(const TraceArgs a) {
                                         a.seg_p1 + (size_t)m * 2 * a.cap, &n1, a.seg_p2 + (size_t)m * 2 * a.cap, &n2, a.cap, &sh);
     sn[0] = n1; sn[1] = n2; sn[2] = sh; sn[3] = rc;
 }
+template <class PredT>
+__global__ void __launch_bounds__(128) dip_seg_kernel(const TraceArgs a) { seg_body<PredT>(a); }
+template <class PredT>
+__global__ void __launch_bounds__(128) dip_seg_many_kernel(const TraceArgs* __restrict__ all) { seg_body<PredT>(all[blockIdx.y]); }
 
-__global__ void dip_merge_kernel(const TraceArgs a) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__device__ __forceinline__ void merge_body(const TraceArgs& a) {
     int n1 = 0, n2 = 0, sh = 0, rc = 0;
     for (int m = 0; m < a.M && rc == 0; ++m) {      // m = 0 is nearest the sink: lists come out newest-first
         const int32_t* sn = a.seg_n + 4 * m;
@@ -1054,6 +1069,14 @@ __global__ void dip_merge_kernel(const TraceArgs a) {
     }
     if (rc == -1) { n1 = 0; n2 = 0; sh = 0; }
     a.out->rc = rc; a.out->s_het = sh; a.out->n1 = n1; a.out->n2 = n2;
+}
+__global__ void dip_merge_kernel(const TraceArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    merge_body(a);
+}
+__global__ void dip_merge_many_kernel(const TraceArgs* __restrict__ all, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) merge_body(all[i]);
 }
 
 }  // namespace dg
@@ -1136,6 +1159,7 @@ struct dg_dip {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float delta_ms = 0.f, sweep_ms = 0.f, trace_ms = 0.f, plan_ms = 0.f, upload_ms = 0.f;
     float fused_ms = 0.f;            // > 0: the last run's sweep was part of a fused launch of this duration (dg_dip_run_many)
+    float group_trace_ms = 0.f;      // > 0: ... and so was its traceback (no per-problem events were recorded)
     int launches = 0;
     bool ran = false, checks = false;
     uint64_t device_bytes = 0;
@@ -1172,6 +1196,7 @@ static const void* sweep4_fn(int slog, int rc, bool check) {
     if (slog == 10 && rc == 5) return check ? (const void*)dip_sweep4_kernel<10, 5, true> : (const void*)dip_sweep4_kernel<10, 5, false>;
     if (slog == 9 && rc == 10) return check ? (const void*)dip_sweep4_kernel<9, 10, true> : (const void*)dip_sweep4_kernel<9, 10, false>;
     if (slog == 9 && rc == 5) return check ? (const void*)dip_sweep4_kernel<9, 5, true> : (const void*)dip_sweep4_kernel<9, 5, false>;
+    if (slog == 8 && rc == 10) return check ? (const void*)dip_sweep4_kernel<8, 10, true> : (const void*)dip_sweep4_kernel<8, 10, false>;
     return nullptr;
 }
 static const void* sweep4_many_fn(int slog, int rc) {
@@ -1179,25 +1204,34 @@ static const void* sweep4_many_fn(int slog, int rc) {
     if (slog == 10 && rc == 5) return (const void*)dip_sweep4_many_kernel<10, 5>;
     if (slog == 9 && rc == 10) return (const void*)dip_sweep4_many_kernel<9, 10>;
     if (slog == 9 && rc == 5) return (const void*)dip_sweep4_many_kernel<9, 5>;
+    if (slog == 8 && rc == 10) return (const void*)dip_sweep4_many_kernel<8, 10>;
     return nullptr;
 }
 constexpr size_t S4_SMEM_MAX = 226 * 1024;   // 227 KB per CTA, less the fused kernel's static argument block
 // Layer chunk and shared-memory layer stride for R: the widest stride whose two tiles of RL + 2 layers fit beside the
 // slot ring.  False: no variant fits (R too large): the task-stream engine takes the problem.
-static bool sweep4_shape(int R, int grid, Sweep4Shape& sh, int& rc) {
+// `packed`: the problem shares the GPU with other resident problems, one CTA each (batch slots): narrow shared-memory
+// layers (stride 256: levels up to 16 wide), small ring and few warps, so that two CTAs fit an SM — the sweep of one
+// problem is a chain of dependent levels that leaves its SM mostly idle, a second problem fills the gaps (measured on
+// B200, MHC_4, R = 18: 144 problems x 1 CTA per SM 430 samples/s, 256 problems x 2 per SM 630 samples/s in the fused
+// launch).  Otherwise the problem has SMs to itself: stride 1024 (levels up to 32 wide stay in shared memory).
+static bool sweep4_shape(int R, int grid, bool packed, Sweep4Shape& sh, int& rc, int& ncw) {
     rc = 10;
     if (const char* e = getenv("DG_V4_RC")) rc = atoi(e) == 5 ? 5 : 10;
-    sh.slot_bytes = 8192;
+    sh.slot_bytes = packed ? 4096 : 8192;
     if (const char* e = getenv("DG_V4_SLOT")) sh.slot_bytes = std::max(256, atoi(e) / 16 * 16);
     sh.nslot = 4;
     if (const char* e = getenv("DG_V4_NSLOT")) sh.nslot = std::max(2, std::min(16, atoi(e)));
+    ncw = packed ? 8 : 12;
+    if (const char* e = getenv("DG_V4_NCW")) ncw = std::max(1, std::min(16, atoi(e)));
     sh.grid = std::max(1, grid);
     const int RL = (R + rc) / rc * rc;
-    int want = 10;
-    if (const char* e = getenv("DG_V4_SLOG")) want = atoi(e) == 9 ? 9 : 10;
-    for (int slog = want; slog >= 9; --slog)
+    int want = packed ? 8 : 10;
+    if (const char* e = getenv("DG_V4_SLOG")) want = std::max(8, std::min(10, atoi(e)));
+    if (rc != 10) want = std::max(want, 9);
+    for (int slog = want; slog >= (rc == 10 ? 8 : 9); --slog)
         if (sweep4_smem_bytes(slog, RL, sh.slot_bytes, sh.nslot) <= S4_SMEM_MAX) {
-            sh.slog = slog; sh.kn = slog == 10 ? 32 : 22;
+            sh.slog = slog; sh.kn = slog == 10 ? 32 : (slog == 9 ? 22 : 16);
             return true;
         }
     return false;
@@ -1224,7 +1258,8 @@ static int dip_limits(dg_ctx* ctx, DipLimits& lim) {
         const void* fns[] = {(const void*)dip_delta_kernel, (const void*)dip_anc_kernel<uint16_t>, (const void*)dip_anc_kernel<uint32_t>,
                              (const void*)dip_hop_kernel, (const void*)dip_seg_kernel<uint16_t>, (const void*)dip_seg_kernel<uint32_t>,
                              (const void*)dip_merge_kernel, (const void*)dip_sweep_many_kernel<false>, (const void*)dip_sweep_many_kernel<true>,
-                             (const void*)prog_fill_kernel, (const void*)fill_dead_kernel};
+                             (const void*)prog_fill_kernel, (const void*)fill_dead_kernel, (const void*)dip_anc_many_kernel<uint16_t>,
+                             (const void*)dip_hop_many_kernel, (const void*)dip_seg_many_kernel<uint16_t>, (const void*)dip_merge_many_kernel};
         for (const void* f : fns) DG_CUDA(ctx, cudaFuncGetAttributes(&fa, f));
     }
     int per_sm = 0;
@@ -1270,14 +1305,12 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
         Sweep4Shape s4;
         int rc = 10;
         std::string why = "no kernel variant for this R";
-        if (sweep4_shape(p.R, shape.grid, s4, rc) && plan4_build(p, s4, rc, d->p4, why)) d->v4 = true;
+        if (sweep4_shape(p.R, shape.grid, !d->cooperative && shape.grid == 1, s4, rc, d->v4_ncw) && plan4_build(p, s4, rc, d->p4, why)) d->v4 = true;
         else if (getenv("DG_TIMING")) fprintf(stderr, "dg_dip: task-stream engine (%s)\n", why.c_str());
     }
     if (d->v4) {
         d->grid = d->p4.wide_list.empty() ? 1 : shape.grid;      // no HBM-resident transition: CTA 0 does everything
         d->pred_bytes = 2; d->shift = KEY_SHIFT;
-        d->v4_ncw = 12;
-        if (const char* e = getenv("DG_V4_NCW")) d->v4_ncw = std::max(1, std::min(16, atoi(e)));
     } else {
         plan_tasks(p, shape);
         d->grid = 1;
@@ -1500,6 +1533,7 @@ static int dip_run_pre(dg_ctx* ctx, dg_dip* d, bool check) {
         DG_CUDA(ctx, cudaStreamSynchronize(s));   // basis is a stack-lifetime staging buffer
     }
     d->launches = 0;
+    d->group_trace_ms = 0.f;
     DG_CUDA(ctx, cudaEventRecord(d->ev[0], s));
     if (!d->v4 && !p.delta_list.empty()) {
         DeltaArgs da;
@@ -1548,12 +1582,8 @@ static void fill_sweep4_args(const dg_dip* d, Sweep4Args& a) {
     if (const char* e = getenv("DG_SHARD_TIMEOUT_MS")) a.timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
 }
 
-template <class PredT>
-static int dip_run_post(dg_ctx* ctx, dg_dip* d, bool check) {
+static void fill_trace_args(const dg_dip* d, TraceArgs& ta) {
     const DipPlan& p = d->plan;
-    cudaStream_t s = d->stream;
-    DG_CUDA(ctx, cudaEventRecord(d->ev[2], s));
-    TraceArgs ta;
     TraceView& v = ta.v;
     v.L = p.L; v.R = p.R; v.level_off = d->level_off.p; v.in_off = d->in_off.p; v.in_edge = d->in_edge.p;
     v.lvlW = d->lvlW.p; v.msrc_off = d->msrc_off.p; v.mdst_off = d->mdst_off.p; v.masks = d->masks.p;
@@ -1567,6 +1597,14 @@ static int dip_run_post(dg_ctx* ctx, dg_dip* d, bool check) {
         v.vinfo = d->v4_vinfo.p; v.lvl_n1 = d->v4_n1.p; v.lvl_m = d->v4_m.p; v.RL = d->p4.RL;
     }
     ta.cap = p.R + 2; ta.shift = d->shift; ta.out = d->tout.p; ta.p1 = d->p1.p; ta.p2 = d->p2.p;
+}
+
+template <class PredT>
+static int dip_run_post(dg_ctx* ctx, dg_dip* d, bool check) {
+    cudaStream_t s = d->stream;
+    DG_CUDA(ctx, cudaEventRecord(d->ev[2], s));
+    TraceArgs ta;
+    fill_trace_args(d, ta);
     if (d->anc_cells > 0) {
         const unsigned blocks = (unsigned)((d->anc_cells + 255) / 256);
         dip_anc_kernel<PredT><<<blocks, 256, 0, s>>>(ta);
@@ -1590,7 +1628,7 @@ static int dip_run_post(dg_ctx* ctx, dg_dip* d, bool check) {
 template <class PredT>
 static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     if (int rc = dip_run_pre(ctx, d, check)) return rc;
-    d->fused_ms = 0.f;
+    d->fused_ms = 0.f; d->group_trace_ms = 0.f;
     const DipPlan& p = d->plan;
     cudaStream_t s = d->stream;
     if (d->v4) {
@@ -1669,10 +1707,13 @@ int dg_dip_result(dg_ctx* ctx, dg_dip* d, int32_t* sink_value, int32_t* sink_s_h
     if (shard_err)
         return fail(ctx, DG_ERR_CUDA, "dg_dip_result: row-sharded sweep of rank %d timed out at a cross-GPU barrier (%s %u): a peer is not running",
                     d->rank, shard_err == 0x7FFFFFFFu ? "exit barrier, code" : "level", shard_err == 0x7FFFFFFFu ? shard_err : shard_err - 1);
-    DG_CUDA(ctx, cudaEventElapsedTime(&d->delta_ms, d->ev[0], d->ev[1]));
-    DG_CUDA(ctx, cudaEventElapsedTime(&d->sweep_ms, d->ev[1], d->ev[2]));
-    if (d->fused_ms > 0.f) d->sweep_ms = d->fused_ms;      // (its own events also cover the wait for the other problems' pair scores)
-    DG_CUDA(ctx, cudaEventElapsedTime(&d->trace_ms, d->ev[2], d->ev[3]));
+    if (d->group_trace_ms > 0.f) { d->delta_ms = 0.f; d->sweep_ms = d->fused_ms; d->trace_ms = d->group_trace_ms; }
+    else {
+        DG_CUDA(ctx, cudaEventElapsedTime(&d->delta_ms, d->ev[0], d->ev[1]));
+        DG_CUDA(ctx, cudaEventElapsedTime(&d->sweep_ms, d->ev[1], d->ev[2]));
+        if (d->fused_ms > 0.f) d->sweep_ms = d->fused_ms;      // (its own events also cover the wait for the other problems' pair scores)
+        DG_CUDA(ctx, cudaEventElapsedTime(&d->trace_ms, d->ev[2], d->ev[3]));
+    }
     if (t.rc == -2) return fail(ctx, DG_ERR_CAPACITY, "dg_dip_result: more than R+2 recorded edges on a path");
     if (sink_value) *sink_value = t.value;
     if (sink_s_het) *sink_s_het = t.s_het;
@@ -1993,8 +2034,9 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
     std::vector<cudaEvent_t> done((size_t)n, nullptr);
     int rc = DG_OK;
     int64_t ctas = 0;
-    for (int32_t i = 0; i < n; ++i) if (ds[i] && !ds[i]->cooperative) ctas += ds[i]->grid;
-    if (ctas > ctx->sm_count) return fail(ctx, DG_ERR_CAPACITY, "dg_dip_run_many: %lld sweep CTAs do not fit %d SMs", (long long)ctas, ctx->sm_count);
+    bool spins = false;                 // some problem's CTAs wait on one another: the whole group must be co-resident
+    for (int32_t i = 0; i < n; ++i) if (ds[i] && !ds[i]->cooperative) { ctas += ds[i]->grid; spins = spins || ds[i]->grid > 1 || !ds[i]->v4; }
+    if (spins && ctas > ctx->sm_count) return fail(ctx, DG_ERR_CAPACITY, "dg_dip_run_many: %lld sweep CTAs do not fit %d SMs", (long long)ctas, ctx->sm_count);
     // One fused sweep launch for all problems when they allow it (plain-launch slots, same code width, no sharding):
     // the sweeps then do not need a hardware work queue each, so more than 32 samples can be resident together.
     bool fused = n >= 2 && !getenv("DG_NO_FUSED_MANY");
@@ -2007,6 +2049,60 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
                     ds[i]->v4_ncw == ds[0]->v4_ncw;
     }
     DG_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    if (fused && ds[0]->v4) {
+        // Level-program problems: resets, ONE sweep launch and ONE traceback launch set for the whole group, all on the
+        // context's stream (no per-problem streams, events or launches: with hundreds of resident problems those cost
+        // more than the kernels they order).
+        std::vector<Sweep4Args> h_args((size_t)n);
+        std::vector<TraceArgs> h_ta((size_t)n);
+        std::vector<int2> h_map;
+        int64_t max_anc = 0;
+        int max_M = 0;
+        for (int32_t i = 0; i < n; ++i) {
+            dg_dip* d = ds[i];
+            d->want_prof = false; d->launches = 0;
+            DG_CUDA(ctx, cudaMemsetAsync(d->counter.p, 0, 4 * sizeof(unsigned int), ctx->stream));
+            fill_sweep4_args(d, h_args[(size_t)i]);
+            fill_trace_args(d, h_ta[(size_t)i]);
+            for (int c = 0; c < d->grid; ++c) h_map.push_back(make_int2(i, c));
+            max_anc = std::max(max_anc, d->anc_cells); max_M = std::max(max_M, d->M);
+        }
+        DevBuf<Sweep4Args> d_args;
+        DevBuf<TraceArgs> d_ta;
+        DevBuf<int2> d_map;
+        DG_CUDA(ctx, d_args.upload(h_args.data(), h_args.size(), ctx->stream));
+        DG_CUDA(ctx, d_ta.upload(h_ta.data(), h_ta.size(), ctx->stream));
+        DG_CUDA(ctx, d_map.upload(h_map.data(), h_map.size(), ctx->stream));
+        cudaEvent_t f0 = nullptr, swept = nullptr;
+        DG_CUDA(ctx, cudaEventCreate(&f0));
+        DG_CUDA(ctx, cudaEventCreate(&swept));
+        const Plan4& q = ds[0]->p4;
+        const void* fn = sweep4_many_fn(q.shape.slog, q.rc);
+        const size_t smem = sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
+        const Sweep4Args* pa = d_args.p;
+        const int2* pm = d_map.p;
+        void* args[] = {(void*)&pa, (void*)&pm};
+        DG_CUDA(ctx, cudaEventRecord(f0, ctx->stream));
+        DG_CUDA(ctx, cudaLaunchKernel(fn, dim3((unsigned)h_map.size()), dim3((unsigned)(ds[0]->v4_ncw + 1) * 32u), args, smem, ctx->stream));
+        DG_CUDA(ctx, cudaEventRecord(swept, ctx->stream));
+        const TraceArgs* pt = d_ta.p;
+        if (max_anc > 0) dip_anc_many_kernel<uint16_t><<<dim3((unsigned)((max_anc + 255) / 256), (unsigned)n), 256, 0, ctx->stream>>>(pt);
+        dip_hop_many_kernel<<<(n + 31) / 32, 32, 0, ctx->stream>>>(pt, n);
+        if (max_M > 0) dip_seg_many_kernel<uint16_t><<<dim3((unsigned)((max_M + 127) / 128), (unsigned)n), 128, 0, ctx->stream>>>(pt);
+        dip_merge_many_kernel<<<(n + 31) / 32, 32, 0, ctx->stream>>>(pt, n);
+        DG_CUDA(ctx, cudaGetLastError());
+        DG_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+        DG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // (the argument vectors are read by the copies until here)
+        float ms = 0.f, fm = 0.f, tm = 0.f;
+        DG_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+        DG_CUDA(ctx, cudaEventElapsedTime(&fm, f0, swept));
+        DG_CUDA(ctx, cudaEventElapsedTime(&tm, swept, e1));
+        if (wall_ms) *wall_ms = ms;
+        for (int32_t i = 0; i < n; ++i) { ds[i]->fused_ms = fm; ds[i]->group_trace_ms = tm; ds[i]->ran = true; ds[i]->checks = false; ds[i]->launches = i == 0 ? 5 : 0; }
+        cudaEventDestroy(f0); cudaEventDestroy(swept);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        return DG_OK;
+    }
     if (fused) {
         const bool v4 = ds[0]->v4;
         std::vector<SweepArgs> h_args(v4 ? 0 : (size_t)n);

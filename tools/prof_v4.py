@@ -21,7 +21,7 @@ print(json.dumps(dict(single=dict(value=r['value'], engine=st['engine'], grid=st
                                   code_MB=st['code_bytes'] / 1e6, device_MB=st['device_bytes'] / 1e6, n_smem=st['n_narrow'], n_wide=st['n_wide']))), flush=True)
 p.close()
 for S in [int(a) for a in sys.argv[1:]]:
-    probs = [ctx.dip_create(g, R, slot=i, ctas=1) for i in range(S)]
+    probs = [ctx.dip_create(g, R, slot=i % 1024, ctas=1) for i in range(S)]
     for rep in range(3):
         ms = ctx.dip_run_many(probs)
     res = [q.result() for q in probs]

@@ -1,0 +1,13 @@
+"""One fused launch of S resident problems (MHC_4, R = 18), for ncu captures.  Usage: prof_v4_many.py S [reps]"""
+import os, sys
+sys.path.insert(0, os.getcwd())
+from dipgenie_b200.cuda_api import Context, LevelGraph
+g, _ = LevelGraph.from_npz('tests/golden/mhc4_chm13_dipin.npz')
+S = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+ctx = Context(0)
+probs = [ctx.dip_create(g, 18, slot=i % 1024, ctas=1) for i in range(S)]
+for rep in range(reps):
+    ms = ctx.dip_run_many(probs)
+assert all(q.result()['value'] == 60729 for q in probs)
+print(f"S={S}: group {ms:.1f} ms, fused sweep {probs[0].stats()['sweep_ms']:.1f} ms", flush=True)
