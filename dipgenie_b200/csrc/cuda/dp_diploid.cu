@@ -1168,14 +1168,15 @@ struct dg_dip {
     Plan4 p4;
     int v4_ncw = 12;
     float build_ms = 0.f;            // prog_fill_kernel
-    DevBuf<ProgDir> v4_dir;
+    DevBuf<ProgDir> v4_dir, v4_dir_full;        // the timed directory (idle transitions skipped) and the complete one (checksums)
     DevBuf<ProgHdr> v4_hdr;
     DevBuf<uint64_t> v4_prog_off;
-    DevBuf<int32_t> v4_wide, v4_sink;
-    DevBuf<uint8_t> v4_prog;
-    DevBuf<uint16_t> v4_pred, v4_cls;
-    DevBuf<uint32_t> v4_vinfo, v4_mpre, v4_n1, v4_m, v4_z, v4_dm;
+    DevBuf<int32_t> v4_wide, v4_wide_full, v4_sink;
+    DevBuf<uint8_t> v4_prog, v4_dom;
+    DevBuf<uint16_t> v4_pred, v4_cls, v4_vslot;
+    DevBuf<uint32_t> v4_vinfo, v4_mpre, v4_n1, v4_np, v4_m, v4_z, v4_dm, v4_tflags;
     DevBuf<int64_t> v4_mpre_off;
+    DevBuf<Fill4Args> v4_tables;                 // the builder's view of the device tables (also read by the checksum variant)
     ~dg_dip() {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (ipc_opened)
@@ -1210,11 +1211,12 @@ static const void* sweep4_many_fn(int slog, int rc) {
 constexpr size_t S4_SMEM_MAX = 226 * 1024;   // 227 KB per CTA, less the fused kernel's static argument block
 // Layer chunk and shared-memory layer stride for R: the widest stride whose two tiles of RL + 2 layers fit beside the
 // slot ring.  False: no variant fits (R too large): the task-stream engine takes the problem.
-// `packed`: the problem shares the GPU with other resident problems, one CTA each (batch slots): narrow shared-memory
-// layers (stride 256: levels up to 16 wide), small ring and few warps, so that two CTAs fit an SM — the sweep of one
-// problem is a chain of dependent levels that leaves its SM mostly idle, a second problem fills the gaps (measured on
-// B200, MHC_4, R = 18: 144 problems x 1 CTA per SM 430 samples/s, 256 problems x 2 per SM 630 samples/s in the fused
-// launch).  Otherwise the problem has SMs to itself: stride 1024 (levels up to 32 wide stay in shared memory).
+// `packed`: the problem shares the GPU with other resident problems, one CTA each (batch slots): a shared-memory tile of
+// stride 512 (22 slots), small ring and few warps, so that two CTAs fit an SM with room left for L1 — the sweep of
+// one problem is a chain of dependent levels that leaves its SM mostly idle, a second problem fills the gaps (measured
+// on B200, MHC_4, R = 18, fused launch: 144 problems x 1 CTA per SM 262 ms; 256 problems x 2 per SM 416 ms; with stride
+// 1024 the two CTAs leave 20 KB of L1 and the pair takes 568 ms).  Otherwise the problem has SMs to itself: stride 1024
+// (32 slots).
 static bool sweep4_shape(int R, int grid, bool packed, Sweep4Shape& sh, int& rc, int& ncw) {
     rc = 10;
     if (const char* e = getenv("DG_V4_RC")) rc = atoi(e) == 5 ? 5 : 10;
@@ -1226,7 +1228,7 @@ static bool sweep4_shape(int R, int grid, bool packed, Sweep4Shape& sh, int& rc,
     if (const char* e = getenv("DG_V4_NCW")) ncw = std::max(1, std::min(16, atoi(e)));
     sh.grid = std::max(1, grid);
     const int RL = (R + rc) / rc * rc;
-    int want = packed ? 8 : 10;
+    int want = packed ? 9 : 10;
     if (const char* e = getenv("DG_V4_SLOG")) want = std::max(8, std::min(10, atoi(e)));
     if (rc != 10) want = std::max(want, 9);
     for (int slog = want; slog >= (rc == 10 ? 8 : 9); --slog)
@@ -1305,11 +1307,11 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
         Sweep4Shape s4;
         int rc = 10;
         std::string why = "no kernel variant for this R";
-        if (sweep4_shape(p.R, shape.grid, !d->cooperative && shape.grid == 1, s4, rc, d->v4_ncw) && plan4_build(p, s4, rc, d->p4, why)) d->v4 = true;
+        if (sweep4_shape(p.R, shape.grid, !d->cooperative && shape.grid == 1, s4, rc, d->v4_ncw) && plan4_build(p, g, s4, rc, d->p4, why)) d->v4 = true;
         else if (getenv("DG_TIMING")) fprintf(stderr, "dg_dip: task-stream engine (%s)\n", why.c_str());
     }
     if (d->v4) {
-        d->grid = d->p4.wide_list.empty() ? 1 : shape.grid;      // no HBM-resident transition: CTA 0 does everything
+        d->grid = d->p4.full.wide_list.empty() ? 1 : shape.grid;      // no HBM-resident transition: CTA 0 does everything
         d->pred_bytes = 2; d->shift = KEY_SHIFT;
     } else {
         plan_tasks(p, shape);
@@ -1357,6 +1359,8 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
         const int smem = (int)sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
         for (int c = 0; c < 2; ++c) DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_fn(q.shape.slog, q.rc, c != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_many_fn(q.shape.slog, q.rc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // all of the SM's unified L1/shared memory as shared memory: two packed CTAs of ~105 KB each must fit
+        DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_many_fn(q.shape.slog, q.rc), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     }
     DG_CUDA(ctx, d->level_off.upload(p.level_off.data(), p.level_off.size(), s));
     DG_CUDA(ctx, d->in_off.upload(p.in_off.data(), p.in_off.size(), s));
@@ -1368,10 +1372,16 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     DG_CUDA(ctx, d->pred_off.upload(q.pred_off.data(), q.pred_off.size(), s));
     DG_CUDA(ctx, d->cp.upload(d->h_cp.data(), d->h_cp.size(), s));
     DG_CUDA(ctx, d->aoff.upload(d->h_aoff.data(), d->h_aoff.size(), s));
-    DG_CUDA(ctx, d->v4_dir.upload(q.dir.data(), q.dir.size(), s));
+    DG_CUDA(ctx, d->v4_dir.upload(q.timed.dir.data(), q.timed.dir.size(), s));
+    DG_CUDA(ctx, d->v4_dir_full.upload(q.full.dir.data(), q.full.dir.size(), s));
     DG_CUDA(ctx, d->v4_hdr.upload(q.hdr.data(), q.hdr.size(), s));
     DG_CUDA(ctx, d->v4_prog_off.upload(q.prog_off.data(), q.prog_off.size(), s));
-    DG_CUDA(ctx, d->v4_wide.upload(q.wide_list.data(), q.wide_list.size(), s));
+    DG_CUDA(ctx, d->v4_wide.upload(q.timed.wide_list.data(), q.timed.wide_list.size(), s));
+    DG_CUDA(ctx, d->v4_wide_full.upload(q.full.wide_list.data(), q.full.wide_list.size(), s));
+    DG_CUDA(ctx, d->v4_vslot.upload(q.vslot.data(), q.vslot.size(), s));
+    DG_CUDA(ctx, d->v4_dom.upload(q.lvl_dom.data(), q.lvl_dom.size(), s));
+    DG_CUDA(ctx, d->v4_tflags.upload(q.tflags.data(), q.tflags.size(), s));
+    DG_CUDA(ctx, d->v4_np.upload(q.lvl_np.data(), q.lvl_np.size(), s));
     DG_CUDA(ctx, d->v4_cls.upload(q.cls_list.data(), q.cls_list.size(), s));
     DG_CUDA(ctx, d->v4_vinfo.upload(q.vinfo.data(), q.vinfo.size(), s));
     DG_CUDA(ctx, d->v4_mpre.upload(q.mpre.data(), q.mpre.size(), s));
@@ -1384,7 +1394,6 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     DG_CUDA(ctx, d->v4_pred.alloc((size_t)q.pred_elems + 8, s));
     DG_CUDA(ctx, d->v4_sink.alloc((size_t)p.R + 1, s));
     DG_CUDA(ctx, d->tile0.alloc((size_t)std::max<int64_t>(q.gtile_cells, 1), s));
-    DG_CUDA(ctx, d->tile1.alloc((size_t)std::max<int64_t>(q.gtile_cells, 1), s));
     DG_CUDA(ctx, d->counter.alloc(4, s));
     DG_CUDA(ctx, d->level_sum.alloc((size_t)L, s));
     DG_CUDA(ctx, d->level_live.alloc((size_t)L, s));
@@ -1403,16 +1412,17 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     // the program: zero (section padding), then one CTA per transition
     DG_CUDA(ctx, cudaEventRecord(d->ev[0], s));
     DG_CUDA(ctx, cudaMemsetAsync(d->v4_prog.p, 0, (size_t)q.prog_bytes + 16, s));
-    if (q.gpad > 0) {
-        fill_dead_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(d->tile0.p, (long long)q.gpad);
-        fill_dead_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(d->tile1.p, (long long)q.gpad);
-    }
+    if (q.gpad > 0 && !q.full.wide_list.empty() + q.n_relocate > 0)
+        fill_dead_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(d->tile0.p, (long long)q.gpad);      // the two padding layers of the HBM tile
     Fill4Args fa;
     fa.l0 = 0; fa.l1 = L - 1; fa.level_off = d->level_off.p; fa.in_off = d->in_off.p; fa.in_edge = d->in_edge.p;
     fa.cls_list = d->v4_cls.p; fa.mpre = d->v4_mpre.p; fa.mpre_off = d->v4_mpre_off.p;
-    fa.lvl_n1 = d->v4_n1.p; fa.lvl_m = d->v4_m.p; fa.lvl_z = d->v4_z.p; fa.lvl_dm = d->v4_dm.p;
+    fa.lvl_n1 = d->v4_n1.p; fa.lvl_np = d->v4_np.p; fa.lvl_m = d->v4_m.p; fa.lvl_z = d->v4_z.p; fa.lvl_dm = d->v4_dm.p;
+    fa.vslot = d->v4_vslot.p; fa.lvl_dom = d->v4_dom.p; fa.tflags = d->v4_tflags.p; fa.kn = q.shape.kn; fa.hstride = q.hstride;
     fa.lvlW = d->lvlW.p; fa.msrc_off = d->msrc_off.p; fa.mdst_off = d->mdst_off.p; fa.masks = d->masks.p;
-    fa.hdr = d->v4_hdr.p; fa.dir = d->v4_dir.p; fa.prog_off = d->v4_prog_off.p; fa.prog_base = 0; fa.prog = d->v4_prog.p;
+    fa.hdr = d->v4_hdr.p; fa.prog_off = d->v4_prog_off.p; fa.prog_base = 0; fa.prog = d->v4_prog.p;
+    DG_CUDA(ctx, d->v4_tables.alloc(1, s));
+    DG_CUDA(ctx, cudaMemcpyAsync(d->v4_tables.p, &fa, sizeof fa, cudaMemcpyHostToDevice, s));
     prog_fill_kernel<<<std::min(L - 1, ctx->sm_count * 16), FILL4_THREADS, 0, s>>>(fa);
     DG_CUDA(ctx, cudaGetLastError());
     DG_CUDA(ctx, cudaEventRecord(d->ev[1], s));
@@ -1422,7 +1432,7 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     d->device_bytes = d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->lvlW.bytes() + d->masks.bytes() +
                       d->msrc_off.bytes() + d->mdst_off.bytes() + d->pred_off.bytes() + d->v4_dir.bytes() + d->v4_hdr.bytes() +
                       d->v4_prog_off.bytes() + d->v4_cls.bytes() + d->v4_vinfo.bytes() + d->v4_mpre.bytes() + d->v4_prog.bytes() +
-                      d->v4_pred.bytes() + d->tile0.bytes() + d->tile1.bytes() + d->level_sum.bytes() + d->level_live.bytes() +
+                      d->v4_pred.bytes() + d->tile0.bytes() + d->v4_vslot.bytes() + d->v4_dir_full.bytes() + d->level_sum.bytes() + d->level_live.bytes() +
                       d->anc.bytes() + d->seg_p1.bytes() + d->seg_p2.bytes();
     p.in_edge.clear(); p.in_edge.shrink_to_fit();
     p.in_dst.clear(); p.in_dst.shrink_to_fit();
@@ -1430,9 +1440,9 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     p.in_off.clear(); p.in_off.shrink_to_fit();
     q.cls_list.clear(); q.cls_list.shrink_to_fit();
     q.vinfo.clear(); q.vinfo.shrink_to_fit();
+    q.vslot.clear(); q.vslot.shrink_to_fit();
     q.mpre.clear(); q.mpre.shrink_to_fit();
     q.hdr.clear(); q.hdr.shrink_to_fit();
-    q.dir.clear(); q.dir.shrink_to_fit();
     if (d->staging) d->staging->release();
     return DG_OK;
 }
@@ -1568,15 +1578,19 @@ static void fill_sweep_args(const dg_dip* d, SweepArgs& a) {
     }
 }
 
-static void fill_sweep4_args(const dg_dip* d, Sweep4Args& a) {
+static void fill_sweep4_args(const dg_dip* d, Sweep4Args& a, bool check) {
     const DipPlan& p = d->plan;
     const Plan4& q = d->p4;
-    a.dir = d->v4_dir.p; a.wide_list = d->v4_wide.p; a.n_trans = p.L - 1; a.n_wide = (int32_t)q.wide_list.size();
-    a.prog = d->v4_prog.p; a.gtile0 = d->tile0.p; a.gtile1 = d->tile1.p; a.gpad = (long long)q.gpad;
+    const Plan4Dir& dir = check ? q.full : q.timed;         // the checksum variant folds every level, idle transitions included
+    a.dir = check ? d->v4_dir_full.p : d->v4_dir.p; a.wide_list = check ? d->v4_wide_full.p : d->v4_wide.p;
+    a.n_trans = (int32_t)dir.dir.size(); a.n_wide = (int32_t)dir.wide_list.size();
+    a.prog = d->v4_prog.p; a.gtile = d->tile0.p; a.gpad = (long long)q.gpad; a.hkk = (long long)q.hstride * q.hstride;
     a.pred = d->v4_pred.p; a.counter = d->counter.p; a.level_sum = d->level_sum.p; a.level_live = d->level_live.p;
     a.sink = d->v4_sink.p; a.R = p.R; a.nchunk = q.nchunk; a.grid = d->grid; a.ncw = d->v4_ncw;
-    a.slot_bytes = q.shape.slot_bytes; a.nslot = q.shape.nslot; a.m_nchunk = make_magic((uint32_t)q.nchunk); a.last_k = p.level_off[p.L] - p.level_off[p.L - 1]; a.kn = q.shape.kn;
-    a.final_target = q.final_target;
+    a.slot_bytes = q.shape.slot_bytes; a.nslot = q.shape.nslot; a.m_nchunk = make_magic((uint32_t)q.nchunk);
+    a.last_smem = q.lvl_dom[(size_t)p.L - 1] == 0; a.sink_cell = q.sink_cell;
+    a.chk = check ? d->v4_tables.p : nullptr;
+    a.final_target = dir.final_target;
     a.prof = d->want_prof ? d->prof.p : nullptr;
     a.timeout_ns = 10000ull * 1000000ull;
     if (const char* e = getenv("DG_SHARD_TIMEOUT_MS")) a.timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
@@ -1633,7 +1647,7 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
     cudaStream_t s = d->stream;
     if (d->v4) {
         Sweep4Args a4;
-        fill_sweep4_args(d, a4);
+        fill_sweep4_args(d, a4, check);
         void* args[] = {(void*)&a4};
         const Plan4& q = d->p4;
         const void* fn = sweep4_fn(q.shape.slog, q.rc, check);
@@ -1748,8 +1762,9 @@ int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out) {
     out->delta_bytes = (uint64_t)d->plan.delta_elems * 2;
     out->engine = d->v4 ? 4 : 3;
     if (d->v4) {
-        out->n_narrow = (int32_t)d->p4.n_smem_trans; out->n_wide = (int32_t)d->p4.wide_list.size();
-        out->n_tasks = d->plan.L - 1;
+        out->n_narrow = (int32_t)d->p4.n_smem_trans; out->n_wide = (int32_t)d->p4.timed.wide_list.size();
+        out->n_tasks = (int64_t)d->p4.timed.dir.size();
+        out->cells_written = d->p4.cells_written * (uint64_t)(d->plan.R + 1); out->n_relocate = (int32_t)d->p4.n_relocate;
         out->prog_bytes = d->p4.prog_bytes; out->code_bytes = (uint64_t)d->p4.pred_elems * 2;
         out->build_ms = d->build_ms;
     } else {
@@ -2062,7 +2077,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
             dg_dip* d = ds[i];
             d->want_prof = false; d->launches = 0;
             DG_CUDA(ctx, cudaMemsetAsync(d->counter.p, 0, 4 * sizeof(unsigned int), ctx->stream));
-            fill_sweep4_args(d, h_args[(size_t)i]);
+            fill_sweep4_args(d, h_args[(size_t)i], false);
             fill_trace_args(d, h_ta[(size_t)i]);
             for (int c = 0; c < d->grid; ++c) h_map.push_back(make_int2(i, c));
             max_anc = std::max(max_anc, d->anc_cells); max_M = std::max(max_M, d->M);
@@ -2082,6 +2097,11 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
         const Sweep4Args* pa = d_args.p;
         const int2* pm = d_map.p;
         void* args[] = {(void*)&pa, (void*)&pm};
+        if (getenv("DG_TIMING")) {
+            int per_sm = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (ds[0]->v4_ncw + 1) * 32, smem);
+            fprintf(stderr, "dg_dip_run_many: %zu CTAs of %d threads, %zu bytes of shared memory: %d per SM\n", h_map.size(), (ds[0]->v4_ncw + 1) * 32, smem, per_sm);
+        }
         DG_CUDA(ctx, cudaEventRecord(f0, ctx->stream));
         DG_CUDA(ctx, cudaLaunchKernel(fn, dim3((unsigned)h_map.size()), dim3((unsigned)(ds[0]->v4_ncw + 1) * 32u), args, smem, ctx->stream));
         DG_CUDA(ctx, cudaEventRecord(swept, ctx->stream));
@@ -2116,7 +2136,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
             DG_CUDA(ctx, cudaEventCreateWithFlags(&done[(size_t)i], cudaEventDisableTiming));
             DG_CUDA(ctx, cudaEventRecord(done[(size_t)i], d->stream));
             DG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, done[(size_t)i], 0));
-            if (v4) fill_sweep4_args(d, h_args4[(size_t)i]); else fill_sweep_args(d, h_args[(size_t)i]);
+            if (v4) fill_sweep4_args(d, h_args4[(size_t)i], false); else fill_sweep_args(d, h_args[(size_t)i]);
             for (int c = 0; c < d->grid; ++c) h_map.push_back(make_int2(i, c));
         }
         DevBuf<SweepArgs> d_args;

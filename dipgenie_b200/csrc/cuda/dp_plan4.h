@@ -2,11 +2,13 @@
 // compiled into the CPU kernel-logic emulator under tests/emu/.
 //
 // From the gather-form plan of dp_prep.h (in-edge CSR by destination in ascending source position, colour masks)
-// this computes what is O(V): the S1/M/Z class tables of every level, the closed-form descriptor counts, the
-// program and predecessor-code offsets, the placement of every layer (shared memory of CTA 0 or HBM/L2) and the
-// barrier schedule.  The O(sum E^2) part — the descriptors themselves — is written by the device
-// (dp_sweep4.cu: prog_fill_kernel) with the per-descriptor functions of dp_prog.h; prog_fill_level_host runs the same
-// functions serially for the emulator and for the test that compares the device-built program byte for byte.
+// this computes what is O(V): the slot of every vertex (passive vertices inherit their predecessor's, the others get
+// a fresh one; dp_prog.h), the placement of every level (shared-memory tile of CTA 0 or HBM tile), the
+// S1a/S1p/M/Z class tables, the closed-form descriptor counts, the program and predecessor-code offsets, and two
+// directories with their barrier schedules: every transition (the checksum variant needs them all) and the transitions
+// that have something to do (the timed variant).  The O(sum E^2) part — the descriptors themselves — is written by the
+// device (dp_sweep4.cuh: prog_fill_kernel) with the per-descriptor functions of dp_prog.h; prog_fill_level_host runs
+// the same functions serially for the emulator and for the test that compares the device-built program byte for byte.
 #pragma once
 #include <cstdint>
 #include <string>
@@ -17,30 +19,41 @@
 
 namespace dg {
 
+struct Plan4Dir {
+    std::vector<ProgDir> dir;            // transitions in level order
+    std::vector<int32_t> wide_list;      // indices into `dir` of the transitions every CTA takes part in
+    uint32_t final_target = 0;           // barrier arrivals once the last transition is complete
+};
+
 struct Plan4 {
     Sweep4Shape shape;
     int32_t L = 0, R = 0, rc = 10, nchunk = 1, RL = 0;   // RL = nchunk * rc layers are computed (>= R+1)
-    std::vector<uint16_t> cls_list;      // [V]   per level: S1 | M | Z positions
-    std::vector<uint32_t> vinfo;         // [V]   rank in class | class << 30
+    std::vector<uint16_t> cls_list;      // [V]   per level: S1a | S1p | M | Z positions
+    std::vector<uint32_t> vinfo;         // [V]   rank in class | class << 30 (S1 ranks over S1a | S1p)
+    std::vector<uint16_t> vslot;         // [V]   slot of the vertex in its level's tile
+    std::vector<uint8_t> lvl_dom;        // [L]   0: shared-memory tile, 1: HBM tile
     std::vector<uint32_t> mpre;          // per level m+1 entries: prefix of in-degrees over M
     std::vector<int64_t> mpre_off;       // [L]
-    std::vector<uint32_t> lvl_n1, lvl_m, lvl_z, lvl_dm;   // [L]
+    std::vector<uint32_t> lvl_n1, lvl_np, lvl_m, lvl_z, lvl_dm;   // [L]
     std::vector<ProgHdr> hdr;            // [L-1] header of transition l
-    std::vector<ProgDir> dir;            // [L-1]
+    std::vector<uint32_t> tflags;        // [L-1] PF_COMPACT / SRC_SMEM / DST_SMEM / RELOCATE of transition l
+    Plan4Dir full, timed;
     std::vector<uint64_t> prog_off;      // [L]   byte offset of transition l's program (prog_off[L-1] = total)
     std::vector<int64_t> pred_off;       // [L+1] u16 elements: codes of level l
-    std::vector<int32_t> wide_list;      // transitions every CTA takes part in
     uint64_t prog_bytes = 0;
     int64_t pred_elems = 0;
-    int64_t gpad = 0, gtile_cells = 0;   // HBM tile: gpad dead cells, then RL layers of the widest HBM-resident level
-    int64_t n_smem_trans = 0;            // transitions with both layers in shared memory
+    int32_t hstride = 1;                 // slots per row of the HBM tile
+    int64_t gpad = 0, gtile_cells = 0;   // HBM tile: gpad dead cells, then RL layers of hstride^2 cells
+    int64_t n_smem_trans = 0;            // transitions with both levels in shared memory
+    int64_t n_relocate = 0, n_skipped = 0;
+    uint64_t cells_written = 0, cells_total = 0;   // destination cells in the programs / of the levels (per layer)
     uint32_t max_cand = 0;
-    uint32_t final_target = 0;           // barrier arrivals once the last transition is complete
+    uint32_t sink_cell = 0;              // cell (0,0) of the last level in its tile
 };
 
 // Returns false (with `why`) when the problem is outside what the packed-key level program covers; the caller then
 // takes the task-stream engine.
-bool plan4_build(const DipPlan& p, const Sweep4Shape& shape, int rc, Plan4& out, std::string& why);
+bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& shape, int rc, Plan4& out, std::string& why);
 
 // The view of transition l the dp_prog.h functions take.
 ProgLevelIn plan4_level_in(const DipPlan& p, const Plan4& q, int l);

@@ -1,5 +1,5 @@
 // dp_prog.h — the LEVEL PROGRAM of the diploid DP sweep (engine "v4"), shared verbatim by the device builder
-// (dp_sweep4.cu: prog_fill_kernel), the sweep kernel (dp_sweep4.cu: dip_sweep4_kernel) and the CPU kernel-logic
+// (dp_sweep4.cuh: prog_fill_kernel), the sweep kernel (dp_sweep4.cuh: dip_sweep4_kernel) and the CPU kernel-logic
 // emulator of the `-m "not gpu"` tests (tests/emu/dp_emu4.cpp).  Nothing here is a fallback: the product only runs
 // it on the device.
 //
@@ -11,9 +11,22 @@
 // the chain: a fully parallel pre-pass expands every transition into a flat program of descriptors, and the
 // sweep kernel only streams descriptors and layers.
 //
-// A destination vertex is S1 (one in-edge), M (two or more) or Z (none).  The cells of level l+1 are
-//   * copy cells   S1 x S1            one candidate: dst = src shifted by w, plus delta; NO predecessor code is stored
-//                                     (the code is implied: ordinal 0);
+// IN-PLACE LAYERS.  The reference copies every cell of every level (dp_cur -> dp_next, :565-576, :704-706), although
+// most of a pangenome level is a relabelling: a lane or dummy vertex with one weight-0 in-edge, no colours on either
+// end.  Here a vertex owns a SLOT (row and column index of the layer tile) instead of its level-local position, and such
+// a "passive" vertex inherits the slot of its predecessor: the cells of passive x passive pairs are the same memory
+// in level l and l+1, their value is unchanged (delta = 0, no layer shift) — they are not touched and appear in no
+// program.  Every other vertex of level l+1 gets a FRESH slot (one no vertex of level l holds), so every written cell
+// has a fresh row or column and never aliases a cell that is read in the same transition: one tile, no ping-pong, no
+// hazards.  Slots of level-l vertices that nobody inherits are recycled after the transition.  Tie-breaking is
+// unaffected: the candidates of a cell are still enumerated in ascending source POSITION (i, then j).
+// A level lives in the shared-memory tile of CTA 0 (at most `kn` slots) or in the HBM tile; a transition that changes
+// the placement RELOCATES the level: all its cells are written (compact slots 0..k-1), passive ones included.
+//
+// A destination vertex is S1 (one in-edge), M (two or more) or Z (none); S1 splits into passive (S1p) and the rest
+// (S1a).  The cells of level l+1 are
+//   * copy cells   S1 x S1 minus S1p x S1p   one candidate: dst = src shifted by w, plus delta; NO predecessor code is
+//                                     stored (the code is implied: ordinal 0);
 //   * multi cells  A = M x S1, B = S1 x M, C = M x M, enumerated in that order ("slot" t = position in this
 //                                     enumeration, closed form below); candidates in (e1,e2) lexicographic order;
 //                                     a 16-bit predecessor code (the winner's ordinal) per layer is stored at
@@ -42,33 +55,35 @@ constexpr int V4_SHIFT = KEY_SHIFT;                       // 10
 constexpr uint32_t V4_ORD_MASK = (1u << V4_SHIFT) - 1u;   // 1023
 constexpr uint32_t PROG_BIG_MIN = 12;                     // multi cells with this many candidates go to the warp form
 constexpr uint32_t PROG_MAX_CAND = 1024;                  // candidates per cell the packed ordinal can hold
-constexpr int PROG_COMPACT_K = 32;                        // compact descriptors: both levels at most this wide
-constexpr uint32_t PROG_COMPACT_DELTA = 1023;             // ... and at most this many colours on the two levels
+constexpr uint32_t PROG_COMPACT_DELTA = 1023;             // compact descriptors: at most this many colours on the two levels
 
 enum : uint32_t {
-    PF_COMPACT = 1,      // compact descriptors (10-bit cell indices)
+    PF_COMPACT = 1,      // compact descriptors (10-bit cell indices: both levels in the shared-memory tile)
     PF_SRC_SMEM = 2,     // level l lives in CTA 0's shared-memory tile
-    PF_DST_SMEM = 4,     // level l+1 goes to CTA 0's shared-memory tile
+    PF_DST_SMEM = 4,     // level l+1 lives in CTA 0's shared-memory tile
     PF_STAGED = 8,       // the whole program travels into the ring slot (else only dir entry + header)
     PF_WAIT = 16,        // wait for dir.wait_target arrivals before the level
     PF_ARRIVE = 32,      // arrive after the level
-    PF_ALL_CTAS = 64,    // every CTA of the problem takes part (both layers in HBM/L2)
+    PF_ALL_CTAS = 64,    // every CTA of the problem takes part (both levels in HBM/L2)
+    PF_RELOCATE = 128,   // the level changes tiles: every cell is written (else in place: passive x passive cells are not)
 };
 
-// Directory entry of a transition (16 bytes, copied into the slot in front of the program).
+// Directory entry of a transition (32 bytes, copied into the slot in front of the program).
 struct ProgDir {
     uint32_t off16;        // program offset in the program buffer, units of 16 bytes
     uint32_t stage_bytes;  // bytes the producer copies after the entry: the whole program or just the header
     uint32_t wait_target;
     uint32_t flags;
+    int32_t level;         // transition level -> level + 1 (the timed directory skips the transitions with nothing to do)
+    uint32_t rsv[3];
 };
-static_assert(sizeof(ProgDir) == 16, "ProgDir layout");
+static_assert(sizeof(ProgDir) == 32, "ProgDir layout");
 
 struct ProgHdr {           // 64 bytes
     uint16_t k, k2;
     uint32_t n_copy, n_multi, n_cand, n_big, n_dead;
     uint32_t max_n;        // most candidates of a thread-form multi cell (loop bound hint)
-    uint32_t rsv;
+    uint32_t n_passive;    // S1p vertices of level l+1 (their pairs are not in the program)
     uint64_t pred_off;     // u16 elements: codes of level l+1 start here, layout [layer][slot]
     uint64_t rsv2;
     uint32_t off_cell, off_cand, off_big, off_dead;   // section offsets from the header's start (prog_layout; the copy section follows the header)
@@ -92,7 +107,7 @@ DG_HD ProgLayout prog_layout(bool compact, uint64_t n_copy, uint64_t n_multi, ui
     return o;
 }
 
-// ---- descriptors -----------------------------------------------------------------------------------------------
+// ---- descriptors (cell indices are SLOT based: slot(i) * stride + slot(j)) ------------------------------------------
 // compact copy  u32 : src[0:10) dst[10:20) w[20:22) delta[22:32)
 // compact cell  u32x2: dst[0:10) | n << 16 ; cand_off (level-local candidate index)
 // compact cand  u32 : src[0:10) w[10:12) delta[12:32)
@@ -108,23 +123,22 @@ DG_HD CopyDesc unpack_copy_c(uint32_t x) { return {x & 1023u, (x >> 10) & 1023u,
 DG_HD uint32_t pack_cand_c(const CandDesc& d) { return d.src | (d.w << 10) | (d.delta << 12); }
 DG_HD CandDesc unpack_cand_c(uint32_t x) { return {x & 1023u, (x >> 10) & 3u, x >> 12}; }
 
-// ---- per-level class tables (built once per problem, prog_classify) ------------------------------------------------
-// For the vertices of one level, in position order: S1 positions first, then M, then Z (cls_list), the rank of every
-// vertex within its class (vrank), and for the M vertices the running sum of their in-degrees (mpre, m+1 entries at
-// cls offset of the level + n1).
+// ---- per-level class tables (built once per problem, dp_plan4.cpp) -----------------------------------------------
+// For the vertices of one level, positions in class order S1a | S1p | M | Z (each class in position order), and for the M
+// vertices the running sum of their in-degrees.
 struct LevelClass {
-    uint32_t k2, n1, m, z, dm;       // dm = sum of in-degrees over M
-    const uint16_t* list;            // [k2]  S1 | M | Z positions
+    uint32_t k2, n1, np, m, z, dm;   // n1 = all S1 vertices, np of them passive; dm = sum of in-degrees over M
+    const uint16_t* list;            // [k2]  S1a | S1p | M | Z positions
     const uint32_t* mpre;            // [m+1] prefix of in-degrees over M in rank order
 };
 
 struct ProgCounts { uint64_t n_copy, n_multi, n_cand, n_big, n_dead; uint32_t max_n; };
 
-// in_off: in-edge CSR offsets of the level's vertices (k2+1 entries, absolute); counts are closed-form except n_big.
-DG_HD ProgCounts prog_counts(const LevelClass& c) {
+// `relocate`: passive vertices are written like the others (np counts as 0).
+DG_HD ProgCounts prog_counts(const LevelClass& c, bool relocate) {
     ProgCounts o;
-    const uint64_t n1 = c.n1, m = c.m, dm = c.dm, k2 = c.k2, live = n1 + m;
-    o.n_copy = n1 * n1;
+    const uint64_t n1 = c.n1, np = relocate ? 0 : c.np, m = c.m, dm = c.dm, k2 = c.k2, live = n1 + m;
+    o.n_copy = n1 * n1 - np * np;
     o.n_multi = 2 * m * n1 + m * m;
     o.n_cand = 2 * dm * n1 + dm * dm;
     o.n_dead = k2 * k2 - live * live;
@@ -161,6 +175,10 @@ struct ProgLevelIn {
     const int32_t* in_off;      // &in_off[level_off[l+1]] : k2+1 absolute offsets
     const uint32_t* in_edge;    // whole array: entry = source position | weight << 16
     LevelClass cls;
+    const uint16_t* slot_src;   // [k]  slot of every vertex of level l (by position)
+    const uint16_t* slot_dst;   // [k2] ... of level l+1
+    uint32_t stride_src, stride_dst;   // slots per row of the tile level l / l+1 lives in
+    bool relocate;
     int32_t W;                  // mask words (0: no colours on the two levels)
     const uint64_t* msrc;
     const uint64_t* mdst;
@@ -170,17 +188,25 @@ DG_HD void in_edge_at(const ProgLevelIn& L, uint32_t pos, uint32_t e, uint32_t& 
     const uint32_t x = L.in_edge[L.in_off[pos] + (int32_t)e];
     src_pos = x & 0xFFFFu; w = x >> 16;
 }
+DG_HD uint32_t src_cell(const ProgLevelIn& L, uint32_t i, uint32_t j) { return (uint32_t)L.slot_src[i] * L.stride_src + L.slot_src[j]; }
+DG_HD uint32_t dst_cell(const ProgLevelIn& L, uint32_t i2, uint32_t j2) { return (uint32_t)L.slot_dst[i2] * L.stride_dst + L.slot_dst[j2]; }
 
-// copy cell t in [0, n1^2)
+// copy cell t in [0, n1^2 - np^2): the rows of the S1a vertices in full (all S1 columns), then the S1a columns of the S1p rows
+DG_HD void copy_pair(const ProgLevelIn& L, uint64_t t, uint32_t& i2, uint32_t& j2) {
+    const uint64_t n1 = L.cls.n1, np = L.relocate ? 0 : L.cls.np, na = n1 - np;
+    uint32_t a, b;
+    if (t < na * n1) { a = (uint32_t)(t / n1); b = (uint32_t)(t - (uint64_t)a * n1); }
+    else { const uint64_t u = t - na * n1; const uint32_t r = (uint32_t)(u / na); a = (uint32_t)na + r; b = (uint32_t)(u - (uint64_t)r * na); }
+    i2 = L.cls.list[a]; j2 = L.cls.list[b];
+}
 DG_HD CopyDesc make_copy(const ProgLevelIn& L, uint64_t t) {
-    const uint32_t n1 = L.cls.n1;
-    const uint32_t a = (uint32_t)(t / n1), b = (uint32_t)(t - (uint64_t)a * n1);
-    const uint32_t i2 = L.cls.list[a], j2 = L.cls.list[b];
+    uint32_t i2, j2;
+    copy_pair(L, t, i2, j2);
     uint32_t i, wi, j, wj;
     in_edge_at(L, i2, 0, i, wi);
     in_edge_at(L, j2, 0, j, wj);
     CopyDesc d;
-    d.src = i * L.k + j; d.dst = i2 * L.k2 + j2; d.w = wi + wj;
+    d.src = src_cell(L, i, j); d.dst = dst_cell(L, i2, j2); d.w = wi + wj;
     d.delta = L.W ? (uint32_t)mask_delta(L.W, L.msrc, L.mdst, (int)i, (int)j, (int)i2, (int)j2) : 0u;
     return d;
 }
@@ -221,7 +247,7 @@ DG_HD CandDesc make_cand(const ProgLevelIn& L, const MultiCell& c, uint32_t ord)
     in_edge_at(L, c.i2, e1, i, wi);
     in_edge_at(L, c.j2, e2, j, wj);
     CandDesc d;
-    d.src = i * L.k + j; d.w = wi + wj;
+    d.src = src_cell(L, i, j); d.w = wi + wj;
     d.delta = L.W ? (uint32_t)mask_delta(L.W, L.msrc, L.mdst, (int)i, (int)j, (int)c.i2, (int)c.j2) : 0u;
     return d;
 }
@@ -232,17 +258,25 @@ DG_HD uint32_t dead_cell(const ProgLevelIn& L, uint64_t x) {
     const uint16_t* Z = L.cls.list + live;
     if (x < z * k2) {
         const uint32_t a = (uint32_t)(x / k2), j2 = (uint32_t)(x - (uint64_t)a * k2);
-        return (uint32_t)(Z[a] * k2 + j2);
+        return dst_cell(L, Z[a], j2);
     }
     const uint64_t u = x - z * k2;
     const uint32_t a = (uint32_t)(u / z), b = (uint32_t)(u - (uint64_t)a * z);
-    return (uint32_t)(L.cls.list[a] * k2 + Z[b]);      // list[0 .. live) = the S1 and M positions
+    return dst_cell(L, L.cls.list[a], Z[b]);      // list[0 .. live) = the S1 and M positions
+}
+
+// Passive pair x in [0, np^2) of an in-place transition (not in the program: the cell is the same memory in both
+// levels): destination positions; the sources are the single in-edges' (checksum variant and emulator only).
+DG_HD void passive_pair(const ProgLevelIn& L, uint64_t x, uint32_t& i2, uint32_t& j2) {
+    const uint32_t np = L.cls.np, na = L.cls.n1 - np;
+    const uint32_t a = (uint32_t)(x / np), b = (uint32_t)(x - (uint64_t)a * np);
+    i2 = L.cls.list[na + a]; j2 = L.cls.list[na + b];
 }
 
 // Kernel geometry the directory is made for.
 struct Sweep4Shape {
     int slog = 10;             // shared-memory layer stride = 1 << slog cells
-    int kn = 32;               // levels at most this wide live in shared memory (kn * kn <= 1 << slog)
+    int kn = 32;               // slots of the shared-memory tile (kn * kn <= 1 << slog)
     int slot_bytes = 8192;     // ring slot (directory entry + program)
     int nslot = 4;             // ring depth
     int grid = 1;              // CTAs of the problem

@@ -33,16 +33,41 @@ struct Fill4Args {
     const uint16_t* cls_list;
     const uint32_t* mpre;
     const int64_t* mpre_off;
-    const uint32_t* lvl_n1; const uint32_t* lvl_m; const uint32_t* lvl_z; const uint32_t* lvl_dm;
+    const uint32_t* lvl_n1; const uint32_t* lvl_np; const uint32_t* lvl_m; const uint32_t* lvl_z; const uint32_t* lvl_dm;
+    const uint16_t* vslot;               // [V] slot of every vertex in its level's tile
+    const uint8_t* lvl_dom;              // [L] 0 shared-memory tile, 1 HBM tile
+    const uint32_t* tflags;              // [L-1] PF_COMPACT / PF_RELOCATE ... of the transition
+    int32_t kn, hstride;                 // slots per row of the two tiles
     const int32_t* lvlW;
     const int64_t* msrc_off; const int64_t* mdst_off;
     const uint64_t* masks;
     const ProgHdr* hdr;
-    const ProgDir* dir;
     const uint64_t* prog_off;            // byte offsets, absolute
     uint64_t prog_base;                  // byte offset of `prog` within the whole program (windowed building)
     uint8_t* prog;
 };
+
+// The dp_prog.h view of transition l from the device tables (builder and checksum variant).
+template <class A>
+__device__ __forceinline__ ProgLevelIn level_in(const A& a, int l) {
+    ProgLevelIn in;
+    const int32_t lo = a.level_off[l], mid = a.level_off[l + 1];
+    in.k = (uint32_t)(mid - lo); in.k2 = (uint32_t)(a.level_off[l + 2] - mid);
+    in.in_off = a.in_off + mid;
+    in.in_edge = a.in_edge;
+    in.cls.k2 = in.k2; in.cls.n1 = a.lvl_n1[l + 1]; in.cls.np = a.lvl_np[l + 1]; in.cls.m = a.lvl_m[l + 1]; in.cls.z = a.lvl_z[l + 1];
+    in.cls.dm = a.lvl_dm[l + 1];
+    in.cls.list = a.cls_list + mid;
+    in.cls.mpre = a.mpre + a.mpre_off[l + 1];
+    in.slot_src = a.vslot + lo; in.slot_dst = a.vslot + mid;
+    in.stride_src = a.lvl_dom[l] == 0 ? (uint32_t)a.kn : (uint32_t)a.hstride;
+    in.stride_dst = a.lvl_dom[l + 1] == 0 ? (uint32_t)a.kn : (uint32_t)a.hstride;
+    in.relocate = (a.tflags[l] & PF_RELOCATE) != 0;
+    in.W = a.lvlW[l];
+    in.msrc = in.W ? a.masks + a.msrc_off[l] : nullptr;
+    in.mdst = in.W ? a.masks + a.mdst_off[l] : nullptr;
+    return in;
+}
 
 constexpr int FILL4_THREADS = 256;
 
@@ -53,20 +78,10 @@ __global__ void __launch_bounds__(FILL4_THREADS) prog_fill_kernel(const Fill4Arg
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int l = a.l0 + (int)blockIdx.x; l < a.l1; l += (int)gridDim.x) {
         const ProgHdr h = a.hdr[l];
-        const bool compact = (a.dir[l].flags & PF_COMPACT) != 0;
+        const bool compact = (a.tflags[l] & PF_COMPACT) != 0;
         const ProgLayout lay = prog_layout(compact, h.n_copy, h.n_multi, h.n_cand, h.n_big, h.n_dead);
         uint8_t* const out = a.prog + (a.prog_off[l] - a.prog_base);
-        ProgLevelIn in;
-        const int32_t mid = a.level_off[l + 1];
-        in.k = h.k; in.k2 = h.k2;
-        in.in_off = a.in_off + mid;
-        in.in_edge = a.in_edge;
-        in.cls.k2 = h.k2; in.cls.n1 = a.lvl_n1[l + 1]; in.cls.m = a.lvl_m[l + 1]; in.cls.z = a.lvl_z[l + 1]; in.cls.dm = a.lvl_dm[l + 1];
-        in.cls.list = a.cls_list + mid;
-        in.cls.mpre = a.mpre + a.mpre_off[l + 1];
-        in.W = a.lvlW[l];
-        in.msrc = in.W ? a.masks + a.msrc_off[l] : nullptr;
-        in.mdst = in.W ? a.masks + a.mdst_off[l] : nullptr;
+        const ProgLevelIn in = level_in(a, l);
         if (tid < (int)(sizeof(ProgHdr) / 4)) reinterpret_cast<uint32_t*>(out)[tid] = reinterpret_cast<const uint32_t*>(&a.hdr[l])[tid];
         if (tid == 0) big_base = 0;
         __syncthreads();
@@ -81,7 +96,7 @@ __global__ void __launch_bounds__(FILL4_THREADS) prog_fill_kernel(const Fill4Arg
             bool is_big = false;
             if (t < h.n_multi) {
                 const MultiCell c = multi_cell(in, t);
-                const uint32_t dst = c.i2 * in.k2 + c.j2;
+                const uint32_t dst = dst_cell(in, c.i2, c.j2);
                 if (compact) reinterpret_cast<uint2*>(out + lay.cell)[t] = make_uint2(dst | (c.n << 16), (uint32_t)c.cand_off);
                 else reinterpret_cast<uint4*>(out + lay.cell)[t] = make_uint4(dst, c.n, (uint32_t)c.cand_off, 0u);
                 for (uint32_t o = 0; o < c.n; ++o) {
@@ -120,8 +135,8 @@ struct Sweep4Args {
     const int32_t* wide_list;     // transitions every CTA takes part in
     int32_t n_trans, n_wide;
     const uint8_t* prog;
-    int32_t* gtile0; int32_t* gtile1;     // HBM tiles: gpad dead cells, then RL layers of stride k^2
-    long long gpad;
+    int32_t* gtile;               // HBM tile: gpad dead cells, then RL layers of hkk = hstride^2 cells (in place: dp_prog.h)
+    long long gpad, hkk;
     uint16_t* pred;
     unsigned int* counter;        // [0] level arrivals, [1] first barrier that timed out (level + 1), sticky
     unsigned long long* level_sum;
@@ -131,8 +146,9 @@ struct Sweep4Args {
     int32_t grid, ncw;            // CTAs of the problem, compute warps per CTA
     int32_t slot_bytes, nslot;    // ring geometry
     uint32_t m_nchunk;            // magic of nchunk (dp_cell.h: make_magic; 0 when nchunk == 1)
-    int32_t last_k;               // width of the last level
-    int32_t kn;
+    int32_t last_smem;            // the last level lives in the shared-memory tile
+    uint32_t sink_cell;           // its cell (0,0)
+    const Fill4Args* chk;         // checksum variant: the device tables the positions of a descriptor are decoded from
     uint32_t final_target;        // arrivals once the last transition is complete
     unsigned long long* prof;     // diagnostics (nullable): cycles of CTA 0 / thread 0 in [slot wait, level work, barrier], levels
     unsigned long long timeout_ns;
@@ -161,11 +177,12 @@ __device__ __forceinline__ void sts_layers(uint32_t a, const int32_t (&v)[RC]) {
 struct Lvl4 {
     const uint8_t* copy_p; const uint8_t* cell_p; const uint8_t* cand_p; const uint8_t* big_p; const uint8_t* dead_p;   // generic pointers (slot or HBM)
     uint32_t k, k2, n_copy, n_multi, n_big, n_dead;
-    uint32_t src32, dst32;                // shared-memory tiles: address of padding layer -2
-    const int32_t* gsrc; int32_t* gdst;   // HBM tiles: address of layer 0
-    long long kk, kk2;
+    uint32_t src32, dst32;                // shared-memory tile: address of padding layer -2
+    const int32_t* gsrc; int32_t* gdst;   // HBM tile: address of layer 0
+    long long kk, kk2;                    // layer strides there
     uint16_t* pl;                         // codes of level l+1, [layer][slot]
     int level, R, nchunk;
+    const ProgLevelIn* in;                // checksum variant only
 };
 
 template <bool COMPACT> __device__ __forceinline__ CopyDesc ld_copy(const uint8_t* p, uint32_t t) {
@@ -206,11 +223,30 @@ __device__ __forceinline__ void store_layers(const Lvl4& c, int r0, uint32_t dst
     }
 }
 
+// Checksum variant: the fold of oracle/ref_hook.h over (flat POSITION index, value, source positions) of a live cell.
 struct Fold4 { unsigned long long sum, live; };
-__device__ __forceinline__ void fold4(Fold4& f, const Lvl4& c, int r, uint32_t dst, int32_t val, uint32_t src) {
-    if (r > c.R || val < 0) return;
+__device__ __forceinline__ void fold_pos(Fold4& f, int R, uint32_t k2, int r, uint32_t i2, uint32_t j2, int32_t val, uint32_t i, uint32_t j) {
+    if (r > R || val < 0) return;
     ++f.live;
-    f.sum += cell_fold((uint64_t)r * (uint64_t)c.kk2 + dst, val >> V4_SHIFT, (int)(src / c.k), (int)(src % c.k));
+    f.sum += cell_fold(((uint64_t)r * k2 + i2) * k2 + j2, val >> V4_SHIFT, (int)i, (int)j);
+}
+__device__ __forceinline__ void fold_copy(Fold4& f, const ProgLevelIn& in, int R, uint32_t t, int r0, const int32_t* v, int n) {
+    uint32_t i2, j2, i, wi, j, wj;
+    copy_pair(in, t, i2, j2);
+    in_edge_at(in, i2, 0, i, wi); in_edge_at(in, j2, 0, j, wj);
+    for (int q = 0; q < n; ++q) fold_pos(f, R, in.k2, r0 + q, i2, j2, v[q], i, j);
+}
+__device__ __forceinline__ void fold_multi(Fold4& f, const ProgLevelIn& in, int R, uint32_t t, int r0, const int32_t* key, int n) {
+    const MultiCell mc = multi_cell(in, t);
+    for (int q = 0; q < n; ++q) {
+        const int32_t val = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
+        if (val < 0 || r0 + q > R) continue;
+        const uint32_t o = V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
+        const uint32_t e1 = o / mc.d2, e2 = o - e1 * mc.d2;
+        uint32_t i, wi, j, wj;
+        in_edge_at(in, mc.i2, e1, i, wi); in_edge_at(in, mc.j2, e2, j, wj);
+        fold_pos(f, R, in.k2, r0 + q, mc.i2, mc.j2, val, i, j);
+    }
 }
 
 // 32 copy cells, one thread each: dst = src shifted by w layers, plus delta.
@@ -229,10 +265,7 @@ __device__ __forceinline__ void copy_block(const Lvl4& c, uint32_t blk, int lane
         for (int q = 0; q < RC; ++q) v[q] += add;
         if (active) {
             store_layers<SLOG, RC, DS>(c, r0, d.dst, v);
-            if (CHECK) {
-#pragma unroll
-                for (int q = 0; q < RC; ++q) fold4(f, c, r0 + q, d.dst, v[q], d.src);
-            }
+            if (CHECK) fold_copy(f, *c.in, c.R, t, r0, v, RC);
         }
     }
 }
@@ -270,15 +303,7 @@ __device__ __forceinline__ void multi_block(const Lvl4& c, uint32_t blk, int lan
                 pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
             }
             store_layers<SLOG, RC, DS>(c, r0, cd.dst, val);
-            if (CHECK) {
-#pragma unroll
-                for (int q = 0; q < RC; ++q) {
-                    if (val[q] >= 0 && r0 + q <= c.R) {
-                        const uint32_t o = V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
-                        fold4(f, c, r0 + q, cd.dst, val[q], ld_cand<COMPACT>(c.cand_p, cd.cand_off + o).src);
-                    }
-                }
-            }
+            if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
         }
     }
 }
@@ -312,15 +337,7 @@ __device__ __forceinline__ void big_cell(const Lvl4& c, uint32_t u, int lane, Fo
                 pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
             }
             store_layers<SLOG, RC, DS>(c, r0, cd.dst, val);
-            if (CHECK) {
-#pragma unroll
-                for (int q = 0; q < RC; ++q) {
-                    if (val[q] >= 0 && r0 + q <= c.R) {
-                        const uint32_t o = V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
-                        fold4(f, c, r0 + q, cd.dst, val[q], ld_cand<COMPACT>(c.cand_p, cd.cand_off + o).src);
-                    }
-                }
-            }
+            if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
         }
     }
 }
@@ -353,8 +370,7 @@ __device__ __forceinline__ void run_level(const Lvl4& c, uint32_t gw, uint32_t g
 // wide-format programs, programs read in place.  Out of line, with a handful of scalar arguments: the narrow loop keeps
 // its own register allocation.  `sb` = the ring slot (directory entry, then the header and, if staged, the program).
 template <int SLOG, int RC, bool CHECK>
-__device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_t* sb, uint32_t tiles32, uint32_t tile_bytes,
-                                               int l, int cta, int warp, int lane) {
+__device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_t* sb, uint32_t tile32, int l, int cta, int warp, int lane) {
     const ProgDir d = *reinterpret_cast<const ProgDir*>(sb);
     const ProgHdr h = *reinterpret_cast<const ProgHdr*>(sb + sizeof(ProgDir));
     const uint32_t flags = d.flags;
@@ -363,11 +379,13 @@ __device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_
     const uint8_t* const pb = (flags & PF_STAGED) ? sb + sizeof(ProgDir) : a.prog + (size_t)d.off16 * 16;
     c.copy_p = pb + sizeof(ProgHdr); c.cell_p = pb + h.off_cell; c.cand_p = pb + h.off_cand; c.big_p = pb + h.off_big; c.dead_p = pb + h.off_dead;
     c.level = l; c.R = a.R; c.nchunk = a.nchunk;
-    const uint32_t odd = (uint32_t)l & 1u;
-    c.src32 = tiles32 + odd * tile_bytes; c.dst32 = tiles32 + (odd ^ 1u) * tile_bytes;
-    c.gsrc = (odd ? a.gtile1 : a.gtile0) + a.gpad; c.gdst = (odd ? a.gtile0 : a.gtile1) + a.gpad;
-    c.kk = (long long)c.k * c.k; c.kk2 = (long long)c.k2 * c.k2;
+    c.src32 = tile32; c.dst32 = tile32;
+    c.gsrc = a.gtile + a.gpad; c.gdst = a.gtile + a.gpad;
+    c.kk = a.hkk; c.kk2 = a.hkk;
     c.pl = a.pred + h.pred_off;
+    ProgLevelIn in;
+    if (CHECK) in = level_in(*a.chk, l);
+    c.in = &in;
     const bool all = (flags & PF_ALL_CTAS) != 0;
     const uint32_t gw = all ? (uint32_t)(cta * a.ncw + warp) : (uint32_t)warp;
     const uint32_t gs = all ? (uint32_t)(a.grid * a.ncw) : (uint32_t)a.ncw;
@@ -389,20 +407,14 @@ struct Fast4 {
     uint32_t n_copy, n_multi, n_big, n_dead;
     uint32_t src32, dst32;        // tiles: address of padding layer -2
     uint16_t* pl;                 // codes of level l+1
-    uint32_t k, kk2;
     int R;
+    const ProgLevelIn* in;        // checksum variant only
 };
 
 __device__ __forceinline__ uint2 lds_v2(uint32_t a) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
-}
-
-__device__ __forceinline__ void fold4f(Fold4& f, const Fast4& c, int r, uint32_t dst, int32_t val, uint32_t src) {
-    if (r > c.R || val < 0) return;
-    ++f.live;
-    f.sum += cell_fold((uint64_t)r * c.kk2 + dst, val >> V4_SHIFT, (int)(src / c.k), (int)(src % c.k));
 }
 
 template <int SLOG, int RC, bool CHECK>
@@ -418,10 +430,7 @@ __device__ __forceinline__ void fast_copy(const Fast4& c, uint32_t blk, int r0, 
     for (int q = 0; q < RC; ++q) v[q] += add;
     if (active) {
         sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, v);
-        if (CHECK) {
-#pragma unroll
-            for (int q = 0; q < RC; ++q) fold4f(f, c, r0 + q, dst, v[q], src);
-        }
+        if (CHECK) fold_copy(f, *c.in, c.R, t, r0, v, RC);
     }
 }
 
@@ -462,15 +471,7 @@ __device__ __forceinline__ void fast_multi(const Fast4& c, uint32_t blk, int r0,
             pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
         }
         sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, val);
-        if (CHECK) {
-#pragma unroll
-            for (int q = 0; q < RC; ++q) {
-                if (val[q] >= 0 && r0 + q <= c.R) {
-                    const uint32_t o = V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
-                    fold4f(f, c, r0 + q, dst, val[q], lds_u32(ca + 4u * o) & 1023u);
-                }
-            }
-        }
+        if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
     }
 }
 
@@ -504,15 +505,7 @@ __device__ __forceinline__ void fast_big(const Fast4& c, uint32_t u, int r0, int
             pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
         }
         sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, val);
-        if (CHECK) {
-#pragma unroll
-            for (int q = 0; q < RC; ++q) {
-                if (val[q] >= 0 && r0 + q <= c.R) {
-                    const uint32_t o = V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
-                    fold4f(f, c, r0 + q, dst, val[q], lds_u32(ca + 4u * o) & 1023u);
-                }
-            }
-        }
+        if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
     }
 }
 
@@ -554,7 +547,7 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
     const uint32_t tile_bytes = (uint32_t)(RL + 2) << (SLOG + 2);
     uint8_t* const slots = smem4;
     uint8_t* const tiles = slots + (size_t)a.nslot * a.slot_bytes;
-    uint64_t* const full = reinterpret_cast<uint64_t*>(tiles + 2 * (size_t)tile_bytes);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(tiles + (size_t)tile_bytes);
     uint64_t* const empty = full + a.nslot;
     uint64_t* const failw = empty + a.nslot;               // set once a barrier of the problem has timed out
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -567,10 +560,9 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
         *failw = 0ull;
     }
     if (cta == 0) {
-        // two dead padding layers below layer 0 of both tiles; level 0 (one vertex): every layer starts at 0 (:535)
+        // two dead padding layers below layer 0 of the tile; level 0 (one vertex, slot 0): every layer starts at 0 (:535)
         int32_t* const t0 = reinterpret_cast<int32_t*>(tiles);
-        int32_t* const t1 = reinterpret_cast<int32_t*>(tiles + tile_bytes);
-        for (int x = tid; x < (2 << SLOG); x += blockDim.x) { t0[x] = V4_DEAD; t1[x] = V4_DEAD; }
+        for (int x = tid; x < (2 << SLOG); x += blockDim.x) t0[x] = V4_DEAD;
         for (int r = tid; r < RL; r += blockDim.x) t0[((r + 2) << SLOG)] = r <= a.R ? 0 : V4_DEAD;
     }
     __syncthreads();
@@ -620,7 +612,7 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
         if (profiling) tk1 = clock64();
         const uint4 d = lds_v4(sb32);                       // directory entry
         const uint32_t flags = d.w;
-        const int l = cta == 0 ? i : __ldg(a.wide_list + i);
+        const int l = lds_s32(sb32 + 16u);                  // (the timed directory skips the transitions with nothing to do)
         if (a.grid > 1 && (flags & PF_WAIT) && !failed) {
             if (tid == 0 && !wait_counter4(a.counter, d.z, a.timeout_ns, l)) sts_s32(fail32, 1);
             bar_named(1, CT);
@@ -630,15 +622,17 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
         constexpr uint32_t FAST = PF_COMPACT | PF_STAGED;
         if (!failed) {
             if ((flags & FAST) == FAST) {
-                const uint4 h0 = lds_v4(sb32 + 16u), h1 = lds_v4(sb32 + 32u), h2 = lds_v4(sb32 + 48u), h3 = lds_v4(sb32 + 64u);
+                const uint4 h0 = lds_v4(sb32 + 32u), h1 = lds_v4(sb32 + 48u), h2 = lds_v4(sb32 + 64u), h3 = lds_v4(sb32 + 80u);
                 Fast4 c;
                 const uint32_t pb32 = sb32 + (uint32_t)sizeof(ProgDir);
                 c.copy32 = pb32 + (uint32_t)sizeof(ProgHdr); c.cell32 = pb32 + h3.x; c.cand32 = pb32 + h3.y; c.big32 = pb32 + h3.z; c.dead32 = pb32 + h3.w;
                 c.n_copy = h0.y; c.n_multi = h0.z; c.n_big = h1.x; c.n_dead = h1.y;
-                const uint32_t odd = (uint32_t)l & 1u;
-                c.src32 = tiles32 + odd * tile_bytes; c.dst32 = tiles32 + (odd ^ 1u) * tile_bytes;
+                c.src32 = tiles32; c.dst32 = tiles32;
                 c.pl = a.pred + (((unsigned long long)h2.y << 32) | h2.x);
-                c.k = h0.x & 0xFFFFu; c.kk2 = (h0.x >> 16) * (h0.x >> 16); c.R = a.R;
+                c.R = a.R;
+                ProgLevelIn in;
+                if (CHECK) in = level_in(*a.chk, l);
+                c.in = &in;
                 const uint32_t nch = (uint32_t)a.nchunk;
                 const uint32_t e0 = c.n_big * nch, e1 = e0 + ((c.n_multi + 31u) >> 5) * nch, e2 = e1 + ((c.n_copy + 31u) >> 5) * nch,
                                e3 = e2 + ((c.n_dead + 31u) >> 5) * nch;
@@ -653,7 +647,7 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                     else fast_dead<SLOG, RC>(c, blk, r0, lane);
                 }
             } else {
-                const ulonglong2 fs = run_generic<SLOG, RC, CHECK>(a, slots + (size_t)slot * a.slot_bytes, tiles32, tile_bytes, l, cta, warp, lane);
+                const ulonglong2 fs = run_generic<SLOG, RC, CHECK>(a, slots + (size_t)slot * a.slot_bytes, tiles32, l, cta, warp, lane);
                 f.sum = fs.x; f.live = fs.y;
             }
         }
@@ -667,6 +661,25 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
             pc_wait += tk1 - tk0; pc_work += tk2 - tk1; pc_bar += tk3 - tk2;
             const int cls = (flags & FAST) == FAST ? 0 : ((flags & PF_ALL_CTAS) ? 2 : 1);      // narrow loop / hand-over and other / HBM to HBM
             a.prof[4 + 2 * cls] += 1; a.prof[5 + 2 * cls] += (unsigned long long)(tk3 - tk0);
+        }
+        if (CHECK && !failed && cta == 0) {
+            // the passive pairs of level l+1: untouched memory, the same cells as in level l (dp_prog.h); every CTA-0
+            // thread folds its share (HBM-resident cells of this level were completed before this transition's wait)
+            const ProgLevelIn in = level_in(*a.chk, l);
+            if (!in.relocate) {
+                const uint64_t npp = (uint64_t)in.cls.np * in.cls.np;
+                const bool dsm = (flags & PF_DST_SMEM) != 0;
+                for (uint64_t x = (uint64_t)tid; x < npp; x += (uint64_t)CT) {
+                    uint32_t i2, j2, i, wi, j, wj;
+                    passive_pair(in, x, i2, j2);
+                    in_edge_at(in, i2, 0, i, wi); in_edge_at(in, j2, 0, j, wj);
+                    const uint32_t dc = dst_cell(in, i2, j2);
+                    for (int r = 0; r <= a.R; ++r) {
+                        const int32_t v = dsm ? lds_s32(tiles32 + (((uint32_t)(r + 2) << SLOG) + dc) * 4u) : __ldcg(a.gtile + a.gpad + (long long)r * a.hkk + dc);
+                        fold_pos(f, a.R, in.k2, r, i2, j2, v, i, j);
+                    }
+                }
+            }
         }
         if (CHECK) {
             for (int o = 16; o > 0; o >>= 1) {
@@ -683,16 +696,14 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
     if (profiling) { a.prof[0] = pc_wait; a.prof[1] = pc_work; a.prof[2] = pc_bar; a.prof[3] = (unsigned long long)n_my; }
     // the sink: layers of cell (0,0) of the last level (the traceback starts from layer R, :774-776)
     if (cta == 0) {
-        const int last = a.n_trans;                             // level index L-1
-        if (a.last_k > a.kn) {                                  // last level in HBM (DipGenie's sink level is one vertex: never there)
-            if (a.grid > 1 && tid == 0 && !failed) wait_counter4(a.counter, a.final_target, a.timeout_ns, last);
+        if (!a.last_smem) {                                     // last level in HBM (DipGenie's sink level is one vertex: never there)
+            if (a.grid > 1 && tid == 0 && !failed) wait_counter4(a.counter, a.final_target, a.timeout_ns, a.n_trans);
             bar_named(1, CT);
         }
-        const long long kk = (long long)a.last_k * a.last_k;
         for (int r = tid; r <= a.R; r += CT) {
             int32_t v;
-            if (a.last_k <= a.kn) v = lds_s32(tiles32 + ((uint32_t)last & 1u) * tile_bytes + ((uint32_t)(r + 2) << (SLOG + 2)));
-            else v = __ldcg(((last & 1) ? a.gtile1 : a.gtile0) + a.gpad + (long long)r * kk);
+            if (a.last_smem) v = lds_s32(tiles32 + (((uint32_t)(r + 2) << SLOG) + a.sink_cell) * 4u);
+            else v = __ldcg(a.gtile + a.gpad + (long long)r * a.hkk + a.sink_cell);
             a.sink[r] = v;
         }
     }
@@ -718,7 +729,7 @@ __global__ void __launch_bounds__(544, 1) dip_sweep4_many_kernel(const Sweep4Arg
 }
 
 constexpr size_t sweep4_smem_bytes(int slog, int RL, int slot_bytes, int nslot) {
-    return (size_t)nslot * (size_t)slot_bytes + 2 * ((size_t)(RL + 2) << (slog + 2)) + (2 * (size_t)nslot + 1) * 8;
+    return (size_t)nslot * (size_t)slot_bytes + ((size_t)(RL + 2) << (slog + 2)) + (2 * (size_t)nslot + 1) * 8;
 }
 
 }  // namespace dg

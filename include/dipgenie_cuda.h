@@ -98,6 +98,8 @@ typedef struct {
     uint64_t code_bytes;                /* HBM held by the predecessor codes */
     int32_t engine;                     /* 4 = level programs (dp_prog.h), 3 = task streams */
     float build_ms;                     /* prog_fill_kernel inside dg_dip_create (engine 4) */
+    uint64_t cells_written;             /* engine 4: destination cells the sweep writes (in-place layers skip the passive pairs) */
+    int32_t n_relocate, pad_;           /* engine 4: transitions that move the level between the shared-memory and the HBM tile */
 } dg_dip_stats_t;
 int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out);
 /* out24: for each of {shared-memory layers, HBM/L2 layers} six counters {tasks, slot-wait, grid-wait,

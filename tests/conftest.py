@@ -128,7 +128,7 @@ class DpEmu4:
         shp = np.zeros(8, np.int32)
         if shape:
             shp[: len(shape)] = list(shape)
-        counts = np.zeros(10, np.int64)
+        counts = np.zeros(16, np.int64)
         val, sh, n1, n2 = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         p1 = np.zeros(2 * (R + 2), np.int32)
         p2 = np.zeros(2 * (R + 2), np.int32)
@@ -147,7 +147,8 @@ class DpEmu4:
                     p2_edges=p2[: 2 * n2.value].reshape(-1, 2).copy(), checksum=cs, live=lv,
                     modes=dict(smem=int(counts[0]), all_ctas=int(counts[1]), compact=int(counts[2]), staged=int(counts[3]),
                                big_cells=int(counts[4]), prog_bytes=int(counts[5]), code_elems=int(counts[6]),
-                               max_cand=int(counts[7])))
+                               max_cand=int(counts[7]), relocations=int(counts[8]), skipped=int(counts[9]),
+                               cells_written=int(counts[10]), cells_total=int(counts[11])))
 
 
     def build_program(self, g, R, shape=None) -> np.ndarray:

@@ -1,10 +1,12 @@
 // tests/emu/dp_emu4.cpp — TEST-ONLY CPU emulation of the level-program sweep (engine v4).
 // Runs the exact host planning (dp_prep.cpp + dp_plan4.cpp), builds every transition's program with the very
 // descriptor functions the device builder runs (dp_prog.h), then interprets the programs the way
-// dip_sweep4_kernel does — same tile layouts (shared-memory tiles of stride 1 << slog with two dead padding layers,
-// HBM tiles of stride k^2 behind gpad dead cells), same packed keys, same predecessor-code slots — with the thread
-// grid replaced by serial loops.  `-m "not gpu"` tests check value, s_het, edge lists and the per-level checksums of
-// every live cell against the oracle without a GPU.  Never part of the product library.
+// dip_sweep4_kernel does — same in-place tiles (one shared-memory tile of layer stride 1 << slog, one HBM tile of layer
+// stride hstride^2, two dead padding layers below layer 0), same slots, same packed keys, same predecessor-code
+// slots, the timed directory's skipping of idle transitions — with the thread grid replaced by serial loops.  It also
+// checks what the design relies on: no cell that a transition reads is written by it, every written cell exactly once.
+// `-m "not gpu"` tests check value, s_het, edge lists and the per-level checksums of every live cell against the
+// oracle without a GPU.  Never part of the product library.
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
@@ -21,19 +23,34 @@ using namespace dg;
 namespace {
 
 struct Tiles {
-    int slog; int64_t gpad; int RL;
-    std::vector<int32_t> s[2], g[2];
-    // address of (layer r, cell idx) of level parity `par`, placement smem / HBM with layer stride kk
-    int32_t& at(bool smem, int par, int64_t kk, int r, uint32_t idx) {
-        if (smem) return s[par][(size_t)(((int64_t)(r + 2) << slog) + idx)];
-        return g[par][(size_t)(gpad + (int64_t)r * kk + idx)];
+    int slog; int64_t gpad, hkk;
+    std::vector<int32_t> s, g;
+    int32_t& at(bool smem, int r, uint32_t idx) {
+        if (smem) return s[(size_t)(((int64_t)(r + 2) << slog) + idx)];
+        return g[(size_t)(gpad + (int64_t)r * hkk + idx)];
     }
 };
+
+bool plan(const DipGraphView& gv, const int32_t* shape, DipPlan& p, Plan4& q) {
+    if (!build_dip_plan(gv, p)) return false;
+    Sweep4Shape sh;
+    int rc = 10;
+    if (shape) {
+        if (shape[0] > 0) sh.slog = shape[0];
+        if (shape[1] > 0) sh.kn = shape[1];
+        if (shape[2] > 0) sh.slot_bytes = shape[2];
+        if (shape[3] > 0) sh.grid = shape[3];
+        if (shape[4] > 0) rc = shape[4];
+    }
+    std::string why;
+    return plan4_build(p, gv, sh, rc, q, why);
+}
 
 }  // namespace
 
 // shape: [slog, kn, slot_bytes, grid, rc] (0 = default).  counts: [transitions in shared memory, transitions over all
-// CTAs, compact programs, staged programs, big cells, program bytes, code elements, max candidates]
+// CTAs, compact programs, staged programs, big cells, program bytes, code elements, max candidates, relocations,
+// skipped transitions, cells written, cells of all levels]
 extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
                                const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off,
                                const int32_t* col_val, const uint8_t* colour_is_hom, int32_t n_colours, int32_t R,
@@ -44,64 +61,80 @@ extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const
     gv.n_levels = n_levels; gv.level_off = level_off; gv.adj_off = adj_off; gv.adj_dst = adj_dst; gv.adj_w = adj_w;
     gv.col_off = col_off; gv.col_val = col_val; gv.colour_is_hom = colour_is_hom; gv.n_colours = n_colours; gv.R = R;
     DipPlan p;
-    if (!build_dip_plan(gv, p)) return -1;
-    Sweep4Shape sh;
-    int rc = 10;
-    if (shape) {
-        if (shape[0] > 0) sh.slog = shape[0];
-        if (shape[1] > 0) sh.kn = shape[1];
-        if (shape[2] > 0) sh.slot_bytes = shape[2];
-        if (shape[3] > 0) sh.grid = shape[3];
-        if (shape[4] > 0) rc = shape[4];
-    }
     Plan4 q;
-    std::string why;
-    if (!plan4_build(p, sh, rc, q, why)) return -2;
+    {
+        DipPlan probe;
+        if (!build_dip_plan(gv, probe)) return -1;
+    }
+    if (!plan(gv, shape, p, q)) return -2;
+    const Sweep4Shape& sh = q.shape;
     const int L = p.L, RL = q.RL;
 
     Tiles T;
-    T.slog = sh.slog; T.gpad = q.gpad; T.RL = RL;
-    for (int x = 0; x < 2; ++x) {
-        T.s[x].assign((size_t)(RL + 2) << sh.slog, 0x5A5A5A5A);                 // (garbage: nothing may rely on zeros)
-        std::fill(T.s[x].begin(), T.s[x].begin() + ((size_t)2 << sh.slog), V4_DEAD);
-        T.g[x].assign((size_t)std::max<int64_t>(q.gtile_cells, 1), 0x5A5A5A5A);
-        std::fill(T.g[x].begin(), T.g[x].begin() + (size_t)q.gpad, V4_DEAD);
-    }
-    // level 0: one vertex, every layer starts at 0 (approximator.cpp:535); it always lives in shared memory
-    for (int r = 0; r < RL; ++r) T.at(true, 0, 1, r, 0) = r <= R ? 0 : V4_DEAD;
+    T.slog = sh.slog; T.gpad = q.gpad; T.hkk = (int64_t)q.hstride * q.hstride;
+    T.s.assign((size_t)(RL + 2) << sh.slog, 0x5A5A5A5A);                 // (garbage: nothing may rely on zeros)
+    std::fill(T.s.begin(), T.s.begin() + ((size_t)2 << sh.slog), V4_DEAD);
+    T.g.assign((size_t)std::max<int64_t>(q.gtile_cells, 1), 0x5A5A5A5A);
+    std::fill(T.g.begin(), T.g.begin() + (size_t)q.gpad, V4_DEAD);
+    // level 0: one vertex in slot 0 of the shared-memory tile, every layer starts at 0 (approximator.cpp:535)
+    for (int r = 0; r < RL; ++r) T.at(true, r, 0) = r <= R ? 0 : V4_DEAD;
 
     std::vector<uint16_t> pred((size_t)std::max<int64_t>(q.pred_elems, 1), 0xABCD);
     std::vector<uint64_t> sum((size_t)L, FOLD_BASIS), live((size_t)L, 0);
     std::vector<uint8_t> prog;
     int64_t n_compact = 0, n_staged = 0, n_big = 0, n_all = 0;
-    uint32_t cum = 0;
+    // the two directories: same transitions in level order, the timed one without the idle ones
+    std::vector<int> timed_at((size_t)L, -1);
+    for (size_t x = 0; x < q.timed.dir.size(); ++x) timed_at[(size_t)q.timed.dir[x].level] = (int)x;
+    if ((int)q.full.dir.size() != L - 1) return -9;
+    for (const Plan4Dir* D : {&q.full, &q.timed}) {                     // barrier schedules
+        uint32_t cum = 0;
+        size_t nw = 0;
+        for (size_t x = 0; x < D->dir.size(); ++x) {
+            const ProgDir& d = D->dir[x];
+            const bool ss = d.flags & PF_SRC_SMEM, ds = d.flags & PF_DST_SMEM;
+            if ((d.flags & PF_WAIT) && d.wait_target != cum) return -12;
+            if (d.flags & PF_ARRIVE) cum += (d.flags & PF_ALL_CTAS) ? (uint32_t)sh.grid : 1u;
+            if (((d.flags & PF_ALL_CTAS) != 0) != (!ss && !ds)) return -13;
+            if (!ss && ds && !(d.flags & PF_WAIT)) return -13;
+            if (ss && !ds && !(d.flags & PF_ARRIVE)) return -13;
+            if (d.flags & PF_ALL_CTAS) { if (nw >= D->wide_list.size() || D->wide_list[nw] != (int32_t)x) return -13; ++nw; }
+        }
+        if (nw != D->wide_list.size() || cum != D->final_target) return -13;
+    }
+    std::vector<uint8_t> written, readset;
     for (int l = 0; l + 1 < L; ++l) {
-        const ProgDir& d = q.dir[l];
+        const ProgDir& d = q.full.dir[l];
+        if (d.level != l) return -9;
         const size_t bytes = (size_t)(q.prog_off[(size_t)l + 1] - q.prog_off[l]);
         prog.assign(bytes, 0);
         prog_fill_level_host(p, q, l, prog.data());
         ProgHdr h;
         memcpy(&h, prog.data(), sizeof h);
-        const bool compact = d.flags & PF_COMPACT, ss = d.flags & PF_SRC_SMEM, ds = d.flags & PF_DST_SMEM;
-        n_compact += compact; n_staged += (d.flags & PF_STAGED) != 0; n_big += h.n_big; n_all += (d.flags & PF_ALL_CTAS) != 0;
-        if ((d.flags & PF_STAGED) ? (d.stage_bytes != bytes || bytes + 16 > (size_t)sh.slot_bytes) : d.stage_bytes != sizeof(ProgHdr)) return -10;
+        const bool compact = d.flags & PF_COMPACT, ss = d.flags & PF_SRC_SMEM, ds = d.flags & PF_DST_SMEM, reloc = d.flags & PF_RELOCATE;
+        if ((d.flags & PF_STAGED) ? (d.stage_bytes != bytes || bytes + sizeof(ProgDir) > (size_t)sh.slot_bytes) : d.stage_bytes != sizeof(ProgHdr)) return -10;
         if ((uint64_t)d.off16 * 16 != q.prog_off[l]) return -11;
-        // barrier schedule: a waiting level sees every arrival issued so far, no more
-        if ((d.flags & PF_WAIT) && d.wait_target != cum) return -12;
-        if (d.flags & PF_ARRIVE) cum += (d.flags & PF_ALL_CTAS) ? (uint32_t)sh.grid : 1u;
-        if (((d.flags & PF_ALL_CTAS) != 0) != (!ss && !ds)) return -13;
+        if (reloc != (ss != ds)) return -16;
+        if (ss != (q.lvl_dom[l] == 0) || ds != (q.lvl_dom[l + 1] == 0)) return -16;
         const ProgLayout lay = prog_layout(compact, h.n_copy, h.n_multi, h.n_cand, h.n_big, h.n_dead);
-        if (lay.end != bytes) return -14;
+        if (lay.end != bytes || h.off_cell != lay.cell || h.off_cand != lay.cand || h.off_big != lay.big || h.off_dead != lay.dead) return -14;
         const int k = h.k, k2 = h.k2;
-        const int64_t kk = (int64_t)k * k, kk2 = (int64_t)k2 * k2;
-        if (ss && kk > ((int64_t)1 << sh.slog)) return -15;
-        if (ds && kk2 > ((int64_t)1 << sh.slog)) return -15;
-        const int sp = l & 1, dp = (l + 1) & 1;
-        std::vector<uint8_t> written((size_t)kk2, 0);
-        auto fold = [&](int r, uint32_t dst, int32_t val, uint32_t src) {
+        const int64_t kk2 = (int64_t)k2 * k2;
+        const ProgLevelIn in = plan4_level_in(p, q, l);
+        const int64_t cap_s = ss ? (int64_t)sh.kn * sh.kn : T.hkk, cap_d = ds ? (int64_t)sh.kn * sh.kn : T.hkk;
+        const bool idle = timed_at[l] < 0;
+        if (idle && (reloc || h.n_copy + h.n_multi + h.n_dead != 0)) return -17;
+        if (!idle) {
+            const ProgDir& dt = q.timed.dir[(size_t)timed_at[l]];
+            if (dt.off16 != d.off16 || dt.stage_bytes != d.stage_bytes || ((dt.flags ^ d.flags) & ~(uint32_t)(PF_WAIT | PF_ARRIVE)) != 0) return -17;
+            n_compact += compact; n_staged += (d.flags & PF_STAGED) != 0; n_big += h.n_big; n_all += (d.flags & PF_ALL_CTAS) != 0;
+        }
+        written.assign((size_t)cap_d, 0);
+        readset.assign((size_t)cap_s, 0);
+        auto fold = [&](int r, uint32_t i2, uint32_t j2, int32_t val, uint32_t i, uint32_t j) {
             if (r > R || val < 0) return;
             ++live[(size_t)l + 1];
-            sum[(size_t)l + 1] += cell_fold((uint64_t)r * kk2 + dst, val >> V4_SHIFT, (int)(src / k), (int)(src % k));
+            sum[(size_t)l + 1] += cell_fold((uint64_t)r * kk2 + (uint64_t)i2 * k2 + j2, val >> V4_SHIFT, (int)i, (int)j);
         };
         const uint32_t* wcopy = reinterpret_cast<const uint32_t*>(prog.data() + lay.copy);
         const uint32_t* wcell = reinterpret_cast<const uint32_t*>(prog.data() + lay.cell);
@@ -112,62 +145,92 @@ extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const
             CopyDesc c;
             if (compact) c = unpack_copy_c(wcopy[t]);
             else { c.src = wcopy[4 * t] & 0x3FFFFFFFu; c.w = wcopy[4 * t] >> 30; c.dst = wcopy[4 * t + 1]; c.delta = wcopy[4 * t + 2]; }
-            if (c.dst >= kk2 || c.src >= kk || written[c.dst]) return -20;
-            written[c.dst] = 1;
-            for (int r = 0; r < RL; ++r) {
-                const int32_t v = T.at(ss, sp, kk, r - (int)c.w, c.src) + (int32_t)(c.delta << V4_SHIFT);
-                T.at(ds, dp, kk2, r, c.dst) = v;
-                fold(r, c.dst, v, c.src);
-            }
+            if (c.dst >= cap_d || c.src >= cap_s || written[c.dst]) return -20;
+            written[c.dst] = 1; readset[c.src] = 1;
+            uint32_t i2, j2, i, wi, j, wj;
+            copy_pair(in, t, i2, j2);
+            in_edge_at(in, i2, 0, i, wi); in_edge_at(in, j2, 0, j, wj);
+            std::vector<int32_t> vals((size_t)RL);
+            for (int r = 0; r < RL; ++r) vals[r] = T.at(ss, r - (int)c.w, c.src) + (int32_t)(c.delta << V4_SHIFT);
+            for (int r = 0; r < RL; ++r) { T.at(ds, r, c.dst) = vals[r]; fold(r, i2, j2, vals[r], i, j); }
         }
         uint32_t nb_seen = 0;
+        std::vector<int32_t> keys((size_t)RL);
         for (uint32_t t = 0; t < h.n_multi; ++t) {
             CellDesc c;
             if (compact) { c.dst = wcell[2 * t] & 1023u; c.n = wcell[2 * t] >> 16; c.cand_off = wcell[2 * t + 1]; }
             else { c.dst = wcell[4 * t]; c.n = wcell[4 * t + 1]; c.cand_off = wcell[4 * t + 2]; }
-            if (c.dst >= kk2 || written[c.dst] || c.n < 2 || c.n > PROG_MAX_CAND || (uint64_t)c.cand_off + c.n > h.n_cand) return -21;
+            if (c.dst >= cap_d || written[c.dst] || c.n < 2 || c.n > PROG_MAX_CAND || (uint64_t)c.cand_off + c.n > h.n_cand) return -21;
             written[c.dst] = 1;
             if (c.n >= PROG_BIG_MIN) { if (nb_seen >= h.n_big || wbig[nb_seen] != t) return -22; ++nb_seen; }
             else if (c.n > h.max_n) return -23;
+            const MultiCell mc = multi_cell(in, t);
             for (int r = 0; r < RL; ++r) {
                 int32_t key = V4_DEAD;
                 for (uint32_t o = 0; o < c.n; ++o) {
                     CandDesc e;
                     if (compact) e = unpack_cand_c(wcand[c.cand_off + o]);
                     else { e.src = wcand[2 * (c.cand_off + o)] & 0x3FFFFFFFu; e.w = wcand[2 * (c.cand_off + o)] >> 30; e.delta = wcand[2 * (c.cand_off + o) + 1]; }
-                    if (e.src >= kk) return -24;
-                    const int32_t cand = T.at(ss, sp, kk, r - (int)e.w, e.src) + (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - o));
+                    if (e.src >= cap_s) return -24;
+                    readset[e.src] = 1;
+                    const int32_t cand = T.at(ss, r - (int)e.w, e.src) + (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - o));
                     key = std::max(key, cand);
                 }
-                const int32_t val = (int32_t)((uint32_t)key & ~V4_ORD_MASK);
-                T.at(ds, dp, kk2, r, c.dst) = val;
+                keys[r] = key;
+            }
+            for (int r = 0; r < RL; ++r) {
+                const int32_t key = keys[r], val = (int32_t)((uint32_t)key & ~V4_ORD_MASK);
+                T.at(ds, r, c.dst) = val;
                 pred[(size_t)(h.pred_off + (uint64_t)r * h.n_multi + t)] = (uint16_t)key;
                 if (val >= 0 && r <= R) {
                     const uint32_t o = V4_ORD_MASK - ((uint32_t)key & V4_ORD_MASK);
-                    const uint32_t src = compact ? unpack_cand_c(wcand[c.cand_off + o]).src : (wcand[2 * (c.cand_off + o)] & 0x3FFFFFFFu);
-                    fold(r, c.dst, val, src);
+                    const uint32_t e1 = o / mc.d2, e2 = o - e1 * mc.d2;
+                    uint32_t i, wi, j, wj;
+                    in_edge_at(in, mc.i2, e1, i, wi); in_edge_at(in, mc.j2, e2, j, wj);
+                    fold(r, mc.i2, mc.j2, val, i, j);
                 }
             }
         }
         if (nb_seen != h.n_big) return -25;
         for (uint32_t x = 0; x < h.n_dead; ++x) {
             const uint32_t dst = wdead[x];
-            if (dst >= kk2 || written[dst]) return -26;
+            if (dst >= cap_d || written[dst]) return -26;
             written[dst] = 1;
-            for (int r = 0; r < RL; ++r) T.at(ds, dp, kk2, r, dst) = V4_DEAD;
+            for (int r = 0; r < RL; ++r) T.at(ds, r, dst) = V4_DEAD;
         }
-        for (uint8_t b : written) if (!b) return -27;
+        // passive pairs: the same memory in both levels, untouched
+        if ((uint64_t)h.n_copy + h.n_multi + h.n_dead + (uint64_t)h.n_passive * h.n_passive != (uint64_t)kk2) return -27;
+        for (uint64_t x = 0; x < (uint64_t)h.n_passive * h.n_passive; ++x) {
+            uint32_t i2, j2, i, wi, j, wj;
+            passive_pair(in, x, i2, j2);
+            in_edge_at(in, i2, 0, i, wi); in_edge_at(in, j2, 0, j, wj);
+            const uint32_t dc = dst_cell(in, i2, j2);
+            if (dc != src_cell(in, i, j) || wi + wj != 0 || written[dc]) return -28;
+            written[dc] = 1;
+            for (int r = 0; r < RL; ++r) fold(r, i2, j2, T.at(ds, r, dc), i, j);
+        }
+        if (ss == ds)                                                  // in place: nothing that was read may have been written
+            for (size_t x = 0; x < readset.size(); ++x) if (readset[x] && written[x] && !(x < (size_t)cap_d && false)) {
+                // (a passive cell is "written" in the bookkeeping above but not in memory: reads of it are fine)
+                bool passive_cell = false;
+                for (uint64_t y = 0; y < (uint64_t)h.n_passive * h.n_passive && !passive_cell; ++y) {
+                    uint32_t i2, j2; passive_pair(in, y, i2, j2);
+                    passive_cell = dst_cell(in, i2, j2) == x;
+                }
+                if (!passive_cell) return -29;
+            }
+        (void)k;
     }
     // sink cell (r = R, 0, 0) of the last level and the walk back through the codes
-    const int32_t ks = p.level_off[L] - p.level_off[L - 1];
-    const bool last_smem = ks <= sh.kn;
-    const int32_t raw = T.at(last_smem, (L - 1) & 1, (int64_t)ks * ks, R, 0);
+    const bool last_smem = q.lvl_dom[L - 1] == 0;
+    const int32_t raw = T.at(last_smem, R, q.sink_cell);
     *sink_value = raw < 0 ? NEG_INF : (raw >> V4_SHIFT);
     *sink_s_het = 0; *n_p1 = 0; *n_p2 = 0;
     if (level_checksum) for (int l = 0; l < L; ++l) { level_checksum[l] = sum[l]; level_live[l] = live[l]; }
     if (counts) {
         counts[0] = q.n_smem_trans; counts[1] = n_all; counts[2] = n_compact; counts[3] = n_staged; counts[4] = n_big;
-        counts[5] = (int64_t)q.prog_bytes; counts[6] = q.pred_elems; counts[7] = q.max_cand;
+        counts[5] = (int64_t)q.prog_bytes; counts[6] = q.pred_elems; counts[7] = q.max_cand; counts[8] = q.n_relocate; counts[9] = q.n_skipped;
+        counts[10] = (int64_t)q.cells_written; counts[11] = (int64_t)q.cells_total;
     }
     if (raw < 0) return 0;
     TraceView v;
@@ -197,19 +260,12 @@ extern "C" int64_t emu4_build_program(int32_t n_levels, const int32_t* level_off
     gv.n_levels = n_levels; gv.level_off = level_off; gv.adj_off = adj_off; gv.adj_dst = adj_dst; gv.adj_w = adj_w;
     gv.col_off = col_off; gv.col_val = col_val; gv.colour_is_hom = colour_is_hom; gv.n_colours = n_colours; gv.R = R;
     DipPlan p;
-    if (!build_dip_plan(gv, p)) return -1;
-    Sweep4Shape sh;
-    int rc = 10;
-    if (shape) {
-        if (shape[0] > 0) sh.slog = shape[0];
-        if (shape[1] > 0) sh.kn = shape[1];
-        if (shape[2] > 0) sh.slot_bytes = shape[2];
-        if (shape[3] > 0) sh.grid = shape[3];
-        if (shape[4] > 0) rc = shape[4];
-    }
     Plan4 q;
-    std::string why;
-    if (!plan4_build(p, sh, rc, q, why)) return -2;
+    {
+        DipPlan probe;
+        if (!build_dip_plan(gv, probe)) return -1;
+    }
+    if (!plan(gv, shape, p, q)) return -2;
     if (out && cap >= (int64_t)q.prog_bytes) {
 #pragma omp parallel for schedule(dynamic, 64)
         for (int l = 0; l < p.L - 1; ++l) prog_fill_level_host(p, q, l, out + q.prog_off[l]);
