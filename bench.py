@@ -4,14 +4,15 @@
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA, one process per GPU)
   python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU solver on the host cores
 
-A step = one full pass of the DP (pair scores, sweep, traceback) over one batch of samples: S samples per GPU
-(default 32, 4 CTAs each), every sample the levelized graph of BASELINE config 2's shape (MHC_4 panel, -p2 -R18), resident in
-HBM, each running as its own persistent sweep on its own stream and CTA group.  The DP of one H=5 sample is a
-chain of 120 362 dependent levels that keeps about one SM busy, so samples side by side is how the path fills a
-B200 (the reference's own batch use: data/run_DipGenie_batch.sh).  With N ranks every rank owns its own S
-samples (no collective) -> weak scaling; value = cell-updates of all samples / max-over-ranks device
-time.  e2e = the same through dg_dp_diploid_batch with host buffers (22 samples per GPU).
-Prints ONE JSON line on rank 0.
+A step = one full pass of the DP (sweep + traceback) over one batch of samples: S samples per GPU (default 256: two
+sweep CTAs per SM, one per sample), every sample a levelized graph of BASELINE config 2's shape (MHC_4 panel, -p2 -R18;
+the samples differ in their read-derived colours, see load_samples), resident in HBM (level programs + predecessor
+codes, about 0.53 GB each), all swept by ONE fused launch and traced back by one launch set.  The DP of one H=5 sample
+is a chain of ~10^5 dependent level transitions that keeps one SM partly busy, so samples side by side is how the path
+fills a B200 (the reference's own batch use: data/run_DipGenie_batch.sh).  With N ranks every rank owns its own S
+samples (no collective) -> weak scaling; value = cell-updates of all samples / max-over-ranks device time.
+e2e = the same through dg_dp_diploid_batch with host buffers (22 samples per GPU: planning, H2D, program build, sweep,
+traceback, D2H in the timed region).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -41,10 +42,18 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 REF_PLAIN = os.path.join(ROOT, "oracle", "_ref", "ref_driver_plain")
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum PER SAMPLE of the sweep, from the `ncu --set full` capture of an 8-sample
-# dip_sweep_many_kernel launch (profiles/r01c_sweep_many_ncu.md: 0.740 GB + 6.981 GB for 8 samples; the single-sample
-# dip_sweep_kernel capture of profiles/r01b_sweep_v3.md gave 919.6 MB); None where no capture exists.
-NCU_TRAFFIC = {("mhc4_chm13", 18): 965196000}
+# dram__bytes_read.sum + dram__bytes_write.sum of the fused sweep launch PER SAMPLE, with the ncu capture it comes from
+# (a DRAM counter cannot be read from inside the timed run; the capture is of the same command and configuration).
+# None where no capture exists for the configuration.
+NCU_TRAFFIC = {
+    # (workload, R, samples per GPU): (bytes per sample, capture)
+}
+try:
+    with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as _f:
+        for _e in json.load(_f):
+            NCU_TRAFFIC[(_e["workload"], _e["R"], _e["samples_per_gpu"])] = (_e["dram_bytes_per_sample"], _e["capture"])
+except OSError:
+    pass
 
 
 def load_workload(name: str):
@@ -60,6 +69,30 @@ def load_workload(name: str):
         g = synth.lane_panel_graph(90, n_lanes=H, n_blocks=nb, rec_per_block=max(2, H // 16), p_colour=0.08, n_colours=1 << 15)
         return g, f"synthetic lane-panel model, {H} haplotype lanes, {nb} blocks (seed 90)"
     raise SystemExit(f"unknown workload {name}")
+
+
+def load_samples(name: str, n: int, seed: int = 2):
+    """n samples of the workload's shape.  Sample 0 is the fixture itself; the others keep its panel graph (every sample of
+    the study is genotyped against a panel of this shape) and get their own read-derived part: the colour sets are dealt to
+    the coloured vertices in a seeded permutation and the hom/het flags are redrawn at the same ratio — the levels differ in
+    which cells carry scores, so values, predecessor codes and paths differ from sample to sample."""
+    from dipgenie_b200.cuda_api import LevelGraph
+    g, desc = load_workload(name)
+    out = [g]
+    ncol = np.diff(g.col_off)
+    coloured = np.nonzero(ncol > 0)[0]
+    for i in range(1, n):
+        rng = np.random.default_rng(seed * 1000 + i)
+        perm = rng.permutation(len(coloured))
+        new_n = np.zeros_like(ncol)
+        new_n[coloured] = ncol[coloured[perm]]
+        off = np.concatenate([[0], np.cumsum(new_n)])
+        val = np.empty(int(off[-1]), np.int32)
+        for dst, src in zip(coloured, coloured[perm]):
+            val[off[dst]:off[dst + 1]] = g.col_val[g.col_off[src]:g.col_off[src + 1]]
+        hom = rng.permutation(g.colour_is_hom)
+        out.append(LevelGraph(g.level_off, g.adj_off, g.adj_dst, g.adj_w, off, val, hom))
+    return out, desc
 
 
 def graph_to_dgd(g, path):
@@ -192,8 +225,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="mhc4_chm13")
     ap.add_argument("--R", type=int, default=18)
-    ap.add_argument("--samples-per-gpu", type=int, default=144, help="samples resident together on one GPU in the timed step (about 1 GB of HBM each)")
-    ap.add_argument("--ctas-per-sample", type=int, default=1, help="sweep CTAs per resident sample (samples x CTAs <= SM count)")
+    ap.add_argument("--samples-per-gpu", type=int, default=256, help="samples resident together on one GPU in the timed step (about 0.53 GB of HBM each)")
+    ap.add_argument("--distinct", type=int, default=8, help="distinct samples among the resident ones and in the batch call (see load_samples)")
+    ap.add_argument("--ctas-per-sample", type=int, default=1, help="sweep CTAs per resident sample")
     ap.add_argument("--batch-ctas", type=int, default=0, help="CTAs per sample of the end-to-end batch call (0 = library default)")
     ap.add_argument("--batch", type=int, default=22, help="samples per GPU in the end-to-end batch call (22-sample study)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -220,12 +254,13 @@ def main():
 
     # one process per GPU: this rank's share of the host cores for the planning threads of the batch call
     os.environ.setdefault("DG_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))))
-    g, desc = load_workload(args.workload)
+    samples, desc = load_samples(args.workload, max(1, args.distinct), seed=2 + rank)
+    g = samples[0]
     ctx = Context(local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     # end-to-end through the host-buffer C-ABI batch call (planning, H2D, kernels, D2H inside the timed region)
-    graphs = [g] * max(1, args.batch)
+    graphs = [samples[i % len(samples)] for i in range(max(1, args.batch))]
     e2e_t, single_t = [], []
     for i in range(args.e2e_steps + 1):
         flush.fill_(1)
@@ -239,7 +274,10 @@ def main():
         if i > 0:
             e2e_t.append(dt)
             single_t.append(d1)
-        assert all(r["value"] == o1["value"] for r in res)
+        assert res[0]["value"] == o1["value"]
+        if i == 0:
+            batch_values = [r["value"] for r in res]
+        assert [r["value"] for r in res] == batch_values
     e2e_value = o1["value"]
     e2e_s, single_s = float(np.mean(e2e_t)), float(np.mean(single_t))
     print("bench: e2e batch calls (s): %s; single-sample calls (s): %s" % ([round(x, 3) for x in e2e_t], [round(x, 3) for x in single_t]), file=sys.stderr)
@@ -248,7 +286,7 @@ def main():
     ctx.release_cached_memory()      # the batch calls' device blocks go back: the resident group needs most of the HBM
     # device-resident throughput: S samples in HBM (about 1 GB each), swept together
     S = max(1, args.samples_per_gpu)
-    probs = [ctx.dip_create(g, args.R, slot=i, ctas=args.ctas_per_sample) for i in range(S)]
+    probs = [ctx.dip_create(samples[i % len(samples)], args.R, slot=i % 1024, ctas=args.ctas_per_sample) for i in range(S)]
 
     def barrier():
         if world > 1:
@@ -280,7 +318,8 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     st = sts[0]
     dev_ms = float(np.mean(group_ms))
-    assert all(o["value"] == e2e_value for o in outs)
+    assert outs[0]["value"] == e2e_value
+    assert all(o["value"] == batch_values[i % len(samples)] for i, o in enumerate(outs) if i % len(samples) < len(batch_values))
 
     tmax = torch.tensor([dev_ms, e2e_s * 1e3, single_s * 1e3, float(np.mean(sweep))], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -288,15 +327,18 @@ def main():
     dev_ms_max, e2e_ms_max, single_ms_max, sweep_ms_max = [float(x) for x in tmax.tolist()]
 
     if rank == 0:
-        U = st["cell_updates"]
         B = len(graphs)
         peak, peak_src = peaks()
         sweep_ms = float(np.mean(sweep))
         # dg_dip_run_many sweeps all S resident samples in ONE launch (dip_sweep_many_kernel) when it can: that launch's
         # algorithmic bytes are S samples' worth
-        fused = S >= 2 and sts[1]["launches"] == sts[0]["launches"] - 1
+        fused = S >= 2 and sts[1]["launches"] < sts[0]["launches"]
         per_launch = S if fused else 1
-        achieved = per_launch * st["algo_bytes"] / (sweep_ms * 1e-3) / 1e9
+        algo = float(np.mean([x["algo_bytes"] for x in sts]))
+        U = float(np.mean([x["cell_updates"] for x in sts]))
+        achieved = per_launch * algo / (sweep_ms * 1e-3) / 1e9
+        traffic = NCU_TRAFFIC.get((args.workload, args.R, S))
+        kname = ("dip_sweep4_many_kernel" if fused else "dip_sweep4_kernel") if st["engine"] == 4 else ("dip_sweep_many_kernel" if fused else "dip_sweep_kernel")
         line = {
             "metric": "dp_cell_updates_per_sec", "value": world * S * U / (dev_ms_max * 1e-3), "unit": "cell-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max, "higher_is_better": True,
@@ -305,29 +347,33 @@ def main():
             "config": {"workload": args.workload, "description": desc, "R": args.R, "ploidy": 2, "levels": st["n_levels"],
                        "vertices": st["n_vertices"], "max_width": st["max_width"], "cell_updates_per_sample": U,
                        "dest_cells_per_sample": st["cells"], "samples_per_step": world * S, "samples_per_gpu": S,
-                       "ctas_per_sample": st["grid_ctas"], "sharding": "independent samples per GPU and per CTA group, no collective", "fused_sweep_launch": bool(S >= 2 and sts[1]["launches"] == sts[0]["launches"] - 1),
+                       "ctas_per_sample": st["grid_ctas"], "distinct_samples": len(samples), "engine": st["engine"],
+                       "sharding": "independent samples per GPU and per CTA, no collective", "fused_sweep_launch": bool(fused),
                        "l2": "256 MiB device buffer rewritten between timed iterations",
                        "timing": "CUDA events on the library stream around the fork/join of the S resident sweeps (delta + sweep + traceback kernels)"},
             "samples_per_sec": world * B / (e2e_ms_max * 1e-3),
             "dp_value": outs[0]["value"],
             "gpu_launches": int(sum(x["launches"] for x in sts)) * args.steps,
             "kernel_ms": {"pair_scores": float(np.mean(delta)), "sweep": sweep_ms, "traceback": float(np.mean(trace)),
-                          "note": ("sweep: the one fused launch over all S samples; pair scores / traceback: per sample, S of them side by side"
+                          "note": ("sweep: the one fused launch over all S samples; traceback: the four launches over all S samples"
                                    if fused else "per launch, with S launches resident together")},
             "wall_s_timed_region": t_wall,
-            "roofline": {"bound": "hbm", "kernel": "dip_sweep_many_kernel" if fused else "dip_sweep_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (NCU_TRAFFIC.get((args.workload, args.R)) or 0) * per_launch or None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": st["algo_bytes"] * per_launch, "samples_per_launch": per_launch,
+                         "traffic": traffic[0] * per_launch if traffic else None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo * per_launch, "samples_per_launch": per_launch,
                          "launches_resident_together": 1 if fused else S,
                          "aggregate_achieved": achieved * (1 if fused else S),
-                         "traffic_note": "dram bytes per sample from the ncu --set full capture of an 8-sample fused launch (profiles/r01c_sweep_many_ncu.md) x samples per launch",
-                         "note": "latency-bound at H=5: every sample is a chain of 120 362 dependent level transitions, almost all on one SM; "
-                                 "the machine is filled by sweeping samples side by side, one CTA each, in one launch (see DESIGN.md)"},
+                         "traffic_source": traffic[1] if traffic else "no ncu capture for this (workload, R, samples per GPU)",
+                         "cells_written_frac": float(np.mean([x["cells_written"] for x in sts])) / max(1.0, float(np.mean([x["cells"] for x in sts]))),
+                         "note": "algorithmic bytes (SURVEY 8d) count an HBM round trip of every cell of every level; the in-place layers "
+                                 "leave the passive pairs untouched and keep the narrow levels in shared memory, so achieved/peak above 1 is possible; "
+                                 "H = 5 samples are chains of ~10^5 dependent level transitions and the GPU is filled with samples side by side (DESIGN.md)"},
             "e2e": {"value": world * B * U / (e2e_ms_max * 1e-3), "unit": "cell-updates/s", "ms_per_step": e2e_ms_max,
-                    "samples_per_step": world * B, "h2d_bytes_per_step": int(g.nbytes) * B,
+                    "samples_per_step": world * B, "h2d_bytes_per_step": int(np.mean([x["h2d_bytes"] for x in sts])) * B,
                     "d2h_bytes_per_step": int(ctypes_out_bytes()) * B,
-                    "api": "dg_dp_diploid_batch (host buffers -> planning -> H2D -> pair scores -> sweep -> traceback -> D2H), %d samples per GPU" % B},
+                    "h2d_note": "the gather-form tables dg_dip_create uploads (in-edge CSR, colour masks, slot / class tables, headers, directories); the level programs are built on the device",
+                    "api": "dg_dp_diploid_batch (host buffers -> planning -> H2D -> program build -> sweep -> traceback -> D2H), %d samples per GPU" % B},
             "e2e_single_sample": {"value": U / (single_ms_max * 1e-3), "unit": "cell-updates/s", "ms_per_step": single_ms_max,
                                   "api": "dg_dp_diploid, one sample, whole GPU"},
             "clocks": clk.summary(),

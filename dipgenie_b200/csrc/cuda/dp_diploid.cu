@@ -1119,7 +1119,8 @@ struct PlanStaging {
 
 struct dg_dip {
     explicit dg_dip(std::unique_ptr<PlanStaging> st = nullptr)
-        : staging(std::move(st)), plan(staging ? staging->resource() : std::pmr::get_default_resource()) {}
+        : staging(std::move(st)), plan(staging ? staging->resource() : std::pmr::get_default_resource()),
+          p4(staging ? staging->resource() : std::pmr::get_default_resource()) {}
     std::unique_ptr<PlanStaging> staging;   // declared before `plan`: outlives the plan's arrays
     cudaStream_t stream = nullptr;   // the context's stream, or one of the batch streams
     bool cooperative = true;         // batch slots use plain launches (see dip_run_impl)
@@ -1128,6 +1129,7 @@ struct dg_dip {
     std::vector<int32_t> h_cp;       // traceback checkpoints (host copies until uploaded)
     std::vector<int64_t> h_aoff;
     DipPlan plan;                 // host copy (small arrays kept for stats; big ones released after upload)
+    Plan4 p4;                     // level-program engine: its planning (same storage rules)
     int pred_bytes = 2;
     int grid = 1;
     // row-sharded over `world` GPUs (dg_dip_create_sharded): peer mappings of tile0, tile1, pred, counter
@@ -1163,9 +1165,9 @@ struct dg_dip {
     int launches = 0;
     bool ran = false, checks = false;
     uint64_t device_bytes = 0;
+    uint64_t h2d_bytes = 0;          // host arrays copied to the device by dg_dip_create
     // level-program engine (dp_prog.h, dp_sweep4.cuh); v4 == false: the task-stream engine above
     bool v4 = false;
-    Plan4 p4;
     int v4_ncw = 12;
     float build_ms = 0.f;            // prog_fill_kernel
     DevBuf<ProgDir> v4_dir, v4_dir_full;        // the timed directory (idle transitions skipped) and the complete one (checksums)
@@ -1233,7 +1235,7 @@ static bool sweep4_shape(int R, int grid, bool packed, Sweep4Shape& sh, int& rc,
     if (rc != 10) want = std::max(want, 9);
     for (int slog = want; slog >= (rc == 10 ? 8 : 9); --slog)
         if (sweep4_smem_bytes(slog, RL, sh.slot_bytes, sh.nslot) <= S4_SMEM_MAX) {
-            sh.slog = slog; sh.kn = slog == 10 ? 32 : (slog == 9 ? 22 : 16);
+            sh.slog = slog; sh.kn = slog == 10 ? 31 : (slog == 9 ? 22 : 15);     // kn^2 < 1 << slog: the last cell of a layer stays DEAD
             return true;
         }
     return false;
@@ -1308,7 +1310,10 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
         int rc = 10;
         std::string why = "no kernel variant for this R";
         if (sweep4_shape(p.R, shape.grid, !d->cooperative && shape.grid == 1, s4, rc, d->v4_ncw) && plan4_build(p, g, s4, rc, d->p4, why)) d->v4 = true;
-        else if (getenv("DG_TIMING")) fprintf(stderr, "dg_dip: task-stream engine (%s)\n", why.c_str());
+        else {
+            d->p4.release_arrays();           // (whatever the failed attempt left in the page-locked block: it is handed back before d dies)
+            if (getenv("DG_TIMING")) fprintf(stderr, "dg_dip: task-stream engine (%s)\n", why.c_str());
+        }
     }
     if (d->v4) {
         d->grid = d->p4.full.wide_list.empty() ? 1 : shape.grid;      // no HBM-resident transition: CTA 0 does everything
@@ -1359,8 +1364,8 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
         const int smem = (int)sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
         for (int c = 0; c < 2; ++c) DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_fn(q.shape.slog, q.rc, c != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_many_fn(q.shape.slog, q.rc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        // all of the SM's unified L1/shared memory as shared memory: two packed CTAs of ~105 KB each must fit
-        DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_many_fn(q.shape.slog, q.rc), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        // (no shared-memory carveout preference: the generic path's descriptor and spill traffic wants the L1 that two packed
+        //  CTAs of ~61 KB leave — with the carveout forced to 100 % the same launch took 636 instead of 416 ms)
     }
     DG_CUDA(ctx, d->level_off.upload(p.level_off.data(), p.level_off.size(), s));
     DG_CUDA(ctx, d->in_off.upload(p.in_off.data(), p.in_off.size(), s));
@@ -1390,6 +1395,11 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     DG_CUDA(ctx, d->v4_m.upload(q.lvl_m.data(), q.lvl_m.size(), s));
     DG_CUDA(ctx, d->v4_z.upload(q.lvl_z.data(), q.lvl_z.size(), s));
     DG_CUDA(ctx, d->v4_dm.upload(q.lvl_dm.data(), q.lvl_dm.size(), s));
+    d->h2d_bytes = d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->lvlW.bytes() + d->masks.bytes() + d->msrc_off.bytes() +
+                   d->mdst_off.bytes() + d->pred_off.bytes() + d->cp.bytes() + d->aoff.bytes() + d->v4_dir.bytes() + d->v4_dir_full.bytes() +
+                   d->v4_hdr.bytes() + d->v4_prog_off.bytes() + d->v4_wide.bytes() + d->v4_wide_full.bytes() + d->v4_vslot.bytes() +
+                   d->v4_dom.bytes() + d->v4_tflags.bytes() + d->v4_np.bytes() + d->v4_cls.bytes() + d->v4_vinfo.bytes() + d->v4_mpre.bytes() +
+                   d->v4_mpre_off.bytes() + d->v4_n1.bytes() + d->v4_m.bytes() + d->v4_z.bytes() + d->v4_dm.bytes();
     DG_CUDA(ctx, d->v4_prog.alloc((size_t)q.prog_bytes + 16, s));
     DG_CUDA(ctx, d->v4_pred.alloc((size_t)q.pred_elems + 8, s));
     DG_CUDA(ctx, d->v4_sink.alloc((size_t)p.R + 1, s));
@@ -1438,11 +1448,7 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     p.in_dst.clear(); p.in_dst.shrink_to_fit();
     p.masks.clear(); p.masks.shrink_to_fit();
     p.in_off.clear(); p.in_off.shrink_to_fit();
-    q.cls_list.clear(); q.cls_list.shrink_to_fit();
-    q.vinfo.clear(); q.vinfo.shrink_to_fit();
-    q.vslot.clear(); q.vslot.shrink_to_fit();
-    q.mpre.clear(); q.mpre.shrink_to_fit();
-    q.hdr.clear(); q.hdr.shrink_to_fit();
+    q.release_arrays();
     if (d->staging) d->staging->release();
     return DG_OK;
 }
@@ -1474,6 +1480,9 @@ static int dip_create_device(dg_ctx* ctx, dg_dip* d) {
     DG_CUDA(ctx, d->pred_off.upload(p.pred_off.data(), p.pred_off.size(), s));
     DG_CUDA(ctx, d->cp.upload(cp.data(), cp.size(), s));
     DG_CUDA(ctx, d->aoff.upload(aoff.data(), aoff.size(), s));
+    d->h2d_bytes = d->tasks.bytes() + d->task_begin.bytes() + d->records.bytes() + d->delta_off.bytes() + d->delta_list.bytes() +
+                   d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->in_dst.bytes() + d->lvlW.bytes() + d->masks.bytes() +
+                   d->msrc_off.bytes() + d->mdst_off.bytes() + d->pred_off.bytes() + d->cp.bytes() + d->aoff.bytes();
     // (layers rounded up to whole lane-form chunks: the last chunk loads, but never stores, layers above R)
     const uint64_t widest = (uint64_t)(p.R + d->lane_rc) * (uint64_t)p.kmax * (uint64_t)p.kmax;
     const size_t tile = (size_t)std::max<uint64_t>(widest, (uint64_t)(p.R + 1));
@@ -1583,12 +1592,13 @@ static void fill_sweep4_args(const dg_dip* d, Sweep4Args& a, bool check) {
     const Plan4& q = d->p4;
     const Plan4Dir& dir = check ? q.full : q.timed;         // the checksum variant folds every level, idle transitions included
     a.dir = check ? d->v4_dir_full.p : d->v4_dir.p; a.wide_list = check ? d->v4_wide_full.p : d->v4_wide.p;
-    a.n_trans = (int32_t)dir.dir.size(); a.n_wide = (int32_t)dir.wide_list.size();
+    a.n_trans = dir.n; a.n_wide = (int32_t)dir.wide_list.size();
     a.prog = d->v4_prog.p; a.gtile = d->tile0.p; a.gpad = (long long)q.gpad; a.hkk = (long long)q.hstride * q.hstride;
     a.pred = d->v4_pred.p; a.counter = d->counter.p; a.level_sum = d->level_sum.p; a.level_live = d->level_live.p;
     a.sink = d->v4_sink.p; a.R = p.R; a.nchunk = q.nchunk; a.grid = d->grid; a.ncw = d->v4_ncw;
     a.slot_bytes = q.shape.slot_bytes; a.nslot = q.shape.nslot; a.m_nchunk = make_magic((uint32_t)q.nchunk);
-    a.last_smem = q.lvl_dom[(size_t)p.L - 1] == 0; a.sink_cell = q.sink_cell;
+    a.last_smem = q.last_smem ? 1 : 0; a.sink_cell = q.sink_cell;
+    a.use_l1 = getenv("DG_V4_NO_L1") ? 0 : 1;
     a.chk = check ? d->v4_tables.p : nullptr;
     a.final_target = dir.final_target;
     a.prof = d->want_prof ? d->prof.p : nullptr;
@@ -1761,9 +1771,10 @@ int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out) {
     out->n_tasks = d->plan.task_begin.empty() ? 0 : (int64_t)d->plan.task_begin.back();
     out->delta_bytes = (uint64_t)d->plan.delta_elems * 2;
     out->engine = d->v4 ? 4 : 3;
+    out->h2d_bytes = d->h2d_bytes;
     if (d->v4) {
         out->n_narrow = (int32_t)d->p4.n_smem_trans; out->n_wide = (int32_t)d->p4.timed.wide_list.size();
-        out->n_tasks = (int64_t)d->p4.timed.dir.size();
+        out->n_tasks = (int64_t)d->p4.timed.n;
         out->cells_written = d->p4.cells_written * (uint64_t)(d->plan.R + 1); out->n_relocate = (int32_t)d->p4.n_relocate;
         out->prog_bytes = d->p4.prog_bytes; out->code_bytes = (uint64_t)d->p4.pred_elems * 2;
         out->build_ms = d->build_ms;
@@ -1868,7 +1879,7 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
             if (pinned && x.n_levels > 0 && x.level_off) {
                 st.reset(new PlanStaging());
                 const size_t V = (size_t)x.level_off[x.n_levels];
-                st->acquire(ctx, ((size_t)68 * V + ((size_t)4 << 20) + ((size_t)1 << 20) - 1) >> 20 << 20);
+                st->acquire(ctx, ((size_t)120 * V + ((size_t)6 << 20) + ((size_t)1 << 20) - 1) >> 20 << 20);
             }
             std::unique_ptr<dg_dip> d(new dg_dip(std::move(st)));
             d->stream = ctx->batch_streams[(size_t)(i % K)];

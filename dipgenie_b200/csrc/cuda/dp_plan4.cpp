@@ -24,12 +24,12 @@ void schedule(Plan4Dir& d, int grid) {
         else if (!ss && ds) { e.flags |= PF_WAIT; e.wait_target = cum; }
     }
     d.final_target = cum;
+    d.n = (int32_t)d.dir.size();
 }
 
 }  // namespace
 
 bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& shape, int rc, Plan4& q, std::string& why) {
-    q = Plan4();
     q.shape = shape;
     const int L = p.L;
     q.L = L; q.R = p.R; q.rc = rc;
@@ -140,11 +140,26 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
         for (int32_t v = lo; v < hi; ++v) {
             const uint32_t d = (uint32_t)(p.in_off[(size_t)v + 1] - p.in_off[v]);
             const uint16_t pos = (uint16_t)(v - lo);
-            if (d == 1 && !passive[v]) { q.vinfo[v] = a; list[a++] = pos; }
-            else if (d == 1) { q.vinfo[v] = na + ap; list[na + ap++] = pos; }
-            else if (d >= 2) { q.vinfo[v] = b | (1u << 30); P[b] = dm; dm += d; dmax = std::max(dmax, d); list[n1 + b++] = pos; }
-            else { q.vinfo[v] = c | (2u << 30); list[n1 + m + c++] = pos; }
+            if (d == 1 && !passive[v]) list[a++] = pos;
+            else if (d == 1) list[na + ap++] = pos;
+            else if (d >= 2) list[n1 + b++] = pos;
+            else list[n1 + m + c++] = pos;
         }
+        // every class in ascending SLOT order: the cells of a block of 32 then sit next to each other in the tile wherever
+        // the block runs along a row (coalesced HBM accesses); the tie-break is not affected — it orders the candidates
+        // of one cell, by source position
+        auto by_slot = [&](uint16_t x, uint16_t y) { return q.vslot[(size_t)lo + x] < q.vslot[(size_t)lo + y]; };
+        std::sort(list, list + na, by_slot);
+        std::sort(list + na, list + n1, by_slot);
+        std::sort(list + n1, list + n1 + m, by_slot);
+        std::sort(list + n1 + m, list + (hi - lo), by_slot);
+        for (uint32_t x = 0; x < n1; ++x) q.vinfo[(size_t)lo + list[x]] = x;
+        for (uint32_t x = 0; x < m; ++x) {
+            const int32_t v = lo + list[n1 + x];
+            const uint32_t d = (uint32_t)(p.in_off[(size_t)v + 1] - p.in_off[v]);
+            q.vinfo[v] = x | (1u << 30); P[x] = dm; dm += d; dmax = std::max(dmax, d);
+        }
+        for (uint32_t x = 0; x < (uint32_t)(hi - lo) - n1 - m; ++x) q.vinfo[(size_t)lo + list[n1 + m + x]] = x | (2u << 30);
         P[m] = dm;
         q.lvl_dm[l] = dm;
         max_cand = std::max<uint64_t>(max_cand, (uint64_t)dmax * dmax);
@@ -217,6 +232,7 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
     const int32_t last = p.level_off[L - 1];
     const uint32_t ls = q.vslot[last];
     q.sink_cell = ls * (uint32_t)(q.lvl_dom[L - 1] == 0 ? kn : q.hstride) + ls;
+    q.last_smem = q.lvl_dom[L - 1] == 0;
     return true;
 }
 

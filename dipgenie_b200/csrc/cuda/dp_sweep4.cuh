@@ -146,6 +146,7 @@ struct Sweep4Args {
     int32_t grid, ncw;            // CTAs of the problem, compute warps per CTA
     int32_t slot_bytes, nslot;    // ring geometry
     uint32_t m_nchunk;            // magic of nchunk (dp_cell.h: make_magic; 0 when nchunk == 1)
+    int32_t use_l1;               // diagnostics switch for Lvl4::l1
     int32_t last_smem;            // the last level lives in the shared-memory tile
     uint32_t sink_cell;           // its cell (0,0)
     const Fill4Args* chk;         // checksum variant: the device tables the positions of a descriptor are decoded from
@@ -163,6 +164,18 @@ template <int IMM> __device__ __forceinline__ int32_t lds_imm(uint32_t a) {
 }
 template <int IMM> __device__ __forceinline__ void sts_imm(uint32_t a, int32_t v) {
     asm volatile("st.shared.s32 [%0+%1], %2;" ::"r"(a), "n"(IMM), "r"(v) : "memory");
+}
+// The same without `volatile`: the compiler may schedule these among the arithmetic of neighbouring candidates (software
+// pipelining).  Safe here because a unit reads cells of level l (old slots) and writes cells of fresh slots only, and the
+// addresses of every level come from descriptors that are themselves loaded after the level's barrier (volatile).
+template <int IMM> __device__ __forceinline__ int32_t lds_imm_free(uint32_t a) {
+    int32_t v;
+    asm("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(IMM));
+    return v;
+}
+template <int SLOG, int RC, int Q = 0>
+__device__ __forceinline__ void lds_layers_free(uint32_t a, int32_t (&v)[RC]) {
+    if constexpr (Q < RC) { v[Q] = lds_imm_free<(Q << (SLOG + 2))>(a); lds_layers_free<SLOG, RC, Q + 1>(a, v); }
 }
 template <int SLOG, int RC, int Q = 0>
 __device__ __forceinline__ void lds_layers(uint32_t a, int32_t (&v)[RC]) {
@@ -182,6 +195,7 @@ struct Lvl4 {
     long long kk, kk2;                    // layer strides there
     uint16_t* pl;                         // codes of level l+1, [layer][slot]
     int level, R, nchunk;
+    bool l1;                              // HBM-tile loads may be served by L1 (the problem runs on one SM)
     const ProgLevelIn* in;                // checksum variant only
 };
 
@@ -208,8 +222,13 @@ __device__ __forceinline__ void load_layers(const Lvl4& c, int r0, uint32_t src,
         lds_layers<SLOG, RC>(c.src32 + ((((uint32_t)(r0 + 2) - w) << SLOG) + src) * 4u, v);
     } else {
         const int32_t* p = c.gsrc + ((long long)(r0 - (int)w) * c.kk + (long long)src);
+        if (c.l1) {              // one CTA per problem: the cells were written by this SM, its L1 is coherent with them
 #pragma unroll
-        for (int q = 0; q < RC; ++q) v[q] = __ldcg(p + (long long)q * c.kk);
+            for (int q = 0; q < RC; ++q) v[q] = p[(long long)q * c.kk];
+        } else {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) v[q] = __ldcg(p + (long long)q * c.kk);
+        }
     }
 }
 template <int SLOG, int RC, bool DS>
@@ -218,8 +237,13 @@ __device__ __forceinline__ void store_layers(const Lvl4& c, int r0, uint32_t dst
         sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, v);
     } else {
         int32_t* p = c.gdst + ((long long)r0 * c.kk2 + (long long)dst);
+        if (c.l1) {
 #pragma unroll
-        for (int q = 0; q < RC; ++q) __stcg(p + (long long)q * c.kk2, v[q]);
+            for (int q = 0; q < RC; ++q) p[(long long)q * c.kk2] = v[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) __stcg(p + (long long)q * c.kk2, v[q]);
+        }
     }
 }
 
@@ -378,7 +402,7 @@ __device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_
     c.k = h.k; c.k2 = h.k2; c.n_copy = h.n_copy; c.n_multi = h.n_multi; c.n_big = h.n_big; c.n_dead = h.n_dead;
     const uint8_t* const pb = (flags & PF_STAGED) ? sb + sizeof(ProgDir) : a.prog + (size_t)d.off16 * 16;
     c.copy_p = pb + sizeof(ProgHdr); c.cell_p = pb + h.off_cell; c.cand_p = pb + h.off_cand; c.big_p = pb + h.off_big; c.dead_p = pb + h.off_dead;
-    c.level = l; c.R = a.R; c.nchunk = a.nchunk;
+    c.level = l; c.R = a.R; c.nchunk = a.nchunk; c.l1 = a.grid == 1 && a.use_l1;
     c.src32 = tile32; c.dst32 = tile32;
     c.gsrc = a.gtile + a.gpad; c.gdst = a.gtile + a.gpad;
     c.kk = a.hkk; c.kk2 = a.hkk;
@@ -434,6 +458,10 @@ __device__ __forceinline__ void fast_copy(const Fast4& c, uint32_t blk, int r0, 
     }
 }
 
+// A candidate descriptor that changes nothing: the last cell of every layer is never a slot pair (kn^2 < 1 << SLOG) and is
+// kept DEAD, so lanes that have run out of candidates walk on branch-free.
+template <int SLOG> __device__ __forceinline__ constexpr uint32_t dead_cand() { return (1u << SLOG) - 1u; }
+
 template <int SLOG, int RC, bool CHECK>
 __device__ __forceinline__ void fast_multi(const Fast4& c, uint32_t blk, int r0, int lane, Fold4& f) {
     const uint32_t t = blk * 32u + (uint32_t)lane;
@@ -449,18 +477,18 @@ __device__ __forceinline__ void fast_multi(const Fast4& c, uint32_t blk, int r0,
     int32_t key[RC];
 #pragma unroll
     for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
-    uint32_t x = n ? lds_u32(ca) : 0u;                               // candidate descriptors one ahead
-    for (uint32_t o = 0; o < nmax; ++o) {
-        if (o < n) {
-            const uint32_t e = x;
-            if (o + 1u < n) x = lds_u32(ca + 4u * (o + 1u));
-            const uint32_t src = e & 1023u, w = (e >> 10) & 3u;
-            const int32_t add = (int32_t)(((e >> 12) << V4_SHIFT) + (V4_ORD_MASK - o));
-            int32_t v[RC];
-            lds_layers<SLOG, RC>(base + (src << 2) - (w << (SLOG + 2)), v);
+    // two candidates per round, branch-free; the descriptors of the next round are fetched before this round's layers
+    uint32_t x0 = lds_u32(ca), x1 = lds_u32(ca + 4u);
+    for (uint32_t o = 0; o < nmax; o += 2u) {
+        const uint32_t e0 = o < n ? x0 : dead_cand<SLOG>(), e1 = o + 1u < n ? x1 : dead_cand<SLOG>();
+        x0 = lds_u32(ca + 4u * (o + 2u)); x1 = lds_u32(ca + 4u * (o + 3u));      // (may run past the cell's list: unused then)
+        const int32_t add0 = (int32_t)(((e0 >> 12) << V4_SHIFT) + (V4_ORD_MASK - o));
+        const int32_t add1 = (int32_t)(((e1 >> 12) << V4_SHIFT) + (V4_ORD_MASK - o - 1u));
+        int32_t v0[RC], v1[RC];
+        lds_layers_free<SLOG, RC>(base + ((e0 & 1023u) << 2) - (((e0 >> 10) & 3u) << (SLOG + 2)), v0);
+        lds_layers_free<SLOG, RC>(base + ((e1 & 1023u) << 2) - (((e1 >> 10) & 3u) << (SLOG + 2)), v1);
 #pragma unroll
-            for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
-        }
+        for (int q = 0; q < RC; ++q) key[q] = max(key[q], max(v0[q] + add0, v1[q] + add1));
     }
     if (n) {
         uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
@@ -487,10 +515,9 @@ __device__ __forceinline__ void fast_big(const Fast4& c, uint32_t u, int r0, int
     for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
     for (uint32_t o = (uint32_t)lane; o < n; o += 32u) {
         const uint32_t e = lds_u32(ca + 4u * o);
-        const uint32_t src = e & 1023u, w = (e >> 10) & 3u;
         const int32_t add = (int32_t)(((e >> 12) << V4_SHIFT) + (V4_ORD_MASK - o));
         int32_t v[RC];
-        lds_layers<SLOG, RC>(base + (src << 2) - (w << (SLOG + 2)), v);
+        lds_layers_free<SLOG, RC>(base + ((e & 1023u) << 2) - (((e >> 10) & 3u) << (SLOG + 2)), v);
 #pragma unroll
         for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
     }
@@ -563,7 +590,10 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
         // two dead padding layers below layer 0 of the tile; level 0 (one vertex, slot 0): every layer starts at 0 (:535)
         int32_t* const t0 = reinterpret_cast<int32_t*>(tiles);
         for (int x = tid; x < (2 << SLOG); x += blockDim.x) t0[x] = V4_DEAD;
-        for (int r = tid; r < RL; r += blockDim.x) t0[((r + 2) << SLOG)] = r <= a.R ? 0 : V4_DEAD;
+        for (int r = tid; r < RL; r += blockDim.x) {
+            t0[((r + 2) << SLOG)] = r <= a.R ? 0 : V4_DEAD;
+            t0[((r + 2) << SLOG) + (int)dead_cand<SLOG>()] = V4_DEAD;       // the cell no slot pair maps to (fast_multi)
+        }
     }
     __syncthreads();
 
@@ -636,7 +666,10 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                 const uint32_t nch = (uint32_t)a.nchunk;
                 const uint32_t e0 = c.n_big * nch, e1 = e0 + ((c.n_multi + 31u) >> 5) * nch, e2 = e1 + ((c.n_copy + 31u) >> 5) * nch,
                                e3 = e2 + ((c.n_dead + 31u) >> 5) * nch;
+                long long tu0 = 0;
+                if (profiling) { tu0 = clock64(); a.prof[18] += (unsigned long long)(tu0 - tk1); }
                 for (uint32_t u = (uint32_t)warp; u < e3; u += (uint32_t)ncw) {
+                    if (profiling) { a.prof[20] += 1; a.prof[21 + (u < e0 ? 0 : (u < e1 ? 1 : (u < e2 ? 2 : 3)))] += 1; }
                     // unit -> (kind, block, chunk): chunks of one block are neighbours
                     const uint32_t lo = u < e0 ? 0u : (u < e1 ? e0 : (u < e2 ? e1 : e2));
                     const uint32_t v = u - lo, blk = a.m_nchunk ? __umulhi(v, a.m_nchunk) : v, ch = v - blk * nch;
@@ -646,6 +679,7 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                     else if (u < e2) fast_copy<SLOG, RC, CHECK>(c, blk, r0, lane, f);
                     else fast_dead<SLOG, RC>(c, blk, r0, lane);
                 }
+                if (profiling) a.prof[19] += (unsigned long long)(clock64() - tu0);
             } else {
                 const ulonglong2 fs = run_generic<SLOG, RC, CHECK>(a, slots + (size_t)slot * a.slot_bytes, tiles32, l, cta, warp, lane);
                 f.sum = fs.x; f.live = fs.y;

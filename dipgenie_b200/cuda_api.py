@@ -26,6 +26,7 @@ class DipStats(C.Structure):
         ("upload_ms", C.c_float), ("n_narrow", C.c_int32), ("n_wide", C.c_int32), ("n_tasks", C.c_int64),
         ("delta_bytes", C.c_uint64), ("prog_bytes", C.c_uint64), ("code_bytes", C.c_uint64), ("engine", C.c_int32),
         ("build_ms", C.c_float), ("cells_written", C.c_uint64), ("n_relocate", C.c_int32), ("pad_", C.c_int32),
+        ("h2d_bytes", C.c_uint64),
     ]
 
 

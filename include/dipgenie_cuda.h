@@ -100,6 +100,7 @@ typedef struct {
     float build_ms;                     /* prog_fill_kernel inside dg_dip_create (engine 4) */
     uint64_t cells_written;             /* engine 4: destination cells the sweep writes (in-place layers skip the passive pairs) */
     int32_t n_relocate, pad_;           /* engine 4: transitions that move the level between the shared-memory and the HBM tile */
+    uint64_t h2d_bytes;                 /* host arrays dg_dip_create copied to the device (the program itself is built there) */
 } dg_dip_stats_t;
 int dg_dip_stats(dg_ctx* ctx, dg_dip* d, dg_dip_stats_t* out);
 /* out24: for each of {shared-memory layers, HBM/L2 layers} six counters {tasks, slot-wait, grid-wait,

@@ -222,7 +222,8 @@ extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const
         (void)k;
     }
     // sink cell (r = R, 0, 0) of the last level and the walk back through the codes
-    const bool last_smem = q.lvl_dom[L - 1] == 0;
+    const bool last_smem = q.last_smem;
+    if (last_smem != (q.lvl_dom[L - 1] == 0) || q.full.n != L - 1 || q.timed.n != (int32_t)q.timed.dir.size()) return -9;
     const int32_t raw = T.at(last_smem, R, q.sink_cell);
     *sink_value = raw < 0 ? NEG_INF : (raw >> V4_SHIFT);
     *sink_s_het = 0; *n_p1 = 0; *n_p2 = 0;

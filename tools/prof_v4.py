@@ -15,6 +15,7 @@ import numpy as np, ctypes as C
 pr = np.zeros(24, np.uint64)
 ctx.lib.dg_dip_profile(C.c_void_p(ctx.h), p.h, pr.ctypes.data_as(C.c_void_p))
 print("per class [levels, cycles/level]: compact %d %.0f | hand-over %d %.0f | HBM %d %.0f" % (pr[4], pr[5] / max(1, pr[4]), pr[6], pr[7] / max(1, pr[6]), pr[8], pr[9] / max(1, pr[8])), flush=True)
+print("narrow loop, warp 0: set-up %.1f M, units %.1f M cycles; %d units (big %d, multi %d, copy %d, dead %d)" % (pr[18] / 1e6, pr[19] / 1e6, pr[20], pr[21], pr[22], pr[23], 0), flush=True)
 print("CTA0/thread0 cycles: slot wait %.1f M, work %.1f M, barrier %.1f M over %d levels (%.0f cycles/level)" % (pr[0] / 1e6, pr[1] / 1e6, pr[2] / 1e6, pr[3], (pr[0] + pr[1] + pr[2]) / max(1, pr[3])), flush=True)
 print(json.dumps(dict(single=dict(value=r['value'], engine=st['engine'], grid=st['grid_ctas'], sweep_ms=st['sweep_ms'], trace_ms=st['traceback_ms'],
                                   plan_ms=st['plan_ms'], upload_ms=st['upload_ms'], build_ms=st['build_ms'], prog_MB=st['prog_bytes'] / 1e6,
