@@ -114,7 +114,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-__device__ __noinline__ bool wait_counter_sys(const unsigned int* counter, unsigned int target, unsigned long long timeout_ns) {
+// `failed` = the run's error word (counter[2] of this GPU): non-zero once any wait of any rank has timed out (the rank that
+// gives up writes it into every peer's word too), after which nobody waits any more — the failure is sticky, so a dead
+// peer costs ONE timeout, not one per level.
+__device__ __noinline__ bool wait_counter_sys(const unsigned int* counter, unsigned int target, unsigned long long timeout_ns,
+                                              const unsigned int* failed) {
     const unsigned long long t0 = global_ns();
     bool ok = true;
     for (unsigned int it = 0;; ++it) {
@@ -122,7 +126,11 @@ __device__ __noinline__ bool wait_counter_sys(const unsigned int* counter, unsig
         asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
         if (v >= target) break;
         __nanosleep(40);
-        if ((it & 1023u) == 1023u && global_ns() - t0 > timeout_ns) { ok = false; break; }
+        if ((it & 255u) == 255u) {
+            unsigned int f;
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(failed) : "memory");
+            if (f != 0u || global_ns() - t0 > timeout_ns) { ok = false; break; }
+        }
     }
     asm volatile("fence.acq_rel.sys;" ::: "memory");
     return ok;
@@ -796,6 +804,9 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const int cta) {
     }
 
     // ---- compute warps ----
+    __shared__ int s_failed;                 // row-sharded sweep: a cross-GPU wait has timed out, stop working (the ring keeps moving)
+    if (tid == 0) s_failed = 0;
+    bar_compute();
     const bool profiling = PROF && cta == 0 && tid == 0;
     unsigned long long pc0 = 0, pc1 = 0, pc2 = 0, pc3 = 0, pc4 = 0, pc5 = 0, pc6 = 0, pc7 = 0, pc8 = 0, pc9 = 0;
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0;
@@ -817,14 +828,19 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const int cta) {
         if (flags & TK_WAIT) {
             if (tid == 0) {
                 if (a.world > 1) {
-                    if (!wait_counter_sys(a.counter, h1.z, a.timeout_ns)) {
-                        if (atomicCAS(a.counter + 2, 0u, (unsigned int)l + 1u) == 0u)
+                    if (!s_failed && !wait_counter_sys(a.counter, h1.z, a.timeout_ns, a.counter + 2)) {
+                        s_failed = 1;
+                        if (atomicCAS(a.counter + 2, 0u, (unsigned int)l + 1u) == 0u) {
                             printf("dip_sweep_kernel: rank %d CTA %d gave up at level %d: %u of %u arrivals\n", a.rank, cta, l, *(volatile unsigned int*)a.counter, h1.z);
+                            for (int q = 0; q < a.world; ++q)          // tell the peers: nobody waits for this run any more
+                                if (q != a.rank) atomicCAS(a.peer_counter[q] + 2, 0u, (unsigned int)l + 1u);
+                        }
                     }
                 } else wait_counter(a.counter, h1.z);
             }
             bar_compute();
         }
+        const bool failed = a.world > 1 && s_failed != 0;      // (set before a block barrier: the same for every thread of the task)
         if (profiling) tk2 = clock64();
         unsigned long long hsum = 0, hlive = 0;
         const bool ssm = (flags & TK_SRC_SMEM) != 0, dsm = (flags & TK_DST_SMEM) != 0;
@@ -835,7 +851,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const int cta) {
             for (uint32_t x = (uint32_t)tid; x < total; x += DIP_CT) scratch[x] = 0ull;
             bar_compute();
         }
-        if ((uint32_t)(tid & ~31) < h2.w) {          // this warp owns work of the task
+        if ((uint32_t)(tid & ~31) < h2.w && !failed) {          // this warp owns work of the task
             if (flags & TK_LANES) {
                 if (a.shift && !is_long) {
                     LaneTask lt;
@@ -880,7 +896,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const int cta) {
         __syncwarp();
         if (lane == 0) mbar_arrive(empty32 + 8u * slot);       // this warp is done with the slot
         if (flags & TK_BAR) bar_compute();                     // the destination rows of this CTA are whole
-        if (flags & TK_PUSH) {
+        if ((flags & TK_PUSH) && !failed) {
             // row-sharded sweep: this CTA's rows of layer l+1 (values and predecessor codes) go to every peer over NVLink
             push_rows<PRED32>(a, l, h2.x >> 16, pw & 0xFFFFu, pw >> 16, push_pred_off, tid);
             __threadfence_system();
@@ -920,7 +936,7 @@ __device__ __forceinline__ void sweep_body(const SweepArgs& a, const int cta) {
         bar_compute();
         if (tid == 0) {
             for (int q = 0; q < a.world; ++q) red_release_sys_add_u32(a.peer_counter[q] + 1, 1u);
-            if (cta == 0 && !wait_counter_sys(a.counter + 1, a.exit_target, a.timeout_ns)) {
+            if (cta == 0 && !s_failed && !wait_counter_sys(a.counter + 1, a.exit_target, a.timeout_ns, a.counter + 2)) {
                 if (atomicCAS(a.counter + 2, 0u, 0x7FFFFFFFu) == 0u)
                     printf("dip_sweep_kernel: rank %d gave up at the exit barrier: %u of %u CTAs\n", a.rank, *(volatile unsigned int*)(a.counter + 1), a.exit_target);
             }
@@ -1694,6 +1710,19 @@ static int batch_stream(dg_ctx* ctx, int slot, cudaStream_t* out) {
     return DG_OK;
 }
 
+// Events of one dg_dip_run_many call: destroyed on every way out (the DG_CUDA early returns included).
+namespace {
+struct EventBag {
+    std::vector<cudaEvent_t> all;
+    cudaError_t make(cudaEvent_t* e, unsigned flags = cudaEventDefault) {
+        const cudaError_t r = cudaEventCreateWithFlags(e, flags);
+        if (r == cudaSuccess) all.push_back(*e);
+        return r;
+    }
+    ~EventBag() { for (cudaEvent_t e : all) cudaEventDestroy(e); }
+};
+}  // namespace
+
 extern "C" {
 
 int dg_dip_create(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
@@ -2054,9 +2083,10 @@ int dg_dip_create_slot(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off, 
 int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
     if (!ctx || n < 0 || (n > 0 && !ds)) return DG_ERR_ARG;
     DG_CUDA(ctx, cudaSetDevice(ctx->device));
+    EventBag bag;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    DG_CUDA(ctx, cudaEventCreate(&e0));
-    DG_CUDA(ctx, cudaEventCreate(&e1));
+    DG_CUDA(ctx, bag.make(&e0));
+    DG_CUDA(ctx, bag.make(&e1));
     std::vector<cudaEvent_t> done((size_t)n, nullptr);
     int rc = DG_OK;
     int64_t ctas = 0;
@@ -2100,8 +2130,8 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
         DG_CUDA(ctx, d_ta.upload(h_ta.data(), h_ta.size(), ctx->stream));
         DG_CUDA(ctx, d_map.upload(h_map.data(), h_map.size(), ctx->stream));
         cudaEvent_t f0 = nullptr, swept = nullptr;
-        DG_CUDA(ctx, cudaEventCreate(&f0));
-        DG_CUDA(ctx, cudaEventCreate(&swept));
+        DG_CUDA(ctx, bag.make(&f0));
+        DG_CUDA(ctx, bag.make(&swept));
         const Plan4& q = ds[0]->p4;
         const void* fn = sweep4_many_fn(q.shape.slog, q.rc);
         const size_t smem = sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
@@ -2130,8 +2160,6 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
         DG_CUDA(ctx, cudaEventElapsedTime(&tm, swept, e1));
         if (wall_ms) *wall_ms = ms;
         for (int32_t i = 0; i < n; ++i) { ds[i]->fused_ms = fm; ds[i]->group_trace_ms = tm; ds[i]->ran = true; ds[i]->checks = false; ds[i]->launches = i == 0 ? 5 : 0; }
-        cudaEventDestroy(f0); cudaEventDestroy(swept);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
         return DG_OK;
     }
     if (fused) {
@@ -2144,7 +2172,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
             d->want_prof = false;
             DG_CUDA(ctx, cudaStreamWaitEvent(d->stream, e0, 0));
             if (int r = dip_run_pre(ctx, d, false)) { rc = r; break; }           // resets + pair scores, on the problem's stream
-            DG_CUDA(ctx, cudaEventCreateWithFlags(&done[(size_t)i], cudaEventDisableTiming));
+            DG_CUDA(ctx, bag.make(&done[(size_t)i], cudaEventDisableTiming));
             DG_CUDA(ctx, cudaEventRecord(done[(size_t)i], d->stream));
             DG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, done[(size_t)i], 0));
             if (v4) fill_sweep4_args(d, h_args4[(size_t)i], false); else fill_sweep_args(d, h_args[(size_t)i]);
@@ -2159,7 +2187,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
             else DG_CUDA(ctx, d_args.upload(h_args.data(), h_args.size(), ctx->stream));
             DG_CUDA(ctx, d_map.upload(h_map.data(), h_map.size(), ctx->stream));
             const int2* pm = d_map.p;
-            DG_CUDA(ctx, cudaEventCreate(&f0));
+            DG_CUDA(ctx, bag.make(&f0));
             if (v4) {
                 const Plan4& q = ds[0]->p4;
                 const void* fn = sweep4_many_fn(q.shape.slog, q.rc);
@@ -2177,7 +2205,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
                 DG_CUDA(ctx, cudaEventRecord(f0, ctx->stream));
                 DG_CUDA(ctx, cudaLaunchKernel(fn, dim3((unsigned)h_map.size()), dim3(DIP_THREADS), args, DIP_SMEM_BYTES, ctx->stream));
             }
-            DG_CUDA(ctx, cudaEventCreate(&swept));
+            DG_CUDA(ctx, bag.make(&swept));
             DG_CUDA(ctx, cudaEventRecord(swept, ctx->stream));
             for (int32_t i = 0; i < n && !rc; ++i) {
                 dg_dip* d = ds[i];
@@ -2199,10 +2227,6 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
             DG_CUDA(ctx, cudaEventElapsedTime(&fm, f0, swept));
             for (int32_t i = 0; i < n; ++i) ds[i]->fused_ms = fm;
         }
-        if (f0) cudaEventDestroy(f0);
-        if (swept) cudaEventDestroy(swept);
-        for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
         return rc;
     }
     for (int32_t i = 0; i < n && !rc; ++i) {
@@ -2210,7 +2234,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
         DG_CUDA(ctx, cudaStreamWaitEvent(ds[i]->stream, e0, 0));
         rc = dg_dip_run(ctx, ds[i], 0);
         if (rc) break;
-        DG_CUDA(ctx, cudaEventCreateWithFlags(&done[(size_t)i], cudaEventDisableTiming));
+        DG_CUDA(ctx, bag.make(&done[(size_t)i], cudaEventDisableTiming));
         DG_CUDA(ctx, cudaEventRecord(done[(size_t)i], ds[i]->stream));
         DG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, done[(size_t)i], 0));
     }
@@ -2219,8 +2243,6 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
     float ms = 0.f;
     if (!rc) DG_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
     if (wall_ms) *wall_ms = ms;
-    for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }
 

@@ -25,7 +25,7 @@ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
     p = DipPlan();
-    if (g.n_levels < 1 || g.R < 0 || !g.level_off || !g.adj_off) { p.error = "bad arguments"; return false; }
+    if (g.n_levels < 1 || g.R < 0 || !g.level_off || !g.adj_off || !g.col_off) { p.error = "bad arguments"; return false; }
     const int L = g.n_levels;
     p.L = L; p.R = g.R;
     p.level_off.assign(g.level_off, g.level_off + L + 1);
@@ -41,6 +41,8 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
         p.kmax = std::max(p.kmax, k);
     }
     if (g.adj_off[0] != 0) { p.error = "adj_off[0] must be 0"; return false; }
+    if (g.adj_off[V] < 0 || (g.adj_off[V] > 0 && (!g.adj_dst || !g.adj_w))) { p.error = "adj_dst / adj_w missing"; return false; }
+    if (g.col_off[0] != 0 || g.col_off[V] < 0 || (g.col_off[V] > 0 && (!g.col_val || !g.colour_is_hom))) { p.error = "col_val / colour_is_hom missing"; return false; }
     const int NT = n_threads();
     (void)NT;
     std::atomic<int> bad(0);      // 1 adj_off, 2 edge span, 3 colour id
@@ -61,6 +63,7 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
             for (int64_t e = g.adj_off[u]; e < g.adj_off[u + 1]; ++e) {
                 const int32_t v = g.adj_dst[e];
                 if (v < nlo || v >= nhi) { bad = 2; break; }
+                if (g.adj_w[e] > 1) { bad = 4; break; }            // weights are 0 / 1 (ExpandedGraph: lane edge / recombination edge)
                 ++p.in_off[(size_t)v + 1];
             }
         }
@@ -68,6 +71,7 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
     }
     if (bad == 1) { p.error = "adj_off not monotone"; return false; }
     if (bad == 2) { p.error = "edge does not span exactly one level"; return false; }
+    if (bad == 4) { p.error = "edge weight above 1"; return false; }
     p.cell_updates = cell_updates;
     for (int32_t v = 0; v < V; ++v) {
         p.max_indeg = std::max(p.max_indeg, p.in_off[(size_t)v + 1]);
@@ -89,6 +93,20 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
                     p.in_dst[slot] = (uint16_t)(v - hi);
                 }
         }
+    }
+
+    // Parallel edges u -> v of DIFFERENT weight: their candidates reach one destination cell from two layers of the same
+    // source pair; on a tie the reference keeps whichever its racing relax loop (approximator.cpp:627-701, `omp for
+    // collapse(3) schedule(guided)`) writes first — the result depends on thread timing, there is nothing to be
+    // bit-exact with.  (The reference's own front end never builds such edges; same-weight duplicates are fine: identical
+    // candidates.)  In-edges are grouped by destination in ascending source position, so such a pair is adjacent.
+    {
+        std::atomic<int> mixed(0);
+#pragma omp parallel for schedule(static) num_threads(NT)
+        for (int32_t v = 0; v < V; ++v)
+            for (int32_t e = p.in_off[v] + 1; e < p.in_off[(size_t)v + 1]; ++e)
+                if ((p.in_edge[e] & IN_POS_MASK) == (p.in_edge[(size_t)e - 1] & IN_POS_MASK) && p.in_edge[e] != p.in_edge[(size_t)e - 1]) mixed = 1;
+        if (mixed) { p.error = "parallel edges of differing weight between one vertex pair (the reference's tie-break is thread-order dependent for them)"; return false; }
     }
 
     // ---- per-transition colour masks (approximator.cpp:431-453 + :269-311 as popcounts) ----
@@ -278,7 +296,8 @@ void plan_tasks(DipPlan& p, const SweepShape& sh) {
     for (int l = 0; l < T; ++l) {
         const int64_t n_in = nin_of(l);
         if (rec_staged[l] || rec_inplace[l]) { p.rec_off[l] = (int64_t)rec_total; rec_total += rec_bytes[l]; }
-        if (p.lvlW[l] > 0 && n_in <= sh.delta_max_in && (p.delta_elems + n_in * n_in) * 2 <= sh.delta_budget) {
+        // (u16 pair scores: a transition with more than 65535 colours takes the on-the-fly masks, whose delta is an int)
+        if (p.lvlW[l] > 0 && (int64_t)p.lvlW[l] * 64 <= 65535 && n_in <= sh.delta_max_in && (p.delta_elems + n_in * n_in) * 2 <= sh.delta_budget) {
             p.delta_off[l] = p.delta_elems;
             p.delta_elems += (int64_t)align_up((size_t)(n_in * n_in), 8);
             p.delta_list.push_back(l);

@@ -18,7 +18,7 @@
  * order so level l owns ids [level_off[l], level_off[l+1]) and a vertex's position in its level
  * is id - level_off[l]; every edge goes from level l to level l+1.
  *
- * Parity pin: tests/test_oracle_pin.py checks this file against the reference binary's own
+ * Parity pin: tests/test_dp_diploid_cpu.py checks this file against the reference binary's own
  * per-level DP checksums, sink value, s_het and edge lists (oracle/ref_driver dumps).
  */
 #include <stdint.h>

@@ -137,6 +137,18 @@ def test_cuda_edge_cases(ctx, oracle_mod):
     assert_dip_equal(oracle_dip(oracle_mod, g, 2), o)
 
 
+def test_cuda_rejects_malformed_input(ctx):
+    """dg_dip_create returns DG_ERR_ARG (no launch) for weights above 1 and for parallel edges of differing weight."""
+    from dipgenie_b200.cuda_api import DipGenieCudaError
+    heavy = LevelGraph([0, 1, 3, 4], [0, 2, 3, 4, 4], [1, 2, 3, 3], [0, 2, 0, 0], [0, 0, 0, 0, 0], [], [0])
+    mixed = LevelGraph([0, 1, 2, 3], [0, 2, 3, 3], [1, 1, 2], [0, 1, 0], [0, 0, 0, 0], [], [0])
+    for bad, what in ((heavy, "weight above 1"), (mixed, "parallel edges")):
+        with pytest.raises(DipGenieCudaError, match=what):
+            ctx.dip_create(bad, 2)
+        with pytest.raises(DipGenieCudaError, match=what):
+            ctx.dp_diploid(bad, 2)
+
+
 def test_cuda_wide_levels_use_many_ctas(ctx, oracle_mod):
     """Widths large enough that transitions are spread over the whole grid and closed by the counter barrier."""
     g = synth.lane_panel_graph(11, n_lanes=72, n_blocks=8, rec_per_block=3, p_colour=0.2, n_colours=500)

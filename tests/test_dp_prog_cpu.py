@@ -69,3 +69,19 @@ def test_program_lane_panels(oracle_mod, dp_emu4):
                 assert lanes * lanes > 1024
                 continue
             assert_dip_equal(ref, o)
+
+
+def test_planner_rejects_what_the_kernels_cannot_take(dp_emu4, dp_emu):
+    """C-ABI input validation (dp_prep.cpp: build_dip_plan): weights above 1, and parallel edges of differing weight —
+    the reference resolves their ties by thread timing (approximator.cpp:627-701), so there is nothing to be exact with."""
+    ok = LevelGraph([0, 1, 3, 4], [0, 2, 3, 4, 4], [1, 2, 3, 3], [0, 1, 0, 0], [0, 0, 0, 0, 0], [], [0])
+    assert dp_emu4.dp_diploid(ok, 2) is not None
+    heavy = LevelGraph([0, 1, 3, 4], [0, 2, 3, 4, 4], [1, 2, 3, 3], [0, 2, 0, 0], [0, 0, 0, 0, 0], [], [0])
+    mixed = LevelGraph([0, 1, 2, 3], [0, 2, 3, 3], [1, 1, 2], [0, 1, 0], [0, 0, 0, 0], [], [0])
+    same = LevelGraph([0, 1, 2, 3], [0, 2, 3, 3], [1, 1, 2], [1, 1, 0], [0, 0, 0, 0], [], [0])     # duplicates of equal weight are fine
+    assert dp_emu4.dp_diploid(same, 2) is not None
+    for bad in (heavy, mixed):
+        with pytest.raises(RuntimeError):
+            dp_emu4.dp_diploid(bad, 2)
+        with pytest.raises(RuntimeError):
+            dp_emu.dp_diploid(bad, 2)

@@ -89,3 +89,24 @@ def test_two_processes_two_gpus():
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert "row-sharded OK" in p.stdout
+
+
+def test_dead_peer_costs_one_timeout_not_one_per_level(ctx, monkeypatch):
+    """A rank whose peer never runs gives up at its first cross-GPU wait, flags the run (sticky: no later wait spins,
+    no further pushes) and dg_dip_result fails loudly — hundreds of wide levels must not cost hundreds of timeouts."""
+    import time
+    from dipgenie_b200.cuda_api import DipGenieCudaError
+    monkeypatch.setenv("DG_SHARD_TIMEOUT_MS", "300")
+    g = synth.lane_panel_graph(5, n_lanes=48, n_blocks=60, rec_per_block=2, p_colour=0.2, n_colours=256)   # ~240 wide levels
+    probs = ctx.dip_sharded_in_process(g, 3, 2, 4)
+    try:
+        for p in probs:
+            p.shard_arm()
+        t0 = time.perf_counter()
+        probs[0].run()                        # rank 1 is never launched
+        with pytest.raises(DipGenieCudaError, match="timed out"):
+            probs[0].result()
+        assert time.perf_counter() - t0 < 5.0
+    finally:
+        for p in probs:
+            p.close()
