@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--batch", type=int, default=22, help="samples per GPU in the end-to-end batch call (22-sample study)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--skip-e2e", action="store_true", help="diagnostics: no host-buffer batch calls before the resident group (the line then carries no e2e)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
@@ -262,7 +263,7 @@ def main():
     # end-to-end through the host-buffer C-ABI batch call (planning, H2D, kernels, D2H inside the timed region)
     graphs = [samples[i % len(samples)] for i in range(max(1, args.batch))]
     e2e_t, single_t = [], []
-    for i in range(args.e2e_steps + 1):
+    for i in range(0 if args.skip_e2e else args.e2e_steps + 1):
         flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -278,6 +279,9 @@ def main():
         if i == 0:
             batch_values = [r["value"] for r in res]
         assert [r["value"] for r in res] == batch_values
+    if args.skip_e2e:
+        e2e_t, single_t, batch_values = [float("nan")], [float("nan")], []
+        o1 = ctx.dp_diploid(g, args.R)
     e2e_value = o1["value"]
     e2e_s, single_s = float(np.mean(e2e_t)), float(np.mean(single_t))
     print("bench: e2e batch calls (s): %s; single-sample calls (s): %s" % ([round(x, 3) for x in e2e_t], [round(x, 3) for x in single_t]), file=sys.stderr)

@@ -268,7 +268,8 @@ struct TraceView {
     const uint64_t* masks;
     const int64_t* pred_off;
     // level-program engine (dp_prog.h): codes exist for multi-candidate cells only, one u16 per (layer, slot), the
-    // winner's ordinal in (e1,e2) order as 1023 - (code & 1023); vinfo == nullptr selects the task-stream layout
+    // winner's ordinal in (e1,e2) order as 1023 - (code & 1023) (cells of more than 1024 candidates: the ordinal itself);
+    // vinfo == nullptr selects the task-stream layout
     const uint32_t* vinfo = nullptr;    // [V] rank in class | class << 30
     const uint32_t* lvl_n1 = nullptr;   // [L] S1 vertices of the level
     const uint32_t* lvl_m = nullptr;    // [L] M vertices of the level
@@ -294,7 +295,7 @@ DG_HD bool trace_step(const TraceView& v, const PredT* pred, int l, TraceState& 
             const int64_t slot = multi_slot_of(v.vinfo[mid + s.i2], v.vinfo[mid + s.j2], n1, m);
             const int64_t nm = 2 * (int64_t)m * n1 + (int64_t)m * m;
             const uint32_t raw = (uint32_t)pred[v.pred_off[l + 1] + (int64_t)s.r * nm + slot];
-            ord = (int32_t)(1023u - (raw & 1023u));
+            ord = d1 * d2 > 1024 ? (int32_t)raw : (int32_t)(1023u - (raw & 1023u));     // (dp_prog.h: PROG_KEY_CAND)
             if (ord >= d1 * d2) ord = d1 * d2 - 1;       // (codes of dead cells are arbitrary; only live paths are ever followed)
         }
         const int32_t o1 = ord / d2, o2 = ord - o1 * d2;

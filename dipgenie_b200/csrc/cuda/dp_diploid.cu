@@ -1438,8 +1438,8 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     // the program: zero (section padding), then one CTA per transition
     DG_CUDA(ctx, cudaEventRecord(d->ev[0], s));
     DG_CUDA(ctx, cudaMemsetAsync(d->v4_prog.p, 0, (size_t)q.prog_bytes + 16, s));
-    if (q.gpad > 0 && !q.full.wide_list.empty() + q.n_relocate > 0)
-        fill_dead_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(d->tile0.p, (long long)q.gpad);      // the two padding layers of the HBM tile
+    if (!q.full.wide_list.empty() + q.n_relocate > 0)      // the two padding layers of every cell of the HBM tile (the sweep only writes layers >= 0)
+        fill_dead_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(d->tile0.p, (long long)q.gtile_cells);
     Fill4Args fa;
     fa.l0 = 0; fa.l1 = L - 1; fa.level_off = d->level_off.p; fa.in_off = d->in_off.p; fa.in_edge = d->in_edge.p;
     fa.cls_list = d->v4_cls.p; fa.mpre = d->v4_mpre.p; fa.mpre_off = d->v4_mpre_off.p;
@@ -1609,7 +1609,7 @@ static void fill_sweep4_args(const dg_dip* d, Sweep4Args& a, bool check) {
     const Plan4Dir& dir = check ? q.full : q.timed;         // the checksum variant folds every level, idle transitions included
     a.dir = check ? d->v4_dir_full.p : d->v4_dir.p; a.wide_list = check ? d->v4_wide_full.p : d->v4_wide.p;
     a.n_trans = dir.n; a.n_wide = (int32_t)dir.wide_list.size();
-    a.prog = d->v4_prog.p; a.gtile = d->tile0.p; a.gpad = (long long)q.gpad; a.hkk = (long long)q.hstride * q.hstride;
+    a.prog = d->v4_prog.p; a.gtile = d->tile0.p; a.gcs = (long long)q.gcs;
     a.pred = d->v4_pred.p; a.counter = d->counter.p; a.level_sum = d->level_sum.p; a.level_live = d->level_live.p;
     a.sink = d->v4_sink.p; a.R = p.R; a.nchunk = q.nchunk; a.grid = d->grid; a.ncw = d->v4_ncw;
     a.slot_bytes = q.shape.slot_bytes; a.nslot = q.shape.nslot; a.m_nchunk = make_magic((uint32_t)q.nchunk);

@@ -129,6 +129,7 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
         mp += (int64_t)m + 1;
     }
     q.mpre.assign((size_t)mp, 0);
+    std::vector<uint32_t> lvl_dmax((size_t)L, 0);      // largest in-degree of the level
     uint64_t max_cand = 0;
 #pragma omp parallel for schedule(static) reduction(max : max_cand)
     for (int l = 0; l < L; ++l) {
@@ -162,6 +163,7 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
         for (uint32_t x = 0; x < (uint32_t)(hi - lo) - n1 - m; ++x) q.vinfo[(size_t)lo + list[n1 + m + x]] = x | (2u << 30);
         P[m] = dm;
         q.lvl_dm[l] = dm;
+        lvl_dmax[l] = dmax;
         max_cand = std::max<uint64_t>(max_cand, (uint64_t)dmax * dmax);
     }
     q.max_cand = (uint32_t)std::min<uint64_t>(max_cand, 0xFFFFFFFFu);
@@ -183,7 +185,9 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
         const bool relocate = q.tflags[l] & PF_RELOCATE;
         const ProgCounts n = prog_counts(c, relocate);
         const bool both_smem = (q.tflags[l] & PF_SRC_SMEM) && (q.tflags[l] & PF_DST_SMEM);
-        const bool compact = both_smem && (int64_t)p.lvlW[l] * 64 <= (int64_t)PROG_COMPACT_DELTA;
+        // (a cell of more than PROG_KEY_CAND candidates needs the generic path's warp form: striped ordinals)
+        const bool compact = both_smem && (int64_t)p.lvlW[l] * 64 <= (int64_t)PROG_COMPACT_DELTA &&
+                             (uint64_t)lvl_dmax[(size_t)l + 1] * lvl_dmax[(size_t)l + 1] <= PROG_KEY_CAND;
         if (compact) q.tflags[l] |= PF_COMPACT;
         ProgHdr& h = q.hdr[l];
         h.k = (uint16_t)k; h.k2 = (uint16_t)k2;
@@ -217,6 +221,7 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
         d.off16 = (uint32_t)(q.prog_off[l] / 16);
         d.flags = q.tflags[l];
         d.level = l;
+        d.prog16 = (uint32_t)(bytes[l] / 16);
         if (bytes[l] + sizeof(ProgDir) <= (uint64_t)shape.slot_bytes) { d.flags |= PF_STAGED; d.stage_bytes = (uint32_t)bytes[l]; }
         else d.stage_bytes = (uint32_t)sizeof(ProgHdr);
         if ((d.flags & PF_SRC_SMEM) && (d.flags & PF_DST_SMEM)) ++q.n_smem_trans;
@@ -227,8 +232,8 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
     }
     schedule(q.full, shape.grid);
     schedule(q.timed, shape.grid);
-    q.gpad = 2 * (int64_t)q.hstride * q.hstride;
-    q.gtile_cells = q.gpad + (int64_t)q.RL * q.hstride * q.hstride;
+    q.gcs = (q.RL + 2 + 7) / 8 * 8;
+    q.gtile_cells = (int64_t)q.gcs * q.hstride * q.hstride;
     const int32_t last = p.level_off[L - 1];
     const uint32_t ls = q.vslot[last];
     q.sink_cell = ls * (uint32_t)(q.lvl_dom[L - 1] == 0 ? kn : q.hstride) + ls;

@@ -51,7 +51,8 @@ struct Plan4 {
     uint64_t prog_bytes = 0;
     int64_t pred_elems = 0;
     int32_t hstride = 1;                 // slots per row of the HBM tile
-    int64_t gpad = 0, gtile_cells = 0;   // HBM tile: gpad dead cells, then RL layers of hstride^2 cells
+    int32_t gcs = 0;                     // words per cell of the HBM tile (cell-major: 2 dead padding layers, RL layers, padded to 32 bytes)
+    int64_t gtile_cells = 0;             // words of the HBM tile: hstride^2 cells of gcs words
     int64_t n_smem_trans = 0;            // transitions with both levels in shared memory
     int64_t n_relocate = 0, n_skipped = 0;
     uint64_t cells_written = 0, cells_total = 0;   // destination cells in the programs / of the levels (per layer)

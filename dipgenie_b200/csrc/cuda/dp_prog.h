@@ -54,7 +54,11 @@ constexpr int32_t V4_DEAD = INT32_MIN;
 constexpr int V4_SHIFT = KEY_SHIFT;                       // 10
 constexpr uint32_t V4_ORD_MASK = (1u << V4_SHIFT) - 1u;   // 1023
 constexpr uint32_t PROG_BIG_MIN = 12;                     // multi cells with this many candidates go to the warp form
-constexpr uint32_t PROG_MAX_CAND = 1024;                  // candidates per cell the packed ordinal can hold
+constexpr uint32_t PROG_KEY_CAND = 1024;                  // candidates per cell whose ordinal fits the packed key (code = low 16 key bits)
+constexpr uint32_t PROG_MAX_CAND = 32768;                 // most candidates of a cell: above PROG_KEY_CAND the warp form keeps the ROUND
+                                                          // (ordinal / 32) in the key, the winner's lane comes from a ballot, and the code
+                                                          // is the plain ordinal (panels of up to 181 walks: a recombination x recombination
+                                                          // cell has in-degree^2 candidates)
 constexpr uint32_t PROG_COMPACT_DELTA = 1023;             // compact descriptors: at most this many colours on the two levels
 
 enum : uint32_t {
@@ -75,7 +79,8 @@ struct ProgDir {
     uint32_t wait_target;
     uint32_t flags;
     int32_t level;         // transition level -> level + 1 (the timed directory skips the transitions with nothing to do)
-    uint32_t rsv[3];
+    uint32_t prog16;       // size of the whole program, units of 16 bytes (the producer prefetches unstaged programs into L2)
+    uint32_t rsv[2];
 };
 static_assert(sizeof(ProgDir) == 32, "ProgDir layout");
 

@@ -135,8 +135,8 @@ struct Sweep4Args {
     const int32_t* wide_list;     // transitions every CTA takes part in
     int32_t n_trans, n_wide;
     const uint8_t* prog;
-    int32_t* gtile;               // HBM tile: gpad dead cells, then RL layers of hkk = hstride^2 cells (in place: dp_prog.h)
-    long long gpad, hkk;
+    int32_t* gtile;               // HBM tile, CELL-major: hstride^2 cells of gcs words — two dead padding layers, then the RL layers
+    long long gcs;                //   (in place: dp_prog.h); a chunk of layers of a cell is 1-2 sectors whichever way the block runs
     uint16_t* pred;
     unsigned int* counter;        // [0] level arrivals, [1] first barrier that timed out (level + 1), sticky
     unsigned long long* level_sum;
@@ -155,6 +155,9 @@ struct Sweep4Args {
     unsigned long long timeout_ns;
 };
 
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bar_named(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 template <int IMM> __device__ __forceinline__ int32_t lds_imm(uint32_t a) {
@@ -191,10 +194,11 @@ struct Lvl4 {
     const uint8_t* copy_p; const uint8_t* cell_p; const uint8_t* cand_p; const uint8_t* big_p; const uint8_t* dead_p;   // generic pointers (slot or HBM)
     uint32_t k, k2, n_copy, n_multi, n_big, n_dead;
     uint32_t src32, dst32;                // shared-memory tile: address of padding layer -2
-    const int32_t* gsrc; int32_t* gdst;   // HBM tile: address of layer 0
-    long long kk, kk2;                    // layer strides there
+    int32_t* gt;                          // HBM tile (cell-major): layer r of cell c at gt[c * cs + 2 + r]
+    long long cs;
     uint16_t* pl;                         // codes of level l+1, [layer][slot]
-    int level, R, nchunk;
+    int level, R, nchunk, rc;
+    uint32_t m_nchunk;                    // magic of nchunk (0: one chunk)
     bool l1;                              // HBM-tile loads may be served by L1 (the problem runs on one SM)
     const ProgLevelIn* in;                // checksum variant only
 };
@@ -221,13 +225,13 @@ __device__ __forceinline__ void load_layers(const Lvl4& c, int r0, uint32_t src,
     if (SS) {
         lds_layers<SLOG, RC>(c.src32 + ((((uint32_t)(r0 + 2) - w) << SLOG) + src) * 4u, v);
     } else {
-        const int32_t* p = c.gsrc + ((long long)(r0 - (int)w) * c.kk + (long long)src);
+        const int32_t* p = c.gt + ((long long)src * c.cs + (long long)(r0 + 2 - (int)w));
         if (c.l1) {              // one CTA per problem: the cells were written by this SM, its L1 is coherent with them
 #pragma unroll
-            for (int q = 0; q < RC; ++q) v[q] = p[(long long)q * c.kk];
+            for (int q = 0; q < RC; ++q) v[q] = p[q];
         } else {
 #pragma unroll
-            for (int q = 0; q < RC; ++q) v[q] = __ldcg(p + (long long)q * c.kk);
+            for (int q = 0; q < RC; ++q) v[q] = __ldcg(p + q);
         }
     }
 }
@@ -236,13 +240,22 @@ __device__ __forceinline__ void store_layers(const Lvl4& c, int r0, uint32_t dst
     if (DS) {
         sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, v);
     } else {
-        int32_t* p = c.gdst + ((long long)r0 * c.kk2 + (long long)dst);
-        if (c.l1) {
+        int32_t* p = c.gt + ((long long)dst * c.cs + (long long)(r0 + 2));
+        if constexpr (RC % 2 == 0) {          // r0 and RC even, cells 32-byte aligned: 8-byte stores
+            int2* p2 = reinterpret_cast<int2*>(p);
+            if (c.l1) {
 #pragma unroll
-            for (int q = 0; q < RC; ++q) p[(long long)q * c.kk2] = v[q];
+                for (int q = 0; q < RC; q += 2) p2[q >> 1] = make_int2(v[q], v[q + 1]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < RC; q += 2) __stcg(p2 + (q >> 1), make_int2(v[q], v[q + 1]));
+            }
+        } else if (c.l1) {
+#pragma unroll
+            for (int q = 0; q < RC; ++q) p[q] = v[q];
         } else {
 #pragma unroll
-            for (int q = 0; q < RC; ++q) __stcg(p + (long long)q * c.kk2, v[q]);
+            for (int q = 0; q < RC; ++q) __stcg(p + q, v[q]);
         }
     }
 }
@@ -260,12 +273,13 @@ __device__ __forceinline__ void fold_copy(Fold4& f, const ProgLevelIn& in, int R
     in_edge_at(in, i2, 0, i, wi); in_edge_at(in, j2, 0, j, wj);
     for (int q = 0; q < n; ++q) fold_pos(f, R, in.k2, r0 + q, i2, j2, v[q], i, j);
 }
-__device__ __forceinline__ void fold_multi(Fold4& f, const ProgLevelIn& in, int R, uint32_t t, int r0, const int32_t* key, int n) {
+// (`ord` != nullptr: the ordinals themselves — cells of more than PROG_KEY_CAND candidates)
+__device__ __forceinline__ void fold_multi(Fold4& f, const ProgLevelIn& in, int R, uint32_t t, int r0, const int32_t* key, int n, const uint32_t* ord = nullptr) {
     const MultiCell mc = multi_cell(in, t);
     for (int q = 0; q < n; ++q) {
         const int32_t val = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
         if (val < 0 || r0 + q > R) continue;
-        const uint32_t o = V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
+        const uint32_t o = ord ? ord[q] : V4_ORD_MASK - ((uint32_t)key[q] & V4_ORD_MASK);
         const uint32_t e1 = o / mc.d2, e2 = o - e1 * mc.d2;
         uint32_t i, wi, j, wj;
         in_edge_at(in, mc.i2, e1, i, wi); in_edge_at(in, mc.j2, e2, j, wj);
@@ -273,115 +287,142 @@ __device__ __forceinline__ void fold_multi(Fold4& f, const ProgLevelIn& in, int 
     }
 }
 
-// 32 copy cells, one thread each: dst = src shifted by w layers, plus delta.
-template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
-__device__ __forceinline__ void copy_block(const Lvl4& c, uint32_t blk, int lane, Fold4& f) {
-    const uint32_t t = blk * 32u + (uint32_t)lane;
-    const bool active = t < c.n_copy;
-    CopyDesc d = {0u, 0u, 0u, 0u};
-    if (active) d = ld_copy<COMPACT>(c.copy_p, t);
-    const int32_t add = (int32_t)(d.delta << V4_SHIFT);
-    for (int ch = 0; ch < c.nchunk; ++ch) {
-        const int r0 = ch * RC;
-        int32_t v[RC];
-        load_layers<SLOG, RC, SS>(c, r0, d.src, d.w, v);
-#pragma unroll
-        for (int q = 0; q < RC; ++q) v[q] += add;
-        if (active) {
-            store_layers<SLOG, RC, DS>(c, r0, d.dst, v);
-            if (CHECK) fold_copy(f, *c.in, c.R, t, r0, v, RC);
-        }
-    }
+// The generic path works on ITEMS = (cell, chunk of RC layers): a warp takes 32 items, so a block of cells is spread over
+// nchunk times as many lanes and nothing loops over the chunks — every global access of an item (descriptor, candidate
+// descriptors, layers) is one link of a short chain of L2 round trips, and the chain is the critical path of the level.
+struct Item { uint32_t t; int r0; bool in; };
+__device__ __forceinline__ Item item_of(const Lvl4& c, uint32_t blk, int lane, uint32_t n_cells) {
+    const uint32_t x = blk * 32u + (uint32_t)lane;
+    const uint32_t t = c.m_nchunk ? __umulhi(x, c.m_nchunk) : x;
+    return {t, (int)(x - t * (uint32_t)c.nchunk) * c.rc, t < n_cells};
 }
 
-// 32 multi cells, one thread each, candidates in a loop (cells of PROG_BIG_MIN candidates or more belong to the warp form).
+// 32 copy items: dst = src shifted by w layers, plus delta.
+template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
+__device__ __forceinline__ void copy_block(const Lvl4& c, uint32_t blk, int lane, Fold4& f) {
+    const Item it = item_of(c, blk, lane, c.n_copy);
+    if (!it.in) return;
+    const CopyDesc d = ld_copy<COMPACT>(c.copy_p, it.t);
+    const int32_t add = (int32_t)(d.delta << V4_SHIFT);
+    int32_t v[RC];
+    load_layers<SLOG, RC, SS>(c, it.r0, d.src, d.w, v);
+#pragma unroll
+    for (int q = 0; q < RC; ++q) v[q] += add;
+    store_layers<SLOG, RC, DS>(c, it.r0, d.dst, v);
+    if (CHECK) fold_copy(f, *c.in, c.R, it.t, it.r0, v, RC);
+}
+
+// 32 multi items, candidates two at a time: the two descriptors are fetched first, then their 2 x RC layers, so a cell
+// of n candidates costs n / 2 chains of two round trips instead of n (cells of PROG_BIG_MIN candidates or more belong to
+// the warp form).
 template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
 __device__ __forceinline__ void multi_block(const Lvl4& c, uint32_t blk, int lane, Fold4& f) {
-    const uint32_t t = blk * 32u + (uint32_t)lane;
+    const Item it = item_of(c, blk, lane, c.n_multi);
     CellDesc cd = {0u, 0u, 0u};
-    if (t < c.n_multi) cd = ld_cell<COMPACT>(c.cell_p, t);
+    if (it.in) cd = ld_cell<COMPACT>(c.cell_p, it.t);
     const uint32_t n = cd.n >= PROG_BIG_MIN ? 0u : cd.n;
     const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n);
     if (nmax == 0) return;
-    for (int ch = 0; ch < c.nchunk; ++ch) {
-        const int r0 = ch * RC;
-        int32_t key[RC];
+    int32_t key[RC];
 #pragma unroll
-        for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
-        for (uint32_t o = 0; o < nmax; ++o) {
-            if (o < n) {
-                const CandDesc e = ld_cand<COMPACT>(c.cand_p, cd.cand_off + o);
-                const int32_t add = (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - o));
-                int32_t v[RC];
-                load_layers<SLOG, RC, SS>(c, r0, e.src, e.w, v);
+    for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
+    for (uint32_t o = 0; o < nmax; o += 2u) {
+        const bool p0 = o < n, p1 = o + 1u < n;
+        CandDesc e0 = {0u, 0u, 0u}, e1 = {0u, 0u, 0u};
+        if (p0) e0 = ld_cand<COMPACT>(c.cand_p, cd.cand_off + o);
+        if (p1) e1 = ld_cand<COMPACT>(c.cand_p, cd.cand_off + o + 1u);
+        int32_t v0[RC], v1[RC];
 #pragma unroll
-                for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
-            }
+        for (int q = 0; q < RC; ++q) { v0[q] = V4_DEAD; v1[q] = V4_DEAD; }
+        if (p0) load_layers<SLOG, RC, SS>(c, it.r0, e0.src, e0.w, v0);
+        if (p1) load_layers<SLOG, RC, SS>(c, it.r0, e1.src, e1.w, v1);
+        // (a lane without the candidate keeps DEAD + something small: never the maximum of a cell that has candidates)
+        const int32_t a0 = (int32_t)((e0.delta << V4_SHIFT) + (V4_ORD_MASK - o)), a1 = (int32_t)((e1.delta << V4_SHIFT) + (V4_ORD_MASK - o - 1u));
+#pragma unroll
+        for (int q = 0; q < RC; ++q) key[q] = max(key[q], max(v0[q] + a0, v1[q] + a1));
+    }
+    if (n) {
+        uint16_t* pl = c.pl + ((size_t)it.r0 * c.n_multi + it.t);
+        int32_t val[RC];
+#pragma unroll
+        for (int q = 0; q < RC; ++q) {
+            val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
+            pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
         }
-        if (n) {
-            uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
-            int32_t val[RC];
-#pragma unroll
-            for (int q = 0; q < RC; ++q) {
-                val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
-                pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
-            }
-            store_layers<SLOG, RC, DS>(c, r0, cd.dst, val);
-            if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
-        }
+        store_layers<SLOG, RC, DS>(c, it.r0, cd.dst, val);
+        if (CHECK) fold_multi(f, *c.in, c.R, it.t, it.r0, key, RC);
     }
 }
 
-// One big cell per warp: lanes over candidates, 32 at a time, then one REDUX.MAX per layer.
+// One (big cell, chunk) per warp: lanes over candidates, 32 at a time, then one REDUX.MAX per layer.  A cell of more than
+// PROG_KEY_CAND candidates keeps the ROUND o / 32 in the key's ordinal field: a lane's candidates come in ascending round,
+// the warp maximum carries the earliest round of the best value, and among the lanes that hold it the lowest one has the
+// smallest ordinal round * 32 + lane — the same first strict maximum in (e1,e2) order, for up to PROG_MAX_CAND candidates.
 template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
-__device__ __forceinline__ void big_cell(const Lvl4& c, uint32_t u, int lane, Fold4& f) {
+__device__ __forceinline__ void big_cell(const Lvl4& c, uint32_t x, int lane, Fold4& f) {
+    const uint32_t u = c.m_nchunk ? __umulhi(x, c.m_nchunk) : x;
+    const int r0 = (int)(x - u * (uint32_t)c.nchunk) * c.rc;
     const uint32_t t = reinterpret_cast<const uint32_t*>(c.big_p)[u];
     const CellDesc cd = ld_cell<COMPACT>(c.cell_p, t);
-    for (int ch = 0; ch < c.nchunk; ++ch) {
-        const int r0 = ch * RC;
-        int32_t key[RC];
+    const bool striped = cd.n > PROG_KEY_CAND;
+    int32_t key[RC];
 #pragma unroll
-        for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
-        for (uint32_t o = (uint32_t)lane; o < cd.n; o += 32u) {
-            const CandDesc e = ld_cand<COMPACT>(c.cand_p, cd.cand_off + o);
-            const int32_t add = (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - o));
-            int32_t v[RC];
-            load_layers<SLOG, RC, SS>(c, r0, e.src, e.w, v);
+    for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
+    // (the next candidate's descriptor is fetched before this one's layers: two independent chains of loads)
+    CandDesc e = {0u, 0u, 0u};
+    if ((uint32_t)lane < cd.n) e = ld_cand<COMPACT>(c.cand_p, cd.cand_off + (uint32_t)lane);
+    for (uint32_t o = (uint32_t)lane; o < cd.n; o += 32u) {
+        CandDesc en = {0u, 0u, 0u};
+        if (o + 32u < cd.n) en = ld_cand<COMPACT>(c.cand_p, cd.cand_off + o + 32u);
+        const int32_t add = (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - (striped ? (o >> 5) : o)));
+        int32_t v[RC];
+        load_layers<SLOG, RC, SS>(c, r0, e.src, e.w, v);
 #pragma unroll
-            for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
-        }
+        for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
+        e = en;
+    }
+    int32_t val[RC];
+    uint32_t code[RC];
 #pragma unroll
-        for (int q = 0; q < RC; ++q) key[q] = __reduce_max_sync(0xFFFFFFFFu, key[q]);
-        if (lane == 0) {
-            uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
-            int32_t val[RC];
+    for (int q = 0; q < RC; ++q) {
+        const int32_t m = __reduce_max_sync(0xFFFFFFFFu, key[q]);
+        val[q] = (int32_t)((uint32_t)m & ~V4_ORD_MASK);
+        if (striped) {
+            const uint32_t who = __ballot_sync(0xFFFFFFFFu, key[q] == m);
+            code[q] = ((V4_ORD_MASK - ((uint32_t)m & V4_ORD_MASK)) << 5) | (uint32_t)(__ffs((int)who) - 1);
+        } else code[q] = (uint32_t)m & 0xFFFFu;
+    }
+    if (lane == 0) {
+        uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
 #pragma unroll
-            for (int q = 0; q < RC; ++q) {
-                val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
-                pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
-            }
-            store_layers<SLOG, RC, DS>(c, r0, cd.dst, val);
-            if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
+        for (int q = 0; q < RC; ++q) pl[(size_t)q * c.n_multi] = (uint16_t)code[q];
+        store_layers<SLOG, RC, DS>(c, r0, cd.dst, val);
+        if (CHECK) {
+            int32_t k2[RC];       // the fold decodes an ordinal from the key's low bits
+#pragma unroll
+            for (int q = 0; q < RC; ++q) k2[q] = val[q] | (int32_t)(striped ? 0u : (code[q] & V4_ORD_MASK));
+            fold_multi(f, *c.in, c.R, t, r0, k2, RC, striped ? code : nullptr);
         }
     }
 }
 
 template <int SLOG, int RC, bool DS>
 __device__ __forceinline__ void dead_block(const Lvl4& c, uint32_t blk, int lane) {
-    const uint32_t x = blk * 32u + (uint32_t)lane;
-    if (x >= c.n_dead) return;
-    const uint32_t dst = reinterpret_cast<const uint32_t*>(c.dead_p)[x];
+    const Item it = item_of(c, blk, lane, c.n_dead);
+    if (!it.in) return;
+    const uint32_t dst = reinterpret_cast<const uint32_t*>(c.dead_p)[it.t];
     int32_t v[RC];
 #pragma unroll
     for (int q = 0; q < RC; ++q) v[q] = V4_DEAD;
-    for (int ch = 0; ch < c.nchunk; ++ch) store_layers<SLOG, RC, DS>(c, ch * RC, dst, v);
+    store_layers<SLOG, RC, DS>(c, it.r0, dst, v);
 }
 
 // The work units of one transition, dealt round-robin to the (global) warps gw, gw + gstride, ...: heaviest first.
 template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
 __device__ __forceinline__ void run_level(const Lvl4& c, uint32_t gw, uint32_t gstride, int lane, Fold4& f) {
-    const uint32_t nmb = (c.n_multi + 31u) >> 5, ncb = (c.n_copy + 31u) >> 5, ndb = (c.n_dead + 31u) >> 5;
-    const uint32_t e0 = c.n_big, e1 = e0 + nmb, e2 = e1 + ncb, e3 = e2 + ndb;
+    const uint32_t nch = (uint32_t)c.nchunk;
+    const uint32_t nmb = (c.n_multi * nch + 31u) >> 5, ncb = (c.n_copy * nch + 31u) >> 5, ndb = (c.n_dead * nch + 31u) >> 5;
+    const uint32_t e0 = c.n_big * nch, e1 = e0 + nmb, e2 = e1 + ncb, e3 = e2 + ndb;
     for (uint32_t u = gw; u < e3; u += gstride) {
         if (u < e0) big_cell<SLOG, RC, SS, DS, COMPACT, CHECK>(c, u, lane, f);
         else if (u < e1) multi_block<SLOG, RC, SS, DS, COMPACT, CHECK>(c, u - e0, lane, f);
@@ -402,10 +443,9 @@ __device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_
     c.k = h.k; c.k2 = h.k2; c.n_copy = h.n_copy; c.n_multi = h.n_multi; c.n_big = h.n_big; c.n_dead = h.n_dead;
     const uint8_t* const pb = (flags & PF_STAGED) ? sb + sizeof(ProgDir) : a.prog + (size_t)d.off16 * 16;
     c.copy_p = pb + sizeof(ProgHdr); c.cell_p = pb + h.off_cell; c.cand_p = pb + h.off_cand; c.big_p = pb + h.off_big; c.dead_p = pb + h.off_dead;
-    c.level = l; c.R = a.R; c.nchunk = a.nchunk; c.l1 = a.grid == 1 && a.use_l1;
+    c.level = l; c.R = a.R; c.nchunk = a.nchunk; c.rc = RC; c.m_nchunk = a.m_nchunk; c.l1 = a.grid == 1 && a.use_l1;
     c.src32 = tile32; c.dst32 = tile32;
-    c.gsrc = a.gtile + a.gpad; c.gdst = a.gtile + a.gpad;
-    c.kk = a.hkk; c.kk2 = a.hkk;
+    c.gt = a.gtile; c.cs = a.gcs;
     c.pl = a.pred + h.pred_off;
     ProgLevelIn in;
     if (CHECK) in = level_in(*a.chk, l);
@@ -605,15 +645,21 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
         for (int32_t i0 = 0; i0 < n_my; i0 += 32) {
             int32_t lv = 0;
             uint4 f = make_uint4(0u, 0u, 0u, 0u);
+            uint32_t p16 = 0u;
             if (i0 + lane < n_my) {
                 lv = cta == 0 ? i0 + lane : __ldg(a.wide_list + i0 + lane);
                 f = __ldg(reinterpret_cast<const uint4*>(a.dir + lv));
+                p16 = __ldg(&a.dir[lv].prog16);
             }
             const int cnt = min(32, n_my - i0);
             for (int j = 0; j < cnt; ++j) {
                 const int32_t l = __shfl_sync(0xFFFFFFFFu, lv, j);
                 const uint32_t off16 = __shfl_sync(0xFFFFFFFFu, f.x, j), bytes = __shfl_sync(0xFFFFFFFFu, f.y, j);
+                const uint32_t fl = __shfl_sync(0xFFFFFFFFu, f.w, j), all16 = __shfl_sync(0xFFFFFFFFu, p16, j);
                 if (lane == 0) {
+                    // a program too large for a slot is read in place by the compute warps: bring it into L2 now, NS levels
+                    // ahead of its use (its first touch is otherwise a chain of cold DRAM reads inside the level)
+                    if (!(fl & PF_STAGED)) l2_prefetch_bulk(a.prog + (size_t)off16 * 16, min(all16, 16384u) * 16u);
                     if (!first_round) mbar_wait(smem_u32(empty + slot), use_parity);
                     const uint32_t bar = smem_u32(full + slot);
                     const uint32_t dst = smem_u32(slots + (size_t)slot * a.slot_bytes);
@@ -709,7 +755,7 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                     in_edge_at(in, i2, 0, i, wi); in_edge_at(in, j2, 0, j, wj);
                     const uint32_t dc = dst_cell(in, i2, j2);
                     for (int r = 0; r <= a.R; ++r) {
-                        const int32_t v = dsm ? lds_s32(tiles32 + (((uint32_t)(r + 2) << SLOG) + dc) * 4u) : __ldcg(a.gtile + a.gpad + (long long)r * a.hkk + dc);
+                        const int32_t v = dsm ? lds_s32(tiles32 + (((uint32_t)(r + 2) << SLOG) + dc) * 4u) : __ldcg(a.gtile + (long long)dc * a.gcs + 2 + r);
                         fold_pos(f, a.R, in.k2, r, i2, j2, v, i, j);
                     }
                 }
@@ -737,7 +783,7 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
         for (int r = tid; r <= a.R; r += CT) {
             int32_t v;
             if (a.last_smem) v = lds_s32(tiles32 + (((uint32_t)(r + 2) << SLOG) + a.sink_cell) * 4u);
-            else v = __ldcg(a.gtile + a.gpad + (long long)r * a.hkk + a.sink_cell);
+            else v = __ldcg(a.gtile + (long long)a.sink_cell * a.gcs + 2 + r);
             a.sink[r] = v;
         }
     }

@@ -2,6 +2,8 @@
 //   gfa_read -> Solver::read_gfa -> read_ip_reads -> compute_and_classify_anchors -> solve
 #include "pipeline.h"
 
+#include "../common/dgd_dump.h"
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -182,6 +184,16 @@ int run_pipeline(const Options& o, const Backend& be, RunSummary& sum, std::stri
     if (o.ploidy == 1) {
         rc = solve_haploid(P, be, err);
     } else {
+        // Tooling (bench.py's wide-panel workloads, tests): DG_DUMP_DIPIN=<file> writes the DP's input — the levelized graph
+        // this front end built — as a DGD1 container; DG_DUMP_ONLY=1 stops there.
+        if (const char* dump = getenv("DG_DUMP_DIPIN")) {
+            dgd::Writer w(dump);
+            if (!w.ok()) { err = std::string("cannot write ") + dump; return 1; }
+            w.put("level_off", P.level_off); w.put("adj_off", P.adj_off); w.put("adj_dst", P.adj_dst); w.put("adj_w", P.adj_w);
+            w.put("col_off", P.col_off); w.put("col_val", P.col_val);
+            w.put("colour_is_hom", P.ex.color_homo_bv);
+            if (getenv("DG_DUMP_ONLY")) { sum = P.sum; return 0; }
+        }
         // ---- device stage 3b: diploid DP + edge lists ----
         int32_t value = 0, s_het = 0, n1 = 0, n2 = 0;
         std::vector<int32_t> e1(2 * ((size_t)o.R + 2)), e2(2 * ((size_t)o.R + 2));

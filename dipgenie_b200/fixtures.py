@@ -46,6 +46,26 @@ def materialize_mhc(gold_dir: str, out_dir: str):
     return gfa, fa
 
 
+def materialize_mhc_replicated(gold_dir: str, out_dir: str, times: int):
+    """The MHC_4 panel with every walk written `times` times (4 x = 20 W-lines, 18 x = 90 W-lines — identical
+    lanes, the hardest case for the DP's tie-break under a different evaluation order) + the CHM13 reads
+    -> (gfa path, reads path).  Copy r of a walk is sample "<name>_r<r>" with the original haplotype index."""
+    z = np.load(os.path.join(gold_dir, "sketch_mhc4_chm13.npz"))
+    k = np.load(os.path.join(gold_dir, "mhc4_panel_links.npz"))
+    names = [s.decode() if isinstance(s, bytes) else str(s) for s in k["walk_sample"].tolist()]
+    H = len(names)
+    walk_vtx, walk_off = np.asarray(z["walk_vtx"]), np.asarray(z["walk_off"])
+    vtx = np.concatenate([walk_vtx[int(walk_off[h]):int(walk_off[h + 1])] for _ in range(times) for h in range(H)])
+    lens = np.diff(walk_off)
+    off = np.concatenate([[0], np.cumsum(np.tile(lens, times))])
+    gfa = os.path.join(out_dir, "mhc4_panel_x%d.gfa" % times)
+    fa = os.path.join(out_dir, "chm13_reads.fa")
+    write_gfa(gfa, z["seg_bases"], z["seg_off"], vtx, off, k["link_src"], k["link_dst"],
+              [names[h] + ("_r%d" % r if r else "") for r in range(times) for h in range(H)], np.tile(np.asarray(k["walk_hap"]), times))
+    write_fasta(fa, z["read_bases"], z["read_off"])
+    return gfa, fa
+
+
 def materialize_mhc_hg002_reads(gold_dir: str, out_dir: str, seed: int = 20261018, coverage: float = 2.0):
     """BASELINE config 2 with the documented substitute for the absent HG002 2x read set: 150-bp reads drawn
     uniformly from the HG002.1 and HG002.2 walk sequences of the MHC_4 panel (half each), random strand, 0.1 %

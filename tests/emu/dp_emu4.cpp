@@ -9,6 +9,8 @@
 // oracle without a GPU.  Never part of the product library.
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -32,7 +34,7 @@ struct Tiles {
 };
 
 bool plan(const DipGraphView& gv, const int32_t* shape, DipPlan& p, Plan4& q) {
-    if (!build_dip_plan(gv, p)) return false;
+    if (!build_dip_plan(gv, p)) { if (getenv("EMU4_VERBOSE")) fprintf(stderr, "build_dip_plan: %s\n", p.error.c_str()); return false; }
     Sweep4Shape sh;
     int rc = 10;
     if (shape) {
@@ -43,7 +45,9 @@ bool plan(const DipGraphView& gv, const int32_t* shape, DipPlan& p, Plan4& q) {
         if (shape[4] > 0) rc = shape[4];
     }
     std::string why;
-    return plan4_build(p, gv, sh, rc, q, why);
+    const bool ok = plan4_build(p, gv, sh, rc, q, why);
+    if (!ok && getenv("EMU4_VERBOSE")) fprintf(stderr, "plan4_build: %s\n", why.c_str());
+    return ok;
 }
 
 }  // namespace
@@ -71,11 +75,11 @@ extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const
     const int L = p.L, RL = q.RL;
 
     Tiles T;
-    T.slog = sh.slog; T.gpad = q.gpad; T.hkk = (int64_t)q.hstride * q.hstride;
+    T.slog = sh.slog; T.hkk = (int64_t)q.hstride * q.hstride; T.gpad = 2 * T.hkk;      // (the emulator keeps its own layer-major model of the HBM tile)
     T.s.assign((size_t)(RL + 2) << sh.slog, 0x5A5A5A5A);                 // (garbage: nothing may rely on zeros)
     std::fill(T.s.begin(), T.s.begin() + ((size_t)2 << sh.slog), V4_DEAD);
-    T.g.assign((size_t)std::max<int64_t>(q.gtile_cells, 1), 0x5A5A5A5A);
-    std::fill(T.g.begin(), T.g.begin() + (size_t)q.gpad, V4_DEAD);
+    T.g.assign((size_t)std::max<int64_t>(T.gpad + (int64_t)RL * T.hkk, 1), 0x5A5A5A5A);
+    std::fill(T.g.begin(), T.g.begin() + (size_t)T.gpad, V4_DEAD);
     // level 0: one vertex in slot 0 of the shared-memory tile, every layer starts at 0 (approximator.cpp:535)
     for (int r = 0; r < RL; ++r) T.at(true, r, 0) = r <= R ? 0 : V4_DEAD;
 
@@ -165,6 +169,8 @@ extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const
             if (c.n >= PROG_BIG_MIN) { if (nb_seen >= h.n_big || wbig[nb_seen] != t) return -22; ++nb_seen; }
             else if (c.n > h.max_n) return -23;
             const MultiCell mc = multi_cell(in, t);
+            const bool striped = c.n > PROG_KEY_CAND;       // the kernel's warp form: round in the key, lane from a ballot, code = ordinal
+            std::vector<uint32_t> ords((size_t)RL, 0);
             for (int r = 0; r < RL; ++r) {
                 int32_t key = V4_DEAD;
                 for (uint32_t o = 0; o < c.n; ++o) {
@@ -173,6 +179,11 @@ extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const
                     else { e.src = wcand[2 * (c.cand_off + o)] & 0x3FFFFFFFu; e.w = wcand[2 * (c.cand_off + o)] >> 30; e.delta = wcand[2 * (c.cand_off + o) + 1]; }
                     if (e.src >= cap_s) return -24;
                     readset[e.src] = 1;
+                    if (striped) {      // first strict maximum of the value, ordinal kept beside it
+                        const int32_t cv = T.at(ss, r - (int)e.w, e.src) + (int32_t)(e.delta << V4_SHIFT);
+                        if (o == 0 || cv > key) { key = cv; ords[r] = o; }
+                        continue;
+                    }
                     const int32_t cand = T.at(ss, r - (int)e.w, e.src) + (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - o));
                     key = std::max(key, cand);
                 }
@@ -181,9 +192,9 @@ extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const
             for (int r = 0; r < RL; ++r) {
                 const int32_t key = keys[r], val = (int32_t)((uint32_t)key & ~V4_ORD_MASK);
                 T.at(ds, r, c.dst) = val;
-                pred[(size_t)(h.pred_off + (uint64_t)r * h.n_multi + t)] = (uint16_t)key;
+                pred[(size_t)(h.pred_off + (uint64_t)r * h.n_multi + t)] = striped ? (uint16_t)ords[r] : (uint16_t)key;
                 if (val >= 0 && r <= R) {
-                    const uint32_t o = V4_ORD_MASK - ((uint32_t)key & V4_ORD_MASK);
+                    const uint32_t o = striped ? ords[r] : V4_ORD_MASK - ((uint32_t)key & V4_ORD_MASK);
                     const uint32_t e1 = o / mc.d2, e2 = o - e1 * mc.d2;
                     uint32_t i, wi, j, wj;
                     in_edge_at(in, mc.i2, e1, i, wi); in_edge_at(in, mc.j2, e2, j, wj);
@@ -272,4 +283,24 @@ extern "C" int64_t emu4_build_program(int32_t n_levels, const int32_t* level_off
         for (int l = 0; l < p.L - 1; ++l) prog_fill_level_host(p, q, l, out + q.prog_off[l]);
     }
     return (int64_t)q.prog_bytes;
+}
+
+// Per-transition plan statistics (tools/plan_stats.py): out[l * 8 ..] = flags, k, k2, n_copy, n_multi, n_cand, n_big, n_dead.
+extern "C" int64_t emu4_plan_stats(int32_t n_levels, const int32_t* level_off, const int64_t* adj_off,
+                                   const int32_t* adj_dst, const uint8_t* adj_w, const int64_t* col_off,
+                                   const int32_t* col_val, const uint8_t* colour_is_hom, int32_t n_colours, int32_t R,
+                                   const int32_t* shape, int64_t* out) {
+    DipGraphView gv;
+    gv.n_levels = n_levels; gv.level_off = level_off; gv.adj_off = adj_off; gv.adj_dst = adj_dst; gv.adj_w = adj_w;
+    gv.col_off = col_off; gv.col_val = col_val; gv.colour_is_hom = colour_is_hom; gv.n_colours = n_colours; gv.R = R;
+    DipPlan p;
+    Plan4 q;
+    const bool ok = plan(gv, shape, p, q);
+    if (!ok && (int)q.hdr.size() != p.L - 1) return -2;      // (a plan rejected for its size still has its headers: report them)
+    for (int l = 0; l < p.L - 1; ++l) {
+        const ProgHdr& h = q.hdr[l];
+        int64_t* o = out + (size_t)l * 8;
+        o[0] = ok ? q.full.dir[l].flags : q.tflags[l]; o[1] = h.k; o[2] = h.k2; o[3] = h.n_copy; o[4] = h.n_multi; o[5] = h.n_cand; o[6] = h.n_big; o[7] = h.n_dead;
+    }
+    return ok ? (int64_t)q.prog_bytes : -3;
 }

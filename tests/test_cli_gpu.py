@@ -62,6 +62,19 @@ def test_cli_mhc_hg002_simulated_reads(cli, e2e_expected, tmp_path):
     assert "DP value: 184562" in log
 
 
+@pytest.mark.parametrize("times", [4])
+def test_cli_replicated_panel_tie_break_stress(times, cli, e2e_expected, tmp_path):
+    """every MHC_4 walk written `times` times (20 W-lines) — identical lanes, so every maximum of the DP is
+    tied `times`-fold and only the reference's tie-break (smaller i, then smaller j, approximator.cpp:657-659) decides;
+    FASTA, DP value, recombination counts and lengths equal the unmodified reference's (run here on the same files)."""
+    e = e2e_expected["mhc_x%d_p2_R18" % times]
+    gfa, fa = fixtures.materialize_mhc_replicated(GOLD, str(tmp_path), times)
+    log, md5 = run(cli, gfa, fa, str(tmp_path / "out.fa"), ["-p2", "-R18"])
+    assert md5 == e["md5"]
+    assert "DP value: %d" % e["dp_value"] in log
+    assert "Recombinations in P1: %d, P2: %d, bp: %d / %d" % (e["r1"], e["r2"], e["bp1"], e["bp2"]) in log
+
+
 def test_cli_vcf_derived_graph(cli, e2e_expected, tmp_path):
     """BASELINE config 3: -p2 -R18 on the graph dipgenie_b200/vcf2gfa.py derives from MHC_4.vcf.gz + MHC-CHM13.0.fa.gz
     (fixture tests/golden/mhc4_vcf_panel.npz; 100 714 segments, 5 walks) with the HG002 read substitute: FASTA

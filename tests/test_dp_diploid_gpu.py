@@ -157,6 +157,17 @@ def test_cuda_wide_levels_use_many_ctas(ctx, oracle_mod):
     assert_dip_equal(oracle_dip(oracle_mod, g, 5), o)
 
 
+def test_cuda_level_program_cells_beyond_the_packed_ordinal(ctx, oracle_mod):
+    """Panels of 33 .. 181 walks: a recombination x recombination cell has in-degree^2 > 1024 candidates; the warp form keeps
+    the round in the key and takes the lane from a ballot (dp_sweep4.cuh: big_cell), the code is the plain ordinal.  Value,
+    paths and the checksums of every live cell of every level against the oracle, shared-memory and HBM-resident levels."""
+    for seed, lanes, blocks, R in ((41, 40, 6, 4), (42, 90, 4, 7), (43, 128, 3, 2)):
+        g = synth.lane_panel_graph(seed, n_lanes=lanes, n_blocks=blocks, rec_per_block=3, p_colour=0.25, n_colours=300)
+        o = cuda_dip(ctx, g, R)
+        assert o["stats"]["engine"] == 4
+        assert_dip_equal(oracle_dip(oracle_mod, g, R), o)
+
+
 @pytest.mark.parametrize("R", [18, 0, 6, 36])
 def test_cuda_matches_reference_mhc_full_size(R, ctx, expected, engine):
     """BASELINE config 2 graph (MHC_4.gfa.gz, CHM13 reads): every DP layer digest-equal to the reference."""
