@@ -63,12 +63,250 @@ def load_workload(name: str):
         g, _ = LevelGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_dipin.npz"))
         desc = "diploid -p2 DP on test/MHC_4.gfa.gz (5 walks) + test/CHM13_reads.fq.gz anchors; levelized graph from the reference front end"
         return g, desc
+    m = re.fullmatch(r"c4_h(\d+)(?:_s(\d+))?", name)
+    if m:
+        return config4_graph(int(m.group(1)), int(m.group(2) or 1))
     m = re.fullmatch(r"lanes(\d+)x(\d+)", name)
     if m:
         H, nb = int(m.group(1)), int(m.group(2))
         g = synth.lane_panel_graph(90, n_lanes=H, n_blocks=nb, rec_per_block=max(2, H // 16), p_colour=0.08, n_colours=1 << 15)
         return g, f"synthetic lane-panel model, {H} haplotype lanes, {nb} blocks (seed 90)"
     raise SystemExit(f"unknown workload {name}")
+
+
+def config4_graph(walks: int, denom: int):
+    """BASELINE config 4: the seeded synthetic panel (seed 90: 5 Mbp / denom backbone, 33 000 / denom sites, 12
+    founders, `walks` mosaic walks) and its 30x read set, pushed through this repo's own front end (the `dipgenie` CLI:
+    sketch + join on the GPU, anchors, classifier fit, expansion, levelization on the host) up to the DP's input, which the
+    CLI dumps (DG_DUMP_DIPIN).  Cached under /tmp for the R sweep."""
+    from dipgenie_b200 import _build, dgd
+    from dipgenie_b200.cuda_api import LevelGraph
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_config4
+    work = os.path.join(tempfile.gettempdir(), "dg_c4_h%d_s%d" % (walks, denom))
+    dump = os.path.join(work, "dipin.dgd")
+    if not os.path.exists(dump):
+        gfa, fa = make_config4.make(work, scale=1.0 / denom, walks=walks)
+        env = dict(os.environ, DG_DUMP_DIPIN=dump + ".tmp", DG_DUMP_ONLY="1")
+        t0 = time.perf_counter()
+        p = subprocess.run([_build.CLI_BIN, "-g", gfa, "-r", fa, "-o", os.path.join(work, "out.fa"), "-t", str(os.cpu_count() or 8), "-p2", "-R18"],
+                           capture_output=True, text=True, env=env, timeout=3000)
+        if p.returncode != 0:
+            raise SystemExit("bench.py: the front end failed on the config-4 panel: " + p.stderr[-1500:])
+        os.replace(dump + ".tmp", dump)
+        print("bench: config-4 front end (sketch, join, anchors, fit, expansion, levelization): %.1f s" % (time.perf_counter() - t0), file=sys.stderr)
+    d = dgd.load(dump)
+    g = LevelGraph(d["level_off"], d["adj_off"], d["adj_dst"], d["adj_w"], d["col_off"], d["col_val"], d["colour_is_hom"])
+    desc = ("synthetic config-4 panel (seed 90): %d walks, backbone %d bp, %d sites, 30x reads of a diploid mosaic target, "
+            "levelized by this repo's front end" % (walks, 5_000_000 // denom, 33_000 // denom))
+    return g, desc
+
+
+def wide_panel_arm(args):
+    """One wide-panel sample on the whole GPU (config 4): a step = one pass of the DP (program sweep + traceback) of the
+    resident problem; e2e = dg_dp_diploid with host buffers (planning, H2D, program build, sweep, traceback, D2H)."""
+    import torch
+    from dipgenie_b200.cuda_api import Context
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the device path has no CPU fallback")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py: the wide-panel workload is a single-GPU workload (replicas only)")
+    torch.cuda.set_device(0)
+    g, desc = load_workload(args.workload)
+    ctx = Context(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    e2e_t = []
+    for i in range(max(1, args.e2e_steps) + 1):
+        flush.fill_(1); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        o1 = ctx.dp_diploid(g, args.R)
+        if i > 0:
+            e2e_t.append(time.perf_counter() - t0)
+    ctx.release_cached_memory()
+    p = ctx.dip_create(g, args.R)
+    ms, sweep, trace = [], [], []
+    with ClockSampler(0) as clk:
+        for i in range(args.warmup + args.steps):
+            flush.fill_(1); torch.cuda.synchronize()
+            p.run()
+            out = p.result()
+            st = p.stats()
+            if i >= args.warmup:
+                ms.append(st["sweep_ms"] + st["traceback_ms"] + st["delta_ms"]); sweep.append(st["sweep_ms"]); trace.append(st["traceback_ms"])
+    assert out["value"] == o1["value"] and np.array_equal(out["p1_edges"], o1["p1_edges"]) and np.array_equal(out["p2_edges"], o1["p2_edges"])
+    peak, peak_src = peaks()
+    dev_ms, sweep_ms = float(np.mean(ms)), float(np.mean(sweep))
+    U, algo = float(st["cell_updates"]), float(st["algo_bytes"])
+    achieved = algo / (sweep_ms * 1e-3) / 1e9
+    e2e_s = float(np.mean(e2e_t))
+    line = {
+        "metric": "dp_cell_updates_per_sec", "value": U / (dev_ms * 1e-3), "unit": "cell-updates/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic (seeded generator, SURVEY 8d config 4)",
+        "config": {"workload": args.workload, "description": desc, "R": args.R, "ploidy": 2, "levels": st["n_levels"], "vertices": st["n_vertices"],
+                   "max_width": st["max_width"], "max_indegree": st["max_indegree"], "cell_updates_per_sample": U, "dest_cells_per_sample": st["cells"],
+                   "samples_per_step": 1, "ctas_per_sample": st["grid_ctas"], "engine": st["engine"],
+                   "device_bytes": st["device_bytes"], "program_bytes": st["prog_bytes"], "code_bytes": st["code_bytes"],
+                   "l2": "256 MiB device buffer rewritten between timed iterations",
+                   "timing": "CUDA events on the problem's stream (sweep + traceback kernels)"},
+        "dp_value": out["value"], "recombinations": [int(len(out["p1_edges"])) - 1, int(len(out["p2_edges"])) - 1],
+        "gpu_launches": int(st["launches"]) * args.steps,
+        "kernel_ms": {"sweep": sweep_ms, "traceback": float(np.mean(trace))},
+        "roofline": {"bound": "hbm", "kernel": "dip_sweep4_kernel" if st["engine"] == 4 else "dip_sweep_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+                     "cells_written_frac": float(st["cells_written"]) / max(1.0, float(st["cells"])),
+                     "traffic_source": "no ncu capture for this workload"},
+        "e2e": {"value": U / e2e_s, "unit": "cell-updates/s", "ms_per_step": e2e_s * 1e3, "samples_per_step": 1,
+                "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(ctypes_out_bytes()),
+                "api": "dg_dp_diploid (host buffers -> planning -> H2D -> program build -> sweep -> traceback -> D2H)"},
+        "clocks": clk.summary(),
+    }
+    if not args.no_cpu_baseline and os.path.exists(REF_PLAIN):
+        try:
+            with tempfile.TemporaryDirectory() as td:
+                gp = os.path.join(td, "graph.dgd")
+                graph_to_dgd(g, gp)
+                threads = min(os.cpu_count() or 8, 16)
+                first = run_ref_dp(gp, args.R, threads, max_levels=min(g.n_levels, 300))
+                per_level = first["ms"] / first["levels"]
+                max_levels = 0 if per_level * g.n_levels <= 25000 else max(300, int(25000 / per_level))
+                r = run_ref_dp(gp, args.R, threads, max_levels=max_levels)
+                line["cpu_baseline"] = {"value": r["cell_updates"] / (r["ms"] * 1e-3), "unit": "cell-updates/s", "cores": threads, "kind": "reference",
+                                        "sample": ("all %d levels" % g.n_levels) if not max_levels else ("first %d of %d levels" % (max_levels, g.n_levels)),
+                                        "ms": r["ms"], "host_cpus": os.cpu_count()}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": "cell-updates/s", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+    p.close()
+    ctx.close()
+    return 0
+
+
+def haploid_arm(args):
+    """BASELINE config 1's DP: haploid DP + R+1 tracebacks on the Kahn-ordered expanded graph of MHC_4 +
+    CHM13 reads (fixture from the reference front end).  U = (R+1) * nE cell-updates, B = (R+1) * (8 n + 8 nE)."""
+    import torch
+    import oracle
+    from dipgenie_b200.cuda_api import Context, HapGraph
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the device path has no CPU fallback")
+    torch.cuda.set_device(0)
+    g = HapGraph.from_npz(os.path.join(GOLD, "mhc4_chm13_hapin.npz"))
+    R = args.R
+    ctx = Context(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    e2e_t = []
+    for i in range(max(1, args.e2e_steps) + 1):
+        flush.fill_(1); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        o1 = ctx.dp_haploid(g, R)
+        if i > 0:
+            e2e_t.append(time.perf_counter() - t0)
+    p = ctx.hap_create(g, R)
+    ms, sweep, trace = [], [], []
+    with ClockSampler(0) as clk:
+        for i in range(args.warmup + args.steps):
+            flush.fill_(1); torch.cuda.synchronize()
+            p.run()
+            out = p.result()
+            st = p.stats()
+            if i >= args.warmup:
+                ms.append(st["sweep_ms"] + st["traceback_ms"]); sweep.append(st["sweep_ms"]); trace.append(st["traceback_ms"])
+    assert np.array_equal(out["colours_by_r"], o1["colours_by_r"])
+    peak, peak_src = peaks()
+    nE, n = len(g.adj_dst), g.n
+    U, algo = float((R + 1) * nE), float((R + 1) * (8 * n + 8 * nE))
+    dev_ms, sweep_ms, e2e_s = float(np.mean(ms)), float(np.mean(sweep)), float(np.mean(e2e_t))
+    in_bytes = sum(int(np.asarray(a).nbytes) for a in (g.adj_off, g.adj_dst, g.adj_w, g.col_off, g.col_val))
+    line = {
+        "metric": "dp_cell_updates_per_sec", "value": U / (dev_ms * 1e-3), "unit": "cell-updates/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "bundled MHC_4 test panel + CHM13 reads (Kahn-ordered expanded graph fixture)",
+        "config": {"workload": args.workload, "description": "haploid -p1 DP + R+1 tracebacks (approximator.cpp:44-168)", "R": R, "ploidy": 1,
+                   "vertices": n, "edges": nE, "levels": st["n_levels"], "max_width": st["max_width"], "samples_per_step": 1,
+                   "l2": "256 MiB device buffer rewritten between timed iterations", "timing": "CUDA events on the library stream (sweep + traceback kernels)"},
+        "colours_by_r": [int(x) for x in out["colours_by_r"][:3]], "gpu_launches": int(st["launches"]) * args.steps,
+        "kernel_ms": {"sweep": sweep_ms, "traceback": float(np.mean(trace))},
+        "roofline": {"bound": "hbm", "kernel": "hap_sweep_kernel", "achieved": algo / (sweep_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo / (sweep_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo,
+                     "note": "one persistent CTA walks 120 363 dependent levels of 1-13 vertices: bound by the per-level barrier chain, not by HBM (DESIGN.md 5)"},
+        "e2e": {"value": U / e2e_s, "unit": "cell-updates/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": int(sum(len(x) for x in o1["paths"]) * 4 + (R + 1) * 4), "api": "dg_dp_haploid (host buffers)"},
+        "clocks": clk.summary(),
+    }
+    if not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        ref = oracle.dp_haploid(g.adj_off, g.adj_dst, g.adj_w, g.col_off, g.col_val, g.n_colours, R)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(np.asarray(ref["colours_by_r"]), out["colours_by_r"])
+        line["cpu_baseline"] = {"value": U / dt, "unit": "cell-updates/s", "cores": 1, "kind": "port", "sample": "the whole sample (oracle/dp_haploid.c, serial like the reference)", "ms": dt * 1e3}
+    print(json.dumps(line))
+    p.close(); ctx.close()
+    return 0
+
+
+def sketch_arm(args):
+    """canonical (w,k)-minimizer sketch of every read (spectrum, per-hash read counts) and of every
+    walk (joined with the spectrum, covered vertices) of MHC_4 + CHM13 reads.  Metric: input bases per second;
+    B = 1 B per base + 8 B per emitted hash + 16 B per walk minimizer probed + 4 B per covered vertex id."""
+    import torch
+    import oracle
+    from dipgenie_b200.cuda_api import Context
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the device path has no CPU fallback")
+    torch.cuda.set_device(0)
+    z = dict(np.load(os.path.join(GOLD, "sketch_mhc4_chm13.npz")))
+    k, w = int(z["k"]), int(z["w"])
+    ctx = Context(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    walk_bases = int(sum(int(z["seg_off"][v + 1]) - int(z["seg_off"][v]) for v in z["walk_vtx"].tolist()))
+    bases = int(len(z["read_bases"])) + walk_bases
+    wall, kern, launches = [], [], 0
+    with ClockSampler(0) as clk:
+        for i in range(args.warmup + args.steps):
+            flush.fill_(1); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            sp, rcnt = ctx.sketch_reads(z["read_bases"], z["read_off"], k, w)
+            s1 = ctx.sketch_stats()
+            ix = ctx.index_walks(z["seg_bases"], z["seg_off"], z["walk_vtx"], z["walk_off"], z["top_order_map"], k, w, sp)
+            s2 = ctx.sketch_stats()
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                wall.append(dt); kern.append(s1["kernel_ms"] + s2["kernel_ms"]); launches += s1["launches"] + s2["launches"]
+    n_min = int(s1["minimizers"]) + int(np.sum(ix["n_minimizers"]))
+    algo = float(bases + 8 * n_min + 16 * int(np.sum(ix["n_minimizers"])) + 4 * len(ix["hit_vtx"]))
+    peak, peak_src = peaks()
+    kms, e2e_s = float(np.mean(kern)), float(np.mean(wall))
+    h2d = int(z["read_bases"].nbytes + z["read_off"].nbytes + z["seg_bases"].nbytes + z["seg_off"].nbytes + z["walk_vtx"].nbytes + z["walk_off"].nbytes + z["top_order_map"].nbytes + sp.nbytes)
+    d2h = int(sp.nbytes + rcnt.nbytes + sum(int(ix[x].nbytes) for x in ("hit_off", "hit_sid", "hit_vtx_off", "hit_vtx")))
+    line = {
+        "metric": "sketch_bases_per_sec", "value": bases / (kms * 1e-3), "unit": "bases/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": kms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "bundled MHC_4 test panel (5 walks) + CHM13 reads",
+        "config": {"workload": args.workload, "description": "dg_sketch_reads + dg_index_walks (solver.cpp:277-446,526-576)", "k": k, "w": w,
+                   "bases": bases, "read_bases": int(len(z["read_bases"])), "walk_bases": walk_bases, "minimizers": n_min, "spectrum": int(len(sp)),
+                   "hits": int(len(ix["hit_sid"])), "l2": "256 MiB device buffer rewritten between timed iterations",
+                   "timing": "value: CUDA events around the kernels of the two calls (the calls take host buffers: inputs are uploaded first, the timed kernels read them from HBM); e2e: wall clock of the two calls"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "sketch_tile_kernel + cover / spectrum / table kernels", "achieved": algo / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo / (kms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo},
+        "e2e": {"value": bases / e2e_s, "unit": "bases/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "dg_sketch_reads + dg_index_walks (host buffers)"},
+        "clocks": clk.summary(),
+    }
+    if not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        osp, _ = oracle.sketch_reads(z["read_bases"], z["read_off"], k, w)[:2]
+        one = dict(walk_vtx=z["walk_vtx"][int(z["walk_off"][0]):int(z["walk_off"][1])], walk_off=np.array([0, int(z["walk_off"][1]) - int(z["walk_off"][0])], np.uint64))
+        oracle.index_walks(z["seg_bases"], z["seg_off"], one["walk_vtx"], one["walk_off"], z["top_order_map"], k, w, osp)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(np.asarray(osp), sp)
+        sample_bases = int(len(z["read_bases"])) + int(sum(int(z["seg_off"][v + 1]) - int(z["seg_off"][v]) for v in one["walk_vtx"].tolist()))
+        line["cpu_baseline"] = {"value": sample_bases / dt, "unit": "bases/s", "cores": 1, "kind": "port",
+                                "sample": "all reads + the first walk (oracle/sketch.c)", "ms": dt * 1e3}
+    print(json.dumps(line))
+    ctx.close()
+    return 0
 
 
 def load_samples(name: str, n: int, seed: int = 2):
@@ -238,6 +476,12 @@ def main():
 
     if args.impl == "reference":
         return reference_arm(args)
+    if args.workload.startswith("c4_"):
+        return wide_panel_arm(args)
+    if args.workload == "mhc4_chm13_hap":
+        return haploid_arm(args)
+    if args.workload == "sketch_mhc4":
+        return sketch_arm(args)
 
     import torch
     import torch.distributed as dist

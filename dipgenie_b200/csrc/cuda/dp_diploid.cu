@@ -1210,31 +1210,29 @@ static const void* sweep_fn(bool pred32, bool check, bool prof = false) {
 }
 
 // ---- level-program engine: kernel variants and geometry ----
-static const void* sweep4_fn(int slog, int rc, bool check) {
-    if (slog == 10 && rc == 10) return check ? (const void*)dip_sweep4_kernel<10, 10, true> : (const void*)dip_sweep4_kernel<10, 10, false>;
-    if (slog == 10 && rc == 5) return check ? (const void*)dip_sweep4_kernel<10, 5, true> : (const void*)dip_sweep4_kernel<10, 5, false>;
-    if (slog == 9 && rc == 10) return check ? (const void*)dip_sweep4_kernel<9, 10, true> : (const void*)dip_sweep4_kernel<9, 10, false>;
-    if (slog == 9 && rc == 5) return check ? (const void*)dip_sweep4_kernel<9, 5, true> : (const void*)dip_sweep4_kernel<9, 5, false>;
-    if (slog == 8 && rc == 10) return check ? (const void*)dip_sweep4_kernel<8, 10, true> : (const void*)dip_sweep4_kernel<8, 10, false>;
+// Kernel variants: shared-memory layer stride (cells) x layers per register chunk.
+#define DG_S4_VARIANTS(X) X(1024, 10) X(1024, 5) X(680, 10) X(680, 5) X(512, 10) X(512, 5) X(256, 10)
+static const void* sweep4_fn(int stride, int rc, bool check) {
+#define X(ST, RC) if (stride == ST && rc == RC) return check ? (const void*)dip_sweep4_kernel<ST, RC, true> : (const void*)dip_sweep4_kernel<ST, RC, false>;
+    DG_S4_VARIANTS(X)
+#undef X
     return nullptr;
 }
-static const void* sweep4_many_fn(int slog, int rc) {
-    if (slog == 10 && rc == 10) return (const void*)dip_sweep4_many_kernel<10, 10>;
-    if (slog == 10 && rc == 5) return (const void*)dip_sweep4_many_kernel<10, 5>;
-    if (slog == 9 && rc == 10) return (const void*)dip_sweep4_many_kernel<9, 10>;
-    if (slog == 9 && rc == 5) return (const void*)dip_sweep4_many_kernel<9, 5>;
-    if (slog == 8 && rc == 10) return (const void*)dip_sweep4_many_kernel<8, 10>;
+static const void* sweep4_many_fn(int stride, int rc) {
+#define X(ST, RC) if (stride == ST && rc == RC) return (const void*)dip_sweep4_many_kernel<ST, RC>;
+    DG_S4_VARIANTS(X)
+#undef X
     return nullptr;
 }
 constexpr size_t S4_SMEM_MAX = 226 * 1024;   // 227 KB per CTA, less the fused kernel's static argument block
 // Layer chunk and shared-memory layer stride for R: the widest stride whose two tiles of RL + 2 layers fit beside the
 // slot ring.  False: no variant fits (R too large): the task-stream engine takes the problem.
 // `packed`: the problem shares the GPU with other resident problems, one CTA each (batch slots): a shared-memory tile of
-// stride 512 (22 slots), small ring and few warps, so that two CTAs fit an SM with room left for L1 — the sweep of
+// stride 680 (26 slots), small ring and few warps, so that two CTAs fit an SM with room left for L1 — the sweep of
 // one problem is a chain of dependent levels that leaves its SM mostly idle, a second problem fills the gaps (measured
-// on B200, MHC_4, R = 18, fused launch: 144 problems x 1 CTA per SM 262 ms; 256 problems x 2 per SM 416 ms; with stride
-// 1024 the two CTAs leave 20 KB of L1 and the pair takes 568 ms).  Otherwise the problem has SMs to itself: stride 1024
-// (32 slots).
+// on B200, MHC_4, R = 18, fused launch of 256 problems, two per SM: stride 512 316 ms, 680 300 ms, 1024 317 ms; one per
+// SM, 144 problems: 262 ms).  Otherwise the problem has SMs to itself: stride 1024
+// (31 slots).  Strides: 1024 (31 slots), 680 (26), 512 (22), 256 (15); DG_V4_STRIDE / DG_V4_SLOG override the choice.
 static bool sweep4_shape(int R, int grid, bool packed, Sweep4Shape& sh, int& rc, int& ncw) {
     rc = 10;
     if (const char* e = getenv("DG_V4_RC")) rc = atoi(e) == 5 ? 5 : 10;
@@ -1246,14 +1244,18 @@ static bool sweep4_shape(int R, int grid, bool packed, Sweep4Shape& sh, int& rc,
     if (const char* e = getenv("DG_V4_NCW")) ncw = std::max(1, std::min(16, atoi(e)));
     sh.grid = std::max(1, grid);
     const int RL = (R + rc) / rc * rc;
-    int want = packed ? 9 : 10;
-    if (const char* e = getenv("DG_V4_SLOG")) want = std::max(8, std::min(10, atoi(e)));
-    if (rc != 10) want = std::max(want, 9);
-    for (int slog = want; slog >= (rc == 10 ? 8 : 9); --slog)
-        if (sweep4_smem_bytes(slog, RL, sh.slot_bytes, sh.nslot) <= S4_SMEM_MAX) {
-            sh.slog = slog; sh.kn = slog == 10 ? 31 : (slog == 9 ? 22 : 15);     // kn^2 < 1 << slog: the last cell of a layer stays DEAD
+    static const int strides[4] = {1024, 680, 512, 256}, slots[4] = {31, 26, 22, 15};      // kn^2 < stride: the last cell of a layer stays DEAD
+    int first = packed ? 1 : 0;
+    if (const char* e = getenv("DG_V4_SLOG")) { const int sl = std::max(8, std::min(10, atoi(e))); first = sl == 10 ? 0 : (sl == 9 ? 2 : 3); }
+    if (const char* e = getenv("DG_V4_STRIDE")) { const int st = atoi(e); for (int x = 0; x < 4; ++x) if (strides[x] == st) first = x; }
+    for (int x = first; x < 4; ++x) {
+        if (rc != 10 && strides[x] == 256) break;
+        if (sweep4_smem_bytes(strides[x], RL, sh.slot_bytes, sh.nslot) <= S4_SMEM_MAX) {
+            sh.stride = strides[x]; sh.kn = slots[x];
+            sh.slog = 10;      // (unused once stride is set)
             return true;
         }
+    }
     return false;
 }
 
@@ -1377,9 +1379,9 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     const double t_up0 = now_ms();
     cudaStream_t s = d->stream;
     {
-        const int smem = (int)sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
-        for (int c = 0; c < 2; ++c) DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_fn(q.shape.slog, q.rc, c != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_many_fn(q.shape.slog, q.rc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int smem = (int)sweep4_smem_bytes(q.shape.cells(), q.RL, q.shape.slot_bytes, q.shape.nslot);
+        for (int c = 0; c < 2; ++c) DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_fn(q.shape.cells(), q.rc, c != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_many_fn(q.shape.cells(), q.rc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         // (no shared-memory carveout preference: the generic path's descriptor and spill traffic wants the L1 that two packed
         //  CTAs of ~61 KB leave — with the carveout forced to 100 % the same launch took 636 instead of 416 ms)
     }
@@ -1676,8 +1678,8 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
         fill_sweep4_args(d, a4, check);
         void* args[] = {(void*)&a4};
         const Plan4& q = d->p4;
-        const void* fn = sweep4_fn(q.shape.slog, q.rc, check);
-        const size_t smem = sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
+        const void* fn = sweep4_fn(q.shape.cells(), q.rc, check);
+        const size_t smem = sweep4_smem_bytes(q.shape.cells(), q.RL, q.shape.slot_bytes, q.shape.nslot);
         const dim3 block((unsigned)(d->v4_ncw + 1) * 32u);
         if (d->cooperative) DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), block, args, smem, s));
         else DG_CUDA(ctx, cudaLaunchKernel(fn, dim3(d->grid), block, args, smem, s));
@@ -2100,7 +2102,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
         fused = ds[i] && !ds[i]->cooperative && ds[i]->world == 1 && ds[i]->plan.L > 1 && ds[i]->pred_bytes == ds[0]->pred_bytes &&
                 ds[i]->v4 == ds[0]->v4;
         if (fused && ds[i]->v4)
-            fused = ds[i]->p4.shape.slog == ds[0]->p4.shape.slog && ds[i]->p4.rc == ds[0]->p4.rc && ds[i]->p4.RL == ds[0]->p4.RL &&
+            fused = ds[i]->p4.shape.cells() == ds[0]->p4.shape.cells() && ds[i]->p4.rc == ds[0]->p4.rc && ds[i]->p4.RL == ds[0]->p4.RL &&
                     ds[i]->p4.shape.slot_bytes == ds[0]->p4.shape.slot_bytes && ds[i]->p4.shape.nslot == ds[0]->p4.shape.nslot &&
                     ds[i]->v4_ncw == ds[0]->v4_ncw;
     }
@@ -2133,8 +2135,8 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
         DG_CUDA(ctx, bag.make(&f0));
         DG_CUDA(ctx, bag.make(&swept));
         const Plan4& q = ds[0]->p4;
-        const void* fn = sweep4_many_fn(q.shape.slog, q.rc);
-        const size_t smem = sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
+        const void* fn = sweep4_many_fn(q.shape.cells(), q.rc);
+        const size_t smem = sweep4_smem_bytes(q.shape.cells(), q.RL, q.shape.slot_bytes, q.shape.nslot);
         const Sweep4Args* pa = d_args.p;
         const int2* pm = d_map.p;
         void* args[] = {(void*)&pa, (void*)&pm};
@@ -2190,8 +2192,8 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
             DG_CUDA(ctx, bag.make(&f0));
             if (v4) {
                 const Plan4& q = ds[0]->p4;
-                const void* fn = sweep4_many_fn(q.shape.slog, q.rc);
-                const size_t smem = sweep4_smem_bytes(q.shape.slog, q.RL, q.shape.slot_bytes, q.shape.nslot);
+                const void* fn = sweep4_many_fn(q.shape.cells(), q.rc);
+                const size_t smem = sweep4_smem_bytes(q.shape.cells(), q.RL, q.shape.slot_bytes, q.shape.nslot);
                 const Sweep4Args* pa = d_args4.p;
                 void* args[] = {(void*)&pa, (void*)&pm};
                 DG_CUDA(ctx, cudaEventRecord(f0, ctx->stream));

@@ -37,7 +37,7 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
     q.RL = q.nchunk * rc;
     if (L < 2) { why = "single level"; return false; }
     if (p.value_bound >= KEY_VALUE_LIMIT) { why = "DP values may exceed the packed key"; return false; }
-    if ((int64_t)shape.kn * shape.kn > ((int64_t)1 << shape.slog) || shape.kn > 32 || shape.kn < 2) { why = "bad shape"; return false; }
+    if ((int64_t)shape.kn * shape.kn > (int64_t)shape.cells() || shape.kn > 32 || shape.kn < 2) { why = "bad shape"; return false; }
     if (p.kmax >= 32768) { why = "level wider than 32767 vertices"; return false; }
     const int32_t V = p.V;
     const int kn = shape.kn;
@@ -194,6 +194,12 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
         h.n_copy = (uint32_t)n.n_copy; h.n_multi = (uint32_t)n.n_multi; h.n_cand = (uint32_t)n.n_cand;
         h.n_big = (uint32_t)n.n_big; h.n_dead = (uint32_t)n.n_dead; h.max_n = n.max_n;
         h.n_passive = relocate ? 0u : c.np;
+        h.n_mm = c.m * c.m;
+        h.n_giant = 0;
+        if ((uint64_t)lvl_dmax[(size_t)l + 1] * lvl_dmax[(size_t)l + 1] > PROG_KEY_CAND)
+            for (uint32_t x = 0; x < c.m; ++x)
+                for (uint32_t y = 0; y < c.m; ++y)
+                    h.n_giant += (uint64_t)(c.mpre[x + 1] - c.mpre[x]) * (c.mpre[y + 1] - c.mpre[y]) > PROG_KEY_CAND;
         const ProgLayout lay = prog_layout(compact, n.n_copy, n.n_multi, n.n_cand, n.n_big, n.n_dead);
         h.off_cell = (uint32_t)lay.cell; h.off_cand = (uint32_t)lay.cand; h.off_big = (uint32_t)lay.big; h.off_dead = (uint32_t)lay.dead;
         bytes[l] = lay.end > 0xFFFFFFFFull ? ~0ull : (uint64_t)lay.end;

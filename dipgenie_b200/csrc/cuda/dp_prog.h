@@ -90,7 +90,8 @@ struct ProgHdr {           // 64 bytes
     uint32_t max_n;        // most candidates of a thread-form multi cell (loop bound hint)
     uint32_t n_passive;    // S1p vertices of level l+1 (their pairs are not in the program)
     uint64_t pred_off;     // u16 elements: codes of level l+1 start here, layout [layer][slot]
-    uint64_t rsv2;
+    uint32_t n_mm;         // M x M cells (the last n_mm multi cells): the only ones that can exceed PROG_KEY_CAND candidates
+    uint32_t n_giant;      // how many of them have more than PROG_KEY_CAND candidates (dp_sweep4.cuh: giant_cells)
     uint32_t off_cell, off_cand, off_big, off_dead;   // section offsets from the header's start (prog_layout; the copy section follows the header)
 };
 static_assert(sizeof(ProgHdr) == 64, "ProgHdr layout");
@@ -280,8 +281,10 @@ DG_HD void passive_pair(const ProgLevelIn& L, uint64_t x, uint32_t& i2, uint32_t
 
 // Kernel geometry the directory is made for.
 struct Sweep4Shape {
-    int slog = 10;             // shared-memory layer stride = 1 << slog cells
-    int kn = 32;               // slots of the shared-memory tile (kn * kn <= 1 << slog)
+    int slog = 10;             // shared-memory layer stride = 1 << slog cells ...
+    int stride = 0;            // ... or, when non-zero, this many cells (the kernel is instantiated for 1024, 680, 512, 256)
+    int kn = 32;               // slots of the shared-memory tile (kn * kn <= stride)
+    int cells() const { return stride ? stride : 1 << slog; }
     int slot_bytes = 8192;     // ring slot (directory entry + program)
     int nslot = 4;             // ring depth
     int grid = 1;              // CTAs of the problem

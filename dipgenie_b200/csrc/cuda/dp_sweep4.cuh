@@ -6,7 +6,7 @@
 //
 // Sweep kernel, per problem:
 //   * CTA 0 keeps the two DP layers of every level at most `kn` wide in shared-memory tiles of FIXED layer stride
-//     (1 << SLOG cells): layer r of a cell is one LDS/STS with an immediate offset, no address arithmetic per layer;
+//     (ST cells: 1024, 680, 512 or 256): layer r of a cell is one LDS/STS with an immediate offset, no address arithmetic per layer;
 //     wider levels live in HBM/L2 tiles and their transitions are shared by all CTAs of the problem (monotone
 //     counter barrier); hand-over transitions between the two placements run on CTA 0;
 //   * a producer warp streams every transition's directory entry and program into a ring of shared-memory slots
@@ -176,23 +176,23 @@ template <int IMM> __device__ __forceinline__ int32_t lds_imm_free(uint32_t a) {
     asm("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(IMM));
     return v;
 }
-template <int SLOG, int RC, int Q = 0>
+template <int ST, int RC, int Q = 0>
 __device__ __forceinline__ void lds_layers_free(uint32_t a, int32_t (&v)[RC]) {
-    if constexpr (Q < RC) { v[Q] = lds_imm_free<(Q << (SLOG + 2))>(a); lds_layers_free<SLOG, RC, Q + 1>(a, v); }
+    if constexpr (Q < RC) { v[Q] = lds_imm_free<(Q * ST * 4)>(a); lds_layers_free<ST, RC, Q + 1>(a, v); }
 }
-template <int SLOG, int RC, int Q = 0>
+template <int ST, int RC, int Q = 0>
 __device__ __forceinline__ void lds_layers(uint32_t a, int32_t (&v)[RC]) {
-    if constexpr (Q < RC) { v[Q] = lds_imm<(Q << (SLOG + 2))>(a); lds_layers<SLOG, RC, Q + 1>(a, v); }
+    if constexpr (Q < RC) { v[Q] = lds_imm<(Q * ST * 4)>(a); lds_layers<ST, RC, Q + 1>(a, v); }
 }
-template <int SLOG, int RC, int Q = 0>
+template <int ST, int RC, int Q = 0>
 __device__ __forceinline__ void sts_layers(uint32_t a, const int32_t (&v)[RC]) {
-    if constexpr (Q < RC) { sts_imm<(Q << (SLOG + 2))>(a, v[Q]); sts_layers<SLOG, RC, Q + 1>(a, v); }
+    if constexpr (Q < RC) { sts_imm<(Q * ST * 4)>(a, v[Q]); sts_layers<ST, RC, Q + 1>(a, v); }
 }
 
 // What a compute warp knows about the transition it is working on.
 struct Lvl4 {
     const uint8_t* copy_p; const uint8_t* cell_p; const uint8_t* cand_p; const uint8_t* big_p; const uint8_t* dead_p;   // generic pointers (slot or HBM)
-    uint32_t k, k2, n_copy, n_multi, n_big, n_dead;
+    uint32_t k, k2, n_copy, n_multi, n_big, n_dead, n_mm;      // n_mm: M x M cells to scan for giants (0: the level has none)
     uint32_t src32, dst32;                // shared-memory tile: address of padding layer -2
     int32_t* gt;                          // HBM tile (cell-major): layer r of cell c at gt[c * cs + 2 + r]
     long long cs;
@@ -201,6 +201,7 @@ struct Lvl4 {
     uint32_t m_nchunk;                    // magic of nchunk (0: one chunk)
     bool l1;                              // HBM-tile loads may be served by L1 (the problem runs on one SM)
     const ProgLevelIn* in;                // checksum variant only
+    unsigned long long* prof;             // diagnostics: non-null in lane 0 of warp 0 of CTA 0 when the run is profiled
 };
 
 template <bool COMPACT> __device__ __forceinline__ CopyDesc ld_copy(const uint8_t* p, uint32_t t) {
@@ -220,10 +221,10 @@ template <bool COMPACT> __device__ __forceinline__ CandDesc ld_cand(const uint8_
 }
 
 // RC consecutive layers r0 .. r0+RC-1 of source cell `src`, read w layers lower (padding layers are DEAD).
-template <int SLOG, int RC, bool SS>
+template <int ST, int RC, bool SS>
 __device__ __forceinline__ void load_layers(const Lvl4& c, int r0, uint32_t src, uint32_t w, int32_t (&v)[RC]) {
     if (SS) {
-        lds_layers<SLOG, RC>(c.src32 + ((((uint32_t)(r0 + 2) - w) << SLOG) + src) * 4u, v);
+        lds_layers<ST, RC>(c.src32 + (((uint32_t)(r0 + 2) - w) * (uint32_t)ST + src) * 4u, v);
     } else {
         const int32_t* p = c.gt + ((long long)src * c.cs + (long long)(r0 + 2 - (int)w));
         if (c.l1) {              // one CTA per problem: the cells were written by this SM, its L1 is coherent with them
@@ -235,10 +236,10 @@ __device__ __forceinline__ void load_layers(const Lvl4& c, int r0, uint32_t src,
         }
     }
 }
-template <int SLOG, int RC, bool DS>
+template <int ST, int RC, bool DS>
 __device__ __forceinline__ void store_layers(const Lvl4& c, int r0, uint32_t dst, const int32_t (&v)[RC]) {
     if (DS) {
-        sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, v);
+        sts_layers<ST, RC>(c.dst32 + ((uint32_t)(r0 + 2) * (uint32_t)ST + dst) * 4u, v);
     } else {
         int32_t* p = c.gt + ((long long)dst * c.cs + (long long)(r0 + 2));
         if constexpr (RC % 2 == 0) {          // r0 and RC even, cells 32-byte aligned: 8-byte stores
@@ -298,24 +299,24 @@ __device__ __forceinline__ Item item_of(const Lvl4& c, uint32_t blk, int lane, u
 }
 
 // 32 copy items: dst = src shifted by w layers, plus delta.
-template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
+template <int ST, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
 __device__ __forceinline__ void copy_block(const Lvl4& c, uint32_t blk, int lane, Fold4& f) {
     const Item it = item_of(c, blk, lane, c.n_copy);
     if (!it.in) return;
     const CopyDesc d = ld_copy<COMPACT>(c.copy_p, it.t);
     const int32_t add = (int32_t)(d.delta << V4_SHIFT);
     int32_t v[RC];
-    load_layers<SLOG, RC, SS>(c, it.r0, d.src, d.w, v);
+    load_layers<ST, RC, SS>(c, it.r0, d.src, d.w, v);
 #pragma unroll
     for (int q = 0; q < RC; ++q) v[q] += add;
-    store_layers<SLOG, RC, DS>(c, it.r0, d.dst, v);
+    store_layers<ST, RC, DS>(c, it.r0, d.dst, v);
     if (CHECK) fold_copy(f, *c.in, c.R, it.t, it.r0, v, RC);
 }
 
 // 32 multi items, candidates two at a time: the two descriptors are fetched first, then their 2 x RC layers, so a cell
 // of n candidates costs n / 2 chains of two round trips instead of n (cells of PROG_BIG_MIN candidates or more belong to
 // the warp form).
-template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
+template <int ST, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
 __device__ __forceinline__ void multi_block(const Lvl4& c, uint32_t blk, int lane, Fold4& f) {
     const Item it = item_of(c, blk, lane, c.n_multi);
     CellDesc cd = {0u, 0u, 0u};
@@ -334,8 +335,8 @@ __device__ __forceinline__ void multi_block(const Lvl4& c, uint32_t blk, int lan
         int32_t v0[RC], v1[RC];
 #pragma unroll
         for (int q = 0; q < RC; ++q) { v0[q] = V4_DEAD; v1[q] = V4_DEAD; }
-        if (p0) load_layers<SLOG, RC, SS>(c, it.r0, e0.src, e0.w, v0);
-        if (p1) load_layers<SLOG, RC, SS>(c, it.r0, e1.src, e1.w, v1);
+        if (p0) load_layers<ST, RC, SS>(c, it.r0, e0.src, e0.w, v0);
+        if (p1) load_layers<ST, RC, SS>(c, it.r0, e1.src, e1.w, v1);
         // (a lane without the candidate keeps DEAD + something small: never the maximum of a cell that has candidates)
         const int32_t a0 = (int32_t)((e0.delta << V4_SHIFT) + (V4_ORD_MASK - o)), a1 = (int32_t)((e1.delta << V4_SHIFT) + (V4_ORD_MASK - o - 1u));
 #pragma unroll
@@ -349,22 +350,20 @@ __device__ __forceinline__ void multi_block(const Lvl4& c, uint32_t blk, int lan
             val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
             pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
         }
-        store_layers<SLOG, RC, DS>(c, it.r0, cd.dst, val);
+        store_layers<ST, RC, DS>(c, it.r0, cd.dst, val);
         if (CHECK) fold_multi(f, *c.in, c.R, it.t, it.r0, key, RC);
     }
 }
 
-// One (big cell, chunk) per warp: lanes over candidates, 32 at a time, then one REDUX.MAX per layer.  A cell of more than
-// PROG_KEY_CAND candidates keeps the ROUND o / 32 in the key's ordinal field: a lane's candidates come in ascending round,
-// the warp maximum carries the earliest round of the best value, and among the lanes that hold it the lowest one has the
-// smallest ordinal round * 32 + lane — the same first strict maximum in (e1,e2) order, for up to PROG_MAX_CAND candidates.
-template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
+// One (big cell, chunk) per warp: lanes over candidates, 32 at a time, then one REDUX.MAX per layer.  Cells of more than
+// PROG_KEY_CAND candidates belong to giant_cells below.
+template <int ST, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
 __device__ __forceinline__ void big_cell(const Lvl4& c, uint32_t x, int lane, Fold4& f) {
     const uint32_t u = c.m_nchunk ? __umulhi(x, c.m_nchunk) : x;
     const int r0 = (int)(x - u * (uint32_t)c.nchunk) * c.rc;
     const uint32_t t = reinterpret_cast<const uint32_t*>(c.big_p)[u];
     const CellDesc cd = ld_cell<COMPACT>(c.cell_p, t);
-    const bool striped = cd.n > PROG_KEY_CAND;
+    if (cd.n > PROG_KEY_CAND) return;
     int32_t key[RC];
 #pragma unroll
     for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
@@ -374,39 +373,95 @@ __device__ __forceinline__ void big_cell(const Lvl4& c, uint32_t x, int lane, Fo
     for (uint32_t o = (uint32_t)lane; o < cd.n; o += 32u) {
         CandDesc en = {0u, 0u, 0u};
         if (o + 32u < cd.n) en = ld_cand<COMPACT>(c.cand_p, cd.cand_off + o + 32u);
-        const int32_t add = (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - (striped ? (o >> 5) : o)));
+        const int32_t add = (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - o));
         int32_t v[RC];
-        load_layers<SLOG, RC, SS>(c, r0, e.src, e.w, v);
+        load_layers<ST, RC, SS>(c, r0, e.src, e.w, v);
 #pragma unroll
         for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
         e = en;
     }
-    int32_t val[RC];
-    uint32_t code[RC];
 #pragma unroll
-    for (int q = 0; q < RC; ++q) {
-        const int32_t m = __reduce_max_sync(0xFFFFFFFFu, key[q]);
-        val[q] = (int32_t)((uint32_t)m & ~V4_ORD_MASK);
-        if (striped) {
-            const uint32_t who = __ballot_sync(0xFFFFFFFFu, key[q] == m);
-            code[q] = ((V4_ORD_MASK - ((uint32_t)m & V4_ORD_MASK)) << 5) | (uint32_t)(__ffs((int)who) - 1);
-        } else code[q] = (uint32_t)m & 0xFFFFu;
-    }
+    for (int q = 0; q < RC; ++q) key[q] = __reduce_max_sync(0xFFFFFFFFu, key[q]);
     if (lane == 0) {
         uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
+        int32_t val[RC];
 #pragma unroll
-        for (int q = 0; q < RC; ++q) pl[(size_t)q * c.n_multi] = (uint16_t)code[q];
-        store_layers<SLOG, RC, DS>(c, r0, cd.dst, val);
-        if (CHECK) {
-            int32_t k2[RC];       // the fold decodes an ordinal from the key's low bits
+        for (int q = 0; q < RC; ++q) {
+            val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
+            pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
+        }
+        store_layers<ST, RC, DS>(c, r0, cd.dst, val);
+        if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
+    }
+}
+
+// GIANT cells — more than PROG_KEY_CAND candidates: a recombination x recombination cell of a panel of more than 32 walks has
+// in-degree^2 of them (8100 at 90 walks), and one warp walking them 32 at a time would be the critical path of the level.
+// All compute warps of a CTA take such a cell together: warp w, lane x visits ordinals o = round * S + w * 32 + x
+// (S = 32 * ncw), keeping the ROUND in the key's ordinal field — a lane's rounds ascend, so its key is (best value, earliest
+// round); the warp maximum plus the lowest lane holding it gives the warp's first maximum, and the warps' (value, ordinal)
+// pairs meet in shared memory, where the smallest ordinal among the best values wins: the reference's first strict
+// maximum in (e1,e2) order (approximator.cpp:657-659), for up to PROG_MAX_CAND candidates.  The code is the plain ordinal.
+// M x M cells are the last n_mm multi cells; cell x belongs to CTA x mod n_ctas (all-CTA levels) — uniform control flow
+// within a CTA, named barrier 2 over its compute warps.
+template <int ST, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
+__device__ __forceinline__ void giant_cells(const Lvl4& c, int2 (*scratch)[RC], uint32_t cta, uint32_t n_ctas, int warp, int ncw, int lane, Fold4& f) {
+    const uint32_t S = 32u * (uint32_t)ncw;
+    for (uint32_t x = cta; x < c.n_mm; x += n_ctas) {
+        const uint32_t t = c.n_multi - c.n_mm + x;
+        const CellDesc cd = ld_cell<COMPACT>(c.cell_p, t);
+        if (cd.n <= PROG_KEY_CAND) continue;                     // (the warp or thread form's; the same for every thread of the CTA)
+        for (int ch = 0; ch < c.nchunk; ++ch) {
+            const int r0 = ch * RC;
+            int32_t key[RC];
 #pragma unroll
-            for (int q = 0; q < RC; ++q) k2[q] = val[q] | (int32_t)(striped ? 0u : (code[q] & V4_ORD_MASK));
-            fold_multi(f, *c.in, c.R, t, r0, k2, RC, striped ? code : nullptr);
+            for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
+            const uint32_t first = (uint32_t)warp * 32u + (uint32_t)lane;
+            CandDesc e = {0u, 0u, 0u};
+            if (first < cd.n) e = ld_cand<COMPACT>(c.cand_p, cd.cand_off + first);
+            uint32_t round = 0;
+            for (uint32_t o = first; o < cd.n; o += S, ++round) {
+                CandDesc en = {0u, 0u, 0u};
+                if (o + S < cd.n) en = ld_cand<COMPACT>(c.cand_p, cd.cand_off + o + S);
+                const int32_t add = (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - round));
+                int32_t v[RC];
+                load_layers<ST, RC, SS>(c, r0, e.src, e.w, v);
+#pragma unroll
+                for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
+                e = en;
+            }
+#pragma unroll
+            for (int q = 0; q < RC; ++q) {
+                const int32_t m = __reduce_max_sync(0xFFFFFFFFu, key[q]);
+                const uint32_t who = __ballot_sync(0xFFFFFFFFu, key[q] == m);
+                if (lane == 0) {
+                    const uint32_t ord = (V4_ORD_MASK - ((uint32_t)m & V4_ORD_MASK)) * S + (uint32_t)warp * 32u + (uint32_t)(__ffs((int)who) - 1);
+                    scratch[warp][q] = make_int2((int32_t)((uint32_t)m & ~V4_ORD_MASK), (int)ord);
+                }
+            }
+            bar_named(2, ncw * 32);
+            if (warp == 0 && lane < RC) {
+                int2 best = scratch[0][lane];
+                for (int w = 1; w < ncw; ++w) {
+                    const int2 y = scratch[w][lane];
+                    if (y.x > best.x || (y.x == best.x && (uint32_t)y.y < (uint32_t)best.y)) best = y;
+                }
+                c.pl[(size_t)(r0 + lane) * c.n_multi + t] = (uint16_t)best.y;
+                if (DS) sts_s32(c.dst32 + ((uint32_t)(r0 + lane + 2) * (uint32_t)ST + cd.dst) * 4u, best.x);
+                else if (c.l1) c.gt[(long long)cd.dst * c.cs + (long long)(r0 + lane + 2)] = best.x;
+                else __stcg(c.gt + ((long long)cd.dst * c.cs + (long long)(r0 + lane + 2)), best.x);
+                if (CHECK) {
+                    const int32_t k1 = best.x;
+                    const uint32_t o1 = (uint32_t)best.y;
+                    fold_multi(f, *c.in, c.R, t, r0 + lane, &k1, 1, &o1);
+                }
+            }
+            bar_named(2, ncw * 32);
         }
     }
 }
 
-template <int SLOG, int RC, bool DS>
+template <int ST, int RC, bool DS>
 __device__ __forceinline__ void dead_block(const Lvl4& c, uint32_t blk, int lane) {
     const Item it = item_of(c, blk, lane, c.n_dead);
     if (!it.in) return;
@@ -414,39 +469,42 @@ __device__ __forceinline__ void dead_block(const Lvl4& c, uint32_t blk, int lane
     int32_t v[RC];
 #pragma unroll
     for (int q = 0; q < RC; ++q) v[q] = V4_DEAD;
-    store_layers<SLOG, RC, DS>(c, it.r0, dst, v);
+    store_layers<ST, RC, DS>(c, it.r0, dst, v);
 }
 
 // The work units of one transition, dealt round-robin to the (global) warps gw, gw + gstride, ...: heaviest first.
-template <int SLOG, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
+template <int ST, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
 __device__ __forceinline__ void run_level(const Lvl4& c, uint32_t gw, uint32_t gstride, int lane, Fold4& f) {
     const uint32_t nch = (uint32_t)c.nchunk;
     const uint32_t nmb = (c.n_multi * nch + 31u) >> 5, ncb = (c.n_copy * nch + 31u) >> 5, ndb = (c.n_dead * nch + 31u) >> 5;
     const uint32_t e0 = c.n_big * nch, e1 = e0 + nmb, e2 = e1 + ncb, e3 = e2 + ndb;
     for (uint32_t u = gw; u < e3; u += gstride) {
-        if (u < e0) big_cell<SLOG, RC, SS, DS, COMPACT, CHECK>(c, u, lane, f);
-        else if (u < e1) multi_block<SLOG, RC, SS, DS, COMPACT, CHECK>(c, u - e0, lane, f);
-        else if (u < e2) copy_block<SLOG, RC, SS, DS, COMPACT, CHECK>(c, u - e1, lane, f);
-        else dead_block<SLOG, RC, DS>(c, u - e2, lane);
+        const long long t0 = c.prof ? clock64() : 0;
+        if (u < e0) big_cell<ST, RC, SS, DS, COMPACT, CHECK>(c, u, lane, f);
+        else if (u < e1) multi_block<ST, RC, SS, DS, COMPACT, CHECK>(c, u - e0, lane, f);
+        else if (u < e2) copy_block<ST, RC, SS, DS, COMPACT, CHECK>(c, u - e1, lane, f);
+        else dead_block<ST, RC, DS>(c, u - e2, lane);
+        if (c.prof) c.prof[u < e0 ? 12 : (u < e1 ? 13 : (u < e2 ? 14 : 15))] += (unsigned long long)(clock64() - t0);
     }
 }
 
 // Everything but the staged compact transitions (below): hand-overs between the placements, HBM-resident levels,
 // wide-format programs, programs read in place.  Out of line, with a handful of scalar arguments: the narrow loop keeps
 // its own register allocation.  `sb` = the ring slot (directory entry, then the header and, if staged, the program).
-template <int SLOG, int RC, bool CHECK>
+template <int ST, int RC, bool CHECK>
 __device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_t* sb, uint32_t tile32, int l, int cta, int warp, int lane) {
     const ProgDir d = *reinterpret_cast<const ProgDir*>(sb);
     const ProgHdr h = *reinterpret_cast<const ProgHdr*>(sb + sizeof(ProgDir));
     const uint32_t flags = d.flags;
     Lvl4 c;
-    c.k = h.k; c.k2 = h.k2; c.n_copy = h.n_copy; c.n_multi = h.n_multi; c.n_big = h.n_big; c.n_dead = h.n_dead;
+    c.k = h.k; c.k2 = h.k2; c.n_copy = h.n_copy; c.n_multi = h.n_multi; c.n_big = h.n_big; c.n_dead = h.n_dead; c.n_mm = h.n_giant ? h.n_mm : 0u;
     const uint8_t* const pb = (flags & PF_STAGED) ? sb + sizeof(ProgDir) : a.prog + (size_t)d.off16 * 16;
     c.copy_p = pb + sizeof(ProgHdr); c.cell_p = pb + h.off_cell; c.cand_p = pb + h.off_cand; c.big_p = pb + h.off_big; c.dead_p = pb + h.off_dead;
     c.level = l; c.R = a.R; c.nchunk = a.nchunk; c.rc = RC; c.m_nchunk = a.m_nchunk; c.l1 = a.grid == 1 && a.use_l1;
     c.src32 = tile32; c.dst32 = tile32;
     c.gt = a.gtile; c.cs = a.gcs;
     c.pl = a.pred + h.pred_off;
+    c.prof = (a.prof != nullptr && cta == 0 && warp == 0 && lane == 0) ? a.prof : nullptr;
     ProgLevelIn in;
     if (CHECK) in = level_in(*a.chk, l);
     c.in = &in;
@@ -454,12 +512,22 @@ __device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_
     const uint32_t gw = all ? (uint32_t)(cta * a.ncw + warp) : (uint32_t)warp;
     const uint32_t gs = all ? (uint32_t)(a.grid * a.ncw) : (uint32_t)a.ncw;
     const bool ss = (flags & PF_SRC_SMEM) != 0, ds = (flags & PF_DST_SMEM) != 0;
+    const uint32_t gc = all ? (uint32_t)cta : 0u, gn = all ? (uint32_t)a.grid : 1u;      // giant cells: one CTA each
+    __shared__ int2 giant_scratch[16][RC];
     Fold4 f = {0ull, 0ull};
-    if (flags & PF_COMPACT) run_level<SLOG, RC, true, true, true, CHECK>(c, gw, gs, lane, f);
-    else if (ss && ds) run_level<SLOG, RC, true, true, false, CHECK>(c, gw, gs, lane, f);
-    else if (ss) run_level<SLOG, RC, true, false, false, CHECK>(c, gw, gs, lane, f);
-    else if (ds) run_level<SLOG, RC, false, true, false, CHECK>(c, gw, gs, lane, f);
-    else run_level<SLOG, RC, false, false, false, CHECK>(c, gw, gs, lane, f);
+#define DG_RUN(SS_, DS_, C_)                                                                           \
+    do {                                                                                               \
+        const long long tg0 = c.prof ? clock64() : 0;                                                  \
+        if (c.n_mm) giant_cells<ST, RC, SS_, DS_, C_, CHECK>(c, giant_scratch, gc, gn, warp, a.ncw, lane, f); \
+        if (c.prof) c.prof[11] += (unsigned long long)(clock64() - tg0);                               \
+        run_level<ST, RC, SS_, DS_, C_, CHECK>(c, gw, gs, lane, f);                                    \
+    } while (0)
+    if (flags & PF_COMPACT) run_level<ST, RC, true, true, true, CHECK>(c, gw, gs, lane, f);      // (compact levels have no giant cell: dp_plan4.cpp)
+    else if (ss && ds) DG_RUN(true, true, false);
+    else if (ss) DG_RUN(true, false, false);
+    else if (ds) DG_RUN(false, true, false);
+    else DG_RUN(false, false, false);
+#undef DG_RUN
     return make_ulonglong2(f.sum, f.live);
 }
 
@@ -481,7 +549,7 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t a) {
     return v;
 }
 
-template <int SLOG, int RC, bool CHECK>
+template <int ST, int RC, bool CHECK>
 __device__ __forceinline__ void fast_copy(const Fast4& c, uint32_t blk, int r0, int lane, Fold4& f) {
     const uint32_t t = blk * 32u + (uint32_t)lane;
     const bool active = t < c.n_copy;
@@ -489,20 +557,20 @@ __device__ __forceinline__ void fast_copy(const Fast4& c, uint32_t blk, int r0, 
     const uint32_t src = x & 1023u, dst = (x >> 10) & 1023u, w = (x >> 20) & 3u;
     const int32_t add = (int32_t)((x >> 22) << V4_SHIFT);
     int32_t v[RC];
-    lds_layers<SLOG, RC>(c.src32 + ((((uint32_t)(r0 + 2) - w) << SLOG) + src) * 4u, v);
+    lds_layers<ST, RC>(c.src32 + (((uint32_t)(r0 + 2) - w) * (uint32_t)ST + src) * 4u, v);
 #pragma unroll
     for (int q = 0; q < RC; ++q) v[q] += add;
     if (active) {
-        sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, v);
+        sts_layers<ST, RC>(c.dst32 + ((uint32_t)(r0 + 2) * (uint32_t)ST + dst) * 4u, v);
         if (CHECK) fold_copy(f, *c.in, c.R, t, r0, v, RC);
     }
 }
 
-// A candidate descriptor that changes nothing: the last cell of every layer is never a slot pair (kn^2 < 1 << SLOG) and is
+// A candidate descriptor that changes nothing: the last cell of every layer is never a slot pair (kn^2 < ST) and is
 // kept DEAD, so lanes that have run out of candidates walk on branch-free.
-template <int SLOG> __device__ __forceinline__ constexpr uint32_t dead_cand() { return (1u << SLOG) - 1u; }
+template <int ST> __device__ __forceinline__ constexpr uint32_t dead_cand() { return (uint32_t)ST - 1u; }
 
-template <int SLOG, int RC, bool CHECK>
+template <int ST, int RC, bool CHECK>
 __device__ __forceinline__ void fast_multi(const Fast4& c, uint32_t blk, int r0, int lane, Fold4& f) {
     const uint32_t t = blk * 32u + (uint32_t)lane;
     uint2 cd = make_uint2(0u, 0u);
@@ -513,20 +581,20 @@ __device__ __forceinline__ void fast_multi(const Fast4& c, uint32_t blk, int r0,
     const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, n);
     if (nmax == 0u) return;
     const uint32_t ca = c.cand32 + 4u * cd.y;
-    const uint32_t base = c.src32 + ((uint32_t)(r0 + 2) << (SLOG + 2));
+    const uint32_t base = c.src32 + ((uint32_t)(r0 + 2) * (uint32_t)(ST * 4));
     int32_t key[RC];
 #pragma unroll
     for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
     // two candidates per round, branch-free; the descriptors of the next round are fetched before this round's layers
     uint32_t x0 = lds_u32(ca), x1 = lds_u32(ca + 4u);
     for (uint32_t o = 0; o < nmax; o += 2u) {
-        const uint32_t e0 = o < n ? x0 : dead_cand<SLOG>(), e1 = o + 1u < n ? x1 : dead_cand<SLOG>();
+        const uint32_t e0 = o < n ? x0 : dead_cand<ST>(), e1 = o + 1u < n ? x1 : dead_cand<ST>();
         x0 = lds_u32(ca + 4u * (o + 2u)); x1 = lds_u32(ca + 4u * (o + 3u));      // (may run past the cell's list: unused then)
         const int32_t add0 = (int32_t)(((e0 >> 12) << V4_SHIFT) + (V4_ORD_MASK - o));
         const int32_t add1 = (int32_t)(((e1 >> 12) << V4_SHIFT) + (V4_ORD_MASK - o - 1u));
         int32_t v0[RC], v1[RC];
-        lds_layers_free<SLOG, RC>(base + ((e0 & 1023u) << 2) - (((e0 >> 10) & 3u) << (SLOG + 2)), v0);
-        lds_layers_free<SLOG, RC>(base + ((e1 & 1023u) << 2) - (((e1 >> 10) & 3u) << (SLOG + 2)), v1);
+        lds_layers_free<ST, RC>(base + ((e0 & 1023u) << 2) - (((e0 >> 10) & 3u) * (uint32_t)(ST * 4)), v0);
+        lds_layers_free<ST, RC>(base + ((e1 & 1023u) << 2) - (((e1 >> 10) & 3u) * (uint32_t)(ST * 4)), v1);
 #pragma unroll
         for (int q = 0; q < RC; ++q) key[q] = max(key[q], max(v0[q] + add0, v1[q] + add1));
     }
@@ -538,18 +606,18 @@ __device__ __forceinline__ void fast_multi(const Fast4& c, uint32_t blk, int r0,
             val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
             pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
         }
-        sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, val);
+        sts_layers<ST, RC>(c.dst32 + ((uint32_t)(r0 + 2) * (uint32_t)ST + dst) * 4u, val);
         if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
     }
 }
 
-template <int SLOG, int RC, bool CHECK>
+template <int ST, int RC, bool CHECK>
 __device__ __forceinline__ void fast_big(const Fast4& c, uint32_t u, int r0, int lane, Fold4& f) {
     const uint32_t t = lds_u32(c.big32 + 4u * u);
     const uint2 cd = lds_v2(c.cell32 + 8u * t);
     const uint32_t dst = cd.x & 1023u, n = cd.x >> 16;
     const uint32_t ca = c.cand32 + 4u * cd.y;
-    const uint32_t base = c.src32 + ((uint32_t)(r0 + 2) << (SLOG + 2));
+    const uint32_t base = c.src32 + ((uint32_t)(r0 + 2) * (uint32_t)(ST * 4));
     int32_t key[RC];
 #pragma unroll
     for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
@@ -557,7 +625,7 @@ __device__ __forceinline__ void fast_big(const Fast4& c, uint32_t u, int r0, int
         const uint32_t e = lds_u32(ca + 4u * o);
         const int32_t add = (int32_t)(((e >> 12) << V4_SHIFT) + (V4_ORD_MASK - o));
         int32_t v[RC];
-        lds_layers_free<SLOG, RC>(base + ((e & 1023u) << 2) - (((e >> 10) & 3u) << (SLOG + 2)), v);
+        lds_layers_free<ST, RC>(base + ((e & 1023u) << 2) - (((e >> 10) & 3u) * (uint32_t)(ST * 4)), v);
 #pragma unroll
         for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
     }
@@ -571,12 +639,12 @@ __device__ __forceinline__ void fast_big(const Fast4& c, uint32_t u, int r0, int
             val[q] = (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK);
             pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
         }
-        sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, val);
+        sts_layers<ST, RC>(c.dst32 + ((uint32_t)(r0 + 2) * (uint32_t)ST + dst) * 4u, val);
         if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
     }
 }
 
-template <int SLOG, int RC>
+template <int ST, int RC>
 __device__ __forceinline__ void fast_dead(const Fast4& c, uint32_t blk, int r0, int lane) {
     const uint32_t x = blk * 32u + (uint32_t)lane;
     if (x >= c.n_dead) return;
@@ -584,7 +652,7 @@ __device__ __forceinline__ void fast_dead(const Fast4& c, uint32_t blk, int r0, 
     int32_t v[RC];
 #pragma unroll
     for (int q = 0; q < RC; ++q) v[q] = V4_DEAD;
-    sts_layers<SLOG, RC>(c.dst32 + (((uint32_t)(r0 + 2) << SLOG) + dst) * 4u, v);
+    sts_layers<ST, RC>(c.dst32 + ((uint32_t)(r0 + 2) * (uint32_t)ST + dst) * 4u, v);
 }
 
 // Spin until the monotone arrival counter reaches `target`; gives up after timeout_ns or when another wait of the
@@ -607,11 +675,11 @@ __device__ __noinline__ bool wait_counter4(unsigned int* counter, unsigned int t
     return ok;
 }
 
-template <int SLOG, int RC, bool CHECK>
+template <int ST, int RC, bool CHECK>
 __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) {
     extern __shared__ __align__(128) uint8_t smem4[];
     const int RL = a.nchunk * RC;
-    const uint32_t tile_bytes = (uint32_t)(RL + 2) << (SLOG + 2);
+    const uint32_t tile_bytes = (uint32_t)(RL + 2) * (uint32_t)(ST * 4);
     uint8_t* const slots = smem4;
     uint8_t* const tiles = slots + (size_t)a.nslot * a.slot_bytes;
     uint64_t* const full = reinterpret_cast<uint64_t*>(tiles + (size_t)tile_bytes);
@@ -629,10 +697,10 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
     if (cta == 0) {
         // two dead padding layers below layer 0 of the tile; level 0 (one vertex, slot 0): every layer starts at 0 (:535)
         int32_t* const t0 = reinterpret_cast<int32_t*>(tiles);
-        for (int x = tid; x < (2 << SLOG); x += blockDim.x) t0[x] = V4_DEAD;
+        for (int x = tid; x < 2 * ST; x += blockDim.x) t0[x] = V4_DEAD;
         for (int r = tid; r < RL; r += blockDim.x) {
-            t0[((r + 2) << SLOG)] = r <= a.R ? 0 : V4_DEAD;
-            t0[((r + 2) << SLOG) + (int)dead_cand<SLOG>()] = V4_DEAD;       // the cell no slot pair maps to (fast_multi)
+            t0[(r + 2) * ST] = r <= a.R ? 0 : V4_DEAD;
+            t0[(r + 2) * ST + (int)dead_cand<ST>()] = V4_DEAD;       // the cell no slot pair maps to (fast_multi)
         }
     }
     __syncthreads();
@@ -659,7 +727,13 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                 if (lane == 0) {
                     // a program too large for a slot is read in place by the compute warps: bring it into L2 now, NS levels
                     // ahead of its use (its first touch is otherwise a chain of cold DRAM reads inside the level)
-                    if (!(fl & PF_STAGED)) l2_prefetch_bulk(a.prog + (size_t)off16 * 16, min(all16, 16384u) * 16u);
+                    // (a transition shared by all CTAs: CTA c brings in the c-th part)
+                    if (!(fl & PF_STAGED)) {
+                        const uint32_t parts = (fl & PF_ALL_CTAS) ? (uint32_t)a.grid : 1u;
+                        const uint32_t per16 = (all16 + parts - 1u) / parts, lo16 = min(all16, per16 * (uint32_t)(parts > 1u ? cta : 0));
+                        const uint32_t n16 = min(min(all16 - lo16, per16), 16384u);
+                        if (n16) l2_prefetch_bulk(a.prog + ((size_t)off16 + lo16) * 16, n16 * 16u);
+                    }
                     if (!first_round) mbar_wait(smem_u32(empty + slot), use_parity);
                     const uint32_t bar = smem_u32(full + slot);
                     const uint32_t dst = smem_u32(slots + (size_t)slot * a.slot_bytes);
@@ -690,7 +764,9 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
         const uint32_t flags = d.w;
         const int l = lds_s32(sb32 + 16u);                  // (the timed directory skips the transitions with nothing to do)
         if (a.grid > 1 && (flags & PF_WAIT) && !failed) {
+            const long long tw0 = profiling ? clock64() : 0;
             if (tid == 0 && !wait_counter4(a.counter, d.z, a.timeout_ns, l)) sts_s32(fail32, 1);
+            if (profiling) a.prof[10] += (unsigned long long)(clock64() - tw0);
             bar_named(1, CT);
             failed = lds_s32(fail32) != 0;
         }
@@ -720,14 +796,14 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                     const uint32_t lo = u < e0 ? 0u : (u < e1 ? e0 : (u < e2 ? e1 : e2));
                     const uint32_t v = u - lo, blk = a.m_nchunk ? __umulhi(v, a.m_nchunk) : v, ch = v - blk * nch;
                     const int r0 = (int)ch * RC;
-                    if (u < e0) fast_big<SLOG, RC, CHECK>(c, blk, r0, lane, f);
-                    else if (u < e1) fast_multi<SLOG, RC, CHECK>(c, blk, r0, lane, f);
-                    else if (u < e2) fast_copy<SLOG, RC, CHECK>(c, blk, r0, lane, f);
-                    else fast_dead<SLOG, RC>(c, blk, r0, lane);
+                    if (u < e0) fast_big<ST, RC, CHECK>(c, blk, r0, lane, f);
+                    else if (u < e1) fast_multi<ST, RC, CHECK>(c, blk, r0, lane, f);
+                    else if (u < e2) fast_copy<ST, RC, CHECK>(c, blk, r0, lane, f);
+                    else fast_dead<ST, RC>(c, blk, r0, lane);
                 }
                 if (profiling) a.prof[19] += (unsigned long long)(clock64() - tu0);
             } else {
-                const ulonglong2 fs = run_generic<SLOG, RC, CHECK>(a, slots + (size_t)slot * a.slot_bytes, tiles32, l, cta, warp, lane);
+                const ulonglong2 fs = run_generic<ST, RC, CHECK>(a, slots + (size_t)slot * a.slot_bytes, tiles32, l, cta, warp, lane);
                 f.sum = fs.x; f.live = fs.y;
             }
         }
@@ -755,7 +831,7 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                     in_edge_at(in, i2, 0, i, wi); in_edge_at(in, j2, 0, j, wj);
                     const uint32_t dc = dst_cell(in, i2, j2);
                     for (int r = 0; r <= a.R; ++r) {
-                        const int32_t v = dsm ? lds_s32(tiles32 + (((uint32_t)(r + 2) << SLOG) + dc) * 4u) : __ldcg(a.gtile + (long long)dc * a.gcs + 2 + r);
+                        const int32_t v = dsm ? lds_s32(tiles32 + ((uint32_t)(r + 2) * (uint32_t)ST + dc) * 4u) : __ldcg(a.gtile + (long long)dc * a.gcs + 2 + r);
                         fold_pos(f, a.R, in.k2, r, i2, j2, v, i, j);
                     }
                 }
@@ -782,21 +858,21 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
         }
         for (int r = tid; r <= a.R; r += CT) {
             int32_t v;
-            if (a.last_smem) v = lds_s32(tiles32 + (((uint32_t)(r + 2) << SLOG) + a.sink_cell) * 4u);
+            if (a.last_smem) v = lds_s32(tiles32 + ((uint32_t)(r + 2) * (uint32_t)ST + a.sink_cell) * 4u);
             else v = __ldcg(a.gtile + (long long)a.sink_cell * a.gcs + 2 + r);
             a.sink[r] = v;
         }
     }
 }
 
-template <int SLOG, int RC, bool CHECK>
+template <int ST, int RC, bool CHECK>
 __global__ void __launch_bounds__(544, 1) dip_sweep4_kernel(const __grid_constant__ Sweep4Args a) {
-    sweep4_body<SLOG, RC, CHECK>(a, (int)blockIdx.x);
+    sweep4_body<ST, RC, CHECK>(a, (int)blockIdx.x);
 }
 
 // Many independent problems in ONE launch (dg_dip_run_many): CTA b works on problem cta_map[b].x as its local CTA
 // cta_map[b].y; the problem's arguments are copied to shared memory once.
-template <int SLOG, int RC>
+template <int ST, int RC>
 __global__ void __launch_bounds__(544, 1) dip_sweep4_many_kernel(const Sweep4Args* __restrict__ all, const int2* __restrict__ cta_map) {
     __shared__ Sweep4Args sa;
     const int2 who = cta_map[blockIdx.x];
@@ -805,11 +881,11 @@ __global__ void __launch_bounds__(544, 1) dip_sweep4_many_kernel(const Sweep4Arg
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sa);
     for (uint32_t x = threadIdx.x; x < sizeof(Sweep4Args) / 4; x += blockDim.x) dst[x] = src[x];
     __syncthreads();
-    sweep4_body<SLOG, RC, false>(sa, who.y);
+    sweep4_body<ST, RC, false>(sa, who.y);
 }
 
-constexpr size_t sweep4_smem_bytes(int slog, int RL, int slot_bytes, int nslot) {
-    return (size_t)nslot * (size_t)slot_bytes + ((size_t)(RL + 2) << (slog + 2)) + (2 * (size_t)nslot + 1) * 8;
+constexpr size_t sweep4_smem_bytes(int stride, int RL, int slot_bytes, int nslot) {
+    return (size_t)nslot * (size_t)slot_bytes + (size_t)(RL + 2) * (size_t)stride * 4 + (2 * (size_t)nslot + 1) * 8;
 }
 
 }  // namespace dg

@@ -155,7 +155,14 @@ bool read_gfa_file(const std::string& path, GfaGraph& g, std::string& err) {
                 size_t r = q + 1;
                 while (r < e && line[r] != '>' && line[r] != '<') ++r;
                 auto it = ids.find(line.substr(q + 1, r - q - 1));
-                if (it != ids.end()) w.v.push_back((uint32_t)it->second << 1 | (d == '<'));
+                // (the reference adds a sequence-less segment for an unknown name, src/gfa-io.cpp: gfa_add_seg, which its
+                // finalize step then deletes; a walk through a segment without sequence is a malformed input here)
+                if (it == ids.end()) {
+                    err = "W line of " + w.sample + " visits segment " + line.substr(q + 1, r - q - 1) + ", which has no S line before it";
+                    gzclose(fp);
+                    return false;
+                }
+                w.v.push_back((uint32_t)it->second << 1 | (d == '<'));
                 q = r;
             }
             g.walks.push_back(std::move(w));

@@ -23,7 +23,9 @@ static void usage(FILE* f) {
     fprintf(f, "  -R INT    recombination limit [18]\n");
     fprintf(f, "  -k INT    k-mer size [31]      -w INT   minimizer window [25]\n");
     fprintf(f, "  -T FLOAT  shared-anchor threshold [1.0]\n");
-    fprintf(f, "  -d INT    CUDA device [0]      -q       quiet\n");
+    fprintf(f, "  --device INT   CUDA device [0]      --quiet   no progress lines\n");
+    fprintf(f, "  (the reference's other flags are accepted with its own arity and ignored: -x -d -c -l -s -m -P -a -q -H -N take a\n");
+    fprintf(f, "   value, -D -S do not; they steer its ILP branch and debug output only)\n");
     fprintf(f, "  -B FILE   batch: one job per line, \"graph<TAB>reads<TAB>out\" (then -g/-r/-o are not needed); the\n");
     fprintf(f, "            diploid DPs of all jobs run side by side on the GPU\n");
 }
@@ -36,9 +38,11 @@ int main(int argc, char** argv) {
         const char* a = argv[i];
         if (!strcmp(a, "--version")) { puts("dipgenie-b200 1.0"); return 0; }
         if (!strcmp(a, "-h")) { usage(stdout); return 0; }
+        if (!strcmp(a, "--quiet")) { o.verbose = false; continue; }
+        if (!strcmp(a, "--device")) { if (i + 1 >= argc) { usage(stderr); return 1; } device = atoi(argv[++i]); continue; }
         if (a[0] != '-' || !a[1]) continue;
         const char f = a[1];
-        if (f == 'q') { o.verbose = false; continue; }
+        if (f == 'D' || f == 'S') continue;                                         // argument-less in the reference's opt_str (src/main.cpp:39)
         const char* v = a[2] ? a + 2 : (i + 1 < argc ? argv[++i] : nullptr);       // "-R18" and "-R 18" both parse, like ketopt
         if (!v) { usage(stderr); return 1; }
         switch (f) {
@@ -51,9 +55,8 @@ int main(int argc, char** argv) {
             case 'k': o.k = atoi(v); break;
             case 'w': o.w = atoi(v); break;
             case 'T': o.threshold = (float)atof(v); break;
-            case 'd': device = atoi(v); break;
             case 'B': batch_file = v; break;
-            default: break;                                                         // other reference flags (-c -m -N -H -P -l -a) steer the ILP branch only
+            default: break;                                                         // the reference's -x -d -c -l -s -m -P -a -q -H -N: value consumed, ignored
         }
     }
     if (batch_file.empty() && (o.gfa.empty() || o.reads.empty() || o.out.empty())) { usage(stderr); return 1; }

@@ -75,6 +75,24 @@ def test_cli_replicated_panel_tie_break_stress(times, cli, e2e_expected, tmp_pat
     assert "Recombinations in P1: %d, P2: %d, bp: %d / %d" % (e["r1"], e["r2"], e["bp1"], e["bp2"]) in log
 
 
+def test_cli_config4_panel_h90(cli, e2e_expected, tmp_path):
+    """BASELINE config 4's panel shape at 1/16 of the backbone (seeded generator, 90 walks, 30x reads of a diploid
+    mosaic target; tools/make_config4.py): level widths up to ~830, recombination vertices of in-degree 90 — recombination x
+    recombination cells have 8100 candidates (the CTA-cooperative form of dp_sweep4.cuh).  FASTA, DP value, recombination
+    counts and lengths equal the unmodified reference's on the same files (its DP alone: 282 s on 4 threads)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import make_config4
+    e = e2e_expected["c4_h90_s16_p2_R18"]
+    gfa, fa = make_config4.make(str(tmp_path), scale=0.0625)
+    assert hashlib.md5(open(gfa, "rb").read()).hexdigest() == e["gfa_md5"]
+    assert hashlib.md5(open(fa, "rb").read()).hexdigest() == e["reads_md5"]
+    log, md5 = run(cli, gfa, fa, str(tmp_path / "out.fa"), ["-p2", "-R18"])
+    assert "DP value: %d" % e["dp_value"] in log
+    assert "Recombinations in P1: %d, P2: %d, bp: %d / %d" % (e["r1"], e["r2"], e["bp1"], e["bp2"]) in log
+    assert md5 == e["md5"]
+
+
 def test_cli_vcf_derived_graph(cli, e2e_expected, tmp_path):
     """BASELINE config 3: -p2 -R18 on the graph dipgenie_b200/vcf2gfa.py derives from MHC_4.vcf.gz + MHC-CHM13.0.fa.gz
     (fixture tests/golden/mhc4_vcf_panel.npz; 100 714 segments, 5 walks) with the HG002 read substitute: FASTA
