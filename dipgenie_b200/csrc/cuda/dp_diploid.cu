@@ -1190,6 +1190,8 @@ struct dg_dip {
     DevBuf<ProgHdr> v4_hdr;
     DevBuf<uint64_t> v4_prog_off;
     DevBuf<int32_t> v4_wide, v4_wide_full, v4_sink;
+    DevBuf<unsigned long long> v4_gkey;          // giant cells: where the CTAs' slices meet (dp_sweep4.cuh: giant_cells); null without such cells
+    DevBuf<unsigned int> v4_gcnt;
     DevBuf<uint8_t> v4_prog, v4_dom;
     DevBuf<uint16_t> v4_pred, v4_cls, v4_vslot;
     DevBuf<uint32_t> v4_vinfo, v4_mpre, v4_n1, v4_np, v4_m, v4_z, v4_dm, v4_tflags;
@@ -1421,6 +1423,10 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     DG_CUDA(ctx, d->v4_prog.alloc((size_t)q.prog_bytes + 16, s));
     DG_CUDA(ctx, d->v4_pred.alloc((size_t)q.pred_elems + 8, s));
     DG_CUDA(ctx, d->v4_sink.alloc((size_t)p.R + 1, s));
+    if (q.max_giant > 0) {
+        DG_CUDA(ctx, d->v4_gkey.alloc((size_t)GIANT_LIST_MAX * (size_t)q.RL, s));
+        DG_CUDA(ctx, d->v4_gcnt.alloc((size_t)GIANT_LIST_MAX, s));
+    }
     DG_CUDA(ctx, d->tile0.alloc((size_t)std::max<int64_t>(q.gtile_cells, 1), s));
     DG_CUDA(ctx, d->counter.alloc(4, s));
     DG_CUDA(ctx, d->level_sum.alloc((size_t)L, s));
@@ -1559,6 +1565,10 @@ static int dip_run_pre(dg_ctx* ctx, dg_dip* d, bool check) {
         d->armed = false;
     } else if (d->v4) {
         DG_CUDA(ctx, cudaMemsetAsync(d->counter.p, 0, 4 * sizeof(unsigned int), s));            // (level 0 is set up by the kernel)
+        if (d->v4_gkey.p) {          // (clean after a complete run; a run that timed out may have left slices behind)
+            DG_CUDA(ctx, cudaMemsetAsync(d->v4_gkey.p, 0, d->v4_gkey.bytes(), s));
+            DG_CUDA(ctx, cudaMemsetAsync(d->v4_gcnt.p, 0, d->v4_gcnt.bytes(), s));
+        }
     } else {
         DG_CUDA(ctx, cudaMemsetAsync(d->counter.p, 0, 2 * sizeof(unsigned int), s));
         DG_CUDA(ctx, cudaMemsetAsync(d->tile0.p, 0, (size_t)(p.R + 1) * sizeof(int32_t), s));   // dp_cur.assign(R+1, {0,0}) :535
@@ -1620,6 +1630,7 @@ static void fill_sweep4_args(const dg_dip* d, Sweep4Args& a, bool check) {
     a.chk = check ? d->v4_tables.p : nullptr;
     a.final_target = dir.final_target;
     a.prof = d->want_prof ? d->prof.p : nullptr;
+    a.giant_key = d->v4_gkey.p; a.giant_cnt = d->v4_gcnt.p;
     a.timeout_ns = 10000ull * 1000000ull;
     if (const char* e = getenv("DG_SHARD_TIMEOUT_MS")) a.timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
 }

@@ -207,6 +207,8 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
         total += (uint64_t)k2 * (uint64_t)k2;
     }
     q.cells_written = written; q.cells_total = total;
+    for (int l = 0; l + 1 < L; ++l) q.max_giant = std::max(q.max_giant, q.hdr[l].n_giant);
+    if (q.max_giant > 256) { why = "more than 256 cells above 1024 candidates in one level"; return false; }     // dp_sweep4.cuh: GIANT_LIST_MAX
     for (int l = 0; l + 1 < L; ++l) {
         if (bytes[l] == ~0ull) { why = "a transition's program exceeds 4 GB"; return false; }
         q.prog_off[(size_t)l + 1] = q.prog_off[l] + bytes[l];

@@ -57,6 +57,7 @@ struct Plan4 {
     int64_t n_relocate = 0, n_skipped = 0;
     uint64_t cells_written = 0, cells_total = 0;   // destination cells in the programs / of the levels (per layer)
     uint32_t max_cand = 0;
+    uint32_t max_giant = 0;              // most cells of more than PROG_KEY_CAND candidates in one level
     // Hands the storage of every array back (after the upload; the scalars and wide lists stay).
     void release_arrays() {
         auto drop = [](auto& v) { v.clear(); v.shrink_to_fit(); };

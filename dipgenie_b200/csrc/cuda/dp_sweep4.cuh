@@ -153,6 +153,8 @@ struct Sweep4Args {
     uint32_t final_target;        // arrivals once the last transition is complete
     unsigned long long* prof;     // diagnostics (nullable): cycles of CTA 0 / thread 0 in [slot wait, level work, barrier], levels
     unsigned long long timeout_ns;
+    unsigned long long* giant_key; // [GIANT_LIST_MAX][nchunk * RC] slices of a giant cell meet here (zero between levels)
+    unsigned int* giant_cnt;       // [GIANT_LIST_MAX] slices arrived
 };
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
@@ -397,66 +399,139 @@ __device__ __forceinline__ void big_cell(const Lvl4& c, uint32_t x, int lane, Fo
 
 // GIANT cells — more than PROG_KEY_CAND candidates: a recombination x recombination cell of a panel of more than 32 walks has
 // in-degree^2 of them (8100 at 90 walks), and one warp walking them 32 at a time would be the critical path of the level.
-// All compute warps of a CTA take such a cell together: warp w, lane x visits ordinals o = round * S + w * 32 + x
-// (S = 32 * ncw), keeping the ROUND in the key's ordinal field — a lane's rounds ascend, so its key is (best value, earliest
-// round); the warp maximum plus the lowest lane holding it gives the warp's first maximum, and the warps' (value, ordinal)
-// pairs meet in shared memory, where the smallest ordinal among the best values wins: the reference's first strict
-// maximum in (e1,e2) order (approximator.cpp:657-659), for up to PROG_MAX_CAND candidates.  The code is the plain ordinal.
-// M x M cells are the last n_mm multi cells; cell x belongs to CTA x mod n_ctas (all-CTA levels) — uniform control flow
-// within a CTA, named barrier 2 over its compute warps.
+// A giant cell is cut into SLICES, one per CTA (transitions shared by all CTAs: cell j of ng goes to the CTAs c with
+// c mod ng == j; otherwise one slice), and within a CTA all compute warps take the slice together: slice s, warp w, lane x
+// visits the ordinals o = round * (ns * S) + s * S + w * 32 + x (S = 32 * ncw), keeping the ROUND in the key's ordinal field —
+// a lane's rounds ascend, so its key is (best value, earliest round); the warp maximum plus the lowest lane holding it give
+// the warp's first maximum; the warps' (value, ordinal) pairs meet in shared memory and the slices' in a 64-bit global word
+// per layer (atomicMax of value : ~ordinal), which the last slice to arrive turns into the cell (and clears).  The smallest
+// ordinal among the best values wins at every stage: the reference's first strict maximum in (e1,e2) order
+// (approximator.cpp:657-659), for up to PROG_MAX_CAND candidates.  The code is the plain ordinal.  M x M cells are the last
+// n_mm multi cells; every CTA derives the same ordered list of the giant ones.  Uniform control flow within a CTA, named
+// barrier 2 over its compute warps.
+constexpr int GIANT_LIST_MAX = 256;
+struct GiantShared {
+    int2 part[16][10];              // [warp][layer of the chunk]: (value, ordinal)
+    uint32_t list[GIANT_LIST_MAX];  // M x M indices of the giant cells, ascending
+    uint32_t wcnt[16];
+    uint32_t last;
+};
+__device__ __forceinline__ unsigned long long giant_pack(int32_t value, uint32_t ord) {
+    return ((unsigned long long)((uint32_t)value ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - ord);
+}
+
+// (out of line, arguments by value: its register needs and spills stay out of the paths every level takes)
 template <int ST, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
-__device__ __forceinline__ void giant_cells(const Lvl4& c, int2 (*scratch)[RC], uint32_t cta, uint32_t n_ctas, int warp, int ncw, int lane, Fold4& f) {
-    const uint32_t S = 32u * (uint32_t)ncw;
-    for (uint32_t x = cta; x < c.n_mm; x += n_ctas) {
-        const uint32_t t = c.n_multi - c.n_mm + x;
+__device__ __noinline__ void giant_cells(const Lvl4 c, GiantShared* gsp, uint32_t cta, uint32_t n_ctas, int warp, int ncw, int lane, Fold4* fp,
+                                         unsigned long long* gkey, unsigned int* gcnt, int RL) {
+    GiantShared& gs = *gsp;
+    Fold4& f = *fp;
+    static_assert(RC <= 10, "GiantShared::part");
+    const uint32_t S = 32u * (uint32_t)ncw, CT = S, tid = (uint32_t)warp * 32u + (uint32_t)lane;
+    const uint32_t t_mm = c.n_multi - c.n_mm;
+    // ---- the ordered list of giant cells ----
+    uint32_t ng = 0;
+    for (uint32_t x0 = 0; x0 < c.n_mm; x0 += CT) {
+        const uint32_t x = x0 + tid;
+        const bool is = x < c.n_mm && ld_cell<COMPACT>(c.cell_p, t_mm + x).n > PROG_KEY_CAND;
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, is);
+        if (lane == 0) gs.wcnt[warp] = (uint32_t)__popc(bal);
+        bar_named(2, (int)CT);
+        uint32_t before = ng, all = 0;
+        for (int w = 0; w < ncw; ++w) { const uint32_t n = gs.wcnt[w]; if (w < warp) before += n; all += n; }
+        if (is) { const uint32_t idx = before + (uint32_t)__popc(bal & ((1u << lane) - 1u)); if (idx < (uint32_t)GIANT_LIST_MAX) gs.list[idx] = x; }
+        ng += all;
+        bar_named(2, (int)CT);
+    }
+    if (ng > (uint32_t)GIANT_LIST_MAX) ng = (uint32_t)GIANT_LIST_MAX;       // (the planner refuses levels with more: dp_plan4.cpp)
+    if (ng == 0) return;
+    const bool split = n_ctas >= ng && n_ctas > 1;
+    for (uint32_t j = split ? cta % ng : cta; j < ng; j += split ? ng : n_ctas) {
+        const uint32_t slice = split ? cta / ng : 0u, ns = split ? (n_ctas - j + ng - 1u) / ng : 1u;
+        const uint32_t t = t_mm + gs.list[j];
         const CellDesc cd = ld_cell<COMPACT>(c.cell_p, t);
-        if (cd.n <= PROG_KEY_CAND) continue;                     // (the warp or thread form's; the same for every thread of the CTA)
+        const uint32_t step = ns * S, first = slice * S + tid;
         for (int ch = 0; ch < c.nchunk; ++ch) {
             const int r0 = ch * RC;
             int32_t key[RC];
 #pragma unroll
             for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
-            const uint32_t first = (uint32_t)warp * 32u + (uint32_t)lane;
-            CandDesc e = {0u, 0u, 0u};
-            if (first < cd.n) e = ld_cand<COMPACT>(c.cand_p, cd.cand_off + first);
+            // two rounds per iteration, the descriptors of the next two fetched before this pair's layers
+            const CandDesc none = {0u, 0u, 0u};
+            CandDesc e0 = first < cd.n ? ld_cand<COMPACT>(c.cand_p, cd.cand_off + first) : none;
+            CandDesc e1 = first + step < cd.n ? ld_cand<COMPACT>(c.cand_p, cd.cand_off + first + step) : none;
             uint32_t round = 0;
-            for (uint32_t o = first; o < cd.n; o += S, ++round) {
-                CandDesc en = {0u, 0u, 0u};
-                if (o + S < cd.n) en = ld_cand<COMPACT>(c.cand_p, cd.cand_off + o + S);
-                const int32_t add = (int32_t)((e.delta << V4_SHIFT) + (V4_ORD_MASK - round));
-                int32_t v[RC];
-                load_layers<ST, RC, SS>(c, r0, e.src, e.w, v);
+            for (uint32_t o = first; o < cd.n; o += 2u * step, round += 2u) {
+                const CandDesc n0 = o + 2u * step < cd.n ? ld_cand<COMPACT>(c.cand_p, cd.cand_off + o + 2u * step) : none;
+                const CandDesc n1 = o + 3u * step < cd.n ? ld_cand<COMPACT>(c.cand_p, cd.cand_off + o + 3u * step) : none;
+                const bool p1 = o + step < cd.n;
+                int32_t v0[RC], v1[RC];
 #pragma unroll
-                for (int q = 0; q < RC; ++q) key[q] = max(key[q], v[q] + add);
-                e = en;
+                for (int q = 0; q < RC; ++q) v1[q] = V4_DEAD;
+                load_layers<ST, RC, SS>(c, r0, e0.src, e0.w, v0);
+                if (p1) load_layers<ST, RC, SS>(c, r0, e1.src, e1.w, v1);
+                const int32_t a0 = (int32_t)((e0.delta << V4_SHIFT) + (V4_ORD_MASK - round)), a1 = (int32_t)((e1.delta << V4_SHIFT) + (V4_ORD_MASK - round - 1u));
+#pragma unroll
+                for (int q = 0; q < RC; ++q) key[q] = max(key[q], max(v0[q] + a0, v1[q] + a1));
+                e0 = n0; e1 = n1;
             }
 #pragma unroll
             for (int q = 0; q < RC; ++q) {
                 const int32_t m = __reduce_max_sync(0xFFFFFFFFu, key[q]);
                 const uint32_t who = __ballot_sync(0xFFFFFFFFu, key[q] == m);
                 if (lane == 0) {
-                    const uint32_t ord = (V4_ORD_MASK - ((uint32_t)m & V4_ORD_MASK)) * S + (uint32_t)warp * 32u + (uint32_t)(__ffs((int)who) - 1);
-                    scratch[warp][q] = make_int2((int32_t)((uint32_t)m & ~V4_ORD_MASK), (int)ord);
+                    // (a warp without candidates reports ordinal ~0 with a value no candidate can fall below)
+                    const uint32_t ord = (uint32_t)warp * 32u + slice * S < cd.n
+                                             ? (V4_ORD_MASK - ((uint32_t)m & V4_ORD_MASK)) * step + slice * S + (uint32_t)warp * 32u + (uint32_t)(__ffs((int)who) - 1)
+                                             : 0xFFFFFFFEu;
+                    gs.part[warp][q] = make_int2((int32_t)((uint32_t)m & ~V4_ORD_MASK), (int)ord);
                 }
             }
-            bar_named(2, ncw * 32);
+            bar_named(2, (int)CT);
             if (warp == 0 && lane < RC) {
-                int2 best = scratch[0][lane];
+                int2 best = gs.part[0][lane];
                 for (int w = 1; w < ncw; ++w) {
-                    const int2 y = scratch[w][lane];
+                    const int2 y = gs.part[w][lane];
                     if (y.x > best.x || (y.x == best.x && (uint32_t)y.y < (uint32_t)best.y)) best = y;
                 }
-                c.pl[(size_t)(r0 + lane) * c.n_multi + t] = (uint16_t)best.y;
-                if (DS) sts_s32(c.dst32 + ((uint32_t)(r0 + lane + 2) * (uint32_t)ST + cd.dst) * 4u, best.x);
-                else if (c.l1) c.gt[(long long)cd.dst * c.cs + (long long)(r0 + lane + 2)] = best.x;
-                else __stcg(c.gt + ((long long)cd.dst * c.cs + (long long)(r0 + lane + 2)), best.x);
-                if (CHECK) {
-                    const int32_t k1 = best.x;
-                    const uint32_t o1 = (uint32_t)best.y;
-                    fold_multi(f, *c.in, c.R, t, r0 + lane, &k1, 1, &o1);
+                if (ns > 1u) {
+                    if ((uint32_t)best.y != 0xFFFFFFFEu) atomicMax(gkey + (size_t)j * (size_t)RL + (size_t)(r0 + lane), giant_pack(best.x, (uint32_t)best.y));
+                    __threadfence();
+                } else {
+                    c.pl[(size_t)(r0 + lane) * c.n_multi + t] = (uint16_t)best.y;
+                    if (DS) sts_s32(c.dst32 + ((uint32_t)(r0 + lane + 2) * (uint32_t)ST + cd.dst) * 4u, best.x);
+                    else if (c.l1) c.gt[(long long)cd.dst * c.cs + (long long)(r0 + lane + 2)] = best.x;
+                    else __stcg(c.gt + ((long long)cd.dst * c.cs + (long long)(r0 + lane + 2)), best.x);
+                    if (CHECK) {
+                        const int32_t k1 = best.x;
+                        const uint32_t o1 = (uint32_t)best.y;
+                        fold_multi(f, *c.in, c.R, t, r0 + lane, &k1, 1, &o1);
+                    }
                 }
             }
-            bar_named(2, ncw * 32);
+            bar_named(2, (int)CT);
+        }
+        if (ns > 1u) {
+            // the last slice to arrive owns the cell: every slice's maxima are in the global words by then
+            if (tid == 0) {
+                __threadfence();
+                gs.last = atomicAdd(gcnt + j, 1u) == ns - 1u ? 1u : 0u;
+                __threadfence();
+            }
+            bar_named(2, (int)CT);
+            if (gs.last) {
+                for (int r = (int)tid; r < c.nchunk * RC; r += (int)CT) {
+                    const unsigned long long k = atomicExch(gkey + (size_t)j * (size_t)RL + (size_t)r, 0ull);
+                    const int32_t val = (int32_t)((uint32_t)(k >> 32) ^ 0x80000000u);
+                    const uint32_t ord = 0xFFFFFFFFu - (uint32_t)k;
+                    c.pl[(size_t)r * c.n_multi + t] = (uint16_t)ord;
+                    if (DS) sts_s32(c.dst32 + ((uint32_t)(r + 2) * (uint32_t)ST + cd.dst) * 4u, val);
+                    else __stcg(c.gt + ((long long)cd.dst * c.cs + (long long)(r + 2)), val);
+                    if (CHECK) fold_multi(f, *c.in, c.R, t, r, &val, 1, &ord);
+                }
+                if (tid == 0) gcnt[j] = 0u;
+            }
+            bar_named(2, (int)CT);
         }
     }
 }
@@ -513,12 +588,12 @@ __device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_
     const uint32_t gs = all ? (uint32_t)(a.grid * a.ncw) : (uint32_t)a.ncw;
     const bool ss = (flags & PF_SRC_SMEM) != 0, ds = (flags & PF_DST_SMEM) != 0;
     const uint32_t gc = all ? (uint32_t)cta : 0u, gn = all ? (uint32_t)a.grid : 1u;      // giant cells: one CTA each
-    __shared__ int2 giant_scratch[16][RC];
+    __shared__ GiantShared giant_sh;
     Fold4 f = {0ull, 0ull};
 #define DG_RUN(SS_, DS_, C_)                                                                           \
     do {                                                                                               \
         const long long tg0 = c.prof ? clock64() : 0;                                                  \
-        if (c.n_mm) giant_cells<ST, RC, SS_, DS_, C_, CHECK>(c, giant_scratch, gc, gn, warp, a.ncw, lane, f); \
+        if (c.n_mm) giant_cells<ST, RC, SS_, DS_, C_, CHECK>(c, &giant_sh, gc, gn, warp, a.ncw, lane, &f, a.giant_key, a.giant_cnt, a.nchunk * RC); \
         if (c.prof) c.prof[11] += (unsigned long long)(clock64() - tg0);                               \
         run_level<ST, RC, SS_, DS_, C_, CHECK>(c, gw, gs, lane, f);                                    \
     } while (0)

@@ -62,9 +62,9 @@ def test_cli_mhc_hg002_simulated_reads(cli, e2e_expected, tmp_path):
     assert "DP value: 184562" in log
 
 
-@pytest.mark.parametrize("times", [4])
+@pytest.mark.parametrize("times", [4, 18])
 def test_cli_replicated_panel_tie_break_stress(times, cli, e2e_expected, tmp_path):
-    """every MHC_4 walk written `times` times (20 W-lines) — identical lanes, so every maximum of the DP is
+    """every MHC_4 walk written `times` times (20 / 90 W-lines) — identical lanes, so every maximum of the DP is
     tied `times`-fold and only the reference's tie-break (smaller i, then smaller j, approximator.cpp:657-659) decides;
     FASTA, DP value, recombination counts and lengths equal the unmodified reference's (run here on the same files)."""
     e = e2e_expected["mhc_x%d_p2_R18" % times]

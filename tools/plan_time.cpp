@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <vector>
 #include "dp_prep.h"
+#include "dp_plan4.h"
+#include <string>
 using namespace dg;
 template <class T> static std::vector<T> rd(const char* dir, const char* name) {
     char path[512]; snprintf(path, sizeof path, "%s/%s.bin", dir, name);
@@ -34,6 +36,13 @@ int main(int argc, char** argv) {
         printf("build %.1f ms  tasks %.1f ms  total %.1f ms | tasks %.1f MB records %.1f MB masks %.1f MB in_* %.1f MB all %.1f MB\n", t1 - t0, t2 - t1, t2 - t0,
                p.tasks.size() * sizeof(TaskHdr) / 1e6, p.records.size() / 1e6, p.masks.size() * 8 / 1e6,
                (p.in_edge.size() * 4 + p.in_dst.size() * 2 + p.in_off.size() * 4) / 1e6, bytes / 1e6);
+        {   // the level-program engine's host plan (what dg_dip_create runs for engine 4)
+            const double t4 = now();
+            Sweep4Shape s4; s4.stride = 680; s4.kn = 26; s4.slot_bytes = 4096; s4.grid = 1;
+            Plan4 q4; std::string why;
+            const bool ok = plan4_build(p, g, s4, 10, q4, why);
+            printf("  plan4_build %.1f ms (%s) program %.1f MB codes %.1f MB\n", now() - t4, ok ? "ok" : why.c_str(), q4.prog_bytes / 1e6, q4.pred_elems * 2 / 1e6);
+        }
         const double t3 = now();
         { DipPlan q; std::swap(q, p); }
         printf("  free %.1f ms\n", now() - t3);

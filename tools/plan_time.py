@@ -9,5 +9,5 @@ for name, dt in (("level_off", np.int32), ("adj_off", np.int64), ("adj_dst", np.
                  ("col_off", np.int64), ("col_val", np.int32), ("colour_is_hom", np.uint8)):
     np.ascontiguousarray(getattr(z, name), dtype=dt).tofile(f"{out}/{name}.bin")
 src = 'dipgenie_b200/csrc/cuda'
-subprocess.check_call(["g++", "-O3", "-fopenmp", "-std=c++17", "-I", src, "tools/plan_time.cpp", f"{src}/dp_prep.cpp", "-o", "/tmp/plan_time"])
+subprocess.check_call(["g++", "-O3", "-fopenmp", "-std=c++17", "-I", src, "tools/plan_time.cpp", f"{src}/dp_prep.cpp", f"{src}/dp_plan4.cpp", "-o", "/tmp/plan_time"])
 subprocess.check_call(["/tmp/plan_time", out] + sys.argv[2:])
