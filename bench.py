@@ -309,6 +309,58 @@ def sketch_arm(args):
     return 0
 
 
+def row_sharded_arm(args):
+    """ONE diploid DP over the N GPUs of the node (`--mode row-sharded`, under torchrun): wide transitions split by destination
+    row over world x ctas CTAs, rows and barrier arrivals exchanged inside the sweep kernel over NVLink peer mappings
+    (dipgenie_b200.shard.RowShardedDip; no NCCL on the data path).  Strong scaling: the line also carries the single-GPU time
+    of the same problem, and the run asserts that every rank's result is identical to it."""
+    import torch
+    import torch.distributed as dist
+    from dipgenie_b200.cuda_api import Context
+    from dipgenie_b200.shard import RowShardedDip
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world < 2:
+        raise SystemExit("bench.py --mode row-sharded needs torchrun with at least 2 ranks")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    name = args.workload if args.workload.startswith("lanes") else "lanes640x24"
+    g, desc = load_workload(name)
+    ctx = Context(local)
+    single = ctx.dip_create(g, args.R)
+    t1 = []
+    for _ in range(args.warmup + args.steps):
+        single.run(); ref = single.result(); st1 = single.stats(); t1.append(st1["sweep_ms"] + st1["traceback_ms"] + st1["delta_ms"])
+    single.close()
+    prob = RowShardedDip(ctx, g, args.R, dist)
+    tn = []
+    for _ in range(args.warmup + args.steps):
+        out = prob.run(); st = prob.stats(); tn.append(st["sweep_ms"] + st["traceback_ms"] + st["delta_ms"])
+    good = bool(out["value"] == ref["value"] and out["s_het"] == ref["s_het"] and np.array_equal(out["p1_edges"], ref["p1_edges"])
+                and np.array_equal(out["p2_edges"], ref["p2_edges"]))
+    t = torch.tensor([float(np.mean(tn[args.warmup:])), float(np.mean(t1[args.warmup:])), 0.0 if good else 1.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_sharded, ms_single, bad = [float(x) for x in t.tolist()]
+    prob.close()
+    if rank == 0:
+        U = float(st["cell_updates"])
+        peak, peak_src = peaks()
+        print(json.dumps({
+            "metric": "dp_cell_updates_per_sec", "value": U / (ms_sharded * 1e-3), "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_sharded, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "mode": "row-sharded",
+            "config": {"workload": name, "description": desc, "R": args.R, "levels": st["n_levels"], "max_width": st["max_width"],
+                       "ctas_per_rank": st["grid_ctas"], "engine_sharded": st["engine"], "engine_single_gpu": st1["engine"],
+                       "single_gpu_ms": ms_single, "identical_on_every_rank": bad == 0.0,
+                       "exchange": "in-kernel stores through NVLink peer mappings + system-scope counter barrier; no NCCL on the data path"},
+            "roofline": {"bound": "hbm", "kernel": "dip_sweep_kernel (row-sharded)", "achieved": float(st["algo_bytes"]) / (ms_sharded * 1e-3) / 1e9,
+                         "peak": peak * world, "unit": "GB/s", "frac": float(st["algo_bytes"]) / (ms_sharded * 1e-3) / 1e9 / (peak * world),
+                         "traffic": None, "peak_source": peak_src + " x n_gpus"}}))
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+    return 0 if bad == 0.0 else 1
+
+
 def load_samples(name: str, n: int, seed: int = 2):
     """n samples of the workload's shape.  Sample 0 is the fixture itself; the others keep its panel graph (every sample of
     the study is genotyped against a panel of this shape) and get their own read-derived part: the colour sets are dealt to
@@ -470,12 +522,15 @@ def main():
     ap.add_argument("--batch", type=int, default=22, help="samples per GPU in the end-to-end batch call (22-sample study)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--mode", default="samples", help="samples (default: independent samples per GPU) | row-sharded (one DP over all GPUs)")
     ap.add_argument("--skip-e2e", action="store_true", help="diagnostics: no host-buffer batch calls before the resident group (the line then carries no e2e)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else max(args.warmup, 1)
 
     if args.impl == "reference":
         return reference_arm(args)
+    if args.mode == "row-sharded":
+        return row_sharded_arm(args)
     if args.workload.startswith("c4_"):
         return wide_panel_arm(args)
     if args.workload == "mhc4_chm13_hap":

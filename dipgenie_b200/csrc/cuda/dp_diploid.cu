@@ -1212,16 +1212,27 @@ static const void* sweep_fn(bool pred32, bool check, bool prof = false) {
 }
 
 // ---- level-program engine: kernel variants and geometry ----
-// Kernel variants: shared-memory layer stride (cells) x layers per register chunk.
+// Kernel variants: shared-memory layer stride (cells) x layers per register chunk; problems with giant cells (an in-degree
+// above 32: dp_sweep4.cuh) always take stride 1024 and the variants that carry that code.
 #define DG_S4_VARIANTS(X) X(1024, 10) X(1024, 5) X(680, 10) X(680, 5) X(512, 10) X(512, 5) X(256, 10)
-static const void* sweep4_fn(int stride, int rc, bool check) {
-#define X(ST, RC) if (stride == ST && rc == RC) return check ? (const void*)dip_sweep4_kernel<ST, RC, true> : (const void*)dip_sweep4_kernel<ST, RC, false>;
+static const void* sweep4_fn(int stride, int rc, bool check, bool giant) {
+    if (giant) {
+        if (stride == 1024 && rc == 10) return check ? (const void*)dip_sweep4_kernel<1024, 10, true, true> : (const void*)dip_sweep4_kernel<1024, 10, false, true>;
+        if (stride == 1024 && rc == 5) return check ? (const void*)dip_sweep4_kernel<1024, 5, true, true> : (const void*)dip_sweep4_kernel<1024, 5, false, true>;
+        return nullptr;
+    }
+#define X(ST, RC) if (stride == ST && rc == RC) return check ? (const void*)dip_sweep4_kernel<ST, RC, true, false> : (const void*)dip_sweep4_kernel<ST, RC, false, false>;
     DG_S4_VARIANTS(X)
 #undef X
     return nullptr;
 }
-static const void* sweep4_many_fn(int stride, int rc) {
-#define X(ST, RC) if (stride == ST && rc == RC) return (const void*)dip_sweep4_many_kernel<ST, RC>;
+static const void* sweep4_many_fn(int stride, int rc, bool giant) {
+    if (giant) {
+        if (stride == 1024 && rc == 10) return (const void*)dip_sweep4_many_kernel<1024, 10, true>;
+        if (stride == 1024 && rc == 5) return (const void*)dip_sweep4_many_kernel<1024, 5, true>;
+        return nullptr;
+    }
+#define X(ST, RC) if (stride == ST && rc == RC) return (const void*)dip_sweep4_many_kernel<ST, RC, false>;
     DG_S4_VARIANTS(X)
 #undef X
     return nullptr;
@@ -1235,7 +1246,7 @@ constexpr size_t S4_SMEM_MAX = 226 * 1024;   // 227 KB per CTA, less the fused k
 // on B200, MHC_4, R = 18, fused launch of 256 problems, two per SM: stride 512 316 ms, 680 300 ms, 1024 317 ms; one per
 // SM, 144 problems: 262 ms).  Otherwise the problem has SMs to itself: stride 1024
 // (31 slots).  Strides: 1024 (31 slots), 680 (26), 512 (22), 256 (15); DG_V4_STRIDE / DG_V4_SLOG override the choice.
-static bool sweep4_shape(int R, int grid, bool packed, Sweep4Shape& sh, int& rc, int& ncw) {
+static bool sweep4_shape(int R, int grid, bool packed, bool giant, Sweep4Shape& sh, int& rc, int& ncw) {
     rc = 10;
     if (const char* e = getenv("DG_V4_RC")) rc = atoi(e) == 5 ? 5 : 10;
     sh.slot_bytes = packed ? 4096 : 8192;
@@ -1247,10 +1258,11 @@ static bool sweep4_shape(int R, int grid, bool packed, Sweep4Shape& sh, int& rc,
     sh.grid = std::max(1, grid);
     const int RL = (R + rc) / rc * rc;
     static const int strides[4] = {1024, 680, 512, 256}, slots[4] = {31, 26, 22, 15};      // kn^2 < stride: the last cell of a layer stays DEAD
-    int first = packed ? 1 : 0;
+    int first = packed && !giant ? 1 : 0;
     if (const char* e = getenv("DG_V4_SLOG")) { const int sl = std::max(8, std::min(10, atoi(e))); first = sl == 10 ? 0 : (sl == 9 ? 2 : 3); }
     if (const char* e = getenv("DG_V4_STRIDE")) { const int st = atoi(e); for (int x = 0; x < 4; ++x) if (strides[x] == st) first = x; }
     for (int x = first; x < 4; ++x) {
+        if (giant && x > 0) break;                     // (giant cells: stride 1024 only)
         if (rc != 10 && strides[x] == 256) break;
         if (sweep4_smem_bytes(strides[x], RL, sh.slot_bytes, sh.nslot) <= S4_SMEM_MAX) {
             sh.stride = strides[x]; sh.kn = slots[x];
@@ -1329,7 +1341,7 @@ static bool dip_plan_host(const DipGraphView& g, const DipLimits& lim, int grid_
         Sweep4Shape s4;
         int rc = 10;
         std::string why = "no kernel variant for this R";
-        if (sweep4_shape(p.R, shape.grid, !d->cooperative && shape.grid == 1, s4, rc, d->v4_ncw) && plan4_build(p, g, s4, rc, d->p4, why)) d->v4 = true;
+        if (sweep4_shape(p.R, shape.grid, !d->cooperative && shape.grid == 1, p.max_indeg > 32, s4, rc, d->v4_ncw) && plan4_build(p, g, s4, rc, d->p4, why)) d->v4 = true;
         else {
             d->p4.release_arrays();           // (whatever the failed attempt left in the page-locked block: it is handed back before d dies)
             if (getenv("DG_TIMING")) fprintf(stderr, "dg_dip: task-stream engine (%s)\n", why.c_str());
@@ -1382,8 +1394,8 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     cudaStream_t s = d->stream;
     {
         const int smem = (int)sweep4_smem_bytes(q.shape.cells(), q.RL, q.shape.slot_bytes, q.shape.nslot);
-        for (int c = 0; c < 2; ++c) DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_fn(q.shape.cells(), q.rc, c != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_many_fn(q.shape.cells(), q.rc), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        for (int c = 0; c < 2; ++c) DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_fn(q.shape.cells(), q.rc, c != 0, q.max_giant > 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DG_CUDA(ctx, cudaFuncSetAttribute(sweep4_many_fn(q.shape.cells(), q.rc, q.max_giant > 0), cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         // (no shared-memory carveout preference: the generic path's descriptor and spill traffic wants the L1 that two packed
         //  CTAs of ~61 KB leave — with the carveout forced to 100 % the same launch took 636 instead of 416 ms)
     }
@@ -1689,7 +1701,7 @@ static int dip_run_impl(dg_ctx* ctx, dg_dip* d, bool check) {
         fill_sweep4_args(d, a4, check);
         void* args[] = {(void*)&a4};
         const Plan4& q = d->p4;
-        const void* fn = sweep4_fn(q.shape.cells(), q.rc, check);
+        const void* fn = sweep4_fn(q.shape.cells(), q.rc, check, q.max_giant > 0);
         const size_t smem = sweep4_smem_bytes(q.shape.cells(), q.RL, q.shape.slot_bytes, q.shape.nslot);
         const dim3 block((unsigned)(d->v4_ncw + 1) * 32u);
         if (d->cooperative) DG_CUDA(ctx, cudaLaunchCooperativeKernel(fn, dim3(d->grid), block, args, smem, s));
@@ -2113,7 +2125,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
         fused = ds[i] && !ds[i]->cooperative && ds[i]->world == 1 && ds[i]->plan.L > 1 && ds[i]->pred_bytes == ds[0]->pred_bytes &&
                 ds[i]->v4 == ds[0]->v4;
         if (fused && ds[i]->v4)
-            fused = ds[i]->p4.shape.cells() == ds[0]->p4.shape.cells() && ds[i]->p4.rc == ds[0]->p4.rc && ds[i]->p4.RL == ds[0]->p4.RL &&
+            fused = ds[i]->p4.shape.cells() == ds[0]->p4.shape.cells() && (ds[i]->p4.max_giant > 0) == (ds[0]->p4.max_giant > 0) && ds[i]->p4.rc == ds[0]->p4.rc && ds[i]->p4.RL == ds[0]->p4.RL &&
                     ds[i]->p4.shape.slot_bytes == ds[0]->p4.shape.slot_bytes && ds[i]->p4.shape.nslot == ds[0]->p4.shape.nslot &&
                     ds[i]->v4_ncw == ds[0]->v4_ncw;
     }
@@ -2146,7 +2158,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
         DG_CUDA(ctx, bag.make(&f0));
         DG_CUDA(ctx, bag.make(&swept));
         const Plan4& q = ds[0]->p4;
-        const void* fn = sweep4_many_fn(q.shape.cells(), q.rc);
+        const void* fn = sweep4_many_fn(q.shape.cells(), q.rc, q.max_giant > 0);
         const size_t smem = sweep4_smem_bytes(q.shape.cells(), q.RL, q.shape.slot_bytes, q.shape.nslot);
         const Sweep4Args* pa = d_args.p;
         const int2* pm = d_map.p;
@@ -2203,7 +2215,7 @@ int dg_dip_run_many(dg_ctx* ctx, dg_dip** ds, int32_t n, float* wall_ms) {
             DG_CUDA(ctx, bag.make(&f0));
             if (v4) {
                 const Plan4& q = ds[0]->p4;
-                const void* fn = sweep4_many_fn(q.shape.cells(), q.rc);
+                const void* fn = sweep4_many_fn(q.shape.cells(), q.rc, q.max_giant > 0);
                 const size_t smem = sweep4_smem_bytes(q.shape.cells(), q.RL, q.shape.slot_bytes, q.shape.nslot);
                 const Sweep4Args* pa = d_args4.p;
                 void* args[] = {(void*)&pa, (void*)&pm};

@@ -75,7 +75,7 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
             bool relocate;
             uint8_t ndom;
             if (dom == 0) { relocate = k + (k2 - np) > kn; ndom = relocate ? 1 : 0; }
-            else { relocate = k2 <= kn / 2; ndom = relocate ? 0 : 1; }
+            else { relocate = k2 <= kn * 3 / 4; ndom = relocate ? 0 : 1; }
             q.lvl_dom[l + 1] = ndom;
             uint32_t f = 0;
             if (dom == 0) f |= PF_SRC_SMEM;

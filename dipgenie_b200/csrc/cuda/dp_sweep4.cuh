@@ -222,6 +222,16 @@ template <bool COMPACT> __device__ __forceinline__ CandDesc ld_cand(const uint8_
     return {y.x & 0x3FFFFFFFu, y.x >> 30, y.y};
 }
 
+// The raw descriptor words (compact: x only) and their decoding: raw words keep an item's whole candidate list in registers.
+template <bool COMPACT> __device__ __forceinline__ uint2 ld_cand_raw(const uint8_t* p, uint32_t x) {
+    if (COMPACT) return make_uint2(reinterpret_cast<const uint32_t*>(p)[x], 0u);
+    return reinterpret_cast<const uint2*>(p)[x];
+}
+template <bool COMPACT> __device__ __forceinline__ CandDesc cand_of(uint2 y) {
+    if (COMPACT) return unpack_cand_c(y.x);
+    return {y.x & 0x3FFFFFFFu, y.x >> 30, y.y};
+}
+
 // RC consecutive layers r0 .. r0+RC-1 of source cell `src`, read w layers lower (padding layers are DEAD).
 template <int ST, int RC, bool SS>
 __device__ __forceinline__ void load_layers(const Lvl4& c, int r0, uint32_t src, uint32_t w, int32_t (&v)[RC]) {
@@ -315,8 +325,7 @@ __device__ __forceinline__ void copy_block(const Lvl4& c, uint32_t blk, int lane
     if (CHECK) fold_copy(f, *c.in, c.R, it.t, it.r0, v, RC);
 }
 
-// 32 multi items, candidates two at a time: the two descriptors are fetched first, then their 2 x RC layers, so a cell
-// of n candidates costs n / 2 chains of two round trips instead of n (cells of PROG_BIG_MIN candidates or more belong to
+// 32 multi items (cells of PROG_BIG_MIN candidates or more belong to
 // the warp form).
 template <int ST, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
 __device__ __forceinline__ void multi_block(const Lvl4& c, uint32_t blk, int lane, Fold4& f) {
@@ -329,6 +338,8 @@ __device__ __forceinline__ void multi_block(const Lvl4& c, uint32_t blk, int lan
     int32_t key[RC];
 #pragma unroll
     for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
+    // candidates two at a time: the two descriptors are fetched first, then their 2 x RC layers (more at a time, or all the
+    // descriptors first, spills at 96 registers and is slower: 342 against 299 ms for 256 resident MHC_4 samples)
     for (uint32_t o = 0; o < nmax; o += 2u) {
         const bool p0 = o < n, p1 = o + 1u < n;
         CandDesc e0 = {0u, 0u, 0u}, e1 = {0u, 0u, 0u};
@@ -339,7 +350,6 @@ __device__ __forceinline__ void multi_block(const Lvl4& c, uint32_t blk, int lan
         for (int q = 0; q < RC; ++q) { v0[q] = V4_DEAD; v1[q] = V4_DEAD; }
         if (p0) load_layers<ST, RC, SS>(c, it.r0, e0.src, e0.w, v0);
         if (p1) load_layers<ST, RC, SS>(c, it.r0, e1.src, e1.w, v1);
-        // (a lane without the candidate keeps DEAD + something small: never the maximum of a cell that has candidates)
         const int32_t a0 = (int32_t)((e0.delta << V4_SHIFT) + (V4_ORD_MASK - o)), a1 = (int32_t)((e1.delta << V4_SHIFT) + (V4_ORD_MASK - o - 1u));
 #pragma unroll
         for (int q = 0; q < RC; ++q) key[q] = max(key[q], max(v0[q] + a0, v1[q] + a1));
@@ -420,12 +430,9 @@ __device__ __forceinline__ unsigned long long giant_pack(int32_t value, uint32_t
     return ((unsigned long long)((uint32_t)value ^ 0x80000000u) << 32) | (unsigned long long)(0xFFFFFFFFu - ord);
 }
 
-// (out of line, arguments by value: its register needs and spills stay out of the paths every level takes)
 template <int ST, int RC, bool SS, bool DS, bool COMPACT, bool CHECK>
-__device__ __noinline__ void giant_cells(const Lvl4 c, GiantShared* gsp, uint32_t cta, uint32_t n_ctas, int warp, int ncw, int lane, Fold4* fp,
-                                         unsigned long long* gkey, unsigned int* gcnt, int RL) {
-    GiantShared& gs = *gsp;
-    Fold4& f = *fp;
+__device__ __forceinline__ void giant_cells(const Lvl4& c, GiantShared& gs, uint32_t cta, uint32_t n_ctas, int warp, int ncw, int lane, Fold4& f,
+                                            unsigned long long* gkey, unsigned int* gcnt, int RL) {
     static_assert(RC <= 10, "GiantShared::part");
     const uint32_t S = 32u * (uint32_t)ncw, CT = S, tid = (uint32_t)warp * 32u + (uint32_t)lane;
     const uint32_t t_mm = c.n_multi - c.n_mm;
@@ -563,11 +570,55 @@ __device__ __forceinline__ void run_level(const Lvl4& c, uint32_t gw, uint32_t g
     }
 }
 
+// The giant cells of a transition (header: n_giant > 0; never a compact one, dp_plan4.cpp), before its other units.  A function
+// of its own, with its own view of the transition: what it needs in registers (and spills) stays out of the paths every
+// level takes — inlined into run_generic it cost the 256-sample MHC_4 sweep 299 -> 380 ms without ever running there.
+template <int ST, int RC, bool CHECK>
+__device__ __noinline__ ulonglong2 run_giants(const Sweep4Args& a, const uint8_t* sb, uint32_t tile32, int l, int cta, int warp, int lane) {
+    const ProgDir d = *reinterpret_cast<const ProgDir*>(sb);
+    const ProgHdr h = *reinterpret_cast<const ProgHdr*>(sb + sizeof(ProgDir));
+    const uint32_t flags = d.flags;
+    Lvl4 c;
+    c.k = h.k; c.k2 = h.k2; c.n_copy = h.n_copy; c.n_multi = h.n_multi; c.n_big = h.n_big; c.n_dead = h.n_dead; c.n_mm = h.n_mm;
+    const uint8_t* const pb = (flags & PF_STAGED) ? sb + sizeof(ProgDir) : a.prog + (size_t)d.off16 * 16;
+    c.copy_p = pb + sizeof(ProgHdr); c.cell_p = pb + h.off_cell; c.cand_p = pb + h.off_cand; c.big_p = pb + h.off_big; c.dead_p = pb + h.off_dead;
+    c.level = l; c.R = a.R; c.nchunk = a.nchunk; c.rc = RC; c.m_nchunk = a.m_nchunk; c.l1 = a.grid == 1 && a.use_l1;
+    c.src32 = tile32; c.dst32 = tile32;
+    c.gt = a.gtile; c.cs = a.gcs;
+    c.pl = a.pred + h.pred_off;
+    c.prof = nullptr;
+    ProgLevelIn in;
+    if (CHECK) in = level_in(*a.chk, l);
+    c.in = &in;
+    const bool all = (flags & PF_ALL_CTAS) != 0;
+    const uint32_t gc = all ? (uint32_t)cta : 0u, gn = all ? (uint32_t)a.grid : 1u;
+    const bool ss = (flags & PF_SRC_SMEM) != 0, ds = (flags & PF_DST_SMEM) != 0;
+    __shared__ GiantShared giant_sh;
+    Fold4 f = {0ull, 0ull};
+    const int RL = a.nchunk * RC;
+    if (ss && ds) giant_cells<ST, RC, true, true, false, CHECK>(c, giant_sh, gc, gn, warp, a.ncw, lane, f, a.giant_key, a.giant_cnt, RL);
+    else if (ss) giant_cells<ST, RC, true, false, false, CHECK>(c, giant_sh, gc, gn, warp, a.ncw, lane, f, a.giant_key, a.giant_cnt, RL);
+    else if (ds) giant_cells<ST, RC, false, true, false, CHECK>(c, giant_sh, gc, gn, warp, a.ncw, lane, f, a.giant_key, a.giant_cnt, RL);
+    else giant_cells<ST, RC, false, false, false, CHECK>(c, giant_sh, gc, gn, warp, a.ncw, lane, f, a.giant_key, a.giant_cnt, RL);
+    return make_ulonglong2(f.sum, f.live);
+}
+
 // Everything but the staged compact transitions (below): hand-overs between the placements, HBM-resident levels,
 // wide-format programs, programs read in place.  Out of line, with a handful of scalar arguments: the narrow loop keeps
 // its own register allocation.  `sb` = the ring slot (directory entry, then the header and, if staged, the program).
-template <int ST, int RC, bool CHECK>
+// GIANT: the kernel variant for problems that have giant cells (in-degrees above 32).  The others run a variant without that
+// code: its mere presence — never executed — cost the 256-sample MHC_4 sweep 295 -> 344 ms (code layout, registers of the callers).
+template <int ST, int RC, bool CHECK, bool GIANT>
 __device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_t* sb, uint32_t tile32, int l, int cta, int warp, int lane) {
+    Fold4 f = {0ull, 0ull};
+    // giant cells first, before anything of this function is live in registers
+    if constexpr (GIANT) if (reinterpret_cast<const ProgHdr*>(sb + sizeof(ProgDir))->n_giant) {
+        const bool prof = a.prof != nullptr && cta == 0 && warp == 0 && lane == 0;
+        const long long tg0 = prof ? clock64() : 0;
+        const ulonglong2 fg = run_giants<ST, RC, CHECK>(a, sb, tile32, l, cta, warp, lane);
+        f.sum = fg.x; f.live = fg.y;
+        if (prof) a.prof[11] += (unsigned long long)(clock64() - tg0);
+    }
     const ProgDir d = *reinterpret_cast<const ProgDir*>(sb);
     const ProgHdr h = *reinterpret_cast<const ProgHdr*>(sb + sizeof(ProgDir));
     const uint32_t flags = d.flags;
@@ -587,22 +638,11 @@ __device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_
     const uint32_t gw = all ? (uint32_t)(cta * a.ncw + warp) : (uint32_t)warp;
     const uint32_t gs = all ? (uint32_t)(a.grid * a.ncw) : (uint32_t)a.ncw;
     const bool ss = (flags & PF_SRC_SMEM) != 0, ds = (flags & PF_DST_SMEM) != 0;
-    const uint32_t gc = all ? (uint32_t)cta : 0u, gn = all ? (uint32_t)a.grid : 1u;      // giant cells: one CTA each
-    __shared__ GiantShared giant_sh;
-    Fold4 f = {0ull, 0ull};
-#define DG_RUN(SS_, DS_, C_)                                                                           \
-    do {                                                                                               \
-        const long long tg0 = c.prof ? clock64() : 0;                                                  \
-        if (c.n_mm) giant_cells<ST, RC, SS_, DS_, C_, CHECK>(c, &giant_sh, gc, gn, warp, a.ncw, lane, &f, a.giant_key, a.giant_cnt, a.nchunk * RC); \
-        if (c.prof) c.prof[11] += (unsigned long long)(clock64() - tg0);                               \
-        run_level<ST, RC, SS_, DS_, C_, CHECK>(c, gw, gs, lane, f);                                    \
-    } while (0)
-    if (flags & PF_COMPACT) run_level<ST, RC, true, true, true, CHECK>(c, gw, gs, lane, f);      // (compact levels have no giant cell: dp_plan4.cpp)
-    else if (ss && ds) DG_RUN(true, true, false);
-    else if (ss) DG_RUN(true, false, false);
-    else if (ds) DG_RUN(false, true, false);
-    else DG_RUN(false, false, false);
-#undef DG_RUN
+    if (flags & PF_COMPACT) run_level<ST, RC, true, true, true, CHECK>(c, gw, gs, lane, f);
+    else if (ss && ds) run_level<ST, RC, true, true, false, CHECK>(c, gw, gs, lane, f);
+    else if (ss) run_level<ST, RC, true, false, false, CHECK>(c, gw, gs, lane, f);
+    else if (ds) run_level<ST, RC, false, true, false, CHECK>(c, gw, gs, lane, f);
+    else run_level<ST, RC, false, false, false, CHECK>(c, gw, gs, lane, f);
     return make_ulonglong2(f.sum, f.live);
 }
 
@@ -686,6 +726,61 @@ __device__ __forceinline__ void fast_multi(const Fast4& c, uint32_t blk, int r0,
     }
 }
 
+// The same with TWO lanes per cell (16 cells per unit): lane pair (2c, 2c+1) splits the cell's candidates by parity, the two
+// keys meet in one SHFL.BFLY per layer, and each lane stores half of the layers — the critical path of a narrow level is one
+// unit, and this halves it (the level's units still fit the CTA's warps: 4-6 blocks of 32 cells become 8-12 of 16).
+template <int ST, int RC, bool CHECK>
+__device__ __forceinline__ void fast_multi2(const Fast4& c, uint32_t blk, int r0, int lane, Fold4& f) {
+    const uint32_t t = blk * 16u + ((uint32_t)lane >> 1), sub = (uint32_t)lane & 1u;
+    uint2 cd = make_uint2(0u, 0u);
+    if (t < c.n_multi) cd = lds_v2(c.cell32 + 8u * t);
+    const uint32_t dst = cd.x & 1023u;
+    uint32_t n = cd.x >> 16;
+    if (n >= PROG_BIG_MIN) n = 0u;                                   // the warp form's
+    const uint32_t mine = (n + 1u - sub) >> 1;                       // candidates sub, sub + 2, ...
+    const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, mine);
+    if (nmax == 0u) return;
+    const uint32_t ca = c.cand32 + 4u * (cd.y + sub);
+    const uint32_t base = c.src32 + ((uint32_t)(r0 + 2) * (uint32_t)(ST * 4));
+    int32_t key[RC];
+#pragma unroll
+    for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
+    uint32_t x0 = lds_u32(ca), x1 = lds_u32(ca + 8u);
+    for (uint32_t i = 0; i < nmax; i += 2u) {
+        const uint32_t e0 = i < mine ? x0 : dead_cand<ST>(), e1 = i + 1u < mine ? x1 : dead_cand<ST>();
+        x0 = lds_u32(ca + 8u * (i + 2u)); x1 = lds_u32(ca + 8u * (i + 3u));      // (may run past the cell's list: unused then)
+        const uint32_t o = 2u * i + sub;
+        const int32_t add0 = (int32_t)(((e0 >> 12) << V4_SHIFT) + (V4_ORD_MASK - o));
+        const int32_t add1 = (int32_t)(((e1 >> 12) << V4_SHIFT) + (V4_ORD_MASK - o - 2u));
+        int32_t v0[RC], v1[RC];
+        lds_layers_free<ST, RC>(base + ((e0 & 1023u) << 2) - (((e0 >> 10) & 3u) * (uint32_t)(ST * 4)), v0);
+        lds_layers_free<ST, RC>(base + ((e1 & 1023u) << 2) - (((e1 >> 10) & 3u) * (uint32_t)(ST * 4)), v1);
+#pragma unroll
+        for (int q = 0; q < RC; ++q) key[q] = max(key[q], max(v0[q] + add0, v1[q] + add1));
+    }
+#pragma unroll
+    for (int q = 0; q < RC; ++q) key[q] = max(key[q], __shfl_xor_sync(0xFFFFFFFFu, key[q], 1));
+    if (n) {
+        uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
+        const uint32_t da = c.dst32 + ((uint32_t)(r0 + 2) * (uint32_t)ST + dst) * 4u;
+        constexpr int H = RC / 2;
+        if (sub == 0u) {
+#pragma unroll
+            for (int q = 0; q < H; ++q) {
+                pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
+                sts_s32(da + (uint32_t)(q * ST * 4), (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK));
+            }
+            if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
+        } else {
+#pragma unroll
+            for (int q = H; q < RC; ++q) {
+                pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
+                sts_s32(da + (uint32_t)(q * ST * 4), (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK));
+            }
+        }
+    }
+}
+
 template <int ST, int RC, bool CHECK>
 __device__ __forceinline__ void fast_big(const Fast4& c, uint32_t u, int r0, int lane, Fold4& f) {
     const uint32_t t = lds_u32(c.big32 + 4u * u);
@@ -750,7 +845,7 @@ __device__ __noinline__ bool wait_counter4(unsigned int* counter, unsigned int t
     return ok;
 }
 
-template <int ST, int RC, bool CHECK>
+template <int ST, int RC, bool CHECK, bool GIANT>
 __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) {
     extern __shared__ __align__(128) uint8_t smem4[];
     const int RL = a.nchunk * RC;
@@ -861,7 +956,12 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                 if (CHECK) in = level_in(*a.chk, l);
                 c.in = &in;
                 const uint32_t nch = (uint32_t)a.nchunk;
-                const uint32_t e0 = c.n_big * nch, e1 = e0 + ((c.n_multi + 31u) >> 5) * nch, e2 = e1 + ((c.n_copy + 31u) >> 5) * nch,
+#ifdef DG_FAST_LPC1
+                const uint32_t nmb = (c.n_multi + 31u) >> 5;
+#else
+                const uint32_t nmb = (c.n_multi + 15u) >> 4;        // two lanes per multi cell (fast_multi2)
+#endif
+                const uint32_t e0 = c.n_big * nch, e1 = e0 + nmb * nch, e2 = e1 + ((c.n_copy + 31u) >> 5) * nch,
                                e3 = e2 + ((c.n_dead + 31u) >> 5) * nch;
                 long long tu0 = 0;
                 if (profiling) { tu0 = clock64(); a.prof[18] += (unsigned long long)(tu0 - tk1); }
@@ -872,13 +972,17 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                     const uint32_t v = u - lo, blk = a.m_nchunk ? __umulhi(v, a.m_nchunk) : v, ch = v - blk * nch;
                     const int r0 = (int)ch * RC;
                     if (u < e0) fast_big<ST, RC, CHECK>(c, blk, r0, lane, f);
+#ifdef DG_FAST_LPC1
                     else if (u < e1) fast_multi<ST, RC, CHECK>(c, blk, r0, lane, f);
+#else
+                    else if (u < e1) fast_multi2<ST, RC, CHECK>(c, blk, r0, lane, f);
+#endif
                     else if (u < e2) fast_copy<ST, RC, CHECK>(c, blk, r0, lane, f);
                     else fast_dead<ST, RC>(c, blk, r0, lane);
                 }
                 if (profiling) a.prof[19] += (unsigned long long)(clock64() - tu0);
             } else {
-                const ulonglong2 fs = run_generic<ST, RC, CHECK>(a, slots + (size_t)slot * a.slot_bytes, tiles32, l, cta, warp, lane);
+                const ulonglong2 fs = run_generic<ST, RC, CHECK, GIANT>(a, slots + (size_t)slot * a.slot_bytes, tiles32, l, cta, warp, lane);
                 f.sum = fs.x; f.live = fs.y;
             }
         }
@@ -940,14 +1044,14 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
     }
 }
 
-template <int ST, int RC, bool CHECK>
+template <int ST, int RC, bool CHECK, bool GIANT>
 __global__ void __launch_bounds__(544, 1) dip_sweep4_kernel(const __grid_constant__ Sweep4Args a) {
-    sweep4_body<ST, RC, CHECK>(a, (int)blockIdx.x);
+    sweep4_body<ST, RC, CHECK, GIANT>(a, (int)blockIdx.x);
 }
 
 // Many independent problems in ONE launch (dg_dip_run_many): CTA b works on problem cta_map[b].x as its local CTA
 // cta_map[b].y; the problem's arguments are copied to shared memory once.
-template <int ST, int RC>
+template <int ST, int RC, bool GIANT>
 __global__ void __launch_bounds__(544, 1) dip_sweep4_many_kernel(const Sweep4Args* __restrict__ all, const int2* __restrict__ cta_map) {
     __shared__ Sweep4Args sa;
     const int2 who = cta_map[blockIdx.x];
@@ -956,7 +1060,7 @@ __global__ void __launch_bounds__(544, 1) dip_sweep4_many_kernel(const Sweep4Arg
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sa);
     for (uint32_t x = threadIdx.x; x < sizeof(Sweep4Args) / 4; x += blockDim.x) dst[x] = src[x];
     __syncthreads();
-    sweep4_body<ST, RC, false>(sa, who.y);
+    sweep4_body<ST, RC, false, GIANT>(sa, who.y);
 }
 
 constexpr size_t sweep4_smem_bytes(int stride, int RL, int slot_bytes, int nslot) {

@@ -70,7 +70,7 @@ def load() -> C.CDLL:
             raise DipGenieCudaError(
                 f"{_build.CUDA_LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(there is no CPU fallback for the device path)")
-        lib = C.CDLL(_build.CUDA_LIB)
+        lib = C.CDLL(os.environ.get("DG_CUDA_LIB_OVERRIDE") or _build.CUDA_LIB)      # (override: A/B builds of tools/ab)
         lib.dg_create.restype = C.c_void_p
         lib.dg_create.argtypes = [C.c_int]
         lib.dg_destroy.argtypes = [C.c_void_p]
