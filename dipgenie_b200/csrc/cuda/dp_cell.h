@@ -274,6 +274,9 @@ struct TraceView {
     const uint32_t* lvl_n1 = nullptr;   // [L] S1 vertices of the level
     const uint32_t* lvl_m = nullptr;    // [L] M vertices of the level
     int32_t RL = 0;                     // layers per level in the code array
+    // [V] fast path of a step (device traceback): bit 31 set = the vertex has exactly ONE in-edge, whose `pos | w << 16`
+    // sits in the low bits — a cell of two such vertices steps with two independent loads and no code (nullable)
+    const uint32_t* vup = nullptr;
 };
 
 struct TraceState { int32_t r, i2, j2; };   // cell (r, i2, j2) of some level
@@ -286,6 +289,15 @@ DG_HD bool trace_step(const TraceView& v, const PredT* pred, int l, TraceState& 
     constexpr uint32_t MK = (sizeof(PredT) == 2) ? 0xFFu : 0xFFFFu;
     const int32_t mid = v.level_off[l + 1];
     if (v.vinfo) {
+        if (v.vup) {
+            const uint32_t ux = v.vup[mid + s.i2], uy = v.vup[mid + s.j2];
+            if ((ux & uy) >> 31) {
+                wu = (int)((ux >> 16) & 0x7FFFu); wv = (int)((uy >> 16) & 0x7FFFu);
+                i2_old = s.i2; j2_old = s.j2;
+                s.r -= wu + wv; s.i2 = (int)(ux & 0xFFFFu); s.j2 = (int)(uy & 0xFFFFu);
+                return s.r >= 0;
+            }
+        }
         const int32_t a0 = v.in_off[mid + s.i2], d1 = v.in_off[mid + s.i2 + 1] - a0;
         const int32_t b0 = v.in_off[mid + s.j2], d2 = v.in_off[mid + s.j2 + 1] - b0;
         if (d1 <= 0 || d2 <= 0) return false;

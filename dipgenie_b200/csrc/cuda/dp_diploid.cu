@@ -1192,6 +1192,7 @@ struct dg_dip {
     DevBuf<int32_t> v4_wide, v4_wide_full, v4_sink;
     DevBuf<unsigned long long> v4_gkey;          // giant cells: where the CTAs' slices meet (dp_sweep4.cuh: giant_cells); null without such cells
     DevBuf<unsigned int> v4_gcnt;
+    DevBuf<uint32_t> v4_vup;                     // traceback fast path (dp_cell.h: TraceView::vup)
     DevBuf<uint8_t> v4_prog, v4_dom;
     DevBuf<uint16_t> v4_pred, v4_cls, v4_vslot;
     DevBuf<uint32_t> v4_vinfo, v4_mpre, v4_n1, v4_np, v4_m, v4_z, v4_dm, v4_tflags;
@@ -1458,6 +1459,8 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     // the program: zero (section padding), then one CTA per transition
     DG_CUDA(ctx, cudaEventRecord(d->ev[0], s));
     DG_CUDA(ctx, cudaMemsetAsync(d->v4_prog.p, 0, (size_t)q.prog_bytes + 16, s));
+    DG_CUDA(ctx, d->v4_vup.alloc((size_t)p.V, s));
+    vup_fill_kernel<<<ctx->sm_count * 4, 256, 0, s>>>(d->in_off.p, d->in_edge.p, p.V, d->v4_vup.p);
     if (!q.full.wide_list.empty() + q.n_relocate > 0)      // the two padding layers of every cell of the HBM tile (the sweep only writes layers >= 0)
         fill_dead_kernel<<<ctx->sm_count * 2, 256, 0, s>>>(d->tile0.p, (long long)q.gtile_cells);
     Fill4Args fa;
@@ -1478,7 +1481,7 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     d->device_bytes = d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->lvlW.bytes() + d->masks.bytes() +
                       d->msrc_off.bytes() + d->mdst_off.bytes() + d->pred_off.bytes() + d->v4_dir.bytes() + d->v4_hdr.bytes() +
                       d->v4_prog_off.bytes() + d->v4_cls.bytes() + d->v4_vinfo.bytes() + d->v4_mpre.bytes() + d->v4_prog.bytes() +
-                      d->v4_pred.bytes() + d->tile0.bytes() + d->v4_vslot.bytes() + d->v4_dir_full.bytes() + d->level_sum.bytes() + d->level_live.bytes() +
+                      d->v4_pred.bytes() + d->tile0.bytes() + d->v4_vup.bytes() + d->v4_gkey.bytes() + d->v4_vslot.bytes() + d->v4_dir_full.bytes() + d->level_sum.bytes() + d->level_live.bytes() +
                       d->anc.bytes() + d->seg_p1.bytes() + d->seg_p2.bytes();
     p.in_edge.clear(); p.in_edge.shrink_to_fit();
     p.in_dst.clear(); p.in_dst.shrink_to_fit();
@@ -1660,6 +1663,7 @@ static void fill_trace_args(const dg_dip* d, TraceArgs& ta) {
     if (d->v4) {
         ta.pred = d->v4_pred.p; ta.sink_v4 = d->v4_sink.p;
         v.vinfo = d->v4_vinfo.p; v.lvl_n1 = d->v4_n1.p; v.lvl_m = d->v4_m.p; v.RL = d->p4.RL;
+        v.vup = getenv("DG_NO_VUP") ? nullptr : d->v4_vup.p;
     }
     ta.cap = p.R + 2; ta.shift = d->shift; ta.out = d->tout.p; ta.p1 = d->p1.p; ta.p2 = d->p2.p;
 }
@@ -1988,6 +1992,18 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
         }
         const int k = i % K;
         collect(k);                               // the slot's previous sample (its kernels ran while the host planned others)
+        // Admission by memory: a wide-panel sample needs gigabytes (programs + codes); wait for earlier samples to finish
+        // (oldest first) until this one fits, instead of failing its allocation.
+        if (d->v4) {
+            const size_t need = (size_t)d->p4.prog_bytes + (size_t)d->p4.pred_elems * 2 + (size_t)d->p4.gtile_cells * 4 +
+                                (size_t)d->plan.V * 128 + ((size_t)256 << 20);
+            for (int back = K - 1; back >= 1; --back) {
+                size_t free_b = 0, total_b = 0;
+                if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b >= need) break;
+                const int kk = (int)((i + K - back) % K);          // slots in launch order, oldest first
+                if (slot[(size_t)kk]) { collect(kk); dg_release_cached_memory(ctx); }
+            }
+        }
         int r = dip_create_device(ctx, d.get());     // (uploads stay on this thread: a pageable H2D issued by a worker on a
                                                      //  busy slot stream blocks that worker until the slot's sweep ends)
         if (!r) r = dg_dip_run(ctx, d.get(), 0);

@@ -123,6 +123,14 @@ __global__ void __launch_bounds__(FILL4_THREADS) prog_fill_kernel(const Fill4Arg
     }
 }
 
+// vup[v] = 1 << 31 | in_edge of v when v has exactly one in-edge, else 0 (dp_cell.h: TraceView::vup).
+__global__ void vup_fill_kernel(const int32_t* __restrict__ in_off, const uint32_t* __restrict__ in_edge, int32_t V, uint32_t* __restrict__ vup) {
+    for (int32_t v = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x); v < V; v += (int32_t)(gridDim.x * blockDim.x)) {
+        const int32_t a0 = in_off[v];
+        vup[v] = in_off[v + 1] - a0 == 1 ? (0x80000000u | in_edge[a0]) : 0u;
+    }
+}
+
 // Fills `n` int32 cells with DEAD (padding layers of the HBM tiles).
 __global__ void fill_dead_kernel(int32_t* p, long long n) {
     for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (long long)gridDim.x * blockDim.x) p[x] = V4_DEAD;
@@ -726,61 +734,6 @@ __device__ __forceinline__ void fast_multi(const Fast4& c, uint32_t blk, int r0,
     }
 }
 
-// The same with TWO lanes per cell (16 cells per unit): lane pair (2c, 2c+1) splits the cell's candidates by parity, the two
-// keys meet in one SHFL.BFLY per layer, and each lane stores half of the layers — the critical path of a narrow level is one
-// unit, and this halves it (the level's units still fit the CTA's warps: 4-6 blocks of 32 cells become 8-12 of 16).
-template <int ST, int RC, bool CHECK>
-__device__ __forceinline__ void fast_multi2(const Fast4& c, uint32_t blk, int r0, int lane, Fold4& f) {
-    const uint32_t t = blk * 16u + ((uint32_t)lane >> 1), sub = (uint32_t)lane & 1u;
-    uint2 cd = make_uint2(0u, 0u);
-    if (t < c.n_multi) cd = lds_v2(c.cell32 + 8u * t);
-    const uint32_t dst = cd.x & 1023u;
-    uint32_t n = cd.x >> 16;
-    if (n >= PROG_BIG_MIN) n = 0u;                                   // the warp form's
-    const uint32_t mine = (n + 1u - sub) >> 1;                       // candidates sub, sub + 2, ...
-    const uint32_t nmax = __reduce_max_sync(0xFFFFFFFFu, mine);
-    if (nmax == 0u) return;
-    const uint32_t ca = c.cand32 + 4u * (cd.y + sub);
-    const uint32_t base = c.src32 + ((uint32_t)(r0 + 2) * (uint32_t)(ST * 4));
-    int32_t key[RC];
-#pragma unroll
-    for (int q = 0; q < RC; ++q) key[q] = V4_DEAD;
-    uint32_t x0 = lds_u32(ca), x1 = lds_u32(ca + 8u);
-    for (uint32_t i = 0; i < nmax; i += 2u) {
-        const uint32_t e0 = i < mine ? x0 : dead_cand<ST>(), e1 = i + 1u < mine ? x1 : dead_cand<ST>();
-        x0 = lds_u32(ca + 8u * (i + 2u)); x1 = lds_u32(ca + 8u * (i + 3u));      // (may run past the cell's list: unused then)
-        const uint32_t o = 2u * i + sub;
-        const int32_t add0 = (int32_t)(((e0 >> 12) << V4_SHIFT) + (V4_ORD_MASK - o));
-        const int32_t add1 = (int32_t)(((e1 >> 12) << V4_SHIFT) + (V4_ORD_MASK - o - 2u));
-        int32_t v0[RC], v1[RC];
-        lds_layers_free<ST, RC>(base + ((e0 & 1023u) << 2) - (((e0 >> 10) & 3u) * (uint32_t)(ST * 4)), v0);
-        lds_layers_free<ST, RC>(base + ((e1 & 1023u) << 2) - (((e1 >> 10) & 3u) * (uint32_t)(ST * 4)), v1);
-#pragma unroll
-        for (int q = 0; q < RC; ++q) key[q] = max(key[q], max(v0[q] + add0, v1[q] + add1));
-    }
-#pragma unroll
-    for (int q = 0; q < RC; ++q) key[q] = max(key[q], __shfl_xor_sync(0xFFFFFFFFu, key[q], 1));
-    if (n) {
-        uint16_t* pl = c.pl + ((size_t)r0 * c.n_multi + t);
-        const uint32_t da = c.dst32 + ((uint32_t)(r0 + 2) * (uint32_t)ST + dst) * 4u;
-        constexpr int H = RC / 2;
-        if (sub == 0u) {
-#pragma unroll
-            for (int q = 0; q < H; ++q) {
-                pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
-                sts_s32(da + (uint32_t)(q * ST * 4), (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK));
-            }
-            if (CHECK) fold_multi(f, *c.in, c.R, t, r0, key, RC);
-        } else {
-#pragma unroll
-            for (int q = H; q < RC; ++q) {
-                pl[(size_t)q * c.n_multi] = (uint16_t)key[q];
-                sts_s32(da + (uint32_t)(q * ST * 4), (int32_t)((uint32_t)key[q] & ~V4_ORD_MASK));
-            }
-        }
-    }
-}
-
 template <int ST, int RC, bool CHECK>
 __device__ __forceinline__ void fast_big(const Fast4& c, uint32_t u, int r0, int lane, Fold4& f) {
     const uint32_t t = lds_u32(c.big32 + 4u * u);
@@ -956,11 +909,9 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                 if (CHECK) in = level_in(*a.chk, l);
                 c.in = &in;
                 const uint32_t nch = (uint32_t)a.nchunk;
-#ifdef DG_FAST_LPC1
+                // (two lanes per multi cell — 16 cells per unit, candidates split by parity, SHFL.BFLY combine — was tried: the
+                // shorter units do not pay for their doubled count: 301 against 289 ms for 256 resident MHC_4 samples)
                 const uint32_t nmb = (c.n_multi + 31u) >> 5;
-#else
-                const uint32_t nmb = (c.n_multi + 15u) >> 4;        // two lanes per multi cell (fast_multi2)
-#endif
                 const uint32_t e0 = c.n_big * nch, e1 = e0 + nmb * nch, e2 = e1 + ((c.n_copy + 31u) >> 5) * nch,
                                e3 = e2 + ((c.n_dead + 31u) >> 5) * nch;
                 long long tu0 = 0;
@@ -972,11 +923,7 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                     const uint32_t v = u - lo, blk = a.m_nchunk ? __umulhi(v, a.m_nchunk) : v, ch = v - blk * nch;
                     const int r0 = (int)ch * RC;
                     if (u < e0) fast_big<ST, RC, CHECK>(c, blk, r0, lane, f);
-#ifdef DG_FAST_LPC1
                     else if (u < e1) fast_multi<ST, RC, CHECK>(c, blk, r0, lane, f);
-#else
-                    else if (u < e1) fast_multi2<ST, RC, CHECK>(c, blk, r0, lane, f);
-#endif
                     else if (u < e2) fast_copy<ST, RC, CHECK>(c, blk, r0, lane, f);
                     else fast_dead<ST, RC>(c, blk, r0, lane);
                 }
