@@ -208,11 +208,11 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
     }
     q.cells_written = written; q.cells_total = total;
     for (int l = 0; l + 1 < L; ++l) q.max_giant = std::max(q.max_giant, q.hdr[l].n_giant);
-    if (q.max_giant > 256) { why = "more than 256 cells above 1024 candidates in one level"; return false; }     // dp_sweep4.cuh: GIANT_LIST_MAX
+    if (q.max_giant > 1024) { why = "more than 1024 cells above 1024 candidates in one level"; return false; }     // dp_sweep4.cuh: GIANT_LIST_MAX
     for (int l = 0; l + 1 < L; ++l) {
         if (bytes[l] == ~0ull) { why = "a transition's program exceeds 4 GB"; return false; }
-        q.prog_off[(size_t)l + 1] = q.prog_off[l] + bytes[l];
-        if (q.prog_off[l] / 16 > 0xFFFFFFFFull) { why = "program larger than 64 GB"; return false; }
+        q.prog_off[(size_t)l + 1] = q.prog_off[l] + (bytes[l] + PROG_ALIGN - 1) / PROG_ALIGN * PROG_ALIGN;
+        if (q.prog_off[l] / PROG_ALIGN > 0xFFFFFFFFull) { why = "program larger than 256 GB"; return false; }
     }
     q.prog_bytes = q.prog_off[(size_t)L - 1];
     for (int l = 0; l < L; ++l) {
@@ -226,7 +226,7 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
     for (int l = 0; l + 1 < L; ++l) {
         ProgDir d;
         memset(&d, 0, sizeof d);
-        d.off16 = (uint32_t)(q.prog_off[l] / 16);
+        d.off64 = (uint32_t)(q.prog_off[l] / PROG_ALIGN);
         d.flags = q.tflags[l];
         d.level = l;
         d.prog16 = (uint32_t)(bytes[l] / 16);

@@ -232,10 +232,23 @@ int lane_blocks(const DipPlan& p, int l, bool allow_long, uint16_t* out, uint16_
 
 }  // namespace
 
+// Checkpoints of the traceback: every cell of a checkpoint level walks back to the next checkpoint (dip_anc_kernel), so a
+// checkpoint costs (R+1) k^2 walkers times its distance to the next one — the narrow levels are the cheap ones.  From `cur` the
+// next checkpoint is the narrowest level T/2 .. 3T/2 below; when that one is still wide (above 1.6 x the 10th percentile of
+// the widths: a bubble of the graph that spans the whole window), the search goes on down to 16 T below for the first level
+// under that bound — the walkers of the narrow level `cur` pay the longer way, a wide level's (quadratically more) never start.
 std::vector<int32_t> choose_checkpoints(const std::vector<int32_t>& level_off, int T) {
     const int L = (int)level_off.size() - 1;
     std::vector<int32_t> cp;
     if (T < 1) T = 1;
+    auto width = [&](int l) { return level_off[l + 1] - level_off[l]; };
+    int32_t bound = 0;
+    {
+        std::vector<int32_t> w((size_t)L);
+        for (int l = 0; l < L; ++l) w[(size_t)l] = width(l);
+        std::nth_element(w.begin(), w.begin() + L / 10, w.end());
+        bound = w[(size_t)(L / 10)] + (w[(size_t)(L / 10)] * 3 + 4) / 5;
+    }
     int cur = L - 1;
     cp.push_back(cur);
     while (cur > 0) {
@@ -243,7 +256,14 @@ std::vector<int32_t> choose_checkpoints(const std::vector<int32_t>& level_off, i
         if (lo <= 0) { cp.push_back(0); break; }
         int best = hi;
         for (int l = hi; l >= lo; --l)
-            if (level_off[l + 1] - level_off[l] < level_off[best + 1] - level_off[best]) best = l;
+            if (width(l) < width(best)) best = l;
+        if (width(best) > bound) {
+            const int far = std::max(1, cur - 16 * T);
+            for (int l = lo - 1; l >= far; --l) {
+                if (width(l) < width(best)) best = l;
+                if (width(best) <= bound) break;
+            }
+        }
         cp.push_back(best);
         cur = best;
     }

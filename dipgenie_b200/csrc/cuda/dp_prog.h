@@ -53,6 +53,7 @@ namespace dg {
 constexpr int32_t V4_DEAD = INT32_MIN;
 constexpr int V4_SHIFT = KEY_SHIFT;                       // 10
 constexpr uint32_t V4_ORD_MASK = (1u << V4_SHIFT) - 1u;   // 1023
+constexpr uint32_t PROG_ALIGN = 64;                       // alignment of a transition's program in the program buffer (ProgDir::off64)
 constexpr uint32_t PROG_BIG_MIN = 12;                     // multi cells with this many candidates go to the warp form
 constexpr uint32_t PROG_KEY_CAND = 1024;                  // candidates per cell whose ordinal fits the packed key (code = low 16 key bits)
 constexpr uint32_t PROG_MAX_CAND = 32768;                 // most candidates of a cell: above PROG_KEY_CAND the warp form keeps the ROUND
@@ -74,7 +75,7 @@ enum : uint32_t {
 
 // Directory entry of a transition (32 bytes, copied into the slot in front of the program).
 struct ProgDir {
-    uint32_t off16;        // program offset in the program buffer, units of 16 bytes
+    uint32_t off64;        // program offset in the program buffer, units of 64 bytes (programs start 64-byte aligned: 256 GB)
     uint32_t stage_bytes;  // bytes the producer copies after the entry: the whole program or just the header
     uint32_t wait_target;
     uint32_t flags;

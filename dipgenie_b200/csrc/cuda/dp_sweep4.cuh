@@ -427,7 +427,7 @@ __device__ __forceinline__ void big_cell(const Lvl4& c, uint32_t x, int lane, Fo
 // (approximator.cpp:657-659), for up to PROG_MAX_CAND candidates.  The code is the plain ordinal.  M x M cells are the last
 // n_mm multi cells; every CTA derives the same ordered list of the giant ones.  Uniform control flow within a CTA, named
 // barrier 2 over its compute warps.
-constexpr int GIANT_LIST_MAX = 256;
+constexpr int GIANT_LIST_MAX = 1024;
 struct GiantShared {
     int2 part[16][10];              // [warp][layer of the chunk]: (value, ordinal)
     uint32_t list[GIANT_LIST_MAX];  // M x M indices of the giant cells, ascending
@@ -588,7 +588,7 @@ __device__ __noinline__ ulonglong2 run_giants(const Sweep4Args& a, const uint8_t
     const uint32_t flags = d.flags;
     Lvl4 c;
     c.k = h.k; c.k2 = h.k2; c.n_copy = h.n_copy; c.n_multi = h.n_multi; c.n_big = h.n_big; c.n_dead = h.n_dead; c.n_mm = h.n_mm;
-    const uint8_t* const pb = (flags & PF_STAGED) ? sb + sizeof(ProgDir) : a.prog + (size_t)d.off16 * 16;
+    const uint8_t* const pb = (flags & PF_STAGED) ? sb + sizeof(ProgDir) : a.prog + (size_t)d.off64 * PROG_ALIGN;
     c.copy_p = pb + sizeof(ProgHdr); c.cell_p = pb + h.off_cell; c.cand_p = pb + h.off_cand; c.big_p = pb + h.off_big; c.dead_p = pb + h.off_dead;
     c.level = l; c.R = a.R; c.nchunk = a.nchunk; c.rc = RC; c.m_nchunk = a.m_nchunk; c.l1 = a.grid == 1 && a.use_l1;
     c.src32 = tile32; c.dst32 = tile32;
@@ -632,7 +632,7 @@ __device__ __noinline__ ulonglong2 run_generic(const Sweep4Args& a, const uint8_
     const uint32_t flags = d.flags;
     Lvl4 c;
     c.k = h.k; c.k2 = h.k2; c.n_copy = h.n_copy; c.n_multi = h.n_multi; c.n_big = h.n_big; c.n_dead = h.n_dead; c.n_mm = h.n_giant ? h.n_mm : 0u;
-    const uint8_t* const pb = (flags & PF_STAGED) ? sb + sizeof(ProgDir) : a.prog + (size_t)d.off16 * 16;
+    const uint8_t* const pb = (flags & PF_STAGED) ? sb + sizeof(ProgDir) : a.prog + (size_t)d.off64 * PROG_ALIGN;
     c.copy_p = pb + sizeof(ProgHdr); c.cell_p = pb + h.off_cell; c.cand_p = pb + h.off_cand; c.big_p = pb + h.off_big; c.dead_p = pb + h.off_dead;
     c.level = l; c.R = a.R; c.nchunk = a.nchunk; c.rc = RC; c.m_nchunk = a.m_nchunk; c.l1 = a.grid == 1 && a.use_l1;
     c.src32 = tile32; c.dst32 = tile32;
@@ -845,7 +845,7 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
             const int cnt = min(32, n_my - i0);
             for (int j = 0; j < cnt; ++j) {
                 const int32_t l = __shfl_sync(0xFFFFFFFFu, lv, j);
-                const uint32_t off16 = __shfl_sync(0xFFFFFFFFu, f.x, j), bytes = __shfl_sync(0xFFFFFFFFu, f.y, j);
+                const uint32_t off64 = __shfl_sync(0xFFFFFFFFu, f.x, j), bytes = __shfl_sync(0xFFFFFFFFu, f.y, j);
                 const uint32_t fl = __shfl_sync(0xFFFFFFFFu, f.w, j), all16 = __shfl_sync(0xFFFFFFFFu, p16, j);
                 if (lane == 0) {
                     // a program too large for a slot is read in place by the compute warps: bring it into L2 now, NS levels
@@ -855,14 +855,14 @@ __device__ __forceinline__ void sweep4_body(const Sweep4Args& a, const int cta) 
                         const uint32_t parts = (fl & PF_ALL_CTAS) ? (uint32_t)a.grid : 1u;
                         const uint32_t per16 = (all16 + parts - 1u) / parts, lo16 = min(all16, per16 * (uint32_t)(parts > 1u ? cta : 0));
                         const uint32_t n16 = min(min(all16 - lo16, per16), 16384u);
-                        if (n16) l2_prefetch_bulk(a.prog + ((size_t)off16 + lo16) * 16, n16 * 16u);
+                        if (n16) l2_prefetch_bulk(a.prog + (size_t)off64 * PROG_ALIGN + (size_t)lo16 * 16, n16 * 16u);
                     }
                     if (!first_round) mbar_wait(smem_u32(empty + slot), use_parity);
                     const uint32_t bar = smem_u32(full + slot);
                     const uint32_t dst = smem_u32(slots + (size_t)slot * a.slot_bytes);
                     mbar_expect_tx(bar, (uint32_t)sizeof(ProgDir) + bytes);
                     bulk_g2s(dst, a.dir + l, (uint32_t)sizeof(ProgDir), bar);
-                    bulk_g2s(dst + (uint32_t)sizeof(ProgDir), a.prog + (size_t)off16 * 16, bytes, bar);
+                    bulk_g2s(dst + (uint32_t)sizeof(ProgDir), a.prog + (size_t)off64 * PROG_ALIGN, bytes, bar);
                 }
                 if (++slot == NS) { slot = 0; if (first_round) first_round = false; else use_parity ^= 1u; }
             }

@@ -110,14 +110,15 @@ extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const
     for (int l = 0; l + 1 < L; ++l) {
         const ProgDir& d = q.full.dir[l];
         if (d.level != l) return -9;
-        const size_t bytes = (size_t)(q.prog_off[(size_t)l + 1] - q.prog_off[l]);
+        const size_t bytes = (size_t)d.prog16 * 16, room = (size_t)(q.prog_off[(size_t)l + 1] - q.prog_off[l]);
+        if (room < bytes || room - bytes >= PROG_ALIGN) return -11;      // programs start PROG_ALIGN-aligned
         prog.assign(bytes, 0);
         prog_fill_level_host(p, q, l, prog.data());
         ProgHdr h;
         memcpy(&h, prog.data(), sizeof h);
         const bool compact = d.flags & PF_COMPACT, ss = d.flags & PF_SRC_SMEM, ds = d.flags & PF_DST_SMEM, reloc = d.flags & PF_RELOCATE;
         if ((d.flags & PF_STAGED) ? (d.stage_bytes != bytes || bytes + sizeof(ProgDir) > (size_t)sh.slot_bytes) : d.stage_bytes != sizeof(ProgHdr)) return -10;
-        if ((uint64_t)d.off16 * 16 != q.prog_off[l]) return -11;
+        if ((uint64_t)d.off64 * PROG_ALIGN != q.prog_off[l]) return -11;
         if (reloc != (ss != ds)) return -16;
         if (ss != (q.lvl_dom[l] == 0) || ds != (q.lvl_dom[l + 1] == 0)) return -16;
         const ProgLayout lay = prog_layout(compact, h.n_copy, h.n_multi, h.n_cand, h.n_big, h.n_dead);
@@ -130,7 +131,7 @@ extern "C" int emu4_dp_diploid(int32_t n_levels, const int32_t* level_off, const
         if (idle && (reloc || h.n_copy + h.n_multi + h.n_dead != 0)) return -17;
         if (!idle) {
             const ProgDir& dt = q.timed.dir[(size_t)timed_at[l]];
-            if (dt.off16 != d.off16 || dt.stage_bytes != d.stage_bytes || ((dt.flags ^ d.flags) & ~(uint32_t)(PF_WAIT | PF_ARRIVE)) != 0) return -17;
+            if (dt.off64 != d.off64 || dt.stage_bytes != d.stage_bytes || ((dt.flags ^ d.flags) & ~(uint32_t)(PF_WAIT | PF_ARRIVE)) != 0) return -17;
             n_compact += compact; n_staged += (d.flags & PF_STAGED) != 0; n_big += h.n_big; n_all += (d.flags & PF_ALL_CTAS) != 0;
         }
         written.assign((size_t)cap_d, 0);

