@@ -1254,7 +1254,7 @@ static bool sweep4_shape(int R, int grid, bool packed, bool giant, Sweep4Shape& 
     if (const char* e = getenv("DG_V4_SLOT")) sh.slot_bytes = std::max(256, atoi(e) / 16 * 16);
     sh.nslot = 4;
     if (const char* e = getenv("DG_V4_NSLOT")) sh.nslot = std::max(2, std::min(16, atoi(e)));
-    ncw = packed ? 8 : 12;
+    ncw = packed || giant ? 8 : 12;            // (wide panels, 90 walks: 8 / 12 / 16 compute warps 618 / 636 / 661 ms per sweep)
     if (const char* e = getenv("DG_V4_NCW")) ncw = std::max(1, std::min(16, atoi(e)));
     sh.grid = std::max(1, grid);
     const int RL = (R + rc) / rc * rc;
@@ -1906,7 +1906,8 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
     // uploads, launches and collects in sample order
     int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     if (const char* e = getenv("DG_HOST_THREADS")) hw = std::max(1, atoi(e));   // this process's share of the host cores (one process per GPU)
-    int W = std::max(1, std::min({(int)n, 8, hw / 2}));          // two planner threads per worker scale best (profiles/r01b)
+    int W = std::max(1, std::min((int)n, hw));                   // one planner per core when there are samples enough (22 samples, 16 cores:
+                                                                 // 16 x 1 thread 324 ms per call, 8 x 2 threads 349-366 ms, 11 x 1 363-374 ms)
     if (const char* e = getenv("DG_PLAN_WORKERS")) W = std::max(1, std::min({atoi(e), (int)n, hw}));
     const int lookahead = W + 2;
     const bool pinned = !getenv("DG_NO_PINNED_PLAN");

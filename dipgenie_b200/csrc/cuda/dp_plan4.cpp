@@ -146,14 +146,9 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
             else if (d >= 2) list[n1 + b++] = pos;
             else list[n1 + m + c++] = pos;
         }
-        // every class in ascending SLOT order: the cells of a block of 32 then sit next to each other in the tile wherever
-        // the block runs along a row (coalesced HBM accesses); the tie-break is not affected — it orders the candidates
-        // of one cell, by source position
-        auto by_slot = [&](uint16_t x, uint16_t y) { return q.vslot[(size_t)lo + x] < q.vslot[(size_t)lo + y]; };
-        std::sort(list, list + na, by_slot);
-        std::sort(list + na, list + n1, by_slot);
-        std::sort(list + n1, list + n1 + m, by_slot);
-        std::sort(list + n1 + m, list + (hi - lo), by_slot);
+        // (every class stays in POSITION order.  Slot order was worth something while the HBM tile was layer-major — the cells of
+        // a block then sat next to each other; with the cell-major tile a cell is its own 96-byte record, and the four sorts
+        // per level were 15 % of the planner's time.  The tie-break never depended on it: it orders the candidates of one cell.)
         for (uint32_t x = 0; x < n1; ++x) q.vinfo[(size_t)lo + list[x]] = x;
         for (uint32_t x = 0; x < m; ++x) {
             const int32_t v = lo + list[n1 + x];

@@ -160,7 +160,8 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
                 const int32_t col = g.col_val[c];
                 if (local[col] < 0) { local[col] = 0; uni.push_back(col); }
             }
-            std::sort(uni.begin(), uni.end());
+            // (bit positions in first-seen order: the masks only ever meet in popcounts of AND / XOR within this transition, any
+            // bijection of its colours onto bits gives the same pair scores)
             for (size_t x = 0; x < uni.size(); ++x) local[uni[x]] = (int32_t)x;
             for (int32_t v = lo; v < hi; ++v) {
                 uint64_t* m = (v < mid) ? &p.masks[(size_t)p.msrc_off[l] + (size_t)(v - lo) * 2 * W]
