@@ -1906,8 +1906,9 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
     // uploads, launches and collects in sample order
     int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     if (const char* e = getenv("DG_HOST_THREADS")) hw = std::max(1, atoi(e));   // this process's share of the host cores (one process per GPU)
-    int W = std::max(1, std::min((int)n, hw));                   // one planner per core when there are samples enough (22 samples, 16 cores:
-                                                                 // 16 x 1 thread 324 ms per call, 8 x 2 threads 349-366 ms, 11 x 1 363-374 ms)
+    int W = std::max(1, std::min({(int)n, 8, hw / 2}));          // two planner threads per worker (22 samples, 16 cores: 8 x 2 threads 349-366 ms
+                                                                 // per call; 16 x 1 thread 324 ms once 18 page-locked plan blocks are pinned, but
+                                                                 // 380-700 ms in the calls that still pin them: DG_PLAN_WORKERS=16 for long runs)
     if (const char* e = getenv("DG_PLAN_WORKERS")) W = std::max(1, std::min({atoi(e), (int)n, hw}));
     const int lookahead = W + 2;
     const bool pinned = !getenv("DG_NO_PINNED_PLAN");
@@ -1920,9 +1921,6 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
     std::condition_variable cv;
     int next = 0, consumed = 0;
     auto worker = [&]() {
-#if defined(_OPENMP)
-        omp_set_num_threads(std::max(1, hw / W));
-#endif
         for (;;) {
             int i;
             {
@@ -1931,6 +1929,10 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
                 if (next >= n) return;
                 i = next++;
             }
+#if defined(_OPENMP)
+            // the cores are shared by the planners still at work: the last wave (fewer samples than workers) gets more each
+            omp_set_num_threads(std::max(1, hw / std::max(1, std::min(W, (int)n - i))));
+#endif
             const dg_dip_input_t& x = in[i];
             // the plan is written straight into page-locked memory: about 60 bytes per vertex on the pangenome
             // panels (an array that does not fit any more goes to the heap and is copied from there)
