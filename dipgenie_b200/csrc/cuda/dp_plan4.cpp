@@ -235,7 +235,10 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
     }
     schedule(q.full, shape.grid);
     schedule(q.timed, shape.grid);
+    // cell records padded to whole 32-byte sectors — unless the tile then outgrows the L2 (126 MB on B200: 40 layers x 824^2
+    // slots = 130 MB at 192 bytes per cell, 114 MB at 168), where an even word count (8-byte stores) has to do
     q.gcs = (q.RL + 2 + 7) / 8 * 8;
+    if ((int64_t)q.gcs * q.hstride * q.hstride * 4 > ((int64_t)96 << 20)) q.gcs = (q.RL + 2 + 1) / 2 * 2;
     q.gtile_cells = (int64_t)q.gcs * q.hstride * q.hstride;
     const int32_t last = p.level_off[L - 1];
     const uint32_t ls = q.vslot[last];
