@@ -42,13 +42,15 @@ def test_replicated_panel_fixture(tmp_path):
     assert s1 == s4
 
 
-def test_checkpoint_chooser_contract(dp_emu4):
-    """choose_checkpoints (dp_prep.cpp) through the emulator's traceback: strictly descending levels from the sink to level 0
-    is what the device traceback relies on; here the end-to-end effect — a graph with a wide bubble longer than the search
-    window still traces to the oracle's edge lists."""
+def test_checkpoint_chooser_contract(dp_emu4, dp_emu):
+    """choose_checkpoints (dp_prep.cpp) through the task-stream emulator's checkpointed traceback (tests/emu/dp_emu.cpp runs the
+    same anc / hop / seg scheme serially) and the level-program emulator: a long graph with recombination blocks still traces
+    to the oracle's edge lists."""
     import oracle
     from dipgenie_b200 import synth
     g = synth.lane_panel_graph(77, n_lanes=6, n_blocks=40, rec_per_block=2, p_colour=0.2, n_colours=64)
+    o3 = dp_emu.dp_diploid(g, 3)
     o = dp_emu4.dp_diploid(g, 3)
     ref = oracle.dp_diploid(g.level_off, g.adj_off, g.adj_dst, g.adj_w, g.col_off, g.col_val, g.colour_is_hom, 3)
-    assert o["value"] == ref["value"] and np.array_equal(o["p1_edges"], ref["p1_edges"]) and np.array_equal(o["p2_edges"], ref["p2_edges"])
+    for x in (o, o3):
+        assert x["value"] == ref["value"] and np.array_equal(x["p1_edges"], ref["p1_edges"]) and np.array_equal(x["p2_edges"], ref["p2_edges"])
