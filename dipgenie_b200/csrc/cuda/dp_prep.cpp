@@ -48,52 +48,62 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
     std::atomic<int> bad(0);      // 1 adj_off, 2 edge span, 3 colour id
 
     // ---- in-edge CSR (gather form of approximator.cpp:640-649) ----
-    // the in-edges of level l+1 come from level l only: counting and filling are level-parallel
-    p.in_off.assign((size_t)V + 1, 0);
+    // The in-edges of level l+1 are the out-edges of level l and nothing else, so the CSR of level l+1 starts at
+    // adj_off[level_off[l]] and every level is counted, prefixed and filled on its own — one pass over a level's edges to count,
+    // one (cache-hot) to scatter, no global prefix sum.  Sources are visited in ascending position: the lists come out in the
+    // tie-break order (smaller i first).
     const int64_t E = g.adj_off[V];
-    uint64_t cell_updates = 0;
-#pragma omp parallel for schedule(static) num_threads(NT) reduction(+ : cell_updates)
-    for (int l = 0; l < L; ++l) {
-        const int32_t lo = p.level_off[l], hi = p.level_off[l + 1];
-        const int32_t nlo = (l + 1 < L) ? p.level_off[l + 1] : V, nhi = (l + 1 < L) ? p.level_off[l + 2] : V;
-        uint64_t El = 0;
-        for (int32_t u = lo; u < hi; ++u) {
-            if (g.adj_off[u + 1] < g.adj_off[u]) { bad = 1; break; }
-            El += (uint64_t)(g.adj_off[u + 1] - g.adj_off[u]);
-            for (int64_t e = g.adj_off[u]; e < g.adj_off[u + 1]; ++e) {
-                const int32_t v = g.adj_dst[e];
-                if (v < nlo || v >= nhi) { bad = 2; break; }
-                if (g.adj_w[e] > 1) { bad = 4; break; }            // weights are 0 / 1 (ExpandedGraph: lane edge / recombination edge)
-                ++p.in_off[(size_t)v + 1];
-            }
-        }
-        if (l + 1 < L) cell_updates += (uint64_t)(g.R + 1) * El * El;
-    }
-    if (bad == 1) { p.error = "adj_off not monotone"; return false; }
-    if (bad == 2) { p.error = "edge does not span exactly one level"; return false; }
-    if (bad == 4) { p.error = "edge weight above 1"; return false; }
-    p.cell_updates = cell_updates;
-    for (int32_t v = 0; v < V; ++v) {
-        p.max_indeg = std::max(p.max_indeg, p.in_off[(size_t)v + 1]);
-        p.in_off[(size_t)v + 1] += p.in_off[v];
-    }
+    p.in_off.assign((size_t)V + 1, 0);
     p.n_in = E;
     p.in_edge.assign((size_t)E, 0);
     p.in_dst.assign((size_t)E, 0);
+    uint64_t cell_updates = 0;
+    int32_t max_indeg = 0;
+    for (int32_t u = 0; u < V && !bad; ++u) if (g.adj_off[u + 1] < g.adj_off[u]) bad = 1;
+    if (bad == 1) { p.error = "adj_off not monotone"; return false; }
+    if (E > 0x7FFFFFFF) { p.error = "more than 2^31 edges"; return false; }
+#pragma omp parallel num_threads(NT) reduction(+ : cell_updates) reduction(max : max_indeg)
     {
-        std::vector<int32_t> fill(p.in_off.begin(), p.in_off.end() - 1);
-#pragma omp parallel for schedule(static) num_threads(NT)
-        for (int l = 0; l < L - 1; ++l) {
-            const int32_t lo = p.level_off[l], hi = p.level_off[l + 1];
-            for (int32_t u = lo; u < hi; ++u)
+        std::vector<int32_t> cur;
+#pragma omp for schedule(static)
+        for (int l = 0; l < L; ++l) {
+            const int32_t lo = p.level_off[l], mid = p.level_off[l + 1];
+            const int64_t e0 = g.adj_off[lo], e1 = g.adj_off[mid];
+            if (l + 1 == L) { if (e1 != e0) bad = 2; continue; }          // (an edge out of the last level spans no level)
+            const int32_t hi = p.level_off[l + 2], k2 = hi - mid;
+            cur.assign((size_t)k2 + 1, 0);
+            bool ok = true;
+            for (int64_t e = e0; e < e1; ++e) {
+                const int32_t v = g.adj_dst[e];
+                if (v < mid || v >= hi) { bad = 2; ok = false; break; }
+                if (g.adj_w[e] > 1) { bad = 4; ok = false; break; }        // weights are 0 / 1 (ExpandedGraph: lane edge / recombination edge)
+                ++cur[(size_t)(v - mid) + 1];
+            }
+            if (!ok) continue;
+            int32_t run = (int32_t)e0;
+            for (int32_t j = 0; j < k2; ++j) {
+                const int32_t c = cur[(size_t)j + 1];
+                max_indeg = std::max(max_indeg, c);
+                p.in_off[(size_t)mid + j] = run;
+                cur[(size_t)j] = run;                 // cursor of destination j
+                run += c;
+            }
+            for (int32_t u = lo; u < mid; ++u)
                 for (int64_t e = g.adj_off[u]; e < g.adj_off[u + 1]; ++e) {
-                    const int32_t v = g.adj_dst[e];
-                    const size_t slot = (size_t)fill[v]++;
+                    const int32_t j = g.adj_dst[e] - mid;
+                    const size_t slot = (size_t)cur[(size_t)j]++;
                     p.in_edge[slot] = (uint32_t)(u - lo) | ((uint32_t)g.adj_w[e] << IN_W_SHIFT);
-                    p.in_dst[slot] = (uint16_t)(v - hi);
+                    p.in_dst[slot] = (uint16_t)j;
                 }
+            const uint64_t El = (uint64_t)(e1 - e0);
+            cell_updates += (uint64_t)(g.R + 1) * El * El;
         }
     }
+    p.in_off[(size_t)V] = (int32_t)E;
+    if (bad == 2) { p.error = "edge does not span exactly one level"; return false; }
+    if (bad == 4) { p.error = "edge weight above 1"; return false; }
+    p.cell_updates = cell_updates;
+    p.max_indeg = max_indeg;
 
     // Parallel edges u -> v of DIFFERENT weight: their candidates reach one destination cell from two layers of the same
     // source pair; on a tie the reference keeps whichever its racing relax loop (approximator.cpp:627-701, `omp for
