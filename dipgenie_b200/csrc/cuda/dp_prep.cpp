@@ -59,6 +59,7 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
     p.in_dst.assign((size_t)E, 0);
     uint64_t cell_updates = 0;
     int32_t max_indeg = 0;
+    std::atomic<int> mixed(0);
     for (int32_t u = 0; u < V && !bad; ++u) if (g.adj_off[u + 1] < g.adj_off[u]) bad = 1;
     if (bad == 1) { p.error = "adj_off not monotone"; return false; }
     if (E > 0x7FFFFFFF) { p.error = "more than 2^31 edges"; return false; }
@@ -92,7 +93,10 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
                 for (int64_t e = g.adj_off[u]; e < g.adj_off[u + 1]; ++e) {
                     const int32_t j = g.adj_dst[e] - mid;
                     const size_t slot = (size_t)cur[(size_t)j]++;
-                    p.in_edge[slot] = (uint32_t)(u - lo) | ((uint32_t)g.adj_w[e] << IN_W_SHIFT);
+                    const uint32_t x = (uint32_t)(u - lo) | ((uint32_t)g.adj_w[e] << IN_W_SHIFT);
+                    // parallel edges u -> v sit next to each other in v's list (sources ascend): differing weights are refused below
+                    if (slot > (size_t)p.in_off[(size_t)mid + j] && ((p.in_edge[slot - 1] ^ x) & IN_POS_MASK) == 0 && p.in_edge[slot - 1] != x) mixed = 1;
+                    p.in_edge[slot] = x;
                     p.in_dst[slot] = (uint16_t)j;
                 }
             const uint64_t El = (uint64_t)(e1 - e0);
@@ -109,15 +113,8 @@ bool build_dip_plan(const DipGraphView& g, DipPlan& p) {
     // source pair; on a tie the reference keeps whichever its racing relax loop (approximator.cpp:627-701, `omp for
     // collapse(3) schedule(guided)`) writes first — the result depends on thread timing, there is nothing to be
     // bit-exact with.  (The reference's own front end never builds such edges; same-weight duplicates are fine: identical
-    // candidates.)  In-edges are grouped by destination in ascending source position, so such a pair is adjacent.
-    {
-        std::atomic<int> mixed(0);
-#pragma omp parallel for schedule(static) num_threads(NT)
-        for (int32_t v = 0; v < V; ++v)
-            for (int32_t e = p.in_off[v] + 1; e < p.in_off[(size_t)v + 1]; ++e)
-                if ((p.in_edge[e] & IN_POS_MASK) == (p.in_edge[(size_t)e - 1] & IN_POS_MASK) && p.in_edge[e] != p.in_edge[(size_t)e - 1]) mixed = 1;
-        if (mixed) { p.error = "parallel edges of differing weight between one vertex pair (the reference's tie-break is thread-order dependent for them)"; return false; }
-    }
+    // candidates.)  Found while the lists were filled.
+    if (mixed) { p.error = "parallel edges of differing weight between one vertex pair (the reference's tie-break is thread-order dependent for them)"; return false; }
 
     // ---- per-transition colour masks (approximator.cpp:431-453 + :269-311 as popcounts) ----
     // pass 1: size of the local colour universe of every transition; prefix; pass 2: fill
