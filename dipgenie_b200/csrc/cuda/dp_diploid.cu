@@ -1930,8 +1930,9 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
                 i = next++;
             }
 #if defined(_OPENMP)
-            // the cores are shared by the planners still at work: the last wave (fewer samples than workers) gets more each
-            omp_set_num_threads(std::max(1, hw / std::max(1, std::min(W, (int)n - i))));
+            // (a fixed share: handing the idle cores of the last wave to its planners oversubscribes while the wave before
+            // still runs — OpenMP's waiting threads spin — and cost 90 ms per 22-sample call)
+            omp_set_num_threads(std::max(1, hw / W));
 #endif
             const dg_dip_input_t& x = in[i];
             // the plan is written straight into page-locked memory: about 60 bytes per vertex on the pangenome
