@@ -1198,7 +1198,13 @@ struct dg_dip {
     DevBuf<uint32_t> v4_vinfo, v4_mpre, v4_n1, v4_np, v4_m, v4_z, v4_dm, v4_tflags;
     DevBuf<int64_t> v4_mpre_off;
     DevBuf<Fill4Args> v4_tables;                 // the builder's view of the device tables (also read by the checksum variant)
+    // batch path: dg_dip_create's device half returns without waiting for the uploads; the plan's page-locked arrays are
+    // handed back once `ev_up` (recorded behind the last copy and the program builder) has completed
+    bool async_create = false, release_pending = false;
+    cudaEvent_t ev_up = nullptr;
     ~dg_dip() {
+        if ((release_pending || async_create) && stream) cudaStreamSynchronize(stream);      // (copies out of the plan's arrays may still be in flight)
+        if (ev_up) cudaEventDestroy(ev_up);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         if (ipc_opened)
             for (int a = 0; a < 4; ++a)
@@ -1385,6 +1391,18 @@ static int dip_create_impl(dg_ctx* ctx, const DipGraphView& g, dg_dip** out, cud
     return DG_OK;
 }
 
+// Hands the plan's big host arrays (and their page-locked block) back: only once the copies out of them have completed.
+static void dip4_release_host(dg_dip* d) {
+    DipPlan& p = d->plan;
+    p.in_edge.clear(); p.in_edge.shrink_to_fit();
+    p.in_dst.clear(); p.in_dst.shrink_to_fit();
+    p.masks.clear(); p.masks.shrink_to_fit();
+    p.in_off.clear(); p.in_off.shrink_to_fit();
+    d->p4.release_arrays();
+    if (d->staging) d->staging->release();
+    d->release_pending = false;
+}
+
 // Device half of the level-program engine: the O(V) tables go up, the O(sum E^2) program is written by the device.
 static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     DG_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1475,20 +1493,22 @@ static int dip4_create_device(dg_ctx* ctx, dg_dip* d) {
     prog_fill_kernel<<<std::min(L - 1, ctx->sm_count * 16), FILL4_THREADS, 0, s>>>(fa);
     DG_CUDA(ctx, cudaGetLastError());
     DG_CUDA(ctx, cudaEventRecord(d->ev[1], s));
-    DG_CUDA(ctx, cudaStreamSynchronize(s));
-    DG_CUDA(ctx, cudaEventElapsedTime(&d->build_ms, d->ev[0], d->ev[1]));
+    if (d->async_create) {
+        DG_CUDA(ctx, cudaEventCreateWithFlags(&d->ev_up, cudaEventDisableTiming));
+        DG_CUDA(ctx, cudaEventRecord(d->ev_up, s));
+        d->release_pending = true;
+        d->build_ms = 0.f;               // (ev[0] / ev[1] are recorded again by the run that follows at once)
+    } else {
+        DG_CUDA(ctx, cudaStreamSynchronize(s));
+        DG_CUDA(ctx, cudaEventElapsedTime(&d->build_ms, d->ev[0], d->ev[1]));
+    }
     d->upload_ms = (float)(now_ms() - t_up0);
     d->device_bytes = d->level_off.bytes() + d->in_off.bytes() + d->in_edge.bytes() + d->lvlW.bytes() + d->masks.bytes() +
                       d->msrc_off.bytes() + d->mdst_off.bytes() + d->pred_off.bytes() + d->v4_dir.bytes() + d->v4_hdr.bytes() +
                       d->v4_prog_off.bytes() + d->v4_cls.bytes() + d->v4_vinfo.bytes() + d->v4_mpre.bytes() + d->v4_prog.bytes() +
                       d->v4_pred.bytes() + d->tile0.bytes() + d->v4_vup.bytes() + d->v4_gkey.bytes() + d->v4_vslot.bytes() + d->v4_dir_full.bytes() + d->level_sum.bytes() + d->level_live.bytes() +
                       d->anc.bytes() + d->seg_p1.bytes() + d->seg_p2.bytes();
-    p.in_edge.clear(); p.in_edge.shrink_to_fit();
-    p.in_dst.clear(); p.in_dst.shrink_to_fit();
-    p.masks.clear(); p.masks.shrink_to_fit();
-    p.in_off.clear(); p.in_off.shrink_to_fit();
-    q.release_arrays();
-    if (d->staging) d->staging->release();
+    if (!d->async_create) dip4_release_host(d);
     return DG_OK;
 }
 
@@ -1967,8 +1987,11 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
     std::vector<dg_dip*> slot((size_t)K, nullptr);
     std::vector<int32_t> owner((size_t)K, -1);
     int rc = DG_OK;
+    std::vector<dg_dip*> uploading;          // launched, copies out of the plan's page-locked block possibly still in flight
     auto collect = [&](int k) {
         if (!slot[(size_t)k]) return;
+        for (size_t x = 0; x < uploading.size(); ++x)
+            if (uploading[x] == slot[(size_t)k]) { uploading.erase(uploading.begin() + (long)x); break; }      // (its destructor waits and releases)
         dg_dip_output_t& o = out[owner[(size_t)k]];
         const int r = dg_dip_result(ctx, slot[(size_t)k], &o.sink_value, &o.sink_s_het, o.p1_edges, &o.n_p1, o.p2_edges, &o.n_p2);
         o.status = r;
@@ -2008,11 +2031,19 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
                 if (slot[(size_t)kk]) { collect(kk); dg_release_cached_memory(ctx); }
             }
         }
+        // (the level-program engine's device half does not wait for its copies here: 22 x 5 ms of waiting were a third of the
+        //  call; the page-locked plan block goes back to the pool when the copies are through)
+        for (size_t x = 0; x < uploading.size();) {
+            if (cudaEventQuery(uploading[x]->ev_up) == cudaSuccess) { dip4_release_host(uploading[x]); uploading.erase(uploading.begin() + (long)x); }
+            else ++x;
+        }
+        d->async_create = d->v4 && d->staging != nullptr;
         int r = dip_create_device(ctx, d.get());     // (uploads stay on this thread: a pageable H2D issued by a worker on a
                                                      //  busy slot stream blocks that worker until the slot's sweep ends)
         if (!r) r = dg_dip_run(ctx, d.get(), 0);
         if (timing) fprintf(stderr, "batch: sample %d launched at %.1f ms (alloc+upload %.1f ms)\n", (int)i, now_ms() - t_batch0, d->upload_ms);
         if (r) { out[i].status = r; if (!rc) rc = r; continue; }
+        if (d->release_pending) uploading.push_back(d.get());
         slot[(size_t)k] = d.release(); owner[(size_t)k] = i;
     }
     for (std::thread& t : pool) t.join();
