@@ -562,7 +562,8 @@ def main():
     # end-to-end through the host-buffer C-ABI batch call (planning, H2D, kernels, D2H inside the timed region)
     graphs = [samples[i % len(samples)] for i in range(max(1, args.batch))]
     e2e_t, single_t = [], []
-    for i in range(0 if args.skip_e2e else args.e2e_steps + 1):
+    E2E_WARMUP = 2      # untimed calls: the library pins its page-locked plan blocks and fills its device pool during the first ones
+    for i in range(0 if args.skip_e2e else args.e2e_steps + E2E_WARMUP):
         flush.fill_(1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -571,7 +572,7 @@ def main():
         t0 = time.perf_counter()
         o1 = ctx.dp_diploid(g, args.R)
         d1 = time.perf_counter() - t0
-        if i > 0:
+        if i >= E2E_WARMUP:
             e2e_t.append(dt)
             single_t.append(d1)
         assert res[0]["value"] == o1["value"]
