@@ -1926,9 +1926,10 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
     // uploads, launches and collects in sample order
     int hw = (int)std::max(1u, std::thread::hardware_concurrency());
     if (const char* e = getenv("DG_HOST_THREADS")) hw = std::max(1, atoi(e));   // this process's share of the host cores (one process per GPU)
-    int W = std::max(1, std::min({(int)n, 8, hw / 2}));          // two planner threads per worker (22 samples, 16 cores: 8 x 2 threads 349-366 ms
-                                                                 // per call; 16 x 1 thread 324 ms once 18 page-locked plan blocks are pinned, but
-                                                                 // 380-700 ms in the calls that still pin them: DG_PLAN_WORKERS=16 for long runs)
+    // Eight planners of two threads.  Measured on the GPU box (22 MHC_4 samples, 16 cores, ms per call): 8 x 2 threads 310 / 309 /
+    // 309; 11 x 1 thread 327 / 325 / 346 / 318 / 545; 16 x 1 thread 299 / 632 / 301 — more planners keep more page-locked plan
+    // blocks in flight, and a call that has to pin another one pays 0.1-0.3 s for it (DG_PLAN_WORKERS overrides).
+    int W = std::max(1, std::min({(int)n, 8, hw / 2}));
     if (const char* e = getenv("DG_PLAN_WORKERS")) W = std::max(1, std::min({atoi(e), (int)n, hw}));
     const int lookahead = W + 2;
     const bool pinned = !getenv("DG_NO_PINNED_PLAN");

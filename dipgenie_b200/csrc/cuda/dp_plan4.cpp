@@ -218,6 +218,8 @@ bool plan4_build(const DipPlan& p, const DipGraphView& g, const Sweep4Shape& sha
     q.pred_elems = q.pred_off[L];
 
     // ---- directories ----
+    q.full.dir.reserve((size_t)L - 1);          // (no regrowth: the storage is a monotonic page-locked block)
+    q.timed.dir.reserve((size_t)L - 1);
     for (int l = 0; l + 1 < L; ++l) {
         ProgDir d;
         memset(&d, 0, sizeof d);
