@@ -497,7 +497,9 @@ def reference_arm(args):
             "impl": "reference", "metric": "dp_cell_updates_per_sec", "value": val, "unit": "cell-updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "bundled MHC_4 test panel (levelized graph fixture), synthetic only where named",
-            "config": {"workload": args.workload, "description": desc, "R": args.R, "ploidy": 2,
+            "config": {"workload": args.workload, "description": desc, "R": args.R, "ploidy": 2, "levels": int(g.n_levels),
+                       "vertices": int(g.level_off[-1]), "max_width": int(np.diff(g.level_off).max()),
+                       "cell_updates_per_sample": float(U) if not max_levels else None,
                        "reference_fn": "Approximator::diploid_dp_approximation_solver (src/approximator.cpp:362), unmodified objects, -G mode of oracle/ref_driver"},
             "cpu_baseline": {"value": val, "unit": "cell-updates/s", "cores": threads, "kind": "reference", "sample": sample,
                              "host_cpus": os.cpu_count(), "thread_probe": f"fastest of {{8,16,32,nproc}} on a {probe}-level sample"},
