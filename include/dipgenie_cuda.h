@@ -55,6 +55,11 @@ int dg_device_info(dg_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total
  *   sink_s_het   dp_entry::s_het of that cell
  *   p1_edges / p2_edges   weighted_p1_edges / weighted_p2_edges (:781-782) as (from,to) vertex-id pairs,
  *                oldest first; capacity 2*(R+2) int32 each; n_p1 / n_p2 = number of pairs
+ * Refused with DG_ERR_ARG, before anything is launched: null arrays, level 0 with more than one vertex, an empty
+ * level, offsets that are not monotone, an edge that does not go to the next level, a colour id outside
+ * [0, n_colours), an edge weight above 1, and parallel edges of differing weight between one vertex pair (the
+ * reference resolves their ties by the timing of its racing relax loop, :627-701 — there is no result to be exact
+ * with; edges of equal weight may repeat).
  */
 int dg_dp_diploid(dg_ctx* ctx, int32_t n_levels, const int32_t* level_off,
                   const int64_t* adj_off, const int32_t* adj_dst, const uint8_t* adj_w,
@@ -117,7 +122,8 @@ void dg_dip_destroy(dg_ctx* ctx, dg_dip* d);
  * spread over the GPU: sample i runs as its own persistent sweep of `ctas_per_sample` CTAs (0 = 4) on its own
  * stream, up to `max_concurrent` samples resident together (0 = min(SM count / ctas_per_sample, 32)), while
  * host threads plan the next samples.  No data-path exchange between samples.  Results are identical to n calls of
- * dg_dp_diploid.  out[i].status = DG_OK or that sample's error code; returns the first error, if any. */
+ * dg_dp_diploid.  A sample whose level programs and predecessor codes do not fit the free HBM (wide panels need
+ * gigabytes) waits for earlier samples to finish instead of failing its allocation.  out[i].status = DG_OK or that sample's error code; returns the first error, if any. */
 #define DG_BATCH_MAX_EDGES 64        /* capacity of the edge lists below: needs R + 2 <= 64 */
 typedef struct {
     int32_t n_levels; const int32_t* level_off;
