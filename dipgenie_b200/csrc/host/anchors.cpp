@@ -2,6 +2,7 @@
 // of Solver::compute_and_classify_anchors (reference src/solver.cpp:560-887).
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 #include <map>
 #include <string>
 
@@ -36,25 +37,44 @@ void build_anchors(const Panel& p, const SketchResult& s, float threshold, int t
     a.vtx_off.assign(1, 0);
     a.anchors_per_walk.assign(H, 0);
     std::vector<std::vector<int64_t>> kept(H);     // per walk: hit indices of the current id, in the reference's order
+    // The reference groups the occurrences of an id in a std::map keyed by the TEXT "v1_v2_..._" of their vertex lists (:596-611):
+    // groups come out in the lexicographic order of those strings, occurrences inside a group in insertion order (walk, then
+    // position).  The same order without building a string or a map node per occurrence: a stable sort of the occurrences by
+    // a comparator that is the string comparison — the first differing vertex decides, by its decimal digits followed by
+    // '_' (which sorts above every digit), and a list that is a prefix of the other comes first.
+    auto token_less = [](int32_t x, int32_t y) {          // "x_" < "y_" as strings, x != y
+        char a[16], b[16];
+        const int la = snprintf(a, sizeof a, "%d_", x), lb = snprintf(b, sizeof b, "%d_", y);
+        const int c = memcmp(a, b, (size_t)std::min(la, lb));
+        return c != 0 ? c < 0 : la < lb;
+    };
+    auto key_cmp = [&](int64_t A, int64_t B) {            // <0, 0, >0
+        const uint64_t a0 = s.hit_vtx_off[A], a1 = s.hit_vtx_off[A + 1], b0 = s.hit_vtx_off[B], b1 = s.hit_vtx_off[B + 1];
+        const uint64_t n = std::min(a1 - a0, b1 - b0);
+        for (uint64_t t = 0; t < n; ++t) {
+            const int32_t x = s.hit_vtx[a0 + t], y = s.hit_vtx[b0 + t];
+            if (x != y) return token_less(x, y) ? -1 : 1;
+        }
+        return (a1 - a0) < (b1 - b0) ? -1 : ((a1 - a0) > (b1 - b0) ? 1 : 0);
+    };
+    std::vector<int64_t> occ;                              // occurrences of the current id, grouped
     for (int64_t id = 0; id < S; ++id) {
-        // occurrences grouped by the textual key "v1_v2_..._" in std::map (string) order, then insertion order
-        std::map<std::string, std::vector<int64_t>> by_key;
+        occ.clear();
         for (int h = 0; h < H; ++h) {
             if (p.paths[h].empty()) continue;
-            for (int64_t b = bucket_off[(size_t)id * H + h]; b < bucket_off[(size_t)id * H + h + 1]; ++b) {
-                const int64_t x = bucket[(size_t)b];
-                std::string key;
-                for (uint64_t t = s.hit_vtx_off[x]; t < s.hit_vtx_off[x + 1]; ++t) { key += std::to_string(s.hit_vtx[t]); key += '_'; }
-                by_key[key].push_back(x);
-            }
+            for (int64_t b = bucket_off[(size_t)id * H + h]; b < bucket_off[(size_t)id * H + h + 1]; ++b) occ.push_back(bucket[(size_t)b]);
         }
+        if (occ.size() > 1) std::stable_sort(occ.begin(), occ.end(), [&](int64_t A, int64_t B) { return key_cmp(A, B) < 0; });
         bool all_haps = false;
-        for (const auto& kv : by_key)
-            if ((float)kv.second.size() >= threshold * (float)(uint32_t)H) { all_haps = true; break; }   // int >= float*uint (:618)
+        for (size_t g0 = 0; g0 < occ.size() && !all_haps;) {
+            size_t g1 = g0 + 1;
+            while (g1 < occ.size() && key_cmp(occ[g0], occ[g1]) == 0) ++g1;
+            if ((float)(g1 - g0) >= threshold * (float)(uint32_t)H) all_haps = true;      // int >= float*uint (:618)
+            g0 = g1;
+        }
         for (int h = 0; h < H; ++h) kept[h].clear();
         if (!all_haps)
-            for (const auto& kv : by_key)
-                for (int64_t x : kv.second) kept[hit_walk[x]].push_back(x);
+            for (int64_t x : occ) kept[hit_walk[x]].push_back(x);
         for (int h = 0; h < H; ++h) {
             auto& v = kept[h];
             // (first vertex, last vertex), empties last (:643-661); equal keys on one walk are identical lists

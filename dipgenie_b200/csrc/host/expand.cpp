@@ -39,10 +39,9 @@ bool kahn_reorder(ExpGraph& g, int sink, std::string& err) {
     for (size_t i = 0; i < n; ++i) { nc[i] = std::move(g.color[order[i]]); no[i] = std::move(g.original_vertex[order[i]]); nh[i] = g.haplotype[order[i]]; }
     g.color.swap(nc); g.original_vertex.swap(no); g.haplotype.swap(nh);
     std::vector<std::vector<std::pair<int32_t, int32_t>>> na(n);
-    for (size_t u = 0; u < n; ++u) {
-        auto& dst = na[new_idx[u]];
-        dst.reserve(g.adj[u].size());
-        for (auto& e : g.adj[u]) dst.emplace_back(new_idx[e.first], e.second);
+    for (size_t u = 0; u < n; ++u) {              // the lists move, their targets are renamed in place
+        for (auto& e : g.adj[u]) e.first = new_idx[e.first];
+        na[new_idx[u]] = std::move(g.adj[u]);
     }
     g.adj.swap(na);
     return true;
@@ -217,7 +216,15 @@ bool levelize(ExpGraph& g, std::string& err) {
     // 4) dummy vertices so that every edge spans exactly one level (:319-352)
     std::vector<std::vector<std::pair<int32_t, int32_t>>> nadj(n0);
     std::vector<int32_t> nlvl(lvl.begin(), lvl.end());
+    {
+        size_t n_dummy = 0;                         // (known up front: no regrowth of the per-vertex tables)
+        for (int u = 0; u < n0; ++u)
+            for (auto& e : g.adj[u]) { const int gap = lvl[e.first] - lvl[u] - 1; if (gap > 0) n_dummy += (size_t)gap; }
+        nadj.reserve((size_t)n0 + n_dummy); nlvl.reserve((size_t)n0 + n_dummy);
+        g.color.reserve((size_t)n0 + n_dummy); g.original_vertex.reserve((size_t)n0 + n_dummy); g.haplotype.reserve((size_t)n0 + n_dummy);
+    }
     for (int u = 0; u < n0; ++u) {
+        nadj[u].reserve(g.adj[u].size());
         for (auto& e : g.adj[u]) {
             const int v = e.first, w = e.second;
             const int gap = nlvl[v] - nlvl[u] - 1;
@@ -239,11 +246,16 @@ bool levelize(ExpGraph& g, std::string& err) {
     g.adj.swap(nadj);
     // 5) order by (level, id) (:360-400)
     const int n1 = (int)g.adj.size();
-    std::vector<int> order(n1);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return nlvl[x] != nlvl[y] ? nlvl[x] < nlvl[y] : x < y; });
     int max_level = 0;
     for (int v = 0; v < n1; ++v) max_level = std::max(max_level, nlvl[v]);
+    std::vector<int> order(n1);                     // (level, id) ascending: a counting sort by level, ids stay in order
+    std::vector<int> lvl_start((size_t)max_level + 2, 0);
+    for (int v = 0; v < n1; ++v) ++lvl_start[(size_t)nlvl[v] + 1];
+    for (int l = 0; l <= max_level; ++l) lvl_start[(size_t)l + 1] += lvl_start[l];
+    {
+        std::vector<int> cursor(lvl_start.begin(), lvl_start.end() - 1);
+        for (int v = 0; v < n1; ++v) order[(size_t)cursor[nlvl[v]]++] = v;
+    }
     std::vector<int> new_id(n1);
     for (int i = 0; i < n1; ++i) new_id[order[i]] = i;
     std::vector<std::vector<int32_t>> nc(n1), no(n1);
@@ -255,14 +267,17 @@ bool levelize(ExpGraph& g, std::string& err) {
     g.color.swap(nc); g.original_vertex.swap(no); g.level.swap(nl); g.haplotype.swap(nh);
     std::vector<std::vector<std::pair<int32_t, int32_t>>> na(n1);
     for (int u = 0; u < n1; ++u) {
-        auto& dst = na[new_id[u]];
-        dst.reserve(g.adj[u].size());
-        for (auto& e : g.adj[u]) dst.emplace_back(new_id[e.first], e.second);
+        for (auto& e : g.adj[u]) e.first = new_id[e.first];
+        na[new_id[u]] = std::move(g.adj[u]);
     }
     g.adj.swap(na);
     // 7) per-level buckets (:402-407)
     g.vertices_in_level.assign(max_level + 1, {});
-    for (int u = 0; u < n1; ++u) g.vertices_in_level[g.level[u]].push_back(u);
+    for (int l = 0; l <= max_level; ++l) {          // vertex ids are (level, id)-ordered now: level l owns a contiguous range
+        auto& b = g.vertices_in_level[l];
+        b.resize((size_t)(lvl_start[(size_t)l + 1] - lvl_start[l]));
+        std::iota(b.begin(), b.end(), lvl_start[l]);
+    }
     return true;
 }
 

@@ -41,19 +41,35 @@ struct Prepared {
     double t0 = 0;
 };
 
+// DG_TIMING=1: host stage times on stderr (diagnostics).
+struct StageClock {
+    const bool on = getenv("DG_TIMING") != nullptr;
+    double last = now_s();
+    void tick(const char* what) {
+        if (!on) return;
+        const double t = now_s();
+        fprintf(stderr, "[T::host] %-28s %8.1f ms\n", what, (t - last) * 1e3);
+        last = t;
+    }
+};
+
 static int prepare(const Options& o, const Backend& be, Prepared& P, std::mutex* gpu, std::string& err) {
     const double t0 = now_s();
+    StageClock clk;
     P.o = o; P.t0 = t0;
     RunSummary& sum = P.sum;
     sum = RunSummary();
     GfaGraph gfa;
     if (!read_gfa_file(o.gfa, gfa, err)) return 1;
+    clk.tick("read_gfa_file");
     Panel& panel = P.panel;
     if (!build_panel(gfa, panel, err)) return 1;
+    clk.tick("build_panel");
     const int H = (int)panel.paths.size();
     if (o.verbose) fprintf(stderr, "[M::%s::%.3f] loaded the graph: %d segments, %d walks\n", __func__, now_s() - t0, panel.n_vtx, H);
     std::vector<std::string> reads;
     if (!read_sequences(o.reads, reads, err)) return 1;
+    clk.tick("read_sequences");
 
     // ---- device stage 1: read sketch -> spectrum + multiplicities (solver.cpp:526-558, :711-732) ----
     SketchResult sk;
@@ -72,6 +88,7 @@ static int prepare(const Options& o, const Backend& be, Prepared& P, std::mutex*
         sk.spectrum.assign(sp.p, sp.p + ns);
         sk.read_count.assign(rc.p, rc.p + ns);
     }
+    clk.tick("stage: sketch_reads");
     sum.spectrum = (int64_t)sk.spectrum.size();
     if (o.verbose) fprintf(stderr, "[M::%s::%.3f] Count_Sp_R : %lld\n", __func__, now_s() - t0, (long long)sum.spectrum);
 
@@ -103,9 +120,11 @@ static int prepare(const Options& o, const Backend& be, Prepared& P, std::mutex*
                 fprintf(stderr, "Haplotype: %s Number of Minimizers: %llu\n", panel.walk_names[h].c_str(), (unsigned long long)sk.n_minimizers[h]);
     }
 
+    clk.tick("stage: index_walks");
     // ---- host: filter, occurrence order, hom/het classifier (solver.cpp:590-887) ----
     Anchors anchors;
     build_anchors(panel, sk, o.threshold, o.threads, anchors);
+    clk.tick("build_anchors (+ fit)");
     sum.n_hom = anchors.n_hom; sum.n_het = anchors.n_het;
     if (o.verbose) {
         for (int h = 0; h < H; ++h)
@@ -116,6 +135,7 @@ static int prepare(const Options& o, const Backend& be, Prepared& P, std::mutex*
     // ---- host: haplotype-expanded graph in Kahn order (approximator.cpp:1014-1256) ----
     Expanded& ex = P.ex;
     if (!expand_graph(panel, anchors, ex, err)) return 1;
+    clk.tick("expand_graph");
     auto flatten = [](const ExpGraph& g, std::vector<int64_t>& adj_off, std::vector<int32_t>& adj_dst, std::vector<uint8_t>& adj_w,
                       std::vector<int64_t>& col_off, std::vector<int32_t>& col_val) {
         const size_t n = g.adj.size();
@@ -135,7 +155,9 @@ static int prepare(const Options& o, const Backend& be, Prepared& P, std::mutex*
         P.level_off.assign((size_t)L + 1, 0);
         for (int l = 0; l < L; ++l) P.level_off[(size_t)l + 1] = P.level_off[l] + (int32_t)ex.g.vertices_in_level[l].size();
     }
+    clk.tick("levelize");
     flatten(ex.g, P.adj_off, P.adj_dst, P.adj_w, P.col_off, P.col_val);
+    clk.tick("flatten");
     return 0;
 }
 

@@ -23,7 +23,7 @@ int dgo_dp_diploid(int32_t, const int32_t*, const int64_t*, const int32_t*, cons
 
 int main(int argc, char** argv) {
     dgh::Options o;
-    o.verbose = false;
+    o.verbose = getenv("HOST_CHECK_VERBOSE") != nullptr;      // the stage timeline on stderr (diagnostics)
     for (int i = 1; i + 1 < argc; i += 2) {
         const char f = argv[i][1];
         const char* v = argv[i + 1];

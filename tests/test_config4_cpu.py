@@ -54,3 +54,32 @@ def test_checkpoint_chooser_contract(dp_emu4, dp_emu):
     ref = oracle.dp_diploid(g.level_off, g.adj_off, g.adj_dst, g.adj_w, g.col_off, g.col_val, g.colour_is_hom, 3)
     for x in (o, o3):
         assert x["value"] == ref["value"] and np.array_equal(x["p1_edges"], ref["p1_edges"]) and np.array_equal(x["p2_edges"], ref["p2_edges"])
+
+
+def test_front_end_builds_the_reference_dp_input_on_a_90_walk_panel(tmp_path):
+    """The host glue (GFA reader, panel columns, anchor filter and order, classifier fit, expansion, Kahn order, levelization)
+    with the oracle standing in for the device stages, on the config-4 panel at 1/16 of the backbone: the DP input it dumps
+    (DG_DUMP_DIPIN) is array-for-array the one the unmodified reference built for the same files (digest recorded from
+    oracle/_ref/ref_driver's dump)."""
+    import subprocess
+    import make_config4
+    from dipgenie_b200 import _build, dgd
+    import oracle
+    oracle.build(); _build.build_host()
+    exe = os.path.join(ROOT, "tests", "host", "host_check")
+    if not os.path.exists(exe):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-o", exe, os.path.join(ROOT, "tests", "host", "host_check.cpp"),
+                               "-L" + _build.PKG, "-ldipgenie_host", "-L" + os.path.join(ROOT, "oracle"), "-loracle",
+                               "-Wl,-rpath," + _build.PKG, "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-lz", "-lm"])
+    e = json.load(open(os.path.join(GOLD, "e2e_expected.json")))["c4_h90_s16_p2_R18"]
+    gfa, fa = make_config4.make(str(tmp_path), scale=0.0625)
+    dump = str(tmp_path / "dipin.dgd")
+    env = dict(os.environ, DG_DUMP_DIPIN=dump, DG_DUMP_ONLY="1")
+    p = subprocess.run([exe, "-g", gfa, "-r", fa, "-o", str(tmp_path / "o.fa"), "-t", "8", "-p", "2", "-R", "18"], capture_output=True, text=True, env=env, timeout=900)
+    assert p.returncode == 0, p.stderr[-2000:]
+    a = dgd.load(dump)
+    h = hashlib.sha256()
+    for name, dt in (("level_off", np.int64), ("adj_off", np.int64), ("adj_dst", np.int32), ("adj_w", np.uint8), ("col_off", np.int64),
+                     ("col_val", np.int32), ("colour_is_hom", np.uint8)):
+        h.update(np.ascontiguousarray(np.asarray(a[name]).astype(dt)).tobytes())
+    assert h.hexdigest() == e["dipin_sha256"]
