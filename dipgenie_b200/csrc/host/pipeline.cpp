@@ -202,6 +202,7 @@ static int solve_haploid(Prepared& P, const Backend& be, std::string& err) {
 int run_pipeline(const Options& o, const Backend& be, RunSummary& sum, std::string& err) {
     Prepared P;
     if (int rc = prepare(o, be, P, nullptr, err)) return rc;
+    StageClock clk;
     int rc = 0;
     if (o.ploidy == 1) {
         rc = solve_haploid(P, be, err);
@@ -223,7 +224,9 @@ int run_pipeline(const Options& o, const Backend& be, RunSummary& sum, std::stri
                                     P.adj_w.data(), P.col_off.data(), P.col_val.data(), P.ex.color_homo_bv.data(),
                                     (int32_t)P.ex.color_homo_bv.size(), o.R, &value, &s_het, e1.data(), &n1, e2.data(), &n2);
         if (e) { err = std::string("dg_dp_diploid: ") + (be.last_error ? be.last_error(be.ctx) : "failed"); return 1; }
+        clk.tick("stage: dp_diploid");
         rc = finish_diploid(P, value, e1.data(), n1, e2.data(), n2, err);
+        clk.tick("stitch + FASTA");
     }
     sum = P.sum;
     if (!rc && o.verbose) fprintf(stderr, "[M::%s] Real time: %.3f sec\n", __func__, now_s() - P.t0);
