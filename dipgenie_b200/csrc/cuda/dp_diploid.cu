@@ -1929,7 +1929,10 @@ int dg_dp_diploid_batch(dg_ctx* ctx, int32_t n, const dg_dip_input_t* in, dg_dip
     // Eight planners of two threads.  Measured on the GPU box (22 MHC_4 samples, 16 cores, ms per call): 8 x 2 threads 310 / 309 /
     // 309; 11 x 1 thread 327 / 325 / 346 / 318 / 545; 16 x 1 thread 299 / 632 / 301 — more planners keep more page-locked plan
     // blocks in flight, and a call that has to pin another one pays 0.1-0.3 s for it (DG_PLAN_WORKERS overrides).
-    int W = std::max(1, std::min({(int)n, 8, hw / 2}));
+    // With fewer cores than that (several ranks sharing a host: DG_HOST_THREADS) the cores go to planners first, threads
+    // second: the planner's OpenMP regions scale poorly (MHC_4: 1 / 2 / 4 threads 70 / 118 / 62 ms here, 2 / 16 threads 40 / 42 ms
+    // on the GPU box), sample-parallelism does.
+    int W = std::max(1, std::min({(int)n, 8, hw}));
     if (const char* e = getenv("DG_PLAN_WORKERS")) W = std::max(1, std::min({atoi(e), (int)n, hw}));
     const int lookahead = W + 2;
     const bool pinned = !getenv("DG_NO_PINNED_PLAN");
